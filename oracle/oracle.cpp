@@ -1,0 +1,1878 @@
+// oracle.cpp -- CPU ORACLE for the variant-lookup hot path of proycon/analiticcl (v0.4.9).
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  This file is a plain C++ restatement of the REFERENCE'S
+// algorithm (BFS deletion enumeration + full `sortedindex[charcount]` scan with big-integer
+// modulo, full-matrix true Damerau-Levenshtein, f64 scoring and ranking).  It is used by
+//   * tests/            as the parity checker for the CUDA path,
+//   * __graft_entry__.smoke()  as the checker of the smoke run,
+//   * bench.py          as the timed CPU baseline ("port") and the `--impl reference` arm.
+// Nothing under analiticcl_b200/ links, imports or executes it.  The Rust reference cannot be
+// compiled in this environment (no cargo/rustc), so this restatement is pinned against the
+// reference's own known-answer tests and documentation goldens (tests/test_oracle_golden.py).
+//
+// Each function cites the reference file:line it restates (paths relative to the reference
+// repository root).  Written from the behaviour of that code, not copied from it.
+//
+// Build: see oracle/Makefile (g++ -O3 -march=native -fopenmp -shared -fPIC).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "unicode_tables.h"
+
+namespace orc {
+
+// ------------------------------------------------------------------------------------------
+// Arbitrary-(bounded-)precision unsigned integer.  Stands in for ibig::UBig (Cargo.toml:24,
+// src/types.rs:33).  Exact integer arithmetic, so any correct implementation is equivalent.
+// 32-bit limbs, little endian, normalised (no leading zero limbs; zero has n == 0).
+// ------------------------------------------------------------------------------------------
+static const int BIG_LIMBS = 48;  // 1536 bits: > 150 symbols at the largest prime (997)
+
+struct Big {
+  uint32_t n;
+  uint32_t d[BIG_LIMBS];
+  Big() : n(0) {}
+  explicit Big(uint64_t v) : n(0) {
+    while (v) {
+      d[n++] = (uint32_t)v;
+      v >>= 32;
+    }
+  }
+  bool is_zero() const { return n == 0; }
+  bool is_one() const { return n == 1 && d[0] == 1; }
+  bool operator==(const Big& o) const { return n == o.n && memcmp(d, o.d, n * 4) == 0; }
+  bool operator!=(const Big& o) const { return !(*this == o); }
+  int cmp(const Big& o) const {
+    if (n != o.n) return n < o.n ? -1 : 1;
+    for (int i = (int)n - 1; i >= 0; --i)
+      if (d[i] != o.d[i]) return d[i] < o.d[i] ? -1 : 1;
+    return 0;
+  }
+  bool operator<(const Big& o) const { return cmp(o) < 0; }
+  bool operator>(const Big& o) const { return cmp(o) > 0; }
+
+  // this * m (m < 2^32).  Aborts on capacity overflow: the oracle must never be silently wrong.
+  Big mul_small(uint32_t m) const {
+    Big r;
+    uint64_t carry = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      uint64_t t = (uint64_t)d[i] * m + carry;
+      r.d[i] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    r.n = n;
+    if (carry) {
+      if (r.n >= BIG_LIMBS) {
+        fprintf(stderr, "oracle: Big overflow\n");
+        abort();
+      }
+      r.d[r.n++] = (uint32_t)carry;
+    }
+    return r;
+  }
+  // General product (schoolbook).
+  Big mul(const Big& o) const {
+    Big r;
+    if (is_zero() || o.is_zero()) return r;
+    if (n + o.n > (uint32_t)BIG_LIMBS) {
+      fprintf(stderr, "oracle: Big overflow\n");
+      abort();
+    }
+    uint32_t len = n + o.n;
+    for (uint32_t i = 0; i < len; ++i) r.d[i] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      uint64_t carry = 0;
+      for (uint32_t j = 0; j < o.n; ++j) {
+        uint64_t t = (uint64_t)d[i] * o.d[j] + r.d[i + j] + carry;
+        r.d[i + j] = (uint32_t)t;
+        carry = t >> 32;
+      }
+      r.d[i + o.n] = (uint32_t)carry;
+    }
+    r.n = len;
+    while (r.n && r.d[r.n - 1] == 0) --r.n;
+    return r;
+  }
+  // quotient and remainder by a small divisor
+  Big divmod_small(uint32_t m, uint32_t* rem) const {
+    Big q;
+    uint64_t r = 0;
+    for (int i = (int)n - 1; i >= 0; --i) {
+      uint64_t cur = (r << 32) | d[i];
+      q.d[i] = (uint32_t)(cur / m);
+      r = cur % m;
+    }
+    q.n = n;
+    while (q.n && q.d[q.n - 1] == 0) --q.n;
+    *rem = (uint32_t)r;
+    return q;
+  }
+  // Full division (Knuth algorithm D): *this = q * v + r.  v must be non-zero.
+  void divmod(const Big& v, Big* q, Big* r) const {
+    if (cmp(v) < 0) {
+      if (q) *q = Big();
+      if (r) *r = *this;
+      return;
+    }
+    if (v.n == 1) {
+      uint32_t rem;
+      Big qq = divmod_small(v.d[0], &rem);
+      if (q) *q = qq;
+      if (r) *r = Big((uint64_t)rem);
+      return;
+    }
+    const uint32_t nn = v.n, m = n - v.n;
+    int s = __builtin_clz(v.d[nn - 1]);
+    uint32_t vn[BIG_LIMBS], un[BIG_LIMBS + 1];
+    for (uint32_t i = nn - 1; i > 0; --i)
+      vn[i] = s ? ((v.d[i] << s) | (v.d[i - 1] >> (32 - s))) : v.d[i];
+    vn[0] = v.d[0] << s;
+    un[n] = s ? (d[n - 1] >> (32 - s)) : 0;
+    for (uint32_t i = n - 1; i > 0; --i) un[i] = s ? ((d[i] << s) | (d[i - 1] >> (32 - s))) : d[i];
+    un[0] = d[0] << s;
+    Big qq;
+    qq.n = m + 1;
+    for (int j = (int)m; j >= 0; --j) {
+      uint64_t num = ((uint64_t)un[j + nn] << 32) | un[j + nn - 1];
+      uint64_t qhat = num / vn[nn - 1];
+      uint64_t rhat = num % vn[nn - 1];
+      while (qhat >= (1ULL << 32) || qhat * vn[nn - 2] > ((rhat << 32) | un[j + nn - 2])) {
+        --qhat;
+        rhat += vn[nn - 1];
+        if (rhat >= (1ULL << 32)) break;
+      }
+      int64_t borrow = 0;
+      uint64_t carry = 0;
+      for (uint32_t i = 0; i < nn; ++i) {
+        uint64_t p = qhat * vn[i] + carry;
+        carry = p >> 32;
+        int64_t t = (int64_t)un[i + j] - borrow - (int64_t)(p & 0xFFFFFFFFULL);
+        un[i + j] = (uint32_t)t;
+        borrow = (t < 0) ? 1 : 0;
+      }
+      int64_t t = (int64_t)un[j + nn] - borrow - (int64_t)carry;
+      un[j + nn] = (uint32_t)t;
+      qq.d[j] = (uint32_t)qhat;
+      if (t < 0) {
+        --qq.d[j];
+        uint64_t c = 0;
+        for (uint32_t i = 0; i < nn; ++i) {
+          uint64_t tt = (uint64_t)un[i + j] + vn[i] + c;
+          un[i + j] = (uint32_t)tt;
+          c = tt >> 32;
+        }
+        un[j + nn] += (uint32_t)c;
+      }
+    }
+    while (qq.n && qq.d[qq.n - 1] == 0) --qq.n;
+    if (q) *q = qq;
+    if (r) {
+      Big rr;
+      rr.n = nn;
+      for (uint32_t i = 0; i < nn; ++i)
+        rr.d[i] = s ? ((un[i] >> s) | ((uint64_t)un[i + 1] << (32 - s))) : un[i];
+      while (rr.n && rr.d[rr.n - 1] == 0) --rr.n;
+      *r = rr;
+    }
+  }
+  bool divisible_by(const Big& v) const {
+    Big r;
+    divmod(v, nullptr, &r);
+    return r.is_zero();
+  }
+  std::string to_decimal() const {
+    if (is_zero()) return "0";
+    Big t = *this;
+    std::string out;
+    while (!t.is_zero()) {
+      uint32_t rem;
+      t = t.divmod_small(1000000000u, &rem);
+      char buf[16];
+      if (t.is_zero())
+        snprintf(buf, sizeof buf, "%u", rem);
+      else
+        snprintf(buf, sizeof buf, "%09u", rem);
+      out = std::string(buf) + out;
+    }
+    return out;
+  }
+  unsigned bits() const { return n ? 32 * (n - 1) + (32 - __builtin_clz(d[n - 1])) : 0; }
+};
+
+struct BigHash {
+  size_t operator()(const Big& b) const {
+    uint64_t h = 1469598103934665603ULL;
+    for (uint32_t i = 0; i < b.n; ++i) {
+      h ^= b.d[i];
+      h *= 1099511628211ULL;
+    }
+    return (size_t)h;
+  }
+};
+
+// src/types.rs:20-30
+static const uint32_t PRIMES[168] = {
+    2,   3,   5,   7,   11,  13,  17,  19,  23,  29,  31,  37,  41,  43,  47,  53,  59,  61,  67,
+    71,  73,  79,  83,  89,  97,  101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163,
+    167, 173, 179, 181, 191, 193, 197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269,
+    271, 277, 281, 283, 293, 307, 311, 313, 317, 331, 337, 347, 349, 353, 359, 367, 373, 379, 383,
+    389, 397, 401, 409, 419, 421, 431, 433, 439, 443, 449, 457, 461, 463, 467, 479, 487, 491, 499,
+    503, 509, 521, 523, 541, 547, 557, 563, 569, 571, 577, 587, 593, 599, 601, 607, 613, 617, 619,
+    631, 641, 643, 647, 653, 659, 661, 673, 677, 683, 691, 701, 709, 719, 727, 733, 739, 743, 751,
+    757, 761, 769, 773, 787, 797, 809, 811, 821, 823, 827, 829, 839, 853, 857, 859, 863, 877, 881,
+    883, 887, 907, 911, 919, 929, 937, 941, 947, 953, 967, 971, 977, 983, 991, 997};
+
+typedef std::vector<std::vector<std::string>> Alphabet;  // src/types.rs:37
+typedef std::vector<uint8_t> NormString;                  // src/types.rs:17
+
+// ---- AnaValue operations: src/anahash.rs:139-171, 250-260 -------------------------------
+static Big ana_character(unsigned seqnr) {
+  if (seqnr >= 168) {
+    fprintf(stderr, "oracle: prime index out of range\n");
+    abort();
+  }
+  return Big((uint64_t)PRIMES[seqnr]);
+}
+static Big ana_insert(const Big& self, const Big& value) {  // :146 (0 -> value)
+  if (self.is_zero()) return value;
+  return self.mul(value);
+}
+static bool ana_contains(const Big& self, const Big& value) {  // :165
+  if (value > self) return false;
+  return self.divisible_by(value);
+}
+static bool ana_delete(const Big& self, const Big& value, Big* out) {  // :156
+  if (!ana_contains(self, value)) return false;
+  self.divmod(value, out, nullptr);
+  return true;
+}
+static bool ana_is_empty(const Big& v) { return v.is_one() || v.is_zero(); }  // :258
+
+// UTF-8 helpers -------------------------------------------------------------------------------
+static inline unsigned utf8_len(unsigned char c) {
+  if (c < 0x80) return 1;
+  if ((c >> 5) == 6) return 2;
+  if ((c >> 4) == 14) return 3;
+  if ((c >> 3) == 30) return 4;
+  return 1;
+}
+static inline uint32_t utf8_decode(const char* s, size_t avail, unsigned* len) {
+  unsigned char c = (unsigned char)s[0];
+  unsigned l = utf8_len(c);
+  if (l > avail) l = (unsigned)avail;
+  *len = l;
+  if (l == 1) return c;
+  uint32_t cp = c & (0xFF >> (l + 1));
+  for (unsigned i = 1; i < l; ++i) cp = (cp << 6) | ((unsigned char)s[i] & 0x3F);
+  return cp;
+}
+static size_t utf8_count(const std::string& s) {
+  size_t n = 0;
+  for (size_t i = 0; i < s.size(); i += utf8_len((unsigned char)s[i])) ++n;
+  return n;
+}
+
+// ---- src/anahash.rs:16-80 : greedy alphabet matching ----------------------------------------
+// Walks the characters of `text`; at each character tries every alphabet line in file order and
+// every member of that line in order; the first member equal to the bytes at this position wins
+// and consumes as many characters as the member has.  `on_symbol(seqnr, matched)` is called per
+// emitted symbol.
+template <class F>
+static void alphabet_scan(const std::string& text, const Alphabet& alphabet, F on_symbol) {
+  size_t skip = 0;
+  for (size_t bytepos = 0; bytepos < text.size(); bytepos += utf8_len((unsigned char)text[bytepos])) {
+    if (skip > 0) {
+      --skip;
+      continue;
+    }
+    bool matched = false;
+    for (size_t seqnr = 0; seqnr < alphabet.size() && !matched; ++seqnr) {
+      for (const std::string& element : alphabet[seqnr]) {
+        size_t bytelen = element.size();
+        if (bytepos + bytelen <= text.size() && memcmp(text.data() + bytepos, element.data(), bytelen) == 0) {
+          on_symbol((unsigned)seqnr, true);
+          matched = true;
+          skip = utf8_count(element) - 1;
+          break;
+        }
+      }
+    }
+    if (!matched) on_symbol(0, false);
+  }
+}
+
+static Big anahash(const std::string& text, const Alphabet& alphabet) {  // :16-47
+  Big hash((uint64_t)1);                                                // AnaValue::empty()
+  alphabet_scan(text, alphabet, [&](unsigned seqnr, bool matched) {
+    // unknown symbols use prime index alphabet.len()            (:42)
+    unsigned idx = matched ? seqnr : (unsigned)alphabet.size();
+    hash = ana_insert(hash, ana_character(idx & 0xFF));
+  });
+  return hash;
+}
+
+static NormString normalize_to_alphabet(const std::string& text, const Alphabet& alphabet) {  // :50-80
+  NormString result;
+  alphabet_scan(text, alphabet, [&](unsigned seqnr, bool matched) {
+    // unknown symbols are encoded as alphabet.len() + 1          (:76)
+    result.push_back(matched ? (uint8_t)seqnr : (uint8_t)(alphabet.size() + 1));
+  });
+  return result;
+}
+
+// ---- src/iterators.rs:21-70 : single deletions, descending alphabet index -------------------
+struct DeletionResult {
+  Big value;
+  uint8_t charindex;
+};
+static std::vector<DeletionResult> deletion_children(const Big& value, unsigned alphabet_size) {
+  std::vector<DeletionResult> out;
+  if (value.is_one()) return out;
+  for (unsigned iteration = 0; iteration < alphabet_size; ++iteration) {
+    unsigned charindex = alphabet_size - iteration - 1;
+    Big r;
+    if (ana_delete(value, ana_character(charindex), &r)) out.push_back({r, (uint8_t)charindex});
+  }
+  return out;
+}
+
+// ---- src/iterators.rs:95-236 : RecurseDeletionIterator ---------------------------------------
+struct IterParams {
+  bool singlebeam = false;
+  unsigned mindepth = 1;
+  int maxdepth = -1;  // -1 = None
+  bool breadthfirst = false;
+  bool unique = false;
+  bool empty_leaves = true;
+};
+struct IterItem {
+  DeletionResult node;
+  unsigned depth;
+};
+static std::vector<IterItem> recurse_deletions(const Big& start, unsigned alphabet_size, const IterParams& p) {
+  std::vector<IterItem> yielded;
+  std::deque<IterItem> queue;
+  std::unordered_set<Big, BigHash> visited;
+  queue.push_back({{start, 0}, 0});
+  while (!queue.empty()) {
+    if (p.breadthfirst) {
+      IterItem cur = queue.front();
+      queue.pop_front();
+      if (p.unique && visited.count(cur.node.value)) continue;
+      if (p.maxdepth < 0 || (int)cur.depth < p.maxdepth) {
+        for (auto& child : deletion_children(cur.node.value, alphabet_size)) {
+          if (p.unique && visited.count(child.value)) continue;
+          queue.push_back({child, cur.depth + 1});
+        }
+      }
+      if (cur.depth < p.mindepth || (!p.empty_leaves && ana_is_empty(cur.node.value))) continue;
+      if (p.unique) visited.insert(cur.node.value);
+      yielded.push_back(cur);
+    } else {
+      IterItem cur = queue.back();
+      queue.pop_back();
+      if (p.maxdepth < 0 || (int)cur.depth < p.maxdepth) {
+        if (p.unique && visited.count(cur.node.value)) continue;
+        auto children = deletion_children(cur.node.value, alphabet_size);
+        if (p.singlebeam) {
+          if (!children.empty()) queue.push_back({children[0], cur.depth + 1});
+        } else {
+          for (auto it = children.rbegin(); it != children.rend(); ++it) {
+            if (p.unique && visited.count(it->value)) continue;
+            queue.push_back({*it, cur.depth + 1});
+          }
+        }
+      }
+      if (cur.depth < p.mindepth || (!p.empty_leaves && ana_is_empty(cur.node.value))) continue;
+      if (p.unique) visited.insert(cur.node.value);
+      yielded.push_back(cur);
+    }
+  }
+  return yielded;
+}
+
+// src/anahash.rs:126-137 : (max class index, character count) via the single-beam walk
+static void alphabet_upper_bound(const Big& v, unsigned alphabet_size, unsigned* maxidx, unsigned* count) {
+  IterParams p;
+  p.singlebeam = true;
+  *maxidx = 0;
+  *count = 0;
+  for (auto& it : recurse_deletions(v, alphabet_size, p)) {
+    ++*count;
+    if (it.node.charindex > *maxidx) *maxidx = it.node.charindex;
+  }
+}
+
+// ---- src/distance.rs:101-179 : true Damerau-Levenshtein, full matrix --------------------------
+static int damerau_levenshtein(const uint8_t* s, size_t len_s, const uint8_t* t, size_t len_t, unsigned max_distance,
+                               uint64_t* cells) {
+  if (len_s == 0) return len_t > max_distance ? -1 : (int)len_t;
+  if (len_s > len_t && len_s - len_t > max_distance) return -1;
+  if (len_t == 0) return len_s > max_distance ? -1 : (int)len_s;
+  if (len_t > len_s && len_t - len_s > max_distance) return -1;
+  if (cells) *cells += (uint64_t)len_s * len_t;
+  const size_t ub = len_s + len_t;
+  const size_t W = len_t + 2;
+  std::vector<size_t> mat((len_s + 2) * W, 0);
+  mat[0] = ub;
+  for (size_t i = 0; i <= len_s; ++i) {
+    mat[(i + 1) * W + 0] = ub;
+    mat[(i + 1) * W + 1] = i;
+  }
+  for (size_t j = 0; j <= len_t; ++j) {
+    mat[0 * W + j + 1] = ub;
+    mat[1 * W + j + 1] = j;
+  }
+  size_t char_map[256];
+  bool char_seen[256];
+  memset(char_seen, 0, sizeof char_seen);
+  for (size_t i = 1; i <= len_s; ++i) {
+    size_t db = 0;
+    uint8_t s_char = s[i - 1];
+    for (size_t j = 1; j <= len_t; ++j) {
+      uint8_t t_char = t[j - 1];
+      size_t last = char_seen[t_char] ? char_map[t_char] : 0;
+      size_t cost = (s_char == t_char) ? 0 : 1;
+      size_t a = mat[(i + 1) * W + j] + 1;
+      size_t b = mat[i * W + j + 1] + 1;
+      size_t c = mat[i * W + j] + cost;
+      size_t d = mat[last * W + db] + (i - last - 1) + 1 + (j - db - 1);
+      mat[(i + 1) * W + j + 1] = std::min(std::min(std::min(a, b), c), d);
+      if (cost == 0) db = j;
+    }
+    char_seen[s_char] = true;
+    char_map[s_char] = (uint8_t)i;  // stored `as u8` (:170); wraps beyond 255 symbols
+  }
+  size_t result = mat[(len_s + 1) * W + len_t + 1];
+  if (result > max_distance) return -1;
+  return (int)(uint8_t)result;
+}
+
+// src/distance.rs:181-205
+static unsigned longest_common_substring_length(const uint8_t* s1, size_t n1, const uint8_t* s2, size_t n2) {
+  unsigned lcs = 0;
+  for (size_t i = 0; i < n1; ++i)
+    for (size_t j = 0; j < n2; ++j)
+      if (s1[i] == s2[j]) {
+        unsigned tmp = 1;
+        size_t ti = i + 1, tj = j + 1;
+        while (ti < n1 && tj < n2 && s1[ti] == s2[tj]) {
+          ++tmp;
+          ++ti;
+          ++tj;
+        }
+        if (tmp > lcs) lcs = tmp;
+      }
+  return lcs;
+}
+// src/distance.rs:208-218
+static unsigned common_prefix_length(const uint8_t* s1, size_t n1, const uint8_t* s2, size_t n2) {
+  unsigned p = 0;
+  for (size_t i = 0; i < std::min(n1, n2); ++i) {
+    if (s1[i] == s2[i])
+      ++p;
+    else
+      break;
+  }
+  return p;
+}
+// src/distance.rs:221-231
+static unsigned common_suffix_length(const uint8_t* s1, size_t n1, const uint8_t* s2, size_t n2) {
+  unsigned p = 0;
+  for (size_t i = 0; i < std::min(n1, n2); ++i) {
+    if (s1[n1 - i - 1] == s2[n2 - i - 1])
+      ++p;
+    else
+      break;
+  }
+  return p;
+}
+
+// ---- shortest edit script: sesdiff 0.3.1 -> dissimilar (NOT vendored in the reference) -------
+// Restated from the published diff-match-patch algorithm that `dissimilar` ports (Myers bisect,
+// semantic clean-up, lossless semantic shift, overlap extraction, merge).  Parity with the real
+// crate is pinned only by tests/main.rs:914-1020 ("confusable parity unpinned").
+enum DiffOp { DEL = -1, EQ = 0, INS = 1 };
+typedef std::vector<uint32_t> U32S;
+struct Diff {
+  DiffOp op;
+  U32S text;
+};
+typedef std::vector<Diff> Diffs;
+
+static U32S to_u32(const std::string& s) {
+  U32S out;
+  for (size_t i = 0; i < s.size();) {
+    unsigned l;
+    out.push_back(utf8_decode(s.data() + i, s.size() - i, &l));
+    i += l;
+  }
+  return out;
+}
+static std::string from_u32(const U32S& v) {
+  std::string out;
+  for (uint32_t cp : v) {
+    if (cp < 0x80)
+      out.push_back((char)cp);
+    else if (cp < 0x800) {
+      out.push_back((char)(0xC0 | (cp >> 6)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    } else if (cp < 0x10000) {
+      out.push_back((char)(0xE0 | (cp >> 12)));
+      out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    } else {
+      out.push_back((char)(0xF0 | (cp >> 18)));
+      out.push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+      out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    }
+  }
+  return out;
+}
+static U32S sub(const U32S& v, size_t a, size_t b) { return U32S(v.begin() + a, v.begin() + b); }
+static size_t common_prefix(const U32S& a, const U32S& b) {
+  size_t n = std::min(a.size(), b.size()), i = 0;
+  while (i < n && a[i] == b[i]) ++i;
+  return i;
+}
+static size_t common_suffix(const U32S& a, const U32S& b) {
+  size_t n = std::min(a.size(), b.size()), i = 0;
+  while (i < n && a[a.size() - 1 - i] == b[b.size() - 1 - i]) ++i;
+  return i;
+}
+static long find_sub(const U32S& hay, const U32S& needle) {
+  if (needle.empty()) return 0;
+  if (needle.size() > hay.size()) return -1;
+  for (size_t i = 0; i + needle.size() <= hay.size(); ++i)
+    if (std::equal(needle.begin(), needle.end(), hay.begin() + i)) return (long)i;
+  return -1;
+}
+static size_t common_overlap(const U32S& a_in, const U32S& b_in) {
+  U32S a = a_in, b = b_in;
+  if (a.empty() || b.empty()) return 0;
+  if (a.size() > b.size())
+    a = sub(a, a.size() - b.size(), a.size());
+  else if (a.size() < b.size())
+    b = sub(b, 0, a.size());
+  size_t text_length = std::min(a.size(), b.size());
+  if (a == b) return text_length;
+  size_t best = 0, length = 1;
+  for (;;) {
+    U32S pattern = sub(a, text_length - length, text_length);
+    long found = find_sub(b, pattern);
+    if (found < 0) return best;
+    length += (size_t)found;
+    if (found == 0 || sub(a, text_length - length, text_length) == sub(b, 0, length)) {
+      best = length;
+      ++length;
+    }
+    if (length > text_length) return best;
+  }
+}
+
+static void diff_cleanup_merge(Diffs& diffs);
+static Diffs diff_main(const U32S& t1, const U32S& t2);
+
+static Diffs diff_bisect(const U32S& text1, const U32S& text2) {
+  const long n1 = (long)text1.size(), n2 = (long)text2.size();
+  const long max_d = (n1 + n2 + 1) / 2;
+  const long v_offset = max_d, v_length = 2 * max_d;
+  std::vector<long> v1(v_length, -1), v2(v_length, -1);
+  v1[v_offset + 1] = 0;
+  v2[v_offset + 1] = 0;
+  const long delta = n1 - n2;
+  const bool front = (delta % 2 != 0);
+  long k1start = 0, k1end = 0, k2start = 0, k2end = 0;
+  for (long d = 0; d < max_d; ++d) {
+    for (long k1 = -d + k1start; k1 <= d - k1end; k1 += 2) {
+      long k1_offset = v_offset + k1, x1;
+      if (k1 == -d || (k1 != d && v1[k1_offset - 1] < v1[k1_offset + 1]))
+        x1 = v1[k1_offset + 1];
+      else
+        x1 = v1[k1_offset - 1] + 1;
+      long y1 = x1 - k1;
+      while (x1 < n1 && y1 < n2 && text1[x1] == text2[y1]) {
+        ++x1;
+        ++y1;
+      }
+      v1[k1_offset] = x1;
+      if (x1 > n1)
+        k1end += 2;
+      else if (y1 > n2)
+        k1start += 2;
+      else if (front) {
+        long k2_offset = v_offset + delta - k1;
+        if (k2_offset >= 0 && k2_offset < v_length && v2[k2_offset] != -1) {
+          long x2 = n1 - v2[k2_offset];
+          if (x1 >= x2) {
+            Diffs a = diff_main(sub(text1, 0, x1), sub(text2, 0, y1));
+            Diffs b = diff_main(sub(text1, x1, n1), sub(text2, y1, n2));
+            a.insert(a.end(), b.begin(), b.end());
+            return a;
+          }
+        }
+      }
+    }
+    for (long k2 = -d + k2start; k2 <= d - k2end; k2 += 2) {
+      long k2_offset = v_offset + k2, x2;
+      if (k2 == -d || (k2 != d && v2[k2_offset - 1] < v2[k2_offset + 1]))
+        x2 = v2[k2_offset + 1];
+      else
+        x2 = v2[k2_offset - 1] + 1;
+      long y2 = x2 - k2;
+      while (x2 < n1 && y2 < n2 && text1[n1 - x2 - 1] == text2[n2 - y2 - 1]) {
+        ++x2;
+        ++y2;
+      }
+      v2[k2_offset] = x2;
+      if (x2 > n1)
+        k2end += 2;
+      else if (y2 > n2)
+        k2start += 2;
+      else if (!front) {
+        long k1_offset = v_offset + delta - k2;
+        if (k1_offset >= 0 && k1_offset < v_length && v1[k1_offset] != -1) {
+          long x1 = v1[k1_offset];
+          long y1 = v_offset + x1 - k1_offset;
+          long x2m = n1 - x2;
+          if (x1 >= x2m) {
+            Diffs a = diff_main(sub(text1, 0, x1), sub(text2, 0, y1));
+            Diffs b = diff_main(sub(text1, x1, n1), sub(text2, y1, n2));
+            a.insert(a.end(), b.begin(), b.end());
+            return a;
+          }
+        }
+      }
+    }
+  }
+  return Diffs{{DEL, text1}, {INS, text2}};
+}
+
+static Diffs diff_compute(const U32S& text1, const U32S& text2) {
+  if (text1.empty() && text2.empty()) return {};
+  if (text1.empty()) return Diffs{{INS, text2}};
+  if (text2.empty()) return Diffs{{DEL, text1}};
+  if (text1.size() > text2.size()) {
+    long i = find_sub(text1, text2);
+    if (i >= 0)
+      return Diffs{{DEL, sub(text1, 0, i)}, {EQ, text2}, {DEL, sub(text1, i + text2.size(), text1.size())}};
+  } else {
+    long i = find_sub(text2, text1);
+    if (i >= 0)
+      return Diffs{{INS, sub(text2, 0, i)}, {EQ, text1}, {INS, sub(text2, i + text1.size(), text2.size())}};
+  }
+  if (text1.size() == 1 || text2.size() == 1) return Diffs{{DEL, text1}, {INS, text2}};
+  return diff_bisect(text1, text2);
+}
+
+static Diffs diff_main(const U32S& t1, const U32S& t2) {
+  size_t cp = common_prefix(t1, t2);
+  U32S a = sub(t1, cp, t1.size()), b = sub(t2, cp, t2.size());
+  size_t cs = common_suffix(a, b);
+  U32S am = sub(a, 0, a.size() - cs), bm = sub(b, 0, b.size() - cs);
+  Diffs diffs = diff_compute(am, bm);
+  if (cp > 0) diffs.insert(diffs.begin(), Diff{EQ, sub(t1, 0, cp)});
+  if (cs > 0) diffs.push_back(Diff{EQ, sub(a, a.size() - cs, a.size())});
+  diff_cleanup_merge(diffs);
+  return diffs;
+}
+
+static void diff_cleanup_merge(Diffs& diffs) {
+  for (;;) {
+    diffs.push_back(Diff{EQ, {}});
+    size_t pointer = 0, count_delete = 0, count_insert = 0;
+    U32S text_delete, text_insert;
+    while (pointer < diffs.size()) {
+      switch (diffs[pointer].op) {
+        case INS:
+          ++count_insert;
+          text_insert.insert(text_insert.end(), diffs[pointer].text.begin(), diffs[pointer].text.end());
+          ++pointer;
+          break;
+        case DEL:
+          ++count_delete;
+          text_delete.insert(text_delete.end(), diffs[pointer].text.begin(), diffs[pointer].text.end());
+          ++pointer;
+          break;
+        case EQ:
+          if (count_delete + count_insert > 1) {
+            if (count_delete != 0 && count_insert != 0) {
+              size_t cl = common_prefix(text_insert, text_delete);
+              if (cl != 0) {
+                size_t before = pointer - count_delete - count_insert;
+                if (before > 0 && diffs[before - 1].op == EQ) {
+                  U32S& t = diffs[before - 1].text;
+                  t.insert(t.end(), text_insert.begin(), text_insert.begin() + cl);
+                } else {
+                  diffs.insert(diffs.begin(), Diff{EQ, sub(text_insert, 0, cl)});
+                  ++pointer;
+                }
+                text_insert = sub(text_insert, cl, text_insert.size());
+                text_delete = sub(text_delete, cl, text_delete.size());
+              }
+              cl = common_suffix(text_insert, text_delete);
+              if (cl != 0) {
+                U32S tail = sub(text_insert, text_insert.size() - cl, text_insert.size());
+                tail.insert(tail.end(), diffs[pointer].text.begin(), diffs[pointer].text.end());
+                diffs[pointer].text = tail;
+                text_insert = sub(text_insert, 0, text_insert.size() - cl);
+                text_delete = sub(text_delete, 0, text_delete.size() - cl);
+              }
+            }
+            pointer -= count_delete + count_insert;
+            diffs.erase(diffs.begin() + pointer, diffs.begin() + pointer + count_delete + count_insert);
+            if (!text_delete.empty()) {
+              diffs.insert(diffs.begin() + pointer, Diff{DEL, text_delete});
+              ++pointer;
+            }
+            if (!text_insert.empty()) {
+              diffs.insert(diffs.begin() + pointer, Diff{INS, text_insert});
+              ++pointer;
+            }
+            ++pointer;
+          } else if (pointer != 0 && diffs[pointer - 1].op == EQ) {
+            U32S& t = diffs[pointer - 1].text;
+            t.insert(t.end(), diffs[pointer].text.begin(), diffs[pointer].text.end());
+            diffs.erase(diffs.begin() + pointer);
+          } else {
+            ++pointer;
+          }
+          count_insert = count_delete = 0;
+          text_delete.clear();
+          text_insert.clear();
+          break;
+      }
+    }
+    if (diffs.back().text.empty()) diffs.pop_back();
+    bool changes = false;
+    pointer = 1;
+    while (pointer + 1 < diffs.size()) {
+      if (diffs[pointer - 1].op == EQ && diffs[pointer + 1].op == EQ) {
+        U32S& cur = diffs[pointer].text;
+        const U32S& prev = diffs[pointer - 1].text;
+        const U32S& next = diffs[pointer + 1].text;
+        if (cur.size() >= prev.size() && std::equal(prev.begin(), prev.end(), cur.end() - prev.size())) {
+          U32S nt = prev;
+          nt.insert(nt.end(), cur.begin(), cur.end() - prev.size());
+          U32S nn = prev;
+          nn.insert(nn.end(), next.begin(), next.end());
+          diffs[pointer].text = nt;
+          diffs[pointer + 1].text = nn;
+          diffs.erase(diffs.begin() + pointer - 1);
+          changes = true;
+        } else if (cur.size() >= next.size() && std::equal(next.begin(), next.end(), cur.begin())) {
+          diffs[pointer - 1].text.insert(diffs[pointer - 1].text.end(), next.begin(), next.end());
+          U32S nt = sub(cur, next.size(), cur.size());
+          nt.insert(nt.end(), next.begin(), next.end());
+          diffs[pointer].text = nt;
+          diffs.erase(diffs.begin() + pointer + 1);
+          changes = true;
+        }
+      }
+      ++pointer;
+    }
+    if (!changes) break;
+  }
+}
+
+static bool is_alnum_cp(uint32_t c) {
+  return orc_unicode::is_alphabetic(c) || (c >= '0' && c <= '9');
+}
+static bool is_space_cp(uint32_t c) {
+  return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+         c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+static int semantic_score(const U32S& one, const U32S& two) {
+  if (one.empty() || two.empty()) return 6;
+  uint32_t c1 = one.back(), c2 = two.front();
+  bool na1 = !is_alnum_cp(c1), na2 = !is_alnum_cp(c2);
+  bool ws1 = na1 && is_space_cp(c1), ws2 = na2 && is_space_cp(c2);
+  bool lb1 = ws1 && (c1 == '\r' || c1 == '\n'), lb2 = ws2 && (c2 == '\r' || c2 == '\n');
+  auto ends_blank = [](const U32S& s) {
+    size_t n = s.size();
+    if (n >= 2 && s[n - 1] == '\n' && s[n - 2] == '\n') return true;
+    if (n >= 3 && s[n - 1] == '\n' && s[n - 2] == '\r' && s[n - 3] == '\n') return true;
+    return false;
+  };
+  auto starts_blank = [](const U32S& s) {
+    size_t n = s.size();
+    if (n >= 2 && s[0] == '\n' && s[1] == '\n') return true;
+    if (n >= 3 && s[0] == '\n' && s[1] == '\r' && s[2] == '\n') return true;
+    if (n >= 3 && s[0] == '\r' && s[1] == '\n' && s[2] == '\n') return true;
+    if (n >= 4 && s[0] == '\r' && s[1] == '\n' && s[2] == '\r' && s[3] == '\n') return true;
+    return false;
+  };
+  bool bl1 = lb1 && ends_blank(one), bl2 = lb2 && starts_blank(two);
+  if (bl1 || bl2) return 5;
+  if (lb1 || lb2) return 4;
+  if (na1 && !ws1 && ws2) return 3;
+  if (ws1 || ws2) return 2;
+  if (na1 || na2) return 1;
+  return 0;
+}
+
+static void diff_cleanup_semantic_lossless(Diffs& diffs) {
+  size_t pointer = 1;
+  while (pointer + 1 < diffs.size()) {
+    if (diffs[pointer - 1].op == EQ && diffs[pointer + 1].op == EQ) {
+      U32S equality1 = diffs[pointer - 1].text, edit = diffs[pointer].text, equality2 = diffs[pointer + 1].text;
+      size_t co = common_suffix(equality1, edit);
+      if (co) {
+        U32S cs = sub(edit, edit.size() - co, edit.size());
+        equality1 = sub(equality1, 0, equality1.size() - co);
+        U32S ne = cs;
+        ne.insert(ne.end(), edit.begin(), edit.end() - co);
+        edit = ne;
+        U32S n2 = cs;
+        n2.insert(n2.end(), equality2.begin(), equality2.end());
+        equality2 = n2;
+      }
+      U32S best1 = equality1, beste = edit, best2 = equality2;
+      int best_score = semantic_score(equality1, edit) + semantic_score(edit, equality2);
+      while (!edit.empty() && !equality2.empty() && edit[0] == equality2[0]) {
+        equality1.push_back(edit[0]);
+        edit.erase(edit.begin());
+        edit.push_back(equality2[0]);
+        equality2.erase(equality2.begin());
+        int score = semantic_score(equality1, edit) + semantic_score(edit, equality2);
+        if (score >= best_score) {
+          best_score = score;
+          best1 = equality1;
+          beste = edit;
+          best2 = equality2;
+        }
+      }
+      if (diffs[pointer - 1].text != best1) {
+        if (!best1.empty())
+          diffs[pointer - 1].text = best1;
+        else {
+          diffs.erase(diffs.begin() + pointer - 1);
+          --pointer;
+        }
+        diffs[pointer].text = beste;
+        if (!best2.empty())
+          diffs[pointer + 1].text = best2;
+        else {
+          diffs.erase(diffs.begin() + pointer + 1);
+          --pointer;
+        }
+      }
+    }
+    ++pointer;
+  }
+}
+
+static void diff_cleanup_semantic(Diffs& diffs) {
+  bool changes = false;
+  std::vector<size_t> equalities;
+  bool have_last = false;
+  U32S lastequality;
+  long pointer = 0;
+  size_t li1 = 0, ld1 = 0, li2 = 0, ld2 = 0;
+  while (pointer < (long)diffs.size()) {
+    if (diffs[pointer].op == EQ) {
+      equalities.push_back(pointer);
+      li1 = li2;
+      ld1 = ld2;
+      li2 = 0;
+      ld2 = 0;
+      lastequality = diffs[pointer].text;
+      have_last = true;
+    } else {
+      if (diffs[pointer].op == INS)
+        li2 += diffs[pointer].text.size();
+      else
+        ld2 += diffs[pointer].text.size();
+      if (have_last && lastequality.size() <= std::max(li1, ld1) && lastequality.size() <= std::max(li2, ld2)) {
+        size_t at = equalities.back();
+        diffs.insert(diffs.begin() + at, Diff{DEL, lastequality});
+        diffs[at + 1].op = INS;
+        equalities.pop_back();
+        if (!equalities.empty()) equalities.pop_back();
+        pointer = equalities.empty() ? -1 : (long)equalities.back();
+        li1 = ld1 = li2 = ld2 = 0;
+        have_last = false;
+        changes = true;
+      }
+    }
+    ++pointer;
+  }
+  if (changes) diff_cleanup_merge(diffs);
+  diff_cleanup_semantic_lossless(diffs);
+  // overlap extraction
+  pointer = 1;
+  while (pointer < (long)diffs.size()) {
+    if (diffs[pointer - 1].op == DEL && diffs[pointer].op == INS) {
+      U32S deletion = diffs[pointer - 1].text, insertion = diffs[pointer].text;
+      size_t ol1 = common_overlap(deletion, insertion), ol2 = common_overlap(insertion, deletion);
+      if (ol1 >= ol2) {
+        if (ol1 * 2 >= deletion.size() || ol1 * 2 >= insertion.size()) {
+          diffs.insert(diffs.begin() + pointer, Diff{EQ, sub(insertion, 0, ol1)});
+          diffs[pointer - 1].text = sub(deletion, 0, deletion.size() - ol1);
+          diffs[pointer + 1].text = sub(insertion, ol1, insertion.size());
+          ++pointer;
+        }
+      } else {
+        if (ol2 * 2 >= deletion.size() || ol2 * 2 >= insertion.size()) {
+          diffs.insert(diffs.begin() + pointer, Diff{EQ, sub(deletion, 0, ol2)});
+          diffs[pointer - 1].op = INS;
+          diffs[pointer - 1].text = sub(insertion, 0, insertion.size() - ol2);
+          diffs[pointer + 1].op = DEL;
+          diffs[pointer + 1].text = sub(deletion, ol2, deletion.size());
+          ++pointer;
+        }
+      }
+      ++pointer;
+    }
+    ++pointer;
+  }
+}
+
+// sesdiff::shortest_edit_script(src, dst, false, false, false)   (call site src/lib.rs:1736)
+struct EditInstr {
+  DiffOp op;
+  std::vector<std::string> options;  // one entry unless parsed from a pattern with `|`
+};
+static std::vector<EditInstr> shortest_edit_script(const std::string& src, const std::string& dst) {
+  Diffs d = diff_main(to_u32(src), to_u32(dst));
+  diff_cleanup_semantic(d);
+  diff_cleanup_merge(d);
+  std::vector<EditInstr> out;
+  for (auto& x : d)
+    if (!x.text.empty()) out.push_back({x.op, {from_u32(x.text)}});
+  return out;
+}
+
+// ---- src/confusables.rs:13-129 -----------------------------------------------------------------
+struct Confusable {
+  std::vector<EditInstr> script;
+  double weight;
+  bool strictbegin, strictend;
+};
+// Pattern syntax `=[..]`, `+[..]`, `-[..]`, options separated by `|` (sesdiff EditScript::from_str).
+static bool parse_editscript(const std::string& s, std::vector<EditInstr>* out) {
+  size_t i = 0;
+  while (i < s.size()) {
+    char c = s[i];
+    DiffOp op;
+    if (c == '=')
+      op = EQ;
+    else if (c == '+')
+      op = INS;
+    else if (c == '-')
+      op = DEL;
+    else
+      return false;
+    if (i + 1 >= s.size() || s[i + 1] != '[') return false;
+    size_t close = s.find(']', i + 2);
+    if (close == std::string::npos) return false;
+    std::string body = s.substr(i + 2, close - (i + 2));
+    EditInstr ins{op, {}};
+    size_t start = 0;
+    for (;;) {
+      size_t bar = body.find('|', start);
+      if (bar == std::string::npos) {
+        ins.options.push_back(body.substr(start));
+        break;
+      }
+      ins.options.push_back(body.substr(start, bar - start));
+      start = bar + 1;
+    }
+    out->push_back(ins);
+    i = close + 1;
+  }
+  return !out->empty();
+}
+static bool confusable_new(const std::string& editscript, double weight, Confusable* c) {
+  if (editscript.empty()) return false;
+  c->strictbegin = editscript[0] == '^';
+  c->strictend = editscript[editscript.size() - 1] == '$';
+  size_t a = c->strictbegin ? 1 : 0, b = editscript.size() - (c->strictend ? 1 : 0);
+  if (b < a) return false;
+  c->weight = weight;
+  c->script.clear();
+  return parse_editscript(editscript.substr(a, b - a), &c->script);
+}
+static bool ends_with(const std::string& s, const std::string& suf) {
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+static bool starts_with(const std::string& s, const std::string& pre) {
+  return s.size() >= pre.size() && s.compare(0, pre.size(), pre) == 0;
+}
+static bool confusable_found_in(const Confusable& c, const std::vector<EditInstr>& ref) {  // :47-128
+  const size_t l = c.script.size();
+  size_t matches = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    if (matches >= l) continue;
+    const EditInstr& ins = c.script[matches];
+    const std::string& sref = ref[i].options[0];
+    bool found = false;
+    if (ins.op == ref[i].op) {
+      for (const std::string& s : ins.options) {
+        bool ok;
+        if (ins.op == EQ) {
+          if (matches == 0 && matches == l - 1)
+            ok = (s == sref);
+          else if (matches == 0)
+            ok = ends_with(sref, s);
+          else if (matches == l - 1)
+            ok = starts_with(sref, s);
+          else
+            ok = (s == sref);
+        } else {
+          ok = ends_with(sref, s);
+        }
+        if (ok) {
+          found = true;
+          break;
+        }
+      }
+    }
+    if (!found) {
+      matches = 0;
+      if (c.strictbegin) return false;
+    } else {
+      ++matches;
+      if (matches == l) {
+        if (c.strictend) return i == ref.size() - 1;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// ---- model ------------------------------------------------------------------------------------
+enum { VT_NONE = 0, VT_INDEXED = 1, VT_LM = 2, VT_TRANSPARENT = 4 };  // src/vocab.rs:31-49
+enum { FH_SUM = 0, FH_MAX = 1, FH_MIN = 2, FH_REPLACE = 3 };          // src/vocab.rs:100-106
+
+struct VocabValue {  // src/vocab.rs:7-29 (variants: out of scope)
+  std::string text;
+  NormString norm;
+  uint32_t frequency;
+  uint8_t tokencount;
+  uint32_t lexindex;
+  uint8_t vocabtype;
+};
+struct IndexNode {  // src/index.rs:8-12
+  std::vector<uint64_t> instances;
+  uint16_t charcount;
+};
+struct Weights {  // src/types.rs:39-73
+  double ld, lcs, prefix, suffix, case_;
+};
+struct Threshold {  // src/types.rs:75-83 ; kind 0=Ratio 1=RatioWithLimit 2=Absolute
+  int32_t kind;
+  float ratio;
+  uint32_t value;
+};
+struct Params {  // the subset of src/types.rs:110-168 that the path reads
+  Threshold max_anagram_distance, max_edit_distance;
+  uint64_t max_matches;
+  double score_threshold, cutoff_threshold;
+  int32_t stop_at_exact_match;
+  float freq_weight;
+  int32_t max_ngram;
+  int32_t unicodeoffsets;
+};
+struct Result {  // src/types.rs:326-332 (via: out of scope, always none)
+  uint64_t vocab_id;
+  double dist_score, freq_score;
+};
+struct Stats {
+  uint64_t queries, modulo_tests, deletions, anagram_hits, dl_pairs, dl_cells, survivors;
+};
+
+struct Model {
+  Alphabet alphabet;
+  std::vector<VocabValue> decoder;
+  std::unordered_map<std::string, uint64_t> encoder;
+  std::unordered_map<Big, IndexNode, BigHash> index;
+  std::map<uint16_t, std::vector<Big>> sortedindex;
+  bool have_freq = false;
+  Weights weights;
+  std::vector<std::string> lexicons;
+  std::vector<Confusable> confusables;
+  bool confusables_before_pruning = false;
+
+  unsigned alphabet_size() const { return (unsigned)((alphabet.size() + 1) & 0xFF); }  // src/lib.rs:163
+
+  void init_vocab() {  // src/vocab.rs:150-181
+    const char* names[3] = {"<bos>", "<eos>", "<unk>"};
+    for (int i = 0; i < 3; ++i) {
+      decoder.push_back(VocabValue{names[i], {}, 0, 1, 0, VT_NONE});
+      encoder[names[i]] = i;
+    }
+  }
+
+  // src/lib.rs:369-407.  Fields split on TAB; `\s`,`\t`,`\n` escapes; fields trimmed, empty dropped.
+  void read_alphabet_text(const std::string& tsv) {
+    size_t pos = 0;
+    while (pos <= tsv.size()) {
+      size_t nl = tsv.find('\n', pos);
+      std::string line = tsv.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+      if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips \r\n
+      if (!line.empty()) {
+        std::vector<std::string> fields;
+        size_t fp = 0;
+        for (;;) {
+          size_t tab = line.find('\t', fp);
+          std::string x = line.substr(fp, tab == std::string::npos ? std::string::npos : tab - fp);
+          if (x == "\\s")
+            fields.push_back(" ");
+          else if (x == "\\t")
+            fields.push_back("\t");
+          else if (x == "\\n")
+            fields.push_back("\n");
+          else {
+            std::string t = trim(x);
+            if (!t.empty()) fields.push_back(t);
+          }
+          if (tab == std::string::npos) break;
+          fp = tab + 1;
+        }
+        alphabet.push_back(fields);
+      }
+      if (nl == std::string::npos) break;
+      pos = nl + 1;
+    }
+  }
+  static std::string trim(const std::string& s) {  // str::trim (Unicode White_Space)
+    U32S u = to_u32(s);
+    size_t a = 0, b = u.size();
+    while (a < b && is_space_cp(u[a])) ++a;
+    while (b > a && is_space_cp(u[b - 1])) --b;
+    return from_u32(sub(u, a, b));
+  }
+
+  // src/lib.rs:900-967
+  uint64_t add_to_vocabulary(const std::string& text, bool has_freq, uint32_t freq, int freq_handling, int vocab_type,
+                             int lex_index) {
+    uint32_t frequency = has_freq ? freq : 1;
+    auto it = encoder.find(text);
+    if (it != encoder.end()) {
+      VocabValue& item = decoder[it->second];
+      switch (freq_handling) {
+        case FH_SUM: item.frequency += frequency; break;
+        case FH_MAX: if (frequency > item.frequency) item.frequency = frequency; break;
+        case FH_MIN: if (frequency < item.frequency) item.frequency = frequency; break;
+        default: item.frequency = frequency; break;
+      }
+      if (it->second <= 2)
+        item.vocabtype = VT_LM;
+      else if ((item.vocabtype & VT_TRANSPARENT) && !(vocab_type & VT_TRANSPARENT))
+        item.vocabtype ^= VT_TRANSPARENT;
+      item.lexindex |= 1u << lex_index;
+      return it->second;
+    }
+    uint64_t id = decoder.size();
+    encoder[text] = id;
+    VocabValue v;
+    v.text = text;
+    v.norm = normalize_to_alphabet(text, alphabet);
+    v.frequency = frequency;
+    v.tokencount = (uint8_t)(std::count(text.begin(), text.end(), ' ') + 1);
+    v.lexindex = 1u << lex_index;
+    v.vocabtype = (uint8_t)vocab_type;
+    decoder.push_back(v);
+    return id;
+  }
+
+  // src/lib.rs:519-568
+  int read_vocabulary(const std::string& filename, int text_column, int freq_column, int freq_handling, int vocab_type) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) return -1;
+    int lex_index = (int)(lexicons.size() & 0xFF);
+    std::string line;
+    while (std::getline(f, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty()) continue;
+      std::vector<std::string> fields;
+      size_t fp = 0;
+      for (;;) {
+        size_t tab = line.find('\t', fp);
+        fields.push_back(line.substr(fp, tab == std::string::npos ? std::string::npos : tab - fp));
+        if (tab == std::string::npos) break;
+        fp = tab + 1;
+      }
+      if ((size_t)text_column >= fields.size()) return -2;  // reference: expect() panic
+      uint32_t frequency = 1;
+      if (freq_column >= 0) {
+        if (vocab_type & VT_INDEXED) have_freq = true;
+        if ((size_t)freq_column < fields.size()) {
+          char* end = nullptr;
+          const std::string& fs = fields[freq_column];
+          unsigned long long v = strtoull(fs.c_str(), &end, 10);
+          if (fs.empty() || *end != '\0' || v > 0xFFFFFFFFULL) return -3;  // reference: expect() panic
+          frequency = (uint32_t)v;
+        }
+      }
+      add_to_vocabulary(fields[text_column], true, frequency, freq_handling, vocab_type, lex_index);
+    }
+    lexicons.push_back(filename);
+    return 0;
+  }
+
+  // src/lib.rs:192-245
+  void build() {
+    index.clear();
+    sortedindex.clear();
+    for (size_t id = 0; id < decoder.size(); ++id) {
+      const VocabValue& v = decoder[id];
+      if (!(v.vocabtype & VT_INDEXED)) continue;
+      Big key = anahash(v.text, alphabet);
+      auto it = index.find(key);
+      if (it == index.end()) {
+        IndexNode node;
+        unsigned maxidx, count;
+        alphabet_upper_bound(key, alphabet_size(), &maxidx, &count);  // char_count(), src/anahash.rs:108
+        node.charcount = (uint16_t)count;
+        it = index.emplace(key, node).first;
+      }
+      it->second.instances.push_back(id);
+    }
+    for (auto& kv : index) sortedindex[kv.second.charcount].push_back(kv.first);
+    for (auto& kv : sortedindex) std::sort(kv.second.begin(), kv.second.end());
+  }
+
+  bool has(const std::string& text) const {  // src/lib.rs:331-338
+    Big key = anahash(text, alphabet);
+    auto it = index.find(key);
+    if (it == index.end()) return false;
+    for (uint64_t id : it->second.instances)
+      if (decoder[id].text == text) return true;
+    return false;
+  }
+
+  static unsigned threshold(const Threshold& t, size_t len) {  // src/lib.rs:982-1012
+    auto sat_u8 = [](double v) -> unsigned {
+      if (!(v == v)) return 0;
+      if (v <= 0) return 0;
+      if (v >= 255) return 255;
+      return (unsigned)v;
+    };
+    switch (t.kind) {
+      case 0: return std::min(sat_u8(std::floor((float)len * t.ratio)), 12u);
+      case 1: return std::min(sat_u8(std::floor((float)len * t.ratio)), t.value & 0xFF);
+      default: return std::min(t.value & 0xFF, sat_u8(std::floor((double)len / 2.0)));
+    }
+  }
+
+  // src/lib.rs:1143-1308.  Returns the matched index keys in ascending order (BTreeSet).
+  std::set<Big> find_nearest_anahashes(const Big& focus, unsigned max_distance, bool stop_at_exact, Stats* st) const {
+    std::set<Big> nearest;
+    auto hit = index.find(focus);
+    if (hit != index.end()) {
+      nearest.insert(hit->first);
+      if (stop_at_exact && !hit->second.instances.empty()) return nearest;
+    }
+    unsigned focus_upper_bound, focus_charcount;
+    alphabet_upper_bound(focus, alphabet_size(), &focus_upper_bound, &focus_charcount);
+    unsigned focus_alphabet_size = focus_upper_bound + 1;
+
+    std::unordered_map<uint8_t, std::vector<Big>> lookups;
+    for (unsigned distance = 1; distance <= max_distance; ++distance)
+      lookups[(uint8_t)(focus_charcount + distance)].push_back(focus);
+
+    IterParams ip;
+    ip.maxdepth = (int)max_distance;
+    ip.breadthfirst = true;
+    ip.empty_leaves = false;
+    ip.unique = true;
+    for (auto& item : recurse_deletions(focus, focus_alphabet_size + 1, ip)) {
+      if (st) ++st->deletions;
+      auto dh = index.find(item.node.value);
+      if (dh != index.end()) nearest.insert(dh->first);
+      unsigned deletion_charcount = focus_charcount - item.depth;
+      for (unsigned sd = 1; sd + item.depth <= max_distance; ++sd)
+        lookups[(uint8_t)(deletion_charcount + sd)].push_back(item.node.value);
+    }
+    for (auto& kv : lookups) {
+      auto si = sortedindex.find((uint16_t)kv.first);
+      if (si == sortedindex.end()) continue;
+      for (const Big& candidate : si->second) {
+        for (const Big& av : kv.second) {
+          if (st) ++st->modulo_tests;
+          if (ana_contains(candidate, av)) {
+            nearest.insert(candidate);
+            break;
+          }
+        }
+      }
+    }
+    return nearest;
+  }
+
+  struct Instance {
+    uint64_t vocab_id;
+    unsigned ld, lcs, prefixlen, suffixlen;
+    bool samecase;
+  };
+
+  // src/lib.rs:1311-1402
+  std::vector<Instance> gather_instances(const std::set<Big>& nearest, const NormString& q, const std::string& query,
+                                         unsigned max_edit_distance, Stats* st) const {
+    std::vector<Instance> found;
+    bool query_lower = false;
+    {
+      unsigned l;
+      uint32_t cp = utf8_decode(query.data(), query.size(), &l);
+      query_lower = orc_unicode::is_lowercase(cp);
+    }
+    for (const Big& key : nearest) {
+      const IndexNode& node = index.at(key);
+      for (uint64_t vocab_id : node.instances) {
+        const VocabValue& item = decoder[vocab_id];
+        if (st) ++st->dl_pairs;
+        int ld = damerau_levenshtein(q.data(), q.size(), item.norm.data(), item.norm.size(), max_edit_distance,
+                                     st ? &st->dl_cells : nullptr);
+        if (ld < 0) continue;
+        Instance in;
+        in.vocab_id = vocab_id;
+        in.ld = (unsigned)ld;
+        in.lcs = weights.lcs > 0.0 ? longest_common_substring_length(q.data(), q.size(), item.norm.data(), item.norm.size()) : 0;
+        in.prefixlen = weights.prefix > 0.0 ? common_prefix_length(q.data(), q.size(), item.norm.data(), item.norm.size()) : 0;
+        in.suffixlen = weights.suffix > 0.0 ? common_suffix_length(q.data(), q.size(), item.norm.data(), item.norm.size()) : 0;
+        if (weights.case_ > 0.0) {
+          unsigned l;
+          uint32_t cp = utf8_decode(item.text.data(), item.text.size(), &l);
+          in.samecase = orc_unicode::is_lowercase(cp) == query_lower;
+        } else {
+          in.samecase = true;
+        }
+        found.push_back(in);
+      }
+    }
+    return found;
+  }
+
+  static double result_score(const Result& r, float freq_weight) {  // src/types.rs:335-341
+    if (freq_weight == 0.0f) return r.dist_score;
+    return (r.dist_score + ((double)freq_weight * r.freq_score)) / (1.0 + (double)freq_weight);
+  }
+  static void rank_results(std::vector<Result>& results, float freq_weight) {  // src/lib.rs:1667, types.rs:344-365
+    std::stable_sort(results.begin(), results.end(), [freq_weight](const Result& a, const Result& b) {
+      if (freq_weight > 0.0f) return result_score(a, freq_weight) > result_score(b, freq_weight);
+      if (a.dist_score > b.dist_score) return true;
+      if (a.dist_score < b.dist_score) return false;
+      return a.freq_score > b.freq_score;
+    });
+  }
+
+  double compute_confusable_weight(const std::string& input, uint64_t candidate) const {  // src/lib.rs:1733-1756
+    double weight = 1.0;
+    auto script = shortest_edit_script(input, decoder[candidate].text);
+    for (const Confusable& c : confusables)
+      if (confusable_found_in(c, script)) weight *= c.weight;
+    return weight;
+  }
+
+  // src/lib.rs:1405-1653
+  std::vector<Result> score_and_rank(const std::vector<Instance>& instances, const std::string& input, size_t input_length,
+                                     const Params& p, Stats* st) const {
+    std::vector<Result> results;
+    double max_freq = 0.0;
+    const double weights_sum = weights.ld + weights.lcs + weights.prefix + weights.suffix + weights.case_;
+    const double L = (double)input_length;
+    for (const Instance& in : instances) {
+      const VocabValue& item = decoder[in.vocab_id];
+      double distance_score = in.ld > input_length ? 0.0 : 1.0 - ((double)in.ld / L);
+      double lcs_score = (double)in.lcs / L;
+      double prefix_score = (double)in.prefixlen / L;
+      double suffix_score = (double)in.suffixlen / L;
+      volatile double t0 = weights.ld * distance_score;  // volatile: forbid FMA contraction / reassociation
+      volatile double t1 = weights.lcs * lcs_score;
+      volatile double t2 = weights.prefix * prefix_score;
+      volatile double t3 = weights.suffix * suffix_score;
+      volatile double acc = t0 + t1;
+      acc = acc + t2;
+      acc = acc + t3;
+      acc = acc + (in.samecase ? weights.case_ : 0.0);
+      double score = acc / weights_sum;
+      double freq_score = have_freq ? (double)item.frequency : 1.0;
+      if (freq_score > max_freq) max_freq = freq_score;
+      if (score >= p.score_threshold) results.push_back(Result{in.vocab_id, score, freq_score});
+    }
+    if (st) st->survivors += instances.size();
+    if (!confusables.empty() && confusables_before_pruning)
+      for (Result& r : results) r.dist_score *= compute_confusable_weight(input, r.vocab_id);
+    if (max_freq > 0.0)
+      for (Result& r : results) r.freq_score = r.freq_score / max_freq;
+    rank_results(results, p.freq_weight);
+    const size_t max_matches = (size_t)p.max_matches;
+    if (max_matches > 0 && results.size() > max_matches) {
+      double last_score = result_score(results[max_matches - 1], p.freq_weight);
+      double cropped_score = result_score(results[max_matches], p.freq_weight);
+      if (cropped_score < last_score) {
+        results.resize(max_matches);
+      } else {
+        size_t early_cutoff = 0, late_cutoff = 0;
+        for (size_t i = 0; i < results.size(); ++i) {
+          if (results[i].dist_score == cropped_score && early_cutoff == 0) early_cutoff = i;
+          if (results[i].dist_score < cropped_score) {
+            late_cutoff = i;
+            break;
+          }
+        }
+        if (early_cutoff > 0)
+          results.resize(early_cutoff + 1);
+        else if (late_cutoff > 0)
+          results.resize(late_cutoff + 1);
+      }
+    }
+    if (!confusables.empty() && !confusables_before_pruning) {
+      for (Result& r : results) r.dist_score *= compute_confusable_weight(input, r.vocab_id);
+      rank_results(results, p.freq_weight);
+    }
+    size_t cutoff = 0;
+    if (p.cutoff_threshold >= 1.0) {
+      bool have_best = false;
+      double bestscore = 0;
+      for (size_t i = 0; i < results.size(); ++i) {
+        if (have_best) {
+          if (result_score(results[i], p.freq_weight) <= bestscore / p.cutoff_threshold) {
+            cutoff = i;
+            break;
+          }
+        } else {
+          bestscore = result_score(results[i], p.freq_weight);
+          have_best = true;
+        }
+      }
+    }
+    if (cutoff > 0) results.resize(cutoff);
+    return results;
+  }
+
+  // src/lib.rs:972-1027
+  std::vector<Result> find_variants(const std::string& input, const Params& p, Stats* st) const {
+    if (index.empty()) return {};
+    NormString normstring = normalize_to_alphabet(input, alphabet);
+    Big key = anahash(input, alphabet);
+    if (normstring.empty()) {
+      // reference: assert!(input_length > 0) panics (src/lib.rs:1420); the oracle reports no result
+      return {};
+    }
+    if (st) ++st->queries;
+    unsigned ka = threshold(p.max_anagram_distance, normstring.size());
+    std::set<Big> nearest = find_nearest_anahashes(key, ka, p.stop_at_exact_match != 0, st);
+    if (st) st->anagram_hits += nearest.size();
+    unsigned ke = threshold(p.max_edit_distance, normstring.size());
+    auto instances = gather_instances(nearest, normstring, input, ke, st);
+    return score_and_rank(instances, input, normstring.size(), p, st);
+  }
+};
+
+// ---- src/search.rs:190-336 + src/lib.rs:1790-1957 : the batch producer -------------------------
+struct Span {
+  size_t begin, end;
+};
+static std::vector<Span> find_boundaries(const std::string& text) {  // src/search.rs:190-235
+  std::vector<Span> out;
+  bool in_boundary = false;
+  size_t b = 0;
+  for (size_t i = 0; i < text.size();) {
+    unsigned l;
+    uint32_t cp = utf8_decode(text.data() + i, text.size() - i, &l);
+    bool alpha = orc_unicode::is_alphabetic(cp);
+    if (in_boundary) {
+      if (alpha) {
+        out.push_back({b, i});
+        in_boundary = false;
+      }
+    } else if (!alpha) {
+      b = i;
+      in_boundary = true;
+    }
+    i += l;
+  }
+  if (in_boundary)
+    out.push_back({b, text.size()});
+  else
+    out.push_back({text.size(), text.size()});
+  return out;
+}
+enum { B_NONE = 0, B_WEAK = 1, B_NORMAL = 2, B_HARD = 3 };
+static std::vector<int> classify_boundaries(const std::string& text, const std::vector<Span>& b) {  // :238-258
+  std::vector<int> out;
+  for (size_t i = 0; i < b.size(); ++i) {
+    size_t len = b[i].end - b[i].begin;
+    if (i == b.size() - 1 || len > 1)
+      out.push_back(B_HARD);
+    else {
+      char c = len == 1 ? text[b[i].begin] : 0;
+      out.push_back((c == '\'' || c == '-' || c == '_') ? B_WEAK : B_NORMAL);
+    }
+  }
+  return out;
+}
+struct Segment {
+  size_t begin, end;
+  unsigned n;
+  bool looked_up;
+  std::vector<Result> variants;
+};
+// src/search.rs:262-312 ; `bounds` is the slice of boundaries of the current batch
+static std::vector<Segment> find_match_ngrams(const std::string& text, const Span* bounds, size_t nbounds, unsigned order,
+                                              size_t begin, size_t end) {
+  std::vector<Segment> ngrams;
+  size_t i = 0;
+  while (i + order - 1 < nbounds) {
+    const Span& boundary = bounds[i + order - 1];
+    if (boundary.begin > end) break;
+    size_t mb = begin, me = boundary.begin;
+    if (me > mb && !(me - mb == 1 && text[mb] == ' ')) ngrams.push_back(Segment{mb, me, order, false, {}});
+    begin = bounds[i].end;
+    ++i;
+  }
+  if (begin < end) {
+    if (!(end - begin == 1 && text[begin] == ' ')) {
+      // internal_boundaries() (src/search.rs:99-116): counts via a begin/end window quirk
+      long ib = -1;
+      size_t ie = 0;
+      for (size_t k = 0; k < nbounds; ++k) {
+        if (bounds[k].begin > begin && bounds[k].end < end) {
+          if (ib < 0)
+            ib = (long)k;
+          else
+            ie = k + 1;
+        }
+      }
+      size_t count = (ib < 0 || (size_t)ib >= ie) ? 0 : ie - (size_t)ib;
+      if (count == order) ngrams.push_back(Segment{begin, end, order, false, {}});
+    }
+  }
+  return ngrams;
+}
+static bool redundant_match(const Segment& cand, const std::vector<Segment>& matches) {  // :317-336
+  for (const Segment& r : matches) {
+    if (r.n == 1) {
+      if (r.begin >= cand.begin && r.end <= cand.end) {
+        if (!r.looked_up) return false;
+        if (r.variants.empty() || r.variants[0].dist_score < 1.0) return false;
+      }
+    } else
+      break;
+  }
+  return true;
+}
+// src/lib.rs:1790-1957 without the FST consolidation stage (out of scope): returns every segment
+// of every order with its variant list, in the reference's batch order.
+static std::vector<Segment> find_all_segments(const Model& m, const std::string& text, const Params& p, Stats* st) {
+  std::vector<Segment> all;
+  if (text.empty() || m.index.empty()) return all;
+  auto boundaries = find_boundaries(text);
+  auto strengths = classify_boundaries(text, boundaries);
+  size_t begin = 0, begin_index = 0;
+  for (size_t i = 0; i < boundaries.size(); ++i) {
+    if (strengths[i] == B_HARD && boundaries[i].begin != begin) {
+      std::vector<Segment> batch;
+      for (unsigned order = 1; order <= (unsigned)p.max_ngram; ++order) {
+        auto cur = find_match_ngrams(text, boundaries.data() + begin_index, i + 1 - begin_index, order, begin,
+                                     boundaries[i].begin);
+        for (Segment& seg : cur) {
+          if (order == 1 || !redundant_match(seg, batch)) {
+            seg.variants = m.find_variants(text.substr(seg.begin, seg.end - seg.begin), p, st);
+            seg.looked_up = true;
+          }
+        }
+        batch.insert(batch.end(), cur.begin(), cur.end());
+      }
+      all.insert(all.end(), batch.begin(), batch.end());
+      begin = boundaries[i].end;
+      begin_index = i + 1;
+    }
+  }
+  return all;
+}
+
+}  // namespace orc
+
+// ================================================================================================
+// C interface (ctypes) -- consumed only by tests/, smoke() and bench.py's CPU baseline.
+// ================================================================================================
+using namespace orc;
+
+static char* dup_cstr(const std::string& s) {
+  char* p = (char*)malloc(s.size() + 1);
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+extern "C" {
+
+void* orc_new(const char* alphabet_tsv, uint64_t len, const double* w) {
+  Model* m = new Model();
+  m->weights = Weights{w[0], w[1], w[2], w[3], w[4]};
+  m->read_alphabet_text(std::string(alphabet_tsv, len));
+  m->init_vocab();
+  return m;
+}
+void orc_free(void* h) { delete (Model*)h; }
+uint32_t orc_alphabet_len(void* h) { return (uint32_t)((Model*)h)->alphabet.size(); }
+int32_t orc_read_vocabulary(void* h, const char* filename, int32_t text_column, int32_t freq_column, int32_t freq_handling,
+                            int32_t vocab_type) {
+  return ((Model*)h)->read_vocabulary(filename, text_column, freq_column, freq_handling, vocab_type);
+}
+uint64_t orc_add_to_vocabulary(void* h, const char* text, int32_t has_freq, uint32_t freq, int32_t freq_handling,
+                               int32_t vocab_type, int32_t lex_index) {
+  return ((Model*)h)->add_to_vocabulary(text, has_freq != 0, freq, freq_handling, vocab_type, lex_index);
+}
+void orc_set_have_freq(void* h, int32_t v) { ((Model*)h)->have_freq = v != 0; }
+int32_t orc_add_confusable(void* h, const char* script, double weight) {
+  Confusable c;
+  if (!confusable_new(script, weight, &c)) return -1;
+  ((Model*)h)->confusables.push_back(c);
+  return 0;
+}
+void orc_set_confusables_before_pruning(void* h) { ((Model*)h)->confusables_before_pruning = true; }
+void orc_build(void* h) { ((Model*)h)->build(); }
+int32_t orc_has(void* h, const char* text) { return ((Model*)h)->has(text) ? 1 : 0; }
+uint64_t orc_vocab_size(void* h) { return ((Model*)h)->decoder.size(); }
+uint64_t orc_index_size(void* h) { return ((Model*)h)->index.size(); }
+uint64_t orc_instance_count(void* h) {
+  uint64_t n = 0;
+  for (auto& kv : ((Model*)h)->index) n += kv.second.instances.size();
+  return n;
+}
+// number of anagrams of a given charcount (0 if none)
+uint64_t orc_sortedindex_count(void* h, uint32_t charcount) {
+  auto& si = ((Model*)h)->sortedindex;
+  auto it = si.find((uint16_t)charcount);
+  return it == si.end() ? 0 : it->second.size();
+}
+uint32_t orc_max_key_bits(void* h) {
+  unsigned b = 0;
+  for (auto& kv : ((Model*)h)->index) b = std::max(b, kv.first.bits());
+  return b;
+}
+const char* orc_vocab_text(void* h, uint64_t id) { return ((Model*)h)->decoder[id].text.c_str(); }
+uint32_t orc_vocab_freq(void* h, uint64_t id) { return ((Model*)h)->decoder[id].frequency; }
+uint32_t orc_vocab_lexindex(void* h, uint64_t id) { return ((Model*)h)->decoder[id].lexindex; }
+int64_t orc_vocab_lookup(void* h, const char* text) {
+  auto& e = ((Model*)h)->encoder;
+  auto it = e.find(text);
+  return it == e.end() ? -1 : (int64_t)it->second;
+}
+void orc_free_str(char* p) { free(p); }
+
+// primitives for the KATs ------------------------------------------------------------------------
+char* orc_anahash(void* h, const char* text) { return dup_cstr(anahash(text, ((Model*)h)->alphabet).to_decimal()); }
+int64_t orc_normalize(void* h, const char* text, uint8_t* out, int64_t cap) {
+  NormString n = normalize_to_alphabet(text, ((Model*)h)->alphabet);
+  for (size_t i = 0; i < n.size() && (int64_t)i < cap; ++i) out[i] = n[i];
+  return (int64_t)n.size();
+}
+// arithmetic on decimal strings (insert/delete/contains KATs)
+static Big big_from_decimal(const char* s) {
+  Big r;
+  for (; *s; ++s) {
+    r = r.mul_small(10);
+    Big dgt((uint64_t)(*s - '0'));
+    // r += dgt
+    uint64_t carry = dgt.is_zero() ? 0 : dgt.d[0];
+    uint32_t i = 0;
+    while (carry) {
+      if (i == r.n) r.d[r.n++] = 0;
+      uint64_t t = (uint64_t)r.d[i] + carry;
+      r.d[i] = (uint32_t)t;
+      carry = t >> 32;
+      ++i;
+    }
+  }
+  return r;
+}
+char* orc_ana_insert(const char* a, const char* b) { return dup_cstr(ana_insert(big_from_decimal(a), big_from_decimal(b)).to_decimal()); }
+int32_t orc_ana_contains(const char* a, const char* b) { return ana_contains(big_from_decimal(a), big_from_decimal(b)) ? 1 : 0; }
+char* orc_ana_delete(const char* a, const char* b) {
+  Big out;
+  if (!ana_delete(big_from_decimal(a), big_from_decimal(b), &out)) return nullptr;
+  return dup_cstr(out.to_decimal());
+}
+void orc_alphabet_upper_bound(const char* v, uint32_t alphabet_size, uint32_t* maxidx, uint32_t* count) {
+  alphabet_upper_bound(big_from_decimal(v), alphabet_size, maxidx, count);
+}
+// Deletion iterators.  mode 0 = iter_parents (single deletions), 1 = iter (single beam),
+// 2 = iter_recursive with the given SearchParams.  Output: "value:depth:charindex" lines.
+char* orc_deletions(const char* v, uint32_t alphabet_size, int32_t mode, int32_t maxdepth, int32_t breadthfirst,
+                    int32_t allow_duplicates, int32_t allow_empty_leaves) {
+  Big start = big_from_decimal(v);
+  std::string out;
+  if (mode == 0) {
+    for (auto& c : deletion_children(start, alphabet_size))
+      out += c.value.to_decimal() + ":1:" + std::to_string(c.charindex) + "\n";
+  } else {
+    IterParams p;
+    if (mode == 1) {
+      p.singlebeam = true;
+    } else {
+      p.maxdepth = maxdepth;
+      p.breadthfirst = breadthfirst != 0;
+      p.unique = allow_duplicates == 0;
+      p.empty_leaves = allow_empty_leaves != 0;
+    }
+    for (auto& it : recurse_deletions(start, alphabet_size, p))
+      out += it.node.value.to_decimal() + ":" + std::to_string(it.depth) + ":" + std::to_string(it.node.charindex) + "\n";
+  }
+  return dup_cstr(out);
+}
+int32_t orc_damerau_levenshtein(const uint8_t* s, uint64_t ns, const uint8_t* t, uint64_t nt, uint32_t maxd) {
+  return damerau_levenshtein(s, ns, t, nt, maxd, nullptr);
+}
+uint32_t orc_lcs(const uint8_t* s, uint64_t ns, const uint8_t* t, uint64_t nt) { return longest_common_substring_length(s, ns, t, nt); }
+uint32_t orc_prefix(const uint8_t* s, uint64_t ns, const uint8_t* t, uint64_t nt) { return common_prefix_length(s, ns, t, nt); }
+uint32_t orc_suffix(const uint8_t* s, uint64_t ns, const uint8_t* t, uint64_t nt) { return common_suffix_length(s, ns, t, nt); }
+uint32_t orc_threshold(int32_t kind, float ratio, uint32_t value, uint64_t len) {
+  return Model::threshold(Threshold{kind, ratio, value}, len);
+}
+// edit script as "=[..]" "+[..]" "-[..]" concatenation
+char* orc_edit_script(const char* src, const char* dst) {
+  std::string out;
+  for (auto& e : shortest_edit_script(src, dst)) {
+    out += e.op == EQ ? "=[" : (e.op == INS ? "+[" : "-[");
+    out += e.options[0];
+    out += "]";
+  }
+  return dup_cstr(out);
+}
+int32_t orc_confusable_found_in(const char* pattern, const char* src, const char* dst) {
+  Confusable c;
+  if (!confusable_new(pattern, 1.0, &c)) return -1;
+  return confusable_found_in(c, shortest_edit_script(src, dst)) ? 1 : 0;
+}
+
+// candidate set (ascending keys, decimal, newline separated)
+char* orc_nearest(void* h, const char* text, uint32_t k, int32_t stop_at_exact) {
+  Model* m = (Model*)h;
+  Big key = anahash(text, m->alphabet);
+  std::string out;
+  for (const Big& b : m->find_nearest_anahashes(key, k, stop_at_exact != 0, nullptr)) out += b.to_decimal() + "\n";
+  return dup_cstr(out);
+}
+
+// single query; returns number of results (all of them are written if cap allows)
+int64_t orc_find_variants(void* h, const char* input, const Params* p, Result* out, int64_t cap) {
+  auto r = ((Model*)h)->find_variants(input, *p, nullptr);
+  for (size_t i = 0; i < r.size() && (int64_t)i < cap; ++i) out[i] = r[i];
+  return (int64_t)r.size();
+}
+
+// Batched queries, OpenMP over queries (== rayon par_iter, src/bin/analiticcl.rs:445-448).
+// offsets has n+1 entries into blob.  out_offsets (n+1) is filled; *out_results is malloc'ed.
+int32_t orc_find_variants_batch(void* h, const char* blob, const uint64_t* offsets, uint64_t n, const Params* p,
+                                int32_t threads, uint64_t* out_offsets, Result** out_results, Stats* stats) {
+  Model* m = (Model*)h;
+  std::vector<std::vector<Result>> all(n);
+  Stats total;
+  memset(&total, 0, sizeof total);
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel
+  {
+    Stats local;
+    memset(&local, 0, sizeof local);
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      std::string q(blob + offsets[i], offsets[i + 1] - offsets[i]);
+      all[i] = m->find_variants(q, *p, stats ? &local : nullptr);
+    }
+#pragma omp critical
+    {
+      total.queries += local.queries;
+      total.modulo_tests += local.modulo_tests;
+      total.deletions += local.deletions;
+      total.anagram_hits += local.anagram_hits;
+      total.dl_pairs += local.dl_pairs;
+      total.dl_cells += local.dl_cells;
+      total.survivors += local.survivors;
+    }
+  }
+  if (stats) *stats = total;
+  uint64_t tot = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    out_offsets[i] = tot;
+    tot += all[i].size();
+  }
+  out_offsets[n] = tot;
+  Result* buf = (Result*)malloc(sizeof(Result) * (tot ? tot : 1));
+  for (uint64_t i = 0; i < n; ++i)
+    if (!all[i].empty()) memcpy(buf + out_offsets[i], all[i].data(), sizeof(Result) * all[i].size());
+  *out_results = buf;
+  return 0;
+}
+void orc_free_results(Result* r) { free(r); }
+int32_t orc_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// find_all_matches batch producer: every looked-up (or skipped) segment with its variants.
+// Output per segment: begin,end,n,looked_up and a CSR of results.
+int64_t orc_find_all_segments(void* h, const char* text, uint64_t len, const Params* p, uint64_t* seg_begin,
+                              uint64_t* seg_end, uint32_t* seg_n, uint8_t* seg_looked, uint64_t* res_offsets, int64_t seg_cap,
+                              Result* results, int64_t res_cap) {
+  auto segs = find_all_segments(*(Model*)h, std::string(text, len), *p, nullptr);
+  int64_t r = 0;
+  for (size_t i = 0; i < segs.size(); ++i) {
+    if ((int64_t)i < seg_cap) {
+      seg_begin[i] = segs[i].begin;
+      seg_end[i] = segs[i].end;
+      seg_n[i] = segs[i].n;
+      seg_looked[i] = segs[i].looked_up;
+      res_offsets[i] = r;
+    }
+    for (auto& v : segs[i].variants) {
+      if (r < res_cap) results[r] = v;
+      ++r;
+    }
+  }
+  if ((int64_t)segs.size() < seg_cap) res_offsets[segs.size()] = r;
+  return (int64_t)segs.size();
+}
+// boundaries as begin,end pairs + strength
+int64_t orc_find_boundaries(const char* text, uint64_t len, uint64_t* begins, uint64_t* ends, int32_t* strengths, int64_t cap) {
+  std::string t(text, len);
+  auto b = find_boundaries(t);
+  auto s = classify_boundaries(t, b);
+  for (size_t i = 0; i < b.size() && (int64_t)i < cap; ++i) {
+    begins[i] = b[i].begin;
+    ends[i] = b[i].end;
+    strengths[i] = s[i];
+  }
+  return (int64_t)b.size();
+}
+int64_t orc_find_match_ngrams(const char* text, uint64_t len, uint32_t order, uint64_t* begins, uint64_t* ends, int64_t cap) {
+  std::string t(text, len);
+  auto b = find_boundaries(t);
+  auto g = find_match_ngrams(t, b.data(), b.size(), order, 0, t.size());
+  for (size_t i = 0; i < g.size() && (int64_t)i < cap; ++i) {
+    begins[i] = g[i].begin;
+    ends[i] = g[i].end;
+  }
+  return (int64_t)g.size();
+}
+int32_t orc_is_alphabetic(uint32_t cp) { return orc_unicode::is_alphabetic(cp); }
+int32_t orc_is_lowercase(uint32_t cp) { return orc_unicode::is_lowercase(cp); }
+
+}  // extern "C"
