@@ -1,0 +1,407 @@
+// capi.cpp -- the extern "C" boundary declared in include/analiticcl_b200.h.
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/analiticcl_b200.h"
+#include "engine.h"
+#include "host_model.h"
+#include "search.h"
+
+using namespace anl;
+
+struct anl_model {
+  HostModel host;
+  Engine engine;
+  anl_model(const Weights& w, int debug) : host(w, debug), engine(&host) {}
+};
+struct anl_result_set {
+  ResultSet rs;
+};
+struct anl_match_set {
+  std::vector<anl_match> matches;
+  std::vector<std::vector<anl_variant>> storage;
+};
+struct anl_device_batch {
+  DeviceBatch* b;
+};
+
+static thread_local std::string g_last_error;
+static anl_status fail(anl_status code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+extern "C" {
+
+const char* anl_last_error(void) { return g_last_error.c_str(); }
+const char* anl_version(void) { return "analiticcl_b200 0.1 (reference: analiticcl 0.4.9; sm_100a)"; }
+
+void anl_weights_default(anl_weights* w) {
+  Weights d;
+  w->ld = d.ld;
+  w->lcs = d.lcs;
+  w->prefix = d.prefix;
+  w->suffix = d.suffix;
+  w->case_ = d.case_;
+}
+void anl_search_params_default(anl_search_params* p) {  // src/types.rs:170-192
+  memset(p, 0, sizeof *p);
+  p->max_anagram_distance = anl_distance_threshold{ANL_THRESHOLD_ABSOLUTE, 0.f, 3};
+  p->max_edit_distance = anl_distance_threshold{ANL_THRESHOLD_ABSOLUTE, 0.f, 3};
+  p->max_matches = 20;
+  p->score_threshold = 0.25;
+  p->cutoff_threshold = 2.0;
+  p->stop_criterion = ANL_STOP_EXHAUSTIVE;
+  p->max_ngram = 3;
+  p->lm_order = 3;
+  p->max_seq = 250;
+  p->single_thread = 0;
+  p->context_weight = 0.0f;
+  p->variantmodel_weight = 3.0f;
+  p->lm_weight = 1.0f;
+  p->contextrules_weight = 1.0f;
+  p->freq_weight = 0.0f;
+  p->consolidate_matches = 1;
+  p->unicodeoffsets = 0;
+}
+void anl_vocab_params_default(anl_vocab_params* p) {  // src/vocab.rs:121-131
+  p->text_column = 0;
+  p->freq_column = 1;
+  p->freq_handling = ANL_FREQ_MAX;
+  p->vocab_type = ANL_VOCAB_INDEXED;
+  p->index = 0;
+}
+
+static Weights to_weights(const anl_weights* w) {
+  Weights r;
+  if (w) {
+    r.ld = w->ld;
+    r.lcs = w->lcs;
+    r.prefix = w->prefix;
+    r.suffix = w->suffix;
+    r.case_ = w->case_;
+  }
+  return r;
+}
+static VocabParams to_vocab_params(const anl_vocab_params* p) {
+  VocabParams r;
+  if (p) {
+    r.text_column = p->text_column;
+    r.freq_column = p->freq_column;
+    r.freq_handling = p->freq_handling;
+    r.vocab_type = p->vocab_type;
+    r.index = p->index;
+  }
+  return r;
+}
+
+anl_status anl_model_new(const char* alphabet_file, const anl_weights* weights, int32_t debug, anl_model** out) {
+  if (!alphabet_file || !out) return fail(ANL_ERR_INVALID, "null argument");
+  anl_model* m = new (std::nothrow) anl_model(to_weights(weights), debug);
+  if (!m) return fail(ANL_ERR_INVALID, "out of memory");
+  std::string err;
+  if (!m->host.read_alphabet_file(alphabet_file, &err)) {
+    delete m;
+    return fail(ANL_ERR_IO, err);
+  }
+  m->host.init_vocab();
+  *out = m;
+  return ANL_OK;
+}
+anl_status anl_model_new_from_tsv(const char* alphabet_tsv, size_t len, const anl_weights* weights, int32_t debug,
+                                  anl_model** out) {
+  if (!alphabet_tsv || !out) return fail(ANL_ERR_INVALID, "null argument");
+  anl_model* m = new (std::nothrow) anl_model(to_weights(weights), debug);
+  if (!m) return fail(ANL_ERR_INVALID, "out of memory");
+  m->host.read_alphabet_text(std::string(alphabet_tsv, len));
+  m->host.init_vocab();
+  *out = m;
+  return ANL_OK;
+}
+void anl_model_free(anl_model* m) { delete m; }
+
+anl_status anl_model_read_vocabulary(anl_model* m, const char* filename, const anl_vocab_params* params) {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.read_vocabulary(filename, to_vocab_params(params), &err)) return fail(ANL_ERR_IO, err);
+  return ANL_OK;
+}
+anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t len, int32_t has_frequency, uint32_t frequency,
+                                       const anl_vocab_params* params, uint64_t* vocab_id) {
+  if (!m || !text) return fail(ANL_ERR_INVALID, "null argument");
+  uint64_t id = m->host.add_to_vocabulary(text, len, has_frequency != 0, frequency, to_vocab_params(params));
+  if (vocab_id) *vocab_id = id;
+  return ANL_OK;
+}
+anl_status anl_model_read_confusablelist(anl_model* m, const char* filename) {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.read_confusablelist(filename, &err)) return fail(ANL_ERR_IO, err);
+  return ANL_OK;
+}
+anl_status anl_model_add_to_confusables(anl_model* m, const char* editscript, double weight) {
+  if (!m || !editscript) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.add_to_confusables(editscript, weight, &err)) return fail(ANL_ERR_INVALID, err);
+  return ANL_OK;
+}
+void anl_model_set_confusables_before_pruning(anl_model* m) {
+  if (m) m->host.confusables_before_pruning = true;
+}
+
+anl_status anl_model_build(anl_model* m, int32_t device) {
+  if (!m) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  int sd = 1;
+  if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
+  if (!m->host.build_index(sd, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+
+int32_t anl_model_has(const anl_model* m, const char* text, size_t len) { return m && m->host.has(text, len) ? 1 : 0; }
+int64_t anl_model_vocab_id(const anl_model* m, const char* text, size_t len) { return m ? m->host.vocab_id(text, len) : -1; }
+uint64_t anl_model_vocab_size(const anl_model* m) { return m ? m->host.decoder.size() : 0; }
+anl_status anl_model_get_vocab(const anl_model* m, uint64_t vocab_id, anl_vocab_info* out) {
+  if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
+  if (vocab_id >= m->host.decoder.size()) return fail(ANL_ERR_INVALID, "vocabulary id out of range");
+  const VocabEntry& e = m->host.decoder[vocab_id];
+  out->text = e.text.c_str();
+  out->text_len = (uint32_t)e.text.size();
+  out->frequency = e.frequency;
+  out->lexindex = e.lexindex;
+  out->vocabtype = e.vocabtype;
+  out->tokencount = e.tokencount;
+  out->norm_len = (uint32_t)e.syms.size();
+  return ANL_OK;
+}
+uint32_t anl_model_lexicon_count(const anl_model* m) { return m ? (uint32_t)m->host.lexicons.size() : 0; }
+const char* anl_model_lexicon_name(const anl_model* m, uint32_t index) {
+  if (!m || index >= m->host.lexicons.size()) return nullptr;
+  return m->host.lexicons[index].c_str();
+}
+uint32_t anl_model_alphabet_size(const anl_model* m) { return m ? m->host.alphabet_size() : 0; }
+uint64_t anl_model_index_size(const anl_model* m) { return m && m->host.built ? m->host.index.ana_key.size() : 0; }
+uint64_t anl_model_instance_count(const anl_model* m) { return m && m->host.built ? m->host.index.inst_vocab.size() : 0; }
+uint64_t anl_model_anagram_count_of_length(const anl_model* m, uint32_t charcount) {
+  if (!m || !m->host.built) return 0;
+  uint64_t n = 0;
+  for (uint16_t cc : m->host.index.ana_charcount) n += (cc == charcount);
+  return n;
+}
+uint32_t anl_model_max_key_bits(const anl_model* m) { return m && m->host.built ? m->host.index.max_key_bits : 0; }
+
+int64_t anl_normalize(const anl_model* m, const char* text, size_t len, uint8_t* out, size_t cap) {
+  if (!m || !text) return -1;
+  std::vector<uint8_t> syms;
+  m->host.alphabet.encode(text, len, &syms);
+  // the reference's NormString encodes unknown symbols as alphabet.len() + 1 (src/anahash.rs:76)
+  const uint8_t unk = (uint8_t)m->host.alphabet.unk_symbol();
+  for (size_t i = 0; i < syms.size() && i < cap; ++i) out[i] = syms[i] == unk ? (uint8_t)(unk + 1) : syms[i];
+  return (int64_t)syms.size();
+}
+int64_t anl_anahash(const anl_model* m, const char* text, size_t len, uint64_t* limbs, size_t cap) {
+  if (!m || !text) return -1;
+  std::vector<uint64_t> v = m->host.anahash_limbs(text, len);
+  for (size_t i = 0; i < v.size() && i < cap; ++i) limbs[i] = v[i];
+  return (int64_t)v.size();
+}
+
+// ---- lookup ------------------------------------------------------------------------------------------
+anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                   const anl_search_params* params, anl_result_set** out) {
+  if (!m || !offsets || !params || !out || (!blob && n_queries > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built || !m->engine.uploaded())
+    return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_variants()");
+  anl_result_set* rs = new anl_result_set();
+  std::string err;
+  int status = ANL_OK;
+  if (!m->engine.find_variants_batch(blob ? blob : "", offsets, n_queries, *params, &rs->rs, &err, &status)) {
+    delete rs;
+    return fail(status ? status : ANL_ERR_CUDA, err);
+  }
+  *out = rs;
+  return ANL_OK;
+}
+uint64_t anl_result_set_len(const anl_result_set* rs) { return rs ? rs->rs.offsets.size() - 1 : 0; }
+const anl_variant* anl_result_set_get(const anl_result_set* rs, uint64_t i, uint64_t* count) {
+  if (!rs || i + 1 >= rs->rs.offsets.size()) {
+    if (count) *count = 0;
+    return nullptr;
+  }
+  if (count) *count = rs->rs.offsets[i + 1] - rs->rs.offsets[i];
+  return rs->rs.variants.data() + rs->rs.offsets[i];
+}
+const uint64_t* anl_result_set_offsets(const anl_result_set* rs) { return rs ? rs->rs.offsets.data() : nullptr; }
+const anl_variant* anl_result_set_variants(const anl_result_set* rs) { return rs ? rs->rs.variants.data() : nullptr; }
+uint32_t anl_result_set_flags(const anl_result_set* rs, uint64_t i) {
+  return rs && i < rs->rs.flags.size() ? rs->rs.flags[i] : 0;
+}
+void anl_result_set_free(anl_result_set* rs) { delete rs; }
+
+// find_all_matches: src/lib.rs:1790-1957 without the FST stage (see the header)
+anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, const anl_search_params* params,
+                                anl_match_set** out) {
+  if (!m || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built || !m->engine.uploaded())
+    return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_all_matches()");
+  const std::string t(text ? text : "", len);
+  anl_match_set* ms = new anl_match_set();
+  std::vector<SpanBatch> batches = segment_text(t, params->max_ngram);
+  // flat list of segments in the reference's output order
+  struct Seg {
+    SegmentSpan span;
+    size_t batch;
+    bool looked_up = false;
+    std::vector<anl_variant> variants;
+  };
+  std::vector<Seg> segs;
+  for (size_t bi = 0; bi < batches.size(); ++bi)
+    for (const SegmentSpan& s : batches[bi].segments) segs.push_back(Seg{s, bi, false, {}});
+  std::string err;
+  int status = ANL_OK;
+  auto lookup = [&](const std::vector<size_t>& which) -> bool {
+    if (which.empty()) return true;
+    std::string blob;
+    std::vector<uint64_t> offs{0};
+    for (size_t k : which) {
+      blob.append(t, segs[k].span.begin, segs[k].span.end - segs[k].span.begin);
+      offs.push_back(blob.size());
+    }
+    ResultSet rs;
+    if (!m->engine.find_variants_batch(blob.data(), offs.data(), which.size(), *params, &rs, &err, &status)) return false;
+    for (size_t i = 0; i < which.size(); ++i) {
+      Seg& s = segs[which[i]];
+      s.looked_up = true;
+      s.variants.assign(rs.variants.begin() + rs.offsets[i], rs.variants.begin() + rs.offsets[i + 1]);
+    }
+    return true;
+  };
+  // pass 1: every unigram
+  std::vector<size_t> pass;
+  for (size_t k = 0; k < segs.size(); ++k)
+    if (segs[k].span.n == 1) pass.push_back(k);
+  bool ok = lookup(pass);
+  // pass 2: higher orders unless redundant (src/search.rs:317-336): every covered unigram of the same
+  // batch already has a best variant with dist_score >= 1.0
+  if (ok && params->max_ngram > 1) {
+    pass.clear();
+    size_t batch_start = 0;
+    for (size_t k = 0; k < segs.size(); ++k) {
+      if (k > 0 && segs[k].batch != segs[k - 1].batch) batch_start = k;
+      if (segs[k].span.n == 1) continue;
+      bool redundant = true;
+      for (size_t u = batch_start; u < segs.size() && segs[u].batch == segs[k].batch && segs[u].span.n == 1; ++u) {
+        if (segs[u].span.begin >= segs[k].span.begin && segs[u].span.end <= segs[k].span.end) {
+          if (segs[u].variants.empty() || segs[u].variants[0].dist_score < 1.0) {
+            redundant = false;
+            break;
+          }
+        }
+      }
+      if (!redundant) pass.push_back(k);
+    }
+    ok = lookup(pass);
+  }
+  if (!ok) {
+    delete ms;
+    return fail(status ? status : ANL_ERR_CUDA, err);
+  }
+  std::vector<uint64_t> cpmap;
+  if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
+  ms->storage.resize(segs.size());
+  ms->matches.resize(segs.size());
+  for (size_t k = 0; k < segs.size(); ++k) {
+    ms->storage[k] = std::move(segs[k].variants);
+    anl_match& mm = ms->matches[k];
+    mm.begin = params->unicodeoffsets ? cpmap[segs[k].span.begin] : segs[k].span.begin;
+    mm.end = params->unicodeoffsets ? cpmap[segs[k].span.end] : segs[k].span.end;
+    mm.n = segs[k].span.n;
+    mm.n_variants = ms->storage[k].size();
+    mm.variants = segs[k].looked_up ? ms->storage[k].data() : nullptr;
+    mm.selected = (segs[k].looked_up && !ms->storage[k].empty()) ? 0 : -1;
+  }
+  *out = ms;
+  return ANL_OK;
+}
+uint64_t anl_match_set_len(const anl_match_set* ms) { return ms ? ms->matches.size() : 0; }
+anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out) {
+  if (!ms || !out || i >= ms->matches.size()) return fail(ANL_ERR_INVALID, "match index out of range");
+  *out = ms->matches[i];
+  return ANL_OK;
+}
+void anl_match_set_free(anl_match_set* ms) { delete ms; }
+
+// ---- device-resident path ---------------------------------------------------------------------------------
+anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                   const anl_search_params* params, anl_device_batch** out) {
+  if (!m || !offsets || !params || !out) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  int status = ANL_OK;
+  DeviceBatch* b = m->engine.create_batch(blob ? blob : "", offsets, n_queries, *params, &err, &status);
+  if (!b) return fail(status ? status : ANL_ERR_CUDA, err);
+  *out = new anl_device_batch{b};
+  return ANL_OK;
+}
+anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream) {
+  if (!m || !b) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.run_batch(b->b, reinterpret_cast<cudaStream_t>(stream), &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms) {
+  if (!m || !b || !probe_ms || !score_ms) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.timings(b->b, probe_ms, score_ms, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) {
+  if (!m || !b || !out) return fail(ANL_ERR_INVALID, "null argument");
+  anl_result_set* rs = new anl_result_set();
+  std::string err;
+  int status = ANL_OK;
+  if (!m->engine.fetch_batch(b->b, &rs->rs, &err, &status)) {
+    delete rs;
+    return fail(status ? status : ANL_ERR_CUDA, err);
+  }
+  *out = rs;
+  return ANL_OK;
+}
+void anl_device_batch_free(anl_model* m, anl_device_batch* b) {
+  if (!b) return;
+  if (m) m->engine.free_batch(b->b);
+  delete b;
+}
+anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out) {
+  if (!m || !b || !out) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.counters(b->b, out, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) {
+  if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "model has not been built");
+  const HostIndex& ix = m->host.index;
+  memset(out, 0, sizeof *out);
+  out->table_slots = ix.table.size();
+  out->slot_bytes = sizeof(Slot);
+  out->table_bytes = ix.table.size() * sizeof(Slot);
+  out->table_keys = ix.table_keys;
+  out->bloom_bytes = ix.bloom.size() * sizeof(uint64_t);
+  out->postings = ix.post_ana.size();
+  out->anagrams = ix.ana_key.size();
+  out->instances = ix.inst_vocab.size();
+  out->instance_bytes = ix.inst_rows.size();
+  out->norm_stride = ix.norm_stride;
+  out->mset_entries = ix.mset.size();
+  out->mset_bytes = ix.mset.size() * sizeof(MsetEntry);
+  out->max_key_bits = ix.max_key_bits;
+  out->max_charcount = ix.max_charcount;
+  out->active_classes = (uint32_t)ix.active_classes.size();
+  out->sd = (uint32_t)ix.sd;
+  return ANL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// device_types.h -- data layout shared by the host index builder and the CUDA kernels.
+//
+// Everything the kernels read is laid out here (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#endif
+#ifndef __device__
+#define __device__
+#endif
+#ifndef __forceinline__
+#define __forceinline__ inline
+#endif
+#endif
+
+namespace anl {
+
+// ---- anagram keys -----------------------------------------------------------------------------
+// The reference's AnaValue is an unbounded UBig (src/types.rs:33).  On the device a key is a
+// fixed-width 192-bit little-endian integer (three 64-bit limbs).  The host builder rejects a
+// lexicon whose largest key needs more than 192 bits (nld needs 166, eng 102).  Query-side keys
+// that overflow 192 bits cannot equal any indexed key and are skipped (exact).
+struct Key192 {
+  uint64_t w0, w1, w2;
+};
+
+// 64-bit mix of a 192-bit key; the same function builds the tables on the host.
+__host__ __device__ __forceinline__ uint64_t hash_key(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t h = a * 0x9E3779B97F4A7C15ULL;
+  h ^= (b + 0x7F4A7C159E3779B9ULL) * 0xC2B2AE3D27D4EB4FULL;
+  h ^= (c + 0x165667B19E3779F9ULL) * 0xD6E8FEB86659FD93ULL;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ULL;
+  h ^= h >> 29;
+  return h;
+}
+
+// ---- the neighbour table ("symmetric delete, depth sd") -------------------------------------------
+// Replaces both `index` (HashMap<AnaValue, AnaIndexNode>, src/index.rs:5) and the linear scan of
+// `sortedindex[charcount]` (src/lib.rs:1268-1281).  Keys X of the table are
+//     sd = 0:  every indexed anagram C                       (posting: C itself, cls = POST_SELF)
+//     sd = 1:  additionally C / p_x for every class x in C   (posting: C, cls = x)
+// A slot stores the 64-bit hash of X as a fingerprint, not X: every posting is verified exactly
+// on the device (X * p_x == key(C)), so fingerprint collisions only cost a wasted verification.
+struct __attribute__((aligned(16))) Slot {
+  uint64_t fp;        // hash_key(X)
+  uint32_t post_off;  // first posting
+  uint16_t post_cnt;  // number of postings; 0 = empty slot
+  uint16_t pad;
+};
+static const uint8_t POST_SELF = 0xFF;
+
+// Blocked Bloom filter in front of the table: one 64-bit word per key, BLOOM_BITS bits inside it.
+// A miss (the overwhelmingly common case) costs one 8-byte load.
+static const int BLOOM_BITS = 3;
+__host__ __device__ __forceinline__ uint64_t bloom_mask(uint64_t h) {
+  // bits taken from the top of the hash (the word index uses the low bits)
+  return (1ULL << ((h >> 58) & 63)) | (1ULL << ((h >> 52) & 63)) | (1ULL << ((h >> 46) & 63));
+}
+
+// ---- insertion multisets --------------------------------------------------------------------------
+// Entry t of the table is one multiset of j >= 1 inserted symbols drawn from the classes that
+// occur in the lexicon ("active classes"), ordered by j (all j=1 first, then j=2, ...), so the
+// multisets of size <= J are the prefix [0, mset_end[J]).
+struct __attribute__((aligned(16))) MsetEntry {
+  uint64_t prod;   // product of the primes of the inserted symbols (< 2^60 for j <= 6)
+  uint8_t cls[6];  // the symbols (prime indices), ascending, padded with 0xFF
+  uint8_t j;       // multiset size
+  uint8_t maxcls;  // largest symbol
+};
+
+static const int ANL_MAX_K = 6;          // largest supported max_anagram_distance after thresholding
+static const int ANL_MAX_SYMBOLS = 250;  // longest query / entry (symbols) the device path accepts
+
+// ---- per-model constant data ------------------------------------------------------------------------
+struct DeviceIndex {
+  const Slot* table;
+  uint64_t table_mask;  // slots - 1 (power of two)
+  const uint64_t* bloom;
+  uint64_t bloom_mask;  // words - 1 (power of two)
+  const uint32_t* post_ana;  // posting -> anagram rank
+  const uint8_t* post_cls;   // posting -> class x (or POST_SELF)
+  int32_t sd;                // symmetric-delete depth of the table (0 or 1)
+  // anagrams in ascending key order (rank = position): key, first gather id (n_anagrams + 1 entries)
+  const Key192* ana_key;
+  const uint32_t* ana_inst_off;
+  // instances in gather order: (anagram key ascending, vocab id ascending) == the order in which
+  // gather_instances (src/lib.rs:1327-1391) visits them, so "gather id ascending" reproduces the
+  // reference's stable-sort tie order.
+  const uint8_t* inst_rows;  // [instances][norm_stride]: byte0 = length, byte1 = flags, bytes 2.. = symbols
+  uint32_t norm_stride;      // multiple of 16
+  const uint32_t* inst_vocab;  // vocab id per gather id
+  const uint32_t* inst_freq;   // VocabValue.frequency per gather id
+  const MsetEntry* mset;
+  uint32_t mset_end[ANL_MAX_K + 1];  // mset_end[J] = number of entries with j <= J; [0] = 0
+  const uint32_t* binom;             // [256][8] saturating binomials C(n, k)
+  uint32_t prime_of[256];            // prime of a symbol (prime index), 0 if unused
+  uint64_t charcount_mask[4];        // bit cc set iff some anagram has that charcount (cc < 256)
+  uint32_t max_charcount;
+  uint32_t max_len;  // longest indexed entry in symbols
+  uint32_t n_anagrams;
+  uint32_t n_instances;
+  int32_t have_freq;
+};
+
+// row flags
+static const uint8_t ROW_FIRST_LOWER = 1;  // first char of the raw text is_lowercase (src/lib.rs:1367-1374)
+
+// ---- per-batch parameters --------------------------------------------------------------------------
+struct Threshold {
+  int32_t kind;  // 0 ratio, 1 ratio with limit, 2 absolute
+  float ratio;
+  uint32_t value;
+};
+
+struct BatchParams {
+  Threshold max_anagram, max_edit;
+  uint32_t max_matches;  // 0 = unlimited
+  double score_threshold, cutoff_threshold;
+  double w_ld, w_lcs, w_prefix, w_suffix, w_case, w_sum;
+  double freq_weight64;  // f32 freq_weight widened to f64 (src/types.rs:339)
+  int32_t freq_weight_nonzero, freq_weight_positive;
+  int32_t stop_at_exact;
+  int32_t finish_mode;    // FINISH_*
+  uint32_t hit_cap;       // per-query capacity of the hit list (gather ids)
+  uint32_t out_cap;       // per-query capacity of the result list
+  uint32_t query_stride;  // bytes per encoded query row (multiple of 16): len, flags, symbols
+};
+static const int FINISH_FULL = 0;       // rank, crop, cutoff on device (no confusables)
+static const int FINISH_CROP = 1;       // rank + crop on device; late confusables + cutoff follow on the host
+static const int FINISH_GATHER = 2;     // emit all survivors in gather order (early confusables on the host)
+
+// query flags
+static const uint8_t Q_FIRST_LOWER = 1;
+
+// result record written by the score/rank kernel
+struct __attribute__((aligned(8))) OutRec {
+  double dist_score;
+  double freq_score;
+  uint32_t vocab_id;
+  uint32_t gather_id;
+};
+
+// per-query status bits
+static const uint32_t QF_EMPTY = 1;         // empty query
+static const uint32_t QF_HIT_OVERFLOW = 2;  // more instance hits than hit_cap: rerun with larger cap
+static const uint32_t QF_OUT_OVERFLOW = 4;  // more results than out_cap: rerun with larger cap
+static const uint32_t QF_UNSUPPORTED = 8;   // thresholded anagram distance > ANL_MAX_K or enumeration too large
+
+struct Counters {
+  unsigned long long deletion_keys, probes, filter_pass, table_steps, postings, anagram_hits, instance_pairs, dl_pairs,
+      dl_cells, survivors, results;
+};
+
+}  // namespace anl

@@ -1,0 +1,585 @@
+// host_model.cpp -- alphabet, vocabulary and the index builder (host side of build()).
+#include "host_model.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "unicode_tables.h"
+
+namespace anl {
+
+const uint32_t kPrimes[168] = {
+    2,   3,   5,   7,   11,  13,  17,  19,  23,  29,  31,  37,  41,  43,  47,  53,  59,  61,  67,
+    71,  73,  79,  83,  89,  97,  101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163,
+    167, 173, 179, 181, 191, 193, 197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269,
+    271, 277, 281, 283, 293, 307, 311, 313, 317, 331, 337, 347, 349, 353, 359, 367, 373, 379, 383,
+    389, 397, 401, 409, 419, 421, 431, 433, 439, 443, 449, 457, 461, 463, 467, 479, 487, 491, 499,
+    503, 509, 521, 523, 541, 547, 557, 563, 569, 571, 577, 587, 593, 599, 601, 607, 613, 617, 619,
+    631, 641, 643, 647, 653, 659, 661, 673, 677, 683, 691, 701, 709, 719, 727, 733, 739, 743, 751,
+    757, 761, 769, 773, 787, 797, 809, 811, 821, 823, 827, 829, 839, 853, 857, 859, 863, 877, 881,
+    883, 887, 907, 911, 919, 929, 937, 941, 947, 953, 967, 971, 977, 983, 991, 997};
+
+// ---- UTF-8 ----------------------------------------------------------------------------------------
+static inline unsigned u8len(unsigned char c) {
+  if (c < 0x80) return 1;
+  if ((c & 0xE0) == 0xC0) return 2;
+  if ((c & 0xF0) == 0xE0) return 3;
+  if ((c & 0xF8) == 0xF0) return 4;
+  return 1;
+}
+static inline uint32_t u8decode(const char* s, size_t avail, unsigned* len) {
+  unsigned char c = (unsigned char)s[0];
+  unsigned l = u8len(c);
+  if (l > avail) l = (unsigned)avail;
+  *len = l;
+  if (l == 1) return c;
+  uint32_t cp = c & (0xFFu >> (l + 1));
+  for (unsigned i = 1; i < l; ++i) cp = (cp << 6) | ((unsigned char)s[i] & 0x3F);
+  return cp;
+}
+static bool is_unicode_space(uint32_t c) {
+  return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+         c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+static std::string trim_unicode(const std::string& s) {
+  size_t a = 0, b = s.size();
+  while (a < b) {
+    unsigned l;
+    uint32_t cp = u8decode(s.data() + a, b - a, &l);
+    if (!is_unicode_space(cp)) break;
+    a += l;
+  }
+  while (b > a) {
+    size_t p = b - 1;
+    while (p > a && ((unsigned char)s[p] & 0xC0) == 0x80) --p;
+    unsigned l;
+    uint32_t cp = u8decode(s.data() + p, b - p, &l);
+    if (!is_unicode_space(cp)) break;
+    b = p;
+  }
+  return s.substr(a, b - a);
+}
+
+// ---- Alphabet -------------------------------------------------------------------------------------
+void Alphabet::load_tsv(const std::string& text) {
+  size_t pos = 0;
+  while (pos < text.size()) {
+    size_t nl = text.find('\n', pos);
+    size_t end = nl == std::string::npos ? text.size() : nl;
+    std::string line = text.substr(pos, end - pos);
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (!line.empty()) {
+      std::vector<std::string> fields;
+      size_t fp = 0;
+      for (;;) {
+        size_t tab = line.find('\t', fp);
+        std::string f = line.substr(fp, tab == std::string::npos ? std::string::npos : tab - fp);
+        if (f == "\\s")
+          fields.push_back(" ");
+        else if (f == "\\t")
+          fields.push_back("\t");
+        else if (f == "\\n")
+          fields.push_back("\n");
+        else {
+          std::string t = trim_unicode(f);
+          if (!t.empty()) fields.push_back(t);
+        }
+        if (tab == std::string::npos) break;
+        fp = tab + 1;
+      }
+      lines_.push_back(fields);  // kept even when it has no members, like the reference
+    }
+    pos = end + 1;
+  }
+  finalize();
+}
+
+void Alphabet::finalize() {
+  for (auto& v : by_first_) v.clear();
+  for (uint32_t seqnr = 0; seqnr < lines_.size(); ++seqnr)
+    for (const std::string& m : lines_[seqnr])
+      if (!m.empty()) by_first_[(unsigned char)m[0]].push_back(Member{seqnr, m});
+}
+
+size_t Alphabet::encode_into(const char* s, size_t n, uint8_t* out, size_t cap) const {
+  size_t count = 0, i = 0;
+  const uint32_t unk = unk_symbol();
+  while (i < n) {
+    const std::vector<Member>& cands = by_first_[(unsigned char)s[i]];
+    const Member* hit = nullptr;
+    for (const Member& m : cands) {
+      if (i + m.bytes.size() <= n && memcmp(s + i, m.bytes.data(), m.bytes.size()) == 0) {
+        hit = &m;
+        break;
+      }
+    }
+    if (hit) {
+      if (count < cap) out[count] = (uint8_t)hit->seqnr;
+      i += hit->bytes.size();
+    } else {
+      if (count < cap) out[count] = (uint8_t)unk;
+      i += u8len((unsigned char)s[i]);
+    }
+    ++count;
+  }
+  return count;
+}
+
+void Alphabet::encode(const char* s, size_t n, std::vector<uint8_t>* out) const {
+  uint8_t buf[512];
+  size_t c = encode_into(s, n, buf, sizeof buf);
+  if (c <= sizeof buf) {
+    out->assign(buf, buf + c);
+  } else {
+    out->resize(c);
+    encode_into(s, n, out->data(), c);
+  }
+}
+
+// ---- HostModel: vocabulary -------------------------------------------------------------------------
+void HostModel::init_vocab() {
+  const char* names[3] = {"<bos>", "<eos>", "<unk>"};
+  for (int i = 0; i < 3; ++i) {
+    VocabEntry e;
+    e.text = names[i];
+    e.frequency = 0;
+    e.tokencount = 1;
+    e.vocabtype = VT_NONE;
+    decoder.push_back(e);
+    encoder[names[i]] = (uint64_t)i;
+  }
+}
+
+bool HostModel::read_alphabet_file(const std::string& filename, std::string* err) {
+  std::ifstream f(filename, std::ios::binary);
+  if (!f) {
+    *err = "cannot open alphabet file " + filename;
+    return false;
+  }
+  std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  alphabet.load_tsv(text);
+  return true;
+}
+
+uint64_t HostModel::add_to_vocabulary(const char* text, size_t len, bool has_freq, uint32_t freq, const VocabParams& p) {
+  const uint32_t frequency = has_freq ? freq : 1;
+  std::string key(text, len);
+  auto it = encoder.find(key);
+  if (it != encoder.end()) {
+    VocabEntry& item = decoder[it->second];
+    switch (p.freq_handling) {
+      case FH_SUM: item.frequency += frequency; break;
+      case FH_MAX: if (frequency > item.frequency) item.frequency = frequency; break;
+      case FH_MIN: if (frequency < item.frequency) item.frequency = frequency; break;
+      default: item.frequency = frequency; break;
+    }
+    if (it->second <= 2)
+      item.vocabtype = VT_LM;
+    else if ((item.vocabtype & VT_TRANSPARENT) && !(p.vocab_type & VT_TRANSPARENT))
+      item.vocabtype ^= VT_TRANSPARENT;
+    item.lexindex |= 1u << (p.index & 31);
+    return it->second;
+  }
+  const uint64_t id = decoder.size();
+  VocabEntry e;
+  e.text = key;
+  alphabet.encode(text, len, &e.syms);
+  e.frequency = frequency;
+  e.tokencount = (uint8_t)(std::count(key.begin(), key.end(), ' ') + 1);
+  e.lexindex = 1u << (p.index & 31);
+  e.vocabtype = (uint8_t)p.vocab_type;
+  if (len > 0) {
+    unsigned l;
+    e.first_lower = anl_unicode::is_lowercase(u8decode(text, len, &l));
+  }
+  encoder.emplace(std::move(key), id);
+  decoder.push_back(std::move(e));
+  built = false;
+  return id;
+}
+
+static bool parse_u32(const std::string& s, uint32_t* out) {  // str::parse::<u32>()
+  size_t i = 0;
+  if (i < s.size() && s[i] == '+') ++i;
+  if (i >= s.size()) return false;
+  uint64_t v = 0;
+  for (; i < s.size(); ++i) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (uint64_t)(s[i] - '0');
+    if (v > 0xFFFFFFFFull) return false;
+  }
+  *out = (uint32_t)v;
+  return true;
+}
+
+bool HostModel::read_vocabulary(const std::string& filename, const VocabParams& params, std::string* err) {
+  std::ifstream f(filename, std::ios::binary);
+  if (!f) {
+    *err = "cannot open vocabulary file " + filename;
+    return false;
+  }
+  VocabParams p = params;
+  p.index = (uint32_t)(lexicons.size() & 0xFF);
+  std::string line;
+  size_t linenr = 0;
+  std::vector<std::pair<size_t, size_t>> fields;
+  while (std::getline(f, line)) {
+    ++linenr;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    fields.clear();
+    size_t fp = 0;
+    for (;;) {
+      size_t tab = line.find('\t', fp);
+      size_t end = tab == std::string::npos ? line.size() : tab;
+      fields.emplace_back(fp, end - fp);
+      if (tab == std::string::npos) break;
+      fp = tab + 1;
+    }
+    if (p.text_column >= fields.size()) {
+      *err = filename + ":" + std::to_string(linenr) + ": expected text column not found";
+      return false;
+    }
+    uint32_t frequency = 1;
+    if (p.freq_column >= 0) {
+      if (p.vocab_type & VT_INDEXED) have_freq = true;
+      if ((size_t)p.freq_column < fields.size()) {
+        std::string fs = line.substr(fields[p.freq_column].first, fields[p.freq_column].second);
+        if (!parse_u32(fs, &frequency)) {
+          *err = filename + ":" + std::to_string(linenr) + ": frequency should be a valid integer";
+          return false;
+        }
+      }
+    }
+    add_to_vocabulary(line.data() + fields[p.text_column].first, fields[p.text_column].second, true, frequency, p);
+  }
+  lexicons.push_back(filename);
+  return true;
+}
+
+bool HostModel::add_to_confusables(const std::string& editscript, double weight, std::string* err) {
+  Confusable c;
+  if (!parse_confusable(editscript, weight, &c)) {
+    *err = "invalid confusable edit script: " + editscript;
+    return false;
+  }
+  confusables.push_back(c);
+  return true;
+}
+
+bool HostModel::read_confusablelist(const std::string& filename, std::string* err) {  // src/lib.rs:414-441
+  std::ifstream f(filename, std::ios::binary);
+  if (!f) {
+    *err = "cannot open confusable list " + filename;
+    return false;
+  }
+  std::string line;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    size_t tab = line.find('\t');
+    double weight = 1.0;
+    std::string script = line.substr(0, tab);
+    if (tab != std::string::npos) {
+      size_t tab2 = line.find('\t', tab + 1);
+      std::string ws = line.substr(tab + 1, tab2 == std::string::npos ? std::string::npos : tab2 - tab - 1);
+      char* end = nullptr;
+      weight = strtod(ws.c_str(), &end);
+      if (ws.empty() || *end != '\0') {
+        *err = "confusable score should be a float: " + ws;
+        return false;
+      }
+    }
+    if (!add_to_confusables(script, weight, err)) return false;
+  }
+  return true;
+}
+
+// ---- keys ----------------------------------------------------------------------------------------------
+static inline bool key_mul(Key192& k, uint64_t m) {
+  unsigned __int128 t0 = (unsigned __int128)k.w0 * m;
+  unsigned __int128 t1 = (unsigned __int128)k.w1 * m + (uint64_t)(t0 >> 64);
+  unsigned __int128 t2 = (unsigned __int128)k.w2 * m + (uint64_t)(t1 >> 64);
+  k.w0 = (uint64_t)t0;
+  k.w1 = (uint64_t)t1;
+  k.w2 = (uint64_t)t2;
+  return (uint64_t)(t2 >> 64) == 0;
+}
+static inline Key192 key_div_exact(const Key192& k, uint64_t m) {
+  Key192 q;
+  unsigned __int128 r = k.w2;
+  q.w2 = (uint64_t)(r / m);
+  r = ((r % m) << 64) | k.w1;
+  q.w1 = (uint64_t)(r / m);
+  r = ((r % m) << 64) | k.w0;
+  q.w0 = (uint64_t)(r / m);
+  return q;
+}
+static inline bool key_less(const Key192& a, const Key192& b) {
+  if (a.w2 != b.w2) return a.w2 < b.w2;
+  if (a.w1 != b.w1) return a.w1 < b.w1;
+  return a.w0 < b.w0;
+}
+static inline bool key_eq(const Key192& a, const Key192& b) { return a.w0 == b.w0 && a.w1 == b.w1 && a.w2 == b.w2; }
+static inline unsigned key_bits(const Key192& k) {
+  if (k.w2) return 128 + 64 - __builtin_clzll(k.w2);
+  if (k.w1) return 64 + 64 - __builtin_clzll(k.w1);
+  if (k.w0) return 64 - __builtin_clzll(k.w0);
+  return 0;
+}
+
+bool HostModel::key_of(const uint8_t* syms, size_t n, Key192* out) const {
+  Key192 k{1, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    if (syms[i] >= 168) return false;
+    if (!key_mul(k, kPrimes[syms[i]])) return false;
+  }
+  *out = k;
+  return true;
+}
+
+std::vector<uint64_t> HostModel::anahash_limbs(const char* text, size_t len) const {
+  std::vector<uint8_t> syms;
+  alphabet.encode(text, len, &syms);
+  std::vector<uint64_t> v{1};
+  for (uint8_t s : syms) {
+    uint64_t m = kPrimes[s < 168 ? s : 167], carry = 0;
+    for (auto& limb : v) {
+      unsigned __int128 t = (unsigned __int128)limb * m + carry;
+      limb = (uint64_t)t;
+      carry = (uint64_t)(t >> 64);
+    }
+    if (carry) v.push_back(carry);
+  }
+  return v;
+}
+
+// ---- index build (src/lib.rs:192-245) ----------------------------------------------------------------------
+bool HostModel::build_index(int sd, std::string* err) {
+  HostIndex ix;
+  ix.sd = sd;
+  if (alphabet.size() + 1 > 168) {
+    *err = "alphabet has more classes than there are primes (168)";
+    return false;
+  }
+  for (uint32_t s = 0; s <= alphabet.size(); ++s) ix.prime_of[s] = kPrimes[s];
+
+  struct Item {
+    Key192 key;
+    uint32_t id;
+  };
+  std::vector<Item> items;
+  items.reserve(decoder.size());
+  bool class_seen[256] = {false};
+  for (size_t id = 0; id < decoder.size(); ++id) {
+    const VocabEntry& v = decoder[id];
+    if (!(v.vocabtype & VT_INDEXED)) continue;
+    if (v.syms.empty()) {
+      // reference: anahash of "" is 1 and the entry is indexed under it; it can never be returned
+      // (deletions never reach the empty value, src/iterators.rs:177) except as an exact match of an
+      // empty query, which the reference rejects (src/lib.rs:1420).  Not indexed here.
+      continue;
+    }
+    if (v.syms.size() > (size_t)ANL_MAX_SYMBOLS) {
+      *err = "lexicon entry longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols: " + v.text;
+      return false;
+    }
+    Item it;
+    if (!key_of(v.syms.data(), v.syms.size(), &it.key)) {
+      *err = "anagram value of lexicon entry exceeds 192 bits: " + v.text;
+      return false;
+    }
+    it.id = (uint32_t)id;
+    items.push_back(it);
+    for (uint8_t s : v.syms) class_seen[s] = true;
+    ix.max_len = std::max<uint32_t>(ix.max_len, (uint32_t)v.syms.size());
+    ix.max_key_bits = std::max(ix.max_key_bits, key_bits(it.key));
+  }
+  if (items.empty()) {
+    *err = "no indexed vocabulary entries";
+    return false;
+  }
+  if (decoder.size() > 0xFFFFFFF0ull) {
+    *err = "vocabulary too large";
+    return false;
+  }
+  // instances in (key ascending, vocab id ascending) order = the reference's gather order
+  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+    if (!key_eq(a.key, b.key)) return key_less(a.key, b.key);
+    return a.id < b.id;
+  });
+  ix.norm_stride = ((ix.max_len + 2) + 15) & ~15u;
+  ix.inst_rows.assign((size_t)items.size() * ix.norm_stride, 0);
+  ix.inst_vocab.resize(items.size());
+  ix.inst_freq.resize(items.size());
+  for (size_t g = 0; g < items.size(); ++g) {
+    const VocabEntry& v = decoder[items[g].id];
+    if (g == 0 || !key_eq(items[g].key, items[g - 1].key)) {
+      ix.ana_key.push_back(items[g].key);
+      ix.ana_inst_off.push_back((uint32_t)g);
+      ix.ana_charcount.push_back((uint16_t)v.syms.size());
+      const uint32_t cc = (uint32_t)v.syms.size();
+      ix.charcount_mask[cc >> 6] |= 1ull << (cc & 63);
+      ix.max_charcount = std::max(ix.max_charcount, cc);
+    }
+    uint8_t* row = ix.inst_rows.data() + g * ix.norm_stride;
+    row[0] = (uint8_t)v.syms.size();
+    row[1] = v.first_lower ? ROW_FIRST_LOWER : 0;
+    memcpy(row + 2, v.syms.data(), v.syms.size());
+    ix.inst_vocab[g] = items[g].id;
+    ix.inst_freq[g] = v.frequency;
+  }
+  ix.ana_inst_off.push_back((uint32_t)items.size());
+  for (uint32_t s = 0; s < 256; ++s)
+    if (class_seen[s]) ix.active_classes.push_back((uint8_t)s);
+
+  // neighbour table: self postings, plus (sd = 1) one posting per distinct class of every anagram
+  struct Post {
+    uint64_t fp;
+    uint32_t ana;
+    uint8_t cls;
+  };
+  std::vector<Post> posts;
+  posts.reserve(ix.ana_key.size() * (sd ? 10 : 1));
+  for (uint32_t r = 0; r < ix.ana_key.size(); ++r) {
+    const Key192& k = ix.ana_key[r];
+    posts.push_back(Post{hash_key(k.w0, k.w1, k.w2), r, POST_SELF});
+    if (sd >= 1) {
+      // distinct classes of this anagram from its first instance's symbols
+      const uint8_t* row = ix.inst_rows.data() + (size_t)ix.ana_inst_off[r] * ix.norm_stride;
+      bool seen[256] = {false};
+      for (uint32_t i = 0; i < row[0]; ++i) {
+        uint8_t x = row[2 + i];
+        if (seen[x]) continue;
+        seen[x] = true;
+        if (row[0] == 1) continue;  // the empty value is never a node (no empty leaves, src/iterators.rs:177)
+        Key192 xk = key_div_exact(k, kPrimes[x]);
+        posts.push_back(Post{hash_key(xk.w0, xk.w1, xk.w2), r, x});
+      }
+    }
+  }
+  std::sort(posts.begin(), posts.end(), [](const Post& a, const Post& b) {
+    if (a.fp != b.fp) return a.fp < b.fp;
+    if (a.ana != b.ana) return a.ana < b.ana;
+    return a.cls < b.cls;
+  });
+  uint64_t groups = 0;
+  for (size_t i = 0; i < posts.size(); ++i)
+    if (i == 0 || posts[i].fp != posts[i - 1].fp) ++groups;
+  ix.table_keys = groups;
+  uint64_t slots = 1;
+  while (slots < groups * 2) slots <<= 1;
+  uint64_t words = 1;
+  while (words * 2 < groups) words <<= 1;  // 1..2 keys per 64-bit word, 3 bits each: false positives < 0.1 %
+  ix.table.assign(slots, Slot{0, 0, 0, 0});
+  ix.bloom.assign(words, 0);
+  ix.post_ana.resize(posts.size());
+  ix.post_cls.resize(posts.size());
+  for (size_t i = 0; i < posts.size();) {
+    size_t j = i;
+    while (j < posts.size() && posts[j].fp == posts[i].fp) ++j;
+    if (j - i > 0xFFFF) {
+      *err = "posting list too long";
+      return false;
+    }
+    const uint64_t fp = posts[i].fp;
+    uint64_t idx = fp & (slots - 1);
+    while (ix.table[idx].post_cnt != 0) idx = (idx + 1) & (slots - 1);
+    ix.table[idx] = Slot{fp, (uint32_t)i, (uint16_t)(j - i), 0};
+    ix.bloom[fp & (words - 1)] |= bloom_mask(fp);
+    for (size_t t = i; t < j; ++t) {
+      ix.post_ana[t] = posts[t].ana;
+      ix.post_cls[t] = posts[t].cls;
+    }
+    i = j;
+  }
+  index = std::move(ix);
+  built = true;
+  return true;
+}
+
+bool HostModel::ensure_msets(uint32_t J, std::string* err) {
+  if (J > (uint32_t)ANL_MAX_K) J = ANL_MAX_K;
+  if (index.mset_built_j >= J && !(J == 0)) return true;
+  if (J == 0) return true;
+  const std::vector<uint8_t>& cls = index.active_classes;
+  const size_t A = cls.size();
+  // count first: C(A + j - 1, j) multisets of size j
+  uint64_t total = 0;
+  for (uint32_t j = 1; j <= J; ++j) {
+    long double c = 1;
+    for (uint32_t i = 1; i <= j; ++i) c = c * (A + j - i) / i;
+    total += (uint64_t)(c + 0.5L);
+  }
+  if (total > (64ull << 20)) {
+    *err = "insertion neighbourhood too large for this alphabet and anagram distance (" + std::to_string(total) +
+           " multisets)";
+    return false;
+  }
+  std::vector<MsetEntry> out;
+  out.reserve(total);
+  uint32_t ends[ANL_MAX_K + 1] = {0};
+  for (uint32_t j = 1; j <= J; ++j) {
+    // non-decreasing index tuples of length j over [0, A)
+    std::vector<size_t> ids(j, 0);
+    for (;;) {
+      MsetEntry e;
+      e.prod = 1;
+      e.j = (uint8_t)j;
+      for (int t = 0; t < 6; ++t) e.cls[t] = 0xFF;
+      for (uint32_t t = 0; t < j; ++t) {
+        e.cls[t] = cls[ids[t]];
+        e.prod *= kPrimes[cls[ids[t]]];
+      }
+      e.maxcls = cls[ids[j - 1]];
+      out.push_back(e);
+      int t = (int)j - 1;
+      while (t >= 0 && ids[t] == A - 1) --t;
+      if (t < 0) break;
+      size_t v = ids[t] + 1;
+      for (uint32_t u = (uint32_t)t; u < j; ++u) ids[u] = v;
+    }
+    ends[j] = (uint32_t)out.size();
+  }
+  for (uint32_t j = J + 1; j <= (uint32_t)ANL_MAX_K; ++j) ends[j] = ends[J];
+  index.mset = std::move(out);
+  memcpy(index.mset_end, ends, sizeof ends);
+  index.mset_built_j = J;
+  return true;
+}
+
+// ---- host-side queries -------------------------------------------------------------------------------------------
+int64_t HostModel::vocab_id(const char* text, size_t len) const {
+  auto it = encoder.find(std::string(text, len));
+  return it == encoder.end() ? -1 : (int64_t)it->second;
+}
+
+bool HostModel::has(const char* text, size_t len) const {
+  if (!built) return false;
+  std::vector<uint8_t> syms;
+  alphabet.encode(text, len, &syms);
+  Key192 k;
+  if (!key_of(syms.data(), syms.size(), &k)) return false;
+  auto it = std::lower_bound(index.ana_key.begin(), index.ana_key.end(), k, key_less);
+  if (it == index.ana_key.end() || !key_eq(*it, k)) return false;
+  size_t r = it - index.ana_key.begin();
+  for (uint32_t g = index.ana_inst_off[r]; g < index.ana_inst_off[r + 1]; ++g) {
+    const std::string& t = decoder[index.inst_vocab[g]].text;
+    if (t.size() == len && memcmp(t.data(), text, len) == 0) return true;
+  }
+  return false;
+}
+
+double HostModel::compute_confusable_weight(const std::string& input, uint64_t candidate) const {
+  double weight = 1.0;
+  if (candidate >= decoder.size()) return weight;
+  std::vector<EditInstruction> script = shortest_edit_script(input, decoder[candidate].text);
+  for (const Confusable& c : confusables)
+    if (confusable_found_in(c, script)) weight *= c.weight;
+  return weight;
+}
+
+}  // namespace anl

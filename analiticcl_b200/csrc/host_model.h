@@ -1,0 +1,153 @@
+// host_model.h -- host-side model of the variant-lookup path: alphabet, vocabulary, confusables and
+// the builder that turns the lexicon into the device-resident index.
+//
+// Mirrors the public surface of the reference's VariantModel for this path (src/lib.rs:50-100,
+// 104-165, 192-245, 331-343, 369-452, 519-568, 900-967) -- same names, argument meaning and error
+// behaviour -- but none of its data structures: there is no HashMap<AnaValue,..> and no
+// sortedindex here, only flat arrays laid out for the GPU (device_types.h).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "device_types.h"
+
+namespace anl {
+
+struct Weights {
+  double ld = 0.5, lcs = 0.125, prefix = 0.125, suffix = 0.125, case_ = 0.125;  // src/types.rs:58-67
+  double sum() const { return ld + lcs + prefix + suffix + case_; }             // src/types.rs:69-73
+};
+
+enum : uint32_t { VT_NONE = 0, VT_INDEXED = 1, VT_LM = 2, VT_TRANSPARENT = 4 };
+enum : int32_t { FH_SUM = 0, FH_MAX = 1, FH_MIN = 2, FH_REPLACE = 3 };
+
+struct VocabParams {  // src/vocab.rs:108-131
+  uint32_t text_column = 0;
+  int32_t freq_column = 1;  // -1 = None
+  int32_t freq_handling = FH_MAX;
+  uint32_t vocab_type = VT_INDEXED;
+  uint32_t index = 0;
+};
+
+struct VocabEntry {  // src/vocab.rs:7-29
+  std::string text;
+  std::vector<uint8_t> syms;  // normalised form in prime-index space (UNK = alphabet length)
+  uint32_t frequency = 1;
+  uint32_t lexindex = 0;
+  uint8_t tokencount = 1;
+  uint8_t vocabtype = VT_NONE;
+  bool first_lower = false;  // char::is_lowercase of the first char (src/lib.rs:1367-1374)
+};
+
+// Greedy alphabet matcher (src/anahash.rs:16-80) with a first-byte dispatch table instead of
+// the reference's nested scan over all alphabet lines at every position.
+class Alphabet {
+ public:
+  void load_tsv(const std::string& text);  // src/lib.rs:369-407
+  size_t size() const { return lines_.size(); }
+  uint32_t unk_symbol() const { return (uint32_t)lines_.size(); }  // prime index of UNK (src/anahash.rs:42)
+  // Appends one symbol (prime index) per matched alphabet member / unknown char.
+  void encode(const char* s, size_t n, std::vector<uint8_t>* out) const;
+  // Encode into a fixed buffer; returns the number of symbols (may exceed cap; extra symbols dropped).
+  size_t encode_into(const char* s, size_t n, uint8_t* out, size_t cap) const;
+  const std::vector<std::vector<std::string>>& lines() const { return lines_; }
+
+ private:
+  struct Member {
+    uint32_t seqnr;
+    std::string bytes;
+  };
+  void finalize();
+  std::vector<std::vector<std::string>> lines_;
+  std::vector<Member> by_first_[256];  // members starting with this byte, in (line, member) priority order
+};
+
+struct ConfusableInstr {
+  int op;  // -1 deletion, 0 identity, +1 insertion
+  std::vector<std::string> options;
+};
+struct Confusable {  // src/confusables.rs:5-11
+  std::vector<ConfusableInstr> script;
+  double weight = 1.0;
+  bool strictbegin = false, strictend = false;
+};
+
+// Host copy of the built index (used for has(), statistics and to size device buffers).
+struct HostIndex {
+  std::vector<Key192> ana_key;         // ascending
+  std::vector<uint32_t> ana_inst_off;  // n_anagrams + 1
+  std::vector<uint16_t> ana_charcount;
+  std::vector<uint32_t> inst_vocab;  // gather order
+  std::vector<uint32_t> inst_freq;
+  std::vector<uint8_t> inst_rows;
+  uint32_t norm_stride = 0;
+  std::vector<Slot> table;
+  std::vector<uint64_t> bloom;
+  std::vector<uint32_t> post_ana;
+  std::vector<uint8_t> post_cls;
+  std::vector<uint8_t> active_classes;  // symbols that occur in indexed entries, ascending
+  std::vector<MsetEntry> mset;
+  uint32_t mset_end[ANL_MAX_K + 1] = {0};
+  uint32_t mset_built_j = 0;
+  uint32_t prime_of[256] = {0};
+  uint64_t charcount_mask[4] = {0, 0, 0, 0};
+  uint32_t max_charcount = 0, max_len = 0, max_key_bits = 0;
+  uint64_t table_keys = 0;
+  int sd = 1;
+};
+
+class HostModel {
+ public:
+  HostModel(const Weights& w, int debug) : weights(w), debug(debug) {}
+  // -- construction (mirrors VariantModel) -----------------------------------------------------
+  void init_vocab();  // src/vocab.rs:150-181
+  bool read_alphabet_file(const std::string& filename, std::string* err);
+  void read_alphabet_text(const std::string& tsv) { alphabet.load_tsv(tsv); }
+  bool read_vocabulary(const std::string& filename, const VocabParams& p, std::string* err);
+  uint64_t add_to_vocabulary(const char* text, size_t len, bool has_freq, uint32_t freq, const VocabParams& p);
+  bool add_to_confusables(const std::string& editscript, double weight, std::string* err);
+  bool read_confusablelist(const std::string& filename, std::string* err);
+  // src/lib.rs:192-245: anagram values, grouping, ordering -> flat arrays (host side of build())
+  bool build_index(int sd, std::string* err);
+  // builds the insertion-multiset table up to size J (idempotent)
+  bool ensure_msets(uint32_t J, std::string* err);
+
+  // -- queries against the host copy ---------------------------------------------------------------
+  bool has(const char* text, size_t len) const;  // src/lib.rs:331-338
+  int64_t vocab_id(const char* text, size_t len) const;
+  // anahash as arbitrary-precision little-endian limbs (src/anahash.rs:16-47)
+  std::vector<uint64_t> anahash_limbs(const char* text, size_t len) const;
+  bool key_of(const uint8_t* syms, size_t n, Key192* out) const;  // false on 192-bit overflow
+  uint32_t alphabet_size() const { return (uint32_t)((alphabet.size() + 1) & 0xFF); }  // src/lib.rs:163-165
+
+  // -- host post-pass ---------------------------------------------------------------------------------
+  double compute_confusable_weight(const std::string& input, uint64_t candidate) const;  // src/lib.rs:1733-1756
+
+  Weights weights;
+  int debug;
+  Alphabet alphabet;
+  std::vector<VocabEntry> decoder;
+  std::unordered_map<std::string, uint64_t> encoder;
+  std::vector<std::string> lexicons;
+  bool have_freq = false;
+  std::vector<Confusable> confusables;
+  bool confusables_before_pruning = false;
+  bool built = false;
+  HostIndex index;
+};
+
+// sesdiff::shortest_edit_script(src, dst, false, false, false) -- see editscript.cpp
+struct EditInstruction {
+  int op;  // -1 deletion, 0 identity, +1 insertion
+  std::string text;
+};
+std::vector<EditInstruction> shortest_edit_script(const std::string& src, const std::string& dst);
+bool parse_confusable(const std::string& editscript, double weight, Confusable* out);
+bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& script);  // src/confusables.rs:47-128
+
+extern const uint32_t kPrimes[168];  // src/types.rs:20-30
+
+}  // namespace anl

@@ -1,0 +1,868 @@
+// kernels.cu -- the two hand-written sm_100a kernels of the variant-lookup hot path.
+//
+//   probe_kernel : candidate generation.  Replaces find_nearest_anahashes (src/lib.rs:1143-1308):
+//                  BFS over deletions (src/iterators.rs:153-187) + linear scan of
+//                  sortedindex[charcount] with a bignum modulo per test (src/lib.rs:1268-1281).
+//   score_kernel : candidate scoring + ranking.  Replaces gather_instances (src/lib.rs:1311-1402),
+//                  damerau_levenshtein / longest_common_substring_length / common_prefix_length /
+//                  common_suffix_length (src/distance.rs:101-231) and score_and_rank
+//                  (src/lib.rs:1405-1653) up to and including crop and cut-off.
+//
+// One warp owns one query at a time (queries are independent, src/bin/analiticcl.rs:445-448);
+// warps pull queries from a global counter, so the grid is persistent: SMs x resident CTAs.
+// Integer / byte work only -- no tensor cores (see DESIGN.md for the rooflines).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace anl {
+
+#define FULL 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// DistanceThreshold -> absolute distance for an input of `len` symbols (src/lib.rs:982-1012).
+__device__ __forceinline__ uint32_t apply_threshold(const Threshold& t, uint32_t len) {
+  if (t.kind == 2) {
+    uint32_t h = len >> 1;  // floor(len as f64 / 2.0) as u8 (saturating)
+    if (h > 255u) h = 255u;
+    return min(t.value & 0xFFu, h);
+  }
+  float f = floorf(__fmul_rn((float)len, t.ratio));  // (len as f32 * x).floor() as u8 (saturating)
+  uint32_t v = (f != f || f <= 0.f) ? 0u : (f >= 255.f ? 255u : (uint32_t)f);
+  return min(v, t.kind == 0 ? 12u : (t.value & 0xFFu));
+}
+
+// k *= m over 192 bits; false if the product does not fit (then it cannot equal any indexed key).
+__device__ __forceinline__ bool mul192(uint64_t& w0, uint64_t& w1, uint64_t& w2, uint64_t m) {
+  uint64_t l0 = w0 * m, h0 = __umul64hi(w0, m);
+  uint64_t l1 = w1 * m, h1 = __umul64hi(w1, m);
+  uint64_t l2 = w2 * m, h2 = __umul64hi(w2, m);
+  uint64_t r1 = l1 + h0;
+  uint64_t c1 = r1 < l1;
+  uint64_t r2 = l2 + h1;
+  uint64_t c2 = r2 < l2;
+  r2 += c1;
+  c2 += (r2 < c1);
+  w0 = l0;
+  w1 = r1;
+  w2 = r2;
+  return (h2 + c2) == 0;
+}
+
+__device__ __forceinline__ bool ccbit(const uint64_t* mask, uint32_t cc) {
+  return cc < 256u && ((mask[cc >> 6] >> (cc & 63)) & 1ull);
+}
+
+// ================================================================================================
+// Kernel 1: candidate generation
+// ================================================================================================
+constexpr int K1_WARPS = 8;
+constexpr int DCH = 64;  // deletion entries per chunk
+constexpr int SQ = 64;   // staging queue capacity (filter positives waiting for the exact lookup)
+
+struct __align__(16) DEntry {  // one element of the deletion neighbourhood of the query
+  uint64_t w0, w1, w2;         // key(D)
+  uint8_t d;                   // number of deleted symbols
+  uint8_t del[6];              // the deleted symbols (ascending, may repeat)
+  uint8_t pad;
+};
+struct __align__(16) SEntry {  // a node X = D + I' that passed the Bloom filter
+  uint64_t w0, w1, w2;         // key(X)
+  uint8_t e;                   // index of D in the current chunk
+  uint8_t isz;                 // |I'|
+  uint8_t imax;                // largest symbol of I' (0 if empty)
+  uint8_t pad[5];
+};
+struct K1Warp {
+  DEntry dch[DCH];
+  SEntry sq[SQ];
+  uint8_t sorted[256];
+  uint32_t nhits;
+  uint32_t pad[3];
+};
+struct K1Shared {
+  DeviceIndex ix;  // block-local copy of the model constants (pointers, masks, small tables)
+  uint32_t binom[256 * 8];
+  K1Warp w[K1_WARPS];
+};
+
+struct K1Ctx {
+  const DeviceIndex* ix;
+  const Slot* table;
+  uint64_t table_mask;
+  const uint64_t* bloom;
+  uint64_t bloom_wmask;
+  uint32_t* hits_q;  // hit list of the current query
+  uint32_t hit_cap;
+  uint32_t L, ka;
+  int sd;
+  // lane-local work counters
+  uint32_t c_probes, c_pass, c_steps, c_postings, c_ana, c_inst;
+};
+
+// Exact lookup of the staged nodes: table slot by fingerprint, then every posting is verified
+// against the anagram's own key and against the canonical-generation rules (each indexed
+// anagram C is produced exactly once: from D = F meet C and the ascending insertion order).
+__device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t cnt) {
+  const uint32_t lane = lane_id();
+  for (uint32_t base = 0; base < cnt; base += 32) {
+    uint32_t i = base + lane;
+    if (i < cnt) {
+      const SEntry s = W.sq[i];
+      const DEntry& de = W.dch[s.e];
+      const uint64_t fp = hash_key(s.w0, s.w1, s.w2);
+      uint64_t idx = fp & c.table_mask;
+      for (;;) {
+        const Slot sl = c.table[idx];
+        ++c.c_steps;
+        if (sl.post_cnt == 0) break;
+        if (sl.fp == fp) {
+          const uint32_t budget_left = c.ka - de.d - s.isz;
+          for (uint32_t p = sl.post_off; p < sl.post_off + sl.post_cnt; ++p) {
+            const uint32_t r = c.ix->post_ana[p];
+            const uint32_t x = c.ix->post_cls[p];
+            ++c.c_postings;
+            uint64_t x0 = s.w0, x1 = s.w1, x2 = s.w2;
+            bool ok;
+            if (x == POST_SELF) {
+              ok = (c.sd == 0) || (s.isz == 0);
+            } else {
+              ok = budget_left >= 1 && (s.isz == 0 || x >= s.imax);
+              for (uint32_t t = 0; t < de.d; ++t) ok = ok && (de.del[t] != x);
+              ok = ok && mul192(x0, x1, x2, prime_of[x]);
+            }
+            if (!ok) continue;
+            const Key192 ck = c.ix->ana_key[r];
+            if (ck.w0 != x0 || ck.w1 != x1 || ck.w2 != x2) continue;  // fingerprint collision
+            const uint32_t io = c.ix->ana_inst_off[r], ie = c.ix->ana_inst_off[r + 1];
+            const uint32_t n = ie - io;
+            ++c.c_ana;
+            c.c_inst += n;
+            const uint32_t pos = atomicAdd(&W.nhits, n);
+            for (uint32_t t = 0; t < n; ++t)
+              if (pos + t < c.hit_cap) c.hits_q[pos + t] = io + t;
+          }
+          break;
+        }
+        idx = (idx + 1) & c.table_mask;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Bloom test of one node per lane; positives are compacted into the staging queue.
+__device__ __forceinline__ void test_and_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t& sqn, bool active,
+                                               uint64_t x0, uint64_t x1, uint64_t x2, uint32_t e, uint32_t isz,
+                                               uint32_t imax) {
+  bool pass = false;
+  if (active) {
+    const uint64_t h = hash_key(x0, x1, x2);
+    const uint64_t word = __ldg(c.bloom + (h & c.bloom_wmask));
+    const uint64_t m = bloom_mask(h);
+    pass = (word & m) == m;
+    ++c.c_probes;
+  }
+  const uint32_t ballot = __ballot_sync(FULL, pass);
+  if (ballot) {
+    if (pass) {
+      ++c.c_pass;
+      SEntry& s = W.sq[sqn + __popc(ballot & lanemask_lt())];
+      s.w0 = x0;
+      s.w1 = x1;
+      s.w2 = x2;
+      s.e = (uint8_t)e;
+      s.isz = (uint8_t)isz;
+      s.imax = (uint8_t)imax;
+    }
+    sqn += __popc(ballot);
+    __syncwarp();
+    if (sqn > SQ - 32) {
+      drain_stage(c, W, prime_of, sqn);
+      sqn = 0;
+    }
+  }
+}
+
+// All nodes of the current chunk of deletion entries.
+__device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t nD) {
+  const uint32_t lane = lane_id();
+  const DeviceIndex* ix = c.ix;
+  uint32_t sqn = 0;
+  // (a) the nodes X = D themselves, one per lane
+  for (uint32_t base = 0; base < nD; base += 32) {
+    const uint32_t e = base + lane;
+    bool active = e < nD;
+    uint64_t x0 = 0, x1 = 0, x2 = 0;
+    if (active) {
+      const DEntry& de = W.dch[e];
+      x0 = de.w0;
+      x1 = de.w1;
+      x2 = de.w2;
+      const uint32_t cx = c.L - de.d;
+      // useful iff C = D may exist, or (sd = 1) C = D + x may exist within the budget
+      active = ccbit(ix->charcount_mask, cx) || (c.sd == 1 && c.ka > de.d && ccbit(ix->charcount_mask, cx + 1));
+    }
+    test_and_stage(c, W, prime_of, sqn, active, x0, x1, x2, e, 0, 0);
+  }
+  // (b) the nodes X = D + I', |I'| >= 1, entry by entry; lanes stride over the multiset table
+  for (uint32_t e = 0; e < nD; ++e) {
+    const DEntry de = W.dch[e];  // warp-uniform broadcast
+    const int jmax = (int)c.ka - (int)de.d - c.sd;
+    for (int j = 1; j <= jmax; ++j) {
+      const uint32_t cx = c.L - de.d + j;
+      const bool useful = (c.sd == 0) ? ccbit(ix->charcount_mask, cx) : ccbit(ix->charcount_mask, cx + 1);
+      if (!useful) continue;
+      const uint32_t lo = ix->mset_end[j - 1], hi = ix->mset_end[j];
+      for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t t = base + lane;
+        bool active = t < hi;
+        uint64_t x0 = de.w0, x1 = de.w1, x2 = de.w2;
+        uint32_t imax = 0;
+        if (active) {
+          const MsetEntry me = ix->mset[t];
+          imax = me.maxcls;
+          // canonical generation: never re-insert a deleted class
+          for (int a = 0; a < j; ++a)
+            for (uint32_t b = 0; b < de.d; ++b) active = active && (me.cls[a] != de.del[b]);
+          active = active && mul192(x0, x1, x2, me.prod);
+        }
+        test_and_stage(c, W, prime_of, sqn, active, x0, x1, x2, e, (uint32_t)j, imax);
+      }
+    }
+  }
+  if (sqn) drain_stage(c, W, prime_of, sqn);
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32, 2)
+probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+             const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
+             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K1Shared& S = *reinterpret_cast<K1Shared*>(smem_raw);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ix);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&S.ix);
+    for (uint32_t i = threadIdx.x; i < sizeof(DeviceIndex) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x) S.binom[i] = ix->binom[i];
+  __syncthreads();
+
+  const uint32_t lane = lane_id();
+  K1Warp& W = S.w[threadIdx.x >> 5];
+  K1Ctx c;
+  c.ix = &S.ix;
+  c.table = ix->table;
+  c.table_mask = ix->table_mask;
+  c.bloom = ix->bloom;
+  c.bloom_wmask = ix->bloom_mask;
+  c.hit_cap = bp.hit_cap;
+  c.sd = ix->sd;
+  c.c_probes = c.c_pass = c.c_steps = c.c_postings = c.c_ana = c.c_inst = 0;
+  uint32_t c_dkeys = 0;
+  const uint32_t max_cc = ix->max_charcount;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t L = qrow[0];
+    c.hits_q = hits + (size_t)qi * bp.hit_cap;
+    uint32_t flags = 0;
+    if (lane == 0) W.nhits = 0;
+    __syncwarp();
+    if (L == 0) {
+      flags = QF_EMPTY;
+    } else {
+      const uint32_t ka = apply_threshold(bp.max_anagram, L);
+      c.L = L;
+      c.ka = ka;
+      if (ka > (uint32_t)ANL_MAX_K) {
+        flags = QF_UNSUPPORTED;
+      } else if (L <= max_cc + ka) {  // else every candidate would be longer than any indexed entry
+        // sort the query symbols (rank sort) so equal symbols are adjacent
+        for (uint32_t i = lane; i < L; i += 32) {
+          const uint8_t v = qrow[2 + i];
+          uint32_t r = 0;
+          for (uint32_t j = 0; j < L; ++j) {
+            const uint8_t u = qrow[2 + j];
+            r += (u < v) || (u == v && j < i);
+          }
+          W.sorted[r] = v;
+        }
+        __syncwarp();
+        bool done = false;
+        if (bp.stop_at_exact) {
+          // StopAtExactMatch (src/lib.rs:1164-1173): if the focus itself is indexed, it is the only result
+          uint64_t f0 = 1, f1 = 0, f2 = 0;
+          bool okf = true;
+          for (uint32_t i = 0; i < L; ++i) okf = okf && mul192(f0, f1, f2, S.ix.prime_of[W.sorted[i]]);
+          if (okf) {
+            if (lane == 0) {
+              W.dch[0].w0 = f0;
+              W.dch[0].w1 = f1;
+              W.dch[0].w2 = f2;
+              W.dch[0].d = 0;
+            }
+            __syncwarp();
+            const uint32_t ka_saved = c.ka;
+            c.ka = 0;  // only the self posting of X = F is acceptable
+            uint32_t sqn = 0;
+            test_and_stage(c, W, S.ix.prime_of, sqn, lane == 0, f0, f1, f2, 0, 0, 0);
+            if (sqn) drain_stage(c, W, S.ix.prime_of, sqn);
+            c.ka = ka_saved;
+            __syncwarp();
+            done = W.nhits > 0;
+          }
+        }
+        if (!done) {
+          // enumerate the deletion neighbourhood: all distinct non-empty sub-multisets of the
+          // query reachable by d <= ka deletions (src/iterators.rs:153-187 yields the same set)
+          const uint32_t dmax = min(ka, L - 1);
+          uint64_t total64 = 0;
+          for (uint32_t d = 0; d <= dmax; ++d) total64 += S.binom[L * 8 + d];
+          if (total64 > 0x7FFFFFFFull) {
+            flags = QF_UNSUPPORTED;
+          } else {
+            const uint32_t total = (uint32_t)total64;
+            uint32_t nD = 0;
+            for (uint32_t base = 0; base < total; base += 32) {
+              const uint32_t t = base + lane;
+              bool ok = t < total;
+              uint64_t k0 = 1, k1 = 0, k2 = 0;
+              uint32_t d = 0;
+              uint8_t pos[ANL_MAX_K];
+#pragma unroll
+              for (int i = 0; i < ANL_MAX_K; ++i) pos[i] = 0xFF;
+              if (ok) {
+                uint32_t rem = t;
+                while (rem >= S.binom[L * 8 + d]) {
+                  rem -= S.binom[L * 8 + d];
+                  ++d;
+                }
+                // combinadic unranking: positions pos[0] < pos[1] < ... < pos[d-1]
+                int cpos = (int)L;
+#pragma unroll
+                for (int i = ANL_MAX_K; i >= 1; --i) {
+                  if (i <= (int)d) {
+                    --cpos;
+                    while (S.binom[cpos * 8 + i] > rem) --cpos;
+                    pos[i - 1] = (uint8_t)cpos;
+                    rem -= S.binom[cpos * 8 + i];
+                  }
+                }
+                // canonical: inside a run of equal symbols only a leading part may be deleted
+#pragma unroll
+                for (int i = 0; i < ANL_MAX_K; ++i) {
+                  if (i < (int)d) {
+                    const uint32_t p = pos[i];
+                    if (p > 0 && W.sorted[p - 1] == W.sorted[p] && !(i > 0 && pos[i - 1] == p - 1)) ok = false;
+                  }
+                }
+                if (ok) {
+                  // key(D) = product of the primes of the remaining symbols
+                  uint64_t pp = 1;
+                  for (uint32_t p = 0; p < L && ok; ++p) {
+                    bool isdel = false;
+#pragma unroll
+                    for (int i = 0; i < ANL_MAX_K; ++i) isdel = isdel || (pos[i] == p);
+                    if (isdel) continue;
+                    pp *= S.ix.prime_of[W.sorted[p]];
+                    if (pp >> 53) {  // next factor (< 2^10) could overflow 64 bits: flush
+                      ok = mul192(k0, k1, k2, pp);
+                      pp = 1;
+                    }
+                  }
+                  if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+                }
+              }
+              const uint32_t ballot = __ballot_sync(FULL, ok);
+              if (ok) {
+                DEntry& de = W.dch[nD + __popc(ballot & lanemask_lt())];
+                de.w0 = k0;
+                de.w1 = k1;
+                de.w2 = k2;
+                de.d = (uint8_t)d;
+#pragma unroll
+                for (int i = 0; i < ANL_MAX_K; ++i) de.del[i] = (i < (int)d) ? W.sorted[pos[i] == 0xFF ? 0 : pos[i]] : 0xFF;
+              }
+              nD += __popc(ballot);
+              c_dkeys += ok ? 1u : 0u;
+              __syncwarp();
+              if (nD > DCH - 32 || base + 32 >= total) {
+                process_chunk(c, W, S.ix.prime_of, nD);
+                nD = 0;
+                __syncwarp();
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t n = W.nhits;
+      hit_count[qi] = n;
+      if (n > bp.hit_cap) flags |= QF_HIT_OVERFLOW;
+      qflags[qi] = flags;
+    }
+    __syncwarp();
+  }
+
+  // flush the work counters (one atomic per counter per warp)
+  if (counters) {
+    unsigned long long v[7] = {c_dkeys, c.c_probes, c.c_pass, c.c_steps, c.c_postings, c.c_ana, c.c_inst};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      unsigned long long x = v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+      v[k] = x;
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->deletion_keys, v[0]);
+      atomicAdd(&counters->probes, v[1]);
+      atomicAdd(&counters->filter_pass, v[2]);
+      atomicAdd(&counters->table_steps, v[3]);
+      atomicAdd(&counters->postings, v[4]);
+      atomicAdd(&counters->anagram_hits, v[5]);
+      atomicAdd(&counters->instance_pairs, v[6]);
+    }
+  }
+}
+
+// ================================================================================================
+// Kernel 2: scoring + ranking
+// ================================================================================================
+constexpr int K2_WARPS = 4;
+
+struct __align__(16) SurvRec {
+  double dist;    // distance score
+  double freq;    // absolute, then normalised frequency score
+  uint32_t g;     // gather id
+  uint32_t pad;
+};
+
+// shared memory of one warp (dynamic; sized by the longest indexed entry ML and the ring depth R)
+//   q[256]                         query symbols
+//   cell[(ML+1)][32] (uint32)      per column j, per lane: {t[j-1], lcs[j], lastrow[j], unused}
+//   ring[R][(ML+1)][32] (uint8)    the last R rows of the DL matrix, per lane
+__host__ __device__ inline size_t k2_warp_bytes(uint32_t ML, uint32_t R) {
+  return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32;
+}
+
+__device__ __forceinline__ double result_score(const BatchParams& bp, double dist, double freq) {
+  // VariantResult::score (src/types.rs:335-341), evaluated without FMA contraction
+  if (!bp.freq_weight_nonzero) return dist;
+  return __ddiv_rn(__dadd_rn(dist, __dmul_rn(bp.freq_weight64, freq)), __dadd_rn(1.0, bp.freq_weight64));
+}
+// rank_cmp (src/types.rs:344-365) with the gather id as the final key (== stable sort of the
+// reference's gather order)
+__device__ __forceinline__ bool ranks_before(const BatchParams& bp, double da, double fa, uint32_t ga, double db, double fb,
+                                             uint32_t gb) {
+  if (bp.finish_mode == FINISH_GATHER) return ga < gb;
+  if (bp.freq_weight_positive) {
+    const double sa = result_score(bp, da, fa), sb = result_score(bp, db, fb);
+    if (sa != sb) return sa > sb;
+    return ga < gb;
+  }
+  if (da != db) return da > db;
+  if (fa != fb) return fa > fb;
+  return ga < gb;
+}
+
+template <int R>
+__global__ void __launch_bounds__(K2_WARPS * 32)
+score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+             const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
+             const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
+             uint32_t* __restrict__ out_count, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters,
+             uint32_t ML) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  unsigned char* base = smem_raw + (size_t)warp * k2_warp_bytes(ML, R);
+  uint8_t* sq = base;
+  uint32_t* cell = reinterpret_cast<uint32_t*>(base + 256);
+  uint8_t* ring = base + 256 + (size_t)(ML + 1) * 32 * 4;
+  const uint32_t rowbytes = (ML + 1) * 32;
+
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
+  SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
+  SurvRec* sorted = surv + bp.hit_cap;
+
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  const int have_freq = ix->have_freq;
+  unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t flags = qflags[qi];
+    if (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
+      if (lane == 0) out_count[qi] = 0;
+      continue;
+    }
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t Lq = qrow[0];
+    const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
+    for (uint32_t i = lane; i < Lq; i += 32) sq[i] = qrow[2 + i];
+    __syncwarp();
+    const uint32_t ke = apply_threshold(bp.max_edit, Lq);
+    const uint32_t nh = hit_count[qi];
+    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    const double Ld = (double)Lq;
+
+    uint32_t nsurv = 0;
+    double maxfreq = 0.0;
+
+    for (uint32_t hb = 0; hb < nh; hb += 32) {
+      const uint32_t hi = hb + lane;
+      bool valid = hi < nh;
+      uint32_t g = 0, Lc = 0;
+      bool c_lower = false;
+      if (valid) {
+        g = hq[hi];
+        const uint8_t* row = rows + (size_t)g * nstride;
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row));
+        Lc = v0.x & 0xFF;
+        c_lower = ((v0.x >> 8) & ROW_FIRST_LOWER) != 0;
+        // length pre-check of damerau_levenshtein (src/distance.rs:109-130)
+        const uint32_t diff = Lq > Lc ? Lq - Lc : Lc - Lq;
+        valid = diff <= ke;
+        if (valid) {
+          // stage the candidate's symbols: cell[j].t = t[j-1]
+          for (uint32_t j0 = 0; j0 < Lc + 2; j0 += 16) {
+            const uint4 v = (j0 == 0) ? v0 : __ldg(reinterpret_cast<const uint4*>(row + j0));
+            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+              const uint32_t bytepos = j0 + b;  // byte in the row; symbol index = bytepos - 2
+              if (bytepos >= 2 && bytepos < Lc + 2) {
+                const uint32_t sym = (wds[b >> 2] >> ((b & 3) * 8)) & 0xFF;
+                cell[(bytepos - 1) * 32 + lane] = sym;  // column j = bytepos - 1: t, lcs = 0, lastrow = 0
+              }
+            }
+          }
+          c_pairs += 1;
+          c_cells += (unsigned long long)Lq * Lc;
+        }
+      }
+      const uint32_t vmask = __ballot_sync(FULL, valid);
+      if (vmask == 0) continue;
+      uint32_t Lcm = valid ? Lc : 0;
+      for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
+
+      // ---- true Damerau-Levenshtein, all lanes in lock-step over (i, j) -----------------------
+      // Row i of the matrix lives in ring[i % R].  Only the last ke+2 <= R rows are ever needed:
+      // a transposition reaching further back costs more than ke ("DP kernel").
+      for (uint32_t j = 0; j <= Lcm; ++j) ring[j * 32 + lane] = (uint8_t)j;  // row 0
+      uint32_t lcs_best = 0;
+      for (uint32_t i = 1; i <= Lq; ++i) {
+        const uint32_t sc = sq[i - 1];
+        uint8_t* cur = ring + (size_t)(i & (R - 1)) * rowbytes;
+        const uint8_t* prev = ring + (size_t)((i - 1) & (R - 1)) * rowbytes;
+        uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
+        cur[lane] = (uint8_t)min(i, 255u);
+        for (uint32_t j = 1; j <= Lcm; ++j) {
+          const uint32_t cw = cell[j * 32 + lane];
+          const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF;
+          const uint32_t up = prev[j * 32 + lane];
+          const bool same = (tc == sc) && (j <= Lc);
+          uint32_t v = min(min(left, up) + 1, diag + (same ? 0u : 1u));
+          if (last > 0 && db > 0 && i - last <= (uint32_t)(R - 2)) {
+            const uint32_t tv = ring[(size_t)((last - 1) & (R - 1)) * rowbytes + (db - 1) * 32 + lane] + (i - last - 1) + 1 +
+                                (j - db - 1);
+            v = min(v, tv);
+          }
+          v = min(v, 255u);
+          cur[j * 32 + lane] = (uint8_t)v;
+          const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
+          lcs_best = max(lcs_best, lcs_new);
+          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? i : last) << 16);
+          if (same) db = j;
+          lcs_diag = lcs_up;
+          diag = up;
+          left = v;
+        }
+      }
+      uint32_t ld = 255;
+      if (valid) ld = ring[(size_t)(Lq & (R - 1)) * rowbytes + Lc * 32 + lane];
+      valid = valid && ld <= ke;
+
+      // ---- prefix / suffix (src/distance.rs:208-231) ------------------------------------------------
+      uint32_t pre = 0, suf = 0;
+      {
+        const uint32_t lim = min(Lq, Lcm);
+        bool pgo = valid, sgo = valid;
+        for (uint32_t i = 0; i < lim; ++i) {
+          if (valid && i < Lc) {
+            const uint32_t a = cell[(i + 1) * 32 + lane] & 0xFF;
+            pgo = pgo && (a == sq[i]);
+            pre += pgo;
+            const uint32_t b = cell[(Lc - i) * 32 + lane] & 0xFF;
+            sgo = sgo && (b == sq[Lq - 1 - i]);
+            suf += sgo;
+          }
+        }
+      }
+      // features are skipped (0 / true) when their weight is <= 0 (src/lib.rs:1352-1377)
+      const uint32_t f_lcs = bp.w_lcs > 0.0 ? lcs_best : 0;
+      const uint32_t f_pre = bp.w_prefix > 0.0 ? pre : 0;
+      const uint32_t f_suf = bp.w_suffix > 0.0 ? suf : 0;
+      const bool samecase = bp.w_case > 0.0 ? (c_lower == q_lower) : true;
+
+      // ---- f64 score, left to right, no FMA (src/lib.rs:1433-1452) -----------------------------------
+      const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, __ddiv_rn((double)ld, Ld));
+      double acc = __dmul_rn(bp.w_ld, ds);
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, __ddiv_rn((double)f_lcs, Ld)));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, __ddiv_rn((double)f_pre, Ld)));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, __ddiv_rn((double)f_suf, Ld)));
+      acc = __dadd_rn(acc, samecase ? bp.w_case : 0.0);
+      const double score = __ddiv_rn(acc, bp.w_sum);
+      double freq = 1.0;
+      if (valid && have_freq) freq = (double)__ldg(ix->inst_freq + g);
+      // max_freq is taken over every instance within the edit distance, before the score threshold
+      double mf = valid ? freq : 0.0;
+      for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
+      maxfreq = fmax(maxfreq, mf);
+      c_surv += valid ? 1 : 0;
+      const bool keep = valid && score >= bp.score_threshold;
+      const uint32_t kmask = __ballot_sync(FULL, keep);
+      if (keep) {
+        SurvRec r;
+        r.dist = score;
+        r.freq = freq;
+        r.g = g;
+        r.pad = 0;
+        surv[nsurv + __popc(kmask & lanemask_lt())] = r;
+      }
+      nsurv += __popc(kmask);
+      __syncwarp();
+    }
+
+    // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
+    __threadfence_block();
+    __syncwarp();
+    for (uint32_t i = lane; i < nsurv; i += 32) {
+      SurvRec r = surv[i];
+      if (maxfreq > 0.0) r.freq = __ddiv_rn(r.freq, maxfreq);
+      surv[i] = r;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nsurv; i += 32) {
+      const SurvRec a = surv[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nsurv; ++j) {
+        const SurvRec b = surv[j];
+        rank += (j != i) && ranks_before(bp, b.dist, b.freq, b.g, a.dist, a.freq, a.g);
+      }
+      sorted[rank] = a;
+    }
+    __syncwarp();
+
+    // ---- crop at max_matches with the reference's tie rules (src/lib.rs:1536-1589) ---------------------
+    uint32_t n = nsurv;
+    if (bp.finish_mode != FINISH_GATHER && bp.max_matches > 0 && n > bp.max_matches) {
+      const SurvRec a = sorted[bp.max_matches - 1], b = sorted[bp.max_matches];
+      const double last_score = result_score(bp, a.dist, a.freq);
+      const double cropped = result_score(bp, b.dist, b.freq);
+      if (cropped < last_score) {
+        n = bp.max_matches;
+      } else {
+        // B = first i with dist_i < cropped; E = first i in [1, B) with dist_i == cropped
+        uint32_t B = n, E = 0xFFFFFFFFu;
+        for (uint32_t b0 = 0; b0 < n && B == n; b0 += 32) {
+          const uint32_t i = b0 + lane;
+          double dsc = 0.0;
+          const bool in = i < n;
+          if (in) dsc = sorted[i].dist;
+          const uint32_t lt = __ballot_sync(FULL, in && dsc < cropped);
+          uint32_t eq = __ballot_sync(FULL, in && i >= 1 && dsc == cropped);
+          if (lt) {
+            const uint32_t first = __ffs(lt) - 1;
+            B = b0 + first;
+            eq &= (first == 0) ? 0u : (0xFFFFFFFFu >> (32 - first));
+          }
+          if (eq && E == 0xFFFFFFFFu) E = b0 + __ffs(eq) - 1;
+        }
+        if (E != 0xFFFFFFFFu)
+          n = E + 1;
+        else if (B < n && B > 0)
+          n = B + 1;
+      }
+    }
+    // ---- cut-off (src/lib.rs:1598-1622); only when no late confusable rescoring follows -----------------
+    if (bp.finish_mode == FINISH_FULL && bp.cutoff_threshold >= 1.0 && n > 1) {
+      const SurvRec a = sorted[0];
+      const double lim = __ddiv_rn(result_score(bp, a.dist, a.freq), bp.cutoff_threshold);
+      uint32_t cut = n;
+      for (uint32_t b0 = 0; b0 < n && cut == n; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        bool hit = false;
+        if (i >= 1 && i < n) {
+          const SurvRec r = sorted[i];
+          hit = result_score(bp, r.dist, r.freq) <= lim;
+        }
+        const uint32_t m = __ballot_sync(FULL, hit);
+        if (m) cut = b0 + __ffs(m) - 1;
+      }
+      n = cut;
+    }
+    // ---- emit ---------------------------------------------------------------------------------------------
+    OutRec* oq = out + (size_t)qi * bp.out_cap;
+    for (uint32_t i = lane; i < n && i < bp.out_cap; i += 32) {
+      const SurvRec r = sorted[i];
+      OutRec o;
+      o.dist_score = r.dist;
+      o.freq_score = r.freq;
+      o.vocab_id = __ldg(ix->inst_vocab + r.g);
+      o.gather_id = r.g;
+      oq[i] = o;
+    }
+    if (lane == 0) {
+      out_count[qi] = n;
+      if (n > bp.out_cap) qflags[qi] = flags | QF_OUT_OVERFLOW;
+    }
+    c_res += (lane == 0) ? min(n, bp.out_cap) : 0;
+    __syncwarp();
+  }
+
+  if (counters) {
+    unsigned long long v[4] = {c_pairs, c_cells, c_surv, c_res};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned long long x = v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+      v[k] = x;
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->dl_pairs, v[0]);
+      atomicAdd(&counters->dl_cells, v[1]);
+      atomicAdd(&counters->survivors, v[2]);
+      atomicAdd(&counters->results, v[3]);
+    }
+  }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static int g_k1_ctas_per_sm = 0;
+static int g_k2_ctas_per_sm[3] = {0, 0, 0};
+
+static uint32_t ring_depth(const BatchParams& bp) {
+  // rows needed = max edit distance + 2; thresholds are capped at 255 but anything beyond 14 is
+  // rejected by the host (ANL_ERR_UNSUPPORTED)
+  uint32_t kmax = bp.max_edit.kind == 0 ? 12u : (bp.max_edit.value & 0xFFu);
+  if (kmax + 2 <= 4) return 4;
+  if (kmax + 2 <= 8) return 8;
+  return 16;
+}
+
+cudaError_t configure_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(score_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(score_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_kernel, K1_WARPS * 32, sizeof(K1Shared));
+  return e;
+}
+
+cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
+                         int sm_count, cudaStream_t stream) {
+  (void)h_ix;
+  if (lb.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  int per_sm = g_k1_ctas_per_sm > 0 ? g_k1_ctas_per_sm : 1;
+  // persistent grid: a whole number of CTAs per SM, no more warps than queries
+  long long want = ((long long)lb.n + K1_WARPS - 1) / K1_WARPS;
+  long long grid = (long long)sm_count * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  probe_kernel<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
+                                                                            lb.hit_count, lb.qflags, lb.work, lb.counters);
+  return cudaGetLastError();
+}
+
+static int k2_ctas_per_sm(uint32_t R, size_t smem) {
+  int n = 0;
+  cudaError_t e;
+  if (R == 4)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<4>, K2_WARPS * 32, smem);
+  else if (R == 8)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<8>, K2_WARPS * 32, smem);
+  else
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<16>, K2_WARPS * 32, smem);
+  if (e != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
+// The score kernel's grid is fixed per (model, params) so its scratch can be allocated once.
+static long long k2_grid(const DeviceIndex& h_ix, const BatchParams& bp, int sm_count) {
+  const uint32_t R = ring_depth(bp);
+  const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
+  int idx = R == 4 ? 0 : (R == 8 ? 1 : 2);
+  (void)idx;
+  return (long long)sm_count * k2_ctas_per_sm(R, smem);
+}
+
+static uint32_t g_scratch_max_len = 0;
+size_t score_scratch_bytes(const BatchParams& bp, int sm_count) {
+  // upper bound on resident warps: 16 CTAs/SM would exceed any smem-limited occupancy here
+  return (size_t)sm_count * 16 * K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
+}
+
+cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
+                         int sm_count, cudaStream_t stream) {
+  (void)g_scratch_max_len;
+  if (lb.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  const uint32_t R = ring_depth(bp);
+  const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  long long grid = k2_grid(h_ix, bp, sm_count);
+  const long long cap = (long long)sm_count * 16;
+  if (grid > cap) grid = cap;
+  long long want = ((long long)lb.n + K2_WARPS - 1) / K2_WARPS;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
+#define ANL_LAUNCH_K2(RR)                                                                                              \
+  score_kernel<RR><<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,    \
+                                                                    lb.hit_count, lb.qflags, lb.out, lb.out_count,    \
+                                                                    scratch, lb.work + 1, lb.counters, h_ix.max_len)
+  if (R == 4)
+    ANL_LAUNCH_K2(4);
+  else if (R == 8)
+    ANL_LAUNCH_K2(8);
+  else
+    ANL_LAUNCH_K2(16);
+#undef ANL_LAUNCH_K2
+  return cudaGetLastError();
+}
+
+}  // namespace anl

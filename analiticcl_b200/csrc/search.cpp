@@ -1,0 +1,126 @@
+// search.cpp -- the batch producer of find_all_matches (src/lib.rs:1790-1957, src/search.rs:190-336).
+//
+// Host-side segmentation: token boundaries, boundary strengths, n-gram spans per hard-delimited
+// batch, redundant-match pruning.  Unlike the reference -- which calls find_variants once per
+// segment from a rayon loop -- the segments of the whole text are looked up in at most two GPU
+// batches: all unigrams first, then every higher-order segment that the unigram results do not make
+// redundant (redundant_match only ever inspects unigram results, src/search.rs:317-336).
+#include "search.h"
+
+#include <algorithm>
+
+#include "unicode_tables.h"
+
+namespace anl {
+
+static inline uint32_t decode_at(const std::string& s, size_t i, unsigned* len) {
+  const unsigned char c = (unsigned char)s[i];
+  unsigned l = c < 0x80 ? 1 : ((c & 0xE0) == 0xC0 ? 2 : ((c & 0xF0) == 0xE0 ? 3 : ((c & 0xF8) == 0xF0 ? 4 : 1)));
+  if (i + l > s.size()) l = (unsigned)(s.size() - i);
+  *len = l;
+  if (l == 1) return c;
+  uint32_t cp = c & (0xFFu >> (l + 1));
+  for (unsigned k = 1; k < l; ++k) cp = (cp << 6) | ((unsigned char)s[i + k] & 0x3F);
+  return cp;
+}
+
+// src/search.rs:190-235: a boundary is a maximal run of non-alphabetic characters; the text always
+// ends with a boundary (possibly of length zero).
+std::vector<Boundary> find_boundaries(const std::string& text) {
+  std::vector<Boundary> out;
+  bool open = false;
+  size_t start = 0;
+  for (size_t i = 0; i < text.size();) {
+    unsigned l;
+    const bool alpha = anl_unicode::is_alphabetic(decode_at(text, i, &l));
+    if (open && alpha) {
+      out.push_back(Boundary{start, i, BOUNDARY_NONE});
+      open = false;
+    } else if (!open && !alpha) {
+      start = i;
+      open = true;
+    }
+    i += l;
+  }
+  if (open)
+    out.push_back(Boundary{start, text.size(), BOUNDARY_NONE});
+  else
+    out.push_back(Boundary{text.size(), text.size(), BOUNDARY_NONE});
+  // src/search.rs:238-258: last or multi-byte boundary = hard; ' - _ = weak; else normal
+  for (size_t i = 0; i < out.size(); ++i) {
+    const size_t len = out[i].end - out[i].begin;
+    if (i + 1 == out.size() || len > 1) {
+      out[i].strength = BOUNDARY_HARD;
+    } else {
+      const char c = len == 1 ? text[out[i].begin] : 0;
+      out[i].strength = (c == '\'' || c == '-' || c == '_') ? BOUNDARY_WEAK : BOUNDARY_NORMAL;
+    }
+  }
+  return out;
+}
+
+// src/search.rs:262-312
+std::vector<SegmentSpan> find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order,
+                                           size_t begin, size_t end) {
+  std::vector<SegmentSpan> out;
+  auto usable = [&](size_t b, size_t e) { return e > b && !(e - b == 1 && text[b] == ' '); };
+  for (size_t i = 0; i + order - 1 < nbounds; ++i) {
+    const Boundary& right = bounds[i + order - 1];
+    if (right.begin > end) break;
+    if (usable(begin, right.begin)) out.push_back(SegmentSpan{begin, right.begin, order});
+    begin = bounds[i].end;
+  }
+  if (begin < end && usable(begin, end)) {
+    // Match::internal_boundaries (src/search.rs:99-116) counts with a first/last window: the first
+    // inner boundary only opens the window, every later one extends it.
+    long first = -1;
+    size_t last_plus1 = 0;
+    for (size_t k = 0; k < nbounds; ++k) {
+      if (bounds[k].begin > begin && bounds[k].end < end) {
+        if (first < 0)
+          first = (long)k;
+        else
+          last_plus1 = k + 1;
+      }
+    }
+    const size_t inner = (first < 0 || (size_t)first >= last_plus1) ? 0 : last_plus1 - (size_t)first;
+    if (inner == order) out.push_back(SegmentSpan{begin, end, order});
+  }
+  return out;
+}
+
+std::vector<SpanBatch> segment_text(const std::string& text, uint32_t max_ngram) {
+  std::vector<SpanBatch> batches;
+  if (text.empty()) return batches;
+  const std::vector<Boundary> bounds = find_boundaries(text);
+  size_t begin = 0, begin_index = 0;
+  for (size_t i = 0; i < bounds.size(); ++i) {
+    if (bounds[i].strength != BOUNDARY_HARD || bounds[i].begin == begin) continue;  // src/lib.rs:1822
+    SpanBatch sb;
+    for (uint32_t order = 1; order <= max_ngram; ++order) {
+      std::vector<SegmentSpan> cur =
+          find_match_ngrams(text, bounds.data() + begin_index, i + 1 - begin_index, order, begin, bounds[i].begin);
+      sb.segments.insert(sb.segments.end(), cur.begin(), cur.end());
+    }
+    batches.push_back(std::move(sb));
+    begin = bounds[i].end;
+    begin_index = i + 1;
+  }
+  return batches;
+}
+
+std::vector<uint64_t> byte_to_codepoint_map(const std::string& text) {
+  std::vector<uint64_t> map(text.size() + 1, 0);
+  uint64_t cp = 0;
+  for (size_t i = 0; i < text.size();) {
+    unsigned l;
+    decode_at(text, i, &l);
+    for (unsigned k = 0; k < l; ++k) map[i + k] = cp;
+    i += l;
+    ++cp;
+  }
+  map[text.size()] = cp;
+  return map;
+}
+
+}  // namespace anl

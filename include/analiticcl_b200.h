@@ -1,0 +1,241 @@
+/* analiticcl_b200.h -- C ABI of the B200-native variant-lookup path.
+ *
+ * Drop-in boundary for the hot path of proycon/analiticcl v0.4.9: `VariantModel::find_variants`
+ * (src/lib.rs:972) and its batching callers (`find_variants_par`, bindings/python/src/lib.rs:720;
+ * `find_all_matches`, src/lib.rs:1790).  The reference has no FFI seam of its own; the seam is the
+ * public methods of `VariantModel`, so every entry point below names the reference method it
+ * replaces.  INTEGRATION.md shows the Rust `-sys` binding and the Python ctypes binding.
+ *
+ * Conventions: plain C types only, opaque handles, inputs borrowed for the duration of the call,
+ * outputs owned by the library until the matching *_free.  Every function that can fail returns
+ * an `anl_status` (0 = ok); `anl_last_error()` gives the message of the calling thread's last
+ * failure.  There is NO CPU fallback: if CUDA is unavailable, anl_model_build() fails.
+ */
+#ifndef ANALITICCL_B200_H
+#define ANALITICCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t anl_status;
+enum {
+  ANL_OK = 0,
+  ANL_ERR_INVALID = 1,     /* bad argument */
+  ANL_ERR_IO = 2,          /* file could not be read / parsed (reference: io::Error) */
+  ANL_ERR_NOT_BUILT = 3,   /* lookup before build() (reference: stderr + empty result, src/lib.rs:973) */
+  ANL_ERR_CUDA = 4,        /* CUDA runtime / kernel failure, or no device */
+  ANL_ERR_UNSUPPORTED = 5, /* outside the documented limits of the GPU path */
+  ANL_ERR_EMPTY_INPUT = 6  /* empty query (reference: assert!(input_length > 0), src/lib.rs:1420) */
+};
+
+typedef struct anl_model anl_model;           /* VariantModel, src/lib.rs:50-100 */
+typedef struct anl_result_set anl_result_set; /* Vec<Vec<VariantResult>> */
+typedef struct anl_match_set anl_match_set;   /* Vec<Match>, src/search.rs:42-68 */
+
+/* Weights, src/types.rs:39-73 (defaults .5 / .125 x4) */
+typedef struct anl_weights {
+  double ld, lcs, prefix, suffix, case_;
+} anl_weights;
+
+/* DistanceThreshold, src/types.rs:75-83 */
+enum { ANL_THRESHOLD_RATIO = 0, ANL_THRESHOLD_RATIO_WITH_LIMIT = 1, ANL_THRESHOLD_ABSOLUTE = 2 };
+typedef struct anl_distance_threshold {
+  int32_t kind;
+  float ratio;    /* Ratio, RatioWithLimit */
+  uint32_t value; /* Absolute value, or the limit of RatioWithLimit (u8 range) */
+} anl_distance_threshold;
+
+/* StopCriterion, src/types.rs:307-313 */
+enum { ANL_STOP_EXHAUSTIVE = 0, ANL_STOP_AT_EXACT_MATCH = 1 };
+
+/* SearchParameters, src/types.rs:110-168, field for field (fields only used by the out-of-scope
+ * FST/LM stage are carried so a caller can pass its struct through unchanged). */
+typedef struct anl_search_params {
+  anl_distance_threshold max_anagram_distance;
+  anl_distance_threshold max_edit_distance;
+  uint64_t max_matches;
+  double score_threshold;
+  double cutoff_threshold;
+  int32_t stop_criterion;
+  uint32_t max_ngram;
+  uint32_t lm_order;
+  uint64_t max_seq;
+  int32_t single_thread;
+  float context_weight;
+  float variantmodel_weight;
+  float lm_weight;
+  float contextrules_weight;
+  float freq_weight;
+  int32_t consolidate_matches;
+  int32_t unicodeoffsets;
+} anl_search_params;
+
+/* VocabType bit flags (src/vocab.rs:31-49) and FrequencyHandling (src/vocab.rs:100-106) */
+enum { ANL_VOCAB_NONE = 0, ANL_VOCAB_INDEXED = 1, ANL_VOCAB_LM = 2, ANL_VOCAB_TRANSPARENT = 4 };
+enum { ANL_FREQ_SUM = 0, ANL_FREQ_MAX = 1, ANL_FREQ_MIN = 2, ANL_FREQ_REPLACE = 3 };
+
+/* VocabParams, src/vocab.rs:108-131 */
+typedef struct anl_vocab_params {
+  uint32_t text_column;
+  int32_t freq_column; /* -1 = None */
+  int32_t freq_handling;
+  uint32_t vocab_type;
+  uint32_t index; /* lexicon index; overwritten by read_vocabulary like the reference does */
+} anl_vocab_params;
+
+/* VariantResult, src/types.rs:326-332 */
+#define ANL_NO_VIA UINT64_MAX
+typedef struct anl_variant {
+  uint64_t vocab_id;
+  double dist_score;
+  double freq_score;
+  uint64_t via; /* ANL_NO_VIA = None (variant lists are out of scope, so always None) */
+} anl_variant;
+
+/* VocabValue, src/vocab.rs:7-29 (read-only view) */
+typedef struct anl_vocab_info {
+  const char* text; /* UTF-8, NUL terminated, owned by the model */
+  uint32_t text_len;
+  uint32_t frequency;
+  uint32_t lexindex;
+  uint32_t vocabtype;
+  uint32_t tokencount;
+  uint32_t norm_len;
+} anl_vocab_info;
+
+/* Defaults: Weights::default(), SearchParameters::default(), VocabParams::default() */
+void anl_weights_default(anl_weights* w);
+void anl_search_params_default(anl_search_params* p);
+void anl_vocab_params_default(anl_vocab_params* p);
+
+const char* anl_last_error(void);
+const char* anl_version(void);
+
+/* ---- model construction ------------------------------------------------------------------ */
+/* VariantModel::new (src/lib.rs:104): alphabet TSV file + weights. */
+anl_status anl_model_new(const char* alphabet_file, const anl_weights* weights, int32_t debug, anl_model** out);
+/* VariantModel::new_with_alphabet (src/lib.rs:132): alphabet given as TSV text in memory. */
+anl_status anl_model_new_from_tsv(const char* alphabet_tsv, size_t len, const anl_weights* weights, int32_t debug,
+                                  anl_model** out);
+void anl_model_free(anl_model* m);
+
+/* read_vocabulary (src/lib.rs:519) */
+anl_status anl_model_read_vocabulary(anl_model* m, const char* filename, const anl_vocab_params* params);
+/* add_to_vocabulary (src/lib.rs:900); has_frequency=0 means None */
+anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t len, int32_t has_frequency,
+                                       uint32_t frequency, const anl_vocab_params* params, uint64_t* vocab_id);
+/* read_confusablelist (src/lib.rs:414), add_to_confusables (src/lib.rs:444) */
+anl_status anl_model_read_confusablelist(anl_model* m, const char* filename);
+anl_status anl_model_add_to_confusables(anl_model* m, const char* editscript, double weight);
+/* set_confusables_before_pruning (src/lib.rs:157) */
+void anl_model_set_confusables_before_pruning(anl_model* m);
+
+/* build (src/lib.rs:192): anagram index on the host, then upload to `device` (-1 = current). */
+anl_status anl_model_build(anl_model* m, int32_t device);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int32_t anl_model_has(const anl_model* m, const char* text, size_t len);          /* has(), src/lib.rs:331 */
+int64_t anl_model_vocab_id(const anl_model* m, const char* text, size_t len);     /* encoder lookup, -1 if absent */
+uint64_t anl_model_vocab_size(const anl_model* m);                                 /* decoder.len() */
+anl_status anl_model_get_vocab(const anl_model* m, uint64_t vocab_id, anl_vocab_info* out); /* get_vocab(), :341 */
+uint32_t anl_model_lexicon_count(const anl_model* m);
+const char* anl_model_lexicon_name(const anl_model* m, uint32_t index);
+uint32_t anl_model_alphabet_size(const anl_model* m); /* alphabet_size(), src/lib.rs:163 (incl. UNK) */
+uint64_t anl_model_index_size(const anl_model* m);    /* number of anagrams */
+uint64_t anl_model_instance_count(const anl_model* m);
+uint64_t anl_model_anagram_count_of_length(const anl_model* m, uint32_t charcount); /* sortedindex[cc].len() */
+uint32_t anl_model_max_key_bits(const anl_model* m);
+/* anahash / normalize_to_alphabet (src/anahash.rs:16,50).  anl_anahash writes the value as little
+ * endian 64-bit limbs; returns the number of limbs needed (may exceed cap). */
+int64_t anl_normalize(const anl_model* m, const char* text, size_t len, uint8_t* out, size_t cap);
+int64_t anl_anahash(const anl_model* m, const char* text, size_t len, uint64_t* limbs, size_t cap);
+
+/* ---- lookup ---------------------------------------------------------------------------------- */
+/* find_variants over a batch (== find_variants_par, bindings/python/src/lib.rs:720).
+ * `blob` holds the UTF-8 queries back to back, query i = blob[offsets[i] .. offsets[i+1]).
+ * Results are final: ranked, cropped, confusable-rescored, cut off -- identical to what
+ * VariantModel::find_variants returns for each query.  An empty query yields an empty list and
+ * sets bit 0 of its flags (the reference panics on it). */
+anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                   const anl_search_params* params, anl_result_set** out);
+uint64_t anl_result_set_len(const anl_result_set* rs);
+/* variants of query i: pointer to a contiguous array + count */
+const anl_variant* anl_result_set_get(const anl_result_set* rs, uint64_t i, uint64_t* count);
+/* whole CSR: offsets[n+1] and the flat variant array */
+const uint64_t* anl_result_set_offsets(const anl_result_set* rs);
+const anl_variant* anl_result_set_variants(const anl_result_set* rs);
+uint32_t anl_result_set_flags(const anl_result_set* rs, uint64_t i);
+void anl_result_set_free(anl_result_set* rs);
+
+/* find_all_matches (src/lib.rs:1790).  Host segmentation (boundaries, n-gram spans, redundant-match
+ * pruning) feeding the batched GPU lookup.  The FST/LM consolidation stage
+ * (most_likely_sequence, src/lib.rs:2088) is out of scope: with max_ngram == 1 and no LM/context
+ * rules the reference does not run it either and results are identical; with max_ngram > 1 every
+ * segment of every order is returned with its variant list and `selected` = 0 where it has variants
+ * (i.e. the `consolidate_matches = false` view). */
+anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, const anl_search_params* params,
+                                anl_match_set** out);
+typedef struct anl_match {
+  uint64_t begin, end; /* byte offsets, or code points if params.unicodeoffsets */
+  uint32_t n;          /* n-gram order of this segment */
+  int32_t selected;    /* index of the selected variant, -1 = none */
+  uint64_t n_variants;
+  const anl_variant* variants; /* NULL when the segment was skipped as redundant */
+} anl_match;
+uint64_t anl_match_set_len(const anl_match_set* ms);
+anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out);
+void anl_match_set_free(anl_match_set* ms);
+
+/* ---- device-resident path (what bench.py times as `value`; plumbing for multi-GPU hosts) ------ */
+typedef struct anl_device_batch anl_device_batch; /* encoded queries + result buffers in HBM */
+/* Encodes on the host (alphabet normalisation) and uploads; buffers are sized for n_queries. */
+anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                   const anl_search_params* params, anl_device_batch** out);
+/* One pass of the hot path over the resident batch: probe kernel + score/rank kernel on the
+ * model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
+anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream);
+/* Device-side cudaEvent timings (ms) of the last run's two kernels; synchronises. */
+anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms);
+/* Downloads the results of the last run and finishes them on the host (same output as
+ * anl_find_variants_batch). */
+anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out);
+void anl_device_batch_free(anl_model* m, anl_device_batch* b);
+
+/* Work counters of the last run (exact, counted inside the kernels). */
+typedef struct anl_counters {
+  uint64_t queries;
+  uint64_t deletion_keys; /* distinct deletion-neighbourhood keys D (incl. the focus)        */
+  uint64_t probes;        /* neighbourhood nodes tested against the Bloom filter (one 8-byte word each) */
+  uint64_t filter_pass;   /* nodes that passed the filter and were looked up exactly          */
+  uint64_t probe_steps;   /* 16-byte table slots read by the exact lookups (linear probing)   */
+  uint64_t postings;      /* postings verified against the anagram keys                       */
+  uint64_t anagram_hits;  /* indexed anagrams found (each exactly once per query)             */
+  uint64_t instance_pairs;/* (query, instance) pairs handed to the distance kernel           */
+  uint64_t dl_pairs;      /* pairs that pass the length pre-check (src/distance.rs:109-130)  */
+  uint64_t dl_cells;      /* sum len_q*len_c over dl_pairs = the reference's matrix cell updates */
+  uint64_t survivors;     /* pairs within max edit distance                                  */
+  uint64_t results;       /* variants returned                                               */
+  uint64_t reruns;        /* queries re-run because a fixed-capacity buffer overflowed       */
+} anl_counters;
+anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out);
+
+/* Size of the device-resident index (bytes per component) for roofline accounting. */
+typedef struct anl_index_stats {
+  uint64_t table_slots, table_bytes, slot_bytes, table_keys;
+  uint64_t bloom_bytes, postings;
+  uint64_t anagrams, instances;
+  uint64_t instance_bytes, norm_stride;
+  uint64_t mset_entries, mset_bytes;
+  uint32_t max_key_bits, max_charcount, active_classes;
+  uint32_t sd; /* symmetric-delete depth of the neighbour table */
+} anl_index_stats;
+anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANALITICCL_B200_H */

@@ -1,0 +1,64 @@
+"""CPU-only: the C-ABI library loads without a GPU and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def so():
+    from analiticcl_b200 import build, _capi
+    build.build()
+    return ctypes.CDLL(_capi.SO_PATH)
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "analiticcl_b200.h"), encoding="utf-8").read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(anl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(so):
+    names = declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(so, n)]
+    assert not missing, missing
+
+
+def test_ctypes_stub_covers_header():
+    from analiticcl_b200 import _capi
+    assert sorted(_capi.SIGNATURES) == declared_symbols()
+
+
+def test_host_side_without_gpu():
+    """Model construction, normalisation and hashing are host code; build() must fail loudly
+    (no CPU fallback) when there is no device."""
+    import torch
+    import analiticcl_b200 as A
+    import workloads
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.AMPHIBIANS)
+    assert m.anahash("least") == 1227306
+    assert m.normalize("aFé") == [0, 32, 1]  # F is not in simple.alphabet.tsv: UNK = alphabet.len()+1
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.build()
+        with pytest.raises(RuntimeError, match="not been built"):
+            m.find_variants("frog", A.SearchParameters())
+
+
+def test_search_parameters_surface():
+    import analiticcl_b200 as A
+    p = A.SearchParameters()
+    assert (p.max_anagram_distance, p.max_edit_distance, p.max_matches) == (3, 3, 20)
+    assert (p.score_threshold, p.cutoff_threshold, p.max_ngram, p.freq_weight) == (0.25, 2.0, 3, 0.0)
+    p = A.SearchParameters(max_edit_distance=(0.5, 4), max_anagram_distance=0.25, stop_at_exact_match=True, bogus=1)
+    assert p.max_edit_distance == (0.5, 4) and p.max_anagram_distance == 0.25 and p.stop_at_exact_match
+    assert A.SearchParameters(max_edit_distance="0.5;4").max_edit_distance == (0.5, 4)
+    w = A.Weights(ld=0.6)
+    assert w.to_dict() == {"ld": 0.6, "lcs": 0.125, "prefix": 0.125, "suffix": 0.125, "case": 0.125}
+    v = A.VocabParams(freq_column=2, vocabtype="TRANSPARENT", freqhandling="sum")
+    assert v.freq_column == 2 and v.data.vocab_type == 5 and v.data.freq_handling == 0

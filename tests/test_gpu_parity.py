@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Compared per query: the list of (vocab_id, dist_score, freq_score) -- same candidates, same order,
+identical f64 bits.  Run on the B200 box: `pytest -m gpu`.
+"""
+import json
+import os
+import struct
+
+import pytest
+
+import workloads
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return struct.unpack("<q", struct.pack("<d", x))[0]
+
+
+def assert_same(got, exp, queries, tag=""):
+    assert len(got) == len(exp)
+    bad = []
+    for i, (g, e) in enumerate(zip(got, exp)):
+        gg = [(v, bits(d), bits(f)) for v, d, f in g]
+        ee = [(v, bits(d), bits(f)) for v, d, f in e]
+        if gg != ee:
+            bad.append((i, queries[i], g[:4], e[:4], len(g), len(e)))
+    assert not bad, f"{tag}: {len(bad)} / {len(got)} queries differ, first: {bad[:3]}"
+
+
+def to_orc_params(sp):
+    d = sp.data
+
+    def thr(t):
+        return {0: float(t.ratio), 1: (float(t.ratio), int(t.value)), 2: int(t.value)}[t.kind]
+    return orc.make_params(thr(d.max_anagram_distance), thr(d.max_edit_distance), d.max_matches, d.score_threshold,
+                           d.cutoff_threshold, d.stop_criterion == 1, d.freq_weight, d.max_ngram, bool(d.unicodeoffsets))
+
+
+@pytest.fixture(scope="module")
+def A():
+    import analiticcl_b200
+    return analiticcl_b200
+
+
+@pytest.fixture(scope="module")
+def eng(A):
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path("eng"))
+    m.build()
+    return m
+
+
+@pytest.fixture(scope="module")
+def nld_pair(A):
+    path = workloads.nld_freq_lexicon()
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(path)
+    m.build()
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    o.read_lexicon(path)
+    o.build()
+    return m, o
+
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial.json"), encoding="utf-8"))
+
+
+def test_index_goldens(eng):
+    assert eng.instance_count() == 119773 and eng.index_size() == 108802
+    hist = [27, 248, 942, 2593, 5623, 10163, 14617, 16911, 16391, 13930, 10650, 7194, 4434, 2459, 1384, 667, 339, 128,
+            62, 20, 9, 8, 2, 1]
+    assert [eng.anagram_count_of_length(i + 1) for i in range(24)] == hist
+    assert eng.max_key_bits() == 102
+    assert "separate" in eng and "seperate" not in eng
+
+
+@pytest.mark.parametrize("q", ["separate", "seperate"])
+def test_tutorial_find_variants(A, eng, q):
+    got = eng.find_variants(q, A.SearchParameters())
+    gold = GOLD["find_variants"][q]
+    assert [g["text"] for g in got] == [g["text"] for g in gold]
+    for g, e in zip(got, gold):
+        assert bits(g["dist_score"]) == bits(e["dist_score"]) and bits(g["score"]) == bits(e["score"])
+        assert g["freq_score"] == e["freq_score"] and len(g["lexicons"]) == 1
+
+
+def test_tutorial_find_all_matches(A, eng):
+    got = eng.find_all_matches("We would like seperate beds", A.SearchParameters(unicodeoffsets=True, max_ngram=1))
+    gold = GOLD["find_all_matches"]["We would like seperate beds"]
+    assert [(g["input"], g["offset"]) for g in got] == [(e["input"], e["offset"]) for e in gold]
+    for g, e in zip(got, gold):
+        assert [(v["text"], bits(v["dist_score"])) for v in g["variants"]] == \
+               [(v["text"], bits(v["dist_score"])) for v in e["variants"]]
+    # the 1-ulp ranking cases of "sep arate" (tutorial.ipynb:476)
+    e = GOLD["find_all_matches"]["We would like sep arate beds"]["match"]
+    g = eng.find_variants("sep arate", A.SearchParameters())
+    assert [(v["text"], bits(v["dist_score"])) for v in g] == [(v["text"], bits(v["dist_score"])) for v in e["variants"]]
+
+
+CASES = [
+    ("cfg1 k2", dict(max_anagram_distance=2, max_edit_distance=2), 3000, 1001),
+    ("default k3", dict(), 1500, 77),
+    ("k4", dict(max_anagram_distance=4, max_edit_distance=4), 300, 4001),
+    ("ratio", dict(max_anagram_distance=0.3, max_edit_distance=(0.4, 3)), 500, 5),
+    ("k3 edit2 unlimited", dict(max_edit_distance=2, max_matches=0, score_threshold=0.0, cutoff_threshold=0.0), 500, 6),
+    ("crop ties", dict(max_matches=3, score_threshold=0.0, cutoff_threshold=0.0), 800, 7),
+    ("crop 1", dict(max_matches=1), 500, 8),
+    ("stop at exact", dict(stop_at_exact_match=True), 600, 9),
+    ("freq weight", dict(freq_weight=0.3), 500, 10),
+    ("k1", dict(max_anagram_distance=1, max_edit_distance=1), 500, 11),
+    ("anagram>edit", dict(max_anagram_distance=3, max_edit_distance=1), 500, 12),
+]
+
+
+@pytest.mark.parametrize("tag,kw,n,seed", CASES, ids=[c[0] for c in CASES])
+def test_eng_parity(A, eng, eng_oracle, tag, kw, n, seed):
+    words = workloads.read_words("eng")
+    qs = workloads.misspellings(words, n, seed, min_len=2, max_len=18, edit_probs=((0, 0.15), (1, 0.45), (2, 0.3), (3, 0.1)))
+    sp = A.SearchParameters(**kw)
+    got = eng.find_variants_raw(qs, sp)
+    exp = eng_oracle.find_variants_batch(qs, to_orc_params(sp), threads=0)
+    assert_same(got, exp, qs, tag)
+
+
+def test_edge_inputs(A, eng, eng_oracle):
+    qs = ["a", "I", "zz", "x" * 30, "Frankfurt", "FRANK", "naïve", "ÆØÅ", "'s", "don't", "12345", "hello world",
+          "the quick brown fox", "œuvre", "ab" * 60, "q" * 240, "Ω≈ç√", " ", "-", "résumé", "e" * 9, "st" * 5,
+          "pneumonoultramicroscopicsilicovolcanoconiosis", "Stael", "Tesla", "steal"]
+    sp = A.SearchParameters()
+    got = eng.find_variants_raw(qs, sp)
+    exp = eng_oracle.find_variants_batch(qs, to_orc_params(sp))
+    assert_same(got, exp, qs, "edge")
+
+
+def test_empty_query_flag(A, eng):
+    out = eng.find_variants_par(["", "frog", ""], A.SearchParameters())
+    assert [o["variants"] == [] for o in out] == [True, False, True]
+
+
+def test_capacity_overflow_rerun(A, eng_oracle, monkeypatch):
+    """Fixed-capacity hit / result buffers overflow -> flagged queries are re-run with exact sizes."""
+    monkeypatch.setenv("ANL_HIT_CAP", "16")
+    monkeypatch.setenv("ANL_OUT_CAP", "4")
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path("eng"))
+    m.build()
+    qs = workloads.misspellings(workloads.read_words("eng"), 400, 99, min_len=3, max_len=10)
+    sp = A.SearchParameters()
+    got = m.find_variants_raw(qs, sp)
+    exp = eng_oracle.find_variants_batch(qs, to_orc_params(sp))
+    assert_same(got, exp, qs, "overflow")
+
+
+def test_nld_frequency_parity(A, nld_pair):
+    m, o = nld_pair
+    qs = workloads.ocr_noise(workloads.read_words("nld"), 1500, 2003)
+    for kw in (dict(freq_weight=0.25), dict(), dict(freq_weight=0.25, max_matches=5)):
+        sp = A.SearchParameters(**kw)
+        assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, f"nld {kw}")
+
+
+@pytest.mark.parametrize("early", [False, True], ids=["late", "early"])
+def test_nld_confusables_parity(A, early):
+    path = workloads.nld_freq_lexicon()
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(path)
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    o.read_lexicon(path)
+    for pat, w in workloads.CFG2_CONFUSABLES:
+        m.add_to_confusables(pat, w)
+        o.add_to_confusables(pat, w)
+    if early:
+        m.set_confusables_before_pruning()
+        o.set_confusables_before_pruning()
+    m.build()
+    o.build()
+    qs = workloads.ocr_noise(workloads.read_words("nld"), 800, 2004)
+    sp = A.SearchParameters(freq_weight=0.25)
+    assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, "confusables")
+
+
+def small(A, words, confusables=(), weights=None):
+    m = A.VariantModel(None, weights or A.Weights(), alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    for w in words:
+        m.add_to_vocabulary(w, None, A.VocabParams())
+    for p, wt in confusables:
+        m.add_to_confusables(p, wt)
+    m.build()
+    return m
+
+
+TEST_PARAMS = dict(max_anagram_distance=2, max_edit_distance=2, max_matches=10, score_threshold=0.0,
+                   cutoff_threshold=0.0, freq_weight=0.0, max_ngram=2)
+
+
+def test_reference_model_kats(A):
+    """tests/main.rs:858-911, 935-1020, 1120-1140 through the product API."""
+    m = small(A, ["rites", "tiers", "tires", "tries", "tyres", "rides", "brides", "dire"])
+    assert all(w in m for w in ["rites", "tiers", "dire"]) and "unknown" not in m
+    r = m.find_variants("rite", A.SearchParameters(**TEST_PARAMS))
+    assert [(v["text"], v["dist_score"]) for v in r] == [("rites", 0.75), ("dire", 0.4375)]
+    m = small(A, ["huis", "huls"])
+    r = m.find_variants("huys", A.SearchParameters(**TEST_PARAMS))
+    assert [v["text"] for v in r] == ["huis", "huls"] and r[0]["dist_score"] == r[1]["dist_score"]
+    for q in ("huys", "Huys"):
+        m = small(A, ["huis", "huls"], [("-[y]+[i]", 1.1)])
+        r = m.find_variants(q, A.SearchParameters(**TEST_PARAMS))
+        assert [v["text"] for v in r] == ["huis", "huls"] and r[0]["dist_score"] > r[1]["dist_score"]
+    m = small(A, ["huis", "huls"], [("-[y]+[p]", 1.1)])
+    r = m.find_variants("Huys", A.SearchParameters(**TEST_PARAMS))
+    assert len(r) == 2 and r[0]["dist_score"] == r[1]["dist_score"]
+    m = small(A, ["I", "think", "sink", "you", "are", "right"])
+    r = m.find_all_matches("I tink you are rihgt", A.SearchParameters(**{**TEST_PARAMS, "max_ngram": 1}))
+    assert [x["input"] for x in r] == ["I", "tink", "you", "are", "rihgt"]
+    assert r[1]["variants"][0]["text"] == "think" and r[4]["variants"][0]["text"] == "right"
+    m = small(A, ["I", "think", "you", "are", "right"])
+    r = m.find_all_matches("I thиnk you are righт", A.SearchParameters(**{**TEST_PARAMS, "max_ngram": 1}, unicodeoffsets=True))
+    assert (r[1]["input"], r[1]["offset"]) == ("thиnk", {"begin": 2, "end": 7}) and r[1]["variants"][0]["text"] == "think"
+    r = m.find_all_matches("I thиnk you are rihgt", A.SearchParameters(**{**TEST_PARAMS, "max_ngram": 1}))
+    assert r[1]["offset"] == {"begin": 2, "end": 8} and r[4]["variants"][0]["text"] == "right"
+
+
+def test_python_binding_test(A):
+    """bindings/python/tests/tests.py:12-26, unchanged apart from the import."""
+    m = A.VariantModel(workloads.ALPHABET, A.Weights(), debug=False)
+    m.read_lexicon(workloads.AMPHIBIANS)
+    m.read_lexicon(workloads.REPTILES)
+    m.build()
+    results = m.find_all_matches("Salamander lizard frog snake toad", A.SearchParameters(max_edit_distance=3, max_ngram=1))
+    assert len(results) == 5
+    exp = [("Salamander", workloads.AMPHIBIANS, "salamander"), ("lizard", workloads.REPTILES, "lizard"),
+           ("frog", workloads.AMPHIBIANS, "frog"), ("snake", workloads.REPTILES, "snake"),
+           ("toad", workloads.AMPHIBIANS, "toad")]
+    for r, (orig, lexicon, term) in zip(results, exp):
+        assert r["input"] == orig and r["variants"][0]["text"] == term and r["variants"][0]["lexicons"] == [lexicon]
+
+
+def test_weights_variants(A):
+    """Features with weight <= 0 are skipped (src/lib.rs:1352-1377); non-default weights stay bit-exact."""
+    words = workloads.read_words("eng")[:30000]
+    qs = workloads.misspellings(words, 400, 31, min_len=3, max_len=12)
+    for wkw in (dict(lcs=0.0, case=0.0), dict(ld=1.0, lcs=0.3, prefix=0.0, suffix=0.2, case=0.05)):
+        m = A.VariantModel(workloads.ALPHABET, A.Weights(**wkw))
+        ww = A.Weights(**wkw)
+        o = orc.OracleModel(alphabet_file=workloads.ALPHABET, weights=(ww.ld, ww.lcs, ww.prefix, ww.suffix, ww.case))
+        for w in words:
+            m.add_to_vocabulary(w, None, A.VocabParams())
+            o.add_to_vocabulary(w)
+        m.build()
+        o.build()
+        sp = A.SearchParameters()
+        assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, f"weights {wkw}")
