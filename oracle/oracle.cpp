@@ -42,7 +42,7 @@ namespace orc {
 // src/types.rs:33).  Exact integer arithmetic, so any correct implementation is equivalent.
 // 32-bit limbs, little endian, normalised (no leading zero limbs; zero has n == 0).
 // ------------------------------------------------------------------------------------------
-static const int BIG_LIMBS = 48;  // 1536 bits: > 150 symbols at the largest prime (997)
+static const int BIG_LIMBS = 96;  // 3072 bits: > 300 symbols at the largest prime (997)
 
 struct Big {
   uint32_t n;
