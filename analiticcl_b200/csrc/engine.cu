@@ -239,7 +239,10 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   for (auto& o : b->offsets) o -= base;
 
   // host normalisation (src/anahash.rs:50-80) into fixed-stride rows: len, flags, symbols
-  const uint32_t stride = 256;
+  // row stride from the longest query in bytes (a symbol consumes at least one byte)
+  uint64_t maxbytes = 0;
+  for (uint64_t i = 0; i < n; ++i) maxbytes = std::max<uint64_t>(maxbytes, b->offsets[i + 1] - b->offsets[i]);
+  const uint32_t stride = (uint32_t)((std::min<uint64_t>(maxbytes, 254) + 2 + 15) & ~15ull);
   b->host_flags.assign(n, 0);
   uint8_t* rows = nullptr;
   if (cudaMallocHost(reinterpret_cast<void**>(&rows), std::max<size_t>((size_t)n * stride, 16)) != cudaSuccess) {
@@ -315,11 +318,6 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     *err = e2;
     return fail();
   }
-  for (auto& ev : b->ev)
-    if (cudaEventCreate(&ev) != cudaSuccess) {
-      *err = "cudaEventCreate failed";
-      return fail();
-    }
   if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, stream_) != cudaSuccess) {
     *err = "H2D copy failed";
     return fail();
@@ -338,7 +336,7 @@ void Engine::free_batch(DeviceBatch* b) {
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
                   (void*)b->d_out_count, b->d_scratch, (void*)b->d_work, (void*)b->d_counters})
     if (p) cudaFree(p);
-  for (auto& ev : b->ev)
+  for (auto& ev : b->events)
     if (ev) cudaEventDestroy(ev);
   delete b;
 }
@@ -358,12 +356,21 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   lb.scratch = b->d_scratch;
   lb.work = b->d_work;
   lb.counters = b->d_counters;
+  if (b->runs_recorded >= 1024) b->runs_recorded = 0;  // keep the newest window
+  while (b->events.size() < (size_t)(b->runs_recorded + 1) * 3) {
+    cudaEvent_t ev = nullptr;
+    CU_TRY(cudaEventCreate(&ev));
+    b->events.push_back(ev);
+  }
+  cudaEvent_t* ev = b->events.data() + (size_t)b->runs_recorded * 3;
   CU_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), stream));
-  CU_TRY(cudaEventRecord(b->ev[0], stream));
+  CU_TRY(cudaEventRecord(ev[0], stream));
   CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
-  CU_TRY(cudaEventRecord(b->ev[1], stream));
+  CU_TRY(cudaEventRecord(ev[1], stream));
   CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
-  CU_TRY(cudaEventRecord(b->ev[2], stream));
+  CU_TRY(cudaEventRecord(ev[2], stream));
+  b->last_done = ev[2];
+  ++b->runs_recorded;
   b->ran = true;
   return true;
 }
@@ -373,9 +380,20 @@ bool Engine::timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::stri
     *err = "batch has not been run";
     return false;
   }
-  CU_TRY(cudaEventSynchronize(b->ev[2]));
-  CU_TRY(cudaEventElapsedTime(probe_ms, b->ev[0], b->ev[1]));
-  CU_TRY(cudaEventElapsedTime(score_ms, b->ev[1], b->ev[2]));
+  // averages over the runs since the previous call (CUDA events on the launching stream)
+  CU_TRY(cudaEventSynchronize(b->last_done));
+  double p = 0, s = 0;
+  for (uint32_t r = 0; r < b->runs_recorded; ++r) {
+    float a = 0, c = 0;
+    CU_TRY(cudaEventElapsedTime(&a, b->events[r * 3 + 0], b->events[r * 3 + 1]));
+    CU_TRY(cudaEventElapsedTime(&c, b->events[r * 3 + 1], b->events[r * 3 + 2]));
+    p += a;
+    s += c;
+  }
+  const uint32_t nr = std::max(1u, b->runs_recorded);
+  *probe_ms = (float)(p / nr);
+  *score_ms = (float)(s / nr);
+  b->runs_recorded = 0;
   return true;
 }
 
@@ -385,7 +403,7 @@ bool Engine::counters(DeviceBatch* b, anl_counters* out, std::string* err) {
     return false;
   }
   Counters c;
-  CU_TRY(cudaEventSynchronize(b->ev[2]));
+  CU_TRY(cudaEventSynchronize(b->last_done));
   CU_TRY(cudaMemcpy(&c, b->d_counters, sizeof c, cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof *out);
   out->queries = b->n;
@@ -540,7 +558,7 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
   OutRec* h_out = nullptr;
   CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&h_out), std::max<size_t>((size_t)n * ocap, 1) * sizeof(OutRec)));
   auto body = [&]() -> bool {
-    CU_TRY(cudaEventSynchronize(b->ev[2]));
+    CU_TRY(cudaEventSynchronize(b->last_done));
     if (n) {
       CU_TRY(cudaMemcpyAsync(out_count.data(), b->d_out_count, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
       CU_TRY(cudaMemcpyAsync(qflags.data(), b->d_qflags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));

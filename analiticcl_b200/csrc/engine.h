@@ -39,7 +39,10 @@ struct DeviceBatch {
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
   Counters* d_counters = nullptr;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  // one event triple (start, after probe, after score) per run since the last timings() call
+  std::vector<cudaEvent_t> events;
+  uint32_t runs_recorded = 0;
+  cudaEvent_t last_done = nullptr;  // end event of the most recent run
   bool ran = false;
   uint64_t reruns = 0;
   uint64_t results = 0;

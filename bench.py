@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the variant-lookup hot path on B200 (queries/s, DP GCUPS, roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
+
+Workload (BASELINE.json configs[1], the one `metric` is quoted on): query mode on
+nld.aspell.lexicon + simple.alphabet.tsv with a synthetic Zipf frequency column, 1M synthetic
+OCR-noise queries, max anagram / edit distance 3, late confusables, freq_weight 0.25.
+A "step" is one pass of the hot path over the whole 1M-query batch.
+
+  value : queries/s with the encoded batch already resident in HBM (probe + score kernels on the
+          device, results left in HBM); CUDA events on the launching stream, max over ranks.
+  e2e   : the same metric through the C-ABI call anl_find_variants_batch with HOST buffers:
+          host normalisation, H2D, both kernels, D2H, host post-pass (confusables, cut-off).
+  N > 1 : one process per GPU (torchrun), index replicated, every rank gets its own 1M-query batch
+          (different seed) -> weak scaling, no data-path collective.
+  --impl reference : the CPU oracle (C++ restatement of the reference algorithm, OpenMP over queries,
+          all host threads) on a bounded sample of the same workload.  The Rust reference itself
+          cannot be built in this image (no cargo/rustc).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import workloads  # noqa: E402
+
+METRIC = "queries/sec and DP GCUPS at 1/2/4/8 B200 vs reference CPU (cores stated)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_spec(name, rank=0):
+    """-> dict(lexicon builder, queries, search kwargs, confusables, label)."""
+    if name == "cfg2":
+        return dict(label="cfg2: nld.aspell.lexicon + Zipf freq, 1M OCR-noise queries, k=3, late confusables, freq_weight=0.25",
+                    lexicon=workloads.nld_freq_lexicon(), queries=lambda n: workloads.cfg2_queries(n, 2003 + rank),
+                    n=1_000_000, params=dict(max_anagram_distance=3, max_edit_distance=3, freq_weight=0.25),
+                    confusables=workloads.CFG2_CONFUSABLES)
+    if name == "cfg1":
+        return dict(label="cfg1: eng.aspell.lexicon, 10k synthetic misspellings, k=2",
+                    lexicon=workloads.lexicon_path("eng"), queries=lambda n: workloads.cfg1_queries(n, 1001 + rank),
+                    n=10_000, params=dict(max_anagram_distance=2, max_edit_distance=2), confusables=[])
+    if name == "cfg4":
+        return dict(label="cfg4: eng.aspell.lexicon, 1M misspellings (len>=8, 2-4 edits), k=4",
+                    lexicon=workloads.lexicon_path("eng"), queries=lambda n: workloads.cfg4_queries(n, 4001 + rank),
+                    n=1_000_000, params=dict(max_anagram_distance=4, max_edit_distance=4), confusables=[])
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_oracle(spec):
+    from oracle import orc
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    o.read_lexicon(spec["lexicon"])
+    for pat, w in spec["confusables"]:
+        o.add_to_confusables(pat, w)
+    o.build()
+    return o, orc.make_params(**spec["params"])
+
+
+def time_oracle(o, oparams, queries, threads):
+    blob, offs = workloads.pack(queries)
+    offs_c = offs.ctypes.data_as(C.POINTER(C.c_uint64))
+    t0 = time.perf_counter()
+    total, st = o.find_variants_batch_raw(blob, offs_c, len(queries), oparams, threads)
+    dt = time.perf_counter() - t0
+    return dt, total, st
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference algorithm, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    spec = workload_spec(args.workload)
+    o, oparams = make_oracle(spec)
+    threads = orc.lib().orc_max_threads()
+    sample_n = min(spec["n"], args.ref_sample)
+    queries = spec["queries"](spec["n"])[:sample_n]
+    for _ in range(args.warmup):
+        time_oracle(o, oparams, queries[: max(64, sample_n // 8)], threads)
+    times, cells = [], 0
+    for _ in range(args.steps):
+        dt, _, st = time_oracle(o, oparams, queries, threads)
+        times.append(dt)
+        cells = st.dl_cells
+    tot = sum(times)
+    qps = sample_n * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 multi-limb integer / u8 DP / f64 score", "data": "synthetic",
+        "config": {"workload": spec["label"], "batch_queries": sample_n,
+                   "note": "CPU port of the reference algorithm (oracle/oracle.cpp); the Rust reference cannot be built here"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": f"first {sample_n} queries of the workload per step, OpenMP over queries",
+                         "gcups": cells * 1e-9 / (tot / args.steps)},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import analiticcl_b200 as A
+    from analiticcl_b200 import _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.cuda.current_device()
+    L = _capi.lib()
+
+    spec = workload_spec(args.workload, rank)
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(spec["lexicon"])
+    for pat, w in spec["confusables"]:
+        m.add_to_confusables(pat, w)
+    t0 = time.perf_counter()
+    m.build(device=dev)
+    build_s = time.perf_counter() - t0
+    n = args.queries or spec["n"]
+    queries = spec["queries"](n)
+    sp = A.SearchParameters(**spec["params"])
+    blob, offs = _capi.pack(queries)
+    offs_p = _capi.u64ptr(offs)
+
+    def check(st):
+        if st != 0:
+            raise RuntimeError(L.anl_last_error().decode())
+
+    # ---- value: device-resident batch ----------------------------------------------------------------
+    batch = C.c_void_p()
+    check(L.anl_device_batch_create(m._h, blob, offs_p, n, C.byref(sp.data), C.byref(batch)))
+    stream = torch.cuda.Stream()
+    sh = C.c_void_p(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        check(L.anl_device_batch_run(m._h, batch, sh))
+    torch.cuda.synchronize()
+    pm, sm_ = C.c_float(), C.c_float()
+    check(L.anl_device_batch_timings(m._h, batch, C.byref(pm), C.byref(sm_)))  # resets the per-run event window
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        check(L.anl_device_batch_run(m._h, batch, sh))
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    check(L.anl_device_batch_timings(m._h, batch, C.byref(pm), C.byref(sm_)))
+    probe_ms, score_ms = pm.value, sm_.value
+    ctr = _capi.Counters()
+    check(L.anl_device_batch_counters(m._h, batch, C.byref(ctr)))
+    launches = 2 * args.steps
+
+    # ---- e2e: host buffers through the public C-ABI call ------------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    rs = C.c_void_p()
+    check(L.anl_find_variants_batch(m._h, blob, offs_p, n, C.byref(sp.data), C.byref(rs)))  # warm-up
+    n_results = L.anl_result_set_offsets(rs)[n]
+    L.anl_result_set_free(rs)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rs = C.c_void_p()
+        check(L.anl_find_variants_batch(m._h, blob, offs_p, n, C.byref(sp.data), C.byref(rs)))
+        L.anl_result_set_free(rs)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()
+    launches += 2 * e2e_steps
+    ist = m.index_stats()
+    max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
+    stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
+    out_cap = min(1024, (sp.max_matches + 1) if sp.max_matches else 64)
+    h2d = n * stride
+    d2h = n * (out_cap * 24 + 12)
+
+    # ---- reduce over ranks: max time, summed work --------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s, probe_ms, score_ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(n), float(ctr.dl_cells)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max, probe_ms_max, score_ms_max = t.tolist()
+    total_q, total_cells = w.tolist()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        step_ms = dev_ms_max / args.steps
+        value = total_q / (step_ms / 1000.0)
+        # algorithmic bytes of one launch of each kernel on this rank (DESIGN.md "rooflines")
+        probe_bytes = (n * stride + 16 * (ctr.probes - ctr.deletion_keys) + 8 * ctr.probes + 16 * ctr.probe_steps +
+                       5 * ctr.postings + 24 * ctr.postings + 8 * ctr.anagram_hits + 4 * ctr.instance_pairs + 8 * n)
+        score_bytes = (n * stride + 4 * ctr.instance_pairs + ist["norm_stride"] * ctr.instance_pairs + 8 * ctr.survivors +
+                       24 * ctr.results + 8 * n)
+        dominant = "probe_kernel" if probe_ms >= score_ms else "score_kernel"
+        dom_ms = probe_ms if dominant == "probe_kernel" else score_ms
+        dom_bytes = probe_bytes if dominant == "probe_kernel" else score_bytes
+        achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
+        cpu = None
+        if world == 1 or True:
+            # bounded CPU baseline on rank 0's host cores: the oracle port, all threads
+            from oracle import orc
+            o, oparams = make_oracle(spec)
+            threads = orc.lib().orc_max_threads()
+            sample_n = min(n, args.cpu_sample)
+            dt, _, st = time_oracle(o, oparams, queries[:sample_n], threads)
+            cpu = {"value": sample_n / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                   "sample": f"first {sample_n} queries of the same workload, one pass, OpenMP over queries "
+                             "(C++ restatement of the reference algorithm; the Rust binary cannot be built here)",
+                   "gcups": st.dl_cells * 1e-9 / dt, "seconds": dt}
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 multi-limb integer / u8 DP / f64 score", "data": "synthetic",
+            "config": {"workload": spec["label"], "batch_queries_per_gpu": n, "parallelism": f"query-partitioned replicas x{world}",
+                       "l2": "per-step working set (query rows + hit lists + results ~ GBs) exceeds the 126 MB L2; "
+                             "the index is L2-resident by design", "index": ist, "build_seconds": build_s,
+                       "value_scope": "probe + score/rank kernels, encoded batch resident in HBM, results left in HBM"},
+            "dp_gcups": total_cells * 1e-9 / (score_ms_max / 1000.0),
+            "dp_gcups_of_step": total_cells * 1e-9 / (step_ms / 1000.0),
+            "kernels": {"probe_ms": probe_ms, "score_ms": score_ms, "probe_share": probe_ms / (probe_ms + score_ms),
+                        "probe_algorithmic_bytes": probe_bytes, "score_algorithmic_bytes": score_bytes,
+                        "probe_gbs": probe_bytes / (probe_ms / 1e3) / 1e9, "score_gbs": score_bytes / (score_ms / 1e3) / 1e9,
+                        "probes_per_s": ctr.probes / (probe_ms / 1e3)},
+            "counters": {f: getattr(ctr, f) for f, _ in ctr._fields_},
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "index (Bloom words, table, postings) is L2-resident for this lexicon, so DRAM traffic is far "
+                                 "below the algorithmic bytes; see DESIGN.md and profiles/"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_q / e2e_s_max, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "results_per_step": int(n_results)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    L.anl_device_batch_free(m._h, batch)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--queries", type=int, default=0, help="override the batch size (default: the config's)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--ref-sample", type=int, default=4000)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

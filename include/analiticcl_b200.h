@@ -198,7 +198,8 @@ anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_
 /* One pass of the hot path over the resident batch: probe kernel + score/rank kernel on the
  * model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
 anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream);
-/* Device-side cudaEvent timings (ms) of the last run's two kernels; synchronises. */
+/* Device-side cudaEvent timings (ms) of the two kernels, averaged over the runs since the previous
+ * call (events recorded on the launching stream); synchronises. */
 anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms);
 /* Downloads the results of the last run and finishes them on the host (same output as
  * anl_find_variants_batch). */
