@@ -126,7 +126,7 @@ struct BatchParams {
   int32_t stop_at_exact;
   int32_t finish_mode;    // FINISH_*
   uint32_t hit_cap;       // per-query capacity of the hit list (gather ids)
-  uint32_t out_cap;       // per-query capacity of the result list
+  uint32_t pool_cap;      // capacity of the packed result pool (records, whole launch)
   uint32_t query_stride;  // bytes per encoded query row (multiple of 16): len, flags, symbols
 };
 static const int FINISH_FULL = 0;       // rank, crop, cutoff on device (no confusables)
@@ -136,18 +136,25 @@ static const int FINISH_GATHER = 2;     // emit all survivors in gather order (e
 // query flags
 static const uint8_t Q_FIRST_LOWER = 1;
 
-// result record written by the score/rank kernel
-struct __attribute__((aligned(8))) OutRec {
+// Result record written by the score/rank kernel into the packed result pool.  The frequency is
+// the raw VocabValue.frequency (or 1 when the model has no frequencies); the host divides by the
+// query's max_freq (same IEEE division as src/lib.rs:1523, so the bits are identical).
+struct __attribute__((aligned(16))) OutRec {
   double dist_score;
-  double freq_score;
   uint32_t vocab_id;
-  uint32_t gather_id;
+  uint32_t freq;
+};
+// per-query result header
+struct __attribute__((aligned(16))) OutHead {
+  double max_freq;    // max over all instances within the edit distance (src/lib.rs:1460)
+  uint32_t offset;    // first record in the pool
+  uint32_t count;     // number of records
 };
 
 // per-query status bits
 static const uint32_t QF_EMPTY = 1;         // empty query
 static const uint32_t QF_HIT_OVERFLOW = 2;  // more instance hits than hit_cap: rerun with larger cap
-static const uint32_t QF_OUT_OVERFLOW = 4;  // more results than out_cap: rerun with larger cap
+static const uint32_t QF_OUT_OVERFLOW = 4;  // the packed result pool was exhausted: rerun the score kernel with a larger pool
 static const uint32_t QF_UNSUPPORTED = 8;   // thresholded anagram distance > ANL_MAX_K or enumeration too large
 
 struct Counters {

@@ -438,6 +438,7 @@ bool parse_confusable(const std::string& editscript, double weight, Confusable* 
       if (bar == std::string::npos) break;
       s = bar + 1;
     }
+    for (const std::string& o : ins.options) ins.options32.push_back(decode(o));
     out->script.push_back(ins);
     i = close + 1;
   }

@@ -2,12 +2,13 @@
 //
 // Replaces the reference's per-query call chain find_variants -> find_nearest_anahashes ->
 // gather_instances -> score_and_rank (src/lib.rs:972-1027) with: host normalisation of a whole
-// batch, one H2D copy, probe kernel, score/rank kernel, one D2H copy, and a thin host post-pass
-// (late confusable rescoring + cut-off, src/lib.rs:1592-1622) that only exists when confusables are
-// loaded.  There is no CPU fallback: every failure of the CUDA path is returned as an error.
+// batch, one H2D copy, probe kernel, score/rank kernel, one packed D2H copy, and a thin host
+// post-pass (late confusable rescoring + cut-off, src/lib.rs:1592-1622) that only exists when
+// confusables are loaded.  There is no CPU fallback: every failure of the CUDA path is an error.
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,50 @@
 #include "unicode_tables.h"
 
 namespace anl {
+
+static bool profile_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("ANL_PROFILE") ? 1 : 0;
+  return v == 1;
+}
+struct PhaseTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!profile_enabled()) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[anl profile] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+static unsigned host_threads() {
+  static unsigned n = 0;
+  if (n == 0) {
+    n = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* e = getenv("ANL_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    n = std::min(n, 64u);
+  }
+  return n;
+}
+// fn(thread index, lo, hi) over [0, n) split into contiguous ranges, one per thread
+template <class F>
+static unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F fn) {
+  unsigned nt = host_threads();
+  const uint64_t mp = std::max<uint64_t>(1, min_per_thread);
+  if (n / mp < nt) nt = (unsigned)std::max<uint64_t>(1, n / mp);
+  if (nt <= 1) {
+    fn(0u, (uint64_t)0, n);
+    return 1;
+  }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const uint64_t lo = std::min(n, (uint64_t)t * per), hi = std::min(n, lo + per);
+    th.emplace_back(fn, t, lo, hi);
+  }
+  for (auto& t : th) t.join();
+  return nt;
+}
 
 // DistanceThreshold on the host (src/lib.rs:982-1012); the kernels carry their own copy.
 static uint32_t host_threshold(const anl_distance_threshold& t, size_t len) {
@@ -35,14 +80,27 @@ static uint32_t host_threshold(const anl_distance_threshold& t, size_t len) {
   } while (0)
 
 template <class T>
-bool Engine::dev_alloc(T** p, size_t count, std::string* err) {
+static bool dev_realloc(T** p, size_t count, std::string* err) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
   void* q = nullptr;
   CU_TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
   *p = reinterpret_cast<T*>(q);
   return true;
 }
+template <class T>
+static bool pinned_realloc(T** p, size_t count, std::string* err) {
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  void* q = nullptr;
+  CU_TRY(cudaMallocHost(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  *p = reinterpret_cast<T*>(q);
+  return true;
+}
 
 Engine::~Engine() {
+  for (DeviceBatch* b : cache_) destroy_batch(b);
+  cache_.clear();
   release_index();
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -85,6 +143,8 @@ bool Engine::upload(int device, std::string* err) {
   }
   if (!stream_) CU_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CU_TRY(configure_kernels());
+  for (DeviceBatch* b : cache_) destroy_batch(b);
+  cache_.clear();
   release_index();
 
   const HostIndex& hx = hm_->index;
@@ -122,7 +182,9 @@ bool Engine::upload(int device, std::string* err) {
   ix.have_freq = hm_->have_freq ? 1 : 0;
   ix.mset = nullptr;
   h_ix_ = ix;
-  if (!dev_alloc(&d_ix_, 1, err)) return false;
+  void* dp = nullptr;
+  CU_TRY(cudaMalloc(&dp, sizeof(DeviceIndex)));
+  d_ix_ = reinterpret_cast<DeviceIndex*>(dp);
   CU_TRY(cudaMemcpy(d_ix_, &h_ix_, sizeof h_ix_, cudaMemcpyHostToDevice));
   hm_->index.mset_built_j = 0;
   return true;
@@ -132,7 +194,7 @@ bool Engine::ensure_msets(uint32_t J, std::string* err) {
   if (J == 0 || (hm_->index.mset_built_j >= J && d_mset_)) return true;
   if (!hm_->ensure_msets(J, err)) return false;
   const HostIndex& hx = hm_->index;
-  CU_TRY(cudaStreamSynchronize(stream_));
+  CU_TRY(cudaDeviceSynchronize());
   if (d_mset_) cudaFree(d_mset_);
   d_mset_ = nullptr;
   CU_TRY(cudaMalloc(&d_mset_, std::max<size_t>(hx.mset.size(), 1) * sizeof(MsetEntry)));
@@ -182,17 +244,8 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
   else
     bp->finish_mode = hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP;
   uint32_t hit_cap = 1024;
-  if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = std::max(1, atoi(e));
+  if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = (uint32_t)std::max(1, atoi(e));
   bp->hit_cap = hit_cap;
-  uint32_t out_cap;
-  if (bp->finish_mode == FINISH_GATHER)
-    out_cap = 256;
-  else if (bp->max_matches > 0)
-    out_cap = bp->max_matches + 1;
-  else
-    out_cap = 64;
-  if (const char* e = getenv("ANL_OUT_CAP")) out_cap = std::max(1, atoi(e));
-  bp->out_cap = std::min(out_cap, hit_cap);
   const uint32_t kcap = std::min<uint32_t>(threshold_cap(p.max_anagram_distance), ANL_MAX_K);
   const uint32_t sd = (uint32_t)hm_->index.sd;
   *needed_j = kcap > sd ? kcap - sd : 0;
@@ -200,8 +253,76 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
 }
 
 // ---- batches -------------------------------------------------------------------------------------------
+void Engine::destroy_batch(DeviceBatch* b) {
+  if (!b) return;
+  for (void* p : {(void*)b->h_rows, (void*)b->h_head, (void*)b->h_flags, (void*)b->h_hitcnt, (void*)b->h_out,
+                  (void*)b->h_work})
+    if (p) cudaFreeHost(p);
+  for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
+                  (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters})
+    if (p) cudaFree(p);
+  for (auto& ev : b->events)
+    if (ev) cudaEventDestroy(ev);
+  delete b;
+}
+
+void Engine::free_batch(DeviceBatch* b) {
+  if (!b) return;
+  if (cache_.size() < 2) {
+    b->owned_blob.clear();
+    b->owned_blob.shrink_to_fit();
+    b->blob = nullptr;
+    b->ran = false;
+    b->runs_recorded = 0;
+    cache_.push_back(b);
+  } else {
+    destroy_batch(b);
+  }
+}
+
+bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err) {
+  if (pool_cap <= b->cap_pool && b->d_out) return true;
+  if (!dev_realloc(&b->d_out, pool_cap, err)) return false;
+  if (!pinned_realloc(&b->h_out, pool_cap, err)) return false;
+  b->cap_pool = pool_cap;
+  return true;
+}
+
+bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
+                             std::string* err) {
+  if ((size_t)n * stride > b->cap_rows_bytes || !b->d_rows) {
+    if (!dev_realloc(&b->d_rows, (size_t)n * stride, err)) return false;
+    if (!pinned_realloc(&b->h_rows, (size_t)n * stride, err)) return false;
+    b->cap_rows_bytes = (size_t)n * stride;
+  }
+  if ((size_t)n * hit_cap > b->cap_hits || !b->d_hits) {
+    if (!dev_realloc(&b->d_hits, (size_t)n * hit_cap, err)) return false;
+    b->cap_hits = (size_t)n * hit_cap;
+  }
+  if (n > b->cap_n || !b->d_head) {
+    if (!dev_realloc(&b->d_hit_count, n, err)) return false;
+    if (!dev_realloc(&b->d_qflags, n, err)) return false;
+    if (!dev_realloc(&b->d_head, n, err)) return false;
+    if (!pinned_realloc(&b->h_head, n, err)) return false;
+    if (!pinned_realloc(&b->h_flags, n, err)) return false;
+    if (!pinned_realloc(&b->h_hitcnt, n, err)) return false;
+    b->cap_n = n;
+  }
+  if (!grow_pool(b, pool_cap, err)) return false;
+  if (scratch > b->cap_scratch || !b->d_scratch) {
+    if (!dev_realloc(reinterpret_cast<uint8_t**>(&b->d_scratch), scratch, err)) return false;
+    b->cap_scratch = scratch;
+  }
+  if (!b->d_work) {
+    if (!dev_realloc(&b->d_work, 4, err)) return false;
+    if (!pinned_realloc(&b->h_work, 4, err)) return false;
+    if (!dev_realloc(&b->d_counters, 1, err)) return false;
+  }
+  return true;
+}
+
 DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
-                                  std::string* err, int* status) {
+                                  bool copy_blob, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!uploaded()) {
     *err = "model has not been built";
@@ -213,49 +334,64 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     *status = ANL_ERR_INVALID;
     return nullptr;
   }
-  DeviceBatch* b = new DeviceBatch();
+  BatchParams bp;
+  uint32_t needed_j = 0;
+  if (!make_batch_params(p, &bp, &needed_j, err) || !ensure_msets(needed_j, err)) {
+    *status = ANL_ERR_UNSUPPORTED;
+    return nullptr;
+  }
+  if (cudaSetDevice(device_) != cudaSuccess) {
+    *err = "cudaSetDevice failed";
+    return nullptr;
+  }
+  PhaseTimer pt;
+  DeviceBatch* b = nullptr;
+  if (!cache_.empty()) {
+    b = cache_.back();
+    cache_.pop_back();
+  } else {
+    b = new DeviceBatch();
+  }
   auto fail = [&]() -> DeviceBatch* {
-    free_batch(b);
+    destroy_batch(b);
     return nullptr;
   };
   b->n = (uint32_t)n;
   b->params = p;
-  uint32_t needed_j = 0;
-  if (!make_batch_params(p, &b->bp, &needed_j, err)) {
-    *status = ANL_ERR_UNSUPPORTED;
-    return fail();
-  }
-  if (!ensure_msets(needed_j, err)) {
-    *status = ANL_ERR_UNSUPPORTED;
-    return fail();
-  }
-  if (cudaSetDevice(device_) != cudaSuccess) {
-    *err = "cudaSetDevice failed";
-    return fail();
-  }
-  b->offsets.assign(offsets, offsets + n + 1);
-  b->blob.assign(blob + offsets[0], blob + offsets[n]);
+  b->reruns = 0;
+  b->results = 0;
+  b->offsets.resize(n + 1);
   const uint64_t base = offsets[0];
-  for (auto& o : b->offsets) o -= base;
-
-  // host normalisation (src/anahash.rs:50-80) into fixed-stride rows: len, flags, symbols
+  for (uint64_t i = 0; i <= n; ++i) b->offsets[i] = offsets[i] - base;
+  if (copy_blob) {
+    b->owned_blob.assign(blob + base, blob + offsets[n]);
+    b->blob = b->owned_blob.data();
+  } else {
+    b->blob = blob + base;
+  }
   // row stride from the longest query in bytes (a symbol consumes at least one byte)
   uint64_t maxbytes = 0;
   for (uint64_t i = 0; i < n; ++i) maxbytes = std::max<uint64_t>(maxbytes, b->offsets[i + 1] - b->offsets[i]);
   const uint32_t stride = (uint32_t)((std::min<uint64_t>(maxbytes, 254) + 2 + 15) & ~15ull);
+  bp.query_stride = stride;
+  // packed result pool: sized for the common case, grown (and the score kernel re-run) on overflow
+  uint64_t per_query = bp.finish_mode == FINISH_GATHER ? 64 : (bp.max_matches ? std::min<uint32_t>(bp.max_matches, 24) : 32);
+  if (const char* e = getenv("ANL_POOL_PER_QUERY")) per_query = (uint64_t)std::max(1, atoi(e));
+  const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, std::max<uint64_t>(1024, n * per_query));
+  if (!ensure_capacity(b, (uint32_t)n, stride, bp.hit_cap, pool_cap, score_scratch_bytes(bp, sm_count_, (uint32_t)n), err)) return fail();
+  bp.pool_cap = b->cap_pool;
+  b->bp = bp;
+  pt.lap("create: buffers");
+
+  // host normalisation (src/anahash.rs:50-80) into fixed-stride rows: len, flags, symbols
   b->host_flags.assign(n, 0);
-  uint8_t* rows = nullptr;
-  if (cudaMallocHost(reinterpret_cast<void**>(&rows), std::max<size_t>((size_t)n * stride, 16)) != cudaSuccess) {
-    *err = "cudaMallocHost failed";
-    return fail();
-  }
-  b->h_rows = rows;
+  uint8_t* rows = b->h_rows;
   const Alphabet& ab = hm_->alphabet;
-  const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  auto encode_range = [&](uint64_t lo, uint64_t hi) {
+  const char* text = b->blob;
+  parallel_ranges(n, 2048, [&](unsigned, uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi; ++i) {
       uint8_t* row = rows + (size_t)i * stride;
-      const char* s = b->blob.data() + b->offsets[i];
+      const char* s = text + b->offsets[i];
       const size_t len = (size_t)(b->offsets[i + 1] - b->offsets[i]);
       size_t c = ab.encode_into(s, len, row + 2, stride - 2);
       uint8_t flags = 0;
@@ -282,42 +418,16 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       row[0] = (uint8_t)c;
       row[1] = flags;
     }
-  };
-  if (n < 4096 || nthreads == 1) {
-    encode_range(0, n);
-  } else {
-    std::vector<std::thread> th;
-    const uint64_t per = (n + nthreads - 1) / nthreads;
-    for (unsigned t = 0; t < nthreads; ++t) {
-      const uint64_t lo = t * per, hi = std::min<uint64_t>(n, lo + per);
-      if (lo < hi) th.emplace_back(encode_range, lo, hi);
-    }
-    for (auto& t : th) t.join();
-  }
+  });
   for (uint64_t i = 0; i < n; ++i) {
     if (b->host_flags[i] == 2) {
       *err = "query " + std::to_string(i) + " is longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols";
       *status = ANL_ERR_UNSUPPORTED;
-      return fail();
+      free_batch(b);
+      return nullptr;
     }
   }
-  b->bp.query_stride = stride;
-
-  bool ok = true;
-  std::string e2;
-  ok = ok && dev_alloc(&b->d_rows, (size_t)n * stride, &e2);
-  ok = ok && dev_alloc(&b->d_hits, (size_t)n * b->bp.hit_cap, &e2);
-  ok = ok && dev_alloc(&b->d_hit_count, n, &e2);
-  ok = ok && dev_alloc(&b->d_qflags, n, &e2);
-  ok = ok && dev_alloc(&b->d_out, (size_t)n * b->bp.out_cap, &e2);
-  ok = ok && dev_alloc(&b->d_out_count, n, &e2);
-  ok = ok && dev_alloc(reinterpret_cast<uint8_t**>(&b->d_scratch), score_scratch_bytes(b->bp, sm_count_), &e2);
-  ok = ok && dev_alloc(&b->d_work, 2, &e2);
-  ok = ok && dev_alloc(&b->d_counters, 1, &e2);
-  if (!ok) {
-    *err = e2;
-    return fail();
-  }
+  pt.lap("create: encode");
   if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, stream_) != cudaSuccess) {
     *err = "H2D copy failed";
     return fail();
@@ -326,24 +436,12 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     *err = "H2D sync failed";
     return fail();
   }
+  pt.lap("create: H2D");
   *status = ANL_OK;
   return b;
 }
 
-void Engine::free_batch(DeviceBatch* b) {
-  if (!b) return;
-  if (b->h_rows) cudaFreeHost(b->h_rows);
-  for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
-                  (void*)b->d_out_count, b->d_scratch, (void*)b->d_work, (void*)b->d_counters})
-    if (p) cudaFree(p);
-  for (auto& ev : b->events)
-    if (ev) cudaEventDestroy(ev);
-  delete b;
-}
-
-bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
-  if (!stream) stream = stream_;
-  CU_TRY(cudaSetDevice(device_));
+static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   LaunchBuffers lb;
   lb.queries = b->d_rows;
   lb.qlist = nullptr;
@@ -352,10 +450,17 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   lb.hit_count = b->d_hit_count;
   lb.qflags = b->d_qflags;
   lb.out = b->d_out;
-  lb.out_count = b->d_out_count;
+  lb.out_head = b->d_head;
   lb.scratch = b->d_scratch;
   lb.work = b->d_work;
   lb.counters = b->d_counters;
+  return lb;
+}
+
+bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
+  if (!stream) stream = stream_;
+  CU_TRY(cudaSetDevice(device_));
+  LaunchBuffers lb = launch_buffers(b);
   if (b->runs_recorded >= 1024) b->runs_recorded = 0;  // keep the newest window
   while (b->events.size() < (size_t)(b->runs_recorded + 1) * 3) {
     cudaEvent_t ev = nullptr;
@@ -409,7 +514,9 @@ bool Engine::counters(DeviceBatch* b, anl_counters* out, std::string* err) {
   out->queries = b->n;
   out->deletion_keys = c.deletion_keys;
   out->probes = c.probes;
+  out->filter_pass = c.filter_pass;
   out->probe_steps = c.table_steps;
+  out->postings = c.postings;
   out->anagram_hits = c.anagram_hits;
   out->instance_pairs = c.instance_pairs;
   out->dl_pairs = c.dl_pairs;
@@ -417,8 +524,6 @@ bool Engine::counters(DeviceBatch* b, anl_counters* out, std::string* err) {
   out->survivors = c.survivors;
   out->results = c.results;
   out->reruns = b->reruns;
-  out->filter_pass = c.filter_pass;
-  out->postings = c.postings;
   return true;
 }
 
@@ -427,81 +532,99 @@ static inline double variant_score(const anl_variant& v, float fw) {  // src/typ
   if (fw == 0.0f) return v.dist_score;
   return (v.dist_score + ((double)fw * v.freq_score)) / (1.0 + (double)fw);
 }
-static void rank_variants(std::vector<anl_variant>& r, float fw) {  // src/lib.rs:1667 + src/types.rs:344-365
-  std::stable_sort(r.begin(), r.end(), [fw](const anl_variant& a, const anl_variant& b) {
+template <class It>
+static void rank_variants(It first, It last, float fw) {  // src/lib.rs:1667 + src/types.rs:344-365
+  std::stable_sort(first, last, [fw](const anl_variant& a, const anl_variant& b) {
     if (fw > 0.0f) return variant_score(a, fw) > variant_score(b, fw);
     if (a.dist_score != b.dist_score) return a.dist_score > b.dist_score;
     return a.freq_score > b.freq_score;
   });
 }
-static void crop_variants(std::vector<anl_variant>& r, size_t max_matches, float fw) {  // src/lib.rs:1536-1589
-  if (max_matches == 0 || r.size() <= max_matches) return;
+// src/lib.rs:1536-1589; returns the number of results kept
+static size_t crop_variants(const anl_variant* r, size_t n, size_t max_matches, float fw) {
+  if (max_matches == 0 || n <= max_matches) return n;
   const double last = variant_score(r[max_matches - 1], fw), cropped = variant_score(r[max_matches], fw);
-  if (cropped < last) {
-    r.resize(max_matches);
-    return;
-  }
+  if (cropped < last) return max_matches;
   size_t early = 0, late = 0;
-  for (size_t i = 0; i < r.size(); ++i) {
+  for (size_t i = 0; i < n; ++i) {
     if (r[i].dist_score == cropped && early == 0) early = i;
     if (r[i].dist_score < cropped) {
       late = i;
       break;
     }
   }
-  if (early > 0)
-    r.resize(early + 1);
-  else if (late > 0)
-    r.resize(late + 1);
+  if (early > 0) return early + 1;
+  if (late > 0) return late + 1;
+  return n;
 }
-static void cutoff_variants(std::vector<anl_variant>& r, double cutoff_threshold, float fw) {  // src/lib.rs:1598-1622
-  if (!(cutoff_threshold >= 1.0) || r.empty()) return;
+// src/lib.rs:1598-1622
+static size_t cutoff_variants(const anl_variant* r, size_t n, double cutoff_threshold, float fw) {
+  if (!(cutoff_threshold >= 1.0) || n == 0) return n;
   const double best = variant_score(r[0], fw);
-  for (size_t i = 1; i < r.size(); ++i)
-    if (variant_score(r[i], fw) <= best / cutoff_threshold) {
-      r.resize(i);
-      return;
-    }
+  for (size_t i = 1; i < n; ++i)
+    if (variant_score(r[i], fw) <= best / cutoff_threshold) return i;
+  return n;
 }
 
-void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count,
+void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
                           std::vector<anl_variant>* out) const {
-  out->clear();
-  out->reserve(count);
-  for (uint32_t i = 0; i < count; ++i) out->push_back(anl_variant{recs[i].vocab_id, recs[i].dist_score, recs[i].freq_score, ANL_NO_VIA});
-  if (b.bp.finish_mode == FINISH_FULL) return;
-  const std::string input(b.blob.data() + b.offsets[qi], (size_t)(b.offsets[qi + 1] - b.offsets[qi]));
+  const size_t start = out->size();
+  for (uint32_t i = 0; i < count; ++i) {
+    // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with
+    const double f = (double)recs[i].freq;
+    out->push_back(anl_variant{recs[i].vocab_id, recs[i].dist_score, max_freq > 0.0 ? f / max_freq : f, ANL_NO_VIA});
+  }
+  if (b.bp.finish_mode == FINISH_FULL || count == 0) return;
+  const char* in = b.blob + b.offsets[qi];
+  const size_t inlen = (size_t)(b.offsets[qi + 1] - b.offsets[qi]);
   const float fw = b.params.freq_weight;
-  for (anl_variant& v : *out) v.dist_score *= hm_->compute_confusable_weight(input, v.vocab_id);  // src/lib.rs:1660-1662
-  rank_variants(*out, fw);
-  if (b.bp.finish_mode == FINISH_GATHER) crop_variants(*out, (size_t)b.params.max_matches, fw);
-  cutoff_variants(*out, b.params.cutoff_threshold, fw);
+  anl_variant* v = out->data() + start;
+  bool changed = false;
+  for (uint32_t i = 0; i < count; ++i) {  // rescore_confusables, src/lib.rs:1656-1663
+    const double w = hm_->compute_confusable_weight(in, inlen, v[i].vocab_id);
+    if (w != 1.0) {
+      v[i].dist_score *= w;
+      changed = true;
+    }
+  }
+  size_t n = count;
+  // a stable sort of an already sorted list is the identity: only re-rank when a score changed
+  if (changed || b.bp.finish_mode == FINISH_GATHER) rank_variants(v, v + n, fw);
+  if (b.bp.finish_mode == FINISH_GATHER) n = crop_variants(v, n, (size_t)b.params.max_matches, fw);
+  n = cutoff_variants(v, n, b.params.cutoff_threshold, fw);
+  out->resize(start + n);
 }
 
-bool Engine::rerun_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, const std::vector<uint32_t>& hit_counts,
-                            const std::vector<uint32_t>& out_counts, std::vector<std::vector<OutRec>>* recs,
-                            std::string* err, int* status) {
-  (void)out_counts;
+// Queries with more instance hits than hit_cap: run both kernels again for just those queries with
+// an exact capacity.  Rare (needs > hit_cap candidate instances for one query).
+bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, std::vector<OutHead>* heads,
+                                std::vector<OutRec>* recs, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   const uint32_t m = (uint32_t)which.size();
   uint32_t cap = b->bp.hit_cap;
-  for (uint32_t i = 0; i < m; ++i) cap = std::max(cap, hit_counts[which[i]]);
+  for (uint32_t i : which) cap = std::max(cap, b->h_hitcnt[i]);
   cap = (cap + 31) & ~31u;
   BatchParams bp = b->bp;
   bp.hit_cap = cap;
-  bp.out_cap = cap;  // results <= survivors <= hits: cannot overflow again
+  const uint64_t pool64 = (uint64_t)m * cap;  // results <= survivors <= hits: cannot overflow
+  if (pool64 > 0xFFFFFF00ull) {
+    *err = "hit overflow rerun too large";
+    return false;
+  }
+  bp.pool_cap = (uint32_t)pool64;
   uint32_t* d_qlist = nullptr;
-  uint32_t *d_hits = nullptr, *d_hit_count = nullptr, *d_qflags = nullptr, *d_out_count = nullptr;
+  uint32_t *d_hits = nullptr, *d_hit_count = nullptr, *d_qflags = nullptr;
+  OutHead* d_head = nullptr;
   OutRec* d_out = nullptr;
   uint8_t* d_scratch = nullptr;
   auto cleanup = [&]() {
-    for (void* p : {(void*)d_qlist, (void*)d_hits, (void*)d_hit_count, (void*)d_qflags, (void*)d_out_count, (void*)d_out,
+    for (void* p : {(void*)d_qlist, (void*)d_hits, (void*)d_hit_count, (void*)d_qflags, (void*)d_head, (void*)d_out,
                     (void*)d_scratch})
       if (p) cudaFree(p);
   };
-  bool ok = dev_alloc(&d_qlist, m, err) && dev_alloc(&d_hits, (size_t)m * cap, err) && dev_alloc(&d_hit_count, m, err) &&
-            dev_alloc(&d_qflags, m, err) && dev_alloc(&d_out_count, m, err) && dev_alloc(&d_out, (size_t)m * cap, err) &&
-            dev_alloc(&d_scratch, score_scratch_bytes(bp, sm_count_), err);
+  bool ok = dev_realloc(&d_qlist, m, err) && dev_realloc(&d_hits, (size_t)m * cap, err) && dev_realloc(&d_hit_count, m, err) &&
+            dev_realloc(&d_qflags, m, err) && dev_realloc(&d_head, m, err) && dev_realloc(&d_out, bp.pool_cap, err) &&
+            dev_realloc(&d_scratch, score_scratch_bytes(bp, sm_count_, m), err);
   if (!ok) {
     cleanup();
     return false;
@@ -516,26 +639,26 @@ bool Engine::rerun_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, 
     lb.hit_count = d_hit_count;
     lb.qflags = d_qflags;
     lb.out = d_out;
-    lb.out_count = d_out_count;
+    lb.out_head = d_head;
     lb.scratch = d_scratch;
     lb.work = b->d_work;
     lb.counters = nullptr;
     CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, stream_));
     CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, stream_));
-    std::vector<uint32_t> oc(m), fl(m);
-    CU_TRY(cudaMemcpyAsync(oc.data(), d_out_count, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    std::vector<uint32_t> fl(m);
+    heads->resize(m);
+    unsigned int total = 0;
+    CU_TRY(cudaMemcpyAsync(heads->data(), d_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, stream_));
     CU_TRY(cudaMemcpyAsync(fl.data(), d_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, stream_));
     CU_TRY(cudaStreamSynchronize(stream_));
-    recs->resize(m);
-    for (uint32_t i = 0; i < m; ++i) {
+    for (uint32_t i = 0; i < m; ++i)
       if (fl[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW | QF_UNSUPPORTED)) {
         *err = "internal error: overflow persisted after rerun";
         return false;
       }
-      (*recs)[i].resize(oc[i]);
-      if (oc[i])
-        CU_TRY(cudaMemcpy((*recs)[i].data(), d_out + (size_t)i * cap, oc[i] * sizeof(OutRec), cudaMemcpyDeviceToHost));
-    }
+    recs->resize(total);
+    if (total) CU_TRY(cudaMemcpy(recs->data(), d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost));
     return true;
   };
   ok = body();
@@ -553,104 +676,161 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
   }
   CU_TRY(cudaSetDevice(device_));
   const uint32_t n = b->n;
-  const uint32_t ocap = b->bp.out_cap;
-  std::vector<uint32_t> out_count(n), qflags(n), hit_count(n);
-  OutRec* h_out = nullptr;
-  CU_TRY(cudaMallocHost(reinterpret_cast<void**>(&h_out), std::max<size_t>((size_t)n * ocap, 1) * sizeof(OutRec)));
-  auto body = [&]() -> bool {
+  PhaseTimer pt;
+  // headers + pool cursor first; grow the pool and re-run the score kernel if it overflowed
+  unsigned int total = 0;
+  for (int attempt = 0;; ++attempt) {
     CU_TRY(cudaEventSynchronize(b->last_done));
+    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
     if (n) {
-      CU_TRY(cudaMemcpyAsync(out_count.data(), b->d_out_count, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-      CU_TRY(cudaMemcpyAsync(qflags.data(), b->d_qflags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-      CU_TRY(cudaMemcpyAsync(hit_count.data(), b->d_hit_count, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-      CU_TRY(cudaMemcpyAsync(h_out, b->d_out, (size_t)n * ocap * sizeof(OutRec), cudaMemcpyDeviceToHost, stream_));
+      CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, stream_));
+      CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+      CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
     }
     CU_TRY(cudaStreamSynchronize(stream_));
-    return true;
-  };
-  if (!body()) {
-    cudaFreeHost(h_out);
-    return false;
+    total = n ? b->h_work[2] : 0;
+    if (total <= b->bp.pool_cap) break;
+    if (attempt >= 2) {
+      *err = "internal error: result pool overflow persisted";
+      return false;
+    }
+    // the cursor counted every query's results, so `total` is the exact requirement
+    if (!grow_pool(b, (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, (uint64_t)total + 1024), err)) return false;
+    b->bp.pool_cap = b->cap_pool;
+    LaunchBuffers lb = launch_buffers(b);
+    lb.counters = nullptr;
+    CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream_));
+    CU_TRY(cudaEventRecord(b->last_done, stream_));
+    b->reruns += 1;
   }
-  // queries whose fixed-capacity buffers overflowed are run again with exact capacities
+  if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, stream_));
+  CU_TRY(cudaStreamSynchronize(stream_));
+  pt.lap("fetch: sync+D2H");
+
+  // queries whose hit list overflowed are run again with an exact capacity
   std::vector<uint32_t> which;
   for (uint32_t i = 0; i < n; ++i) {
-    if (qflags[i] & QF_UNSUPPORTED) {
+    const uint32_t f = b->h_flags[i];
+    if (f & QF_UNSUPPORTED) {
       *err = "query " + std::to_string(i) + ": max_anagram_distance after thresholding exceeds " +
              std::to_string(ANL_MAX_K) + " (or its deletion neighbourhood is too large) -- unsupported by the GPU path";
       *status = ANL_ERR_UNSUPPORTED;
-      cudaFreeHost(h_out);
       return false;
     }
-    if (qflags[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW)) which.push_back(i);
+    if (f & QF_HIT_OVERFLOW) which.push_back(i);
   }
-  std::vector<std::vector<OutRec>> rerun_recs;
+  std::vector<OutHead> rr_heads;
+  std::vector<OutRec> rr_recs;
+  std::vector<int32_t> rr_index;
   if (!which.empty()) {
-    // a hit overflow hides the true result count; size by hits, which bounds everything
-    std::vector<uint32_t> hc = hit_count;
-    for (uint32_t i : which) hc[i] = std::max(hc[i], std::max(out_count[i], b->bp.hit_cap));
-    if (!rerun_overflow(b, which, hc, out_count, &rerun_recs, err, status)) {
-      cudaFreeHost(h_out);
-      return false;
-    }
+    if (profile_enabled()) fprintf(stderr, "[anl profile] %zu queries overflowed hit_cap=%u\n", which.size(), b->bp.hit_cap);
+    if (!rerun_hit_overflow(b, which, &rr_heads, &rr_recs, err, status)) return false;
     b->reruns += which.size();
+    rr_index.assign(n, -1);
+    for (size_t k = 0; k < which.size(); ++k) rr_index[which[k]] = (int32_t)k;
   }
-  // assemble (parallel over queries when the confusable post-pass makes it worthwhile)
-  std::vector<int32_t> rerun_index(n, -1);
-  for (size_t k = 0; k < which.size(); ++k) rerun_index[which[k]] = (int32_t)k;
-  out->offsets.assign((size_t)n + 1, 0);
-  out->flags.assign(n, 0);
-  std::vector<std::vector<anl_variant>> per(n);
-  auto work = [&](uint32_t lo, uint32_t hi) {
-    for (uint32_t i = lo; i < hi; ++i) {
-      if (qflags[i] & QF_EMPTY) {
-        if (b->host_flags[i] == 0) out->flags[i] |= 1;
-        continue;
-      }
-      if (rerun_index[i] >= 0) {
-        const auto& r = rerun_recs[rerun_index[i]];
-        finish_query(*b, i, r.data(), (uint32_t)r.size(), &per[i]);
-      } else {
-        finish_query(*b, i, h_out + (size_t)i * ocap, std::min(out_count[i], ocap), &per[i]);
-      }
+  pt.lap("fetch: hit-overflow reruns");
+
+  auto locate = [&](uint32_t i, const OutRec** recs, uint32_t* count, double* maxf) {
+    if (!rr_index.empty() && rr_index[i] >= 0) {
+      const OutHead& h = rr_heads[rr_index[i]];
+      *recs = rr_recs.data() + h.offset;
+      *count = h.count;
+      *maxf = h.max_freq;
+    } else {
+      const OutHead& h = b->h_head[i];
+      *recs = b->h_out + h.offset;
+      *count = h.count;
+      *maxf = h.max_freq;
     }
   };
-  const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  if (n < 2048 || nthreads == 1) {
-    work(0, n);
-  } else {
-    std::vector<std::thread> th;
-    const uint32_t per_t = (n + nthreads - 1) / nthreads;
-    for (unsigned t = 0; t < nthreads; ++t) {
-      const uint32_t lo = t * per_t, hi = std::min<uint32_t>(n, lo + per_t);
-      if (lo < hi) th.emplace_back(work, lo, hi);
-    }
-    for (auto& t : th) t.join();
-  }
-  cudaFreeHost(h_out);
-  uint64_t total = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    out->offsets[i] = total;
-    total += per[i].size();
-  }
-  out->offsets[n] = total;
-  out->variants.resize(total);
+  out->offsets.assign((size_t)n + 1, 0);
+  out->flags.assign(n, 0);
   for (uint32_t i = 0; i < n; ++i)
-    if (!per[i].empty()) memcpy(out->variants.data() + out->offsets[i], per[i].data(), per[i].size() * sizeof(anl_variant));
-  b->results = total;
+    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[i] |= 1;
+
+  if (b->bp.finish_mode == FINISH_FULL) {
+    // counts are final: prefix-sum the offsets, then convert in parallel straight into place
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const OutRec* r;
+      uint32_t c;
+      double mf;
+      locate(i, &r, &c, &mf);
+      out->offsets[i] = tot;
+      tot += c;
+    }
+    out->offsets[n] = tot;
+    out->variants.resize(tot);
+    parallel_ranges(n, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        const OutRec* r;
+        uint32_t c;
+        double mf;
+        locate((uint32_t)i, &r, &c, &mf);
+        anl_variant* dst = out->variants.data() + out->offsets[i];
+        for (uint32_t k = 0; k < c; ++k) {
+          const double f = (double)r[k].freq;
+          dst[k] = anl_variant{r[k].vocab_id, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
+        }
+      }
+    });
+    b->results = tot;
+  } else {
+    // confusable post-pass: each thread finishes a contiguous range of queries into its own buffer
+    const unsigned maxt = host_threads();
+    std::vector<std::vector<anl_variant>> part(maxt);
+    std::vector<std::pair<uint64_t, uint64_t>> ranges(maxt, {0, 0});
+    std::vector<uint32_t> counts(n, 0);
+    parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
+      ranges[t] = {lo, hi};
+      std::vector<anl_variant>& buf = part[t];
+      buf.reserve((size_t)(hi - lo) * 8);
+      for (uint64_t i = lo; i < hi; ++i) {
+        const OutRec* r;
+        uint32_t c;
+        double mf;
+        locate((uint32_t)i, &r, &c, &mf);
+        const size_t before = buf.size();
+        finish_query(*b, i, r, c, mf, &buf);
+        counts[i] = (uint32_t)(buf.size() - before);
+      }
+    });
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      out->offsets[i] = tot;
+      tot += counts[i];
+    }
+    out->offsets[n] = tot;
+    out->variants.resize(tot);
+    for (unsigned t = 0; t < maxt; ++t)
+      if (!part[t].empty())
+        memcpy(out->variants.data() + out->offsets[ranges[t].first], part[t].data(), part[t].size() * sizeof(anl_variant));
+    b->results = tot;
+  }
+  pt.lap("fetch: post-pass+assemble");
   *status = ANL_OK;
   return true;
 }
 
 bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
                                  ResultSet* out, std::string* err, int* status) {
+  const uint64_t CHUNK = 1u << 21;
+  if (n <= CHUNK) {
+    DeviceBatch* b = create_batch(blob, offsets, n, p, false, err, status);
+    if (!b) return false;
+    bool ok = run_batch(b, nullptr, err);
+    if (!ok) *status = ANL_ERR_CUDA;
+    ok = ok && fetch_batch(b, out, err, status);
+    free_batch(b);
+    return ok;
+  }
   out->offsets.assign(1, 0);
   out->variants.clear();
   out->flags.clear();
-  const uint64_t CHUNK = 1u << 20;
-  for (uint64_t lo = 0; lo < n || (n == 0 && lo == 0); lo += CHUNK) {
+  for (uint64_t lo = 0; lo < n; lo += CHUNK) {
     const uint64_t m = std::min(CHUNK, n - lo);
-    DeviceBatch* b = create_batch(blob, offsets + lo, m, p, err, status);
+    DeviceBatch* b = create_batch(blob, offsets + lo, m, p, false, err, status);
     if (!b) return false;
     ResultSet part;
     bool ok = run_batch(b, nullptr, err);
@@ -662,7 +842,6 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
     out->variants.insert(out->variants.end(), part.variants.begin(), part.variants.end());
     for (uint64_t i = 1; i <= m; ++i) out->offsets.push_back(base + part.offsets[i]);
     out->flags.insert(out->flags.end(), part.flags.begin(), part.flags.end());
-    if (n == 0) break;
   }
   *status = ANL_OK;
   return true;

@@ -19,23 +19,34 @@ struct ResultSet {
   std::vector<uint32_t> flags;  // per query: bit 0 = empty input
 };
 
-// Everything one pass over a batch of queries needs on the device.
+// Everything one pass over a batch of queries needs, on the device and in pinned host memory.
+// Buffers are capacity-based and recycled through Engine's cache: steady-state calls allocate nothing.
 struct DeviceBatch {
+  // ---- capacities (what the buffers can hold) ----
+  uint32_t cap_n = 0, cap_pool = 0;
+  size_t cap_rows_bytes = 0, cap_hits = 0, cap_scratch = 0;
+  // ---- current contents ----
   uint32_t n = 0;
   BatchParams bp;
   anl_search_params params;
-  // host copies
-  std::string blob;               // raw queries (needed by the confusable post-pass)
-  std::vector<uint64_t> offsets;  // n + 1
+  const char* blob = nullptr;  // raw queries (borrowed for the duration of the call, or owned_blob)
+  std::string owned_blob;
+  std::vector<uint64_t> offsets;    // n + 1, relative to blob
   std::vector<uint8_t> host_flags;  // per query: 1 = resolved on the host as empty, 2 = unsupported length
-  uint8_t* h_rows = nullptr;        // pinned, [n][stride]
+  // pinned host buffers
+  uint8_t* h_rows = nullptr;   // [cap_n][cap_stride]
+  OutHead* h_head = nullptr;   // [cap_n]
+  uint32_t* h_flags = nullptr; // [cap_n]
+  uint32_t* h_hitcnt = nullptr;// [cap_n]
+  OutRec* h_out = nullptr;     // [cap_pool]
+  unsigned int* h_work = nullptr;  // [4]
   // device buffers
   uint8_t* d_rows = nullptr;
   uint32_t* d_hits = nullptr;
   uint32_t* d_hit_count = nullptr;
   uint32_t* d_qflags = nullptr;
   OutRec* d_out = nullptr;
-  uint32_t* d_out_count = nullptr;
+  OutHead* d_head = nullptr;
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
   Counters* d_counters = nullptr;
@@ -56,11 +67,12 @@ class Engine {
   bool ensure_msets(uint32_t J, std::string* err);
   bool make_batch_params(const anl_search_params& p, BatchParams* bp, uint32_t* needed_j, std::string* err) const;
 
+  // copy_blob: keep a private copy of the query text (device-batch API) or borrow it (one-shot call)
   DeviceBatch* create_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
-                            std::string* err, int* status);
+                            bool copy_blob, std::string* err, int* status);
   bool run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err);
   bool fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* status);
-  void free_batch(DeviceBatch* b);
+  void free_batch(DeviceBatch* b);  // returns the buffers to the cache
   bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);
 
@@ -73,13 +85,15 @@ class Engine {
   cudaStream_t stream() const { return stream_; }
 
  private:
-  // post-pass of one query's device records -> final variants (confusables, re-sort, cut-off)
-  void finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, std::vector<anl_variant>* out) const;
-  bool rerun_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, const std::vector<uint32_t>& hit_counts,
-                      const std::vector<uint32_t>& out_counts, std::vector<std::vector<OutRec>>* recs, std::string* err,
-                      int* status);
-  template <class T>
-  bool dev_alloc(T** p, size_t count, std::string* err);
+  // post-pass of one query's device records -> final variants (confusables, re-sort, cut-off); appends to `out`
+  void finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
+                    std::vector<anl_variant>* out) const;
+  bool rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, std::vector<OutHead>* heads,
+                          std::vector<OutRec>* recs, std::string* err, int* status);
+  bool ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
+                       std::string* err);
+  bool grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err);
+  void destroy_batch(DeviceBatch* b);
   void release_index();
 
   HostModel* hm_;
@@ -90,6 +104,7 @@ class Engine {
   DeviceIndex* d_ix_ = nullptr;
   std::vector<void*> index_allocs_;
   void* d_mset_ = nullptr;
+  std::vector<DeviceBatch*> cache_;  // idle batches whose buffers can be reused
 };
 
 }  // namespace anl

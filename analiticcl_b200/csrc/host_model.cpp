@@ -573,10 +573,71 @@ bool HostModel::has(const char* text, size_t len) const {
   return false;
 }
 
-double HostModel::compute_confusable_weight(const std::string& input, uint64_t candidate) const {
+// Decodes UTF-8 into `out` (at most cap scalars); returns the count, or cap + 1 if it does not fit.
+static size_t decode_small(const char* s, size_t n, char32_t* out, size_t cap) {
+  size_t c = 0, i = 0;
+  while (i < n) {
+    unsigned l;
+    const uint32_t cp = u8decode(s + i, n - i, &l);
+    if (c >= cap) return cap + 1;
+    out[c++] = cp;
+    i += l;
+  }
+  return c;
+}
+
+// src/lib.rs:1733-1756.  Before paying for the edit script, an exact prefilter: every deletion
+// (insertion) chunk of the script consists of characters of the input's (candidate's) "middle" --
+// what is left after stripping the common prefix and suffix -- because the diff runs on the middles
+// and the clean-up passes only merge equalities that lie between edits or rotate an edit over equal
+// characters.  A pattern whose `-[..]` / `+[..]` instruction has no option made of such characters
+// cannot match; if that rules out every confusable, the weight is 1.0 without computing the script.
+double HostModel::compute_confusable_weight(const char* input, size_t len, uint64_t candidate) const {
   double weight = 1.0;
-  if (candidate >= decoder.size()) return weight;
-  std::vector<EditInstruction> script = shortest_edit_script(input, decoder[candidate].text);
+  if (candidate >= decoder.size() || confusables.empty()) return weight;
+  const std::string& cand = decoder[candidate].text;
+  static const size_t CAP = 128;
+  char32_t a[CAP], b[CAP];
+  const size_t na = decode_small(input, len, a, CAP), nb = decode_small(cand.data(), cand.size(), b, CAP);
+  bool need_script = na > CAP || nb > CAP;
+  if (!need_script) {
+    size_t p = 0;
+    while (p < na && p < nb && a[p] == b[p]) ++p;
+    size_t s = 0;
+    while (s < na - p && s < nb - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
+    const char32_t *ma = a + p, *mb = b + p;
+    const size_t la = na - p - s, lb = nb - p - s;
+    auto made_of = [](const std::u32string& opt, const char32_t* mid, size_t n) {
+      for (char32_t c : opt) {
+        bool found = false;
+        for (size_t i = 0; i < n; ++i) found = found || mid[i] == c;
+        if (!found) return false;
+      }
+      return true;
+    };
+    for (const Confusable& c : confusables) {
+      bool possible = true;
+      for (const ConfusableInstr& ins : c.script) {
+        if (ins.op == 0) continue;
+        bool any = false;
+        for (const std::u32string& opt : ins.options32)
+          if (ins.op < 0 ? made_of(opt, ma, la) : made_of(opt, mb, lb)) {
+            any = true;
+            break;
+          }
+        if (!any) {
+          possible = false;
+          break;
+        }
+      }
+      if (possible) {
+        need_script = true;
+        break;
+      }
+    }
+  }
+  if (!need_script) return weight;
+  const std::vector<EditInstruction> script = shortest_edit_script(std::string(input, len), cand);
   for (const Confusable& c : confusables)
     if (confusable_found_in(c, script)) weight *= c.weight;
   return weight;

@@ -68,6 +68,7 @@ class Alphabet {
 struct ConfusableInstr {
   int op;  // -1 deletion, 0 identity, +1 insertion
   std::vector<std::string> options;
+  std::vector<std::u32string> options32;  // the same options as Unicode scalar values (prefilter)
 };
 struct Confusable {  // src/confusables.rs:5-11
   std::vector<ConfusableInstr> script;
@@ -124,7 +125,7 @@ class HostModel {
   uint32_t alphabet_size() const { return (uint32_t)((alphabet.size() + 1) & 0xFF); }  // src/lib.rs:163-165
 
   // -- host post-pass ---------------------------------------------------------------------------------
-  double compute_confusable_weight(const std::string& input, uint64_t candidate) const;  // src/lib.rs:1733-1756
+  double compute_confusable_weight(const char* input, size_t len, uint64_t candidate) const;  // src/lib.rs:1733-1756
 
   Weights weights;
   int debug;

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "device_types.h"
 #include "kernels.h"
 
@@ -489,8 +491,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
              const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
-             uint32_t* __restrict__ out_count, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters,
-             uint32_t ML) {
+             OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, unsigned int* pool_cursor,
+             Counters* counters, uint32_t ML) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -516,7 +518,13 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     if (qi >= nq) break;
     const uint32_t flags = qflags[qi];
     if (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
-      if (lane == 0) out_count[qi] = 0;
+      if (lane == 0) {
+        OutHead h;
+        h.max_freq = 0.0;
+        h.offset = 0;
+        h.count = 0;
+        out_head[qi] = h;
+      }
       continue;
     }
     const uint32_t q = qlist ? qlist[qi] : qi;
@@ -651,7 +659,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         r.dist = score;
         r.freq = freq;
         r.g = g;
-        r.pad = 0;
+        r.pad = (uint32_t)freq;  // raw frequency (exact: u32 or 1.0)
         surv[nsurv + __popc(kmask & lanemask_lt())] = r;
       }
       nsurv += __popc(kmask);
@@ -659,6 +667,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     }
 
     // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
+    // (surv keeps the raw frequency in `pad`; `freq` becomes the normalised score used for ranking)
     __threadfence_block();
     __syncwarp();
     for (uint32_t i = lane; i < nsurv; i += 32) {
@@ -726,22 +735,31 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       }
       n = cut;
     }
-    // ---- emit ---------------------------------------------------------------------------------------------
-    OutRec* oq = out + (size_t)qi * bp.out_cap;
-    for (uint32_t i = lane; i < n && i < bp.out_cap; i += 32) {
-      const SurvRec r = sorted[i];
-      OutRec o;
-      o.dist_score = r.dist;
-      o.freq_score = r.freq;
-      o.vocab_id = __ldg(ix->inst_vocab + r.g);
-      o.gather_id = r.g;
-      oq[i] = o;
+    // ---- emit into the packed pool (one atomic reservation per query) --------------------------------------
+    uint32_t off = 0;
+    if (lane == 0 && n > 0) off = atomicAdd(pool_cursor, n);
+    off = __shfl_sync(FULL, off, 0);
+    const bool fits = (unsigned long long)off + n <= (unsigned long long)bp.pool_cap;
+    if (fits) {
+      for (uint32_t i = lane; i < n; i += 32) {
+        const SurvRec r = sorted[i];
+        OutRec o;
+        o.dist_score = r.dist;
+        o.vocab_id = __ldg(ix->inst_vocab + r.g);
+        o.freq = r.pad;
+        out[off + i] = o;
+      }
     }
     if (lane == 0) {
-      out_count[qi] = n;
-      if (n > bp.out_cap) qflags[qi] = flags | QF_OUT_OVERFLOW;
+      OutHead h;
+      h.max_freq = maxfreq;
+      h.offset = off;
+      h.count = fits ? n : 0;
+      out_head[qi] = h;
+      const uint32_t nf = (flags & ~QF_OUT_OVERFLOW) | (fits ? 0u : QF_OUT_OVERFLOW);
+      if (nf != flags) qflags[qi] = nf;
     }
-    c_res += (lane == 0) ? min(n, bp.out_cap) : 0;
+    c_res += (lane == 0 && fits) ? n : 0;
     __syncwarp();
   }
 
@@ -830,16 +848,20 @@ static long long k2_grid(const DeviceIndex& h_ix, const BatchParams& bp, int sm_
 }
 
 static uint32_t g_scratch_max_len = 0;
-size_t score_scratch_bytes(const BatchParams& bp, int sm_count) {
-  // upper bound on resident warps: 16 CTAs/SM would exceed any smem-limited occupancy here
-  return (size_t)sm_count * 16 * K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
+size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries) {
+  // one survivor list + one sorted copy per resident warp.  Upper bound on resident warps: 16 CTAs/SM
+  // exceeds any smem-limited occupancy here; the launcher never starts more warps than queries.
+  size_t ctas = (size_t)sm_count * 16;
+  const size_t want = ((size_t)n_queries + K2_WARPS - 1) / K2_WARPS;
+  if (want < ctas) ctas = std::max<size_t>(want, 1);
+  return ctas * K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
 }
 
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream) {
   (void)g_scratch_max_len;
   if (lb.n == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, sizeof(unsigned int), stream);
+  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 2 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   const uint32_t R = ring_depth(bp);
   const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
@@ -853,8 +875,9 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
 #define ANL_LAUNCH_K2(RR)                                                                                              \
   score_kernel<RR><<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,    \
-                                                                    lb.hit_count, lb.qflags, lb.out, lb.out_count,    \
-                                                                    scratch, lb.work + 1, lb.counters, h_ix.max_len)
+                                                                    lb.hit_count, lb.qflags, lb.out, lb.out_head,     \
+                                                                    scratch, lb.work + 1, lb.work + 2, lb.counters,   \
+                                                                    h_ix.max_len)
   if (R == 4)
     ANL_LAUNCH_K2(4);
   else if (R == 8)

@@ -15,10 +15,10 @@ struct LaunchBuffers {
   uint32_t* hits;          // [n][hit_cap] gather ids of candidate instances
   uint32_t* hit_count;     // [n]
   uint32_t* qflags;        // [n] QF_* bits
-  OutRec* out;             // [n][out_cap]
-  uint32_t* out_count;     // [n] number of results (may exceed out_cap -> QF_OUT_OVERFLOW)
+  OutRec* out;             // packed result pool, bp.pool_cap records
+  OutHead* out_head;       // [n] per-query header: offset / count into the pool, max_freq
   void* scratch;           // score kernel scratch: score_scratch_bytes(...)
-  unsigned int* work;      // 2 work-stealing counters (zeroed by the launcher)
+  unsigned int* work;      // [0],[1] work-stealing counters, [2] pool cursor (zeroed by the launchers)
   Counters* counters;      // accumulated work counters (zeroed by the caller when wanted)
 };
 
@@ -29,7 +29,7 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 // cropping and cut-off.
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
-size_t score_scratch_bytes(const BatchParams& bp, int sm_count);
+size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
 cudaError_t configure_kernels();
 
 }  // namespace anl
