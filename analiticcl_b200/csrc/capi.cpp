@@ -340,7 +340,7 @@ anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_
   if (!m || !offsets || !params || !out) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int status = ANL_OK;
-  DeviceBatch* b = m->engine.create_batch(blob ? blob : "", offsets, n_queries, *params, true, &err, &status);
+  DeviceBatch* b = m->engine.create_batch(blob ? blob : "", offsets, n_queries, *params, true, true, &err, &status);
   if (!b) return fail(status ? status : ANL_ERR_CUDA, err);
   *out = new anl_device_batch{b};
   return ANL_OK;
@@ -362,7 +362,7 @@ anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_
   anl_result_set* rs = new anl_result_set();
   std::string err;
   int status = ANL_OK;
-  if (!m->engine.fetch_batch(b->b, &rs->rs, &err, &status)) {
+  if (!m->engine.fetch_batch(b->b, &rs->rs, false, &err, &status)) {
     delete rs;
     return fail(status ? status : ANL_ERR_CUDA, err);
   }

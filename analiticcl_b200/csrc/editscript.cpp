@@ -11,6 +11,7 @@
 // This runs on the host by design: at most max_matches short string pairs per query, pointer-chasing
 // string work with no data parallelism worth a kernel.
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -442,18 +443,21 @@ bool parse_confusable(const std::string& editscript, double weight, Confusable* 
     out->script.push_back(ins);
     i = close + 1;
   }
+  out->simple = !out->strictbegin && !out->strictend;
+  for (const ConfusableInstr& ci : out->script) out->simple = out->simple && ci.op != 0;
   return !out->script.empty();
 }
 
 // Confusable::found_in (src/confusables.rs:47-128)
-bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& ref) {
+bool confusable_found_in_views(const Confusable& c, const EditView* ref, size_t nref) {
   const size_t l = c.script.size();
   size_t matches = 0;
-  auto sfx = [](const std::string& s, const std::string& t) {
-    return s.size() >= t.size() && s.compare(s.size() - t.size(), t.size(), t) == 0;
+  auto sfx = [](const EditView& r, const std::string& t) {
+    return r.n >= t.size() && memcmp(r.p + r.n - t.size(), t.data(), t.size()) == 0;
   };
-  auto pfx = [](const std::string& s, const std::string& t) { return s.size() >= t.size() && s.compare(0, t.size(), t) == 0; };
-  for (size_t i = 0; i < ref.size(); ++i) {
+  auto pfx = [](const EditView& r, const std::string& t) { return r.n >= t.size() && memcmp(r.p, t.data(), t.size()) == 0; };
+  auto eq = [](const EditView& r, const std::string& t) { return r.n == t.size() && memcmp(r.p, t.data(), r.n) == 0; };
+  for (size_t i = 0; i < nref; ++i) {
     if (matches >= l) continue;
     const ConfusableInstr& ins = c.script[matches];
     bool found = false;
@@ -461,15 +465,15 @@ bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>
       for (const std::string& s : ins.options) {
         bool ok;
         if (ins.op != 0)
-          ok = sfx(ref[i].text, s);
+          ok = sfx(ref[i], s);
         else if (matches == 0 && matches == l - 1)
-          ok = s == ref[i].text;
+          ok = eq(ref[i], s);
         else if (matches == 0)
-          ok = sfx(ref[i].text, s);
+          ok = sfx(ref[i], s);
         else if (matches == l - 1)
-          ok = pfx(ref[i].text, s);
+          ok = pfx(ref[i], s);
         else
-          ok = s == ref[i].text;
+          ok = eq(ref[i], s);
         if (ok) {
           found = true;
           break;
@@ -480,10 +484,22 @@ bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>
       matches = 0;
       if (c.strictbegin) return false;
     } else if (++matches == l) {
-      return c.strictend ? i == ref.size() - 1 : true;
+      return c.strictend ? i == nref - 1 : true;
     }
   }
   return false;
+}
+
+bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& ref) {
+  EditView small[16];
+  std::vector<EditView> big;
+  EditView* v = small;
+  if (ref.size() > 16) {
+    big.resize(ref.size());
+    v = big.data();
+  }
+  for (size_t i = 0; i < ref.size(); ++i) v[i] = EditView{ref[i].op, ref[i].text.data(), ref[i].text.size()};
+  return confusable_found_in_views(c, v, ref.size());
 }
 
 }  // namespace anl

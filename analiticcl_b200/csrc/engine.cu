@@ -18,6 +18,8 @@
 
 namespace anl {
 
+void confusable_stats(uint64_t* v);
+
 static bool profile_enabled() {
   static int v = -1;
   if (v < 0) v = getenv("ANL_PROFILE") ? 1 : 0;
@@ -243,7 +245,7 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
     bp->finish_mode = FINISH_FULL;
   else
     bp->finish_mode = hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP;
-  uint32_t hit_cap = 1024;
+  uint32_t hit_cap = 2048;
   if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = (uint32_t)std::max(1, atoi(e));
   bp->hit_cap = hit_cap;
   const uint32_t kcap = std::min<uint32_t>(threshold_cap(p.max_anagram_distance), ANL_MAX_K);
@@ -259,10 +261,14 @@ void Engine::destroy_batch(DeviceBatch* b) {
                   (void*)b->h_work})
     if (p) cudaFreeHost(p);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
-                  (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters})
+                  (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
+                  (void*)b->rr_hits, (void*)b->rr_hit_count, (void*)b->rr_qflags, (void*)b->rr_head, (void*)b->rr_out,
+                  (void*)b->rr_scratch})
     if (p) cudaFree(p);
   for (auto& ev : b->events)
     if (ev) cudaEventDestroy(ev);
+  if (b->uploaded) cudaEventDestroy(b->uploaded);
+  if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
 
@@ -322,7 +328,7 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
 }
 
 DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
-                                  bool copy_blob, std::string* err, int* status) {
+                                  bool copy_blob, bool sync, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!uploaded()) {
     *err = "model has not been built";
@@ -356,6 +362,14 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     destroy_batch(b);
     return nullptr;
   };
+  if (!b->stream && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    *err = "cudaStreamCreate failed";
+    return fail();
+  }
+  if (!b->uploaded && cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    *err = "cudaEventCreate failed";
+    return fail();
+  }
   b->n = (uint32_t)n;
   b->params = p;
   b->reruns = 0;
@@ -428,11 +442,11 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     }
   }
   pt.lap("create: encode");
-  if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, stream_) != cudaSuccess) {
+  if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
     *err = "H2D copy failed";
     return fail();
   }
-  if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+  if (cudaEventRecord(b->uploaded, b->stream) != cudaSuccess || (sync && cudaStreamSynchronize(b->stream) != cudaSuccess)) {
     *err = "H2D sync failed";
     return fail();
   }
@@ -458,8 +472,11 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
 }
 
 bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
-  if (!stream) stream = stream_;
   CU_TRY(cudaSetDevice(device_));
+  if (!stream)
+    stream = b->stream;
+  else
+    CU_TRY(cudaStreamWaitEvent(stream, b->uploaded, 0));  // foreign stream: order after the H2D copy
   LaunchBuffers lb = launch_buffers(b);
   if (b->runs_recorded >= 1024) b->runs_recorded = 0;  // keep the newest window
   while (b->events.size() < (size_t)(b->runs_recorded + 1) * 3) {
@@ -612,25 +629,36 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
     return false;
   }
   bp.pool_cap = (uint32_t)pool64;
-  uint32_t* d_qlist = nullptr;
-  uint32_t *d_hits = nullptr, *d_hit_count = nullptr, *d_qflags = nullptr;
-  OutHead* d_head = nullptr;
-  OutRec* d_out = nullptr;
-  uint8_t* d_scratch = nullptr;
-  auto cleanup = [&]() {
-    for (void* p : {(void*)d_qlist, (void*)d_hits, (void*)d_hit_count, (void*)d_qflags, (void*)d_head, (void*)d_out,
-                    (void*)d_scratch})
-      if (p) cudaFree(p);
-  };
-  bool ok = dev_realloc(&d_qlist, m, err) && dev_realloc(&d_hits, (size_t)m * cap, err) && dev_realloc(&d_hit_count, m, err) &&
-            dev_realloc(&d_qflags, m, err) && dev_realloc(&d_head, m, err) && dev_realloc(&d_out, bp.pool_cap, err) &&
-            dev_realloc(&d_scratch, score_scratch_bytes(bp, sm_count_, m), err);
-  if (!ok) {
-    cleanup();
-    return false;
+  // grow-only buffers kept with the batch: steady state allocates (and frees) nothing, which matters
+  // because cudaFree synchronises the device and would stall the other in-flight chunk
+  const size_t scratch = score_scratch_bytes(bp, sm_count_, m);
+  if (m > b->rr_cap_m) {
+    if (!dev_realloc(&b->rr_qlist, m, err) || !dev_realloc(&b->rr_hit_count, m, err) || !dev_realloc(&b->rr_qflags, m, err) ||
+        !dev_realloc(&b->rr_head, m, err))
+      return false;
+    b->rr_cap_m = m;
   }
+  if ((size_t)m * cap > b->rr_cap_hits) {
+    if (!dev_realloc(&b->rr_hits, (size_t)m * cap, err)) return false;
+    b->rr_cap_hits = (size_t)m * cap;
+  }
+  if (bp.pool_cap > b->rr_cap_pool) {
+    if (!dev_realloc(&b->rr_out, bp.pool_cap, err)) return false;
+    b->rr_cap_pool = bp.pool_cap;
+  }
+  if (scratch > b->rr_cap_scratch) {
+    if (!dev_realloc(&b->rr_scratch, scratch, err)) return false;
+    b->rr_cap_scratch = scratch;
+  }
+  uint32_t* d_qlist = b->rr_qlist;
+  uint32_t *d_hits = b->rr_hits, *d_hit_count = b->rr_hit_count, *d_qflags = b->rr_qflags;
+  OutHead* d_head = b->rr_head;
+  OutRec* d_out = b->rr_out;
+  uint8_t* d_scratch = b->rr_scratch;
+  auto cleanup = [&]() {};
+  bool ok = true;
   auto body = [&]() -> bool {
-    CU_TRY(cudaMemcpyAsync(d_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    CU_TRY(cudaMemcpyAsync(d_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
     LaunchBuffers lb;
     lb.queries = b->d_rows;
     lb.qlist = d_qlist;
@@ -643,15 +671,15 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
     lb.scratch = d_scratch;
     lb.work = b->d_work;
     lb.counters = nullptr;
-    CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, stream_));
-    CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, stream_));
+    CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, b->stream));
+    CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, b->stream));
     std::vector<uint32_t> fl(m);
     heads->resize(m);
     unsigned int total = 0;
-    CU_TRY(cudaMemcpyAsync(heads->data(), d_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, stream_));
-    CU_TRY(cudaMemcpyAsync(fl.data(), d_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-    CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, stream_));
-    CU_TRY(cudaStreamSynchronize(stream_));
+    CU_TRY(cudaMemcpyAsync(heads->data(), d_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(fl.data(), d_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
     for (uint32_t i = 0; i < m; ++i)
       if (fl[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW | QF_UNSUPPORTED)) {
         *err = "internal error: overflow persisted after rerun";
@@ -667,7 +695,7 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
   return ok;
 }
 
-bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* status) {
+bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!b->ran) {
     *err = "batch has not been run";
@@ -676,18 +704,19 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
   }
   CU_TRY(cudaSetDevice(device_));
   const uint32_t n = b->n;
+  cudaStream_t st = b->stream;
   PhaseTimer pt;
   // headers + pool cursor first; grow the pool and re-run the score kernel if it overflowed
   unsigned int total = 0;
   for (int attempt = 0;; ++attempt) {
-    CU_TRY(cudaEventSynchronize(b->last_done));
-    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+    CU_TRY(cudaStreamWaitEvent(st, b->last_done, 0));
+    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     if (n) {
-      CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, stream_));
-      CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-      CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+      CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
-    CU_TRY(cudaStreamSynchronize(stream_));
+    CU_TRY(cudaStreamSynchronize(st));
     total = n ? b->h_work[2] : 0;
     if (total <= b->bp.pool_cap) break;
     if (attempt >= 2) {
@@ -699,12 +728,12 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
     b->bp.pool_cap = b->cap_pool;
     LaunchBuffers lb = launch_buffers(b);
     lb.counters = nullptr;
-    CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream_));
-    CU_TRY(cudaEventRecord(b->last_done, stream_));
+    CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, st));
+    CU_TRY(cudaEventRecord(b->last_done, st));
     b->reruns += 1;
   }
-  if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, stream_));
-  CU_TRY(cudaStreamSynchronize(stream_));
+  if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
   pt.lap("fetch: sync+D2H");
 
   // queries whose hit list overflowed are run again with an exact capacity
@@ -744,23 +773,31 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
       *maxf = h.max_freq;
     }
   };
-  out->offsets.assign((size_t)n + 1, 0);
-  out->flags.assign(n, 0);
+  if (!append || out->offsets.empty()) {
+    out->offsets.assign(1, 0);
+    out->variants.clear();
+    out->flags.clear();
+  }
+  const size_t qbase = out->flags.size();      // queries already in `out`
+  const uint64_t vbase = out->variants.size();  // variants already in `out`
+  out->offsets.resize(qbase + (size_t)n + 1);
+  out->flags.resize(qbase + n, 0);
+  uint64_t* offs = out->offsets.data() + qbase;
   for (uint32_t i = 0; i < n; ++i)
-    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[i] |= 1;
+    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[qbase + i] |= 1;
 
   if (b->bp.finish_mode == FINISH_FULL) {
     // counts are final: prefix-sum the offsets, then convert in parallel straight into place
-    uint64_t tot = 0;
+    uint64_t tot = vbase;
     for (uint32_t i = 0; i < n; ++i) {
       const OutRec* r;
       uint32_t c;
       double mf;
       locate(i, &r, &c, &mf);
-      out->offsets[i] = tot;
+      offs[i] = tot;
       tot += c;
     }
-    out->offsets[n] = tot;
+    offs[n] = tot;
     out->variants.resize(tot);
     parallel_ranges(n, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; ++i) {
@@ -768,14 +805,14 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
         uint32_t c;
         double mf;
         locate((uint32_t)i, &r, &c, &mf);
-        anl_variant* dst = out->variants.data() + out->offsets[i];
+        anl_variant* dst = out->variants.data() + offs[i];
         for (uint32_t k = 0; k < c; ++k) {
           const double f = (double)r[k].freq;
           dst[k] = anl_variant{r[k].vocab_id, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
         }
       }
     });
-    b->results = tot;
+    b->results = tot - vbase;
   } else {
     // confusable post-pass: each thread finishes a contiguous range of queries into its own buffer
     const unsigned maxt = host_threads();
@@ -796,55 +833,79 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* 
         counts[i] = (uint32_t)(buf.size() - before);
       }
     });
-    uint64_t tot = 0;
+    uint64_t tot = vbase;
     for (uint32_t i = 0; i < n; ++i) {
-      out->offsets[i] = tot;
+      offs[i] = tot;
       tot += counts[i];
     }
-    out->offsets[n] = tot;
+    offs[n] = tot;
     out->variants.resize(tot);
     for (unsigned t = 0; t < maxt; ++t)
       if (!part[t].empty())
-        memcpy(out->variants.data() + out->offsets[ranges[t].first], part[t].data(), part[t].size() * sizeof(anl_variant));
-    b->results = tot;
+        memcpy(out->variants.data() + offs[ranges[t].first], part[t].data(), part[t].size() * sizeof(anl_variant));
+    b->results = tot - vbase;
   }
   pt.lap("fetch: post-pass+assemble");
+  if (profile_enabled() && b->bp.finish_mode != FINISH_FULL) {
+    uint64_t v[4];
+    confusable_stats(v);
+    fprintf(stderr, "[anl profile] confusable checks %llu, prefilter pass %llu (ascii), single-edit fast %llu, full script %llu\n",
+            (unsigned long long)v[0], (unsigned long long)v[1], (unsigned long long)v[2], (unsigned long long)v[3]);
+  }
   *status = ANL_OK;
   return true;
 }
 
 bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
                                  ResultSet* out, std::string* err, int* status) {
-  const uint64_t CHUNK = 1u << 21;
-  if (n <= CHUNK) {
-    DeviceBatch* b = create_batch(blob, offsets, n, p, false, err, status);
-    if (!b) return false;
-    bool ok = run_batch(b, nullptr, err);
-    if (!ok) *status = ANL_ERR_CUDA;
-    ok = ok && fetch_batch(b, out, err, status);
-    free_batch(b);
-    return ok;
-  }
+  // Chunks are pipelined over two batches with their own streams: while the GPU works on chunk i,
+  // the host finishes chunk i-1 (D2H, confusable post-pass, assembly) and encodes chunk i+1.
+  uint64_t CHUNK = 1u << 17;
+  if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
   out->offsets.assign(1, 0);
   out->variants.clear();
   out->flags.clear();
-  for (uint64_t lo = 0; lo < n; lo += CHUNK) {
-    const uint64_t m = std::min(CHUNK, n - lo);
-    DeviceBatch* b = create_batch(blob, offsets + lo, m, p, false, err, status);
-    if (!b) return false;
-    ResultSet part;
-    bool ok = run_batch(b, nullptr, err);
-    if (!ok) *status = ANL_ERR_CUDA;
-    ok = ok && fetch_batch(b, &part, err, status);
-    free_batch(b);
-    if (!ok) return false;
-    const uint64_t base = out->variants.size();
-    out->variants.insert(out->variants.end(), part.variants.begin(), part.variants.end());
-    for (uint64_t i = 1; i <= m; ++i) out->offsets.push_back(base + part.offsets[i]);
-    out->flags.insert(out->flags.end(), part.flags.begin(), part.flags.end());
+  if (n > CHUNK) {
+    out->variants.reserve((size_t)n * 8);
+    out->offsets.reserve((size_t)n + 1);
+    out->flags.reserve((size_t)n);
   }
-  *status = ANL_OK;
-  return true;
+  DeviceBatch* inflight = nullptr;
+  bool ok = true;
+  for (uint64_t lo = 0; ok && (lo < n || (n == 0 && lo == 0)); lo += CHUNK) {
+    const uint64_t m = std::min(CHUNK, n - lo);
+    DeviceBatch* b = create_batch(blob, offsets + lo, m, p, false, false, err, status);
+    ok = b != nullptr;
+    if (ok && !run_batch(b, nullptr, err)) {
+      *status = ANL_ERR_CUDA;
+      ok = false;
+    }
+    if (inflight) {
+      std::string e2;
+      int s2 = ANL_OK;
+      if (!fetch_batch(inflight, out, true, &e2, &s2) && ok) {
+        ok = false;
+        *err = e2;
+        *status = s2;
+      }
+      free_batch(inflight);
+      inflight = nullptr;
+    }
+    if (ok)
+      inflight = b;
+    else if (b) {
+      cudaStreamSynchronize(b->stream);
+      free_batch(b);
+    }
+    if (n == 0) break;
+  }
+  if (inflight) {
+    if (ok) ok = fetch_batch(inflight, out, true, err, status);
+    else cudaStreamSynchronize(inflight->stream);
+    free_batch(inflight);
+  }
+  if (ok) *status = ANL_OK;
+  return ok;
 }
 
 }  // namespace anl

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -13,9 +16,44 @@
 
 namespace anl {
 
+// Growable array of PODs that does not value-initialise on resize (a std::vector would memset
+// hundreds of MB that are overwritten immediately, on one thread).
+template <class T>
+class PodBuffer {
+ public:
+  PodBuffer() = default;
+  PodBuffer(const PodBuffer&) = delete;
+  PodBuffer& operator=(const PodBuffer&) = delete;
+  ~PodBuffer() { free(p_); }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  void clear() { n_ = 0; }
+  void reserve(size_t c) {
+    if (c <= cap_) return;
+    T* q = static_cast<T*>(realloc(p_, c * sizeof(T)));
+    if (!q) throw std::bad_alloc();
+    p_ = q;
+    cap_ = c;
+  }
+  void resize(size_t n) {
+    if (n > cap_) reserve(std::max(n, cap_ + cap_ / 2));
+    n_ = n;
+  }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  const T* begin() const { return p_; }
+  const T* end() const { return p_ + n_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
+
 struct ResultSet {
   std::vector<uint64_t> offsets;  // n + 1
-  std::vector<anl_variant> variants;
+  PodBuffer<anl_variant> variants;
   std::vector<uint32_t> flags;  // per query: bit 0 = empty input
 };
 
@@ -50,6 +88,17 @@ struct DeviceBatch {
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
   Counters* d_counters = nullptr;
+  // buffers of the hit-overflow rerun (queries with more than hit_cap candidate instances), grow-only
+  uint32_t* rr_qlist = nullptr;
+  uint32_t* rr_hits = nullptr;
+  uint32_t* rr_hit_count = nullptr;
+  uint32_t* rr_qflags = nullptr;
+  OutHead* rr_head = nullptr;
+  OutRec* rr_out = nullptr;
+  uint8_t* rr_scratch = nullptr;
+  size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;
+  cudaStream_t stream = nullptr;    // this batch's own stream (copies + default launches)
+  cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
   // one event triple (start, after probe, after score) per run since the last timings() call
   std::vector<cudaEvent_t> events;
   uint32_t runs_recorded = 0;
@@ -68,10 +117,12 @@ class Engine {
   bool make_batch_params(const anl_search_params& p, BatchParams* bp, uint32_t* needed_j, std::string* err) const;
 
   // copy_blob: keep a private copy of the query text (device-batch API) or borrow it (one-shot call)
+  // sync: wait for the H2D copy before returning (otherwise it is ordered before the kernels by an event)
   DeviceBatch* create_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
-                            bool copy_blob, std::string* err, int* status);
+                            bool copy_blob, bool sync, std::string* err, int* status);
   bool run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err);
-  bool fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* status);
+  // append: add this batch's queries after the ones already in `out` (pipelined chunks)
+  bool fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status);
   void free_batch(DeviceBatch* b);  // returns the buffers to the cache
   bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);

@@ -2,6 +2,7 @@
 #include "host_model.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -195,6 +196,8 @@ uint64_t HostModel::add_to_vocabulary(const char* text, size_t len, bool has_fre
     unsigned l;
     e.first_lower = anl_unicode::is_lowercase(u8decode(text, len, &l));
   }
+  e.ascii = true;
+  for (size_t i = 0; i < len; ++i) e.ascii = e.ascii && ((unsigned char)text[i] < 0x80);
   encoder.emplace(std::move(key), id);
   decoder.push_back(std::move(e));
   built = false;
@@ -267,6 +270,7 @@ bool HostModel::add_to_confusables(const std::string& editscript, double weight,
     return false;
   }
   confusables.push_back(c);
+  all_confusables_simple = all_confusables_simple && c.simple;
   return true;
 }
 
@@ -592,51 +596,98 @@ static size_t decode_small(const char* s, size_t n, char32_t* out, size_t cap) {
 // and the clean-up passes only merge equalities that lie between edits or rotate an edit over equal
 // characters.  A pattern whose `-[..]` / `+[..]` instruction has no option made of such characters
 // cannot match; if that rules out every confusable, the weight is 1.0 without computing the script.
+template <class Ch, class Opt>
+static bool confusable_possible(const std::vector<Confusable>& confusables, const Ch* ma, size_t la, const Ch* mb, size_t lb,
+                                Opt options_of) {
+  auto made_of = [](const auto& opt, const Ch* mid, size_t n) {
+    for (auto c : opt) {
+      const uint32_t cv = sizeof(c) == 1 ? (uint32_t)(unsigned char)c : (uint32_t)c;
+      bool found = false;
+      for (size_t i = 0; i < n; ++i) found = found || (uint32_t)mid[i] == cv;
+      if (!found) return false;
+    }
+    return true;
+  };
+  for (const Confusable& c : confusables) {
+    bool possible = true;
+    for (const ConfusableInstr& ins : c.script) {
+      if (ins.op == 0) continue;
+      bool any = false;
+      for (const auto& opt : options_of(ins))
+        if (ins.op < 0 ? made_of(opt, ma, la) : made_of(opt, mb, lb)) {
+          any = true;
+          break;
+        }
+      if (!any) {
+        possible = false;
+        break;
+      }
+    }
+    if (possible) return true;
+  }
+  return false;
+}
+
+static std::atomic<uint64_t> g_cw_calls{0}, g_cw_prefilter_pass{0}, g_cw_fast{0}, g_cw_full{0};
+void confusable_stats(uint64_t* v) {
+  v[0] = g_cw_calls.exchange(0);
+  v[1] = g_cw_prefilter_pass.exchange(0);
+  v[2] = g_cw_fast.exchange(0);
+  v[3] = g_cw_full.exchange(0);
+}
+static const bool g_cw_count = getenv("ANL_PROFILE") != nullptr;
+
 double HostModel::compute_confusable_weight(const char* input, size_t len, uint64_t candidate) const {
   double weight = 1.0;
+  if (g_cw_count) g_cw_calls.fetch_add(1, std::memory_order_relaxed);
   if (candidate >= decoder.size() || confusables.empty()) return weight;
-  const std::string& cand = decoder[candidate].text;
-  static const size_t CAP = 128;
-  char32_t a[CAP], b[CAP];
-  const size_t na = decode_small(input, len, a, CAP), nb = decode_small(cand.data(), cand.size(), b, CAP);
-  bool need_script = na > CAP || nb > CAP;
-  if (!need_script) {
+  const VocabEntry& ce = decoder[candidate];
+  const std::string& cand = ce.text;
+  bool input_ascii = true;
+  for (size_t i = 0; i < len; ++i) input_ascii = input_ascii && ((unsigned char)input[i] < 0x80);
+  if (input_ascii && ce.ascii) {
+    // bytes are scalar values: work in place
+    const unsigned char* a = reinterpret_cast<const unsigned char*>(input);
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(cand.data());
+    const size_t na = len, nb = cand.size();
     size_t p = 0;
     while (p < na && p < nb && a[p] == b[p]) ++p;
     size_t s = 0;
     while (s < na - p && s < nb - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
-    const char32_t *ma = a + p, *mb = b + p;
     const size_t la = na - p - s, lb = nb - p - s;
-    auto made_of = [](const std::u32string& opt, const char32_t* mid, size_t n) {
-      for (char32_t c : opt) {
-        bool found = false;
-        for (size_t i = 0; i < n; ++i) found = found || mid[i] == c;
-        if (!found) return false;
-      }
-      return true;
-    };
-    for (const Confusable& c : confusables) {
-      bool possible = true;
-      for (const ConfusableInstr& ins : c.script) {
-        if (ins.op == 0) continue;
-        bool any = false;
-        for (const std::u32string& opt : ins.options32)
-          if (ins.op < 0 ? made_of(opt, ma, la) : made_of(opt, mb, lb)) {
-            any = true;
-            break;
-          }
-        if (!any) {
-          possible = false;
-          break;
-        }
-      }
-      if (possible) {
-        need_script = true;
-        break;
-      }
+    if (!confusable_possible(confusables, a + p, la, b + p, lb,
+                             [](const ConfusableInstr& i) -> const std::vector<std::string>& { return i.options; }))
+      return weight;
+    if (g_cw_count) g_cw_prefilter_pass.fetch_add(1, std::memory_order_relaxed);
+    if (la <= 1 && lb <= 1 && all_confusables_simple) {
+      if (g_cw_count) g_cw_fast.fetch_add(1, std::memory_order_relaxed);
+      // a single substitution / insertion / deletion: the script is [=prefix] [-x] [+y] [=suffix]; the
+      // clean-up passes can only slide the one-character edit, which does not change the edit chunks
+      EditView v[4];
+      size_t nv = 0;
+      if (p) v[nv++] = EditView{0, input, p};
+      if (la) v[nv++] = EditView{-1, input + p, la};
+      if (lb) v[nv++] = EditView{1, cand.data() + p, lb};
+      if (s) v[nv++] = EditView{0, input + na - s, s};
+      for (const Confusable& c : confusables)
+        if (confusable_found_in_views(c, v, nv)) weight *= c.weight;
+      return weight;
+    }
+  } else {
+    static const size_t CAP = 128;
+    char32_t a[CAP], b[CAP];
+    const size_t na = decode_small(input, len, a, CAP), nb = decode_small(cand.data(), cand.size(), b, CAP);
+    if (na <= CAP && nb <= CAP) {
+      size_t p = 0;
+      while (p < na && p < nb && a[p] == b[p]) ++p;
+      size_t s = 0;
+      while (s < na - p && s < nb - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
+      if (!confusable_possible(confusables, a + p, na - p - s, b + p, nb - p - s,
+                               [](const ConfusableInstr& i) -> const std::vector<std::u32string>& { return i.options32; }))
+        return weight;
     }
   }
-  if (!need_script) return weight;
+  if (g_cw_count) g_cw_full.fetch_add(1, std::memory_order_relaxed);
   const std::vector<EditInstruction> script = shortest_edit_script(std::string(input, len), cand);
   for (const Confusable& c : confusables)
     if (confusable_found_in(c, script)) weight *= c.weight;

@@ -40,6 +40,7 @@ struct VocabEntry {  // src/vocab.rs:7-29
   uint8_t tokencount = 1;
   uint8_t vocabtype = VT_NONE;
   bool first_lower = false;  // char::is_lowercase of the first char (src/lib.rs:1367-1374)
+  bool ascii = false;        // text is pure ASCII (bytes == Unicode scalar values)
 };
 
 // Greedy alphabet matcher (src/anahash.rs:16-80) with a first-byte dispatch table instead of
@@ -74,6 +75,7 @@ struct Confusable {  // src/confusables.rs:5-11
   std::vector<ConfusableInstr> script;
   double weight = 1.0;
   bool strictbegin = false, strictend = false;
+  bool simple = false;  // only insertions / deletions, no anchors: matching depends on edit chunks alone
 };
 
 // Host copy of the built index (used for has(), statistics and to size device buffers).
@@ -136,6 +138,7 @@ class HostModel {
   bool have_freq = false;
   std::vector<Confusable> confusables;
   bool confusables_before_pruning = false;
+  bool all_confusables_simple = true;
   bool built = false;
   HostIndex index;
 };
@@ -145,6 +148,12 @@ struct EditInstruction {
   int op;  // -1 deletion, 0 identity, +1 insertion
   std::string text;
 };
+struct EditView {  // non-owning form of an edit instruction
+  int op;
+  const char* p;
+  size_t n;
+};
+bool confusable_found_in_views(const Confusable& c, const EditView* ref, size_t nref);
 std::vector<EditInstruction> shortest_edit_script(const std::string& src, const std::string& dst);
 bool parse_confusable(const std::string& editscript, double weight, Confusable* out);
 bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& script);  // src/confusables.rs:47-128

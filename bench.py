@@ -257,9 +257,8 @@ def run_ours(args):
     ist = m.index_stats()
     max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
     stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
-    out_cap = min(1024, (sp.max_matches + 1) if sp.max_matches else 64)
-    h2d = n * stride
-    d2h = n * (out_cap * 24 + 12)
+    h2d = n * stride                       # encoded query rows
+    d2h = n * (16 + 4 + 4) + 16 * int(n_results) + 16  # per-query headers/flags/hit counts + packed 16-byte records
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s, probe_ms, score_ms], dtype=torch.float64, device="cuda")

@@ -12,7 +12,7 @@ m.build()
 qs = workloads.cfg2_queries(1_000_000, 2003)[:n]
 sp = A.SearchParameters(freq_weight=0.25)
 blob, offs = _capi.pack(qs); L = _capi.lib()
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", "3"))):
     rs = C.c_void_p(); t = time.perf_counter()
     st = L.anl_find_variants_batch(m._h, blob, _capi.u64ptr(offs), n, C.byref(sp.data), C.byref(rs))
     dt = time.perf_counter() - t
