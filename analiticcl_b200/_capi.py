@@ -99,6 +99,8 @@ SIGNATURES = {
     "anl_model_max_key_bits": (_u32, [_vp]),
     "anl_normalize": (_i64, [_vp, _cp, _sz, _P(C.c_uint8), _sz]),
     "anl_anahash": (_i64, [_vp, _cp, _sz, _P(_u64), _sz]),
+    "anl_shortest_edit_script": (_i64, [_cp, _sz, _cp, _sz, C.c_char_p, _sz]),
+    "anl_confusable_found_in": (_i32, [_cp, _cp, _sz, _cp, _sz]),
     "anl_find_variants_batch": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_result_set_len": (_u64, [_vp]),
     "anl_result_set_get": (_P(Variant), [_vp, _u64, _P(_u64)]),

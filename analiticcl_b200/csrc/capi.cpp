@@ -1,4 +1,5 @@
 // capi.cpp -- the extern "C" boundary declared in include/analiticcl_b200.h.
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -207,6 +208,26 @@ int64_t anl_anahash(const anl_model* m, const char* text, size_t len, uint64_t* 
   std::vector<uint64_t> v = m->host.anahash_limbs(text, len);
   for (size_t i = 0; i < v.size() && i < cap; ++i) limbs[i] = v[i];
   return (int64_t)v.size();
+}
+
+int64_t anl_shortest_edit_script(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap) {
+  std::string text;
+  for (const EditInstruction& e : shortest_edit_script(std::string(src, src_len), std::string(dst, dst_len))) {
+    text += e.op == 0 ? "=[" : (e.op > 0 ? "+[" : "-[");
+    text += e.text;
+    text += "]";
+  }
+  if (out && cap) {
+    const size_t n = std::min(text.size(), cap - 1);
+    memcpy(out, text.data(), n);
+    out[n] = 0;
+  }
+  return (int64_t)text.size();
+}
+int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src_len, const char* dst, size_t dst_len) {
+  Confusable c;
+  if (!pattern || !parse_confusable(pattern, 1.0, &c)) return -1;
+  return confusable_found_in(c, shortest_edit_script(std::string(src, src_len), std::string(dst, dst_len))) ? 1 : 0;
 }
 
 // ---- lookup ------------------------------------------------------------------------------------------

@@ -21,92 +21,110 @@
 namespace anl {
 namespace {
 
-typedef std::u32string Str;
-enum Op { DEL = -1, EQ = 0, INS = 1 };
-struct Chunk {
+// A diff is an ordered partition of both strings, so a script is stored as (op, length) pairs; the
+// text of a chunk is implied by its position: EQ consumes `len` scalars of both strings, DEL of the
+// source, INS of the destination.  Every pass below works on lengths plus comparisons inside the
+// two base arrays: no allocation, no copying of text.
+enum Op : int8_t { DEL = -1, EQ = 0, INS = 1 };
+struct Seg {
   Op op;
-  Str text;
+  int len;
 };
-typedef std::vector<Chunk> Script;
+typedef std::vector<Seg> Script;
+typedef const char32_t* Txt;
 
-Str decode(const std::string& s) {
-  Str out;
+struct Ctx {
+  Txt a;  // source scalars
+  Txt b;  // destination scalars
+};
+
+size_t decode(const char* s, size_t n, std::vector<char32_t>* out) {
+  out->clear();
   size_t i = 0;
-  while (i < s.size()) {
+  while (i < n) {
     unsigned char c = (unsigned char)s[i];
     unsigned l = c < 0x80 ? 1 : ((c & 0xE0) == 0xC0 ? 2 : ((c & 0xF0) == 0xE0 ? 3 : ((c & 0xF8) == 0xF0 ? 4 : 1)));
-    if (i + l > s.size()) l = (unsigned)(s.size() - i);
+    if (i + l > n) l = (unsigned)(n - i);
     char32_t cp = l == 1 ? c : (c & (0xFFu >> (l + 1)));
     for (unsigned k = 1; k < l; ++k) cp = (cp << 6) | ((unsigned char)s[i + k] & 0x3F);
-    out.push_back(cp);
+    out->push_back(cp);
     i += l;
   }
-  return out;
+  return out->size();
 }
-std::string encode(const Str& v) {
-  std::string out;
-  for (char32_t cp : v) {
+std::u32string decode32(const std::string& s) {
+  std::vector<char32_t> v;
+  decode(s.data(), s.size(), &v);
+  return std::u32string(v.begin(), v.end());
+}
+void append_utf8(std::string* out, Txt t, int n) {
+  for (int i = 0; i < n; ++i) {
+    const char32_t cp = t[i];
     if (cp < 0x80) {
-      out += (char)cp;
+      *out += (char)cp;
     } else if (cp < 0x800) {
-      out += (char)(0xC0 | (cp >> 6));
-      out += (char)(0x80 | (cp & 0x3F));
+      *out += (char)(0xC0 | (cp >> 6));
+      *out += (char)(0x80 | (cp & 0x3F));
     } else if (cp < 0x10000) {
-      out += (char)(0xE0 | (cp >> 12));
-      out += (char)(0x80 | ((cp >> 6) & 0x3F));
-      out += (char)(0x80 | (cp & 0x3F));
+      *out += (char)(0xE0 | (cp >> 12));
+      *out += (char)(0x80 | ((cp >> 6) & 0x3F));
+      *out += (char)(0x80 | (cp & 0x3F));
     } else {
-      out += (char)(0xF0 | (cp >> 18));
-      out += (char)(0x80 | ((cp >> 12) & 0x3F));
-      out += (char)(0x80 | ((cp >> 6) & 0x3F));
-      out += (char)(0x80 | (cp & 0x3F));
+      *out += (char)(0xF0 | (cp >> 18));
+      *out += (char)(0x80 | ((cp >> 12) & 0x3F));
+      *out += (char)(0x80 | ((cp >> 6) & 0x3F));
+      *out += (char)(0x80 | (cp & 0x3F));
     }
   }
-  return out;
 }
 
-size_t prefix_len(const Str& a, const Str& b) {
-  size_t n = std::min(a.size(), b.size()), i = 0;
-  while (i < n && a[i] == b[i]) ++i;
+inline int common_prefix(Txt x, int nx, Txt y, int ny) {
+  const int n = std::min(nx, ny);
+  int i = 0;
+  while (i < n && x[i] == y[i]) ++i;
   return i;
 }
-size_t suffix_len(const Str& a, const Str& b) {
-  size_t n = std::min(a.size(), b.size()), i = 0;
-  while (i < n && a[a.size() - 1 - i] == b[b.size() - 1 - i]) ++i;
+inline int common_suffix(Txt x, int nx, Txt y, int ny) {
+  const int n = std::min(nx, ny);
+  int i = 0;
+  while (i < n && x[nx - 1 - i] == y[ny - 1 - i]) ++i;
   return i;
 }
-bool ends_with(const Str& s, const Str& t) { return s.size() >= t.size() && s.compare(s.size() - t.size(), t.size(), t) == 0; }
-bool starts_with(const Str& s, const Str& t) { return s.size() >= t.size() && s.compare(0, t.size(), t) == 0; }
+inline bool same(Txt x, Txt y, int n) {
+  for (int i = 0; i < n; ++i)
+    if (x[i] != y[i]) return false;
+  return true;
+}
+// first occurrence of needle in hay, or -1
+inline int find_in(Txt hay, int nh, Txt needle, int nn) {
+  if (nn == 0) return 0;
+  for (int i = 0; i + nn <= nh; ++i)
+    if (same(hay + i, needle, nn)) return i;
+  return -1;
+}
+// length of the longest suffix of x that is a prefix of y
+inline int overlap_len(Txt x, int nx, Txt y, int ny) {
+  for (int l = std::min(nx, ny); l >= 1; --l)
+    if (same(x + nx - l, y, l)) return l;
+  return 0;
+}
 
-// length of the longest suffix of `a` that is a prefix of `b`
-size_t overlap_len(Str a, Str b) {
-  if (a.empty() || b.empty()) return 0;
-  if (a.size() > b.size())
-    a = a.substr(a.size() - b.size());
-  else if (a.size() < b.size())
-    b = b.substr(0, a.size());
-  const size_t n = a.size();
-  if (a == b) return n;
-  size_t best = 0, len = 1;
-  for (;;) {
-    Str pat = a.substr(n - len);
-    size_t found = b.find(pat);
-    if (found == Str::npos) return best;
-    len += found;
-    if (found == 0 || a.substr(n - len) == b.substr(0, len)) {
-      best = len;
-      ++len;
-    }
-    if (len > n) return best;
+// start positions (in a and b) of segment k of a script whose first segment starts at (a0, b0)
+inline void seg_pos(const Script& d, size_t k, int a0, int b0, int* pa, int* pb) {
+  for (size_t i = 0; i < k; ++i) {
+    if (d[i].op != INS) a0 += d[i].len;
+    if (d[i].op != DEL) b0 += d[i].len;
   }
+  *pa = a0;
+  *pb = b0;
 }
 
-void merge_pass(Script& d);
-Script diff(const Str& a, const Str& b);
+void merge_pass(const Ctx& c, Script& d, int a0, int b0);
+void diff(const Ctx& c, int alo, int ahi, int blo, int bhi, Script* out);
 
-// Myers O(ND) middle snake, then recurse on both halves.
-Script bisect(const Str& a, const Str& b) {
-  const long n = (long)a.size(), m = (long)b.size();
+// Myers O(ND) middle snake on a[alo,ahi) x b[blo,bhi), then recurse on both halves.
+void bisect(const Ctx& c, int alo, int ahi, int blo, int bhi, Script* out) {
+  const long n = ahi - alo, m = bhi - blo;
   const long maxd = (n + m + 1) / 2, off = maxd, vlen = 2 * maxd;
   std::vector<long> vf(vlen, -1), vr(vlen, -1);
   vf[off + 1] = 0;
@@ -114,16 +132,12 @@ Script bisect(const Str& a, const Str& b) {
   const long delta = n - m;
   const bool odd = (delta % 2) != 0;
   long fs = 0, fe = 0, rs = 0, re = 0;
-  auto split = [&](long x, long y) {
-    Script left = diff(a.substr(0, x), b.substr(0, y));
-    Script right = diff(a.substr(x), b.substr(y));
-    left.insert(left.end(), right.begin(), right.end());
-    return left;
-  };
-  for (long d = 0; d < maxd; ++d) {
-    for (long k = -d + fs; k <= d - fe; k += 2) {
+  Txt a = c.a + alo;
+  Txt b = c.b + blo;
+  for (long dd = 0; dd < maxd; ++dd) {
+    for (long k = -dd + fs; k <= dd - fe; k += 2) {
       const long ko = off + k;
-      long x = (k == -d || (k != d && vf[ko - 1] < vf[ko + 1])) ? vf[ko + 1] : vf[ko - 1] + 1;
+      long x = (k == -dd || (k != dd && vf[ko - 1] < vf[ko + 1])) ? vf[ko + 1] : vf[ko - 1] + 1;
       long y = x - k;
       while (x < n && y < m && a[x] == b[y]) {
         ++x;
@@ -136,12 +150,16 @@ Script bisect(const Str& a, const Str& b) {
         fs += 2;
       } else if (odd) {
         const long ro = off + delta - k;
-        if (ro >= 0 && ro < vlen && vr[ro] != -1 && x >= n - vr[ro]) return split(x, y);
+        if (ro >= 0 && ro < vlen && vr[ro] != -1 && x >= n - vr[ro]) {
+          diff(c, alo, alo + (int)x, blo, blo + (int)y, out);
+          diff(c, alo + (int)x, ahi, blo + (int)y, bhi, out);
+          return;
+        }
       }
     }
-    for (long k = -d + rs; k <= d - re; k += 2) {
+    for (long k = -dd + rs; k <= dd - re; k += 2) {
       const long ko = off + k;
-      long x = (k == -d || (k != d && vr[ko - 1] < vr[ko + 1])) ? vr[ko + 1] : vr[ko - 1] + 1;
+      long x = (k == -dd || (k != dd && vr[ko - 1] < vr[ko + 1])) ? vr[ko + 1] : vr[ko - 1] + 1;
       long y = x - k;
       while (x < n && y < m && a[n - x - 1] == b[m - y - 1]) {
         ++x;
@@ -156,106 +174,150 @@ Script bisect(const Str& a, const Str& b) {
         const long fo = off + delta - k;
         if (fo >= 0 && fo < vlen && vf[fo] != -1) {
           const long x1 = vf[fo], y1 = off + x1 - fo;
-          if (x1 >= n - x) return split(x1, y1);
+          if (x1 >= n - x) {
+            diff(c, alo, alo + (int)x1, blo, blo + (int)y1, out);
+            diff(c, alo + (int)x1, ahi, blo + (int)y1, bhi, out);
+            return;
+          }
         }
       }
     }
   }
-  return Script{{DEL, a}, {INS, b}};
+  out->push_back(Seg{DEL, (int)n});
+  out->push_back(Seg{INS, (int)m});
 }
 
-Script middle(const Str& a, const Str& b) {
-  if (a.empty() && b.empty()) return {};
-  if (a.empty()) return Script{{INS, b}};
-  if (b.empty()) return Script{{DEL, a}};
-  const Str& lng = a.size() > b.size() ? a : b;
-  const Str& sht = a.size() > b.size() ? b : a;
-  size_t at = lng.find(sht);
-  if (at != Str::npos) {
-    const Op op = a.size() > b.size() ? DEL : INS;
-    return Script{{op, lng.substr(0, at)}, {EQ, sht}, {op, lng.substr(at + sht.size())}};
+// the diff of two strings without a common prefix or suffix
+void middle(const Ctx& c, int alo, int ahi, int blo, int bhi, Script* out) {
+  const int n = ahi - alo, m = bhi - blo;
+  if (n == 0 && m == 0) return;
+  if (n == 0) {
+    out->push_back(Seg{INS, m});
+    return;
   }
-  if (sht.size() == 1) return Script{{DEL, a}, {INS, b}};
-  return bisect(a, b);
+  if (m == 0) {
+    out->push_back(Seg{DEL, n});
+    return;
+  }
+  const bool a_longer = n > m;
+  const int at = a_longer ? find_in(c.a + alo, n, c.b + blo, m) : find_in(c.b + blo, m, c.a + alo, n);
+  if (at >= 0) {
+    const Op op = a_longer ? DEL : INS;
+    const int lng = a_longer ? n : m, sht = a_longer ? m : n;
+    out->push_back(Seg{op, at});  // may be empty, like the restated algorithm
+    out->push_back(Seg{EQ, sht});
+    out->push_back(Seg{op, lng - at - sht});
+    return;
+  }
+  if (std::min(n, m) == 1) {
+    out->push_back(Seg{DEL, n});
+    out->push_back(Seg{INS, m});
+    return;
+  }
+  bisect(c, alo, ahi, blo, bhi, out);
 }
 
-Script diff(const Str& a, const Str& b) {
-  const size_t p = prefix_len(a, b);
-  const Str a1 = a.substr(p), b1 = b.substr(p);
-  const size_t s = suffix_len(a1, b1);
-  Script out = middle(a1.substr(0, a1.size() - s), b1.substr(0, b1.size() - s));
-  if (p) out.insert(out.begin(), Chunk{EQ, a.substr(0, p)});
-  if (s) out.push_back(Chunk{EQ, a1.substr(a1.size() - s)});
-  merge_pass(out);
-  return out;
+void diff(const Ctx& c, int alo, int ahi, int blo, int bhi, Script* out) {
+  const int p = common_prefix(c.a + alo, ahi - alo, c.b + blo, bhi - blo);
+  const int s = common_suffix(c.a + alo + p, ahi - alo - p, c.b + blo + p, bhi - blo - p);
+  Script local;
+  if (p) local.push_back(Seg{EQ, p});
+  middle(c, alo + p, ahi - s, blo + p, bhi - s, &local);
+  if (s) local.push_back(Seg{EQ, s});
+  merge_pass(c, local, alo, blo);
+  out->insert(out->end(), local.begin(), local.end());
 }
 
 // Reorder and merge like edit sections; factor out common affixes; slide single edits.
-void merge_pass(Script& d) {
+void merge_pass(const Ctx& c, Script& d, int a0, int b0) {
   bool again = true;
   while (again) {
-    d.push_back(Chunk{EQ, Str()});
+    d.push_back(Seg{EQ, 0});
     size_t i = 0, ndel = 0, nins = 0;
-    Str tdel, tins;
+    int dl = 0, il = 0;          // accumulated deletion / insertion lengths of the current run
+    int ra = a0, rb = b0;        // positions where the current run starts
+    int pa = a0, pb = b0;        // positions of segment i
     while (i < d.size()) {
       if (d[i].op == INS) {
         ++nins;
-        tins += d[i].text;
+        il += d[i].len;
+        pb += d[i].len;
         ++i;
       } else if (d[i].op == DEL) {
         ++ndel;
-        tdel += d[i].text;
+        dl += d[i].len;
+        pa += d[i].len;
         ++i;
       } else {
         if (ndel + nins > 1) {
           if (ndel && nins) {
-            size_t c = prefix_len(tins, tdel);
-            if (c) {
+            int cp = common_prefix(c.b + rb, il, c.a + ra, dl);
+            if (cp) {
               const size_t before = i - ndel - nins;
               if (before > 0 && d[before - 1].op == EQ) {
-                d[before - 1].text += tins.substr(0, c);
+                d[before - 1].len += cp;
               } else {
-                d.insert(d.begin(), Chunk{EQ, tins.substr(0, c)});
+                d.insert(d.begin(), Seg{EQ, cp});
                 ++i;
               }
-              tins = tins.substr(c);
-              tdel = tdel.substr(c);
+              ra += cp;
+              rb += cp;
+              il -= cp;
+              dl -= cp;
             }
-            c = suffix_len(tins, tdel);
-            if (c) {
-              d[i].text = tins.substr(tins.size() - c) + d[i].text;
-              tins = tins.substr(0, tins.size() - c);
-              tdel = tdel.substr(0, tdel.size() - c);
+            cp = common_suffix(c.b + rb, il, c.a + ra, dl);
+            if (cp) {
+              d[i].len += cp;
+              il -= cp;
+              dl -= cp;
             }
           }
           i -= ndel + nins;
           d.erase(d.begin() + i, d.begin() + i + ndel + nins);
-          if (!tdel.empty()) d.insert(d.begin() + i++, Chunk{DEL, tdel});
-          if (!tins.empty()) d.insert(d.begin() + i++, Chunk{INS, tins});
+          if (dl) d.insert(d.begin() + i++, Seg{DEL, dl});
+          if (il) d.insert(d.begin() + i++, Seg{INS, il});
+          // positions of the equality now at index i
+          pa = ra + dl;
+          pb = rb + il;
+          pa += d[i].len;
+          pb += d[i].len;
           ++i;
         } else if (i > 0 && d[i - 1].op == EQ) {
-          d[i - 1].text += d[i].text;
+          d[i - 1].len += d[i].len;
+          pa += d[i].len;
+          pb += d[i].len;
           d.erase(d.begin() + i);
         } else {
+          pa += d[i].len;
+          pb += d[i].len;
           ++i;
         }
         ndel = nins = 0;
-        tdel.clear();
-        tins.clear();
+        dl = il = 0;
+        ra = pa;
+        rb = pb;
       }
     }
-    if (d.back().text.empty()) d.pop_back();
+    if (d.back().len == 0) d.pop_back();
     again = false;
     for (size_t k = 1; k + 1 < d.size(); ++k) {
       if (d[k - 1].op != EQ || d[k + 1].op != EQ) continue;
-      if (ends_with(d[k].text, d[k - 1].text)) {
-        d[k].text = d[k - 1].text + d[k].text.substr(0, d[k].text.size() - d[k - 1].text.size());
-        d[k + 1].text = d[k - 1].text + d[k + 1].text;
+      int ka, kb;
+      seg_pos(d, k, a0, b0, &ka, &kb);
+      // text of the edit and of its neighbours, all inside the edit's own string
+      const bool del = d[k].op == DEL;
+      Txt base = del ? c.a : c.b;
+      const int pos = del ? ka : kb;
+      const int len = d[k].len, lp = d[k - 1].len, ln = d[k + 1].len;
+      // the equalities read through the *other* string are identical, so one string suffices
+      if (len >= lp && same(base + pos + len - lp, base + pos - lp, lp)) {
+        // edit ends with the previous equality: shift the edit left over it
+        d[k + 1].len += lp;
         d.erase(d.begin() + k - 1);
         again = true;
-      } else if (starts_with(d[k].text, d[k + 1].text)) {
-        d[k - 1].text += d[k + 1].text;
-        d[k].text = d[k].text.substr(d[k + 1].text.size()) + d[k + 1].text;
+      } else if (len >= ln && same(base + pos, base + pos + len, ln)) {
+        // edit starts with the next equality: shift the edit right over it
+        d[k - 1].len += ln;
         d.erase(d.begin() + k + 1);
         again = true;
       }
@@ -263,32 +325,29 @@ void merge_pass(Script& d) {
   }
 }
 
-bool cp_space(char32_t c) {
-  return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
-         c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+bool cp_space(char32_t ch) {
+  return ch == ' ' || (ch >= 9 && ch <= 13) || ch == 0x85 || ch == 0xA0 || ch == 0x1680 || (ch >= 0x2000 && ch <= 0x200A) ||
+         ch == 0x2028 || ch == 0x2029 || ch == 0x202F || ch == 0x205F || ch == 0x3000;
 }
-bool cp_alnum(char32_t c) { return anl_unicode::is_alphabetic(c) || (c >= '0' && c <= '9'); }
+bool cp_alnum(char32_t ch) { return anl_unicode::is_alphabetic(ch) || (ch >= '0' && ch <= '9'); }
 
 // Boundary quality between two strings (6 = edge ... 0 = inside a word).
-int boundary_score(const Str& one, const Str& two) {
-  if (one.empty() || two.empty()) return 6;
-  const char32_t c1 = one.back(), c2 = two.front();
+int boundary_score(Txt one, int n1, Txt two, int n2) {
+  if (n1 == 0 || n2 == 0) return 6;
+  const char32_t c1 = one[n1 - 1], c2 = two[0];
   const bool na1 = !cp_alnum(c1), na2 = !cp_alnum(c2);
   const bool ws1 = na1 && cp_space(c1), ws2 = na2 && cp_space(c2);
   const bool lb1 = ws1 && (c1 == '\n' || c1 == '\r'), lb2 = ws2 && (c2 == '\n' || c2 == '\r');
-  auto tail_blank = [](const Str& s) {
-    const size_t n = s.size();
-    return (n >= 2 && s[n - 1] == '\n' && s[n - 2] == '\n') ||
-           (n >= 3 && s[n - 1] == '\n' && s[n - 2] == '\r' && s[n - 3] == '\n');
+  auto tail_blank = [](Txt s, int n) {
+    return (n >= 2 && s[n - 1] == '\n' && s[n - 2] == '\n') || (n >= 3 && s[n - 1] == '\n' && s[n - 2] == '\r' && s[n - 3] == '\n');
   };
-  auto head_blank = [](const Str& s) {
-    const size_t n = s.size();
+  auto head_blank = [](Txt s, int n) {
     if (n >= 2 && s[0] == '\n' && s[1] == '\n') return true;
     if (n >= 3 && s[0] == '\n' && s[1] == '\r' && s[2] == '\n') return true;
     if (n >= 3 && s[0] == '\r' && s[1] == '\n' && s[2] == '\n') return true;
     return n >= 4 && s[0] == '\r' && s[1] == '\n' && s[2] == '\r' && s[3] == '\n';
   };
-  if ((lb1 && tail_blank(one)) || (lb2 && head_blank(two))) return 5;
+  if ((lb1 && tail_blank(one, n1)) || (lb2 && head_blank(two, n2))) return 5;
   if (lb1 || lb2) return 4;
   if (na1 && !ws1 && ws2) return 3;
   if (ws1 || ws2) return 2;
@@ -297,70 +356,77 @@ int boundary_score(const Str& one, const Str& two) {
 }
 
 // Slide an edit that is surrounded by equalities sideways to the best boundary.
-void lossless_shift(Script& d) {
+void lossless_shift(const Ctx& c, Script& d) {
   for (size_t k = 1; k + 1 < d.size(); ++k) {
     if (d[k - 1].op != EQ || d[k + 1].op != EQ) continue;
-    Str e1 = d[k - 1].text, ed = d[k].text, e2 = d[k + 1].text;
-    const size_t c = suffix_len(e1, ed);
-    if (c) {
-      const Str tail = ed.substr(ed.size() - c);
-      e1 = e1.substr(0, e1.size() - c);
-      ed = tail + ed.substr(0, ed.size() - c);
-      e2 = tail + e2;
-    }
-    Str b1 = e1, bd = ed, b2 = e2;
-    int best = boundary_score(e1, ed) + boundary_score(ed, e2);
-    while (!ed.empty() && !e2.empty() && ed[0] == e2[0]) {
-      e1 += ed[0];
-      ed = ed.substr(1) + e2[0];
-      e2 = e2.substr(1);
-      const int sc = boundary_score(e1, ed) + boundary_score(ed, e2);
+    int ka, kb;
+    seg_pos(d, k, 0, 0, &ka, &kb);
+    const bool del = d[k].op == DEL;
+    Txt base = del ? c.a : c.b;
+    int pos = del ? ka : kb;  // start of the edit inside its own string
+    const int m = d[k].len;
+    int l1 = d[k - 1].len, l2 = d[k + 1].len;
+    // the window [pos - l1, pos + m + l2) of `base` is  equality1 | edit | equality2
+    const int cs = common_suffix(base + pos - l1, l1, base + pos, m);
+    pos -= cs;
+    l1 -= cs;
+    l2 += cs;
+    int best_pos = pos, best_l1 = l1, best_l2 = l2;
+    int best = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
+    while (m > 0 && l2 > 0 && base[pos] == base[pos + m]) {
+      ++pos;
+      ++l1;
+      --l2;
+      const int sc = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
       if (sc >= best) {
         best = sc;
-        b1 = e1;
-        bd = ed;
-        b2 = e2;
+        best_pos = pos;
+        best_l1 = l1;
+        best_l2 = l2;
       }
     }
-    if (d[k - 1].text != b1) {
-      if (!b1.empty()) {
-        d[k - 1].text = b1;
+    (void)best_pos;
+    if (d[k - 1].len != best_l1) {
+      // (equal lengths mean equal text here: the window is fixed and only the split moves)
+      size_t kk = k;
+      if (best_l1) {
+        d[kk - 1].len = best_l1;
       } else {
-        d.erase(d.begin() + k - 1);
-        --k;
+        d.erase(d.begin() + kk - 1);
+        --kk;
       }
-      d[k].text = bd;
-      if (!b2.empty()) {
-        d[k + 1].text = b2;
+      if (best_l2) {
+        d[kk + 1].len = best_l2;
       } else {
-        d.erase(d.begin() + k + 1);
-        --k;
+        d.erase(d.begin() + kk + 1);
+        --kk;
       }
+      k = kk;
     }
   }
 }
 
 // Remove equalities that are no longer than the edits on both of their sides.
-void semantic_pass(Script& d) {
+void semantic_pass(const Ctx& c, Script& d) {
   bool changed = false;
   std::vector<size_t> eqs;
   bool have = false;
-  Str lasteq;
+  int lasteq = 0;
   long i = 0;
-  size_t ins1 = 0, del1 = 0, ins2 = 0, del2 = 0;
+  int ins1 = 0, del1 = 0, ins2 = 0, del2 = 0;
   while (i < (long)d.size()) {
     if (d[i].op == EQ) {
       eqs.push_back((size_t)i);
       ins1 = ins2;
       del1 = del2;
       ins2 = del2 = 0;
-      lasteq = d[i].text;
+      lasteq = d[i].len;
       have = true;
     } else {
-      (d[i].op == INS ? ins2 : del2) += d[i].text.size();
-      if (have && lasteq.size() <= std::max(ins1, del1) && lasteq.size() <= std::max(ins2, del2)) {
+      (d[i].op == INS ? ins2 : del2) += d[i].len;
+      if (have && lasteq <= std::max(ins1, del1) && lasteq <= std::max(ins2, del2)) {
         const size_t at = eqs.back();
-        d.insert(d.begin() + at, Chunk{DEL, lasteq});
+        d.insert(d.begin() + at, Seg{DEL, lasteq});
         d[at + 1].op = INS;
         eqs.pop_back();
         if (!eqs.empty()) eqs.pop_back();
@@ -372,24 +438,28 @@ void semantic_pass(Script& d) {
     }
     ++i;
   }
-  if (changed) merge_pass(d);
-  lossless_shift(d);
+  if (changed) merge_pass(c, d, 0, 0);
+  lossless_shift(c, d);
   // a deletion followed by an insertion that overlap: pull the overlap out as an equality
   for (size_t k = 1; k < d.size(); ++k) {
     if (d[k - 1].op == DEL && d[k].op == INS) {
-      const Str del = d[k - 1].text, ins = d[k].text;
-      const size_t o1 = overlap_len(del, ins), o2 = overlap_len(ins, del);
+      int ka, kb;
+      seg_pos(d, k - 1, 0, 0, &ka, &kb);
+      const int dl = d[k - 1].len, il = d[k].len;
+      Txt del = c.a + ka;
+      Txt ins = c.b + kb;
+      const int o1 = overlap_len(del, dl, ins, il), o2 = overlap_len(ins, il, del, dl);
       if (o1 >= o2) {
-        if (o1 * 2 >= del.size() || o1 * 2 >= ins.size()) {
-          d.insert(d.begin() + k, Chunk{EQ, ins.substr(0, o1)});
-          d[k - 1].text = del.substr(0, del.size() - o1);
-          d[k + 1].text = ins.substr(o1);
+        if (o1 * 2 >= dl || o1 * 2 >= il) {
+          d.insert(d.begin() + k, Seg{EQ, o1});
+          d[k - 1].len = dl - o1;
+          d[k + 1].len = il - o1;
           ++k;
         }
-      } else if (o2 * 2 >= del.size() || o2 * 2 >= ins.size()) {
-        d.insert(d.begin() + k, Chunk{EQ, del.substr(0, o2)});
-        d[k - 1] = Chunk{INS, ins.substr(0, ins.size() - o2)};
-        d[k + 1] = Chunk{DEL, del.substr(o2)};
+      } else if (o2 * 2 >= dl || o2 * 2 >= il) {
+        d.insert(d.begin() + k, Seg{EQ, o2});
+        d[k - 1] = Seg{INS, il - o2};
+        d[k + 1] = Seg{DEL, dl - o2};
         ++k;
       }
       ++k;
@@ -400,12 +470,27 @@ void semantic_pass(Script& d) {
 }  // namespace
 
 std::vector<EditInstruction> shortest_edit_script(const std::string& src, const std::string& dst) {
-  Script d = diff(decode(src), decode(dst));
-  semantic_pass(d);
-  merge_pass(d);
+  static thread_local std::vector<char32_t> ua, ub;
+  const int na = (int)decode(src.data(), src.size(), &ua), nb = (int)decode(dst.data(), dst.size(), &ub);
+  Ctx c{ua.data(), ub.data()};
+  Script d;
+  d.reserve(16);
+  diff(c, 0, na, 0, nb, &d);
+  semantic_pass(c, d);
+  merge_pass(c, d, 0, 0);
   std::vector<EditInstruction> out;
-  for (const Chunk& c : d)
-    if (!c.text.empty()) out.push_back(EditInstruction{(int)c.op, encode(c.text)});
+  out.reserve(d.size());
+  int pa = 0, pb = 0;
+  for (const Seg& s : d) {
+    if (s.len > 0) {
+      EditInstruction e;
+      e.op = (int)s.op;
+      append_utf8(&e.text, s.op == INS ? c.b + pb : c.a + pa, s.len);
+      out.push_back(std::move(e));
+    }
+    if (s.op != INS) pa += s.len;
+    if (s.op != DEL) pb += s.len;
+  }
   return out;
 }
 
@@ -439,7 +524,7 @@ bool parse_confusable(const std::string& editscript, double weight, Confusable* 
       if (bar == std::string::npos) break;
       s = bar + 1;
     }
-    for (const std::string& o : ins.options) ins.options32.push_back(decode(o));
+    for (const std::string& o : ins.options) ins.options32.push_back(decode32(o));
     out->script.push_back(ins);
     i = close + 1;
   }

@@ -154,6 +154,14 @@ uint32_t anl_model_max_key_bits(const anl_model* m);
 int64_t anl_normalize(const anl_model* m, const char* text, size_t len, uint8_t* out, size_t cap);
 int64_t anl_anahash(const anl_model* m, const char* text, size_t len, uint64_t* limbs, size_t cap);
 
+/* sesdiff::shortest_edit_script(src, dst, false, false, false) as the reference calls it for confusable
+ * rescoring (src/lib.rs:1736), rendered in sesdiff's text form `=[..]-[..]+[..]`.  Returns the number of
+ * bytes needed (excluding the NUL); writes at most cap-1 bytes + NUL. */
+int64_t anl_shortest_edit_script(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap);
+/* Confusable::found_in (src/confusables.rs:47): 1 if `pattern` occurs in the edit script of src -> dst,
+ * 0 if not, -1 if the pattern does not parse. */
+int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src_len, const char* dst, size_t dst_len);
+
 /* ---- lookup ---------------------------------------------------------------------------------- */
 /* find_variants over a batch (== find_variants_par, bindings/python/src/lib.rs:720).
  * `blob` holds the UTF-8 queries back to back, query i = blob[offsets[i] .. offsets[i+1]).

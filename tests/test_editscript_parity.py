@@ -1,0 +1,84 @@
+"""CPU-only: the product's edit script / confusable matcher (csrc/editscript.cpp, through the C ABI)
+against the oracle's independent implementation on many string pairs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import workloads
+from oracle import orc
+
+
+@pytest.fixture(scope="module")
+def L():
+    from analiticcl_b200 import build, _capi
+    build.build()
+    return _capi.lib()
+
+
+def script(L, a, b):
+    ra, rb = a.encode(), b.encode()
+    buf = C.create_string_buffer(4096)
+    n = L.anl_shortest_edit_script(ra, len(ra), rb, len(rb), buf, 4096)
+    assert n < 4096
+    return buf.value.decode()
+
+
+def pairs(seed, n):
+    rng = np.random.default_rng(seed)
+    eng = workloads.read_words("eng")
+    nld = workloads.read_words("nld")
+    out = []
+    for words in (eng, nld):
+        idx = rng.integers(0, len(words), size=n)
+        noisy = workloads.ocr_noise([words[i] for i in idx], n, seed + 1)
+        mis = workloads.misspellings([words[i] for i in idx], n, seed + 2, min_len=1, max_len=40,
+                                     edit_probs=((1, 0.3), (2, 0.3), (3, 0.2), (4, 0.2)))
+        for i in range(n):
+            w = words[idx[i]]
+            out.append((noisy[i], w))
+            out.append((mis[i], words[int(rng.integers(0, len(words)))]))  # unrelated words
+            j = min(len(words) - 1, idx[i] + int(rng.integers(1, 4)))    # alphabetical neighbours share prefixes
+            out.append((w, words[j]))
+            out.append((mis[i], w))
+    out += [("", ""), ("a", ""), ("", "b"), ("abc", "abc"), ("abcd", "axcy"), ("aab", "ab"), ("abbc", "abc"),
+            ("fefarate", "separate"), ("The quick brown fox", "The quick brown dog"), ("naïve café", "naive cafe"),
+            ("mississippi", "missisipi"), ("xaxbxc", "xbxcxa"), ("abcxxx", "xxxdef"), ("xxxabc", "defxxx"),
+            ("a b c d", "a x c y"), ("line\n\nbreak", "line\nbreak"), ("ΑΒΓΔ", "ΑΓΒΔ")]
+    return out
+
+
+def test_edit_scripts_match_oracle(L):
+    ps = pairs(11, 6000)
+    bad = []
+    for a, b in ps:
+        got, exp = script(L, a, b), orc.edit_script(a, b)
+        if got != exp:
+            bad.append((a, b, got, exp))
+    assert not bad, f"{len(bad)} / {len(ps)} differ, first: {bad[:5]}"
+
+
+def test_script_reconstructs_both_strings(L):
+    """Size-independent property: deletions+identities spell the source, insertions+identities the target."""
+    import re
+    for a, b in pairs(12, 1500):
+        s = script(L, a, b)
+        if "[" in a + b or "]" in a + b:
+            continue
+        chunks = re.findall(r"([=+-])\[(.*?)\]", s, flags=re.S)
+        assert "".join(t for op, t in chunks if op in "=-") == a
+        assert "".join(t for op, t in chunks if op in "=+") == b
+
+
+def test_confusable_kats(L):
+    f = lambda p, a, b: L.anl_confusable_found_in(p.encode(), a.encode(), len(a.encode()), b.encode(), len(b.encode()))
+    assert script(L, "huys", "huis") == "=[hu]-[y]+[i]=[s]"          # tests/main.rs:914-933
+    assert f("-[y]+[i]", "huys", "huis") == 1 and f("-[y]+[i]", "huys", "huls") == 0
+    assert f("-[y]+[p]", "Huys", "huis") == 0
+    assert f("^=[hu]-[y]", "huys", "huis") == 1 and f("^-[y]", "huys", "huis") == 0
+    assert f("+[i]=[s]$", "huys", "huis") == 1 and f("-[y]+[i]$", "huys", "huis") == 0
+    assert f("=[c|u]-[y]+[i]", "huys", "huis") == 1 and f("=[c|k]-[y]+[i]", "huys", "huis") == 0
+    assert f("garbage", "a", "b") == -1
+    for pat, _ in workloads.CFG2_CONFUSABLES:
+        for a, b in pairs(13, 300):
+            assert f(pat, a, b) == int(orc.confusable_found_in(pat, a, b))
