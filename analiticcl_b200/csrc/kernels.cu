@@ -89,9 +89,11 @@ struct __align__(16) SEntry {  // a node X = D + I' that passed the Bloom filter
 struct K1Warp {
   DEntry dch[DCH];
   SEntry sq[SQ];
+  uint32_t pfx[33];   // drain stage: exclusive prefix of posting counts (+ sentinel)
+  uint32_t poff[32];  // drain stage: first posting of each staged node
   uint8_t sorted[256];
   uint32_t nhits;
-  uint32_t pad[3];
+  uint32_t pad[2];
 };
 struct K1Shared {
   DeviceIndex ix;  // block-local copy of the model constants (pointers, masks, small tables)
@@ -113,16 +115,18 @@ struct K1Ctx {
   uint32_t c_probes, c_pass, c_steps, c_postings, c_ana, c_inst;
 };
 
-// Exact lookup of the staged nodes: table slot by fingerprint, then every posting is verified
-// against the anagram's own key and against the canonical-generation rules (each indexed
-// anagram C is produced exactly once: from D = F meet C and the ascending insertion order).
+// Exact lookup of the staged nodes, in two lane-parallel stages: (1) one node per lane finds its
+// table slot by fingerprint; (2) the postings of all 32 nodes are flattened (warp scan) and
+// verified one posting per lane -- against the anagram's own key and against the
+// canonical-generation rules (each indexed anagram C is produced exactly once: from D = F meet C
+// and the ascending insertion order).
 __device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t cnt) {
   const uint32_t lane = lane_id();
   for (uint32_t base = 0; base < cnt; base += 32) {
-    uint32_t i = base + lane;
+    const uint32_t i = base + lane;
+    uint32_t poff = 0, pcnt = 0;
     if (i < cnt) {
-      const SEntry s = W.sq[i];
-      const DEntry& de = W.dch[s.e];
+      const SEntry& s = W.sq[i];
       const uint64_t fp = hash_key(s.w0, s.w1, s.w2);
       uint64_t idx = fp & c.table_mask;
       for (;;) {
@@ -130,38 +134,63 @@ __device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t*
         ++c.c_steps;
         if (sl.post_cnt == 0) break;
         if (sl.fp == fp) {
-          const uint32_t budget_left = c.ka - de.d - s.isz;
-          for (uint32_t p = sl.post_off; p < sl.post_off + sl.post_cnt; ++p) {
-            const uint32_t r = c.ix->post_ana[p];
-            const uint32_t x = c.ix->post_cls[p];
-            ++c.c_postings;
-            uint64_t x0 = s.w0, x1 = s.w1, x2 = s.w2;
-            bool ok;
-            if (x == POST_SELF) {
-              ok = (c.sd == 0) || (s.isz == 0);
-            } else {
-              ok = budget_left >= 1 && (s.isz == 0 || x >= s.imax);
-              for (uint32_t t = 0; t < de.d; ++t) ok = ok && (de.del[t] != x);
-              ok = ok && mul192(x0, x1, x2, prime_of[x]);
-            }
-            if (!ok) continue;
-            const Key192 ck = c.ix->ana_key[r];
-            if (ck.w0 != x0 || ck.w1 != x1 || ck.w2 != x2) continue;  // fingerprint collision
-            const uint32_t io = c.ix->ana_inst_off[r], ie = c.ix->ana_inst_off[r + 1];
-            const uint32_t n = ie - io;
-            ++c.c_ana;
-            c.c_inst += n;
-            const uint32_t pos = atomicAdd(&W.nhits, n);
-            for (uint32_t t = 0; t < n; ++t)
-              if (pos + t < c.hit_cap) c.hits_q[pos + t] = io + t;
-          }
+          poff = sl.post_off;
+          pcnt = sl.post_cnt;
           break;
         }
         idx = (idx + 1) & c.table_mask;
       }
     }
+    uint32_t incl = pcnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    W.pfx[lane] = incl - pcnt;
+    W.poff[lane] = poff;
+    __syncwarp();
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      if (t < total) {
+        uint32_t owner = 0;  // largest lane whose exclusive prefix is <= t
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (W.pfx[owner + step] <= t) owner += step;
+        const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
+        const SEntry& s = W.sq[base + owner];
+        const DEntry& de = W.dch[s.e];
+        const uint32_t r = __ldg(c.ix->post_ana + p);
+        const uint32_t x = __ldg(c.ix->post_cls + p);
+        ++c.c_postings;
+        uint64_t x0 = s.w0, x1 = s.w1, x2 = s.w2;
+        bool ok;
+        if (x == POST_SELF) {
+          ok = (c.sd == 0) || (s.isz == 0);
+        } else {
+          const uint32_t budget_left = c.ka - de.d - s.isz;
+          ok = budget_left >= 1 && (s.isz == 0 || x >= s.imax);
+#pragma unroll
+          for (int q = 0; q < ANL_MAX_K; ++q) ok = ok && (q >= (int)de.d || de.del[q] != x);
+          ok = ok && mul192(x0, x1, x2, prime_of[x]);
+        }
+        if (ok) {
+          const Key192 ck = c.ix->ana_key[r];
+          if (ck.w0 == x0 && ck.w1 == x1 && ck.w2 == x2) {  // else: fingerprint collision
+            const uint32_t io = __ldg(c.ix->ana_inst_off + r), ie = __ldg(c.ix->ana_inst_off + r + 1);
+            const uint32_t n = ie - io;
+            ++c.c_ana;
+            c.c_inst += n;
+            const uint32_t pos = atomicAdd(&W.nhits, n);
+            for (uint32_t q = 0; q < n; ++q)
+              if (pos + q < c.hit_cap) c.hits_q[pos + q] = io + q;
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // Bloom test of one node per lane; positives are compacted into the staging queue.
@@ -222,6 +251,7 @@ __device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_
   for (uint32_t e = 0; e < nD; ++e) {
     const DEntry de = W.dch[e];  // warp-uniform broadcast
     const int jmax = (int)c.ka - (int)de.d - c.sd;
+    if (jmax < 1) break;  // entries are in ascending deletion depth: no later entry has insertions left
     for (int j = 1; j <= jmax; ++j) {
       const uint32_t cx = c.L - de.d + j;
       const bool useful = (c.sd == 0) ? ccbit(ix->charcount_mask, cx) : ccbit(ix->charcount_mask, cx + 1);
@@ -454,8 +484,9 @@ constexpr int K2_WARPS = 4;
 struct __align__(16) SurvRec {
   double dist;    // distance score
   double freq;    // absolute, then normalised frequency score
+  double key;     // combined score (VariantResult::score), computed once per record
   uint32_t g;     // gather id
-  uint32_t pad;
+  uint32_t raw;   // raw frequency
 };
 
 // shared memory of one warp (dynamic; sized by the longest indexed entry ML and the ring depth R)
@@ -473,17 +504,15 @@ __device__ __forceinline__ double result_score(const BatchParams& bp, double dis
 }
 // rank_cmp (src/types.rs:344-365) with the gather id as the final key (== stable sort of the
 // reference's gather order)
-__device__ __forceinline__ bool ranks_before(const BatchParams& bp, double da, double fa, uint32_t ga, double db, double fb,
-                                             uint32_t gb) {
-  if (bp.finish_mode == FINISH_GATHER) return ga < gb;
+__device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRec& a, const SurvRec& b) {
+  if (bp.finish_mode == FINISH_GATHER) return a.g < b.g;
   if (bp.freq_weight_positive) {
-    const double sa = result_score(bp, da, fa), sb = result_score(bp, db, fb);
-    if (sa != sb) return sa > sb;
-    return ga < gb;
+    if (a.key != b.key) return a.key > b.key;
+    return a.g < b.g;
   }
-  if (da != db) return da > db;
-  if (fa != fb) return fa > fb;
-  return ga < gb;
+  if (a.dist != b.dist) return a.dist > b.dist;
+  if (a.freq != b.freq) return a.freq > b.freq;
+  return a.g < b.g;
 }
 
 template <int R>
@@ -565,7 +594,8 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
               const uint32_t bytepos = j0 + b;  // byte in the row; symbol index = bytepos - 2
               if (bytepos >= 2 && bytepos < Lc + 2) {
                 const uint32_t sym = (wds[b >> 2] >> ((b & 3) * 8)) & 0xFF;
-                cell[(bytepos - 1) * 32 + lane] = sym;  // column j = bytepos - 1: t, lcs = 0, lastrow = 0
+                // column j = bytepos - 1: {t, lcs = 0, lastrow = 0, D[0][j] = j}
+                cell[(bytepos - 1) * 32 + lane] = sym | ((bytepos - 1) << 24);
               }
             }
           }
@@ -586,16 +616,15 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       for (uint32_t i = 1; i <= Lq; ++i) {
         const uint32_t sc = sq[i - 1];
         uint8_t* cur = ring + (size_t)(i & (R - 1)) * rowbytes;
-        const uint8_t* prev = ring + (size_t)((i - 1) & (R - 1)) * rowbytes;
         uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
         cur[lane] = (uint8_t)min(i, 255u);
         for (uint32_t j = 1; j <= Lcm; ++j) {
           const uint32_t cw = cell[j * 32 + lane];
-          const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF;
-          const uint32_t up = prev[j * 32 + lane];
+          const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF, up = cw >> 24;
           const bool same = (tc == sc) && (j <= Lc);
           uint32_t v = min(min(left, up) + 1, diag + (same ? 0u : 1u));
-          if (last > 0 && db > 0 && i - last <= (uint32_t)(R - 2)) {
+          // transposition (src/distance.rs:160-165); a term that cannot be <= ke is skipped (exact)
+          if (last > 0 && db > 0 && (i - last) + (j - db) <= ke + 1) {
             const uint32_t tv = ring[(size_t)((last - 1) & (R - 1)) * rowbytes + (db - 1) * 32 + lane] + (i - last - 1) + 1 +
                                 (j - db - 1);
             v = min(v, tv);
@@ -604,7 +633,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           cur[j * 32 + lane] = (uint8_t)v;
           const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
           lcs_best = max(lcs_best, lcs_new);
-          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? i : last) << 16);
+          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? i : last) << 16) | (v << 24);
           if (same) db = j;
           lcs_diag = lcs_up;
           diag = up;
@@ -658,8 +687,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         SurvRec r;
         r.dist = score;
         r.freq = freq;
+        r.key = 0.0;
         r.g = g;
-        r.pad = (uint32_t)freq;  // raw frequency (exact: u32 or 1.0)
+        r.raw = (uint32_t)freq;  // raw frequency (exact: u32 or 1.0)
         surv[nsurv + __popc(kmask & lanemask_lt())] = r;
       }
       nsurv += __popc(kmask);
@@ -667,12 +697,13 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     }
 
     // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
-    // (surv keeps the raw frequency in `pad`; `freq` becomes the normalised score used for ranking)
+    // (surv keeps the raw frequency in `raw`; `freq` becomes the normalised score, `key` the combined one)
     __threadfence_block();
     __syncwarp();
     for (uint32_t i = lane; i < nsurv; i += 32) {
       SurvRec r = surv[i];
       if (maxfreq > 0.0) r.freq = __ddiv_rn(r.freq, maxfreq);
+      r.key = result_score(bp, r.dist, r.freq);
       surv[i] = r;
     }
     __syncwarp();
@@ -681,7 +712,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       uint32_t rank = 0;
       for (uint32_t j = 0; j < nsurv; ++j) {
         const SurvRec b = surv[j];
-        rank += (j != i) && ranks_before(bp, b.dist, b.freq, b.g, a.dist, a.freq, a.g);
+        rank += (j != i) && ranks_before(bp, b, a);
       }
       sorted[rank] = a;
     }
@@ -746,7 +777,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         OutRec o;
         o.dist_score = r.dist;
         o.vocab_id = __ldg(ix->inst_vocab + r.g);
-        o.freq = r.pad;
+        o.freq = r.raw;
         out[off + i] = o;
       }
     }

@@ -114,6 +114,13 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_oracle(spec):
     from oracle import orc
     o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
@@ -141,7 +148,7 @@ def run_reference(args):
     from oracle import orc
     spec = workload_spec(args.workload)
     o, oparams = make_oracle(spec)
-    threads = orc.lib().orc_max_threads()
+    threads = host_cores()  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
     sample_n = min(spec["n"], args.ref_sample)
     queries = spec["queries"](spec["n"])[:sample_n]
     for _ in range(args.warmup):
@@ -177,6 +184,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the host side of the e2e path is multi-threaded: split the box's cores between the ranks
+    os.environ.setdefault("ANL_HOST_THREADS", str(max(1, host_cores() // world)))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -283,11 +292,10 @@ def run_ours(args):
         dom_bytes = probe_bytes if dominant == "probe_kernel" else score_bytes
         achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
         cpu = None
-        if world == 1 or True:
-            # bounded CPU baseline on rank 0's host cores: the oracle port, all threads
-            from oracle import orc
+        if world == 1:
+            # bounded CPU baseline on rank 0's host cores (N=1 only): the oracle port, all threads
             o, oparams = make_oracle(spec)
-            threads = orc.lib().orc_max_threads()
+            threads = host_cores()
             sample_n = min(n, args.cpu_sample)
             dt, _, st = time_oracle(o, oparams, queries[:sample_n], threads)
             cpu = {"value": sample_n / dt, "unit": "queries/s", "cores": threads, "kind": "port",
