@@ -73,7 +73,7 @@ struct __attribute__((aligned(16))) MsetEntry {
 };
 
 static const int ANL_MAX_K = 6;          // largest supported max_anagram_distance after thresholding
-static const int ANL_MAX_SYMBOLS = 250;  // longest query / entry (symbols) the device path accepts
+static const int ANL_MAX_SYMBOLS = 236;  // longest query / entry (symbols) the device path accepts (row number + 16 fits a byte)
 
 // ---- per-model constant data ------------------------------------------------------------------------
 struct DeviceIndex {

@@ -515,13 +515,12 @@ __device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRe
   return a.g < b.g;
 }
 
-template <int R>
 __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
              const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, unsigned int* pool_cursor,
-             Counters* counters, uint32_t ML) {
+             Counters* counters, uint32_t ML, uint32_t R) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -609,39 +608,50 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
 
       // ---- true Damerau-Levenshtein, all lanes in lock-step over (i, j) -----------------------
-      // Row i of the matrix lives in ring[i % R].  Only the last ke+2 <= R rows are ever needed:
-      // a transposition reaching further back costs more than ke ("DP kernel").
-      for (uint32_t j = 0; j <= Lcm; ++j) ring[j * 32 + lane] = (uint8_t)j;  // row 0
+      // Row i of the matrix lives in ring slot (i mod R), R = max edit distance + 2: only the last
+      // ke+2 rows are ever needed, because a transposition reaching further back costs more than
+      // ke ("DP kernel").  Row and column numbers are shifted by S = ke + 2 so that
+      // "no previous occurrence" (0) fails the reach test below without a separate check.
+      const uint32_t S = ke + 2;
+      if (!valid) Lc = 0;
+      for (uint32_t j = Lc + 1; j <= Lcm; ++j) cell[j * 32 + lane] = 0xFFu | (j << 24);  // sentinel symbol: never equal
+      for (uint32_t j = 0; j <= Lcm; ++j) ring[j * 32 + lane] = (uint8_t)j;             // row 0 in slot 0
       uint32_t lcs_best = 0;
+      uint32_t slot = 0;  // ring slot of row i - 1
       for (uint32_t i = 1; i <= Lq; ++i) {
         const uint32_t sc = sq[i - 1];
-        uint8_t* cur = ring + (size_t)(i & (R - 1)) * rowbytes;
+        slot = slot + 1 == R ? 0 : slot + 1;
+        uint8_t* cur = ring + (size_t)slot * rowbytes;
+        const uint32_t is = i + S;  // shifted row number
         uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
-        cur[lane] = (uint8_t)min(i, 255u);
+        cur[lane] = (uint8_t)i;
         for (uint32_t j = 1; j <= Lcm; ++j) {
           const uint32_t cw = cell[j * 32 + lane];
           const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF, up = cw >> 24;
-          const bool same = (tc == sc) && (j <= Lc);
+          const bool same = tc == sc;
+          const uint32_t js = j + S;
           uint32_t v = min(min(left, up) + 1, diag + (same ? 0u : 1u));
-          // transposition (src/distance.rs:160-165); a term that cannot be <= ke is skipped (exact)
-          if (last > 0 && db > 0 && (i - last) + (j - db) <= ke + 1) {
-            const uint32_t tv = ring[(size_t)((last - 1) & (R - 1)) * rowbytes + (db - 1) * 32 + lane] + (i - last - 1) + 1 +
-                                (j - db - 1);
+          // transposition (src/distance.rs:160-165): mat[last][db] + (i-last-1) + 1 + (j-db-1); a term that
+          // reaches back more than ke + 1 in total cannot be <= ke and is skipped (exact)
+          const uint32_t reach = (is - last) + (js - db);
+          if (reach <= ke + 1) {
+            const uint32_t back = is - last + 1;  // rows between row i and row last-1
+            const uint32_t ts = slot >= back ? slot - back : slot + R - back;
+            const uint32_t tv = ring[(size_t)ts * rowbytes + (db - S - 1) * 32 + lane] + reach - 1;
             v = min(v, tv);
           }
-          v = min(v, 255u);
           cur[j * 32 + lane] = (uint8_t)v;
           const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
           lcs_best = max(lcs_best, lcs_new);
-          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? i : last) << 16) | (v << 24);
-          if (same) db = j;
+          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? is : last) << 16) | (v << 24);
+          if (same) db = js;
           lcs_diag = lcs_up;
           diag = up;
           left = v;
         }
       }
       uint32_t ld = 255;
-      if (valid) ld = ring[(size_t)(Lq & (R - 1)) * rowbytes + Lc * 32 + lane];
+      if (valid) ld = ring[(size_t)slot * rowbytes + Lc * 32 + lane];
       valid = valid && ld <= ke;
 
       // ---- prefix / suffix (src/distance.rs:208-231) ------------------------------------------------
@@ -815,25 +825,19 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 // launchers
 // ================================================================================================
 static int g_k1_ctas_per_sm = 0;
-static int g_k2_ctas_per_sm[3] = {0, 0, 0};
 
 static uint32_t ring_depth(const BatchParams& bp) {
   // rows needed = max edit distance + 2; thresholds are capped at 255 but anything beyond 14 is
   // rejected by the host (ANL_ERR_UNSUPPORTED)
   uint32_t kmax = bp.max_edit.kind == 0 ? 12u : (bp.max_edit.value & 0xFFu);
-  if (kmax + 2 <= 4) return 4;
-  if (kmax + 2 <= 8) return 8;
-  return 16;
+  if (kmax > 14) kmax = 14;
+  return kmax + 2;
 }
 
 cudaError_t configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(score_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(score_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_kernel, K1_WARPS * 32, sizeof(K1Shared));
   return e;
@@ -857,14 +861,9 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 }
 
 static int k2_ctas_per_sm(uint32_t R, size_t smem) {
+  (void)R;
   int n = 0;
-  cudaError_t e;
-  if (R == 4)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<4>, K2_WARPS * 32, smem);
-  else if (R == 8)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<8>, K2_WARPS * 32, smem);
-  else
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<16>, K2_WARPS * 32, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel, K2_WARPS * 32, smem);
   if (e != cudaSuccess || n < 1) n = 1;
   return n;
 }
@@ -873,12 +872,9 @@ static int k2_ctas_per_sm(uint32_t R, size_t smem) {
 static long long k2_grid(const DeviceIndex& h_ix, const BatchParams& bp, int sm_count) {
   const uint32_t R = ring_depth(bp);
   const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
-  int idx = R == 4 ? 0 : (R == 8 ? 1 : 2);
-  (void)idx;
   return (long long)sm_count * k2_ctas_per_sm(R, smem);
 }
 
-static uint32_t g_scratch_max_len = 0;
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries) {
   // one survivor list + one sorted copy per resident warp.  Upper bound on resident warps: 16 CTAs/SM
   // exceeds any smem-limited occupancy here; the launcher never starts more warps than queries.
@@ -890,7 +886,6 @@ size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queri
 
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream) {
-  (void)g_scratch_max_len;
   if (lb.n == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 2 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
@@ -904,18 +899,9 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
-#define ANL_LAUNCH_K2(RR)                                                                                              \
-  score_kernel<RR><<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,    \
-                                                                    lb.hit_count, lb.qflags, lb.out, lb.out_head,     \
-                                                                    scratch, lb.work + 1, lb.work + 2, lb.counters,   \
-                                                                    h_ix.max_len)
-  if (R == 4)
-    ANL_LAUNCH_K2(4);
-  else if (R == 8)
-    ANL_LAUNCH_K2(8);
-  else
-    ANL_LAUNCH_K2(16);
-#undef ANL_LAUNCH_K2
+score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
+                                                                lb.qflags, lb.out, lb.out_head, scratch, lb.work + 1,
+                                                                lb.work + 2, lb.counters, h_ix.max_len, R);
   return cudaGetLastError();
 }
 
