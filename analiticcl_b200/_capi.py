@@ -119,6 +119,10 @@ SIGNATURES = {
     "anl_device_batch_free": (None, [_vp, _vp]),
     "anl_device_batch_counters": (_i32, [_vp, _vp, _P(Counters)]),
     "anl_model_index_stats": (_i32, [_vp, _P(IndexStats)]),
+    "anl_model_build_sharded": (_i32, [_vp, _i32, _u32, _u32]),
+    "anl_shard_export_size": (_i32, [_vp, _vp, _P(_u64), _P(_u32)]),
+    "anl_shard_export": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "anl_shard_merge": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u64, _u32, _P(_vp)]),
 }
 
 _lib = None

@@ -152,15 +152,16 @@ void anl_model_set_confusables_before_pruning(anl_model* m) {
   if (m) m->host.confusables_before_pruning = true;
 }
 
-anl_status anl_model_build(anl_model* m, int32_t device) {
+anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards) {
   if (!m) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int sd = 1;
   if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
-  if (!m->host.build_index(sd, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  if (!m->host.build_index(sd, shard, n_shards, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
   if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
+anl_status anl_model_build(anl_model* m, int32_t device) { return anl_model_build_sharded(m, device, 0, 1); }
 
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len) { return m && m->host.has(text, len) ? 1 : 0; }
 int64_t anl_model_vocab_id(const anl_model* m, const char* text, size_t len) { return m ? m->host.vocab_id(text, len) : -1; }
@@ -401,6 +402,37 @@ anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_coun
   if (!m->engine.counters(b->b, out, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
+// ---- lexicon-sharded mode --------------------------------------------------------------------------------
+anl_status anl_shard_export_size(anl_model* m, anl_device_batch* b, uint64_t* n_records, uint32_t* max_per_query) {
+  if (!m || !b || !n_records) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  int status = ANL_OK;
+  if (!m->engine.shard_export_size(b->b, n_records, max_per_query, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags) {
+  if (!m || !b || !d_heads || !d_records || !d_gids || !d_flags) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.shard_export(b->b, d_heads, d_records, d_gids, d_flags, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
+anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards, const void* d_heads_all,
+                           const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
+                           uint32_t max_survivors, anl_result_set** out) {
+  if (!m || !b || !out || !d_heads_all || !d_records_all || !d_gids_all || !d_flags_all)
+    return fail(ANL_ERR_INVALID, "null argument");
+  anl_result_set* rs = new anl_result_set();
+  std::string err;
+  int status = ANL_OK;
+  if (!m->engine.shard_merge(b->b, n_shards, d_heads_all, d_records_all, d_gids_all, d_flags_all, record_stride, max_survivors,
+                             &rs->rs, &err, &status)) {
+    delete rs;
+    return fail(status ? status : ANL_ERR_CUDA, err);
+  }
+  *out = rs;
+  return ANL_OK;
+}
+
 anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) {
   if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "model has not been built");

@@ -94,6 +94,7 @@ struct DeviceIndex {
   uint32_t norm_stride;      // multiple of 16
   const uint32_t* inst_vocab;  // vocab id per gather id
   const uint32_t* inst_freq;   // VocabValue.frequency per gather id
+  const uint32_t* inst_gid;    // lexicon-sharded index only: global gather id per local gather id (else null)
   const MsetEntry* mset;
   uint32_t mset_end[ANL_MAX_K + 1];  // mset_end[J] = number of entries with j <= J; [0] = 0
   const uint32_t* binom;             // [256][8] saturating binomials C(n, k)
@@ -132,6 +133,7 @@ struct BatchParams {
 static const int FINISH_FULL = 0;       // rank, crop, cutoff on device (no confusables)
 static const int FINISH_CROP = 1;       // rank + crop on device; late confusables + cutoff follow on the host
 static const int FINISH_GATHER = 2;     // emit all survivors in gather order (early confusables on the host)
+static const int FINISH_SHARD = 3;      // lexicon-sharded mode: emit all survivors unranked; merge_kernel finishes
 
 // query flags
 static const uint8_t Q_FIRST_LOWER = 1;

@@ -165,6 +165,8 @@ bool Engine::upload(int device, std::string* err) {
   ix.norm_stride = hx.norm_stride;
   if (!upload_vec(hx.inst_vocab, &ix.inst_vocab, &index_allocs_, err)) return false;
   if (!upload_vec(hx.inst_freq, &ix.inst_freq, &index_allocs_, err)) return false;
+  ix.inst_gid = nullptr;
+  if (!hx.inst_gid.empty() && !upload_vec(hx.inst_gid, &ix.inst_gid, &index_allocs_, err)) return false;
   // saturating binomials C(n, k), n < 256, k < 8
   std::vector<uint32_t> binom(256 * 8, 0);
   for (int n = 0; n < 256; ++n) {
@@ -245,6 +247,7 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
     bp->finish_mode = FINISH_FULL;
   else
     bp->finish_mode = hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP;
+  if (hm_->index.n_shards > 1) bp->finish_mode = FINISH_SHARD;  // ranking happens after the exchange (shard_merge)
   uint32_t hit_cap = 2048;
   if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = (uint32_t)std::max(1, atoi(e));
   bp->hit_cap = hit_cap;
@@ -261,7 +264,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
                   (void*)b->h_work})
     if (p) cudaFreeHost(p);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
-                  (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
+                  (void*)b->d_gid, (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
                   (void*)b->rr_hits, (void*)b->rr_hit_count, (void*)b->rr_qflags, (void*)b->rr_head, (void*)b->rr_out,
                   (void*)b->rr_scratch})
     if (p) cudaFree(p);
@@ -287,8 +290,11 @@ void Engine::free_batch(DeviceBatch* b) {
 }
 
 bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err) {
-  if (pool_cap <= b->cap_pool && b->d_out) return true;
+  const bool need_gid = hm_->index.n_shards > 1;
+  if (pool_cap <= b->cap_pool && b->d_out && (!need_gid || b->d_gid)) return true;
+  pool_cap = std::max(pool_cap, b->cap_pool);
   if (!dev_realloc(&b->d_out, pool_cap, err)) return false;
+  if (need_gid && !dev_realloc(&b->d_gid, pool_cap, err)) return false;
   if (!pinned_realloc(&b->h_out, pool_cap, err)) return false;
   b->cap_pool = pool_cap;
   return true;
@@ -394,6 +400,9 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, std::max<uint64_t>(1024, n * per_query));
   if (!ensure_capacity(b, (uint32_t)n, stride, bp.hit_cap, pool_cap, score_scratch_bytes(bp, sm_count_, (uint32_t)n), err)) return fail();
   bp.pool_cap = b->cap_pool;
+  b->sharded = hm_->index.n_shards > 1;
+  b->merged = false;
+  b->final_mode = hm_->confusables.empty() ? FINISH_FULL : (hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP);
   b->bp = bp;
   pt.lap("create: buffers");
 
@@ -464,6 +473,7 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   lb.hit_count = b->d_hit_count;
   lb.qflags = b->d_qflags;
   lb.out = b->d_out;
+  lb.out_gid = b->sharded ? b->d_gid : nullptr;
   lb.out_head = b->d_head;
   lb.scratch = b->d_scratch;
   lb.work = b->d_work;
@@ -695,18 +705,9 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
   return ok;
 }
 
-bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
-  *status = ANL_ERR_CUDA;
-  if (!b->ran) {
-    *err = "batch has not been run";
-    *status = ANL_ERR_INVALID;
-    return false;
-  }
-  CU_TRY(cudaSetDevice(device_));
+bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* err) {
   const uint32_t n = b->n;
   cudaStream_t st = b->stream;
-  PhaseTimer pt;
-  // headers + pool cursor first; grow the pool and re-run the score kernel if it overflowed
   unsigned int total = 0;
   for (int attempt = 0;; ++attempt) {
     CU_TRY(cudaStreamWaitEvent(st, b->last_done, 0));
@@ -718,7 +719,7 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
     }
     CU_TRY(cudaStreamSynchronize(st));
     total = n ? b->h_work[2] : 0;
-    if (total <= b->bp.pool_cap) break;
+    if (total <= b->bp.pool_cap || b->merged) break;
     if (attempt >= 2) {
       *err = "internal error: result pool overflow persisted";
       return false;
@@ -732,6 +733,123 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
     CU_TRY(cudaEventRecord(b->last_done, st));
     b->reruns += 1;
   }
+  *total_out = total;
+  return true;
+}
+
+bool Engine::shard_export_size(DeviceBatch* b, uint64_t* n_records, uint32_t* max_per_query, std::string* err, int* status) {
+  *status = ANL_ERR_CUDA;
+  if (!b->ran || !b->sharded) {
+    *err = "not a sharded batch that has been run";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  CU_TRY(cudaSetDevice(device_));
+  unsigned int total = 0;
+  if (!settle_pool(b, &total, err)) return false;
+  uint32_t mx = 0;
+  for (uint32_t i = 0; i < b->n; ++i) mx = std::max(mx, b->h_head[i].count);
+  *n_records = total;
+  if (max_per_query) *max_per_query = mx;
+  *status = ANL_OK;
+  return true;
+}
+
+bool Engine::shard_export(DeviceBatch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags, std::string* err) {
+  CU_TRY(cudaSetDevice(device_));
+  const uint32_t n = b->n;
+  const unsigned int total = n ? b->h_work[2] : 0;
+  cudaStream_t st = b->stream;
+  if (n) {
+    CU_TRY(cudaMemcpyAsync(d_heads, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  if (total) {
+    CU_TRY(cudaMemcpyAsync(d_records, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_gids, b->d_gid, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  return true;
+}
+
+bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_all, const void* d_records_all,
+                         const void* d_gids_all, const void* d_flags_all, uint64_t record_stride, uint32_t max_survivors,
+                         ResultSet* out, std::string* err, int* status) {
+  *status = ANL_ERR_CUDA;
+  if (!b->sharded) {
+    *err = "not a sharded batch";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  CU_TRY(cudaSetDevice(device_));
+  const uint32_t n = b->n;
+  cudaStream_t st = b->stream;
+  // a hit-list overflow on any shard cannot be repaired after the exchange: fail on every rank alike
+  std::vector<uint32_t> flags_all((size_t)n * n_shards);
+  if (n) CU_TRY(cudaMemcpy(flags_all.data(), d_flags_all, flags_all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < flags_all.size(); ++i) {
+    if (flags_all[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
+      *err = "query " + std::to_string(i % std::max<uint32_t>(n, 1)) +
+             " exceeds the per-query candidate capacity (or the supported distance) on a shard; raise ANL_HIT_CAP";
+      *status = ANL_ERR_UNSUPPORTED;
+      return false;
+    }
+  }
+  const uint64_t pool64 = std::max<uint64_t>(1024, record_stride * n_shards);
+  if (pool64 > 0xFFFFFF00ull) {
+    *err = "sharded result pool too large; split the batch";
+    *status = ANL_ERR_UNSUPPORTED;
+    return false;
+  }
+  if (!grow_pool(b, (uint32_t)pool64, err)) return false;
+  const uint32_t cap = std::max<uint32_t>(32, (max_survivors + 31) & ~31u);
+  const size_t scratch = merge_scratch_bytes(sm_count_, n, cap);
+  if (scratch > b->cap_scratch || !b->d_scratch) {
+    if (!dev_realloc(reinterpret_cast<uint8_t**>(&b->d_scratch), scratch, err)) return false;
+    b->cap_scratch = scratch;
+  }
+  BatchParams bp = b->bp;
+  bp.finish_mode = b->final_mode;
+  bp.pool_cap = b->cap_pool;
+  CU_TRY(launch_merge(bp, n, n_shards, reinterpret_cast<const OutHead*>(d_heads_all), reinterpret_cast<const OutRec*>(d_records_all),
+                      reinterpret_cast<const uint32_t*>(d_gids_all), (uint32_t)record_stride,
+                      reinterpret_cast<const uint32_t*>(d_flags_all), b->d_qflags, b->d_out, b->d_head, b->d_scratch, cap,
+                      b->d_work, sm_count_, st));
+  if (b->events.empty()) {
+    cudaEvent_t ev = nullptr;
+    CU_TRY(cudaEventCreate(&ev));
+    b->events.push_back(ev);
+  }
+  CU_TRY(cudaEventRecord(b->events[0], st));
+  b->last_done = b->events[0];
+  b->merged = true;
+  b->bp.finish_mode = b->final_mode;  // the host post-pass of fetch_batch follows the final mode
+  b->bp.pool_cap = b->cap_pool;
+  const bool ok = fetch_batch(b, out, false, err, status);
+  b->bp.finish_mode = FINISH_SHARD;
+  b->merged = false;
+  return ok;
+}
+
+bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
+  *status = ANL_ERR_CUDA;
+  if (!b->ran) {
+    *err = "batch has not been run";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  if (b->sharded && !b->merged) {
+    *err = "this model holds a lexicon shard: use the shard export / merge calls";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  CU_TRY(cudaSetDevice(device_));
+  const uint32_t n = b->n;
+  cudaStream_t st = b->stream;
+  PhaseTimer pt;
+  // headers + pool cursor first; grow the pool and re-run the score kernel if it overflowed
+  unsigned int total = 0;
+  if (!settle_pool(b, &total, err)) return false;
   if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   pt.lap("fetch: sync+D2H");

@@ -84,6 +84,7 @@ struct DeviceBatch {
   uint32_t* d_hit_count = nullptr;
   uint32_t* d_qflags = nullptr;
   OutRec* d_out = nullptr;
+  uint32_t* d_gid = nullptr;  // sharded mode: global gather id per pool record (sized like d_out)
   OutHead* d_head = nullptr;
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
@@ -104,6 +105,9 @@ struct DeviceBatch {
   uint32_t runs_recorded = 0;
   cudaEvent_t last_done = nullptr;  // end event of the most recent run
   bool ran = false;
+  bool sharded = false;        // built against a lexicon shard: results come from shard_export / shard_merge
+  bool merged = false;         // shard_merge has produced the final lists in d_out / d_head
+  int final_mode = FINISH_FULL;  // finish mode of the merged result (bp.finish_mode is FINISH_SHARD while scoring)
   uint64_t reruns = 0;
   uint64_t results = 0;
 };
@@ -127,6 +131,13 @@ class Engine {
   bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);
 
+  // lexicon-sharded mode (see include/analiticcl_b200.h)
+  bool shard_export_size(DeviceBatch* b, uint64_t* n_records, uint32_t* max_per_query, std::string* err, int* status);
+  bool shard_export(DeviceBatch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags, std::string* err);
+  bool shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_all, const void* d_records_all,
+                   const void* d_gids_all, const void* d_flags_all, uint64_t record_stride, uint32_t max_survivors,
+                   ResultSet* out, std::string* err, int* status);
+
   // whole pipeline with internal chunking
   bool find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p, ResultSet* out,
                            std::string* err, int* status);
@@ -144,6 +155,7 @@ class Engine {
   bool ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
                        std::string* err);
   bool grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err);
+  bool settle_pool(DeviceBatch* b, unsigned int* total, std::string* err);  // sync; grow + re-score on pool overflow
   void destroy_batch(DeviceBatch* b);
   void release_index();
 

@@ -362,9 +362,15 @@ std::vector<uint64_t> HostModel::anahash_limbs(const char* text, size_t len) con
 }
 
 // ---- index build (src/lib.rs:192-245) ----------------------------------------------------------------------
-bool HostModel::build_index(int sd, std::string* err) {
+bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::string* err) {
   HostIndex ix;
   ix.sd = sd;
+  if (n_shards == 0 || shard >= n_shards) {
+    *err = "invalid shard";
+    return false;
+  }
+  ix.shard = shard;
+  ix.n_shards = n_shards;
   if (alphabet.size() + 1 > 168) {
     *err = "alphabet has more classes than there are primes (168)";
     return false;
@@ -416,6 +422,35 @@ bool HostModel::build_index(int sd, std::string* err) {
     return a.id < b.id;
   });
   ix.norm_stride = ((ix.max_len + 2) + 15) & ~15u;
+  // lexicon-sharded mode: anagrams are partitioned by hash(key) mod n_shards (instances follow their
+  // key); the position in the global (key, vocab id) order stays the tie-break key on every shard
+  std::vector<uint32_t> gids;
+  if (n_shards > 1) {
+    std::vector<Item> mine;
+    for (size_t g = 0; g < items.size(); ++g) {
+      const Key192& k = items[g].key;
+      if (hash_key(k.w0, k.w1, k.w2) % n_shards == shard) {
+        mine.push_back(items[g]);
+        gids.push_back((uint32_t)g);
+      }
+    }
+    items.swap(mine);
+    if (items.empty()) {
+      *err = "shard holds no anagrams";
+      return false;
+    }
+    memset(class_seen, 0, sizeof class_seen);
+    ix.max_len = 0;
+    ix.max_key_bits = 0;
+    for (const Item& it : items) {
+      const VocabEntry& v = decoder[it.id];
+      for (uint8_t s : v.syms) class_seen[s] = true;
+      ix.max_len = std::max<uint32_t>(ix.max_len, (uint32_t)v.syms.size());
+      ix.max_key_bits = std::max(ix.max_key_bits, key_bits(it.key));
+    }
+    ix.norm_stride = ((ix.max_len + 2) + 15) & ~15u;
+    ix.inst_gid = gids;
+  }
   ix.inst_rows.assign((size_t)items.size() * ix.norm_stride, 0);
   ix.inst_vocab.resize(items.size());
   ix.inst_freq.resize(items.size());

@@ -85,6 +85,8 @@ struct HostIndex {
   std::vector<uint16_t> ana_charcount;
   std::vector<uint32_t> inst_vocab;  // gather order
   std::vector<uint32_t> inst_freq;
+  std::vector<uint32_t> inst_gid;    // lexicon-sharded index: global gather id per local one (empty = identity)
+  uint32_t shard = 0, n_shards = 1;
   std::vector<uint8_t> inst_rows;
   uint32_t norm_stride = 0;
   std::vector<Slot> table;
@@ -114,7 +116,8 @@ class HostModel {
   bool add_to_confusables(const std::string& editscript, double weight, std::string* err);
   bool read_confusablelist(const std::string& filename, std::string* err);
   // src/lib.rs:192-245: anagram values, grouping, ordering -> flat arrays (host side of build())
-  bool build_index(int sd, std::string* err);
+  // shard / n_shards: keep only the anagrams whose key hashes to this shard (lexicon-sharded mode)
+  bool build_index(int sd, uint32_t shard, uint32_t n_shards, std::string* err);
   // builds the insertion-multiset table up to size J (idempotent)
   bool ensure_msets(uint32_t J, std::string* err);
 

@@ -21,6 +21,8 @@
 
 namespace anl {
 
+long long merge_grid(int sm_count, uint32_t n);
+
 #define FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------
@@ -481,12 +483,14 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 // ================================================================================================
 constexpr int K2_WARPS = 4;
 
-struct __align__(16) SurvRec {
-  double dist;    // distance score
-  double freq;    // absolute, then normalised frequency score
-  double key;     // combined score (VariantResult::score), computed once per record
-  uint32_t g;     // gather id
-  uint32_t raw;   // raw frequency
+struct __align__(8) SurvRec {
+  double dist;     // distance score
+  double freq;     // absolute, then normalised frequency score
+  double key;      // combined score (VariantResult::score), computed once per record
+  uint32_t g;      // (global) gather id: the final tie-break key
+  uint32_t raw;    // raw frequency
+  uint32_t vocab;  // vocabulary id
+  uint32_t pad;
 };
 
 // shared memory of one warp (dynamic; sized by the longest indexed entry ML and the ring depth R)
@@ -515,12 +519,123 @@ __device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRe
   return a.g < b.g;
 }
 
+// The tail shared by score_kernel and merge_kernel: frequency normalisation, ranking, crop, cut-off and
+// the packed emission of one query's survivors.  Returns the number of results written (lane 0 only).
+__device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRec* surv, SurvRec* sorted, uint32_t nsurv,
+                                                 double maxfreq, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
+                                                 OutHead* __restrict__ out_head, uint32_t qi, uint32_t flags,
+                                                 uint32_t* __restrict__ qflags, unsigned int* pool_cursor) {
+  const uint32_t lane = lane_id();
+  // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
+  // (surv keeps the raw frequency in `raw`; `freq` becomes the normalised score, `key` the combined one)
+  __threadfence_block();
+  __syncwarp();
+  if (bp.finish_mode == FINISH_SHARD) {
+    // lexicon-sharded mode: ranking happens after the exchange (merge_kernel); pass the survivors through
+    for (uint32_t i = lane; i < nsurv; i += 32) sorted[i] = surv[i];
+  } else {
+    for (uint32_t i = lane; i < nsurv; i += 32) {
+      SurvRec r = surv[i];
+      if (maxfreq > 0.0) r.freq = __ddiv_rn(r.freq, maxfreq);
+      r.key = result_score(bp, r.dist, r.freq);
+      surv[i] = r;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nsurv; i += 32) {
+      const SurvRec a = surv[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nsurv; ++j) {
+        const SurvRec b = surv[j];
+        rank += (j != i) && ranks_before(bp, b, a);
+      }
+      sorted[rank] = a;
+    }
+  }
+  __syncwarp();
+
+  // ---- crop at max_matches with the reference's tie rules (src/lib.rs:1536-1589) ---------------------
+  uint32_t n = nsurv;
+  if (bp.finish_mode != FINISH_GATHER && bp.finish_mode != FINISH_SHARD && bp.max_matches > 0 && n > bp.max_matches) {
+    const SurvRec a = sorted[bp.max_matches - 1], b = sorted[bp.max_matches];
+    const double last_score = result_score(bp, a.dist, a.freq);
+    const double cropped = result_score(bp, b.dist, b.freq);
+    if (cropped < last_score) {
+      n = bp.max_matches;
+    } else {
+      // B = first i with dist_i < cropped; E = first i in [1, B) with dist_i == cropped
+      uint32_t B = n, E = 0xFFFFFFFFu;
+      for (uint32_t b0 = 0; b0 < n && B == n; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        double dsc = 0.0;
+        const bool in = i < n;
+        if (in) dsc = sorted[i].dist;
+        const uint32_t lt = __ballot_sync(FULL, in && dsc < cropped);
+        uint32_t eq = __ballot_sync(FULL, in && i >= 1 && dsc == cropped);
+        if (lt) {
+          const uint32_t first = __ffs(lt) - 1;
+          B = b0 + first;
+          eq &= (first == 0) ? 0u : (0xFFFFFFFFu >> (32 - first));
+        }
+        if (eq && E == 0xFFFFFFFFu) E = b0 + __ffs(eq) - 1;
+      }
+      if (E != 0xFFFFFFFFu)
+        n = E + 1;
+      else if (B < n && B > 0)
+        n = B + 1;
+    }
+  }
+  // ---- cut-off (src/lib.rs:1598-1622); only when no late confusable rescoring follows -----------------
+  if (bp.finish_mode == FINISH_FULL && bp.cutoff_threshold >= 1.0 && n > 1) {
+    const SurvRec a = sorted[0];
+    const double lim = __ddiv_rn(result_score(bp, a.dist, a.freq), bp.cutoff_threshold);
+    uint32_t cut = n;
+    for (uint32_t b0 = 0; b0 < n && cut == n; b0 += 32) {
+      const uint32_t i = b0 + lane;
+      bool hit = false;
+      if (i >= 1 && i < n) {
+        const SurvRec r = sorted[i];
+        hit = result_score(bp, r.dist, r.freq) <= lim;
+      }
+      const uint32_t m = __ballot_sync(FULL, hit);
+      if (m) cut = b0 + __ffs(m) - 1;
+    }
+    n = cut;
+  }
+  // ---- emit into the packed pool (one atomic reservation per query) --------------------------------------
+  uint32_t off = 0;
+  if (lane == 0 && n > 0) off = atomicAdd(pool_cursor, n);
+  off = __shfl_sync(FULL, off, 0);
+  const bool fits = (unsigned long long)off + n <= (unsigned long long)bp.pool_cap;
+  if (fits) {
+    for (uint32_t i = lane; i < n; i += 32) {
+      const SurvRec r = sorted[i];
+      OutRec o;
+      o.dist_score = r.dist;
+      o.vocab_id = r.vocab;
+      o.freq = r.raw;
+      out[off + i] = o;
+      if (out_gid) out_gid[off + i] = r.g;
+    }
+  }
+  if (lane == 0) {
+    OutHead h;
+    h.max_freq = maxfreq;
+    h.offset = off;
+    h.count = fits ? n : 0;
+    out_head[qi] = h;
+    const uint32_t nf = (flags & ~QF_OUT_OVERFLOW) | (fits ? 0u : QF_OUT_OVERFLOW);
+    if (nf != flags) qflags[qi] = nf;
+  }
+  __syncwarp();
+  return (lane == 0 && fits) ? n : 0;
+}
+
 __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
              const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
-             OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, unsigned int* pool_cursor,
-             Counters* counters, uint32_t ML, uint32_t R) {
+             uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
+             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -537,6 +652,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint8_t* __restrict__ rows = ix->inst_rows;
   const uint32_t nstride = ix->norm_stride;
   const int have_freq = ix->have_freq;
+  const uint32_t* __restrict__ gid_of = ix->inst_gid;
   unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0;
 
   for (;;) {
@@ -698,110 +814,17 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         r.dist = score;
         r.freq = freq;
         r.key = 0.0;
-        r.g = g;
-        r.raw = (uint32_t)freq;  // raw frequency (exact: u32 or 1.0)
+        r.g = gid_of ? __ldg(gid_of + g) : g;  // sharded index: global gather id
+        r.raw = (uint32_t)freq;               // raw frequency (exact: u32 or 1.0)
+        r.vocab = __ldg(ix->inst_vocab + g);
+        r.pad = 0;
         surv[nsurv + __popc(kmask & lanemask_lt())] = r;
       }
       nsurv += __popc(kmask);
       __syncwarp();
     }
 
-    // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
-    // (surv keeps the raw frequency in `raw`; `freq` becomes the normalised score, `key` the combined one)
-    __threadfence_block();
-    __syncwarp();
-    for (uint32_t i = lane; i < nsurv; i += 32) {
-      SurvRec r = surv[i];
-      if (maxfreq > 0.0) r.freq = __ddiv_rn(r.freq, maxfreq);
-      r.key = result_score(bp, r.dist, r.freq);
-      surv[i] = r;
-    }
-    __syncwarp();
-    for (uint32_t i = lane; i < nsurv; i += 32) {
-      const SurvRec a = surv[i];
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < nsurv; ++j) {
-        const SurvRec b = surv[j];
-        rank += (j != i) && ranks_before(bp, b, a);
-      }
-      sorted[rank] = a;
-    }
-    __syncwarp();
-
-    // ---- crop at max_matches with the reference's tie rules (src/lib.rs:1536-1589) ---------------------
-    uint32_t n = nsurv;
-    if (bp.finish_mode != FINISH_GATHER && bp.max_matches > 0 && n > bp.max_matches) {
-      const SurvRec a = sorted[bp.max_matches - 1], b = sorted[bp.max_matches];
-      const double last_score = result_score(bp, a.dist, a.freq);
-      const double cropped = result_score(bp, b.dist, b.freq);
-      if (cropped < last_score) {
-        n = bp.max_matches;
-      } else {
-        // B = first i with dist_i < cropped; E = first i in [1, B) with dist_i == cropped
-        uint32_t B = n, E = 0xFFFFFFFFu;
-        for (uint32_t b0 = 0; b0 < n && B == n; b0 += 32) {
-          const uint32_t i = b0 + lane;
-          double dsc = 0.0;
-          const bool in = i < n;
-          if (in) dsc = sorted[i].dist;
-          const uint32_t lt = __ballot_sync(FULL, in && dsc < cropped);
-          uint32_t eq = __ballot_sync(FULL, in && i >= 1 && dsc == cropped);
-          if (lt) {
-            const uint32_t first = __ffs(lt) - 1;
-            B = b0 + first;
-            eq &= (first == 0) ? 0u : (0xFFFFFFFFu >> (32 - first));
-          }
-          if (eq && E == 0xFFFFFFFFu) E = b0 + __ffs(eq) - 1;
-        }
-        if (E != 0xFFFFFFFFu)
-          n = E + 1;
-        else if (B < n && B > 0)
-          n = B + 1;
-      }
-    }
-    // ---- cut-off (src/lib.rs:1598-1622); only when no late confusable rescoring follows -----------------
-    if (bp.finish_mode == FINISH_FULL && bp.cutoff_threshold >= 1.0 && n > 1) {
-      const SurvRec a = sorted[0];
-      const double lim = __ddiv_rn(result_score(bp, a.dist, a.freq), bp.cutoff_threshold);
-      uint32_t cut = n;
-      for (uint32_t b0 = 0; b0 < n && cut == n; b0 += 32) {
-        const uint32_t i = b0 + lane;
-        bool hit = false;
-        if (i >= 1 && i < n) {
-          const SurvRec r = sorted[i];
-          hit = result_score(bp, r.dist, r.freq) <= lim;
-        }
-        const uint32_t m = __ballot_sync(FULL, hit);
-        if (m) cut = b0 + __ffs(m) - 1;
-      }
-      n = cut;
-    }
-    // ---- emit into the packed pool (one atomic reservation per query) --------------------------------------
-    uint32_t off = 0;
-    if (lane == 0 && n > 0) off = atomicAdd(pool_cursor, n);
-    off = __shfl_sync(FULL, off, 0);
-    const bool fits = (unsigned long long)off + n <= (unsigned long long)bp.pool_cap;
-    if (fits) {
-      for (uint32_t i = lane; i < n; i += 32) {
-        const SurvRec r = sorted[i];
-        OutRec o;
-        o.dist_score = r.dist;
-        o.vocab_id = __ldg(ix->inst_vocab + r.g);
-        o.freq = r.raw;
-        out[off + i] = o;
-      }
-    }
-    if (lane == 0) {
-      OutHead h;
-      h.max_freq = maxfreq;
-      h.offset = off;
-      h.count = fits ? n : 0;
-      out_head[qi] = h;
-      const uint32_t nf = (flags & ~QF_OUT_OVERFLOW) | (fits ? 0u : QF_OUT_OVERFLOW);
-      if (nf != flags) qflags[qi] = nf;
-    }
-    c_res += (lane == 0 && fits) ? n : 0;
-    __syncwarp();
+    c_res += rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags, qflags, pool_cursor);
   }
 
   if (counters) {
@@ -819,6 +842,94 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       atomicAdd(&counters->results, v[3]);
     }
   }
+}
+
+
+// ================================================================================================
+// Kernel 3 (lexicon-sharded mode only): merge of the per-shard survivor lists after the exchange
+// ================================================================================================
+// Every shard scored the whole query batch against its part of the index and exported, per query,
+// its survivors (distance score, raw frequency, vocabulary id, GLOBAL gather id) and its local
+// max_freq.  After the all-gather each rank holds all G exports; one warp per query concatenates the
+// G lists, takes the global max_freq (frequency normalisation is global, src/lib.rs:1460,1521-1525)
+// and runs the same rank / crop / cut-off tail as the unsharded kernel.
+__global__ void __launch_bounds__(K2_WARPS * 32)
+merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead* __restrict__ heads_all,
+             const OutRec* __restrict__ recs_all, const uint32_t* __restrict__ gids_all, uint32_t rec_stride,
+             const uint32_t* __restrict__ qflags_in, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
+             OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, uint32_t scratch_cap, unsigned int* work,
+             unsigned int* pool_cursor) {
+  const uint32_t lane = lane_id();
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+  SurvRec* surv = scratch + (size_t)gwarp * 2 * scratch_cap;
+  SurvRec* sorted = surv + scratch_cap;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    uint32_t nsurv = 0;
+    double maxfreq = 0.0;
+    const uint32_t flags = qflags_in[qi];
+    for (uint32_t r = 0; r < n_shards; ++r) {
+      const OutHead h = heads_all[(size_t)r * nq + qi];
+      maxfreq = fmax(maxfreq, h.max_freq);
+      const OutRec* recs = recs_all + (size_t)r * rec_stride + h.offset;
+      const uint32_t* gids = gids_all + (size_t)r * rec_stride + h.offset;
+      for (uint32_t i = lane; i < h.count; i += 32) {
+        if (nsurv + i < scratch_cap) {
+          const OutRec o = recs[i];
+          SurvRec s;
+          s.dist = o.dist_score;
+          s.freq = (double)o.freq;
+          s.key = 0.0;
+          s.g = gids[i];
+          s.raw = o.freq;
+          s.vocab = o.vocab_id;
+          s.pad = 0;
+          surv[nsurv + i] = s;
+        }
+      }
+      nsurv += h.count;
+    }
+    __syncwarp();
+    if (nsurv > scratch_cap) {  // cannot happen: the host sizes scratch_cap from the gathered counts
+      if (lane == 0) {
+        OutHead h;
+        h.max_freq = maxfreq;
+        h.offset = 0;
+        h.count = 0;
+        out_head[qi] = h;
+        qflags[qi] = flags | QF_OUT_OVERFLOW;
+      }
+      continue;
+    }
+    rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, nullptr, out_head, qi, flags, qflags, pool_cursor);
+  }
+}
+
+cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, const OutRec* recs_all,
+                         const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
+                         OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,
+                         cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(work, 0, 4 * sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  long long grid = merge_grid(sm_count, n);
+  merge_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(bp, n, n_shards, heads_all, recs_all, gids_all, rec_stride,
+                                                             qflags_in, qflags, out, out_head,
+                                                             reinterpret_cast<SurvRec*>(scratch), scratch_cap, work + 1,
+                                                             work + 2);
+  return cudaGetLastError();
+}
+long long merge_grid(int sm_count, uint32_t n) {
+  long long grid = (long long)sm_count * 8;
+  const long long want = ((long long)n + K2_WARPS - 1) / K2_WARPS;
+  if (grid > want) grid = want;
+  return grid < 1 ? 1 : grid;
+}
+size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap) {
+  return (size_t)merge_grid(sm_count, n) * K2_WARPS * 2 * scratch_cap * sizeof(SurvRec);
 }
 
 // ================================================================================================
@@ -900,8 +1011,8 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (grid < 1) grid = 1;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
 score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
-                                                                lb.qflags, lb.out, lb.out_head, scratch, lb.work + 1,
-                                                                lb.work + 2, lb.counters, h_ix.max_len, R);
+                                                                lb.qflags, lb.out, lb.out_gid, lb.out_head, scratch,
+                                                                lb.work + 1, lb.work + 2, lb.counters, h_ix.max_len, R);
   return cudaGetLastError();
 }
 

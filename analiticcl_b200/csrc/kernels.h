@@ -9,17 +9,18 @@ namespace anl {
 
 // Buffers of one launch over `n` queries (all device pointers).
 struct LaunchBuffers {
-  const uint8_t* queries;  // [n_total][query_stride] encoded query rows
-  const uint32_t* qlist;   // optional: indices into `queries` (rerun of selected queries); nullptr = identity
-  uint32_t n;              // number of queries in this launch
-  uint32_t* hits;          // [n][hit_cap] gather ids of candidate instances
-  uint32_t* hit_count;     // [n]
-  uint32_t* qflags;        // [n] QF_* bits
-  OutRec* out;             // packed result pool, bp.pool_cap records
-  OutHead* out_head;       // [n] per-query header: offset / count into the pool, max_freq
-  void* scratch;           // score kernel scratch: score_scratch_bytes(...)
-  unsigned int* work;      // [0],[1] work-stealing counters, [2] pool cursor (zeroed by the launchers)
-  Counters* counters;      // accumulated work counters (zeroed by the caller when wanted)
+  const uint8_t* queries = nullptr;  // [n_total][query_stride] encoded query rows
+  const uint32_t* qlist = nullptr;   // optional: indices into `queries` (rerun of selected queries); nullptr = identity
+  uint32_t n = 0;                    // number of queries in this launch
+  uint32_t* hits = nullptr;          // [n][hit_cap] gather ids of candidate instances
+  uint32_t* hit_count = nullptr;     // [n]
+  uint32_t* qflags = nullptr;        // [n] QF_* bits
+  OutRec* out = nullptr;             // packed result pool, bp.pool_cap records
+  uint32_t* out_gid = nullptr;       // optional (sharded mode): global gather id per pool record
+  OutHead* out_head = nullptr;       // [n] per-query header: offset / count into the pool, max_freq
+  void* scratch = nullptr;           // score kernel scratch: score_scratch_bytes(...)
+  unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor (zeroed by the launchers)
+  Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
 };
 
 // Candidate generation: deletion neighbourhood x insertion multisets -> Bloom -> table -> postings.
@@ -31,5 +32,11 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
                          int sm_count, cudaStream_t stream);
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
 cudaError_t configure_kernels();
+// Lexicon-sharded mode: merge the all-gathered per-shard survivor lists (see merge_kernel).
+cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, const OutRec* recs_all,
+                         const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
+                         OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,
+                         cudaStream_t stream);
+size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap);
 
 }  // namespace anl

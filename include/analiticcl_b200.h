@@ -232,6 +232,27 @@ typedef struct anl_counters {
 } anl_counters;
 anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out);
 
+/* ---- lexicon-sharded mode (mode 2): used only when the index is split over GPUs ------
+ * Each rank builds the model with the same vocabulary and anl_model_build_sharded(); anagram keys are
+ * partitioned by hash(key) mod n_shards.  Every rank runs the whole query batch against its shard
+ * (anl_device_batch_create / _run as usual), exports its per-query survivors, the host framework
+ * all-gathers the exports over NCCL (torch.distributed in analiticcl_b200/sharded.py), and
+ * anl_shard_merge() ranks the union with the GLOBAL max frequency -- results identical to the
+ * unsharded model.  All d_* arguments are device pointers on the model's device. */
+anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards);
+/* After anl_device_batch_run: number of survivor records this shard exports, and the largest
+ * per-query survivor count. */
+anl_status anl_shard_export_size(anl_model* m, anl_device_batch* b, uint64_t* n_records, uint32_t* max_per_query);
+/* Copies the export into caller buffers: d_heads [n] x 16 B {f64 max_freq, u32 offset, u32 count},
+ * d_records [n_records] x 16 B {f64 dist_score, u32 vocab_id, u32 frequency}, d_gids [n_records] x u32
+ * (global gather ids = tie-break order), d_flags [n] x u32. */
+anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags);
+/* d_*_all hold the exports of all shards back to back: heads/flags with stride n, records/gids with
+ * stride record_stride.  max_survivors >= the largest per-query survivor count summed over shards. */
+anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards, const void* d_heads_all,
+                           const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
+                           uint32_t max_survivors, anl_result_set** out);
+
 /* Size of the device-resident index (bytes per component) for roofline accounting. */
 typedef struct anl_index_stats {
   uint64_t table_slots, table_bytes, slot_bytes, table_keys;
