@@ -419,17 +419,17 @@ anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, vo
 anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards, const void* d_heads_all,
                            const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
                            uint32_t max_survivors, anl_result_set** out) {
-  if (!m || !b || !out || !d_heads_all || !d_records_all || !d_gids_all || !d_flags_all)
+  if (!m || !b || !d_heads_all || !d_records_all || !d_gids_all || !d_flags_all)
     return fail(ANL_ERR_INVALID, "null argument");
-  anl_result_set* rs = new anl_result_set();
+  anl_result_set* rs = out ? new anl_result_set() : nullptr;
   std::string err;
   int status = ANL_OK;
   if (!m->engine.shard_merge(b->b, n_shards, d_heads_all, d_records_all, d_gids_all, d_flags_all, record_stride, max_survivors,
-                             &rs->rs, &err, &status)) {
+                             rs ? &rs->rs : nullptr, &err, &status)) {
     delete rs;
     return fail(status ? status : ANL_ERR_CUDA, err);
   }
-  *out = rs;
+  if (out) *out = rs;
   return ANL_OK;
 }
 

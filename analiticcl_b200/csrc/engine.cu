@@ -825,7 +825,13 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
   b->merged = true;
   b->bp.finish_mode = b->final_mode;  // the host post-pass of fetch_batch follows the final mode
   b->bp.pool_cap = b->cap_pool;
-  const bool ok = fetch_batch(b, out, false, err, status);
+  bool ok = true;
+  if (out) {
+    ok = fetch_batch(b, out, false, err, status);
+  } else {
+    CU_TRY(cudaStreamSynchronize(st));  // device-only merge: ranked lists stay in the batch's pool
+    *status = ANL_OK;
+  }
   b->bp.finish_mode = FINISH_SHARD;
   b->merged = false;
   return ok;

@@ -248,7 +248,8 @@ anl_status anl_shard_export_size(anl_model* m, anl_device_batch* b, uint64_t* n_
  * (global gather ids = tie-break order), d_flags [n] x u32. */
 anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags);
 /* d_*_all hold the exports of all shards back to back: heads/flags with stride n, records/gids with
- * stride record_stride.  max_survivors >= the largest per-query survivor count summed over shards. */
+ * stride record_stride.  max_survivors >= the largest per-query survivor count summed over shards.
+ * out == NULL: merge on the device only and leave the ranked lists in the batch's result pool. */
 anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards, const void* d_heads_all,
                            const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
                            uint32_t max_survivors, anl_result_set** out);

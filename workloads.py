@@ -178,3 +178,65 @@ def cfg2_queries(n=1_000_000, seed=2003):
 
 def cfg4_queries(n=1_000_000, seed=4001):
     return misspellings(read_words("eng"), n, seed, min_len=8, max_len=24, edit_probs=((2, 1 / 3), (3, 1 / 3), (4, 1 / 3)))
+
+
+def cfg5_lexicon(n_entries=10_000_000, seed=5001, max_len=24):
+    """cfg 5: synthetic corpus lexicon of `n_entries` unique entries built by concatenating two eng
+    entries (total length <= max_len symbols so keys stay <= 169 bits), with a Zipf frequency column.
+    -> path of the `word\tfreq` TSV (generated on first use; ~160 MB for 10 M entries)."""
+    _ensure_cache()
+    dst = os.path.join(CACHE, f"cfg5.n{n_entries}.s{seed}.lexicon")
+    if os.path.exists(dst):
+        return dst
+    rng = np.random.default_rng(seed)
+    words = [w for w in read_words("eng") if w.isascii() and w.isalpha() and 2 <= len(w) <= max_len - 2]
+    warr = np.array(words)
+    wlen = np.array([len(w) for w in words], dtype=np.int64)
+    nw = len(words)
+    pairs = np.empty(0, dtype=np.int64)
+    while len(pairs) < n_entries:
+        m = int((n_entries - len(pairs)) * 1.6) + 1000
+        a = rng.integers(0, nw, size=m)
+        b = rng.integers(0, nw, size=m)
+        ok = wlen[a] + wlen[b] <= max_len
+        pairs = np.unique(np.concatenate([pairs, a[ok] * nw + b[ok]]))
+    pairs = rng.permutation(pairs)[:n_entries]
+    a, b = pairs // nw, pairs % nw
+    entries = np.char.add(warr[a], warr[b])
+    entries = np.unique(entries)  # different pairs can spell the same string
+    freqs = zipf_frequencies(len(entries), seed + 1)
+    tmp = dst + f".tmp{os.getpid()}"
+    with open(tmp, "w", encoding="ascii") as f:
+        chunk = 500_000
+        for i in range(0, len(entries), chunk):
+            f.write("\n".join(f"{w}\t{q}" for w, q in zip(entries[i:i + chunk].tolist(), freqs[i:i + chunk].tolist())))
+            f.write("\n")
+    os.replace(tmp, dst)
+    return dst
+
+
+def cfg5_queries(n=1_000_000, seed=5002, n_entries=10_000_000, lex_seed=5001):
+    """Misspellings (cfg-1 generator) of entries of the cfg-5 lexicon."""
+    _ensure_cache()
+    dst = os.path.join(CACHE, f"cfg5.q{n}.s{seed}.n{n_entries}.txt")
+    if os.path.exists(dst):
+        with open(dst, encoding="utf-8") as f:
+            return f.read().split("\n")[:-1]
+    rng = np.random.default_rng(seed)
+    path = cfg5_lexicon(n_entries, lex_seed)
+    # sample source entries by line without loading 10 M Python strings
+    with open(path, "rb") as f:
+        data = f.read()
+    starts = np.flatnonzero(np.frombuffer(data, dtype=np.uint8) == 10) + 1
+    starts = np.concatenate([[0], starts[:-1]])
+    pick = rng.integers(0, len(starts), size=n)
+    src = []
+    for p in starts[pick]:
+        e = data.index(b"\t", p)
+        src.append(data[p:e].decode("ascii"))
+    qs = misspellings(src, n, seed + 1, min_len=4, max_len=24)
+    tmp = dst + f".tmp{os.getpid()}"
+    with open(tmp, "w", encoding="utf-8") as f:
+        f.write("\n".join(qs) + "\n")
+    os.replace(tmp, dst)
+    return qs
