@@ -279,7 +279,7 @@ __device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_
   if (sqn) drain_stage(c, W, prime_of, sqn);
 }
 
-__global__ void __launch_bounds__(K1_WARPS * 32, 2)
+__global__ void __launch_bounds__(K1_WARPS * 32, 4)
 probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
              uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
