@@ -215,6 +215,51 @@ struct Big {
   unsigned bits() const { return n ? 32 * (n - 1) + (32 - __builtin_clz(d[n - 1])) : 0; }
 };
 
+// Compact copy of a key (<= 256 bits) for the sorted secondary index: the bucket scan of
+// find_nearest_anahashes streams every key of a bucket, so the storage must be as dense as ibig's
+// (a 388-byte Big per key would make the CPU baseline memory-bound for no reason).
+struct CompactKey {
+  uint32_t n;
+  uint32_t d[8];
+};
+static inline bool fits_compact(const Big& b) { return b.n <= 8; }
+static inline CompactKey to_compact(const Big& b) {
+  CompactKey c;
+  c.n = b.n;
+  for (uint32_t i = 0; i < 8; ++i) c.d[i] = i < b.n ? b.d[i] : 0;
+  return c;
+}
+static inline Big from_compact(const CompactKey& c) {
+  Big b;
+  b.n = c.n;
+  for (uint32_t i = 0; i < c.n; ++i) b.d[i] = c.d[i];
+  return b;
+}
+// candidate.contains(value) (src/anahash.rs:165-171) on compact keys: `value > self -> false`, else
+// `self % value == 0`, with native 64/128-bit remainders when the operands are that small.
+static inline bool compact_contains(const CompactKey& self, const CompactKey& value) {
+  if (value.n > self.n) return false;
+  if (value.n == self.n) {
+    for (int i = (int)self.n - 1; i >= 0; --i) {
+      if (value.d[i] != self.d[i]) {
+        if (value.d[i] > self.d[i]) return false;
+        break;
+      }
+    }
+  }
+  if (self.n <= 2) {
+    const uint64_t a = (uint64_t)self.d[0] | ((uint64_t)self.d[1] << 32), b = (uint64_t)value.d[0] | ((uint64_t)value.d[1] << 32);
+    return a % b == 0;
+  }
+  if (self.n <= 4) {
+    typedef unsigned __int128 u128;
+    const u128 a = (u128)self.d[0] | ((u128)self.d[1] << 32) | ((u128)self.d[2] << 64) | ((u128)self.d[3] << 96);
+    const u128 b = (u128)value.d[0] | ((u128)value.d[1] << 32) | ((u128)value.d[2] << 64) | ((u128)value.d[3] << 96);
+    return a % b == 0;
+  }
+  return from_compact(self).divisible_by(from_compact(value));
+}
+
 struct BigHash {
   size_t operator()(const Big& b) const {
     uint64_t h = 1469598103934665603ULL;
@@ -1106,6 +1151,8 @@ struct Model {
   std::unordered_map<std::string, uint64_t> encoder;
   std::unordered_map<Big, IndexNode, BigHash> index;
   std::map<uint16_t, std::vector<Big>> sortedindex;
+  std::map<uint16_t, std::vector<CompactKey>> sortedcompact;  // dense copy of sortedindex when every key fits
+  bool all_compact = false;
   bool have_freq = false;
   Weights weights;
   std::vector<std::string> lexicons;
@@ -1250,6 +1297,12 @@ struct Model {
     }
     for (auto& kv : index) sortedindex[kv.second.charcount].push_back(kv.first);
     for (auto& kv : sortedindex) std::sort(kv.second.begin(), kv.second.end());
+    sortedcompact.clear();
+    all_compact = true;
+    for (auto& kv : index) all_compact = all_compact && fits_compact(kv.first);
+    if (all_compact)
+      for (auto& kv : sortedindex)
+        for (const Big& b : kv.second) sortedcompact[kv.first].push_back(to_compact(b));
   }
 
   bool has(const std::string& text) const {  // src/lib.rs:331-338
@@ -1307,6 +1360,24 @@ struct Model {
     for (auto& kv : lookups) {
       auto si = sortedindex.find((uint16_t)kv.first);
       if (si == sortedindex.end()) continue;
+      bool small = all_compact;
+      for (const Big& av : kv.second) small = small && fits_compact(av);
+      if (small) {
+        // same scan, dense operands (see CompactKey)
+        std::vector<CompactKey> avs;
+        for (const Big& av : kv.second) avs.push_back(to_compact(av));
+        const std::vector<CompactKey>& bucket = sortedcompact.at((uint16_t)kv.first);
+        for (size_t ci = 0; ci < bucket.size(); ++ci) {
+          for (const CompactKey& av : avs) {
+            if (st) ++st->modulo_tests;
+            if (compact_contains(bucket[ci], av)) {
+              nearest.insert(si->second[ci]);
+              break;
+            }
+          }
+        }
+        continue;
+      }
       for (const Big& candidate : si->second) {
         for (const Big& av : kv.second) {
           if (st) ++st->modulo_tests;
