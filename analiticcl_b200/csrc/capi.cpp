@@ -22,7 +22,7 @@ struct anl_result_set {
 };
 struct anl_match_set {
   std::vector<anl_match> matches;
-  std::vector<std::vector<anl_variant>> storage;
+  PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
 };
 struct anl_device_batch {
   DeviceBatch* b;
@@ -263,7 +263,10 @@ uint32_t anl_result_set_flags(const anl_result_set* rs, uint64_t i) {
 }
 void anl_result_set_free(anl_result_set* rs) { delete rs; }
 
-// find_all_matches: src/lib.rs:1790-1957 without the FST stage (see the header)
+// find_all_matches: src/lib.rs:1790-1957 without the FST stage (see the header).
+// The text is processed in windows of whole hard-delimited batches (bounded temporary memory); each
+// window costs two pipelined GPU batches: all unigrams, then the higher-order segments that the
+// unigram results do not make redundant (src/search.rs:317-336).
 anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, const anl_search_params* params,
                                 anl_match_set** out) {
   if (!m || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
@@ -271,80 +274,105 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
     return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_all_matches()");
   const std::string t(text ? text : "", len);
   anl_match_set* ms = new anl_match_set();
-  std::vector<SpanBatch> batches = segment_text(t, params->max_ngram);
-  // flat list of segments in the reference's output order
+  const std::vector<SpanBatch> batches = segment_text(t, params->max_ngram);
+  std::vector<uint64_t> cpmap;
+  if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
   struct Seg {
     SegmentSpan span;
-    size_t batch;
-    bool looked_up = false;
-    std::vector<anl_variant> variants;
+    uint32_t batch;
+    bool looked_up;
+    uint64_t off, cnt;  // into the window's result set (pass 1 or pass 2)
+    uint8_t pass;
   };
-  std::vector<Seg> segs;
-  for (size_t bi = 0; bi < batches.size(); ++bi)
-    for (const SegmentSpan& s : batches[bi].segments) segs.push_back(Seg{s, bi, false, {}});
   std::string err;
   int status = ANL_OK;
-  auto lookup = [&](const std::vector<size_t>& which) -> bool {
-    if (which.empty()) return true;
-    std::string blob;
-    std::vector<uint64_t> offs{0};
-    for (size_t k : which) {
+  size_t WINDOW = 1u << 18;  // unigram segments per window
+  if (const char* e = getenv("ANL_SEARCH_WINDOW")) WINDOW = (size_t)std::max(1, atoi(e));
+  std::vector<Seg> segs;
+  std::vector<size_t> pick;
+  std::string blob;
+  std::vector<uint64_t> offs;
+  ResultSet rs[2];
+  auto lookup = [&](int pass) -> bool {
+    blob.clear();
+    offs.assign(1, 0);
+    for (size_t k : pick) {
       blob.append(t, segs[k].span.begin, segs[k].span.end - segs[k].span.begin);
       offs.push_back(blob.size());
     }
-    ResultSet rs;
-    if (!m->engine.find_variants_batch(blob.data(), offs.data(), which.size(), *params, &rs, &err, &status)) return false;
-    for (size_t i = 0; i < which.size(); ++i) {
-      Seg& s = segs[which[i]];
+    rs[pass].offsets.assign(1, 0);
+    rs[pass].variants.clear();
+    if (pick.empty()) return true;
+    if (!m->engine.find_variants_batch(blob.data(), offs.data(), pick.size(), *params, &rs[pass], &err, &status)) return false;
+    for (size_t i = 0; i < pick.size(); ++i) {
+      Seg& s = segs[pick[i]];
       s.looked_up = true;
-      s.variants.assign(rs.variants.begin() + rs.offsets[i], rs.variants.begin() + rs.offsets[i + 1]);
+      s.pass = (uint8_t)pass;
+      s.off = rs[pass].offsets[i];
+      s.cnt = rs[pass].offsets[i + 1] - rs[pass].offsets[i];
     }
     return true;
   };
-  // pass 1: every unigram
-  std::vector<size_t> pass;
-  for (size_t k = 0; k < segs.size(); ++k)
-    if (segs[k].span.n == 1) pass.push_back(k);
-  bool ok = lookup(pass);
-  // pass 2: higher orders unless redundant (src/search.rs:317-336): every covered unigram of the same
-  // batch already has a best variant with dist_score >= 1.0
-  if (ok && params->max_ngram > 1) {
-    pass.clear();
-    size_t batch_start = 0;
-    for (size_t k = 0; k < segs.size(); ++k) {
-      if (k > 0 && segs[k].batch != segs[k - 1].batch) batch_start = k;
-      if (segs[k].span.n == 1) continue;
-      bool redundant = true;
-      for (size_t u = batch_start; u < segs.size() && segs[u].batch == segs[k].batch && segs[u].span.n == 1; ++u) {
-        if (segs[u].span.begin >= segs[k].span.begin && segs[u].span.end <= segs[k].span.end) {
-          if (segs[u].variants.empty() || segs[u].variants[0].dist_score < 1.0) {
-            redundant = false;
-            break;
+  bool ok = true;
+  size_t bi = 0;
+  while (ok && bi < batches.size()) {
+    // gather whole batches until the window holds enough unigrams
+    segs.clear();
+    size_t unigrams = 0;
+    while (bi < batches.size() && (unigrams < WINDOW || segs.empty())) {
+      for (const SegmentSpan& sp : batches[bi].segments) {
+        segs.push_back(Seg{sp, (uint32_t)bi, false, 0, 0, 0});
+        unigrams += sp.n == 1;
+      }
+      ++bi;
+    }
+    pick.clear();
+    for (size_t k = 0; k < segs.size(); ++k)
+      if (segs[k].span.n == 1) pick.push_back(k);
+    ok = lookup(0);
+    if (ok && params->max_ngram > 1) {
+      pick.clear();
+      size_t batch_start = 0;
+      for (size_t k = 0; k < segs.size(); ++k) {
+        if (k > 0 && segs[k].batch != segs[k - 1].batch) batch_start = k;
+        if (segs[k].span.n == 1) continue;
+        bool redundant = true;
+        for (size_t u = batch_start; u < segs.size() && segs[u].batch == segs[k].batch && segs[u].span.n == 1; ++u) {
+          if (segs[u].span.begin >= segs[k].span.begin && segs[u].span.end <= segs[k].span.end) {
+            if (segs[u].cnt == 0 || rs[0].variants[segs[u].off].dist_score < 1.0) {
+              redundant = false;
+              break;
+            }
           }
         }
+        if (!redundant) pick.push_back(k);
       }
-      if (!redundant) pass.push_back(k);
+      ok = lookup(1);
     }
-    ok = lookup(pass);
+    if (!ok) break;
+    for (const Seg& s : segs) {
+      anl_match mm;
+      mm.begin = params->unicodeoffsets ? cpmap[s.span.begin] : s.span.begin;
+      mm.end = params->unicodeoffsets ? cpmap[s.span.end] : s.span.end;
+      mm.n = s.span.n;
+      mm.n_variants = s.cnt;
+      mm.selected = (s.looked_up && s.cnt > 0) ? 0 : -1;
+      // variants pointer: index into the shared buffer for now, fixed up below (the buffer may move)
+      const uint64_t at = ms->variants.size();
+      mm.variants = s.looked_up ? reinterpret_cast<const anl_variant*>(at + 1) : nullptr;
+      if (s.cnt) {
+        ms->variants.resize(at + s.cnt);
+        memcpy(ms->variants.data() + at, rs[s.pass].variants.data() + s.off, s.cnt * sizeof(anl_variant));
+      }
+      ms->matches.push_back(mm);
+    }
   }
   if (!ok) {
     delete ms;
     return fail(status ? status : ANL_ERR_CUDA, err);
   }
-  std::vector<uint64_t> cpmap;
-  if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
-  ms->storage.resize(segs.size());
-  ms->matches.resize(segs.size());
-  for (size_t k = 0; k < segs.size(); ++k) {
-    ms->storage[k] = std::move(segs[k].variants);
-    anl_match& mm = ms->matches[k];
-    mm.begin = params->unicodeoffsets ? cpmap[segs[k].span.begin] : segs[k].span.begin;
-    mm.end = params->unicodeoffsets ? cpmap[segs[k].span.end] : segs[k].span.end;
-    mm.n = segs[k].span.n;
-    mm.n_variants = ms->storage[k].size();
-    mm.variants = segs[k].looked_up ? ms->storage[k].data() : nullptr;
-    mm.selected = (segs[k].looked_up && !ms->storage[k].empty()) ? 0 : -1;
-  }
+  for (anl_match& mm : ms->matches)
+    if (mm.variants) mm.variants = ms->variants.data() + (reinterpret_cast<uintptr_t>(mm.variants) - 1);
   *out = ms;
   return ANL_OK;
 }

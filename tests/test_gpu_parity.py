@@ -253,3 +253,35 @@ def test_weights_variants(A):
         o.build()
         sp = A.SearchParameters()
         assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, f"weights {wkw}")
+
+
+@pytest.mark.parametrize("max_ngram", [1, 2, 3])
+def test_find_all_matches_segments_parity(A, eng, eng_oracle, max_ngram, monkeypatch):
+    """find_all_matches batch producer (src/lib.rs:1790-1903): same segments (offsets, order), same
+    redundant-match pruning, same variant lists as the reference algorithm -- over several windows."""
+    import ctypes as C
+    from analiticcl_b200 import _capi
+    monkeypatch.setenv("ANL_SEARCH_WINDOW", "300")  # force several windows
+    text = workloads.cfg3_text(2500, 3001) + " It's a well-known co-operative re_entry; über naïve façade!?  Done"
+    sp = A.SearchParameters(max_ngram=max_ngram, max_anagram_distance=2, max_edit_distance=2)
+    raw = text.encode("utf-8")
+    ms = C.c_void_p()
+    L = _capi.lib()
+    assert L.anl_find_all_matches(eng._h, raw, len(raw), C.byref(sp.data), C.byref(ms)) == 0, L.anl_last_error()
+    exp = eng_oracle.find_all_segments(text, to_orc_params(sp))
+    n = L.anl_match_set_len(ms)
+    assert n == len(exp)
+    m = _capi.Match()
+    bad = []
+    for i in range(n):
+        assert L.anl_match_set_get(ms, i, C.byref(m)) == 0
+        e = exp[i]
+        got_vars = [(m.variants[j].vocab_id, bits(m.variants[j].dist_score), bits(m.variants[j].freq_score))
+                    for j in range(m.n_variants)] if m.variants else None
+        exp_vars = [(v, bits(d), bits(f)) for v, d, f in e["variants"]] if e["looked_up"] else None
+        if (m.begin, m.end, m.n) != (e["begin"], e["end"], e["n"]) or got_vars != exp_vars:
+            bad.append((i, e["text"], (m.begin, m.end, m.n), (e["begin"], e["end"], e["n"])))
+    L.anl_match_set_free(ms)
+    assert not bad, bad[:5]
+    if max_ngram > 1:
+        assert any(not e["looked_up"] for e in exp) and any(e["looked_up"] and e["n"] > 1 for e in exp)

@@ -240,3 +240,30 @@ def cfg5_queries(n=1_000_000, seed=5002, n_entries=10_000_000, lex_seed=5001):
         f.write("\n".join(qs) + "\n")
     os.replace(tmp, dst)
     return qs
+
+
+def cfg3_text(n_tokens=1_000_000, seed=3001, misspell=0.10):
+    """cfg 3: running text of `n_tokens` tokens drawn Zipf-like over the eng lexicon, 10 % misspelled
+    (cfg-1 generator), sentences of 8-20 tokens terminated by ". " (a multi-char boundary is Hard,
+    src/search.rs:245-247), single spaces otherwise."""
+    rng = np.random.default_rng(seed)
+    words = [w for w in read_words("eng") if w.isascii() and w.isalpha()]
+    nw = len(words)
+    # Zipf over a seeded permutation of the lexicon
+    ranks = np.minimum(nw - 1, (rng.zipf(1.15, size=n_tokens) - 1)).astype(np.int64)
+    perm = rng.permutation(nw)
+    idx = perm[ranks]
+    noisy = rng.random(n_tokens) < misspell
+    toks = []
+    for i in range(n_tokens):
+        w = words[int(idx[i])]
+        if noisy[i]:
+            w = _edit(w, rng) or w
+        toks.append(w)
+    out = []
+    i = 0
+    while i < n_tokens:
+        k = int(rng.integers(8, 21))
+        out.append(" ".join(toks[i:i + k]))
+        i += k
+    return ". ".join(out) + "."
