@@ -75,6 +75,26 @@ struct __attribute__((aligned(16))) MsetEntry {
 static const int ANL_MAX_K = 6;          // largest supported max_anagram_distance after thresholding
 static const int ANL_MAX_SYMBOLS = 236;  // longest query / entry (symbols) the device path accepts (row number + 16 fits a byte)
 
+// ---- confusable prefilter (device side) ------------------------------------------------------------
+// Late/early confusable rescoring runs on the host (it needs sesdiff's edit script), but most
+// (input, candidate) pairs cannot match any pattern: a `-[..]` / `+[..]` instruction can only match
+// characters of the input's / candidate's "middle" (what remains after stripping the common prefix
+// and suffix).  The score kernel evaluates that necessary condition for
+// pure-ASCII pairs and marks the records the host may skip.  Only patterns that an ASCII pair can
+// satisfy are in the table; each option is the set of characters it needs.
+struct ConfOpt {
+  uint64_t lo, hi;  // required characters: bit c of (lo | hi << 64)
+};
+struct ConfInstr {
+  int8_t op;        // -1 deletion, +1 insertion (identities impose nothing)
+  uint8_t n_opts;
+  uint16_t first_opt;
+};
+struct ConfPat {
+  uint16_t first_instr, n_instr;
+};
+static const uint32_t OUT_SKIP_CONFUSABLES = 0x80000000u;  // OutRec.vocab_id bit: no confusable can match this pair
+
 // ---- per-model constant data ------------------------------------------------------------------------
 struct DeviceIndex {
   const Slot* table;
@@ -95,6 +115,14 @@ struct DeviceIndex {
   const uint32_t* inst_vocab;  // vocab id per gather id
   const uint32_t* inst_freq;   // VocabValue.frequency per gather id
   const uint32_t* inst_gid;    // lexicon-sharded index only: global gather id per local gather id (else null)
+  // confusable prefilter (null / 0 when the model has no confusables)
+  const uint8_t* vocab_text;        // raw UTF-8 text of every vocabulary entry, back to back
+  const uint32_t* vocab_text_off;   // vocab id -> offset (n_vocab + 1 entries)
+  const ConfPat* conf_pats;
+  const ConfInstr* conf_instrs;
+  const ConfOpt* conf_opts;
+  uint32_t n_conf_pats;
+  int32_t conf_prefilter;           // 1: table valid, the kernel may set OUT_SKIP_CONFUSABLES
   const MsetEntry* mset;
   uint32_t mset_end[ANL_MAX_K + 1];  // mset_end[J] = number of entries with j <= J; [0] = 0
   const uint32_t* binom;             // [256][8] saturating binomials C(n, k)

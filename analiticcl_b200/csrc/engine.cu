@@ -110,6 +110,9 @@ Engine::~Engine() {
 void Engine::release_index() {
   for (void* p : index_allocs_) cudaFree(p);
   index_allocs_.clear();
+  for (void* p : conf_allocs_) cudaFree(p);
+  conf_allocs_.clear();
+  conf_uploaded_ = (size_t)-1;
   if (d_mset_) cudaFree(d_mset_);
   d_mset_ = nullptr;
   if (d_ix_) cudaFree(d_ix_);
@@ -209,6 +212,95 @@ bool Engine::ensure_msets(uint32_t J, std::string* err) {
   return true;
 }
 
+// Device copy of what the score kernel needs to prefilter confusable checks: the raw text of every
+// vocabulary entry and, per pattern an ASCII pair could satisfy, the character sets its deletion /
+// insertion options require.  Rebuilt when confusables or vocabulary changed since the last upload.
+bool Engine::ensure_confusable_table(std::string* err) {
+  const std::vector<Confusable>& cf = hm_->confusables;
+  if (conf_uploaded_ == cf.size() && conf_vocab_ == hm_->decoder.size()) return true;
+  CU_TRY(cudaDeviceSynchronize());
+  for (void* p : conf_allocs_) cudaFree(p);
+  conf_allocs_.clear();
+  h_ix_.vocab_text = nullptr;
+  h_ix_.vocab_text_off = nullptr;
+  h_ix_.conf_pats = nullptr;
+  h_ix_.conf_instrs = nullptr;
+  h_ix_.conf_opts = nullptr;
+  h_ix_.n_conf_pats = 0;
+  h_ix_.conf_prefilter = 0;
+  if (!cf.empty()) {
+    std::vector<ConfPat> pats;
+    std::vector<ConfInstr> instrs;
+    std::vector<ConfOpt> opts;
+    bool fits = true;
+    for (const Confusable& c : cf) {
+      ConfPat pat{(uint16_t)instrs.size(), 0};
+      const size_t instr_mark = instrs.size(), opt_mark = opts.size();
+      bool viable = true;
+      for (const ConfusableInstr& ins : c.script) {
+        if (ins.op == 0) continue;
+        ConfInstr ci{(int8_t)ins.op, 0, (uint16_t)opts.size()};
+        for (const std::string& o : ins.options) {
+          ConfOpt m{0, 0};
+          bool ascii = true;
+          for (unsigned char ch : o) {
+            if (ch >= 0x80) {
+              ascii = false;
+              break;
+            }
+            if (ch < 64) m.lo |= 1ull << ch; else m.hi |= 1ull << (ch - 64);
+          }
+          if (ascii && ci.n_opts < 255) {
+            opts.push_back(m);
+            ++ci.n_opts;
+          } else if (ascii) {
+            fits = false;
+          }
+        }
+        if (ci.n_opts == 0) {
+          viable = false;  // every option needs a non-ASCII character: impossible for an ASCII pair
+          break;
+        }
+        instrs.push_back(ci);
+        ++pat.n_instr;
+      }
+      if (!viable) {
+        instrs.resize(instr_mark);
+        opts.resize(opt_mark);
+        continue;
+      }
+      pats.push_back(pat);
+      if (instrs.size() > 60000 || opts.size() > 60000) fits = false;
+    }
+    if (fits && hm_->decoder.size() < 0x7FFFFFFFull) {
+      std::vector<uint8_t> text;
+      std::vector<uint32_t> off;
+      off.reserve(hm_->decoder.size() + 1);
+      size_t total = 0;
+      for (const VocabEntry& v : hm_->decoder) total += v.text.size();
+      if (total < 0xFFFFFFF0ull) {
+        text.reserve(total);
+        for (const VocabEntry& v : hm_->decoder) {
+          off.push_back((uint32_t)text.size());
+          text.insert(text.end(), v.text.begin(), v.text.end());
+        }
+        off.push_back((uint32_t)text.size());
+        if (!upload_vec(text, &h_ix_.vocab_text, &conf_allocs_, err)) return false;
+        if (!upload_vec(off, &h_ix_.vocab_text_off, &conf_allocs_, err)) return false;
+        if (!upload_vec(pats, &h_ix_.conf_pats, &conf_allocs_, err)) return false;
+        if (!upload_vec(instrs, &h_ix_.conf_instrs, &conf_allocs_, err)) return false;
+        if (!upload_vec(opts, &h_ix_.conf_opts, &conf_allocs_, err)) return false;
+        h_ix_.n_conf_pats = (uint32_t)pats.size();
+        h_ix_.conf_prefilter = 1;
+      }
+    }
+  }
+  CU_TRY(cudaMemcpy(d_ix_, &h_ix_, sizeof h_ix_, cudaMemcpyHostToDevice));
+  conf_uploaded_ = cf.size();
+  conf_vocab_ = hm_->decoder.size();
+  return true;
+}
+
 static uint32_t threshold_cap(const anl_distance_threshold& t) {
   // largest value the thresholded distance can take for any input (src/lib.rs:982-1012)
   if (t.kind == ANL_THRESHOLD_RATIO) return 12;
@@ -261,8 +353,10 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
 void Engine::destroy_batch(DeviceBatch* b) {
   if (!b) return;
   for (void* p : {(void*)b->h_rows, (void*)b->h_head, (void*)b->h_flags, (void*)b->h_hitcnt, (void*)b->h_out,
-                  (void*)b->h_work})
+                  (void*)b->h_work, (void*)b->h_qboff})
     if (p) cudaFreeHost(p);
+  if (b->d_qblob) cudaFree(b->d_qblob);
+  if (b->d_qboff) cudaFree(b->d_qboff);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
                   (void*)b->d_gid, (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
                   (void*)b->rr_hits, (void*)b->rr_hit_count, (void*)b->rr_qflags, (void*)b->rr_head, (void*)b->rr_out,
@@ -352,6 +446,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     *status = ANL_ERR_UNSUPPORTED;
     return nullptr;
   }
+  if (!ensure_confusable_table(err)) return nullptr;
   if (cudaSetDevice(device_) != cudaSuccess) {
     *err = "cudaSetDevice failed";
     return nullptr;
@@ -450,6 +545,33 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       return nullptr;
     }
   }
+  // raw query bytes for the device-side confusable prefilter (only when the host post-pass follows)
+  b->has_qblob = false;
+  const uint64_t blob_bytes = b->offsets[n];
+  if (h_ix_.conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER) && n > 0 &&
+      blob_bytes < 0xFFFFFFF0ull) {
+    std::string e2;
+    bool okb = true;
+    if (blob_bytes > b->cap_qblob || !b->d_qblob) {
+      okb = dev_realloc(&b->d_qblob, (size_t)blob_bytes + 16, &e2);
+      b->cap_qblob = okb ? (size_t)blob_bytes + 16 : 0;
+    }
+    if (okb && (n + 1 > b->cap_qboff || !b->d_qboff)) {
+      okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2);
+      b->cap_qboff = okb ? (size_t)n + 1 : 0;
+    }
+    if (!okb) {
+      *err = e2;
+      return fail();
+    }
+    for (uint64_t i = 0; i <= n; ++i) b->h_qboff[i] = (uint32_t)b->offsets[i];
+    if (cudaMemcpyAsync(b->d_qblob, b->blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+        cudaMemcpyAsync(b->d_qboff, b->h_qboff, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
+      *err = "H2D copy of the query text failed";
+      return fail();
+    }
+    b->has_qblob = true;
+  }
   pt.lap("create: encode");
   if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
     *err = "H2D copy failed";
@@ -468,6 +590,8 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   LaunchBuffers lb;
   lb.queries = b->d_rows;
   lb.qlist = nullptr;
+  lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
+  lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
   lb.n = b->n;
   lb.hits = b->d_hits;
   lb.hit_count = b->d_hit_count;
@@ -599,7 +723,8 @@ void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs,
   for (uint32_t i = 0; i < count; ++i) {
     // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with
     const double f = (double)recs[i].freq;
-    out->push_back(anl_variant{recs[i].vocab_id, recs[i].dist_score, max_freq > 0.0 ? f / max_freq : f, ANL_NO_VIA});
+    out->push_back(anl_variant{recs[i].vocab_id & ~OUT_SKIP_CONFUSABLES, recs[i].dist_score, max_freq > 0.0 ? f / max_freq : f,
+                               ANL_NO_VIA});
   }
   if (b.bp.finish_mode == FINISH_FULL || count == 0) return;
   const char* in = b.blob + b.offsets[qi];
@@ -608,6 +733,7 @@ void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs,
   anl_variant* v = out->data() + start;
   bool changed = false;
   for (uint32_t i = 0; i < count; ++i) {  // rescore_confusables, src/lib.rs:1656-1663
+    if (recs[i].vocab_id & OUT_SKIP_CONFUSABLES) continue;  // the score kernel proved that no pattern can match
     const double w = hm_->compute_confusable_weight(in, inlen, v[i].vocab_id);
     if (w != 1.0) {
       v[i].dist_score *= w;
@@ -672,6 +798,8 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
     LaunchBuffers lb;
     lb.queries = b->d_rows;
     lb.qlist = d_qlist;
+    lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
+    lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
     lb.n = m;
     lb.hits = d_hits;
     lb.hit_count = d_hit_count;
@@ -932,7 +1060,7 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
         anl_variant* dst = out->variants.data() + offs[i];
         for (uint32_t k = 0; k < c; ++k) {
           const double f = (double)r[k].freq;
-          dst[k] = anl_variant{r[k].vocab_id, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
+          dst[k] = anl_variant{r[k].vocab_id & ~OUT_SKIP_CONFUSABLES, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
         }
       }
     });

@@ -80,6 +80,11 @@ struct DeviceBatch {
   unsigned int* h_work = nullptr;  // [4]
   // device buffers
   uint8_t* d_rows = nullptr;
+  uint8_t* d_qblob = nullptr;   // raw query bytes (confusable prefilter), grow-only
+  uint32_t* d_qboff = nullptr;  // n + 1 byte offsets into d_qblob
+  uint32_t* h_qboff = nullptr;  // pinned staging of the offsets
+  size_t cap_qblob = 0, cap_qboff = 0;
+  bool has_qblob = false;
   uint32_t* d_hits = nullptr;
   uint32_t* d_hit_count = nullptr;
   uint32_t* d_qflags = nullptr;
@@ -118,6 +123,7 @@ class Engine {
   ~Engine();
   bool upload(int device, std::string* err);  // device side of build()
   bool ensure_msets(uint32_t J, std::string* err);
+  bool ensure_confusable_table(std::string* err);  // device copy of the confusable prefilter table + vocabulary text
   bool make_batch_params(const anl_search_params& p, BatchParams* bp, uint32_t* needed_j, std::string* err) const;
 
   // copy_blob: keep a private copy of the query text (device-batch API) or borrow it (one-shot call)
@@ -167,6 +173,9 @@ class Engine {
   DeviceIndex* d_ix_ = nullptr;
   std::vector<void*> index_allocs_;
   void* d_mset_ = nullptr;
+  std::vector<void*> conf_allocs_;
+  size_t conf_uploaded_ = (size_t)-1;  // number of confusables the device table was built from
+  size_t conf_vocab_ = 0;              // vocabulary size the device text blob was built from
   std::vector<DeviceBatch*> cache_;  // idle batches whose buffers can be reused
 };
 

@@ -519,12 +519,54 @@ __device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRe
   return a.g < b.g;
 }
 
+// Necessary condition for any confusable pattern to match the edit script of (a -> b); evaluated for
+// pure-ASCII pairs only (bytes == Unicode scalar values).  true = provably no pattern can match.
+__device__ __forceinline__ bool confusables_cannot_match(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
+                                                         const uint8_t* __restrict__ b, uint32_t nb) {
+  uint32_t hibits = 0;
+  for (uint32_t i = 0; i < na; ++i) hibits |= a[i];
+  for (uint32_t i = 0; i < nb; ++i) hibits |= b[i];
+  if (hibits & 0x80) return false;
+  uint32_t p = 0;
+  const uint32_t m = min(na, nb);
+  while (p < m && a[p] == b[p]) ++p;
+  uint32_t s = 0;
+  while (s < m - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
+  uint64_t alo = 0, ahi = 0, blo = 0, bhi = 0;
+  for (uint32_t i = p; i < na - s; ++i) {
+    const uint32_t ch = a[i];
+    if (ch < 64) alo |= 1ull << ch; else ahi |= 1ull << (ch - 64);
+  }
+  for (uint32_t i = p; i < nb - s; ++i) {
+    const uint32_t ch = b[i];
+    if (ch < 64) blo |= 1ull << ch; else bhi |= 1ull << (ch - 64);
+  }
+  for (uint32_t k = 0; k < ix->n_conf_pats; ++k) {
+    const ConfPat pat = ix->conf_pats[k];
+    bool possible = true;
+    for (uint32_t q = 0; q < pat.n_instr && possible; ++q) {
+      const ConfInstr ins = ix->conf_instrs[pat.first_instr + q];
+      const uint64_t slo = ins.op < 0 ? alo : blo, shi = ins.op < 0 ? ahi : bhi;
+      bool any = false;
+      for (uint32_t o = 0; o < ins.n_opts && !any; ++o) {
+        const ConfOpt opt = ix->conf_opts[ins.first_opt + o];
+        any = ((opt.lo & ~slo) | (opt.hi & ~shi)) == 0;
+      }
+      possible = any;
+    }
+    if (possible) return false;
+  }
+  return true;
+}
+
 // The tail shared by score_kernel and merge_kernel: frequency normalisation, ranking, crop, cut-off and
 // the packed emission of one query's survivors.  Returns the number of results written (lane 0 only).
 __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRec* surv, SurvRec* sorted, uint32_t nsurv,
                                                  double maxfreq, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
                                                  OutHead* __restrict__ out_head, uint32_t qi, uint32_t flags,
-                                                 uint32_t* __restrict__ qflags, unsigned int* pool_cursor) {
+                                                 uint32_t* __restrict__ qflags, unsigned int* pool_cursor,
+                                                 const DeviceIndex* ix = nullptr, const uint8_t* qraw = nullptr,
+                                                 uint32_t qraw_len = 0) {
   const uint32_t lane = lane_id();
   // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
   // (surv keeps the raw frequency in `raw`; `freq` becomes the normalised score, `key` the combined one)
@@ -612,6 +654,11 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
       OutRec o;
       o.dist_score = r.dist;
       o.vocab_id = r.vocab;
+      if (qraw) {
+        // confusable prefilter: spare the host the edit script when no pattern can match this pair
+        const uint32_t t0 = __ldg(ix->vocab_text_off + r.vocab), t1 = __ldg(ix->vocab_text_off + r.vocab + 1);
+        if (confusables_cannot_match(ix, qraw, qraw_len, ix->vocab_text + t0, t1 - t0)) o.vocab_id |= OUT_SKIP_CONFUSABLES;
+      }
       o.freq = r.raw;
       out[off + i] = o;
       if (out_gid) out_gid[off + i] = r.g;
@@ -632,7 +679,8 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
-             const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
+             const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+             uint32_t nq, const uint32_t* __restrict__ hits,
              const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
              unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R) {
@@ -824,7 +872,15 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       __syncwarp();
     }
 
-    c_res += rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags, qflags, pool_cursor);
+    const uint8_t* qraw = nullptr;
+    uint32_t qraw_len = 0;
+    if (qblob && ix->conf_prefilter && bp.finish_mode != FINISH_FULL && bp.finish_mode != FINISH_SHARD) {
+      const uint32_t b0 = qboff[q], b1 = qboff[q + 1];
+      qraw = qblob + b0;
+      qraw_len = b1 - b0;
+    }
+    c_res += rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags, qflags, pool_cursor, ix, qraw,
+                            qraw_len);
   }
 
   if (counters) {
@@ -1010,7 +1066,7 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
-score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
+score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.n, lb.hits, lb.hit_count,
                                                                 lb.qflags, lb.out, lb.out_gid, lb.out_head, scratch,
                                                                 lb.work + 1, lb.work + 2, lb.counters, h_ix.max_len, R);
   return cudaGetLastError();

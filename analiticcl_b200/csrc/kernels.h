@@ -11,6 +11,8 @@ namespace anl {
 struct LaunchBuffers {
   const uint8_t* queries = nullptr;  // [n_total][query_stride] encoded query rows
   const uint32_t* qlist = nullptr;   // optional: indices into `queries` (rerun of selected queries); nullptr = identity
+  const uint8_t* qblob = nullptr;    // optional: raw UTF-8 of the queries (confusable prefilter)
+  const uint32_t* qboff = nullptr;   //           byte offsets into qblob, n_total + 1 entries
   uint32_t n = 0;                    // number of queries in this launch
   uint32_t* hits = nullptr;          // [n][hit_cap] gather ids of candidate instances
   uint32_t* hit_count = nullptr;     // [n]
