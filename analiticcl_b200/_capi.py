@@ -100,6 +100,7 @@ SIGNATURES = {
     "anl_normalize": (_i64, [_vp, _cp, _sz, _P(C.c_uint8), _sz]),
     "anl_anahash": (_i64, [_vp, _cp, _sz, _P(_u64), _sz]),
     "anl_shortest_edit_script": (_i64, [_cp, _sz, _cp, _sz, C.c_char_p, _sz]),
+    "anl_shortest_edit_script_fixed": (_i64, [_cp, _sz, _cp, _sz, C.c_char_p, _sz]),
     "anl_confusable_found_in": (_i32, [_cp, _cp, _sz, _cp, _sz]),
     "anl_find_variants_batch": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_result_set_len": (_u64, [_vp]),
@@ -114,7 +115,7 @@ SIGNATURES = {
     "anl_match_set_free": (None, [_vp]),
     "anl_device_batch_create": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_device_batch_run": (_i32, [_vp, _vp, _vp]),
-    "anl_device_batch_timings": (_i32, [_vp, _vp, _P(C.c_float), _P(C.c_float)]),
+    "anl_device_batch_timings": (_i32, [_vp, _vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),
     "anl_device_batch_fetch": (_i32, [_vp, _vp, _P(_vp)]),
     "anl_device_batch_free": (None, [_vp, _vp]),
     "anl_device_batch_counters": (_i32, [_vp, _vp, _P(Counters)]),

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/analiticcl_b200.h"
+#include "editscript_fixed.h"
 #include "engine.h"
 #include "host_model.h"
 #include "search.h"
@@ -225,6 +226,31 @@ int64_t anl_shortest_edit_script(const char* src, size_t src_len, const char* ds
   }
   return (int64_t)text.size();
 }
+int64_t anl_shortest_edit_script_fixed(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap) {
+  // host build of the code the confusable kernel runs per thread (csrc/editscript_fixed.h)
+  for (size_t i = 0; i < src_len; ++i)
+    if ((unsigned char)src[i] >= 0x80) return -1;
+  for (size_t i = 0; i < dst_len; ++i)
+    if ((unsigned char)dst[i] >= 0x80) return -1;
+  if (src_len > (size_t)esf::MAXLEN || dst_len > (size_t)esf::MAXLEN) return -1;
+  esf::View v[esf::MAXSEG];
+  const uint8_t* a = reinterpret_cast<const uint8_t*>(src);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(dst);
+  const int nv = esf::shortest_edit_script(a, (int)src_len, b, (int)dst_len, v);
+  if (nv < 0) return -1;
+  std::string text;
+  for (int i = 0; i < nv; ++i) {
+    text += v[i].op == 0 ? "=[" : (v[i].op > 0 ? "+[" : "-[");
+    text.append(reinterpret_cast<const char*>((v[i].op > 0 ? b : a) + v[i].pos), v[i].len);
+    text += "]";
+  }
+  if (out && cap) {
+    const size_t n = std::min(text.size(), cap - 1);
+    memcpy(out, text.data(), n);
+    out[n] = 0;
+  }
+  return (int64_t)text.size();
+}
 int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src_len, const char* dst, size_t dst_len) {
   Confusable c;
   if (!pattern || !parse_confusable(pattern, 1.0, &c)) return -1;
@@ -401,10 +427,10 @@ anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream)
   if (!m->engine.run_batch(b->b, reinterpret_cast<cudaStream_t>(stream), &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
-anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms) {
+anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms) {
   if (!m || !b || !probe_ms || !score_ms) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
-  if (!m->engine.timings(b->b, probe_ms, score_ms, &err)) return fail(ANL_ERR_CUDA, err);
+  if (!m->engine.timings(b->b, probe_ms, score_ms, rescore_ms, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
 anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) {

@@ -75,25 +75,42 @@ struct __attribute__((aligned(16))) MsetEntry {
 static const int ANL_MAX_K = 6;          // largest supported max_anagram_distance after thresholding
 static const int ANL_MAX_SYMBOLS = 236;  // longest query / entry (symbols) the device path accepts (row number + 16 fits a byte)
 
-// ---- confusable prefilter (device side) ------------------------------------------------------------
-// Late/early confusable rescoring runs on the host (it needs sesdiff's edit script), but most
-// (input, candidate) pairs cannot match any pattern: a `-[..]` / `+[..]` instruction can only match
-// characters of the input's / candidate's "middle" (what remains after stripping the common prefix
-// and suffix).  The score kernel evaluates that necessary condition for
-// pure-ASCII pairs and marks the records the host may skip.  Only patterns that an ASCII pair can
-// satisfy are in the table; each option is the set of characters it needs.
+// ---- confusables on the device ---------------------------------------------------------------------
+// Confusable rescoring (src/lib.rs:1656-1663,1733-1756) needs sesdiff's edit script of the raw strings.
+// Two device stages handle pure-ASCII pairs (bytes == Unicode scalar values):
+//  (1) prefilter, in the score kernel: a `-[..]` / `+[..]` instruction can only match characters of the
+//      input's / candidate's "middle" (what remains after stripping the common prefix and suffix; see
+//      DESIGN.md section 7).  Pairs that fail this necessary condition are settled with weight 1.
+//  (2) confusable kernel (confusables.cu): the full edit script + pattern matching, one pair per thread
+//      (editscript_fixed.h), for the pairs that pass (1).
+// Only patterns an ASCII pair can satisfy are in the table (options with non-ASCII text are dropped; a
+// pattern with an instruction that has no ASCII option is dropped).  Whatever the device cannot settle
+// (non-ASCII text, very long strings) is left to the host post-pass.
 struct ConfOpt {
-  uint64_t lo, hi;  // required characters: bit c of (lo | hi << 64)
+  uint64_t lo, hi;     // characters the option needs: bit c of (lo | hi << 64)
+  uint32_t text_off;   // the option's text inside DeviceIndex::conf_text
+  uint32_t text_len;
 };
 struct ConfInstr {
-  int8_t op;        // -1 deletion, +1 insertion (identities impose nothing)
+  int8_t op;           // -1 deletion, +1 insertion, 0 identity
   uint8_t n_opts;
   uint16_t first_opt;
 };
 struct ConfPat {
+  double weight;
   uint16_t first_instr, n_instr;
+  uint8_t strictbegin, strictend;  // `^` / `$` anchors
+  uint8_t pad[2];
 };
-static const uint32_t OUT_SKIP_CONFUSABLES = 0x80000000u;  // OutRec.vocab_id bit: no confusable can match this pair
+// OutRec.vocab_id bit 31: this record's confusable weight is settled (already applied, or provably 1)
+static const uint32_t OUT_SKIP_CONFUSABLES = 0x80000000u;
+// OutHead.count bit 31: the device could not settle every record of this query -- the host finishes it
+static const uint32_t HEAD_HOST_FINISH = 0x80000000u;
+// one (query, record) pair queued for the confusable kernel
+struct ConfWork {
+  uint32_t rec;    // record index in the result pool
+  uint32_t query;  // query row (index into the batch's raw text offsets)
+};
 
 // ---- per-model constant data ------------------------------------------------------------------------
 struct DeviceIndex {
@@ -121,6 +138,7 @@ struct DeviceIndex {
   const ConfPat* conf_pats;
   const ConfInstr* conf_instrs;
   const ConfOpt* conf_opts;
+  const uint8_t* conf_text;         // option texts of the patterns, back to back
   uint32_t n_conf_pats;
   int32_t conf_prefilter;           // 1: table valid, the kernel may set OUT_SKIP_CONFUSABLES
   const MsetEntry* mset;

@@ -226,22 +226,28 @@ bool Engine::ensure_confusable_table(std::string* err) {
   h_ix_.conf_pats = nullptr;
   h_ix_.conf_instrs = nullptr;
   h_ix_.conf_opts = nullptr;
+  h_ix_.conf_text = nullptr;
   h_ix_.n_conf_pats = 0;
   h_ix_.conf_prefilter = 0;
   if (!cf.empty()) {
     std::vector<ConfPat> pats;
     std::vector<ConfInstr> instrs;
     std::vector<ConfOpt> opts;
+    std::vector<uint8_t> ctext;
     bool fits = true;
     for (const Confusable& c : cf) {
-      ConfPat pat{(uint16_t)instrs.size(), 0};
-      const size_t instr_mark = instrs.size(), opt_mark = opts.size();
+      ConfPat pat;
+      memset(&pat, 0, sizeof pat);
+      pat.weight = c.weight;
+      pat.first_instr = (uint16_t)instrs.size();
+      pat.strictbegin = c.strictbegin ? 1 : 0;
+      pat.strictend = c.strictend ? 1 : 0;
+      const size_t instr_mark = instrs.size(), opt_mark = opts.size(), text_mark = ctext.size();
       bool viable = true;
       for (const ConfusableInstr& ins : c.script) {
-        if (ins.op == 0) continue;
         ConfInstr ci{(int8_t)ins.op, 0, (uint16_t)opts.size()};
         for (const std::string& o : ins.options) {
-          ConfOpt m{0, 0};
+          ConfOpt m{0, 0, (uint32_t)ctext.size(), (uint32_t)o.size()};
           bool ascii = true;
           for (unsigned char ch : o) {
             if (ch >= 0x80) {
@@ -250,10 +256,12 @@ bool Engine::ensure_confusable_table(std::string* err) {
             }
             if (ch < 64) m.lo |= 1ull << ch; else m.hi |= 1ull << (ch - 64);
           }
-          if (ascii && ci.n_opts < 255) {
+          if (!ascii) continue;  // cannot match the text of an ASCII pair
+          if (ci.n_opts < 255) {
             opts.push_back(m);
+            ctext.insert(ctext.end(), o.begin(), o.end());
             ++ci.n_opts;
-          } else if (ascii) {
+          } else {
             fits = false;
           }
         }
@@ -264,14 +272,16 @@ bool Engine::ensure_confusable_table(std::string* err) {
         instrs.push_back(ci);
         ++pat.n_instr;
       }
-      if (!viable) {
+      if (!viable || pat.n_instr == 0) {
         instrs.resize(instr_mark);
         opts.resize(opt_mark);
+        ctext.resize(text_mark);
         continue;
       }
       pats.push_back(pat);
       if (instrs.size() > 60000 || opts.size() > 60000) fits = false;
     }
+    ctext.push_back(0);
     if (fits && hm_->decoder.size() < 0x7FFFFFFFull) {
       std::vector<uint8_t> text;
       std::vector<uint32_t> off;
@@ -290,6 +300,7 @@ bool Engine::ensure_confusable_table(std::string* err) {
         if (!upload_vec(pats, &h_ix_.conf_pats, &conf_allocs_, err)) return false;
         if (!upload_vec(instrs, &h_ix_.conf_instrs, &conf_allocs_, err)) return false;
         if (!upload_vec(opts, &h_ix_.conf_opts, &conf_allocs_, err)) return false;
+        if (!upload_vec(ctext, &h_ix_.conf_text, &conf_allocs_, err)) return false;
         h_ix_.n_conf_pats = (uint32_t)pats.size();
         h_ix_.conf_prefilter = 1;
       }
@@ -357,6 +368,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
     if (p) cudaFreeHost(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
+  if (b->d_conf_work) cudaFree(b->d_conf_work);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
                   (void*)b->d_gid, (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
                   (void*)b->rr_hits, (void*)b->rr_hit_count, (void*)b->rr_qflags, (void*)b->rr_head, (void*)b->rr_out,
@@ -385,10 +397,12 @@ void Engine::free_batch(DeviceBatch* b) {
 
 bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err) {
   const bool need_gid = hm_->index.n_shards > 1;
-  if (pool_cap <= b->cap_pool && b->d_out && (!need_gid || b->d_gid)) return true;
+  const bool need_cw = h_ix_.conf_prefilter && !need_gid;  // the confusable queue can hold every pool record
+  if (pool_cap <= b->cap_pool && b->d_out && (!need_gid || b->d_gid) && (!need_cw || b->d_conf_work)) return true;
   pool_cap = std::max(pool_cap, b->cap_pool);
   if (!dev_realloc(&b->d_out, pool_cap, err)) return false;
   if (need_gid && !dev_realloc(&b->d_gid, pool_cap, err)) return false;
+  if (need_cw && !dev_realloc(&b->d_conf_work, pool_cap, err)) return false;
   if (!pinned_realloc(&b->h_out, pool_cap, err)) return false;
   b->cap_pool = pool_cap;
   return true;
@@ -572,6 +586,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     }
     b->has_qblob = true;
   }
+  b->dev_conf = b->has_qblob && b->d_conf_work != nullptr && !b->sharded;
   pt.lap("create: encode");
   if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
     *err = "H2D copy failed";
@@ -592,6 +607,7 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   lb.qlist = nullptr;
   lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
+  lb.conf_work = b->dev_conf ? b->d_conf_work : nullptr;
   lb.n = b->n;
   lb.hits = b->d_hits;
   lb.hit_count = b->d_hit_count;
@@ -613,42 +629,49 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
     CU_TRY(cudaStreamWaitEvent(stream, b->uploaded, 0));  // foreign stream: order after the H2D copy
   LaunchBuffers lb = launch_buffers(b);
   if (b->runs_recorded >= 1024) b->runs_recorded = 0;  // keep the newest window
-  while (b->events.size() < (size_t)(b->runs_recorded + 1) * 3) {
+  while (b->events.size() < (size_t)(b->runs_recorded + 1) * EV_PER_RUN) {
     cudaEvent_t ev = nullptr;
     CU_TRY(cudaEventCreate(&ev));
     b->events.push_back(ev);
   }
-  cudaEvent_t* ev = b->events.data() + (size_t)b->runs_recorded * 3;
+  cudaEvent_t* ev = b->events.data() + (size_t)b->runs_recorded * EV_PER_RUN;
   CU_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), stream));
   CU_TRY(cudaEventRecord(ev[0], stream));
   CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[1], stream));
   CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[2], stream));
-  b->last_done = ev[2];
+  CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, stream));
+  CU_TRY(cudaEventRecord(ev[3], stream));
+  CU_TRY(launch_finish(b->bp, lb, sm_count_, stream));
+  CU_TRY(cudaEventRecord(ev[4], stream));
+  b->last_done = ev[4];
   ++b->runs_recorded;
   b->ran = true;
   return true;
 }
 
-bool Engine::timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::string* err) {
+bool Engine::timings(DeviceBatch* b, float* probe_ms, float* score_ms, float* rescore_ms, std::string* err) {
   if (!b->ran) {
     *err = "batch has not been run";
     return false;
   }
   // averages over the runs since the previous call (CUDA events on the launching stream)
   CU_TRY(cudaEventSynchronize(b->last_done));
-  double p = 0, s = 0;
+  double p = 0, s = 0, x = 0;
   for (uint32_t r = 0; r < b->runs_recorded; ++r) {
-    float a = 0, c = 0;
-    CU_TRY(cudaEventElapsedTime(&a, b->events[r * 3 + 0], b->events[r * 3 + 1]));
-    CU_TRY(cudaEventElapsedTime(&c, b->events[r * 3 + 1], b->events[r * 3 + 2]));
+    float a = 0, c = 0, d = 0;
+    CU_TRY(cudaEventElapsedTime(&a, b->events[r * EV_PER_RUN + 0], b->events[r * EV_PER_RUN + 1]));
+    CU_TRY(cudaEventElapsedTime(&c, b->events[r * EV_PER_RUN + 1], b->events[r * EV_PER_RUN + 2]));
+    CU_TRY(cudaEventElapsedTime(&d, b->events[r * EV_PER_RUN + 2], b->events[r * EV_PER_RUN + 4]));
     p += a;
     s += c;
+    x += d;
   }
   const uint32_t nr = std::max(1u, b->runs_recorded);
   *probe_ms = (float)(p / nr);
   *score_ms = (float)(s / nr);
+  if (rescore_ms) *rescore_ms = (float)(x / nr);
   b->runs_recorded = 0;
   return true;
 }
@@ -741,8 +764,9 @@ void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs,
     }
   }
   size_t n = count;
-  // a stable sort of an already sorted list is the identity: only re-rank when a score changed
-  if (changed || b.bp.finish_mode == FINISH_GATHER) rank_variants(v, v + n, fw);
+  // a stable sort of an already sorted list is the identity: only re-rank when a score changed (with the
+  // device confusable stage, settled records of this query may already carry their weight)
+  if (changed || b.dev_conf || b.bp.finish_mode == FINISH_GATHER) rank_variants(v, v + n, fw);
   if (b.bp.finish_mode == FINISH_GATHER) n = crop_variants(v, n, (size_t)b.params.max_matches, fw);
   n = cutoff_variants(v, n, b.params.cutoff_threshold, fw);
   out->resize(start + n);
@@ -858,6 +882,8 @@ bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* e
     LaunchBuffers lb = launch_buffers(b);
     lb.counters = nullptr;
     CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, st));
+    CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, st));
+    CU_TRY(launch_finish(b->bp, lb, sm_count_, st));
     CU_TRY(cudaEventRecord(b->last_done, st));
     b->reruns += 1;
   }
@@ -1012,17 +1038,21 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
   }
   pt.lap("fetch: hit-overflow reruns");
 
-  auto locate = [&](uint32_t i, const OutRec** recs, uint32_t* count, double* maxf) {
+  // host = the device did not (or could not) finish this query: confusable rescoring, re-rank, cut-off follow here
+  const bool post_pass = b->bp.finish_mode != FINISH_FULL;
+  auto locate = [&](uint32_t i, const OutRec** recs, uint32_t* count, double* maxf, bool* host) {
     if (!rr_index.empty() && rr_index[i] >= 0) {
       const OutHead& h = rr_heads[rr_index[i]];
       *recs = rr_recs.data() + h.offset;
-      *count = h.count;
+      *count = h.count & ~HEAD_HOST_FINISH;
       *maxf = h.max_freq;
+      *host = post_pass;  // reruns skip the device confusable stage
     } else {
       const OutHead& h = b->h_head[i];
       *recs = b->h_out + h.offset;
-      *count = h.count;
+      *count = h.count & ~HEAD_HOST_FINISH;
       *maxf = h.max_freq;
+      *host = post_pass && (!b->dev_conf || (h.count & HEAD_HOST_FINISH));
     }
   };
   if (!append || out->offsets.empty()) {
@@ -1038,69 +1068,76 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
   for (uint32_t i = 0; i < n; ++i)
     if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[qbase + i] |= 1;
 
-  if (b->bp.finish_mode == FINISH_FULL) {
-    // counts are final: prefix-sum the offsets, then convert in parallel straight into place
-    uint64_t tot = vbase;
+  // pass 1: queries the host must finish go through finish_query into per-thread side buffers; the
+  // counts of all other queries are final as they come from the device
+  const unsigned maxt = host_threads();
+  std::vector<std::vector<anl_variant>> part(post_pass ? maxt : 0);
+  std::vector<uint32_t> counts(n, 0), side_pos(post_pass ? n : 0, 0);
+  uint64_t host_queries = 0;
+  if (post_pass) {
+    std::vector<uint64_t> hq(maxt, 0);
+    parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
+      std::vector<anl_variant>& buf = part[t];
+      for (uint64_t i = lo; i < hi; ++i) {
+        const OutRec* r;
+        uint32_t c;
+        double mf;
+        bool host;
+        locate((uint32_t)i, &r, &c, &mf, &host);
+        if (!host) {
+          counts[i] = c;
+          continue;
+        }
+        const size_t before = buf.size();
+        finish_query(*b, i, r, c, mf, &buf);
+        side_pos[i] = (uint32_t)before;
+        counts[i] = (uint32_t)(buf.size() - before);
+        ++hq[t];
+      }
+    });
+    for (uint64_t v : hq) host_queries += v;
+  } else {
     for (uint32_t i = 0; i < n; ++i) {
+      const OutRec* r;
+      double mf;
+      bool host;
+      locate(i, &r, &counts[i], &mf, &host);
+    }
+  }
+  uint64_t tot = vbase;
+  for (uint32_t i = 0; i < n; ++i) {
+    offs[i] = tot;
+    tot += counts[i];
+  }
+  offs[n] = tot;
+  out->variants.resize(tot);
+  // pass 2: convert / copy straight into place (same thread ranges as pass 1)
+  parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i) {
       const OutRec* r;
       uint32_t c;
       double mf;
-      locate(i, &r, &c, &mf);
-      offs[i] = tot;
-      tot += c;
-    }
-    offs[n] = tot;
-    out->variants.resize(tot);
-    parallel_ranges(n, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; ++i) {
-        const OutRec* r;
-        uint32_t c;
-        double mf;
-        locate((uint32_t)i, &r, &c, &mf);
-        anl_variant* dst = out->variants.data() + offs[i];
-        for (uint32_t k = 0; k < c; ++k) {
-          const double f = (double)r[k].freq;
-          dst[k] = anl_variant{r[k].vocab_id & ~OUT_SKIP_CONFUSABLES, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
-        }
+      bool host;
+      locate((uint32_t)i, &r, &c, &mf, &host);
+      anl_variant* dst = out->variants.data() + offs[i];
+      if (host) {
+        if (counts[i]) memcpy(dst, part[t].data() + side_pos[i], (size_t)counts[i] * sizeof(anl_variant));
+        continue;
       }
-    });
-    b->results = tot - vbase;
-  } else {
-    // confusable post-pass: each thread finishes a contiguous range of queries into its own buffer
-    const unsigned maxt = host_threads();
-    std::vector<std::vector<anl_variant>> part(maxt);
-    std::vector<std::pair<uint64_t, uint64_t>> ranges(maxt, {0, 0});
-    std::vector<uint32_t> counts(n, 0);
-    parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
-      ranges[t] = {lo, hi};
-      std::vector<anl_variant>& buf = part[t];
-      buf.reserve((size_t)(hi - lo) * 8);
-      for (uint64_t i = lo; i < hi; ++i) {
-        const OutRec* r;
-        uint32_t c;
-        double mf;
-        locate((uint32_t)i, &r, &c, &mf);
-        const size_t before = buf.size();
-        finish_query(*b, i, r, c, mf, &buf);
-        counts[i] = (uint32_t)(buf.size() - before);
+      for (uint32_t k = 0; k < c; ++k) {
+        // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with
+        const double f = (double)r[k].freq;
+        dst[k] = anl_variant{r[k].vocab_id & ~OUT_SKIP_CONFUSABLES, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
       }
-    });
-    uint64_t tot = vbase;
-    for (uint32_t i = 0; i < n; ++i) {
-      offs[i] = tot;
-      tot += counts[i];
     }
-    offs[n] = tot;
-    out->variants.resize(tot);
-    for (unsigned t = 0; t < maxt; ++t)
-      if (!part[t].empty())
-        memcpy(out->variants.data() + offs[ranges[t].first], part[t].data(), part[t].size() * sizeof(anl_variant));
-    b->results = tot - vbase;
-  }
+  });
+  b->results = tot - vbase;
   pt.lap("fetch: post-pass+assemble");
   if (profile_enabled() && b->bp.finish_mode != FINISH_FULL) {
     uint64_t v[4];
     confusable_stats(v);
+    fprintf(stderr, "[anl profile] %llu of %u queries finished on the host (device confusables: %s)\n",
+            (unsigned long long)host_queries, n, b->dev_conf ? "on" : "off");
     fprintf(stderr, "[anl profile] confusable checks %llu, prefilter pass %llu (ascii), single-edit fast %llu, full script %llu\n",
             (unsigned long long)v[0], (unsigned long long)v[1], (unsigned long long)v[2], (unsigned long long)v[3]);
   }

@@ -59,6 +59,7 @@ struct ResultSet {
 
 // Everything one pass over a batch of queries needs, on the device and in pinned host memory.
 // Buffers are capacity-based and recycled through Engine's cache: steady-state calls allocate nothing.
+static const int EV_PER_RUN = 5;
 struct DeviceBatch {
   // ---- capacities (what the buffers can hold) ----
   uint32_t cap_n = 0, cap_pool = 0;
@@ -85,6 +86,8 @@ struct DeviceBatch {
   uint32_t* h_qboff = nullptr;  // pinned staging of the offsets
   size_t cap_qblob = 0, cap_qboff = 0;
   bool has_qblob = false;
+  ConfWork* d_conf_work = nullptr;  // queue of (record, query) pairs for the confusable kernel, sized like d_out
+  bool dev_conf = false;            // this batch's confusables are rescored on the device (HEAD_HOST_FINISH marks the rest)
   uint32_t* d_hits = nullptr;
   uint32_t* d_hit_count = nullptr;
   uint32_t* d_qflags = nullptr;
@@ -105,7 +108,7 @@ struct DeviceBatch {
   size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;
   cudaStream_t stream = nullptr;    // this batch's own stream (copies + default launches)
   cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
-  // one event triple (start, after probe, after score) per run since the last timings() call
+  // EV_PER_RUN events (start, after probe, after score, after confusables, after finish) per run since the last timings() call
   std::vector<cudaEvent_t> events;
   uint32_t runs_recorded = 0;
   cudaEvent_t last_done = nullptr;  // end event of the most recent run
@@ -134,7 +137,7 @@ class Engine {
   // append: add this batch's queries after the ones already in `out` (pipelined chunks)
   bool fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status);
   void free_batch(DeviceBatch* b);  // returns the buffers to the cache
-  bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, std::string* err);
+  bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, float* rescore_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);
 
   // lexicon-sharded mode (see include/analiticcl_b200.h)

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "device_types.h"
+#include "editscript_fixed.h"
 #include "kernels.h"
 
 namespace anl {
@@ -508,8 +509,8 @@ __device__ __forceinline__ double result_score(const BatchParams& bp, double dis
 }
 // rank_cmp (src/types.rs:344-365) with the gather id as the final key (== stable sort of the
 // reference's gather order)
-__device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRec& a, const SurvRec& b) {
-  if (bp.finish_mode == FINISH_GATHER) return a.g < b.g;
+__device__ __forceinline__ bool ranks_before(const BatchParams& bp, bool gather_order, const SurvRec& a, const SurvRec& b) {
+  if (gather_order) return a.g < b.g;
   if (bp.freq_weight_positive) {
     if (a.key != b.key) return a.key > b.key;
     return a.g < b.g;
@@ -519,14 +520,17 @@ __device__ __forceinline__ bool ranks_before(const BatchParams& bp, const SurvRe
   return a.g < b.g;
 }
 
-// Necessary condition for any confusable pattern to match the edit script of (a -> b); evaluated for
-// pure-ASCII pairs only (bytes == Unicode scalar values).  true = provably no pattern can match.
-__device__ __forceinline__ bool confusables_cannot_match(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
-                                                         const uint8_t* __restrict__ b, uint32_t nb) {
+// Triage of one (input a, candidate b) pair for confusable rescoring.
+//   CONF_SETTLED : provably no pattern can match (necessary condition on the pair's "middle") -> weight 1
+//   CONF_QUEUE   : a pattern may match -> the confusable kernel computes the edit script
+//   CONF_HOST    : non-ASCII text or longer than the device edit script handles -> host post-pass
+constexpr int CONF_SETTLED = 0, CONF_QUEUE = 1, CONF_HOST = 2;
+__device__ __forceinline__ int confusable_triage(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
+                                                 const uint8_t* __restrict__ b, uint32_t nb) {
   uint32_t hibits = 0;
   for (uint32_t i = 0; i < na; ++i) hibits |= a[i];
   for (uint32_t i = 0; i < nb; ++i) hibits |= b[i];
-  if (hibits & 0x80) return false;
+  if (hibits & 0x80) return CONF_HOST;
   uint32_t p = 0;
   const uint32_t m = min(na, nb);
   while (p < m && a[p] == b[p]) ++p;
@@ -546,6 +550,7 @@ __device__ __forceinline__ bool confusables_cannot_match(const DeviceIndex* ix, 
     bool possible = true;
     for (uint32_t q = 0; q < pat.n_instr && possible; ++q) {
       const ConfInstr ins = ix->conf_instrs[pat.first_instr + q];
+      if (ins.op == 0) continue;  // identities impose nothing on the middle
       const uint64_t slo = ins.op < 0 ? alo : blo, shi = ins.op < 0 ? ahi : bhi;
       bool any = false;
       for (uint32_t o = 0; o < ins.n_opts && !any; ++o) {
@@ -554,28 +559,52 @@ __device__ __forceinline__ bool confusables_cannot_match(const DeviceIndex* ix, 
       }
       possible = any;
     }
-    if (possible) return false;
+    if (possible) return (na > (uint32_t)esf::MAXLEN || nb > (uint32_t)esf::MAXLEN) ? CONF_HOST : CONF_QUEUE;
   }
-  return true;
+  return CONF_SETTLED;
 }
+
+// What the shared tail does for one query.
+constexpr uint32_t RCE_RANK_SCORE = 1;   // normalise frequencies, rank by rank_cmp (src/types.rs:344-365)
+constexpr uint32_t RCE_RANK_GATHER = 2;  // keep the gather order (early confusables: ranking follows the rescoring)
+constexpr uint32_t RCE_CROP = 4;         // crop at max_matches (src/lib.rs:1536-1589)
+constexpr uint32_t RCE_CUTOFF = 8;       // cut-off (src/lib.rs:1598-1622)
+constexpr uint32_t RCE_INPLACE = 16;     // write back over the query's own records instead of reserving from the pool
+__host__ __device__ inline uint32_t rce_mode(int finish_mode) {
+  switch (finish_mode) {
+    case FINISH_FULL: return RCE_RANK_SCORE | RCE_CROP | RCE_CUTOFF;
+    case FINISH_CROP: return RCE_RANK_SCORE | RCE_CROP;
+    case FINISH_GATHER: return RCE_RANK_GATHER;
+    default: return 0;  // FINISH_SHARD: survivors pass through unranked
+  }
+}
+// the confusable stage of a launch (all null when the model has no confusables or the mode has no post-pass)
+struct ConfStage {
+  const DeviceIndex* ix = nullptr;
+  const uint8_t* qraw = nullptr;  // raw text of the current query
+  uint32_t qraw_len = 0;
+  uint32_t qrow = 0;              // the query's row in the batch (indexes the raw-text offsets)
+  ConfWork* worklist = nullptr;
+  unsigned int* work_cursor = nullptr;
+};
 
 // The tail shared by score_kernel and merge_kernel: frequency normalisation, ranking, crop, cut-off and
 // the packed emission of one query's survivors.  Returns the number of results written (lane 0 only).
-__device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRec* surv, SurvRec* sorted, uint32_t nsurv,
-                                                 double maxfreq, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
-                                                 OutHead* __restrict__ out_head, uint32_t qi, uint32_t flags,
-                                                 uint32_t* __restrict__ qflags, unsigned int* pool_cursor,
-                                                 const DeviceIndex* ix = nullptr, const uint8_t* qraw = nullptr,
-                                                 uint32_t qraw_len = 0) {
+__device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const uint32_t mode, SurvRec* surv, SurvRec* sorted,
+                                                 uint32_t nsurv, double maxfreq, OutRec* __restrict__ out,
+                                                 uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, uint32_t qi,
+                                                 uint32_t flags, uint32_t* __restrict__ qflags, unsigned int* pool_cursor,
+                                                 uint32_t inplace_off, const ConfStage& cs) {
   const uint32_t lane = lane_id();
   // ---- normalise frequencies, rank (src/lib.rs:1521-1528) ------------------------------------------
   // (surv keeps the raw frequency in `raw`; `freq` becomes the normalised score, `key` the combined one)
   __threadfence_block();
   __syncwarp();
-  if (bp.finish_mode == FINISH_SHARD) {
+  if (!(mode & (RCE_RANK_SCORE | RCE_RANK_GATHER))) {
     // lexicon-sharded mode: ranking happens after the exchange (merge_kernel); pass the survivors through
     for (uint32_t i = lane; i < nsurv; i += 32) sorted[i] = surv[i];
   } else {
+    const bool gather_order = (mode & RCE_RANK_GATHER) != 0;
     for (uint32_t i = lane; i < nsurv; i += 32) {
       SurvRec r = surv[i];
       if (maxfreq > 0.0) r.freq = __ddiv_rn(r.freq, maxfreq);
@@ -588,7 +617,7 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
       uint32_t rank = 0;
       for (uint32_t j = 0; j < nsurv; ++j) {
         const SurvRec b = surv[j];
-        rank += (j != i) && ranks_before(bp, b, a);
+        rank += (j != i) && ranks_before(bp, gather_order, b, a);
       }
       sorted[rank] = a;
     }
@@ -597,7 +626,7 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
 
   // ---- crop at max_matches with the reference's tie rules (src/lib.rs:1536-1589) ---------------------
   uint32_t n = nsurv;
-  if (bp.finish_mode != FINISH_GATHER && bp.finish_mode != FINISH_SHARD && bp.max_matches > 0 && n > bp.max_matches) {
+  if ((mode & RCE_CROP) && bp.max_matches > 0 && n > bp.max_matches) {
     const SurvRec a = sorted[bp.max_matches - 1], b = sorted[bp.max_matches];
     const double last_score = result_score(bp, a.dist, a.freq);
     const double cropped = result_score(bp, b.dist, b.freq);
@@ -626,8 +655,8 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
         n = B + 1;
     }
   }
-  // ---- cut-off (src/lib.rs:1598-1622); only when no late confusable rescoring follows -----------------
-  if (bp.finish_mode == FINISH_FULL && bp.cutoff_threshold >= 1.0 && n > 1) {
+  // ---- cut-off (src/lib.rs:1598-1622); after the confusable rescoring when there is one --------------
+  if ((mode & RCE_CUTOFF) && bp.cutoff_threshold >= 1.0 && n > 1) {
     const SurvRec a = sorted[0];
     const double lim = __ddiv_rn(result_score(bp, a.dist, a.freq), bp.cutoff_threshold);
     uint32_t cut = n;
@@ -644,24 +673,48 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
     n = cut;
   }
   // ---- emit into the packed pool (one atomic reservation per query) --------------------------------------
-  uint32_t off = 0;
-  if (lane == 0 && n > 0) off = atomicAdd(pool_cursor, n);
-  off = __shfl_sync(FULL, off, 0);
-  const bool fits = (unsigned long long)off + n <= (unsigned long long)bp.pool_cap;
+  uint32_t off = inplace_off;
+  bool fits = true;
+  if (!(mode & RCE_INPLACE)) {
+    off = 0;
+    if (lane == 0 && n > 0) off = atomicAdd(pool_cursor, n);
+    off = __shfl_sync(FULL, off, 0);
+    fits = (unsigned long long)off + n <= (unsigned long long)bp.pool_cap;
+  }
   if (fits) {
-    for (uint32_t i = lane; i < n; i += 32) {
-      const SurvRec r = sorted[i];
-      OutRec o;
-      o.dist_score = r.dist;
-      o.vocab_id = r.vocab;
-      if (qraw) {
-        // confusable prefilter: spare the host the edit script when no pattern can match this pair
-        const uint32_t t0 = __ldg(ix->vocab_text_off + r.vocab), t1 = __ldg(ix->vocab_text_off + r.vocab + 1);
-        if (confusables_cannot_match(ix, qraw, qraw_len, ix->vocab_text + t0, t1 - t0)) o.vocab_id |= OUT_SKIP_CONFUSABLES;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool queue = false;
+      if (i < n) {
+        const SurvRec r = sorted[i];
+        OutRec o;
+        o.dist_score = r.dist;
+        o.vocab_id = r.vocab;
+        if (cs.qraw) {
+          // confusable triage: settle the pairs no pattern can match, queue the rest for the confusable kernel
+          const uint32_t t0 = __ldg(cs.ix->vocab_text_off + r.vocab), t1 = __ldg(cs.ix->vocab_text_off + r.vocab + 1);
+          const int tri = confusable_triage(cs.ix, cs.qraw, cs.qraw_len, cs.ix->vocab_text + t0, t1 - t0);
+          if (tri == CONF_SETTLED) o.vocab_id |= OUT_SKIP_CONFUSABLES;
+          queue = tri == CONF_QUEUE;
+        }
+        o.freq = r.raw;
+        out[off + i] = o;
+        if (out_gid) out_gid[off + i] = r.g;
       }
-      o.freq = r.raw;
-      out[off + i] = o;
-      if (out_gid) out_gid[off + i] = r.g;
+      if (cs.worklist) {
+        const uint32_t qm = __ballot_sync(FULL, queue);
+        if (qm) {
+          uint32_t wbase = 0;
+          if (lane == 0) wbase = atomicAdd(cs.work_cursor, (unsigned int)__popc(qm));
+          wbase = __shfl_sync(FULL, wbase, 0);
+          if (queue) {
+            ConfWork w;
+            w.rec = off + i;
+            w.query = cs.qrow;
+            cs.worklist[wbase + __popc(qm & lanemask_lt())] = w;  // capacity = pool capacity >= records emitted
+          }
+        }
+      }
     }
   }
   if (lane == 0) {
@@ -680,7 +733,7 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, SurvRe
 __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
-             uint32_t nq, const uint32_t* __restrict__ hits,
+             ConfWork* __restrict__ conf_work, uint32_t nq, const uint32_t* __restrict__ hits,
              const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
              unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R) {
@@ -872,15 +925,18 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       __syncwarp();
     }
 
-    const uint8_t* qraw = nullptr;
-    uint32_t qraw_len = 0;
-    if (qblob && ix->conf_prefilter && bp.finish_mode != FINISH_FULL && bp.finish_mode != FINISH_SHARD) {
+    ConfStage cs;
+    if (qblob && ix->conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
       const uint32_t b0 = qboff[q], b1 = qboff[q + 1];
-      qraw = qblob + b0;
-      qraw_len = b1 - b0;
+      cs.ix = ix;
+      cs.qraw = qblob + b0;
+      cs.qraw_len = b1 - b0;
+      cs.qrow = q;
+      cs.worklist = conf_work;
+      cs.work_cursor = pool_cursor + 1;
     }
-    c_res += rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags, qflags, pool_cursor, ix, qraw,
-                            qraw_len);
+    c_res += rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags,
+                            qflags, pool_cursor, 0, cs);
   }
 
   if (counters) {
@@ -960,7 +1016,103 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
       }
       continue;
     }
-    rank_crop_emit(bp, surv, sorted, nsurv, maxfreq, out, nullptr, out_head, qi, flags, qflags, pool_cursor);
+    rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, nullptr, out_head, qi, flags, qflags,
+                   pool_cursor, 0, ConfStage());
+  }
+}
+
+// ================================================================================================
+// Kernels 4 + 5 (only with confusables): device-side rescoring of the ranked lists
+// ================================================================================================
+// confusable_kernel: one queued (input, candidate) pair per thread.  Computes the edit script of the raw
+// strings and the product of the weights of all patterns found in it (rescore_confusables /
+// compute_confusable_weight, src/lib.rs:1656-1663,1733-1756), multiplies the record's distance score and
+// marks it settled.  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
+__global__ void __launch_bounds__(128)
+confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+                  const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
+                  OutRec* __restrict__ out) {
+  const uint32_t total = min(*work_count, work_cap);
+  esf::PatTable T;
+  T.pats = ix->conf_pats;
+  T.instrs = ix->conf_instrs;
+  T.opts = ix->conf_opts;
+  T.text = ix->conf_text;
+  T.n_pats = ix->n_conf_pats;
+  const uint8_t* __restrict__ vtext = ix->vocab_text;
+  const uint32_t* __restrict__ voff = ix->vocab_text_off;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const ConfWork it = worklist[w];
+    const OutRec r = out[it.rec];
+    const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
+    const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
+    const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
+    // private copies: the diff touches every character many times
+    uint8_t a[esf::MAXLEN], b[esf::MAXLEN];
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    if (na > esf::MAXLEN || nb > esf::MAXLEN) continue;
+    for (int i = 0; i < na; ++i) a[i] = qblob[a0 + i];
+    for (int i = 0; i < nb; ++i) b[i] = vtext[b0 + i];
+    esf::View v[esf::MAXSEG];
+    const int nv = esf::shortest_edit_script(a, na, b, nb, v);
+    if (nv < 0) continue;
+    double weight = 1.0;
+    for (uint32_t k = 0; k < T.n_pats; ++k) {
+      const ConfPat pat = T.pats[k];
+      if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
+    }
+    OutRec o = r;
+    if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
+    o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
+    out[it.rec] = o;
+  }
+}
+
+// finish_kernel: one warp per query.  After the rescoring: re-rank (stable: the previous position is the
+// last key), crop when the confusables ran before pruning, cut-off -- written back over the query's own
+// records.  A query with an unsettled record is flagged for the host instead and left untouched.
+__global__ void __launch_bounds__(K2_WARPS * 32)
+finish_kernel(const BatchParams bp, uint32_t nq, OutRec* __restrict__ out, OutHead* __restrict__ out_head,
+              SurvRec* __restrict__ scratch, uint32_t scratch_cap, unsigned int* work) {
+  const uint32_t lane = lane_id();
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+  SurvRec* surv = scratch + (size_t)gwarp * 2 * scratch_cap;
+  SurvRec* sorted = surv + scratch_cap;
+  const uint32_t mode = (bp.finish_mode == FINISH_GATHER ? (RCE_RANK_SCORE | RCE_CROP | RCE_CUTOFF) : (RCE_RANK_SCORE | RCE_CUTOFF)) |
+                        RCE_INPLACE;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const OutHead h = out_head[qi];
+    const uint32_t n = h.count;
+    if (n == 0) continue;
+    OutRec* recs = out + h.offset;
+    bool unsettled = n > scratch_cap;
+    for (uint32_t i0 = 0; i0 < n && !unsettled; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool u = false;
+      if (i < n) {
+        const OutRec o = recs[i];
+        u = !(o.vocab_id & OUT_SKIP_CONFUSABLES);
+        SurvRec s;
+        s.dist = o.dist_score;
+        s.freq = (double)o.freq;
+        s.key = 0.0;
+        s.g = i;
+        s.raw = o.freq;
+        s.vocab = o.vocab_id;
+        s.pad = 0;
+        surv[i] = s;
+      }
+      unsettled = __any_sync(FULL, u);
+    }
+    if (unsettled) {
+      if (lane == 0) out_head[qi].count = n | HEAD_HOST_FINISH;
+      continue;
+    }
+    rank_crop_emit(bp, mode, surv, sorted, n, h.max_freq, out, nullptr, out_head, qi, 0, nullptr, nullptr, h.offset, ConfStage());
   }
 }
 
@@ -1054,7 +1206,7 @@ size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queri
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream) {
   if (lb.n == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 2 * sizeof(unsigned int), stream);
+  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // work counter, pool cursor, confusable queue
   if (e != cudaSuccess) return e;
   const uint32_t R = ring_depth(bp);
   const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
@@ -1066,9 +1218,33 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
-score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.n, lb.hits, lb.hit_count,
-                                                                lb.qflags, lb.out, lb.out_gid, lb.out_head, scratch,
-                                                                lb.work + 1, lb.work + 2, lb.counters, h_ix.max_len, R);
+  score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.conf_work,
+                                                                lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
+                                                                lb.out_head, scratch, lb.work + 1, lb.work + 2, lb.counters,
+                                                                h_ix.max_len, R);
+  return cudaGetLastError();
+}
+
+// The device confusable stage: edit scripts of the queued pairs, then re-rank / crop / cut-off per query.
+// Only launched when the score kernel filled a work list (lb.conf_work).
+cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
+                               cudaStream_t stream) {
+  if (lb.n == 0 || !lb.conf_work) return cudaSuccess;
+  confusable_kernel<<<(unsigned)sm_count * 8, 128, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap,
+                                                                lb.out);
+  return cudaGetLastError();
+}
+cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream) {
+  if (lb.n == 0 || !lb.conf_work) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
+  if (e != cudaSuccess) return e;
+  // the scratch is the score kernel's (score_scratch_bytes): at most sm_count * 16 CTAs of K2_WARPS warps
+  long long grid = (long long)sm_count * 8;
+  const long long want = ((long long)lb.n + K2_WARPS - 1) / K2_WARPS;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  finish_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(bp, lb.n, lb.out, lb.out_head, reinterpret_cast<SurvRec*>(lb.scratch),
+                                                              bp.hit_cap, lb.work);
   return cudaGetLastError();
 }
 

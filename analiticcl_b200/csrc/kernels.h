@@ -11,8 +11,9 @@ namespace anl {
 struct LaunchBuffers {
   const uint8_t* queries = nullptr;  // [n_total][query_stride] encoded query rows
   const uint32_t* qlist = nullptr;   // optional: indices into `queries` (rerun of selected queries); nullptr = identity
-  const uint8_t* qblob = nullptr;    // optional: raw UTF-8 of the queries (confusable prefilter)
+  const uint8_t* qblob = nullptr;    // optional: raw UTF-8 of the queries (confusable triage + edit scripts)
   const uint32_t* qboff = nullptr;   //           byte offsets into qblob, n_total + 1 entries
+  ConfWork* conf_work = nullptr;     // optional: queue of (record, query) pairs for the confusable kernel, bp.pool_cap entries
   uint32_t n = 0;                    // number of queries in this launch
   uint32_t* hits = nullptr;          // [n][hit_cap] gather ids of candidate instances
   uint32_t* hit_count = nullptr;     // [n]
@@ -21,7 +22,7 @@ struct LaunchBuffers {
   uint32_t* out_gid = nullptr;       // optional (sharded mode): global gather id per pool record
   OutHead* out_head = nullptr;       // [n] per-query header: offset / count into the pool, max_freq
   void* scratch = nullptr;           // score kernel scratch: score_scratch_bytes(...)
-  unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor (zeroed by the launchers)
+  unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor, [3] confusable queue length (zeroed by the launchers)
   Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
 };
 
@@ -32,6 +33,12 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 // cropping and cut-off.
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
+// Confusable rescoring on the device (only when launch_score filled lb.conf_work): edit script + pattern
+// matching per queued pair, then re-rank / crop / cut-off per query in place.  Queries the device cannot
+// settle get HEAD_HOST_FINISH in their header.
+cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
+                               cudaStream_t stream);
+cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream);
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
 cudaError_t configure_kernels();
 // Lexicon-sharded mode: merge the all-gathered per-shard survivor lists (see merge_kernel).

@@ -158,6 +158,10 @@ int64_t anl_anahash(const anl_model* m, const char* text, size_t len, uint64_t* 
  * rescoring (src/lib.rs:1736), rendered in sesdiff's text form `=[..]-[..]+[..]`.  Returns the number of
  * bytes needed (excluding the NUL); writes at most cap-1 bytes + NUL. */
 int64_t anl_shortest_edit_script(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap);
+/* The same script computed by the fixed-capacity implementation that the confusable kernel runs per
+ * thread (csrc/editscript_fixed.h), compiled for the host: a test hook.  Returns -1 when the pair is
+ * outside that implementation's limits (non-ASCII text, more than 64 characters, internal capacity). */
+int64_t anl_shortest_edit_script_fixed(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap);
 /* Confusable::found_in (src/confusables.rs:47): 1 if `pattern` occurs in the edit script of src -> dst,
  * 0 if not, -1 if the pattern does not parse. */
 int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src_len, const char* dst, size_t dst_len);
@@ -203,12 +207,13 @@ typedef struct anl_device_batch anl_device_batch; /* encoded queries + result bu
 /* Encodes on the host (alphabet normalisation) and uploads; buffers are sized for n_queries. */
 anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
                                    const anl_search_params* params, anl_device_batch** out);
-/* One pass of the hot path over the resident batch: probe kernel + score/rank kernel on the
- * model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
+/* One pass of the hot path over the resident batch: probe kernel + score/rank kernel (+ confusable and
+ * finish kernels when confusables are loaded) on the model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
 anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream);
-/* Device-side cudaEvent timings (ms) of the two kernels, averaged over the runs since the previous
- * call (events recorded on the launching stream); synchronises. */
-anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms);
+/* Device-side cudaEvent timings (ms) of the kernels, averaged over the runs since the previous call
+ * (events recorded on the launching stream); synchronises.  rescore_ms (may be NULL) = confusable
+ * kernel + finish kernel, which only run when confusables are loaded. */
+anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms);
 /* Downloads the results of the last run and finishes them on the host (same output as
  * anl_find_variants_batch). */
 anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out);

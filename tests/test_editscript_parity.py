@@ -82,3 +82,45 @@ def test_confusable_kats(L):
     for pat, _ in workloads.CFG2_CONFUSABLES:
         for a, b in pairs(13, 300):
             assert f(pat, a, b) == int(orc.confusable_found_in(pat, a, b))
+
+
+def script_fixed(L, a, b):
+    ra, rb = a.encode(), b.encode()
+    buf = C.create_string_buffer(4096)
+    n = L.anl_shortest_edit_script_fixed(ra, len(ra), rb, len(rb), buf, 4096)
+    return None if n < 0 else buf.value.decode()
+
+
+def test_fixed_capacity_script_matches_host_and_oracle(L):
+    """csrc/editscript_fixed.h (what the confusable kernel runs per thread, compiled for the host here)
+    against csrc/editscript.cpp and the oracle; pairs outside its limits must be declined, not approximated."""
+    ps = pairs(21, 5000)
+    rng = np.random.default_rng(5)
+    # low-entropy strings exercise the bisect recursion, the semantic clean-up and the overlap extraction
+    for _ in range(20000):
+        la, lb = int(rng.integers(0, 24)), int(rng.integers(0, 24))
+        k = int(rng.integers(2, 5))
+        a = "".join("abcd"[int(x)] for x in rng.integers(0, k, size=la))
+        b = "".join("abcd"[int(x)] for x in rng.integers(0, k, size=lb))
+        ps.append((a, b))
+    for _ in range(3000):
+        la, lb = int(rng.integers(30, 70)), int(rng.integers(30, 70))
+        a = "".join("ab c"[int(x)] for x in rng.integers(0, 4, size=la))
+        b = "".join("ab c"[int(x)] for x in rng.integers(0, 4, size=lb))
+        ps.append((a, b))
+    bad, declined, handled = [], 0, 0
+    for i, (a, b) in enumerate(ps):
+        got = script_fixed(L, a, b)
+        ascii_ok = all(ord(ch) < 128 for ch in a + b) and len(a) <= 64 and len(b) <= 64
+        if got is None:
+            declined += 1
+            continue
+        assert ascii_ok, (a, b)
+        handled += 1
+        exp = script(L, a, b)
+        if got != exp:
+            bad.append((a, b, got, exp))
+        elif i % 7 == 0:
+            assert got == orc.edit_script(a, b)
+    assert not bad, f"{len(bad)} / {handled} differ, first: {bad[:5]}"
+    assert handled > 0.9 * len(ps) - 3000, (handled, declined)

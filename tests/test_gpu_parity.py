@@ -182,6 +182,40 @@ def test_nld_confusables_parity(A, early):
     assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, "confusables")
 
 
+RICH_CONFUSABLES = [  # identities as context, anchors, alternatives, multi-character and non-ASCII options
+    ("-[f]+[s]", 1.1), ("-[y]+[i]", 1.1), ("-[c]+[e]", 0.95), ("-[l]+[i]", 1.05), ("-[u]+[n]", 0.95),
+    ("=[s]-[c]+[e]", 1.2), ("^-[b]+[h]", 1.15), ("-[rn]+[m]", 1.3), ("-[m]+[rn]", 1.25), ("+[e|n]$", 0.9),
+    ("-[ij]+[y]", 1.07), ("-[a|e|i|o|u]+[a|e|i|o|u]=[n|r|s|t]", 0.97), ("-[é|e]+[ë|a]", 1.4), ("=[ge]-[l]", 0.8),
+    ("^=[ver|be|ge|on]+[s|t]", 1.12), ("-[i]=[l]+[i]", 1.5), ("-[ë]+[e]", 1.21),
+]
+
+
+@pytest.mark.parametrize("early", [False, True], ids=["late", "early"])
+@pytest.mark.parametrize("lex", ["nld", "eng"])
+def test_device_confusable_stage_parity(A, lex, early):
+    """The confusable kernel (edit script per thread) + finish kernel against the oracle: rich pattern set,
+    OCR noise and misspellings, non-ASCII and over-long queries (host post-pass) mixed into one batch."""
+    path = workloads.nld_freq_lexicon() if lex == "nld" else workloads.lexicon_path("eng")
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(path)
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    o.read_lexicon(path)
+    for pat, w in RICH_CONFUSABLES:
+        m.add_to_confusables(pat, w)
+        o.add_to_confusables(pat, w)
+    if early:
+        m.set_confusables_before_pruning()
+        o.set_confusables_before_pruning()
+    m.build()
+    o.build()
+    words = workloads.read_words(lex)
+    qs = workloads.ocr_noise(words, 1500, 77) + workloads.misspellings(words, 700, 78)
+    qs += ["x" * 70, "aan" * 30, "één", "zeeën", "reëel", "cafe", "café", "s", "ij", "geld", "verstaan", "bestaan"]
+    qs += [w for w in words[::4001]][:60]
+    sp = A.SearchParameters(freq_weight=0.25 if lex == "nld" else 0.0, max_matches=7)
+    assert_same(m.find_variants_raw(qs, sp), o.find_variants_batch(qs, to_orc_params(sp)), qs, f"device confusables {lex}")
+
+
 def small(A, words, confusables=(), weights=None):
     m = A.VariantModel(None, weights or A.Weights(), alphabet_tsv=orc.TEST_ALPHABET_TSV)
     for w in words:
