@@ -27,7 +27,7 @@ struct Key192 {
   uint64_t w0, w1, w2;
 };
 
-// 64-bit mix of a 192-bit key; the same function builds the tables on the host.
+// 64-bit mix of a 192-bit key (host only: partitions the anagrams of the lexicon-sharded mode).
 __host__ __device__ __forceinline__ uint64_t hash_key(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t h = a * 0x9E3779B97F4A7C15ULL;
   h ^= (b + 0x7F4A7C159E3779B9ULL) * 0xC2B2AE3D27D4EB4FULL;
@@ -38,15 +38,32 @@ __host__ __device__ __forceinline__ uint64_t hash_key(uint64_t a, uint64_t b, ui
   return h;
 }
 
+// ---- linear multiset fingerprints ---------------------------------------------------------------------
+// The probe side never multiplies primes.  A multiset of symbols X is fingerprinted by
+//     mhash(X) = sum over its symbols s of class_rnd(s)   (mod 2^64)
+// which is LINEAR: mhash(F - deleted + inserted) = mhash(F) - sum rnd(deleted) + sum rnd(inserted), so every
+// node of a query's neighbourhood costs one 64-bit add instead of a 192-bit multiply plus a hash.  The
+// fingerprint only routes a probe to postings; each posting is then verified EXACTLY against the
+// anagram's own 192-bit prime-product key (X * p_x == key(C), X's key computed lazily for the few nodes
+// that reach that stage), so fingerprint collisions cost a wasted compare, never a wrong result.
+__host__ __device__ __forceinline__ uint64_t class_rnd(uint32_t s) {  // splitmix64 of the class index
+  uint64_t z = (uint64_t)(s + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+// slot / Bloom word of a fingerprint: the low byte is skipped (a difference of two multisets whose symbol
+// counts differ by even amounts only is even, so the lowest bits are the least uniform ones)
+__host__ __device__ __forceinline__ uint64_t fp_index(uint64_t h, uint64_t mask) { return (h >> 8) & mask; }
+
 // ---- the neighbour table ("symmetric delete, depth sd") -------------------------------------------
 // Replaces both `index` (HashMap<AnaValue, AnaIndexNode>, src/index.rs:5) and the linear scan of
 // `sortedindex[charcount]` (src/lib.rs:1268-1281).  Keys X of the table are
 //     sd = 0:  every indexed anagram C                       (posting: C itself, cls = POST_SELF)
 //     sd = 1:  additionally C / p_x for every class x in C   (posting: C, cls = x)
-// A slot stores the 64-bit hash of X as a fingerprint, not X: every posting is verified exactly
-// on the device (X * p_x == key(C)), so fingerprint collisions only cost a wasted verification.
+// A slot stores mhash(X) as a fingerprint, not X.
 struct __attribute__((aligned(16))) Slot {
-  uint64_t fp;        // hash_key(X)
+  uint64_t fp;        // mhash(X)
   uint32_t post_off;  // first posting
   uint16_t post_cnt;  // number of postings; 0 = empty slot
   uint16_t pad;
@@ -57,7 +74,7 @@ static const uint8_t POST_SELF = 0xFF;
 // A miss (the overwhelmingly common case) costs one 8-byte load.
 static const int BLOOM_BITS = 3;
 __host__ __device__ __forceinline__ uint64_t bloom_mask(uint64_t h) {
-  // bits taken from the top of the hash (the word index uses the low bits)
+  // bits taken from the top of the fingerprint (the word index uses bits 8..)
   return (1ULL << ((h >> 58) & 63)) | (1ULL << ((h >> 52) & 63)) | (1ULL << ((h >> 46) & 63));
 }
 
@@ -66,12 +83,13 @@ __host__ __device__ __forceinline__ uint64_t bloom_mask(uint64_t h) {
 // occur in the lexicon ("active classes"), ordered by j (all j=1 first, then j=2, ...), so the
 // multisets of size <= J are the prefix [0, mset_end[J]).
 struct __attribute__((aligned(16))) MsetEntry {
-  uint64_t prod;   // product of the primes of the inserted symbols (< 2^60 for j <= 6)
+  uint64_t hsum;   // sum of class_rnd over the inserted symbols (what the multiset adds to a fingerprint)
   uint8_t cls[6];  // the symbols (prime indices), ascending, padded with 0xFF
   uint8_t j;       // multiset size
   uint8_t maxcls;  // largest symbol
 };
 
+static const int COLEX_N = 32;           // queries up to this many symbols unrank deletion sets by table lookup
 static const int ANL_MAX_K = 6;          // largest supported max_anagram_distance after thresholding
 static const int ANL_MAX_SYMBOLS = 236;  // longest query / entry (symbols) the device path accepts (row number + 16 fits a byte)
 
@@ -144,6 +162,10 @@ struct DeviceIndex {
   const MsetEntry* mset;
   uint32_t mset_end[ANL_MAX_K + 1];  // mset_end[J] = number of entries with j <= J; [0] = 0
   const uint32_t* binom;             // [256][8] saturating binomials C(n, k)
+  // colex unranking tables for the deletion neighbourhood of queries up to COLEX_N symbols: entry t of
+  // colex2 / colex3 packs the positions p0 < p1 (< p2) of the t-th 2- / 3-subset in colex order, one per byte
+  const uint32_t* colex2;            // C(COLEX_N, 2) entries
+  const uint32_t* colex3;            // C(COLEX_N, 3) entries
   uint32_t prime_of[256];            // prime of a symbol (prime index), 0 if unused
   uint64_t charcount_mask[4];        // bit cc set iff some anagram has that charcount (cc < 256)
   uint32_t max_charcount;

@@ -371,7 +371,7 @@ void lossless_shift(const Ctx& c, Script& d) {
     pos -= cs;
     l1 -= cs;
     l2 += cs;
-    int best_pos = pos, best_l1 = l1, best_l2 = l2;
+    int best_l1 = l1, best_l2 = l2;
     int best = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
     while (m > 0 && l2 > 0 && base[pos] == base[pos + m]) {
       ++pos;
@@ -380,12 +380,10 @@ void lossless_shift(const Ctx& c, Script& d) {
       const int sc = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
       if (sc >= best) {
         best = sc;
-        best_pos = pos;
         best_l1 = l1;
         best_l2 = l2;
       }
     }
-    (void)best_pos;
     if (d[k - 1].len != best_l1) {
       // (equal lengths mean equal text here: the window is fixed and only the split moves)
       size_t kk = k;

@@ -180,6 +180,15 @@ bool Engine::upload(int device, std::string* err) {
     }
   }
   if (!upload_vec(binom, &ix.binom, &index_allocs_, err)) return false;
+  // colex unranking tables: nested loops visit the subsets in colex (combinadic) rank order
+  std::vector<uint32_t> colex2, colex3;
+  for (uint32_t p1 = 1; p1 < (uint32_t)COLEX_N; ++p1)
+    for (uint32_t p0 = 0; p0 < p1; ++p0) colex2.push_back(p0 | (p1 << 8));
+  for (uint32_t p2 = 2; p2 < (uint32_t)COLEX_N; ++p2)
+    for (uint32_t p1 = 1; p1 < p2; ++p1)
+      for (uint32_t p0 = 0; p0 < p1; ++p0) colex3.push_back(p0 | (p1 << 8) | (p2 << 16));
+  if (!upload_vec(colex2, &ix.colex2, &index_allocs_, err)) return false;
+  if (!upload_vec(colex3, &ix.colex3, &index_allocs_, err)) return false;
   memcpy(ix.prime_of, hx.prime_of, sizeof ix.prime_of);
   memcpy(ix.charcount_mask, hx.charcount_mask, sizeof ix.charcount_mask);
   ix.max_charcount = hx.max_charcount;

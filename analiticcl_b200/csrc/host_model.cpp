@@ -312,16 +312,6 @@ static inline bool key_mul(Key192& k, uint64_t m) {
   k.w2 = (uint64_t)t2;
   return (uint64_t)(t2 >> 64) == 0;
 }
-static inline Key192 key_div_exact(const Key192& k, uint64_t m) {
-  Key192 q;
-  unsigned __int128 r = k.w2;
-  q.w2 = (uint64_t)(r / m);
-  r = ((r % m) << 64) | k.w1;
-  q.w1 = (uint64_t)(r / m);
-  r = ((r % m) << 64) | k.w0;
-  q.w0 = (uint64_t)(r / m);
-  return q;
-}
 static inline bool key_less(const Key192& a, const Key192& b) {
   if (a.w2 != b.w2) return a.w2 < b.w2;
   if (a.w1 != b.w1) return a.w1 < b.w1;
@@ -476,6 +466,8 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     if (class_seen[s]) ix.active_classes.push_back((uint8_t)s);
 
   // neighbour table: self postings, plus (sd = 1) one posting per distinct class of every anagram
+  // The table is keyed by the linear multiset fingerprint mhash (device_types.h), not by the prime
+  // product: mhash(C / p_x) = mhash(C) - class_rnd(x).
   struct Post {
     uint64_t fp;
     uint32_t ana;
@@ -484,19 +476,19 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   std::vector<Post> posts;
   posts.reserve(ix.ana_key.size() * (sd ? 10 : 1));
   for (uint32_t r = 0; r < ix.ana_key.size(); ++r) {
-    const Key192& k = ix.ana_key[r];
-    posts.push_back(Post{hash_key(k.w0, k.w1, k.w2), r, POST_SELF});
+    // symbols of this anagram from its first instance
+    const uint8_t* row = ix.inst_rows.data() + (size_t)ix.ana_inst_off[r] * ix.norm_stride;
+    uint64_t h = 0;
+    for (uint32_t i = 0; i < row[0]; ++i) h += class_rnd(row[2 + i]);
+    posts.push_back(Post{h, r, POST_SELF});
     if (sd >= 1) {
-      // distinct classes of this anagram from its first instance's symbols
-      const uint8_t* row = ix.inst_rows.data() + (size_t)ix.ana_inst_off[r] * ix.norm_stride;
       bool seen[256] = {false};
       for (uint32_t i = 0; i < row[0]; ++i) {
         uint8_t x = row[2 + i];
         if (seen[x]) continue;
         seen[x] = true;
         if (row[0] == 1) continue;  // the empty value is never a node (no empty leaves, src/iterators.rs:177)
-        Key192 xk = key_div_exact(k, kPrimes[x]);
-        posts.push_back(Post{hash_key(xk.w0, xk.w1, xk.w2), r, x});
+        posts.push_back(Post{h - class_rnd(x), r, x});
       }
     }
   }
@@ -525,10 +517,10 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
       return false;
     }
     const uint64_t fp = posts[i].fp;
-    uint64_t idx = fp & (slots - 1);
+    uint64_t idx = fp_index(fp, slots - 1);
     while (ix.table[idx].post_cnt != 0) idx = (idx + 1) & (slots - 1);
     ix.table[idx] = Slot{fp, (uint32_t)i, (uint16_t)(j - i), 0};
-    ix.bloom[fp & (words - 1)] |= bloom_mask(fp);
+    ix.bloom[fp_index(fp, words - 1)] |= bloom_mask(fp);
     for (size_t t = i; t < j; ++t) {
       ix.post_ana[t] = posts[t].ana;
       ix.post_cls[t] = posts[t].cls;
@@ -566,12 +558,12 @@ bool HostModel::ensure_msets(uint32_t J, std::string* err) {
     std::vector<size_t> ids(j, 0);
     for (;;) {
       MsetEntry e;
-      e.prod = 1;
+      e.hsum = 0;
       e.j = (uint8_t)j;
       for (int t = 0; t < 6; ++t) e.cls[t] = 0xFF;
       for (uint32_t t = 0; t < j; ++t) {
         e.cls[t] = cls[ids[t]];
-        e.prod *= kPrimes[cls[ids[t]]];
+        e.hsum += class_rnd(cls[ids[t]]);
       }
       e.maxcls = cls[ids[j - 1]];
       out.push_back(e);

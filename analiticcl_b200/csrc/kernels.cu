@@ -72,26 +72,33 @@ __device__ __forceinline__ bool ccbit(const uint64_t* mask, uint32_t cc) {
 // ================================================================================================
 // Kernel 1: candidate generation
 // ================================================================================================
+// Every node X = D + I' of the query's neighbourhood (D: a sub-multiset of the focus after d deletions,
+// I': a multiset of inserted symbols) is fingerprinted with the LINEAR multiset hash of
+// device_types.h: mhash(X) = mhash(F) - sum rnd(deleted) + sum rnd(inserted).  One 64-bit add per node,
+// one 8-byte Bloom word per probe.  Only the nodes that pass the filter AND find their table slot get
+// their exact 192-bit prime-product key computed, for the exact verification of the postings.
 constexpr int K1_WARPS = 8;
 constexpr int DCH = 64;  // deletion entries per chunk
 constexpr int SQ = 64;   // staging queue capacity (filter positives waiting for the exact lookup)
 
 struct __align__(16) DEntry {  // one element of the deletion neighbourhood of the query
-  uint64_t w0, w1, w2;         // key(D)
+  uint64_t h;                  // mhash(D)
   uint8_t d;                   // number of deleted symbols
   uint8_t del[6];              // the deleted symbols (ascending, may repeat)
   uint8_t pad;
 };
 struct __align__(16) SEntry {  // a node X = D + I' that passed the Bloom filter
-  uint64_t w0, w1, w2;         // key(X)
+  uint64_t h;                  // mhash(X)
+  uint32_t t;                  // index of I' in the multiset table (unused when isz == 0)
   uint8_t e;                   // index of D in the current chunk
   uint8_t isz;                 // |I'|
   uint8_t imax;                // largest symbol of I' (0 if empty)
-  uint8_t pad[5];
+  uint8_t pad;
 };
 struct K1Warp {
   DEntry dch[DCH];
   SEntry sq[SQ];
+  Key192 skey[32];    // drain stage: exact key of each staged node of the current round
   uint32_t pfx[33];   // drain stage: exclusive prefix of posting counts (+ sentinel)
   uint32_t poff[32];  // drain stage: first posting of each staged node
   uint8_t sorted[256];
@@ -100,12 +107,14 @@ struct K1Warp {
 };
 struct K1Shared {
   DeviceIndex ix;  // block-local copy of the model constants (pointers, masks, small tables)
+  uint64_t rnd[256];  // class_rnd of every symbol
   uint32_t binom[256 * 8];
   K1Warp w[K1_WARPS];
 };
 
 struct K1Ctx {
   const DeviceIndex* ix;
+  const uint64_t* rnd;
   const Slot* table;
   uint64_t table_mask;
   const uint64_t* bloom;
@@ -118,20 +127,59 @@ struct K1Ctx {
   uint32_t c_probes, c_pass, c_steps, c_postings, c_ana, c_inst;
 };
 
+// Exact 192-bit key of the node X = F - del(D) + I' (only for nodes whose fingerprint found a slot).
+// false: the product does not fit 192 bits, so X cannot equal or divide into any indexed key.
+__device__ __forceinline__ bool node_key(const K1Ctx& c, const K1Warp& W, const uint32_t* prime_of, const DEntry& de,
+                                         const SEntry& s, uint64_t& k0, uint64_t& k1, uint64_t& k2) {
+  k0 = 1;
+  k1 = 0;
+  k2 = 0;
+  uint64_t pp = 1;
+  bool ok = true;
+  uint32_t dp = 0;  // next deleted symbol to drop (both lists ascend)
+  for (uint32_t p = 0; p < c.L && ok; ++p) {
+    const uint32_t sym = W.sorted[p];
+    if (dp < de.d && de.del[dp] == sym) {
+      ++dp;
+      continue;
+    }
+    pp *= prime_of[sym];
+    if (pp >> 53) {  // next factor (< 2^10) could overflow 64 bits: flush
+      ok = mul192(k0, k1, k2, pp);
+      pp = 1;
+    }
+  }
+  if (ok && s.isz) {
+    const MsetEntry me = c.ix->mset[s.t];
+    for (uint32_t a = 0; a < s.isz && ok; ++a) {
+      pp *= prime_of[me.cls[a]];
+      if (pp >> 53) {
+        ok = mul192(k0, k1, k2, pp);
+        pp = 1;
+      }
+    }
+  }
+  if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+  return ok;
+}
+
 // Exact lookup of the staged nodes, in two lane-parallel stages: (1) one node per lane finds its
-// table slot by fingerprint; (2) the postings of all 32 nodes are flattened (warp scan) and
-// verified one posting per lane -- against the anagram's own key and against the
-// canonical-generation rules (each indexed anagram C is produced exactly once: from D = F meet C
-// and the ascending insertion order).
-__device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t cnt) {
+// table slot by fingerprint and, if there is one, computes the node's exact key; (2) the postings of
+// all 32 nodes are flattened (warp scan) and verified one posting per lane -- against the anagram's
+// own key and against the canonical-generation rules (each indexed anagram C is produced exactly
+// once: from D = F meet C and the ascending insertion order).
+// (Deliberately NOT inlined, like process_chunk: the probe kernel is instruction-fetch bound when its
+// code outgrows the 32 KB L1.5 instruction cache -- ncu: 57 % of the stall samples were "no instruction"
+// with five inlined copies of this function.)
+__device__ __noinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t cnt) {
   const uint32_t lane = lane_id();
   for (uint32_t base = 0; base < cnt; base += 32) {
     const uint32_t i = base + lane;
     uint32_t poff = 0, pcnt = 0;
     if (i < cnt) {
-      const SEntry& s = W.sq[i];
-      const uint64_t fp = hash_key(s.w0, s.w1, s.w2);
-      uint64_t idx = fp & c.table_mask;
+      const SEntry s = W.sq[i];
+      const uint64_t fp = s.h;
+      uint64_t idx = fp_index(fp, c.table_mask);
       for (;;) {
         const Slot sl = c.table[idx];
         ++c.c_steps;
@@ -142,6 +190,16 @@ __device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t*
           break;
         }
         idx = (idx + 1) & c.table_mask;
+      }
+      if (pcnt) {
+        uint64_t k0, k1, k2;
+        if (node_key(c, W, prime_of, W.dch[s.e], s, k0, k1, k2)) {
+          W.skey[lane].w0 = k0;
+          W.skey[lane].w1 = k1;
+          W.skey[lane].w2 = k2;
+        } else {
+          pcnt = 0;
+        }
       }
     }
     uint32_t incl = pcnt;
@@ -162,12 +220,12 @@ __device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t*
         for (int step = 16; step >= 1; step >>= 1)
           if (W.pfx[owner + step] <= t) owner += step;
         const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
-        const SEntry& s = W.sq[base + owner];
+        const SEntry s = W.sq[base + owner];
         const DEntry& de = W.dch[s.e];
         const uint32_t r = __ldg(c.ix->post_ana + p);
         const uint32_t x = __ldg(c.ix->post_cls + p);
         ++c.c_postings;
-        uint64_t x0 = s.w0, x1 = s.w1, x2 = s.w2;
+        uint64_t x0 = W.skey[owner].w0, x1 = W.skey[owner].w1, x2 = W.skey[owner].w2;
         bool ok;
         if (x == POST_SELF) {
           ok = (c.sd == 0) || (s.isz == 0);
@@ -198,12 +256,10 @@ __device__ __forceinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t*
 
 // Bloom test of one node per lane; positives are compacted into the staging queue.
 __device__ __forceinline__ void test_and_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t& sqn, bool active,
-                                               uint64_t x0, uint64_t x1, uint64_t x2, uint32_t e, uint32_t isz,
-                                               uint32_t imax) {
+                                               uint64_t h, uint32_t e, uint32_t isz, uint32_t imax, uint32_t t) {
   bool pass = false;
   if (active) {
-    const uint64_t h = hash_key(x0, x1, x2);
-    const uint64_t word = __ldg(c.bloom + (h & c.bloom_wmask));
+    const uint64_t word = __ldg(c.bloom + fp_index(h, c.bloom_wmask));
     const uint64_t m = bloom_mask(h);
     pass = (word & m) == m;
     ++c.c_probes;
@@ -212,13 +268,14 @@ __device__ __forceinline__ void test_and_stage(K1Ctx& c, K1Warp& W, const uint32
   if (ballot) {
     if (pass) {
       ++c.c_pass;
-      SEntry& s = W.sq[sqn + __popc(ballot & lanemask_lt())];
-      s.w0 = x0;
-      s.w1 = x1;
-      s.w2 = x2;
+      SEntry s;
+      s.h = h;
+      s.t = t;
       s.e = (uint8_t)e;
       s.isz = (uint8_t)isz;
       s.imax = (uint8_t)imax;
+      s.pad = 0;
+      W.sq[sqn + __popc(ballot & lanemask_lt())] = s;
     }
     sqn += __popc(ballot);
     __syncwarp();
@@ -230,7 +287,7 @@ __device__ __forceinline__ void test_and_stage(K1Ctx& c, K1Warp& W, const uint32
 }
 
 // All nodes of the current chunk of deletion entries.
-__device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t nD) {
+__device__ __noinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t nD) {
   const uint32_t lane = lane_id();
   const DeviceIndex* ix = c.ix;
   uint32_t sqn = 0;
@@ -238,17 +295,15 @@ __device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_
   for (uint32_t base = 0; base < nD; base += 32) {
     const uint32_t e = base + lane;
     bool active = e < nD;
-    uint64_t x0 = 0, x1 = 0, x2 = 0;
+    uint64_t h = 0;
     if (active) {
       const DEntry& de = W.dch[e];
-      x0 = de.w0;
-      x1 = de.w1;
-      x2 = de.w2;
+      h = de.h;
       const uint32_t cx = c.L - de.d;
       // useful iff C = D may exist, or (sd = 1) C = D + x may exist within the budget
       active = ccbit(ix->charcount_mask, cx) || (c.sd == 1 && c.ka > de.d && ccbit(ix->charcount_mask, cx + 1));
     }
-    test_and_stage(c, W, prime_of, sqn, active, x0, x1, x2, e, 0, 0);
+    test_and_stage(c, W, prime_of, sqn, active, h, e, 0, 0, 0);
   }
   // (b) the nodes X = D + I', |I'| >= 1, entry by entry; lanes stride over the multiset table
   for (uint32_t e = 0; e < nD; ++e) {
@@ -263,21 +318,40 @@ __device__ __forceinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_
       for (uint32_t base = lo; base < hi; base += 32) {
         const uint32_t t = base + lane;
         bool active = t < hi;
-        uint64_t x0 = de.w0, x1 = de.w1, x2 = de.w2;
+        uint64_t h = de.h;
         uint32_t imax = 0;
         if (active) {
           const MsetEntry me = ix->mset[t];
           imax = me.maxcls;
+          h += me.hsum;
           // canonical generation: never re-insert a deleted class
           for (int a = 0; a < j; ++a)
             for (uint32_t b = 0; b < de.d; ++b) active = active && (me.cls[a] != de.del[b]);
-          active = active && mul192(x0, x1, x2, me.prod);
         }
-        test_and_stage(c, W, prime_of, sqn, active, x0, x1, x2, e, (uint32_t)j, imax);
+        test_and_stage(c, W, prime_of, sqn, active, h, e, (uint32_t)j, imax, t);
       }
     }
   }
   if (sqn) drain_stage(c, W, prime_of, sqn);
+}
+
+// General unranking of deletion set `rem` of size d (queries longer than COLEX_N symbols or more than 3
+// deletions): combinadic positions pos[0] < ... < pos[d-1], then the canonical-run rule.  Cold path.
+__device__ __noinline__ bool unrank_general(const uint32_t* binom, const uint8_t* sorted, uint32_t L, uint32_t d, uint32_t rem,
+                                            uint8_t* pos) {
+  int cpos = (int)L;
+  for (int i = (int)d; i >= 1; --i) {
+    --cpos;
+    while (binom[cpos * 8 + i] > rem) --cpos;
+    pos[i - 1] = (uint8_t)cpos;
+    rem -= binom[cpos * 8 + i];
+  }
+  for (int i = 0; i < (int)d; ++i) {
+    const uint32_t p = pos[i];
+    // canonical: inside a run of equal symbols only a leading part may be deleted
+    if (p > 0 && sorted[p - 1] == sorted[p] && !(i > 0 && pos[i - 1] == p - 1)) return false;
+  }
+  return true;
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32, 4)
@@ -292,12 +366,14 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     for (uint32_t i = threadIdx.x; i < sizeof(DeviceIndex) / 4; i += blockDim.x) dst[i] = src[i];
   }
   for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x) S.binom[i] = ix->binom[i];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) S.rnd[i] = class_rnd(i);
   __syncthreads();
 
   const uint32_t lane = lane_id();
   K1Warp& W = S.w[threadIdx.x >> 5];
   K1Ctx c;
   c.ix = &S.ix;
+  c.rnd = S.rnd;
   c.table = ix->table;
   c.table_mask = ix->table_mask;
   c.bloom = ix->bloom;
@@ -307,6 +383,8 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   c.c_probes = c.c_pass = c.c_steps = c.c_postings = c.c_ana = c.c_inst = 0;
   uint32_t c_dkeys = 0;
   const uint32_t max_cc = ix->max_charcount;
+  const uint32_t* __restrict__ colex2 = ix->colex2;
+  const uint32_t* __restrict__ colex3 = ix->colex3;
 
   for (;;) {
     uint32_t qi = 0;
@@ -329,7 +407,8 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       if (ka > (uint32_t)ANL_MAX_K) {
         flags = QF_UNSUPPORTED;
       } else if (L <= max_cc + ka) {  // else every candidate would be longer than any indexed entry
-        // sort the query symbols (rank sort) so equal symbols are adjacent
+        // sort the query symbols (rank sort) so equal symbols are adjacent; mhash(F) on the way
+        uint64_t hF = 0;
         for (uint32_t i = lane; i < L; i += 32) {
           const uint8_t v = qrow[2 + i];
           uint32_t r = 0;
@@ -338,31 +417,26 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
             r += (u < v) || (u == v && j < i);
           }
           W.sorted[r] = v;
+          hF += S.rnd[v];
         }
+        for (int o = 16; o > 0; o >>= 1) hF += __shfl_xor_sync(FULL, hF, o);
         __syncwarp();
         bool done = false;
         if (bp.stop_at_exact) {
           // StopAtExactMatch (src/lib.rs:1164-1173): if the focus itself is indexed, it is the only result
-          uint64_t f0 = 1, f1 = 0, f2 = 0;
-          bool okf = true;
-          for (uint32_t i = 0; i < L; ++i) okf = okf && mul192(f0, f1, f2, S.ix.prime_of[W.sorted[i]]);
-          if (okf) {
-            if (lane == 0) {
-              W.dch[0].w0 = f0;
-              W.dch[0].w1 = f1;
-              W.dch[0].w2 = f2;
-              W.dch[0].d = 0;
-            }
-            __syncwarp();
-            const uint32_t ka_saved = c.ka;
-            c.ka = 0;  // only the self posting of X = F is acceptable
-            uint32_t sqn = 0;
-            test_and_stage(c, W, S.ix.prime_of, sqn, lane == 0, f0, f1, f2, 0, 0, 0);
-            if (sqn) drain_stage(c, W, S.ix.prime_of, sqn);
-            c.ka = ka_saved;
-            __syncwarp();
-            done = W.nhits > 0;
+          if (lane == 0) {
+            W.dch[0].h = hF;
+            W.dch[0].d = 0;
           }
+          __syncwarp();
+          const uint32_t ka_saved = c.ka;
+          c.ka = 0;  // only the self posting of X = F is acceptable
+          uint32_t sqn = 0;
+          test_and_stage(c, W, S.ix.prime_of, sqn, lane == 0, hF, 0, 0, 0, 0);
+          if (sqn) drain_stage(c, W, S.ix.prime_of, sqn);
+          c.ka = ka_saved;
+          __syncwarp();
+          done = W.nhits > 0;
         }
         if (!done) {
           // enumerate the deletion neighbourhood: all distinct non-empty sub-multisets of the
@@ -374,11 +448,15 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
             flags = QF_UNSUPPORTED;
           } else {
             const uint32_t total = (uint32_t)total64;
+            // fast path: positions fit a 32-bit mask and the unranking tables
+            const bool fast = L <= (uint32_t)COLEX_N && dmax <= 3;
+            uint32_t runstart = 0;  // bit p: sorted[p] starts a run of equal symbols
+            if (fast)
+              for (uint32_t p = 0; p < L; ++p) runstart |= (p == 0 || W.sorted[p - 1] != W.sorted[p]) ? (1u << p) : 0u;
             uint32_t nD = 0;
             for (uint32_t base = 0; base < total; base += 32) {
               const uint32_t t = base + lane;
               bool ok = t < total;
-              uint64_t k0 = 1, k1 = 0, k2 = 0;
               uint32_t d = 0;
               uint8_t pos[ANL_MAX_K];
 #pragma unroll
@@ -389,51 +467,36 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
                   rem -= S.binom[L * 8 + d];
                   ++d;
                 }
-                // combinadic unranking: positions pos[0] < pos[1] < ... < pos[d-1]
-                int cpos = (int)L;
-#pragma unroll
-                for (int i = ANL_MAX_K; i >= 1; --i) {
-                  if (i <= (int)d) {
-                    --cpos;
-                    while (S.binom[cpos * 8 + i] > rem) --cpos;
-                    pos[i - 1] = (uint8_t)cpos;
-                    rem -= S.binom[cpos * 8 + i];
-                  }
-                }
-                // canonical: inside a run of equal symbols only a leading part may be deleted
-#pragma unroll
-                for (int i = 0; i < ANL_MAX_K; ++i) {
-                  if (i < (int)d) {
-                    const uint32_t p = pos[i];
-                    if (p > 0 && W.sorted[p - 1] == W.sorted[p] && !(i > 0 && pos[i - 1] == p - 1)) ok = false;
-                  }
-                }
-                if (ok) {
-                  // key(D) = product of the primes of the remaining symbols
-                  uint64_t pp = 1;
-                  for (uint32_t p = 0; p < L && ok; ++p) {
-                    bool isdel = false;
-#pragma unroll
-                    for (int i = 0; i < ANL_MAX_K; ++i) isdel = isdel || (pos[i] == p);
-                    if (isdel) continue;
-                    pp *= S.ix.prime_of[W.sorted[p]];
-                    if (pp >> 53) {  // next factor (< 2^10) could overflow 64 bits: flush
-                      ok = mul192(k0, k1, k2, pp);
-                      pp = 1;
-                    }
-                  }
-                  if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+                if (fast) {
+                  // colex unranking by table: positions pos[0] < pos[1] < pos[2]
+                  uint32_t pk = rem;  // d == 1: the position itself
+                  if (d == 2) pk = __ldg(colex2 + rem);
+                  if (d == 3) pk = __ldg(colex3 + rem);
+                  if (d >= 1) pos[0] = (uint8_t)(pk & 0xFF);
+                  if (d >= 2) pos[1] = (uint8_t)((pk >> 8) & 0xFF);
+                  if (d >= 3) pos[2] = (uint8_t)((pk >> 16) & 0xFF);
+                  // canonical: inside a run of equal symbols only a leading part may be deleted
+                  if (d >= 1) ok = ok && ((runstart >> pos[0]) & 1u);
+                  if (d >= 2) ok = ok && (((runstart >> pos[1]) & 1u) || pos[0] + 1 == pos[1]);
+                  if (d >= 3) ok = ok && (((runstart >> pos[2]) & 1u) || pos[1] + 1 == pos[2]);
+                } else {
+                  ok = unrank_general(S.binom, W.sorted, L, d, rem, pos);
                 }
               }
               const uint32_t ballot = __ballot_sync(FULL, ok);
               if (ok) {
-                DEntry& de = W.dch[nD + __popc(ballot & lanemask_lt())];
-                de.w0 = k0;
-                de.w1 = k1;
-                de.w2 = k2;
-                de.d = (uint8_t)d;
+                DEntry de;
+                uint64_t h = hF;
 #pragma unroll
-                for (int i = 0; i < ANL_MAX_K; ++i) de.del[i] = (i < (int)d) ? W.sorted[pos[i] == 0xFF ? 0 : pos[i]] : 0xFF;
+                for (int i = 0; i < ANL_MAX_K; ++i) {
+                  const uint8_t sym = (i < (int)d) ? W.sorted[pos[i]] : 0xFF;
+                  de.del[i] = sym;
+                  if (i < (int)d) h -= S.rnd[sym];
+                }
+                de.h = h;
+                de.d = (uint8_t)d;
+                de.pad = 0;
+                W.dch[nD + __popc(ballot & lanemask_lt())] = de;
               }
               nD += __popc(ballot);
               c_dkeys += ok ? 1u : 0u;
