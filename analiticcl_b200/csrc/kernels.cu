@@ -13,6 +13,7 @@
 // Integer / byte work only -- no tensor cores (see DESIGN.md for the rooflines).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -75,286 +76,317 @@ __device__ __forceinline__ bool ccbit(const uint64_t* mask, uint32_t cc) {
 // Every node X = D + I' of the query's neighbourhood (D: a sub-multiset of the focus after d deletions,
 // I': a multiset of inserted symbols) is fingerprinted with the LINEAR multiset hash of
 // device_types.h: mhash(X) = mhash(F) - sum rnd(deleted) + sum rnd(inserted).  One 64-bit add per node,
-// one 8-byte Bloom word per probe.  Only the nodes that pass the filter AND find their table slot get
-// their exact 192-bit prime-product key computed, for the exact verification of the postings.
+// one 8-byte Bloom word per probe.  Nodes that pass the filter are staged (self-contained 32-byte
+// records) and looked up exactly 32 at a time; every posting found is verified EXACTLY with
+// multi-limb arithmetic on the prime-product keys, by cross-multiplication instead of division:
+//     key(C) * prod(deleted)  ==  key(F) * prod(inserted) * p_x        (256-bit products)
+// so the only per-query bignum work is key(F) itself.
+//
+// The kernel is written for a small instruction footprint (ncu showed the previous, fully inlined
+// version stalled 57 % of the time on instruction fetch: 92 KB of SASS against a 32 KB L1.5 I-cache):
+// the exact stage is one non-inlined function, cold general-case code is kept out of line, and
+// per-symbol work runs in short loops over packed bytes instead of unrolled register arrays.
 constexpr int K1_WARPS = 8;
-constexpr int DCH = 64;  // deletion entries per chunk
+constexpr int DCH = 64;  // deletion entries with insertion budget buffered per pass
 constexpr int SQ = 64;   // staging queue capacity (filter positives waiting for the exact lookup)
 
-struct __align__(16) DEntry {  // one element of the deletion neighbourhood of the query
-  uint64_t h;                  // mhash(D)
-  uint8_t d;                   // number of deleted symbols
-  uint8_t del[6];              // the deleted symbols (ascending, may repeat)
-  uint8_t pad;
+// deleted symbols packed one per byte (ascending, unused bytes 0xFF), number of deletions in the top byte
+__device__ __forceinline__ uint32_t dd_count(uint64_t dd) { return (uint32_t)(dd >> 56); }
+// true iff one of the low six bytes of v equals the byte b
+__device__ __forceinline__ bool has_byte6(uint64_t v, uint32_t b) {
+  const uint64_t x = (v ^ (0x0000010101010101ULL * b)) & 0x0000FFFFFFFFFFFFULL;
+  return ((x - 0x0000010101010101ULL) & ~x & 0x0000808080808080ULL) != 0;
+}
+
+struct __align__(8) DEntry {  // an element of the deletion neighbourhood that still has insertion budget
+  uint64_t h;                 // mhash(D)
+  uint64_t dprod;             // product of the primes of the deleted symbols (< 2^60)
+  uint64_t dd;                // deleted symbols, packed
 };
 struct __align__(16) SEntry {  // a node X = D + I' that passed the Bloom filter
   uint64_t h;                  // mhash(X)
+  uint64_t dprod;
+  uint64_t dd;
   uint32_t t;                  // index of I' in the multiset table (unused when isz == 0)
-  uint8_t e;                   // index of D in the current chunk
   uint8_t isz;                 // |I'|
   uint8_t imax;                // largest symbol of I' (0 if empty)
-  uint8_t pad;
+  uint8_t pad[2];
 };
 struct K1Warp {
-  DEntry dch[DCH];
   SEntry sq[SQ];
-  Key192 skey[32];    // drain stage: exact key of each staged node of the current round
-  uint32_t pfx[33];   // drain stage: exclusive prefix of posting counts (+ sentinel)
-  uint32_t poff[32];  // drain stage: first posting of each staged node
+  DEntry dch[DCH];
+  uint64_t nprod[32];  // exact stage: product of the primes of I' per staged node (0 = does not fit: general path)
+  uint64_t kF[3];      // exact key of the focus (valid iff kF_ok)
+  uint32_t pfx[33];    // exact stage: exclusive prefix of posting counts (+ sentinel)
+  uint32_t poff[32];   // exact stage: first posting of each staged node
+  uint32_t stat[6][32];  // lane-local work counters of the non-inlined stages: slots, postings, anagrams, instances, probes, passes
+  uint32_t binomL[8];  // C(L, d)
+  uint32_t kF_ok, nhits, L, ka;
+  uint32_t* hits_q;    // hit list of the current query
   uint8_t sorted[256];
-  uint32_t nhits;
-  uint32_t pad[2];
 };
 struct K1Shared {
-  DeviceIndex ix;  // block-local copy of the model constants (pointers, masks, small tables)
+  DeviceIndex ix;     // block-local copy of the model constants (pointers, masks, small tables)
   uint64_t rnd[256];  // class_rnd of every symbol
-  uint32_t binom[256 * 8];
+  uint32_t hit_cap;
   K1Warp w[K1_WARPS];
 };
 
-struct K1Ctx {
-  const DeviceIndex* ix;
-  const uint64_t* rnd;
-  const Slot* table;
-  uint64_t table_mask;
-  const uint64_t* bloom;
-  uint64_t bloom_wmask;
-  uint32_t* hits_q;  // hit list of the current query
-  uint32_t hit_cap;
-  uint32_t L, ka;
-  int sd;
-  // lane-local work counters
-  uint32_t c_probes, c_pass, c_steps, c_postings, c_ana, c_inst;
-};
+// a[3] * m -> r[4]
+__device__ __forceinline__ void mul192x64(uint64_t a0, uint64_t a1, uint64_t a2, uint64_t m, uint64_t& r0, uint64_t& r1,
+                                          uint64_t& r2, uint64_t& r3) {
+  const uint64_t l0 = a0 * m, h0 = __umul64hi(a0, m);
+  const uint64_t l1 = a1 * m, h1 = __umul64hi(a1, m);
+  const uint64_t l2 = a2 * m, h2 = __umul64hi(a2, m);
+  r0 = l0;
+  r1 = l1 + h0;
+  const uint64_t c1 = r1 < l1;
+  r2 = l2 + h1;
+  uint64_t c2 = r2 < l2;
+  r2 += c1;
+  c2 += r2 < c1;
+  r3 = h2 + c2;
+}
 
-// Exact 192-bit key of the node X = F - del(D) + I' (only for nodes whose fingerprint found a slot).
-// false: the product does not fit 192 bits, so X cannot equal or divide into any indexed key.
-__device__ __forceinline__ bool node_key(const K1Ctx& c, const K1Warp& W, const uint32_t* prime_of, const DEntry& de,
-                                         const SEntry& s, uint64_t& k0, uint64_t& k1, uint64_t& k2) {
-  k0 = 1;
-  k1 = 0;
-  k2 = 0;
-  uint64_t pp = 1;
+// General exact verification (cold): key(F - deleted + I' + x) == key(C) by multiplying out the node's
+// symbols.  Used when key(F) itself does not fit 192 bits or the inserted product does not fit 53 bits.
+__device__ __noinline__ bool verify_general(const K1Shared& S, const K1Warp& W, const SEntry& s, uint32_t x, const Key192& ck) {
+  uint64_t k0 = 1, k1 = 0, k2 = 0, pp = 1;
   bool ok = true;
+  const uint32_t d = dd_count(s.dd);
   uint32_t dp = 0;  // next deleted symbol to drop (both lists ascend)
-  for (uint32_t p = 0; p < c.L && ok; ++p) {
+  #pragma unroll 1
+  for (uint32_t p = 0; p < W.L && ok; ++p) {
     const uint32_t sym = W.sorted[p];
-    if (dp < de.d && de.del[dp] == sym) {
+    if (dp < d && ((s.dd >> (8 * dp)) & 0xFF) == sym) {
       ++dp;
       continue;
     }
-    pp *= prime_of[sym];
+    pp *= S.ix.prime_of[sym];
     if (pp >> 53) {  // next factor (< 2^10) could overflow 64 bits: flush
       ok = mul192(k0, k1, k2, pp);
       pp = 1;
     }
   }
   if (ok && s.isz) {
-    const MsetEntry me = c.ix->mset[s.t];
+    const uint64_t cls = __ldg(reinterpret_cast<const uint64_t*>(S.ix.mset + s.t) + 1);  // cls[6] | j | maxcls
+    #pragma unroll 1
     for (uint32_t a = 0; a < s.isz && ok; ++a) {
-      pp *= prime_of[me.cls[a]];
+      pp *= S.ix.prime_of[(cls >> (8 * a)) & 0xFF];
       if (pp >> 53) {
         ok = mul192(k0, k1, k2, pp);
         pp = 1;
       }
     }
   }
+  if (ok && x != POST_SELF) {
+    pp *= S.ix.prime_of[x];
+    if (pp >> 53) {
+      ok = mul192(k0, k1, k2, pp);
+      pp = 1;
+    }
+  }
   if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
-  return ok;
+  return ok && ck.w0 == k0 && ck.w1 == k1 && ck.w2 == k2;
 }
 
-// Exact lookup of the staged nodes, in two lane-parallel stages: (1) one node per lane finds its
-// table slot by fingerprint and, if there is one, computes the node's exact key; (2) the postings of
-// all 32 nodes are flattened (warp scan) and verified one posting per lane -- against the anagram's
-// own key and against the canonical-generation rules (each indexed anagram C is produced exactly
-// once: from D = F meet C and the ascending insertion order).
-// (Deliberately NOT inlined, like process_chunk: the probe kernel is instruction-fetch bound when its
-// code outgrows the 32 KB L1.5 instruction cache -- ncu: 57 % of the stall samples were "no instruction"
-// with five inlined copies of this function.)
-__device__ __noinline__ void drain_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t cnt) {
+// The exact stage for the first cnt <= 32 staged nodes, in two lane-parallel steps: (1) one node per
+// lane finds its table slot by fingerprint; (2) the postings of all nodes are flattened (warp scan)
+// and verified one posting per lane -- against the canonical-generation rules (each indexed anagram C
+// is produced exactly once: from D = F meet C and the ascending insertion order) and against the
+// anagram's own key.  Not inlined: one copy, called from every place that stages nodes.
+__device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
   const uint32_t lane = lane_id();
-  for (uint32_t base = 0; base < cnt; base += 32) {
-    const uint32_t i = base + lane;
-    uint32_t poff = 0, pcnt = 0;
-    if (i < cnt) {
-      const SEntry s = W.sq[i];
-      const uint64_t fp = s.h;
-      uint64_t idx = fp_index(fp, c.table_mask);
-      for (;;) {
-        const Slot sl = c.table[idx];
-        ++c.c_steps;
-        if (sl.post_cnt == 0) break;
-        if (sl.fp == fp) {
-          poff = sl.post_off;
-          pcnt = sl.post_cnt;
-          break;
-        }
-        idx = (idx + 1) & c.table_mask;
+  const DeviceIndex& ix = S.ix;
+  uint32_t c_steps = 0, c_post = 0, c_ana = 0, c_inst = 0;
+  uint32_t poff = 0, pcnt = 0;
+  if (lane < cnt) {
+    const uint64_t fp = W.sq[lane].h;
+    uint64_t idx = fp_index(fp, ix.table_mask);
+    for (;;) {
+      const Slot sl = ix.table[idx];
+      ++c_steps;
+      if (sl.post_cnt == 0) break;
+      if (sl.fp == fp) {
+        poff = sl.post_off;
+        pcnt = sl.post_cnt;
+        break;
       }
-      if (pcnt) {
-        uint64_t k0, k1, k2;
-        if (node_key(c, W, prime_of, W.dch[s.e], s, k0, k1, k2)) {
-          W.skey[lane].w0 = k0;
-          W.skey[lane].w1 = k1;
-          W.skey[lane].w2 = k2;
-        } else {
-          pcnt = 0;
-        }
+      idx = (idx + 1) & ix.table_mask;
+    }
+    if (pcnt) {
+      uint64_t np = 1;
+      const uint32_t isz = W.sq[lane].isz;
+      if (isz) {
+        const uint64_t cls = __ldg(reinterpret_cast<const uint64_t*>(ix.mset + W.sq[lane].t) + 1);  // cls[6] | j | maxcls
+        #pragma unroll 1
+        for (uint32_t a = 0; a < isz; ++a) np = (np >> 53) ? 0 : np * ix.prime_of[(cls >> (8 * a)) & 0xFF];
+        if (np >> 53) np = 0;
       }
+      W.nprod[lane] = np;
     }
-    uint32_t incl = pcnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= (uint32_t)o) incl += t;
-    }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    W.pfx[lane] = incl - pcnt;
-    W.poff[lane] = poff;
-    __syncwarp();
-    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-      const uint32_t t = t0 + lane;
-      if (t < total) {
-        uint32_t owner = 0;  // largest lane whose exclusive prefix is <= t
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (W.pfx[owner + step] <= t) owner += step;
-        const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
-        const SEntry s = W.sq[base + owner];
-        const DEntry& de = W.dch[s.e];
-        const uint32_t r = __ldg(c.ix->post_ana + p);
-        const uint32_t x = __ldg(c.ix->post_cls + p);
-        ++c.c_postings;
-        uint64_t x0 = W.skey[owner].w0, x1 = W.skey[owner].w1, x2 = W.skey[owner].w2;
-        bool ok;
-        if (x == POST_SELF) {
-          ok = (c.sd == 0) || (s.isz == 0);
-        } else {
-          const uint32_t budget_left = c.ka - de.d - s.isz;
-          ok = budget_left >= 1 && (s.isz == 0 || x >= s.imax);
-#pragma unroll
-          for (int q = 0; q < ANL_MAX_K; ++q) ok = ok && (q >= (int)de.d || de.del[q] != x);
-          ok = ok && mul192(x0, x1, x2, prime_of[x]);
-        }
-        if (ok) {
-          const Key192 ck = c.ix->ana_key[r];
-          if (ck.w0 == x0 && ck.w1 == x1 && ck.w2 == x2) {  // else: fingerprint collision
-            const uint32_t io = __ldg(c.ix->ana_inst_off + r), ie = __ldg(c.ix->ana_inst_off + r + 1);
-            const uint32_t n = ie - io;
-            ++c.c_ana;
-            c.c_inst += n;
-            const uint32_t pos = atomicAdd(&W.nhits, n);
-            for (uint32_t q = 0; q < n; ++q)
-              if (pos + q < c.hit_cap) c.hits_q[pos + q] = io + q;
-          }
-        }
-      }
-    }
-    __syncwarp();
   }
+  uint32_t incl = pcnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(FULL, incl, 31);
+  W.pfx[lane] = incl - pcnt;
+  W.poff[lane] = poff;
+  __syncwarp();
+  const uint32_t ka = W.ka;
+  const int sd = ix.sd;
+  const bool kF_ok = W.kF_ok != 0;
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    if (t < total) {
+      uint32_t owner = 0;  // largest lane whose exclusive prefix is <= t
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1)
+        if (W.pfx[owner + step] <= t) owner += step;
+      const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
+      const SEntry& s = W.sq[owner];
+      const uint32_t r = __ldg(ix.post_ana + p);
+      const uint32_t x = __ldg(ix.post_cls + p);
+      ++c_post;
+      const uint64_t dd = s.dd;
+      const uint32_t isz = s.isz;
+      bool ok;
+      if (x == POST_SELF) {
+        ok = (sd == 0) || (isz == 0);
+      } else {
+        // budget left for the last insertion; ascending insertion order; never re-insert a deleted class
+        ok = ka >= dd_count(dd) + isz + 1 && (isz == 0 || x >= s.imax) && !has_byte6(dd, x);
+      }
+      if (ok) {
+        const Key192 ck = ix.ana_key[r];
+        const uint64_t np = W.nprod[owner];
+        bool match;
+        if (kF_ok && np != 0) {
+          const uint64_t n = (x == POST_SELF) ? np : np * ix.prime_of[x];
+          uint64_t a0, a1, a2, a3, b0, b1, b2, b3;
+          mul192x64(ck.w0, ck.w1, ck.w2, s.dprod, a0, a1, a2, a3);
+          mul192x64(W.kF[0], W.kF[1], W.kF[2], n, b0, b1, b2, b3);
+          match = a0 == b0 && a1 == b1 && a2 == b2 && a3 == b3;
+        } else {
+          match = verify_general(S, W, s, x, ck);
+        }
+        if (match) {  // else: fingerprint collision
+          const uint32_t io = __ldg(ix.ana_inst_off + r), ie = __ldg(ix.ana_inst_off + r + 1);
+          const uint32_t n = ie - io;
+          ++c_ana;
+          c_inst += n;
+          const uint32_t pos = atomicAdd(&W.nhits, n);
+          #pragma unroll 1
+          for (uint32_t q = 0; q < n; ++q)
+            if (pos + q < S.hit_cap) W.hits_q[pos + q] = io + q;
+        }
+      }
+    }
+  }
+  W.stat[0][lane] += c_steps;
+  W.stat[1][lane] += c_post;
+  W.stat[2][lane] += c_ana;
+  W.stat[3][lane] += c_inst;
+  __syncwarp();
 }
 
-// Bloom test of one node per lane; positives are compacted into the staging queue.
-__device__ __forceinline__ void test_and_stage(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t& sqn, bool active,
-                                               uint64_t h, uint32_t e, uint32_t isz, uint32_t imax, uint32_t t) {
-  bool pass = false;
-  if (active) {
-    const uint64_t word = __ldg(c.bloom + fp_index(h, c.bloom_wmask));
-    const uint64_t m = bloom_mask(h);
-    pass = (word & m) == m;
-    ++c.c_probes;
-  }
+// Queue the nodes that passed the Bloom filter; whenever 32 are waiting, run the exact stage on them.
+__device__ __forceinline__ void stage(K1Shared& S, K1Warp& W, uint32_t& sqn, bool pass, uint64_t h, uint64_t dprod, uint64_t dd,
+                                      uint32_t t, uint32_t isz, uint32_t imax) {
   const uint32_t ballot = __ballot_sync(FULL, pass);
-  if (ballot) {
-    if (pass) {
-      ++c.c_pass;
-      SEntry s;
-      s.h = h;
-      s.t = t;
-      s.e = (uint8_t)e;
-      s.isz = (uint8_t)isz;
-      s.imax = (uint8_t)imax;
-      s.pad = 0;
-      W.sq[sqn + __popc(ballot & lanemask_lt())] = s;
-    }
-    sqn += __popc(ballot);
+  if (ballot == 0) return;
+  const uint32_t lane = lane_id();
+  if (pass) {
+    SEntry s;
+    s.h = h;
+    s.dprod = dprod;
+    s.dd = dd;
+    s.t = t;
+    s.isz = (uint8_t)isz;
+    s.imax = (uint8_t)imax;
+    s.pad[0] = s.pad[1] = 0;
+    W.sq[sqn + __popc(ballot & lanemask_lt())] = s;
+  }
+  sqn += __popc(ballot);
+  __syncwarp();
+  if (sqn >= 32) {
+    exact_stage(S, W, 32);
+    const uint32_t rest = sqn - 32;  // < 32: move the tail to the front
+    SEntry tmp;
+    if (lane < rest) tmp = W.sq[32 + lane];
     __syncwarp();
-    if (sqn > SQ - 32) {
-      drain_stage(c, W, prime_of, sqn);
-      sqn = 0;
-    }
+    if (lane < rest) W.sq[lane] = tmp;
+    __syncwarp();
+    sqn = rest;
   }
 }
 
-// All nodes of the current chunk of deletion entries.
-__device__ __noinline__ void process_chunk(K1Ctx& c, K1Warp& W, const uint32_t* prime_of, uint32_t nD) {
+__device__ __forceinline__ bool bloom_pass(const K1Shared& S, uint64_t h) {
+  const uint64_t word = __ldg(S.ix.bloom + fp_index(h, S.ix.bloom_mask));
+  const uint64_t m = bloom_mask(h);
+  return (word & m) == m;
+}
+
+// The nodes X = D + I', |I'| >= 1, of the buffered deletion entries; lanes stride over the multiset table.
+// Returns the new staging-queue length.
+__device__ __noinline__ uint32_t insertion_nodes(K1Shared& S, K1Warp& W, uint32_t nD, uint32_t sqn) {
   const uint32_t lane = lane_id();
-  const DeviceIndex* ix = c.ix;
-  uint32_t sqn = 0;
-  // (a) the nodes X = D themselves, one per lane
-  for (uint32_t base = 0; base < nD; base += 32) {
-    const uint32_t e = base + lane;
-    bool active = e < nD;
-    uint64_t h = 0;
-    if (active) {
-      const DEntry& de = W.dch[e];
-      h = de.h;
-      const uint32_t cx = c.L - de.d;
-      // useful iff C = D may exist, or (sd = 1) C = D + x may exist within the budget
-      active = ccbit(ix->charcount_mask, cx) || (c.sd == 1 && c.ka > de.d && ccbit(ix->charcount_mask, cx + 1));
-    }
-    test_and_stage(c, W, prime_of, sqn, active, h, e, 0, 0, 0);
-  }
-  // (b) the nodes X = D + I', |I'| >= 1, entry by entry; lanes stride over the multiset table
+  const DeviceIndex& ix = S.ix;
+  uint32_t probes = 0, passes = 0;
   for (uint32_t e = 0; e < nD; ++e) {
     const DEntry de = W.dch[e];  // warp-uniform broadcast
-    const int jmax = (int)c.ka - (int)de.d - c.sd;
-    if (jmax < 1) break;  // entries are in ascending deletion depth: no later entry has insertions left
+    const uint32_t d = dd_count(de.dd);
+    const int jmax = (int)W.ka - (int)d - ix.sd;
     for (int j = 1; j <= jmax; ++j) {
-      const uint32_t cx = c.L - de.d + j;
-      const bool useful = (c.sd == 0) ? ccbit(ix->charcount_mask, cx) : ccbit(ix->charcount_mask, cx + 1);
+      const uint32_t cx = W.L - d + j;
+      const bool useful = (ix.sd == 0) ? ccbit(ix.charcount_mask, cx) : ccbit(ix.charcount_mask, cx + 1);
       if (!useful) continue;
-      const uint32_t lo = ix->mset_end[j - 1], hi = ix->mset_end[j];
+      const uint32_t lo = ix.mset_end[j - 1], hi = ix.mset_end[j];
       for (uint32_t base = lo; base < hi; base += 32) {
         const uint32_t t = base + lane;
         bool active = t < hi;
         uint64_t h = de.h;
         uint32_t imax = 0;
         if (active) {
-          const MsetEntry me = ix->mset[t];
-          imax = me.maxcls;
-          h += me.hsum;
+          const ulonglong2 me = __ldg(reinterpret_cast<const ulonglong2*>(ix.mset + t));  // {hsum, cls[6] | j | maxcls}
+          h += me.x;
+          imax = (uint32_t)(me.y >> 56);
           // canonical generation: never re-insert a deleted class
-          for (int a = 0; a < j; ++a)
-            for (uint32_t b = 0; b < de.d; ++b) active = active && (me.cls[a] != de.del[b]);
+          #pragma unroll 1
+          for (uint32_t b = 0; b < d; ++b) active = active && !has_byte6(me.y, (uint32_t)(de.dd >> (8 * b)) & 0xFF);
         }
-        test_and_stage(c, W, prime_of, sqn, active, h, e, (uint32_t)j, imax, t);
+        const bool pass = active && bloom_pass(S, h);
+        probes += active;
+        passes += pass;
+        stage(S, W, sqn, pass, h, de.dprod, de.dd, t, (uint32_t)j, imax);
       }
     }
   }
-  if (sqn) drain_stage(c, W, prime_of, sqn);
+  W.stat[4][lane] += probes;
+  W.stat[5][lane] += passes;
+  return sqn;
 }
 
 // General unranking of deletion set `rem` of size d (queries longer than COLEX_N symbols or more than 3
-// deletions): combinadic positions pos[0] < ... < pos[d-1], then the canonical-run rule.  Cold path.
-__device__ __noinline__ bool unrank_general(const uint32_t* binom, const uint8_t* sorted, uint32_t L, uint32_t d, uint32_t rem,
-                                            uint8_t* pos) {
+// deletions): combinadic positions p0 < ... < p(d-1), packed one per byte.  Cold path.
+__device__ __noinline__ uint64_t unrank_general(const uint32_t* __restrict__ binom, uint32_t L, uint32_t d, uint32_t rem) {
+  uint64_t pk = 0;
   int cpos = (int)L;
+  #pragma unroll 1
   for (int i = (int)d; i >= 1; --i) {
     --cpos;
-    while (binom[cpos * 8 + i] > rem) --cpos;
-    pos[i - 1] = (uint8_t)cpos;
-    rem -= binom[cpos * 8 + i];
+    while (__ldg(binom + cpos * 8 + i) > rem) --cpos;
+    pk |= (uint64_t)(uint32_t)cpos << (8 * (i - 1));
+    rem -= __ldg(binom + cpos * 8 + i);
   }
-  for (int i = 0; i < (int)d; ++i) {
-    const uint32_t p = pos[i];
-    // canonical: inside a run of equal symbols only a leading part may be deleted
-    if (p > 0 && sorted[p - 1] == sorted[p] && !(i > 0 && pos[i - 1] == p - 1)) return false;
-  }
-  return true;
+  return pk;
 }
 
-__global__ void __launch_bounds__(K1_WARPS * 32, 4)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(K1_WARPS * 32, MIN_CTAS)
 probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
              uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
@@ -365,26 +397,19 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.ix);
     for (uint32_t i = threadIdx.x; i < sizeof(DeviceIndex) / 4; i += blockDim.x) dst[i] = src[i];
   }
-  for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x) S.binom[i] = ix->binom[i];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) S.rnd[i] = class_rnd(i);
-  __syncthreads();
-
+  if (threadIdx.x == 0) S.hit_cap = bp.hit_cap;
   const uint32_t lane = lane_id();
   K1Warp& W = S.w[threadIdx.x >> 5];
-  K1Ctx c;
-  c.ix = &S.ix;
-  c.rnd = S.rnd;
-  c.table = ix->table;
-  c.table_mask = ix->table_mask;
-  c.bloom = ix->bloom;
-  c.bloom_wmask = ix->bloom_mask;
-  c.hit_cap = bp.hit_cap;
-  c.sd = ix->sd;
-  c.c_probes = c.c_pass = c.c_steps = c.c_postings = c.c_ana = c.c_inst = 0;
-  uint32_t c_dkeys = 0;
-  const uint32_t max_cc = ix->max_charcount;
-  const uint32_t* __restrict__ colex2 = ix->colex2;
-  const uint32_t* __restrict__ colex3 = ix->colex3;
+  for (int k = 0; k < 6; ++k) W.stat[k][lane] = 0;
+  __syncthreads();
+
+  uint32_t c_dkeys = 0, c_probes = 0, c_pass = 0;
+  const uint32_t max_cc = S.ix.max_charcount;
+  const int sd = S.ix.sd;
+  const uint32_t* __restrict__ colex2 = S.ix.colex2;
+  const uint32_t* __restrict__ colex3 = S.ix.colex3;
+  const uint32_t* __restrict__ binom = S.ix.binom;
 
   for (;;) {
     uint32_t qi = 0;
@@ -394,120 +419,143 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     const uint32_t q = qlist ? qlist[qi] : qi;
     const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
     const uint32_t L = qrow[0];
-    c.hits_q = hits + (size_t)qi * bp.hit_cap;
     uint32_t flags = 0;
-    if (lane == 0) W.nhits = 0;
+    const uint32_t ka = L ? apply_threshold(bp.max_anagram, L) : 0;
+    if (lane == 0) {
+      W.nhits = 0;
+      W.L = L;
+      W.ka = ka;
+      W.hits_q = hits + (size_t)qi * bp.hit_cap;
+    }
     __syncwarp();
     if (L == 0) {
       flags = QF_EMPTY;
-    } else {
-      const uint32_t ka = apply_threshold(bp.max_anagram, L);
-      c.L = L;
-      c.ka = ka;
-      if (ka > (uint32_t)ANL_MAX_K) {
-        flags = QF_UNSUPPORTED;
-      } else if (L <= max_cc + ka) {  // else every candidate would be longer than any indexed entry
-        // sort the query symbols (rank sort) so equal symbols are adjacent; mhash(F) on the way
-        uint64_t hF = 0;
-        for (uint32_t i = lane; i < L; i += 32) {
-          const uint8_t v = qrow[2 + i];
-          uint32_t r = 0;
-          for (uint32_t j = 0; j < L; ++j) {
-            const uint8_t u = qrow[2 + j];
-            r += (u < v) || (u == v && j < i);
-          }
-          W.sorted[r] = v;
-          hF += S.rnd[v];
+    } else if (ka > (uint32_t)ANL_MAX_K) {
+      flags = QF_UNSUPPORTED;
+    } else if (L <= max_cc + ka) {  // else every candidate would be longer than any indexed entry
+      // sort the query symbols (rank sort) so equal symbols are adjacent; mhash(F) on the way
+      uint64_t hF = 0;
+      #pragma unroll 1
+      for (uint32_t i = lane; i < L; i += 32) {
+        const uint8_t v = qrow[2 + i];
+        uint32_t r = 0;
+        #pragma unroll 1
+        for (uint32_t j = 0; j < L; ++j) {
+          const uint8_t u = qrow[2 + j];
+          r += (u < v) || (u == v && j < i);
         }
-        for (int o = 16; o > 0; o >>= 1) hF += __shfl_xor_sync(FULL, hF, o);
+        W.sorted[r] = v;
+        hF += S.rnd[v];
+      }
+      for (int o = 16; o > 0; o >>= 1) hF += __shfl_xor_sync(FULL, hF, o);
+      const uint32_t dmax = min(ka, L - 1);
+      if (lane <= dmax) W.binomL[lane] = __ldg(binom + L * 8 + lane);
+      __syncwarp();
+      {
+        // exact key of the focus (every lane computes the same value; lane 0 publishes it)
+        uint64_t k0 = 1, k1 = 0, k2 = 0, pp = 1;
+        bool ok = true;
+        #pragma unroll 1
+        for (uint32_t p = 0; p < L && ok; ++p) {
+          pp *= S.ix.prime_of[W.sorted[p]];
+          if (pp >> 53) {
+            ok = mul192(k0, k1, k2, pp);
+            pp = 1;
+          }
+        }
+        if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+        if (lane == 0) {
+          W.kF[0] = k0;
+          W.kF[1] = k1;
+          W.kF[2] = k2;
+          W.kF_ok = ok ? 1u : 0u;
+        }
+      }
+      __syncwarp();
+      uint32_t sqn = 0;
+      bool done = false;
+      if (bp.stop_at_exact) {
+        // StopAtExactMatch (src/lib.rs:1164-1173): if the focus itself is indexed, it is the only result
+        if (lane == 0) W.ka = 0;  // only the self posting of X = F is acceptable
         __syncwarp();
-        bool done = false;
-        if (bp.stop_at_exact) {
-          // StopAtExactMatch (src/lib.rs:1164-1173): if the focus itself is indexed, it is the only result
-          if (lane == 0) {
-            W.dch[0].h = hF;
-            W.dch[0].d = 0;
-          }
-          __syncwarp();
-          const uint32_t ka_saved = c.ka;
-          c.ka = 0;  // only the self posting of X = F is acceptable
-          uint32_t sqn = 0;
-          test_and_stage(c, W, S.ix.prime_of, sqn, lane == 0, hF, 0, 0, 0, 0);
-          if (sqn) drain_stage(c, W, S.ix.prime_of, sqn);
-          c.ka = ka_saved;
-          __syncwarp();
-          done = W.nhits > 0;
-        }
-        if (!done) {
-          // enumerate the deletion neighbourhood: all distinct non-empty sub-multisets of the
-          // query reachable by d <= ka deletions (src/iterators.rs:153-187 yields the same set)
-          const uint32_t dmax = min(ka, L - 1);
-          uint64_t total64 = 0;
-          for (uint32_t d = 0; d <= dmax; ++d) total64 += S.binom[L * 8 + d];
-          if (total64 > 0x7FFFFFFFull) {
-            flags = QF_UNSUPPORTED;
-          } else {
-            const uint32_t total = (uint32_t)total64;
-            // fast path: positions fit a 32-bit mask and the unranking tables
-            const bool fast = L <= (uint32_t)COLEX_N && dmax <= 3;
-            uint32_t runstart = 0;  // bit p: sorted[p] starts a run of equal symbols
-            if (fast)
-              for (uint32_t p = 0; p < L; ++p) runstart |= (p == 0 || W.sorted[p - 1] != W.sorted[p]) ? (1u << p) : 0u;
-            uint32_t nD = 0;
-            for (uint32_t base = 0; base < total; base += 32) {
-              const uint32_t t = base + lane;
-              bool ok = t < total;
-              uint32_t d = 0;
-              uint8_t pos[ANL_MAX_K];
-#pragma unroll
-              for (int i = 0; i < ANL_MAX_K; ++i) pos[i] = 0xFF;
-              if (ok) {
-                uint32_t rem = t;
-                while (rem >= S.binom[L * 8 + d]) {
-                  rem -= S.binom[L * 8 + d];
-                  ++d;
-                }
-                if (fast) {
-                  // colex unranking by table: positions pos[0] < pos[1] < pos[2]
-                  uint32_t pk = rem;  // d == 1: the position itself
-                  if (d == 2) pk = __ldg(colex2 + rem);
-                  if (d == 3) pk = __ldg(colex3 + rem);
-                  if (d >= 1) pos[0] = (uint8_t)(pk & 0xFF);
-                  if (d >= 2) pos[1] = (uint8_t)((pk >> 8) & 0xFF);
-                  if (d >= 3) pos[2] = (uint8_t)((pk >> 16) & 0xFF);
-                  // canonical: inside a run of equal symbols only a leading part may be deleted
-                  if (d >= 1) ok = ok && ((runstart >> pos[0]) & 1u);
-                  if (d >= 2) ok = ok && (((runstart >> pos[1]) & 1u) || pos[0] + 1 == pos[1]);
-                  if (d >= 3) ok = ok && (((runstart >> pos[2]) & 1u) || pos[1] + 1 == pos[2]);
-                } else {
-                  ok = unrank_general(S.binom, W.sorted, L, d, rem, pos);
-                }
+        const bool pass = lane == 0 && bloom_pass(S, hF);
+        c_probes += lane == 0;
+        c_pass += pass;
+        stage(S, W, sqn, pass, hF, 1, 0x00FFFFFFFFFFFFFFULL, 0, 0, 0);
+        if (sqn) exact_stage(S, W, sqn);
+        sqn = 0;
+        if (lane == 0) W.ka = ka;
+        __syncwarp();
+        done = W.nhits > 0;
+      }
+      if (!done) {
+        // enumerate the deletion neighbourhood: all distinct non-empty sub-multisets of the
+        // query reachable by d <= ka deletions (src/iterators.rs:153-187 yields the same set)
+        uint64_t total64 = 0;
+        #pragma unroll 1
+        for (uint32_t d = 0; d <= dmax; ++d) total64 += W.binomL[d];
+        if (total64 > 0x7FFFFFFFull) {
+          flags = QF_UNSUPPORTED;
+        } else {
+          const uint32_t total = (uint32_t)total64;
+          const bool fast = L <= (uint32_t)COLEX_N;
+          uint32_t nD = 0;
+          for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t t = base + lane;
+            bool ok = t < total;
+            uint32_t d = 0;
+            uint64_t h = hF, dprod = 1, dd = 0x00FFFFFFFFFFFFFFULL;
+            if (ok) {
+              uint32_t rem = t;
+              while (rem >= W.binomL[d]) {
+                rem -= W.binomL[d];
+                ++d;
               }
-              const uint32_t ballot = __ballot_sync(FULL, ok);
-              if (ok) {
-                DEntry de;
-                uint64_t h = hF;
-#pragma unroll
-                for (int i = 0; i < ANL_MAX_K; ++i) {
-                  const uint8_t sym = (i < (int)d) ? W.sorted[pos[i]] : 0xFF;
-                  de.del[i] = sym;
-                  if (i < (int)d) h -= S.rnd[sym];
-                }
-                de.h = h;
-                de.d = (uint8_t)d;
-                de.pad = 0;
-                W.dch[nD + __popc(ballot & lanemask_lt())] = de;
+              // colex unranking: positions p0 < p1 < ... packed one per byte
+              uint64_t pk = rem;  // d == 1: the position itself
+              if (fast && d == 2) pk = __ldg(colex2 + rem);
+              else if (fast && d == 3) pk = __ldg(colex3 + rem);
+              else if (d >= 2) pk = unrank_general(binom, L, d, rem);
+              uint32_t prev = 0xFFFFFFFFu;
+              #pragma unroll 1
+              for (uint32_t i = 0; i < d; ++i) {
+                const uint32_t p = (uint32_t)(pk >> (8 * i)) & 0xFF;
+                const uint32_t sym = W.sorted[p];
+                // canonical: inside a run of equal symbols only a leading part may be deleted
+                if (p > 0 && W.sorted[p - 1] == sym && prev + 1 != p) ok = false;
+                prev = p;
+                h -= S.rnd[sym];
+                dprod *= S.ix.prime_of[sym];
+                dd = (dd & ~(0xFFULL << (8 * i))) | ((uint64_t)sym << (8 * i));
               }
-              nD += __popc(ballot);
-              c_dkeys += ok ? 1u : 0u;
-              __syncwarp();
-              if (nD > DCH - 32 || base + 32 >= total) {
-                process_chunk(c, W, S.ix.prime_of, nD);
-                nD = 0;
-                __syncwarp();
-              }
+              dd |= (uint64_t)d << 56;
+            }
+            c_dkeys += ok;
+            // the node X = D itself: useful iff C = D may exist, or (sd = 1) C = D + x may exist within the budget
+            const uint32_t cx = L - d;
+            const bool probe = ok && (ccbit(S.ix.charcount_mask, cx) || (sd == 1 && ka > d && ccbit(S.ix.charcount_mask, cx + 1)));
+            const bool pass = probe && bloom_pass(S, h);
+            c_probes += probe;
+            c_pass += pass;
+            stage(S, W, sqn, pass, h, dprod, dd, 0, 0, 0);
+            // entries with budget for insertions beyond the table's own depth are buffered for the insertion pass
+            const bool ins = ok && (int)ka - (int)d - sd >= 1;
+            const uint32_t ballot = __ballot_sync(FULL, ins);
+            if (ins) {
+              DEntry de;
+              de.h = h;
+              de.dprod = dprod;
+              de.dd = dd;
+              W.dch[nD + __popc(ballot & lanemask_lt())] = de;
+            }
+            nD += __popc(ballot);
+            __syncwarp();
+            if (nD > DCH - 32 || (base + 32 >= total && nD)) {
+              sqn = insertion_nodes(S, W, nD, sqn);
+              nD = 0;
             }
           }
+          if (sqn) exact_stage(S, W, sqn);
         }
       }
     }
@@ -523,21 +571,16 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 
   // flush the work counters (one atomic per counter per warp)
   if (counters) {
-    unsigned long long v[7] = {c_dkeys, c.c_probes, c.c_pass, c.c_steps, c.c_postings, c.c_ana, c.c_inst};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      unsigned long long x = v[k];
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-      v[k] = x;
-    }
-    if (lane == 0) {
-      atomicAdd(&counters->deletion_keys, v[0]);
-      atomicAdd(&counters->probes, v[1]);
-      atomicAdd(&counters->filter_pass, v[2]);
-      atomicAdd(&counters->table_steps, v[3]);
-      atomicAdd(&counters->postings, v[4]);
-      atomicAdd(&counters->anagram_hits, v[5]);
-      atomicAdd(&counters->instance_pairs, v[6]);
+    // lane-local u32 counts (a warp handles far fewer than 2^32 units per launch)
+    W.stat[4][lane] += c_probes;
+    W.stat[5][lane] += c_pass;
+    const uint32_t dk = __reduce_add_sync(FULL, c_dkeys);
+    if (lane == 0) atomicAdd(&counters->deletion_keys, (unsigned long long)dk);
+    const int order[6] = {4, 5, 0, 1, 2, 3};  // probes, filter_pass, table_steps, postings, anagram_hits, instance_pairs
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+      const uint32_t x = __reduce_add_sync(FULL, W.stat[order[k]][lane]);
+      if (lane == 0) atomicAdd(&counters->probes + k, (unsigned long long)x);
     }
   }
 }
@@ -1207,6 +1250,10 @@ size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap) {
 // launchers
 // ================================================================================================
 static int g_k1_ctas_per_sm = 0;
+static int g_k1_variant = 4;  // resident CTAs per SM the probe kernel is compiled for (register budget); ANL_K1_CTAS=3|4
+typedef void (*ProbeFn)(const DeviceIndex*, const BatchParams, const uint8_t*, const uint32_t*, uint32_t, uint32_t*, uint32_t*,
+                        uint32_t*, unsigned int*, Counters*);
+static ProbeFn probe_fn() { return g_k1_variant == 3 ? probe_kernel<3> : probe_kernel<4>; }
 
 static uint32_t ring_depth(const BatchParams& bp) {
   // rows needed = max edit distance + 2; thresholds are capped at 255 but anything beyond 14 is
@@ -1217,11 +1264,12 @@ static uint32_t ring_depth(const BatchParams& bp) {
 }
 
 cudaError_t configure_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
+  if (const char* v = getenv("ANL_K1_CTAS")) g_k1_variant = atoi(v) == 3 ? 3 : 4;
+  cudaError_t e = cudaFuncSetAttribute(probe_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_kernel, K1_WARPS * 32, sizeof(K1Shared));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_fn(), K1_WARPS * 32, sizeof(K1Shared));
   return e;
 }
 
@@ -1237,7 +1285,7 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   long long grid = (long long)sm_count * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  probe_kernel<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
+  probe_fn()<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
                                                                             lb.hit_count, lb.qflags, lb.work, lb.counters);
   return cudaGetLastError();
 }
