@@ -12,6 +12,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "unicode_tables.h"
@@ -44,6 +47,122 @@ static unsigned host_threads() {
   }
   return n;
 }
+// ---- recycler of large host blocks (see engine.h) -------------------------------------------------------
+namespace {
+struct ParkedBlock {
+  void* p;
+  size_t bytes;
+};
+std::mutex g_park_m;
+ParkedBlock g_parked[2] = {{nullptr, 0}, {nullptr, 0}};
+const size_t kParkMin = 4u << 20, kParkMax = 2048ull << 20;
+}  // namespace
+void* big_block_take(size_t min_bytes, size_t* got_bytes) {
+  if (min_bytes < kParkMin) return nullptr;
+  std::lock_guard<std::mutex> lk(g_park_m);
+  for (ParkedBlock& b : g_parked) {
+    if (b.p && b.bytes >= min_bytes && b.bytes / 4 <= min_bytes) {
+      void* r = b.p;
+      *got_bytes = b.bytes;
+      b.p = nullptr;
+      b.bytes = 0;
+      return r;
+    }
+  }
+  return nullptr;
+}
+void big_block_give(void* p, size_t bytes) {
+  if (bytes >= kParkMin && bytes <= kParkMax) {
+    std::lock_guard<std::mutex> lk(g_park_m);
+    ParkedBlock* slot = nullptr;
+    for (ParkedBlock& b : g_parked)
+      if (!b.p) slot = &b;
+    if (!slot) {  // replace the smaller parked block if this one is bigger
+      slot = g_parked[0].bytes <= g_parked[1].bytes ? &g_parked[0] : &g_parked[1];
+      if (slot->bytes >= bytes) slot = nullptr;
+    }
+    if (slot) {
+      void* old = slot->p;
+      slot->p = p;
+      slot->bytes = bytes;
+      p = old;
+    }
+  }
+  free(p);
+}
+
+// Persistent worker pool for the host phases of a batch (encode, post-pass, assembly).  Three
+// parallel phases per 131072-query chunk used to mean ~48 thread creations per chunk; the pool's
+// workers sleep on a condition variable between phases instead.  One job at a time: a second caller
+// (another model / another host thread) that finds the pool busy runs its ranges on fresh threads.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* p = new HostPool();  // leaked on purpose: workers outlive static destruction
+    return *p;
+  }
+  // runs fn(part) for part in [0, parts); the caller executes part 0
+  template <class F>
+  void run(unsigned parts, F& fn) {
+    if (parts <= 1) {
+      fn(0u);
+      return;
+    }
+    std::unique_lock<std::mutex> busy(run_m_, std::try_to_lock);
+    if (!busy.owns_lock() || parts - 1 > workers_.size()) {
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < parts; ++t) th.emplace_back([&fn, t]() { fn(t); });
+      fn(0u);
+      for (auto& t : th) t.join();
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = [&fn](unsigned t) { fn(t); };
+      parts_ = parts;
+      pending_ = parts - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    fn(0u);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this]() { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    const unsigned n = host_threads();
+    for (unsigned t = 1; t < n; ++t) workers_.emplace_back([this, t]() { loop(t); });
+    for (auto& w : workers_) w.detach();
+  }
+  void loop(unsigned id) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(unsigned)> job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&]() { return gen_ != seen; });
+        seen = gen_;
+        if (id >= parts_) continue;  // not needed for this job
+        job = job_;
+      }
+      job(id);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        --pending_;
+      }
+      done_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, run_m_;
+  std::condition_variable cv_, done_;
+  std::function<void(unsigned)> job_;
+  unsigned parts_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+};
+
 // fn(thread index, lo, hi) over [0, n) split into contiguous ranges, one per thread
 template <class F>
 static unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F fn) {
@@ -54,13 +173,29 @@ static unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F fn) {
     fn(0u, (uint64_t)0, n);
     return 1;
   }
-  std::vector<std::thread> th;
   const uint64_t per = (n + nt - 1) / nt;
-  for (unsigned t = 0; t < nt; ++t) {
+  std::vector<double> took(profile_enabled() ? nt : 0, 0.0);
+  auto part = [&](unsigned t) {
     const uint64_t lo = std::min(n, (uint64_t)t * per), hi = std::min(n, lo + per);
-    th.emplace_back(fn, t, lo, hi);
+    if (took.empty()) {
+      fn(t, lo, hi);
+    } else {
+      const auto t0 = std::chrono::steady_clock::now();
+      fn(t, lo, hi);
+      took[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  HostPool::get().run(nt, part);
+  if (!took.empty()) {
+    const double all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (all > 15.0) {
+      double mx = 0;
+      for (double v : took) mx = std::max(mx, v);
+      fprintf(stderr, "[anl profile] slow parallel phase: %.2f ms wall, slowest part %.2f ms, own part %.2f ms, %u parts\n", all, mx,
+              took[0], nt);
+    }
   }
-  for (auto& t : th) t.join();
   return nt;
 }
 
@@ -373,7 +508,7 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
 void Engine::destroy_batch(DeviceBatch* b) {
   if (!b) return;
   for (void* p : {(void*)b->h_rows, (void*)b->h_head, (void*)b->h_flags, (void*)b->h_hitcnt, (void*)b->h_out,
-                  (void*)b->h_work, (void*)b->h_qboff})
+                  (void*)b->h_work, (void*)b->h_qboff, (void*)b->h_qblob})
     if (p) cudaFreeHost(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
@@ -568,7 +703,8 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       return nullptr;
     }
   }
-  // raw query bytes for the device-side confusable prefilter (only when the host post-pass follows)
+  pt.lap("create: encode");
+  // raw query bytes for the device-side confusable stage (only when a confusable post-pass follows)
   b->has_qblob = false;
   const uint64_t blob_bytes = b->offsets[n];
   if (h_ix_.conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER) && n > 0 &&
@@ -576,8 +712,10 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     std::string e2;
     bool okb = true;
     if (blob_bytes > b->cap_qblob || !b->d_qblob) {
-      okb = dev_realloc(&b->d_qblob, (size_t)blob_bytes + 16, &e2);
-      b->cap_qblob = okb ? (size_t)blob_bytes + 16 : 0;
+      // headroom: chunk sizes vary a little and cudaFree synchronises the whole device
+      const size_t want = (size_t)blob_bytes + (size_t)blob_bytes / 4 + 4096;
+      okb = dev_realloc(&b->d_qblob, want, &e2) && pinned_realloc(&b->h_qblob, want, &e2);
+      b->cap_qblob = okb ? want : 0;
     }
     if (okb && (n + 1 > b->cap_qboff || !b->d_qboff)) {
       okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2);
@@ -588,7 +726,8 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       return fail();
     }
     for (uint64_t i = 0; i <= n; ++i) b->h_qboff[i] = (uint32_t)b->offsets[i];
-    if (cudaMemcpyAsync(b->d_qblob, b->blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+    memcpy(b->h_qblob, b->blob, (size_t)blob_bytes);  // pinned staging: the caller's memory is pageable
+    if (cudaMemcpyAsync(b->d_qblob, b->h_qblob, (size_t)blob_bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
         cudaMemcpyAsync(b->d_qboff, b->h_qboff, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
       *err = "H2D copy of the query text failed";
       return fail();
@@ -596,7 +735,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     b->has_qblob = true;
   }
   b->dev_conf = b->has_qblob && b->d_conf_work != nullptr && !b->sharded;
-  pt.lap("create: encode");
+  pt.lap("create: query text");
   if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
     *err = "H2D copy failed";
     return fail();

@@ -16,6 +16,11 @@
 
 namespace anl {
 
+// Process-wide recycler of large host blocks (result arrays are hundreds of MB per million queries;
+// a fresh mmap per call costs tens of ms of page faults, a recycled block is already mapped).
+void* big_block_take(size_t min_bytes, size_t* got_bytes);  // nullptr if nothing suitable is parked
+void big_block_give(void* p, size_t bytes);                 // parks or frees
+
 // Growable array of PODs that does not value-initialise on resize (a std::vector would memset
 // hundreds of MB that are overwritten immediately, on one thread).
 template <class T>
@@ -24,7 +29,9 @@ class PodBuffer {
   PodBuffer() = default;
   PodBuffer(const PodBuffer&) = delete;
   PodBuffer& operator=(const PodBuffer&) = delete;
-  ~PodBuffer() { free(p_); }
+  ~PodBuffer() {
+    if (p_) big_block_give(p_, cap_ * sizeof(T));
+  }
   T* data() { return p_; }
   const T* data() const { return p_; }
   size_t size() const { return n_; }
@@ -32,6 +39,14 @@ class PodBuffer {
   void clear() { n_ = 0; }
   void reserve(size_t c) {
     if (c <= cap_) return;
+    if (!p_) {
+      size_t got = 0;
+      if (void* r = big_block_take(c * sizeof(T), &got)) {
+        p_ = static_cast<T*>(r);
+        cap_ = got / sizeof(T);
+        return;
+      }
+    }
     T* q = static_cast<T*>(realloc(p_, c * sizeof(T)));
     if (!q) throw std::bad_alloc();
     p_ = q;
@@ -84,6 +99,7 @@ struct DeviceBatch {
   uint8_t* d_qblob = nullptr;   // raw query bytes (confusable prefilter), grow-only
   uint32_t* d_qboff = nullptr;  // n + 1 byte offsets into d_qblob
   uint32_t* h_qboff = nullptr;  // pinned staging of the offsets
+  char* h_qblob = nullptr;      // pinned staging of the query text
   size_t cap_qblob = 0, cap_qboff = 0;
   bool has_qblob = false;
   ConfWork* d_conf_work = nullptr;  // queue of (record, query) pairs for the confusable kernel, sized like d_out
