@@ -590,6 +590,22 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 // ================================================================================================
 constexpr int K2_WARPS = 4;
 
+// Shared-memory accesses of the DP by 32-bit shared-window address.  (With generic pointers into the
+// dynamic shared array, ptxas re-derived the CTA's shared window base -- S2UR SR_CgaCtaId + ULEA --
+// inside the inner loop: 5 % of the kernel's stall samples.)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 struct __align__(8) SurvRec {
   double dist;     // distance score
   double freq;     // absolute, then normalised frequency score
@@ -846,10 +862,11 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
-  unsigned char* base = smem_raw + (size_t)warp * k2_warp_bytes(ML, R);
-  uint8_t* sq = base;
-  uint32_t* cell = reinterpret_cast<uint32_t*>(base + 256);
-  uint8_t* ring = base + 256 + (size_t)(ML + 1) * 32 * 4;
+  // per-warp shared memory by shared-window address: sq (query symbols), cell[(ML+1)][32] words, ring[R][(ML+1)][32] bytes
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * (uint32_t)k2_warp_bytes(ML, R);
+  const uint32_t sq_a = sbase;
+  const uint32_t cell_a = sbase + 256 + lane * 4;                    // + j * 128
+  const uint32_t ring_a = sbase + 256 + (ML + 1) * 32 * 4 + lane;    // + slot * rowbytes + j * 32
   const uint32_t rowbytes = (ML + 1) * 32;
 
   const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
@@ -882,7 +899,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
     const uint32_t Lq = qrow[0];
     const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
-    for (uint32_t i = lane; i < Lq; i += 32) sq[i] = qrow[2 + i];
+    for (uint32_t i = lane; i < Lq; i += 32) sts_u8(sq_a + i, qrow[2 + i]);
     __syncwarp();
     const uint32_t ke = apply_threshold(bp.max_edit, Lq);
     const uint32_t nh = hit_count[qi];
@@ -917,7 +934,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
               if (bytepos >= 2 && bytepos < Lc + 2) {
                 const uint32_t sym = (wds[b >> 2] >> ((b & 3) * 8)) & 0xFF;
                 // column j = bytepos - 1: {t, lcs = 0, lastrow = 0, D[0][j] = j}
-                cell[(bytepos - 1) * 32 + lane] = sym | ((bytepos - 1) << 24);
+                sts_u32(cell_a + (bytepos - 1) * 128, sym | ((bytepos - 1) << 24));
               }
             }
           }
@@ -937,19 +954,19 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       // "no previous occurrence" (0) fails the reach test below without a separate check.
       const uint32_t S = ke + 2;
       if (!valid) Lc = 0;
-      for (uint32_t j = Lc + 1; j <= Lcm; ++j) cell[j * 32 + lane] = 0xFFu | (j << 24);  // sentinel symbol: never equal
-      for (uint32_t j = 0; j <= Lcm; ++j) ring[j * 32 + lane] = (uint8_t)j;             // row 0 in slot 0
+      for (uint32_t j = Lc + 1; j <= Lcm; ++j) sts_u32(cell_a + j * 128, 0xFFu | (j << 24));  // sentinel symbol: never equal
+      for (uint32_t j = 0; j <= Lcm; ++j) sts_u8(ring_a + j * 32, j);                        // row 0 in slot 0
       uint32_t lcs_best = 0;
       uint32_t slot = 0;  // ring slot of row i - 1
       for (uint32_t i = 1; i <= Lq; ++i) {
-        const uint32_t sc = sq[i - 1];
+        const uint32_t sc = lds_u8(sq_a + i - 1);
         slot = slot + 1 == R ? 0 : slot + 1;
-        uint8_t* cur = ring + (size_t)slot * rowbytes;
+        const uint32_t cur_a = ring_a + slot * rowbytes;
         const uint32_t is = i + S;  // shifted row number
         uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
-        cur[lane] = (uint8_t)i;
+        sts_u8(cur_a, i);
         for (uint32_t j = 1; j <= Lcm; ++j) {
-          const uint32_t cw = cell[j * 32 + lane];
+          const uint32_t cw = lds_u32(cell_a + j * 128);
           const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF, up = cw >> 24;
           const bool same = tc == sc;
           const uint32_t js = j + S;
@@ -960,13 +977,13 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           if (reach <= ke + 1) {
             const uint32_t back = is - last + 1;  // rows between row i and row last-1
             const uint32_t ts = slot >= back ? slot - back : slot + R - back;
-            const uint32_t tv = ring[(size_t)ts * rowbytes + (db - S - 1) * 32 + lane] + reach - 1;
+            const uint32_t tv = lds_u8(ring_a + ts * rowbytes + (db - S - 1) * 32) + reach - 1;
             v = min(v, tv);
           }
-          cur[j * 32 + lane] = (uint8_t)v;
+          sts_u8(cur_a + j * 32, v);
           const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
           lcs_best = max(lcs_best, lcs_new);
-          cell[j * 32 + lane] = tc | (lcs_new << 8) | ((same ? is : last) << 16) | (v << 24);
+          sts_u32(cell_a + j * 128, tc | (lcs_new << 8) | ((same ? is : last) << 16) | (v << 24));
           if (same) db = js;
           lcs_diag = lcs_up;
           diag = up;
@@ -974,7 +991,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         }
       }
       uint32_t ld = 255;
-      if (valid) ld = ring[(size_t)slot * rowbytes + Lc * 32 + lane];
+      if (valid) ld = lds_u8(ring_a + slot * rowbytes + Lc * 32);
       valid = valid && ld <= ke;
 
       // ---- prefix / suffix (src/distance.rs:208-231) ------------------------------------------------
@@ -984,11 +1001,11 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         bool pgo = valid, sgo = valid;
         for (uint32_t i = 0; i < lim; ++i) {
           if (valid && i < Lc) {
-            const uint32_t a = cell[(i + 1) * 32 + lane] & 0xFF;
-            pgo = pgo && (a == sq[i]);
+            const uint32_t a = lds_u32(cell_a + (i + 1) * 128) & 0xFF;
+            pgo = pgo && (a == lds_u8(sq_a + i));
             pre += pgo;
-            const uint32_t b = cell[(Lc - i) * 32 + lane] & 0xFF;
-            sgo = sgo && (b == sq[Lq - 1 - i]);
+            const uint32_t b = lds_u32(cell_a + (Lc - i) * 128) & 0xFF;
+            sgo = sgo && (b == lds_u8(sq_a + Lq - 1 - i));
             suf += sgo;
           }
         }
