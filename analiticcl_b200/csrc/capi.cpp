@@ -9,6 +9,7 @@
 #include "editscript_fixed.h"
 #include "engine.h"
 #include "host_model.h"
+#include "hostpool.h"
 #include "search.h"
 
 using namespace anl;
@@ -22,7 +23,7 @@ struct anl_result_set {
   ResultSet rs;
 };
 struct anl_match_set {
-  std::vector<anl_match> matches;
+  PodBuffer<anl_match> matches;
   PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
 };
 struct anl_device_batch {
@@ -298,107 +299,146 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   if (!m || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built || !m->engine.uploaded())
     return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_all_matches()");
+  // The batch producer (src/lib.rs:1790-1957) as host phases that each run on all cores, around at most
+  // two GPU batches per window of text: all unigrams, then every higher-order segment that the unigram
+  // results do not make redundant (redundant_match only reads unigram results, src/search.rs:317-336).
+  PhaseTimer pt;
   const std::string t(text ? text : "", len);
   anl_match_set* ms = new anl_match_set();
-  const std::vector<SpanBatch> batches = segment_text(t, params->max_ngram);
+  const SegmentedText st = segment_text(t, params->max_ngram);
+  pt.lap("search: segmentation");
   std::vector<uint64_t> cpmap;
   if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
-  struct Seg {
-    SegmentSpan span;
-    uint32_t batch;
-    bool looked_up;
-    uint64_t off, cnt;  // into the window's result set (pass 1 or pass 2)
-    uint8_t pass;
-  };
+  const size_t nseg = st.segs.size(), nbatch = st.batch_first.size() - 1;
+  // per segment: was it looked up, in which pass, where its variants are in that pass's result set
+  // (uninitialised, recycled buffers: each window fills its own part in parallel)
+  PodBuffer<uint8_t> looked;
+  PodBuffer<uint32_t> cnt;
+  PodBuffer<uint64_t> off, dst;  // dst: first variant of each segment in ms->variants
+  looked.resize(nseg + 1);
+  cnt.resize(nseg + 1);
+  off.resize(nseg + 1);
+  dst.resize(nseg + 1);
+  ms->matches.resize(nseg);
   std::string err;
   int status = ANL_OK;
-  size_t WINDOW = 1u << 18;  // unigram segments per window
+  size_t WINDOW = 1u << 20;  // unigram segments per window
   if (const char* e = getenv("ANL_SEARCH_WINDOW")) WINDOW = (size_t)std::max(1, atoi(e));
-  std::vector<Seg> segs;
-  std::vector<size_t> pick;
+  std::vector<uint64_t> pick;
   std::string blob;
   std::vector<uint64_t> offs;
   ResultSet rs[2];
   auto lookup = [&](int pass) -> bool {
-    blob.clear();
-    offs.assign(1, 0);
-    for (size_t k : pick) {
-      blob.append(t, segs[k].span.begin, segs[k].span.end - segs[k].span.begin);
-      offs.push_back(blob.size());
-    }
+    const size_t np = pick.size();
+    offs.resize(np + 1);
+    offs[0] = 0;
+    for (size_t i = 0; i < np; ++i) offs[i + 1] = offs[i] + (st.segs[pick[i]].end - st.segs[pick[i]].begin);
+    blob.resize(offs[np]);
+    parallel_ranges(np, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) memcpy(&blob[offs[i]], t.data() + st.segs[pick[i]].begin, offs[i + 1] - offs[i]);
+    });
     rs[pass].offsets.assign(1, 0);
     rs[pass].variants.clear();
-    if (pick.empty()) return true;
-    if (!m->engine.find_variants_batch(blob.data(), offs.data(), pick.size(), *params, &rs[pass], &err, &status)) return false;
-    for (size_t i = 0; i < pick.size(); ++i) {
-      Seg& s = segs[pick[i]];
-      s.looked_up = true;
-      s.pass = (uint8_t)pass;
-      s.off = rs[pass].offsets[i];
-      s.cnt = rs[pass].offsets[i + 1] - rs[pass].offsets[i];
-    }
+    if (np == 0) return true;
+    if (!m->engine.find_variants_batch(blob.data(), offs.data(), np, *params, &rs[pass], &err, &status)) return false;
+    parallel_ranges(np, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t k = pick[i];
+        looked[k] = (uint8_t)(1 + pass);
+        off[k] = rs[pass].offsets[i];
+        cnt[k] = (uint32_t)(rs[pass].offsets[i + 1] - rs[pass].offsets[i]);
+      }
+    });
     return true;
   };
   bool ok = true;
-  size_t bi = 0;
-  while (ok && bi < batches.size()) {
-    // gather whole batches until the window holds enough unigrams
-    segs.clear();
-    size_t unigrams = 0;
-    while (bi < batches.size() && (unigrams < WINDOW || segs.empty())) {
-      for (const SegmentSpan& sp : batches[bi].segments) {
-        segs.push_back(Seg{sp, (uint32_t)bi, false, 0, 0, 0});
-        unigrams += sp.n == 1;
-      }
-      ++bi;
+  size_t b0 = 0;
+  uint64_t vtotal = 0;
+  const unsigned nt_max = host_threads();
+  while (ok && b0 < nbatch) {
+    // a window: whole batches until it holds enough unigrams
+    size_t b1 = b0, unigrams = 0;
+    while (b1 < nbatch && (unigrams < WINDOW || b1 == b0)) {
+      for (uint64_t k = st.batch_first[b1]; k < st.batch_first[b1 + 1] && st.segs[k].n == 1; ++k) ++unigrams;
+      ++b1;
     }
+    const uint64_t s0 = st.batch_first[b0], s1 = st.batch_first[b1];
+    parallel_ranges(s1 - s0, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t k = s0 + lo; k < s0 + hi; ++k) {
+        looked[k] = 0;
+        cnt[k] = 0;
+        off[k] = 0;
+      }
+    });
     pick.clear();
-    for (size_t k = 0; k < segs.size(); ++k)
-      if (segs[k].span.n == 1) pick.push_back(k);
+    for (uint64_t k = s0; k < s1; ++k)
+      if (st.segs[k].n == 1) pick.push_back(k);
     ok = lookup(0);
+    pt.lap("search: unigram lookups");
     if (ok && params->max_ngram > 1) {
-      pick.clear();
-      size_t batch_start = 0;
-      for (size_t k = 0; k < segs.size(); ++k) {
-        if (k > 0 && segs[k].batch != segs[k - 1].batch) batch_start = k;
-        if (segs[k].span.n == 1) continue;
-        bool redundant = true;
-        for (size_t u = batch_start; u < segs.size() && segs[u].batch == segs[k].batch && segs[u].span.n == 1; ++u) {
-          if (segs[u].span.begin >= segs[k].span.begin && segs[u].span.end <= segs[k].span.end) {
-            if (segs[u].cnt == 0 || rs[0].variants[segs[u].off].dist_score < 1.0) {
-              redundant = false;
-              break;
+      // redundant_match (src/search.rs:317-336), batch by batch; per-thread pick lists keep the segment order
+      std::vector<std::vector<uint64_t>> part(nt_max);
+      const unsigned used = parallel_ranges(b1 - b0, 64, [&](unsigned tid, uint64_t lo, uint64_t hi) {
+        std::vector<uint64_t>& mine = part[tid];
+        for (uint64_t bb = b0 + lo; bb < b0 + hi; ++bb) {
+          const uint64_t f = st.batch_first[bb], l = st.batch_first[bb + 1];
+          for (uint64_t k = f; k < l; ++k) {
+            const SegmentSpan& sp = st.segs[k];
+            if (sp.n == 1) continue;
+            bool redundant = true;
+            for (uint64_t u = f; u < l && st.segs[u].n == 1; ++u) {
+              if (st.segs[u].begin >= sp.begin && st.segs[u].end <= sp.end) {
+                if (cnt[u] == 0 || rs[0].variants[off[u]].dist_score < 1.0) {
+                  redundant = false;
+                  break;
+                }
+              }
             }
+            if (!redundant) mine.push_back(k);
           }
         }
-        if (!redundant) pick.push_back(k);
-      }
+      });
+      pick.clear();
+      for (unsigned tid = 0; tid < used; ++tid) pick.insert(pick.end(), part[tid].begin(), part[tid].end());
+      pt.lap("search: redundancy pruning");
       ok = lookup(1);
+      pt.lap("search: n-gram lookups");
     }
     if (!ok) break;
-    for (const Seg& s : segs) {
-      anl_match mm;
-      mm.begin = params->unicodeoffsets ? cpmap[s.span.begin] : s.span.begin;
-      mm.end = params->unicodeoffsets ? cpmap[s.span.end] : s.span.end;
-      mm.n = s.span.n;
-      mm.n_variants = s.cnt;
-      mm.selected = (s.looked_up && s.cnt > 0) ? 0 : -1;
-      // variants pointer: index into the shared buffer for now, fixed up below (the buffer may move)
-      const uint64_t at = ms->variants.size();
-      mm.variants = s.looked_up ? reinterpret_cast<const anl_variant*>(at + 1) : nullptr;
-      if (s.cnt) {
-        ms->variants.resize(at + s.cnt);
-        memcpy(ms->variants.data() + at, rs[s.pass].variants.data() + s.off, s.cnt * sizeof(anl_variant));
+    // this window's matches: variant lists copied behind those of the earlier windows
+    dst[s0] = vtotal;
+    for (uint64_t k = s0; k < s1; ++k) dst[k + 1] = dst[k] + cnt[k];
+    vtotal = dst[s1];
+    ms->variants.resize(vtotal);
+    anl_variant* vbase = ms->variants.data();
+    parallel_ranges(s1 - s0, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t k = s0 + lo; k < s0 + hi; ++k) {
+        const SegmentSpan& sp = st.segs[k];
+        anl_match& mm = ms->matches[k];
+        mm.begin = params->unicodeoffsets ? cpmap[sp.begin] : sp.begin;
+        mm.end = params->unicodeoffsets ? cpmap[sp.end] : sp.end;
+        mm.n = sp.n;
+        mm.n_variants = cnt[k];
+        mm.selected = (looked[k] && cnt[k] > 0) ? 0 : -1;
+        // index + 1 for now, turned into a pointer below (the buffer may still move)
+        mm.variants = looked[k] ? reinterpret_cast<const anl_variant*>(dst[k] + 1) : nullptr;
+        if (cnt[k]) memcpy(vbase + dst[k], rs[looked[k] - 1].variants.data() + off[k], (size_t)cnt[k] * sizeof(anl_variant));
       }
-      ms->matches.push_back(mm);
-    }
+    });
+    pt.lap("search: assemble matches");
+    b0 = b1;
   }
   if (!ok) {
     delete ms;
     return fail(status ? status : ANL_ERR_CUDA, err);
   }
-  for (anl_match& mm : ms->matches)
-    if (mm.variants) mm.variants = ms->variants.data() + (reinterpret_cast<uintptr_t>(mm.variants) - 1);
+  const anl_variant* vbase = ms->variants.data();
+  parallel_ranges(nseg, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+    for (uint64_t k = lo; k < hi; ++k) {
+      anl_match& mm = ms->matches[k];
+      if (mm.variants) mm.variants = vbase + (reinterpret_cast<uintptr_t>(mm.variants) - 1);
+    }
+  });
   *out = ms;
   return ANL_OK;
 }

@@ -505,6 +505,10 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   while (slots < groups * 2) slots <<= 1;
   uint64_t words = 1;
   while (words * 2 < groups) words <<= 1;  // 1..2 keys per 64-bit word, 3 bits each: false positives < 0.1 %
+  // A filter that outgrows the 126 MB L2 turns every probe into a DRAM sector read.  Large indexes trade
+  // false positives (a wasted exact lookup each) for residency: up to ~8 keys per word (false positives
+  // ~2-3 %) while the filter is larger than 128 MB.
+  while (words * 8 > (128ull << 20) && words * 8 >= groups) words >>= 1;
   ix.table.assign(slots, Slot{0, 0, 0, 0});
   ix.bloom.assign(words, 0);
   ix.post_ana.resize(posts.size());

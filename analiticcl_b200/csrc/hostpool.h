@@ -1,0 +1,150 @@
+// hostpool.h -- host-side helpers shared by the batch engine and the find_all_matches producer:
+// profiling switches, a persistent worker pool, parallel_ranges.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace anl {
+
+inline bool profile_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("ANL_PROFILE") ? 1 : 0;
+  return v == 1;
+}
+struct PhaseTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!profile_enabled()) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[anl profile] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+inline unsigned host_threads() {
+  static unsigned n = 0;
+  if (n == 0) {
+    n = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* e = getenv("ANL_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    n = std::min(n, 64u);
+  }
+  return n;
+}
+
+// Persistent worker pool for the host phases of a batch (encode, post-pass, assembly).  Three
+// parallel phases per 131072-query chunk used to mean ~48 thread creations per chunk; the pool's
+// workers sleep on a condition variable between phases instead.  One job at a time: a second caller
+// (another model / another host thread) that finds the pool busy runs its ranges on fresh threads.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* p = new HostPool();  // leaked on purpose: workers outlive static destruction
+    return *p;
+  }
+  // runs fn(part) for part in [0, parts); the caller executes part 0
+  template <class F>
+  void run(unsigned parts, F& fn) {
+    if (parts <= 1) {
+      fn(0u);
+      return;
+    }
+    std::unique_lock<std::mutex> busy(run_m_, std::try_to_lock);
+    if (!busy.owns_lock() || parts - 1 > workers_.size()) {
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < parts; ++t) th.emplace_back([&fn, t]() { fn(t); });
+      fn(0u);
+      for (auto& t : th) t.join();
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = [&fn](unsigned t) { fn(t); };
+      parts_ = parts;
+      pending_ = parts - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    fn(0u);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this]() { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    const unsigned n = host_threads();
+    for (unsigned t = 1; t < n; ++t) workers_.emplace_back([this, t]() { loop(t); });
+    for (auto& w : workers_) w.detach();
+  }
+  void loop(unsigned id) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(unsigned)> job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&]() { return gen_ != seen; });
+        seen = gen_;
+        if (id >= parts_) continue;  // not needed for this job
+        job = job_;
+      }
+      job(id);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        --pending_;
+      }
+      done_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, run_m_;
+  std::condition_variable cv_, done_;
+  std::function<void(unsigned)> job_;
+  unsigned parts_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+};
+
+// fn(thread index, lo, hi) over [0, n) split into contiguous ranges, one per thread
+template <class F>
+inline unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F fn) {
+  unsigned nt = host_threads();
+  const uint64_t mp = std::max<uint64_t>(1, min_per_thread);
+  if (n / mp < nt) nt = (unsigned)std::max<uint64_t>(1, n / mp);
+  if (nt <= 1) {
+    fn(0u, (uint64_t)0, n);
+    return 1;
+  }
+  const uint64_t per = (n + nt - 1) / nt;
+  std::vector<double> took(profile_enabled() ? nt : 0, 0.0);
+  auto part = [&](unsigned t) {
+    const uint64_t lo = std::min(n, (uint64_t)t * per), hi = std::min(n, lo + per);
+    if (took.empty()) {
+      fn(t, lo, hi);
+    } else {
+      const auto t0 = std::chrono::steady_clock::now();
+      fn(t, lo, hi);
+      took[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  HostPool::get().run(nt, part);
+  if (!took.empty()) {
+    const double all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (all > 15.0) {
+      double mx = 0;
+      for (double v : took) mx = std::max(mx, v);
+      fprintf(stderr, "[anl profile] slow parallel phase: %.2f ms wall, slowest part %.2f ms, own part %.2f ms, %u parts\n", all, mx,
+              took[0], nt);
+    }
+  }
+  return nt;
+}
+
+
+}  // namespace anl

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 
+#include "hostpool.h"
 #include "unicode_tables.h"
 
 namespace anl {
@@ -25,27 +26,48 @@ static inline uint32_t decode_at(const std::string& s, size_t i, unsigned* len) 
 }
 
 // src/search.rs:190-235: a boundary is a maximal run of non-alphabetic characters; the text always
-// ends with a boundary (possibly of length zero).
+// ends with a boundary (possibly of length zero).  The scan runs in parallel over byte ranges; a run
+// that crosses a range border is stitched back together afterwards.
 std::vector<Boundary> find_boundaries(const std::string& text) {
-  std::vector<Boundary> out;
-  bool open = false;
-  size_t start = 0;
-  for (size_t i = 0; i < text.size();) {
-    unsigned l;
-    const bool alpha = anl_unicode::is_alphabetic(decode_at(text, i, &l));
-    if (open && alpha) {
-      out.push_back(Boundary{start, i, BOUNDARY_NONE});
-      open = false;
-    } else if (!open && !alpha) {
-      start = i;
-      open = true;
+  const size_t n = text.size();
+  const unsigned nt_max = host_threads();
+  std::vector<std::vector<Boundary>> part(nt_max);
+  std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+  const unsigned used = parallel_ranges(n, 1u << 16, [&](unsigned t, uint64_t lo, uint64_t hi) {
+    // move both ends to the start of a character (skip UTF-8 continuation bytes)
+    while (lo < n && lo > 0 && ((unsigned char)text[lo] & 0xC0) == 0x80) ++lo;
+    while (hi < n && ((unsigned char)text[hi] & 0xC0) == 0x80) ++hi;
+    range[t] = {lo, hi};
+    std::vector<Boundary>& out = part[t];
+    out.reserve((size_t)(hi - lo) / 5 + 16);
+    bool open = false;
+    size_t start = 0;
+    for (size_t i = lo; i < hi;) {
+      unsigned l;
+      const bool alpha = anl_unicode::is_alphabetic(decode_at(text, i, &l));
+      if (open && alpha) {
+        out.push_back(Boundary{start, i, BOUNDARY_NONE});
+        open = false;
+      } else if (!open && !alpha) {
+        start = i;
+        open = true;
+      }
+      i += l;
     }
-    i += l;
-  }
-  if (open)
-    out.push_back(Boundary{start, text.size(), BOUNDARY_NONE});
-  else
-    out.push_back(Boundary{text.size(), text.size(), BOUNDARY_NONE});
+    if (open) out.push_back(Boundary{start, (size_t)hi, BOUNDARY_NONE});  // may continue in the next range
+  });
+  std::vector<Boundary> out;
+  size_t total = 1;
+  for (unsigned t = 0; t < used; ++t) total += part[t].size();
+  out.reserve(total);
+  for (unsigned t = 0; t < used; ++t)
+    for (const Boundary& b : part[t]) {
+      if (!out.empty() && out.back().end == b.begin)
+        out.back().end = b.end;  // the same run, cut by a range border
+      else
+        out.push_back(b);
+    }
+  if (out.empty() || out.back().end != n) out.push_back(Boundary{n, n, BOUNDARY_NONE});
   // src/search.rs:238-258: last or multi-byte boundary = hard; ' - _ = weak; else normal
   for (size_t i = 0; i < out.size(); ++i) {
     const size_t len = out[i].end - out[i].begin;
@@ -60,14 +82,13 @@ std::vector<Boundary> find_boundaries(const std::string& text) {
 }
 
 // src/search.rs:262-312
-std::vector<SegmentSpan> find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order,
-                                           size_t begin, size_t end) {
-  std::vector<SegmentSpan> out;
+void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order, size_t begin, size_t end,
+                       std::vector<SegmentSpan>* out) {
   auto usable = [&](size_t b, size_t e) { return e > b && !(e - b == 1 && text[b] == ' '); };
   for (size_t i = 0; i + order - 1 < nbounds; ++i) {
     const Boundary& right = bounds[i + order - 1];
     if (right.begin > end) break;
-    if (usable(begin, right.begin)) out.push_back(SegmentSpan{begin, right.begin, order});
+    if (usable(begin, right.begin)) out->push_back(SegmentSpan{begin, right.begin, order});
     begin = bounds[i].end;
   }
   if (begin < end && usable(begin, end)) {
@@ -84,29 +105,55 @@ std::vector<SegmentSpan> find_match_ngrams(const std::string& text, const Bounda
       }
     }
     const size_t inner = (first < 0 || (size_t)first >= last_plus1) ? 0 : last_plus1 - (size_t)first;
-    if (inner == order) out.push_back(SegmentSpan{begin, end, order});
+    if (inner == order) out->push_back(SegmentSpan{begin, end, order});
   }
-  return out;
 }
 
-std::vector<SpanBatch> segment_text(const std::string& text, uint32_t max_ngram) {
-  std::vector<SpanBatch> batches;
-  if (text.empty()) return batches;
+SegmentedText segment_text(const std::string& text, uint32_t max_ngram) {
+  SegmentedText st;
+  st.batch_first.push_back(0);
+  if (text.empty()) return st;
   const std::vector<Boundary> bounds = find_boundaries(text);
-  size_t begin = 0, begin_index = 0;
-  for (size_t i = 0; i < bounds.size(); ++i) {
-    if (bounds[i].strength != BOUNDARY_HARD || bounds[i].begin == begin) continue;  // src/lib.rs:1822
-    SpanBatch sb;
-    for (uint32_t order = 1; order <= max_ngram; ++order) {
-      std::vector<SegmentSpan> cur =
-          find_match_ngrams(text, bounds.data() + begin_index, i + 1 - begin_index, order, begin, bounds[i].begin);
-      sb.segments.insert(sb.segments.end(), cur.begin(), cur.end());
+  // the batches: spans between hard boundaries (src/lib.rs:1822)
+  struct Desc {
+    size_t begin, begin_index, end_index;
+  };
+  std::vector<Desc> descs;
+  {
+    size_t begin = 0, begin_index = 0;
+    for (size_t i = 0; i < bounds.size(); ++i) {
+      if (bounds[i].strength != BOUNDARY_HARD || bounds[i].begin == begin) continue;
+      descs.push_back(Desc{begin, begin_index, i});
+      begin = bounds[i].end;
+      begin_index = i + 1;
     }
-    batches.push_back(std::move(sb));
-    begin = bounds[i].end;
-    begin_index = i + 1;
   }
-  return batches;
+  const size_t nb = descs.size();
+  const unsigned nt_max = host_threads();
+  std::vector<std::vector<SegmentSpan>> part(nt_max);
+  std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+  std::vector<uint64_t> count(nb + 1, 0);  // segments per batch, then exclusive prefix
+  const unsigned used = parallel_ranges(nb, 256, [&](unsigned t, uint64_t lo, uint64_t hi) {
+    range[t] = {lo, hi};
+    std::vector<SegmentSpan>& out = part[t];
+    if (hi > lo) out.reserve((descs[hi - 1].end_index - descs[lo].begin_index + 1) * (size_t)max_ngram + 16);
+    for (uint64_t k = lo; k < hi; ++k) {
+      const Desc& d = descs[k];
+      const size_t before = out.size();
+      for (uint32_t order = 1; order <= max_ngram; ++order)
+        find_match_ngrams(text, bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, order, d.begin,
+                          bounds[d.end_index].begin, &out);
+      count[k] = out.size() - before;
+    }
+  });
+  st.batch_first.assign(nb + 1, 0);
+  for (size_t k = 0; k < nb; ++k) st.batch_first[k + 1] = st.batch_first[k] + count[k];
+  st.segs.resize(st.batch_first[nb]);
+  parallel_ranges(used, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+    for (uint64_t t = lo; t < hi; ++t)
+      if (!part[t].empty()) std::copy(part[t].begin(), part[t].end(), st.segs.begin() + st.batch_first[range[t].first]);
+  });
+  return st;
 }
 
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text) {

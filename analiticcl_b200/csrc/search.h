@@ -17,14 +17,17 @@ struct SegmentSpan {
   size_t begin, end;  // byte offsets into the text
   uint32_t n;         // n-gram order
 };
-struct SpanBatch {  // the segments between two hard boundaries, orders 1..max_ngram (src/lib.rs:1840-1903)
-  std::vector<SegmentSpan> segments;
+// All segments of a text: batch by batch (a batch = the segments between two hard boundaries,
+// src/lib.rs:1840-1903), orders 1..max_ngram ascending inside a batch -- so a batch's unigrams come first.
+struct SegmentedText {
+  std::vector<SegmentSpan> segs;
+  std::vector<uint64_t> batch_first;  // index of each batch's first segment; n_batches + 1 entries
 };
 
 std::vector<Boundary> find_boundaries(const std::string& text);
-std::vector<SegmentSpan> find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order,
-                                           size_t begin, size_t end);
-std::vector<SpanBatch> segment_text(const std::string& text, uint32_t max_ngram);
+void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order, size_t begin, size_t end,
+                       std::vector<SegmentSpan>* out);
+SegmentedText segment_text(const std::string& text, uint32_t max_ngram);
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text);
 
 }  // namespace anl

@@ -1,16 +1,18 @@
 #!/bin/bash
 # ncu evidence for the round (run under gpurun on one B200):
 #   1. launch list with per-launch device time (cold-cache, serialised -> compare SHARES)
-#   2. one full capture of each of the two kernels
+#   2. one full capture of each of the two main kernels, at the bench's own launch size
 # Outputs land in gpurun_out/ ; summaries are copied into profiles/ by tools/summarize_ncu.py.
 set -x
 mkdir -p gpurun_out
-Q=${Q:-262144}
+Q=${Q:-1000000}
+W=${W:-cfg2}
+echo "$W $Q" > gpurun_out/profile_launch.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --queries $Q --steps 2 --warmup 3 --e2e-steps 1 --cpu-sample 64 > gpurun_out/launches_bench.json 2> gpurun_out/launches.err
+    python bench.py --workload $W --queries $Q --steps 2 --warmup 3 --e2e-steps 0 --cpu-sample 64 > gpurun_out/launches_bench.json 2> gpurun_out/launches.err
 ncu --set full --clock-control none --import-source on -k regex:probe_kernel -s 3 -c 1 -f -o gpurun_out/prof_probe \
-    python bench.py --queries $Q --steps 1 --warmup 3 --e2e-steps 1 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_probe.err
+    python bench.py --workload $W --queries $Q --steps 1 --warmup 3 --e2e-steps 0 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_probe.err
 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 3 -c 1 -f -o gpurun_out/prof_score \
-    python bench.py --queries $Q --steps 1 --warmup 3 --e2e-steps 1 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_score.err
+    python bench.py --workload $W --queries $Q --steps 1 --warmup 3 --e2e-steps 0 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_score.err
 ls -la gpurun_out
-tail -3 gpurun_out/*.err
+tail -n 3 gpurun_out/launches.err gpurun_out/prof_probe.err gpurun_out/prof_score.err

@@ -46,6 +46,13 @@ def hot_lines(rep, top=18):
 
 
 os.makedirs(PROF, exist_ok=True)
+traffic = {}
+launch_info = ("cfg2", 0)
+try:
+    w_, q_ = open(os.path.join(OUT, "profile_launch.txt")).read().split()
+    launch_info = (w_, int(q_))
+except (OSError, ValueError):
+    pass
 md = [f"# ncu summary {tag}", "",
       "Source: `tools/profile.sh` under gpurun (1x B200, `--clock-control none`). Full `.ncu-rep` files stay in",
       "`gpurun_out/` (scratch); this file holds what the numbers in DESIGN.md / bench.py are read from.", ""]
@@ -54,7 +61,15 @@ for name in ("probe", "score"):
     if not os.path.exists(rep):
         continue
     m = raw_metrics(rep)
-    md.append(f"## {name}_kernel (`ncu --set full`, one launch)")
+    try:
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
+        traffic[f"{name}_kernel"] = {"dram_bytes": float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]],
+                                     "workload": launch_info[0], "queries": launch_info[1],
+                                     "source": f"profiles/{tag}_ncu_summary.md (ncu --set full, one launch)"}
+    except (KeyError, ValueError):
+        pass
+    md.append(f"## {name}_kernel (`ncu --set full`, one launch of {launch_info[1]} {launch_info[0]} queries)")
     md.append("")
     md.append("| metric | value | unit |")
     md.append("|---|---|---|")
@@ -89,4 +104,7 @@ if os.path.exists(launch):
         md.append(f"| {k} | {len(v)} | {med[k]:.0f} | {med[k] / s:.3f} |")
     md.append("")
 open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w").write("\n".join(md))
+if traffic and launch_info[1]:
+    import json
+    json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
 print("wrote", os.path.join(PROF, f"{tag}_ncu_summary.md"))
