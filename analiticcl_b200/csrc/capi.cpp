@@ -23,6 +23,7 @@ struct anl_result_set {
   ResultSet rs;
 };
 struct anl_match_set {
+  uint64_t logical_lookups = 0, distinct_lookups = 0;
   PodBuffer<anl_match> matches;
   PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
 };
@@ -305,7 +306,8 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   PhaseTimer pt;
   const std::string t(text ? text : "", len);
   anl_match_set* ms = new anl_match_set();
-  const SegmentedText st = segment_text(t, params->max_ngram);
+  SegmentedText st;
+  segment_text(t, params->max_ngram, &st);
   pt.lap("search: segmentation");
   std::vector<uint64_t> cpmap;
   if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
@@ -328,25 +330,122 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   std::string blob;
   std::vector<uint64_t> offs;
   ResultSet rs[2];
+  // Running text repeats itself: a window's segments are de-duplicated first (the lookup is a pure function
+  // of the segment's text) and only the distinct strings go to the GPU; every occurrence then points at its
+  // representative's variant list.  Exact: hash + byte comparison, the first occurrence is the representative.
+  PodBuffer<uint64_t> hashes;
+  PodBuffer<uint32_t> rep;      // per picked segment: position (in pick) of its first occurrence
+  PodBuffer<uint32_t> uniq_of;  // per picked segment: rank of its representative among the distinct strings
+  std::vector<uint64_t> uniq;   // positions (in pick) of the distinct strings, ascending
+  uint64_t distinct_lookups = 0, logical_lookups = 0;
+  auto seg_text = [&](uint64_t k, size_t* n) {
+    *n = st.segs[k].end - st.segs[k].begin;
+    return t.data() + st.segs[k].begin;
+  };
+  auto dedupe = [&]() {
+    const size_t np = pick.size();
+    hashes.resize(np);
+    rep.resize(np);
+    uniq_of.resize(np);
+    parallel_ranges(np, 8192, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        size_t n;
+        const char* p = seg_text(pick[i], &n);
+        uint64_t h = 0x9E3779B97F4A7C15ULL ^ (n * 0xD6E8FEB86659FD93ULL);
+        while (n >= 8) {
+          uint64_t w;
+          memcpy(&w, p, 8);
+          h = (h ^ w) * 0xFF51AFD7ED558CCDULL;
+          h ^= h >> 32;
+          p += 8;
+          n -= 8;
+        }
+        uint64_t w = 0;
+        memcpy(&w, p, n);
+        h = (h ^ w) * 0xC4CEB9FE1A85EC53ULL;
+        h ^= h >> 29;
+        hashes[i] = h;
+      }
+    });
+    // hash-partitioned insertion: thread p owns the strings whose hash falls into its partition, so the
+    // tables need no locks and "first occurrence" is the smallest position in every partition
+    const unsigned parts = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(host_threads(), np / 4096));
+    parallel_ranges(parts, 1, [&](unsigned, uint64_t plo, uint64_t phi) {
+      for (uint64_t part = plo; part < phi; ++part) {
+        size_t cap = 1024;
+        while (cap < 2 * (np / parts + 1) + 1024) cap <<= 1;
+        static thread_local std::vector<uint32_t> table;  // position + 1, 0 = empty
+        table.assign(cap, 0);
+        for (uint64_t i = 0; i < np; ++i) {
+          const uint64_t h = hashes[i];
+          if ((h >> 40) % parts != part) continue;
+          size_t slot = (size_t)h & (cap - 1);
+          size_t n;
+          const char* p = seg_text(pick[i], &n);
+          for (;;) {
+            const uint32_t e = table[slot];
+            if (e == 0) {
+              table[slot] = (uint32_t)i + 1;
+              rep[i] = (uint32_t)i;
+              break;
+            }
+            const uint64_t j = e - 1;
+            if (hashes[j] == h) {
+              size_t m;
+              const char* q = seg_text(pick[j], &m);
+              if (m == n && memcmp(p, q, n) == 0) {
+                rep[i] = (uint32_t)j;
+                break;
+              }
+            }
+            slot = (slot + 1) & (cap - 1);
+          }
+        }
+      }
+    });
+    uniq.clear();
+    for (uint64_t i = 0; i < np; ++i)
+      if (rep[i] == i) {
+        uniq_of[i] = (uint32_t)uniq.size();
+        uniq.push_back(i);
+      }
+    parallel_ranges(np, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i)
+        if (rep[i] != i) uniq_of[i] = uniq_of[rep[i]];
+    });
+  };
   auto lookup = [&](int pass) -> bool {
     const size_t np = pick.size();
-    offs.resize(np + 1);
-    offs[0] = 0;
-    for (size_t i = 0; i < np; ++i) offs[i + 1] = offs[i] + (st.segs[pick[i]].end - st.segs[pick[i]].begin);
-    blob.resize(offs[np]);
-    parallel_ranges(np, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; ++i) memcpy(&blob[offs[i]], t.data() + st.segs[pick[i]].begin, offs[i + 1] - offs[i]);
-    });
     rs[pass].offsets.assign(1, 0);
     rs[pass].variants.clear();
     if (np == 0) return true;
-    if (!m->engine.find_variants_batch(blob.data(), offs.data(), np, *params, &rs[pass], &err, &status)) return false;
+    if (np > 0xFFFFFFF0ull) {
+      err = "window too large";
+      status = ANL_ERR_UNSUPPORTED;
+      return false;
+    }
+    dedupe();
+    const size_t nu = uniq.size();
+    logical_lookups += np;
+    distinct_lookups += nu;
+    offs.resize(nu + 1);
+    offs[0] = 0;
+    for (size_t i = 0; i < nu; ++i) {
+      const SegmentSpan& sp = st.segs[pick[uniq[i]]];
+      offs[i + 1] = offs[i] + (sp.end - sp.begin);
+    }
+    blob.resize(offs[nu]);
+    parallel_ranges(nu, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) memcpy(&blob[offs[i]], t.data() + st.segs[pick[uniq[i]]].begin, offs[i + 1] - offs[i]);
+    });
+    if (!m->engine.find_variants_batch(blob.data(), offs.data(), nu, *params, &rs[pass], &err, &status)) return false;
     parallel_ranges(np, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; ++i) {
         const uint64_t k = pick[i];
+        const uint64_t u = uniq_of[i];
         looked[k] = (uint8_t)(1 + pass);
-        off[k] = rs[pass].offsets[i];
-        cnt[k] = (uint32_t)(rs[pass].offsets[i + 1] - rs[pass].offsets[i]);
+        off[k] = rs[pass].offsets[u];
+        cnt[k] = (uint32_t)(rs[pass].offsets[u + 1] - rs[pass].offsets[u]);
       }
     });
     return true;
@@ -439,6 +538,11 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
       if (mm.variants) mm.variants = vbase + (reinterpret_cast<uintptr_t>(mm.variants) - 1);
     }
   });
+  if (profile_enabled())
+    fprintf(stderr, "[anl profile] search: %llu segment lookups, %llu distinct strings sent to the GPU\n",
+            (unsigned long long)logical_lookups, (unsigned long long)distinct_lookups);
+  ms->logical_lookups = logical_lookups;
+  ms->distinct_lookups = distinct_lookups;
   *out = ms;
   return ANL_OK;
 }
@@ -449,6 +553,10 @@ anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out
   return ANL_OK;
 }
 void anl_match_set_free(anl_match_set* ms) { delete ms; }
+void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_lookups, uint64_t* distinct_strings) {
+  if (segment_lookups) *segment_lookups = ms ? ms->logical_lookups : 0;
+  if (distinct_strings) *distinct_strings = ms ? ms->distinct_lookups : 0;
+}
 
 // ---- device-resident path ---------------------------------------------------------------------------------
 anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,

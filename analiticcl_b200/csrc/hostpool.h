@@ -1,6 +1,8 @@
 // hostpool.h -- host-side helpers shared by the batch engine and the find_all_matches producer:
 // profiling switches, a persistent worker pool, parallel_ranges.
 #pragma once
+#include <stddef.h>
+
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -8,10 +10,62 @@
 #include <cstdlib>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
 namespace anl {
+
+// Process-wide recycler of large host blocks (result arrays are hundreds of MB per million queries;
+// a fresh mmap per call costs tens of ms of page faults, a recycled block is already mapped).
+void* big_block_take(size_t min_bytes, size_t* got_bytes);  // nullptr if nothing suitable is parked
+void big_block_give(void* p, size_t bytes);                 // parks or frees
+
+// Growable array of PODs that does not value-initialise on resize (a std::vector would memset
+// hundreds of MB that are overwritten immediately, on one thread).
+template <class T>
+class PodBuffer {
+ public:
+  PodBuffer() = default;
+  PodBuffer(const PodBuffer&) = delete;
+  PodBuffer& operator=(const PodBuffer&) = delete;
+  ~PodBuffer() {
+    if (p_) big_block_give(p_, cap_ * sizeof(T));
+  }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  void clear() { n_ = 0; }
+  void reserve(size_t c) {
+    if (c <= cap_) return;
+    if (!p_) {
+      size_t got = 0;
+      if (void* r = big_block_take(c * sizeof(T), &got)) {
+        p_ = static_cast<T*>(r);
+        cap_ = got / sizeof(T);
+        return;
+      }
+    }
+    T* q = static_cast<T*>(realloc(p_, c * sizeof(T)));
+    if (!q) throw std::bad_alloc();
+    p_ = q;
+    cap_ = c;
+  }
+  void resize(size_t n) {
+    if (n > cap_) reserve(std::max(n, cap_ + cap_ / 2));
+    n_ = n;
+  }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  const T* begin() const { return p_; }
+  const T* end() const { return p_ + n_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
+
 
 inline bool profile_enabled() {
   static int v = -1;

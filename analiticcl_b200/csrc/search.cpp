@@ -28,17 +28,22 @@ static inline uint32_t decode_at(const std::string& s, size_t i, unsigned* len) 
 // src/search.rs:190-235: a boundary is a maximal run of non-alphabetic characters; the text always
 // ends with a boundary (possibly of length zero).  The scan runs in parallel over byte ranges; a run
 // that crosses a range border is stitched back together afterwards.
-std::vector<Boundary> find_boundaries(const std::string& text) {
+// (Scratch vectors are thread_local: the pool's workers are persistent, so after the first call their
+// capacity is already mapped and a 100 M-token stream does not page-fault hundreds of MB per call.)
+const std::vector<Boundary>& find_boundaries(const std::string& text) {
   const size_t n = text.size();
   const unsigned nt_max = host_threads();
-  std::vector<std::vector<Boundary>> part(nt_max);
+  std::vector<std::vector<Boundary>*> part(nt_max, nullptr);
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
   const unsigned used = parallel_ranges(n, 1u << 16, [&](unsigned t, uint64_t lo, uint64_t hi) {
     // move both ends to the start of a character (skip UTF-8 continuation bytes)
     while (lo < n && lo > 0 && ((unsigned char)text[lo] & 0xC0) == 0x80) ++lo;
     while (hi < n && ((unsigned char)text[hi] & 0xC0) == 0x80) ++hi;
     range[t] = {lo, hi};
-    std::vector<Boundary>& out = part[t];
+    static thread_local std::vector<Boundary> scratch;
+    scratch.clear();
+    part[t] = &scratch;
+    std::vector<Boundary>& out = scratch;
     out.reserve((size_t)(hi - lo) / 5 + 16);
     bool open = false;
     size_t start = 0;
@@ -56,17 +61,21 @@ std::vector<Boundary> find_boundaries(const std::string& text) {
     }
     if (open) out.push_back(Boundary{start, (size_t)hi, BOUNDARY_NONE});  // may continue in the next range
   });
-  std::vector<Boundary> out;
+  static thread_local std::vector<Boundary> out_tl;
+  std::vector<Boundary>& out = out_tl;
+  out.clear();
   size_t total = 1;
-  for (unsigned t = 0; t < used; ++t) total += part[t].size();
+  for (unsigned t = 0; t < used; ++t) total += part[t] ? part[t]->size() : 0;
   out.reserve(total);
-  for (unsigned t = 0; t < used; ++t)
-    for (const Boundary& b : part[t]) {
+  for (unsigned t = 0; t < used; ++t) {
+    if (!part[t]) continue;
+    for (const Boundary& b : *part[t]) {
       if (!out.empty() && out.back().end == b.begin)
         out.back().end = b.end;  // the same run, cut by a range border
       else
         out.push_back(b);
     }
+  }
   if (out.empty() || out.back().end != n) out.push_back(Boundary{n, n, BOUNDARY_NONE});
   // src/search.rs:238-258: last or multi-byte boundary = hard; ' - _ = weak; else normal
   for (size_t i = 0; i < out.size(); ++i) {
@@ -109,16 +118,21 @@ void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t n
   }
 }
 
-SegmentedText segment_text(const std::string& text, uint32_t max_ngram) {
-  SegmentedText st;
-  st.batch_first.push_back(0);
-  if (text.empty()) return st;
-  const std::vector<Boundary> bounds = find_boundaries(text);
+void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp) {
+  SegmentedText& st = *stp;
+  st.segs.clear();
+  st.batch_first.resize(1);
+  st.batch_first[0] = 0;
+  if (text.empty()) return;
+  const std::vector<Boundary>& bounds = find_boundaries(text);
   // the batches: spans between hard boundaries (src/lib.rs:1822)
   struct Desc {
     size_t begin, begin_index, end_index;
   };
-  std::vector<Desc> descs;
+  // (a lambda naming a thread_local would see the executing thread's instance: bind it to a local reference)
+  static thread_local std::vector<Desc> descs_tl;
+  std::vector<Desc>& descs = descs_tl;
+  descs.clear();
   {
     size_t begin = 0, begin_index = 0;
     for (size_t i = 0; i < bounds.size(); ++i) {
@@ -130,12 +144,16 @@ SegmentedText segment_text(const std::string& text, uint32_t max_ngram) {
   }
   const size_t nb = descs.size();
   const unsigned nt_max = host_threads();
-  std::vector<std::vector<SegmentSpan>> part(nt_max);
+  std::vector<std::vector<SegmentSpan>*> part(nt_max, nullptr);
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
-  std::vector<uint64_t> count(nb + 1, 0);  // segments per batch, then exclusive prefix
+  st.batch_first.resize(nb + 1);  // segments per batch first, then the exclusive prefix
+  uint64_t* count = st.batch_first.data() + 1;
   const unsigned used = parallel_ranges(nb, 256, [&](unsigned t, uint64_t lo, uint64_t hi) {
     range[t] = {lo, hi};
-    std::vector<SegmentSpan>& out = part[t];
+    static thread_local std::vector<SegmentSpan> scratch;
+    scratch.clear();
+    part[t] = &scratch;
+    std::vector<SegmentSpan>& out = scratch;
     if (hi > lo) out.reserve((descs[hi - 1].end_index - descs[lo].begin_index + 1) * (size_t)max_ngram + 16);
     for (uint64_t k = lo; k < hi; ++k) {
       const Desc& d = descs[k];
@@ -146,14 +164,14 @@ SegmentedText segment_text(const std::string& text, uint32_t max_ngram) {
       count[k] = out.size() - before;
     }
   });
-  st.batch_first.assign(nb + 1, 0);
-  for (size_t k = 0; k < nb; ++k) st.batch_first[k + 1] = st.batch_first[k] + count[k];
+  st.batch_first[0] = 0;
+  for (size_t k = 0; k < nb; ++k) st.batch_first[k + 1] += st.batch_first[k];  // count[k] lives in batch_first[k + 1]
   st.segs.resize(st.batch_first[nb]);
   parallel_ranges(used, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
     for (uint64_t t = lo; t < hi; ++t)
-      if (!part[t].empty()) std::copy(part[t].begin(), part[t].end(), st.segs.begin() + st.batch_first[range[t].first]);
+      if (part[t] && !part[t]->empty())
+        std::copy(part[t]->begin(), part[t]->end(), st.segs.data() + st.batch_first[range[t].first]);
   });
-  return st;
 }
 
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text) {

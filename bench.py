@@ -408,21 +408,18 @@ def run_search(args):
             L.anl_match_set_free(ms)
     dt = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
-    mm = _capi.Match()
-    looked = variants = 0
-    for i in range(0, n, max(1, n // 200000)):  # sample: decoding every match in Python would dominate
-        L.anl_match_set_get(ms, i, C.byref(mm))
-        looked += 1 if mm.variants else 0
-        variants += mm.n_variants
-    frac = looked / max(1, len(range(0, n, max(1, n // 200000))))
+    a, b = C.c_uint64(), C.c_uint64()
+    L.anl_match_set_lookup_counts(ms, C.byref(a), C.byref(b))
+    lookups, distinct = a.value, b.value
+    frac = lookups / max(1, n)
     L.anl_match_set_free(ms)
-    lookups = n * frac
     line = {
         "metric": METRIC, "value": lookups / dt, "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 multi-limb integer / u8 DP / f64 score", "data": "synthetic",
         "config": {"workload": f"cfg3: find_all_matches over {n_tokens} tokens of synthetic running text, max_ngram=3, k=3 (eng)",
-                   "segments": n, "looked_up_fraction": frac, "text_bytes": len(raw),
+                   "segments": n, "segment_lookups": lookups, "looked_up_fraction": frac,
+                   "distinct_strings_sent_to_gpu": distinct, "text_bytes": len(raw),
                    "value_scope": "end to end through anl_find_all_matches (host segmentation, two pipelined GPU batches per "
                                   "window, result assembly); query = one n-gram segment lookup"},
         "tokens_per_s": n_tokens / dt,

@@ -201,6 +201,10 @@ typedef struct anl_match {
 uint64_t anl_match_set_len(const anl_match_set* ms);
 anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out);
 void anl_match_set_free(anl_match_set* ms);
+/* How many segment lookups the call performed (== what the reference's per-segment find_variants loop
+ * would issue, src/lib.rs:1883-1899) and how many distinct strings were actually sent to the GPU (the
+ * producer de-duplicates identical segments inside a window). */
+void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_lookups, uint64_t* distinct_strings);
 
 /* ---- device-resident path (what bench.py times as `value`; plumbing for multi-GPU hosts) ------ */
 typedef struct anl_device_batch anl_device_batch; /* encoded queries + result buffers in HBM */

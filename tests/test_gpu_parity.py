@@ -319,3 +319,53 @@ def test_find_all_matches_segments_parity(A, eng, eng_oracle, max_ngram, monkeyp
     assert not bad, bad[:5]
     if max_ngram > 1:
         assert any(not e["looked_up"] for e in exp) and any(e["looked_up"] and e["n"] > 1 for e in exp)
+
+
+def _all_matches_raw(A, model, text, sp):
+    import ctypes as C
+    from analiticcl_b200 import _capi
+    L = _capi.lib()
+    raw = text.encode("utf-8")
+    ms = C.c_void_p()
+    assert L.anl_find_all_matches(model._h, raw, len(raw), C.byref(sp.data), C.byref(ms)) == 0, L.anl_last_error()
+    out = []
+    m = _capi.Match()
+    for i in range(L.anl_match_set_len(ms)):
+        assert L.anl_match_set_get(ms, i, C.byref(m)) == 0
+        vs = tuple((m.variants[j].vocab_id, bits(m.variants[j].dist_score), bits(m.variants[j].freq_score))
+                   for j in range(m.n_variants)) if m.variants else None
+        out.append((int(m.begin), int(m.end), int(m.n), int(m.selected), vs))
+    a, b = C.c_uint64(), C.c_uint64()
+    L.anl_match_set_lookup_counts(ms, C.byref(a), C.byref(b))
+    L.anl_match_set_free(ms)
+    return out, a.value, b.value
+
+
+@pytest.mark.gpu
+def test_find_all_matches_large_text_equals_piecewise(A, eng):
+    """Size-independent property for the multi-threaded producer (parallel boundary scan stitched across
+    byte ranges, hash-partitioned de-duplication, parallel assembly): the matches of a long text equal the
+    matches of its sentence groups looked up one small call at a time (single-threaded paths), shifted."""
+    sents = workloads.cfg3_text(60000, 77).split(". ")
+    extra = "It's a well-known co-operative re_entry über naïve façade"
+    pieces, cur = [], []
+    for i, s in enumerate(sents):
+        cur.append(s if i % 97 else s + " " + extra)
+        if len(cur) == 150:
+            pieces.append(". ".join(cur) + ". ")
+            cur = []
+    if cur:
+        pieces.append(". ".join(cur) + ". ")
+    text = "".join(pieces)
+    assert len(text.encode("utf-8")) > 400_000 and all(len(p.encode("utf-8")) < 60_000 for p in pieces)
+    sp = A.SearchParameters(max_ngram=3, max_anagram_distance=2, max_edit_distance=2)
+    whole, lookups, distinct = _all_matches_raw(A, eng, text, sp)
+    assert 0 < distinct < lookups  # running text repeats itself: the producer de-duplicates
+    exp, shift = [], 0
+    for p in pieces:
+        part, _, _ = _all_matches_raw(A, eng, p, sp)
+        exp += [(b + shift, e + shift, n, sel, vs) for b, e, n, sel, vs in part]
+        shift += len(p.encode("utf-8"))
+    assert len(whole) == len(exp)
+    bad = [i for i, (g, e) in enumerate(zip(whole, exp)) if g != e]
+    assert not bad, (len(bad), whole[bad[0]], exp[bad[0]])
