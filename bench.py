@@ -533,7 +533,13 @@ def run_sharded(args):
     dist.destroy_process_group()
 
 
+def keep_stdout_clean():
+    """NCCL writes its version / debug lines to stdout by default; the driver reads ONE JSON line from stdout."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
 def main():
+    keep_stdout_clean()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
