@@ -905,6 +905,10 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     const uint32_t nh = hit_count[qi];
     const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
     const double Ld = (double)Lq;
+    // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
+    // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
+    const double quot_lane = __ddiv_rn((double)lane, Ld);
+    const bool quot_ok = Lq <= 31;
 
     uint32_t nsurv = 0;
     double maxfreq = 0.0;
@@ -1017,11 +1021,23 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       const bool samecase = bp.w_case > 0.0 ? (c_lower == q_lower) : true;
 
       // ---- f64 score, left to right, no FMA (src/lib.rs:1433-1452) -----------------------------------
-      const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, __ddiv_rn((double)ld, Ld));
+      double q_ld, q_lcs, q_pre, q_suf;
+      if (quot_ok) {  // warp-uniform; all four indices are <= Lq <= 31 (ld is clamped: it only matters when <= Lq)
+        q_ld = __shfl_sync(FULL, quot_lane, min(ld, 31u));
+        q_lcs = __shfl_sync(FULL, quot_lane, f_lcs);
+        q_pre = __shfl_sync(FULL, quot_lane, f_pre);
+        q_suf = __shfl_sync(FULL, quot_lane, f_suf);
+      } else {
+        q_ld = __ddiv_rn((double)ld, Ld);
+        q_lcs = __ddiv_rn((double)f_lcs, Ld);
+        q_pre = __ddiv_rn((double)f_pre, Ld);
+        q_suf = __ddiv_rn((double)f_suf, Ld);
+      }
+      const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, q_ld);
       double acc = __dmul_rn(bp.w_ld, ds);
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, __ddiv_rn((double)f_lcs, Ld)));
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, __ddiv_rn((double)f_pre, Ld)));
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, __ddiv_rn((double)f_suf, Ld)));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, q_lcs));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, q_pre));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, q_suf));
       acc = __dadd_rn(acc, samecase ? bp.w_case : 0.0);
       const double score = __ddiv_rn(acc, bp.w_sum);
       double freq = 1.0;
@@ -1151,7 +1167,7 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
 // strings and the product of the weights of all patterns found in it (rescore_confusables /
 // compute_confusable_weight, src/lib.rs:1656-1663,1733-1756), multiplies the record's distance score and
 // marks it settled.  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
                   const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
                   OutRec* __restrict__ out) {
@@ -1358,8 +1374,11 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
                                cudaStream_t stream) {
   if (lb.n == 0 || !lb.conf_work) return cudaSuccess;
-  confusable_kernel<<<(unsigned)sm_count * 8, 128, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap,
-                                                                lb.out);
+  // one thread per possible work item (the queue length is only known on the device): threads beyond the
+  // queue exit at once, and the long, divergent per-pair work is balanced by the block scheduler
+  unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
+  if (blocks < 1) blocks = 1;
+  confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
   return cudaGetLastError();
 }
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream) {
