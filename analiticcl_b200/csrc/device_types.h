@@ -130,6 +130,19 @@ struct ConfWork {
   uint32_t query;  // query row (index into the batch's raw text offsets)
 };
 
+// ---- alphabet on the device (query normalisation, src/anahash.rs:50-80) --------------------------------
+// Greedy matching in alphabet-file order: members that start with a given byte, in (line, member) order.
+struct AlphaMember {
+  uint8_t seqnr;      // class index = symbol
+  uint8_t len;        // bytes of the member (<= 14)
+  uint8_t bytes[14];
+};
+struct AlphaFirst {
+  uint16_t first, count;  // members starting with this byte: alpha_members[first .. first + count)
+};
+// per-query result of the encode kernel
+static const uint8_t ENC_OK = 0, ENC_TOO_LONG_EMPTY = 1, ENC_TOO_LONG_UNSUPPORTED = 2;
+
 // ---- per-model constant data ------------------------------------------------------------------------
 struct DeviceIndex {
   const Slot* table;
@@ -159,6 +172,13 @@ struct DeviceIndex {
   const uint8_t* conf_text;         // option texts of the patterns, back to back
   uint32_t n_conf_pats;
   int32_t conf_prefilter;           // 1: table valid, the kernel may set OUT_SKIP_CONFUSABLES
+  // alphabet tables for the encode kernel (device_encode = 0: the host normalises the queries)
+  const AlphaMember* alpha_members;
+  const AlphaFirst* alpha_first;    // [256]
+  const uint32_t* lower_ranges;     // [n_lower_ranges][2] inclusive code point ranges of char::is_lowercase
+  uint32_t n_lower_ranges;
+  uint32_t unk_symbol;
+  int32_t device_encode;
   const MsetEntry* mset;
   uint32_t mset_end[ANL_MAX_K + 1];  // mset_end[J] = number of entries with j <= J; [0] = 0
   const uint32_t* binom;             // [256][8] saturating binomials C(n, k)

@@ -195,6 +195,26 @@ bool Engine::upload(int device, std::string* err) {
       for (uint32_t p0 = 0; p0 < p1; ++p0) colex3.push_back(p0 | (p1 << 8) | (p2 << 16));
   if (!upload_vec(colex2, &ix.colex2, &index_allocs_, err)) return false;
   if (!upload_vec(colex3, &ix.colex3, &index_allocs_, err)) return false;
+  // alphabet tables for the encode kernel (queries are normalised on the device unless a member does not fit)
+  {
+    std::vector<AlphaMember> members;
+    std::vector<AlphaFirst> first;
+    const char* off = getenv("ANL_HOST_ENCODE");
+    if (!(off && atoi(off)) && hm_->alphabet.export_tables(&members, &first)) {
+      if (members.empty()) members.push_back(AlphaMember{});
+      std::vector<uint32_t> lower(2 * (size_t)anl_unicode::kLowercaseRanges_len);
+      for (unsigned i = 0; i < anl_unicode::kLowercaseRanges_len; ++i) {
+        lower[2 * i] = anl_unicode::kLowercaseRanges[i][0];
+        lower[2 * i + 1] = anl_unicode::kLowercaseRanges[i][1];
+      }
+      if (!upload_vec(members, &ix.alpha_members, &index_allocs_, err)) return false;
+      if (!upload_vec(first, &ix.alpha_first, &index_allocs_, err)) return false;
+      if (!upload_vec(lower, &ix.lower_ranges, &index_allocs_, err)) return false;
+      ix.n_lower_ranges = anl_unicode::kLowercaseRanges_len;
+      ix.unk_symbol = hm_->alphabet.unk_symbol();
+      ix.device_encode = 1;
+    }
+  }
   memcpy(ix.prime_of, hx.prime_of, sizeof ix.prime_of);
   memcpy(ix.charcount_mask, hx.charcount_mask, sizeof ix.charcount_mask);
   ix.max_charcount = hx.max_charcount;
@@ -384,6 +404,8 @@ void Engine::destroy_batch(DeviceBatch* b) {
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
   if (b->d_conf_work) cudaFree(b->d_conf_work);
+  if (b->d_enc_status) cudaFree(b->d_enc_status);
+  if (b->h_enc_status) cudaFreeHost(b->h_enc_status);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
                   (void*)b->d_gid, (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
                   (void*)b->rr_hits, (void*)b->rr_hit_count, (void*)b->rr_qflags, (void*)b->rr_head, (void*)b->rr_out,
@@ -530,56 +552,60 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   b->bp = bp;
   pt.lap("create: buffers");
 
-  // host normalisation (src/anahash.rs:50-80) into fixed-stride rows: len, flags, symbols
+  // query normalisation (src/anahash.rs:50-80) into fixed-stride rows (len, flags, symbols): on the device
+  // from the raw text (encode_kernel), or on the host when the alphabet does not fit the device tables
   b->host_flags.assign(n, 0);
+  const uint64_t blob_bytes = b->offsets[n];
+  b->dev_encode = h_ix_.device_encode && blob_bytes < 0xFFFFFFF0ull;
   uint8_t* rows = b->h_rows;
-  const Alphabet& ab = hm_->alphabet;
-  const char* text = b->blob;
-  parallel_ranges(n, 2048, [&](unsigned, uint64_t lo, uint64_t hi) {
-    for (uint64_t i = lo; i < hi; ++i) {
-      uint8_t* row = rows + (size_t)i * stride;
-      const char* s = text + b->offsets[i];
-      const size_t len = (size_t)(b->offsets[i + 1] - b->offsets[i]);
-      size_t c = ab.encode_into(s, len, row + 2, stride - 2);
-      uint8_t flags = 0;
-      if (len > 0) {
-        // first char lowercase?  (src/lib.rs:1374)
-        unsigned char c0 = (unsigned char)s[0];
-        uint32_t cp = c0;
-        if (c0 >= 0x80) {
-          unsigned l = (c0 & 0xE0) == 0xC0 ? 2 : ((c0 & 0xF0) == 0xE0 ? 3 : ((c0 & 0xF8) == 0xF0 ? 4 : 1));
-          if (l > len) l = (unsigned)len;
-          cp = c0 & (0xFFu >> (l + 1));
-          for (unsigned k = 1; k < l; ++k) cp = (cp << 6) | ((unsigned char)s[k] & 0x3F);
+  if (!b->dev_encode) {
+    const Alphabet& ab = hm_->alphabet;
+    const char* text = b->blob;
+    parallel_ranges(n, 2048, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        uint8_t* row = rows + (size_t)i * stride;
+        const char* s = text + b->offsets[i];
+        const size_t len = (size_t)(b->offsets[i + 1] - b->offsets[i]);
+        size_t c = ab.encode_into(s, len, row + 2, stride - 2);
+        uint8_t flags = 0;
+        if (len > 0) {
+          // first char lowercase?  (src/lib.rs:1374)
+          unsigned char c0 = (unsigned char)s[0];
+          uint32_t cp = c0;
+          if (c0 >= 0x80) {
+            unsigned l = (c0 & 0xE0) == 0xC0 ? 2 : ((c0 & 0xF0) == 0xE0 ? 3 : ((c0 & 0xF8) == 0xF0 ? 4 : 1));
+            if (l > len) l = (unsigned)len;
+            cp = c0 & (0xFFu >> (l + 1));
+            for (unsigned k = 1; k < l; ++k) cp = (cp << 6) | ((unsigned char)s[k] & 0x3F);
+          }
+          if (anl_unicode::is_lowercase(cp)) flags |= Q_FIRST_LOWER;
         }
-        if (anl_unicode::is_lowercase(cp)) flags |= Q_FIRST_LOWER;
+        if (c > (size_t)ANL_MAX_SYMBOLS) {
+          // longer than the device rows hold.  If even after max_anagram_distance deletions the
+          // query is longer than the longest indexed entry, the result is empty (exact); otherwise
+          // the query is outside the supported range.
+          const uint32_t ka = host_threshold(p.max_anagram_distance, c);
+          b->host_flags[i] = (c > (size_t)hm_->index.max_charcount + ka) ? 1 : 2;
+          c = 0;
+        }
+        row[0] = (uint8_t)c;
+        row[1] = flags;
       }
-      if (c > (size_t)ANL_MAX_SYMBOLS) {
-        // longer than the device rows hold.  If even after max_anagram_distance deletions the
-        // query is longer than the longest indexed entry, the result is empty (exact); otherwise
-        // the query is outside the supported range.
-        const uint32_t ka = host_threshold(p.max_anagram_distance, c);
-        b->host_flags[i] = (c > (size_t)hm_->index.max_charcount + ka) ? 1 : 2;
-        c = 0;
+    });
+    for (uint64_t i = 0; i < n; ++i) {
+      if (b->host_flags[i] == 2) {
+        *err = "query " + std::to_string(i) + " is longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols";
+        *status = ANL_ERR_UNSUPPORTED;
+        free_batch(b);
+        return nullptr;
       }
-      row[0] = (uint8_t)c;
-      row[1] = flags;
-    }
-  });
-  for (uint64_t i = 0; i < n; ++i) {
-    if (b->host_flags[i] == 2) {
-      *err = "query " + std::to_string(i) + " is longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols";
-      *status = ANL_ERR_UNSUPPORTED;
-      free_batch(b);
-      return nullptr;
     }
   }
   pt.lap("create: encode");
   // raw query bytes for the device-side confusable stage (only when a confusable post-pass follows)
   b->has_qblob = false;
-  const uint64_t blob_bytes = b->offsets[n];
-  if (h_ix_.conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER) && n > 0 &&
-      blob_bytes < 0xFFFFFFF0ull) {
+  const bool conf_stage = h_ix_.conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER);
+  if ((conf_stage || b->dev_encode) && n > 0 && blob_bytes < 0xFFFFFFF0ull) {
     std::string e2;
     bool okb = true;
     if (blob_bytes > b->cap_qblob || !b->d_qblob) {
@@ -589,15 +615,20 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       b->cap_qblob = okb ? want : 0;
     }
     if (okb && (n + 1 > b->cap_qboff || !b->d_qboff)) {
-      okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2);
+      okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2) &&
+            dev_realloc(&b->d_enc_status, (size_t)n + 1, &e2) && pinned_realloc(&b->h_enc_status, (size_t)n + 1, &e2);
       b->cap_qboff = okb ? (size_t)n + 1 : 0;
     }
     if (!okb) {
       *err = e2;
       return fail();
     }
-    for (uint64_t i = 0; i <= n; ++i) b->h_qboff[i] = (uint32_t)b->offsets[i];
-    memcpy(b->h_qblob, b->blob, (size_t)blob_bytes);  // pinned staging: the caller's memory is pageable
+    parallel_ranges(n + 1, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) b->h_qboff[i] = (uint32_t)b->offsets[i];
+    });
+    parallel_ranges(blob_bytes, 1u << 20, [&](unsigned, uint64_t lo, uint64_t hi) {
+      memcpy(b->h_qblob + lo, b->blob + lo, (size_t)(hi - lo));  // pinned staging: the caller's memory is pageable
+    });
     if (cudaMemcpyAsync(b->d_qblob, b->h_qblob, (size_t)blob_bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
         cudaMemcpyAsync(b->d_qboff, b->h_qboff, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
       *err = "H2D copy of the query text failed";
@@ -605,9 +636,16 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     }
     b->has_qblob = true;
   }
-  b->dev_conf = b->has_qblob && b->d_conf_work != nullptr && !b->sharded;
+  b->dev_conf = conf_stage && b->has_qblob && b->d_conf_work != nullptr && !b->sharded;
+  if (b->dev_encode && !b->has_qblob && n > 0) b->dev_encode = false;  // (cannot happen: the text was staged above)
   pt.lap("create: query text");
-  if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
+  if (b->dev_encode) {
+    if (launch_encode(d_ix_, bp, reinterpret_cast<const uint8_t*>(b->d_qblob), b->d_qboff, (uint32_t)n, b->d_rows, b->d_enc_status,
+                      b->stream) != cudaSuccess) {
+      *err = "encode kernel launch failed";
+      return fail();
+    }
+  } else if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
     *err = "H2D copy failed";
     return fail();
   }
@@ -624,7 +662,7 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   LaunchBuffers lb;
   lb.queries = b->d_rows;
   lb.qlist = nullptr;
-  lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
+  lb.qblob = b->has_qblob ? reinterpret_cast<const uint8_t*>(b->d_qblob) : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
   lb.conf_work = b->dev_conf ? b->d_conf_work : nullptr;
   lb.n = b->n;
@@ -887,8 +925,11 @@ bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* e
       CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      if (b->dev_encode) CU_TRY(cudaMemcpyAsync(b->h_enc_status, b->d_enc_status, (size_t)n, cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(st));
+    if (b->dev_encode)
+      for (uint32_t i = 0; i < n; ++i) b->host_flags[i] = b->h_enc_status[i];
     total = n ? b->h_work[2] : 0;
     if (total <= b->bp.pool_cap || b->merged) break;
     if (attempt >= 2) {

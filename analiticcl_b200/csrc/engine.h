@@ -47,12 +47,15 @@ struct DeviceBatch {
   unsigned int* h_work = nullptr;  // [4]
   // device buffers
   uint8_t* d_rows = nullptr;
-  uint8_t* d_qblob = nullptr;   // raw query bytes (confusable prefilter), grow-only
+  uint8_t* d_qblob = nullptr;   // raw query bytes (encode kernel, confusable stage), grow-only
   uint32_t* d_qboff = nullptr;  // n + 1 byte offsets into d_qblob
   uint32_t* h_qboff = nullptr;  // pinned staging of the offsets
   char* h_qblob = nullptr;      // pinned staging of the query text
   size_t cap_qblob = 0, cap_qboff = 0;
   bool has_qblob = false;
+  uint8_t* d_enc_status = nullptr;  // per query: ENC_* result of the encode kernel
+  uint8_t* h_enc_status = nullptr;
+  bool dev_encode = false;          // the rows of this batch were encoded on the device
   ConfWork* d_conf_work = nullptr;  // queue of (record, query) pairs for the confusable kernel, sized like d_out
   bool dev_conf = false;            // this batch's confusables are rescored on the device (HEAD_HOST_FINISH marks the rest)
   uint32_t* d_hits = nullptr;

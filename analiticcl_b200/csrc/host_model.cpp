@@ -105,6 +105,26 @@ void Alphabet::finalize() {
       if (!m.empty()) by_first_[(unsigned char)m[0]].push_back(Member{seqnr, m});
 }
 
+bool Alphabet::export_tables(std::vector<AlphaMember>* members, std::vector<AlphaFirst>* first) const {
+  members->clear();
+  first->assign(256, AlphaFirst{0, 0});
+  for (int b = 0; b < 256; ++b) {
+    if (by_first_[b].size() > 0xFFFF || members->size() + by_first_[b].size() > 0xFFFF) return false;
+    (*first)[b].first = (uint16_t)members->size();
+    (*first)[b].count = (uint16_t)by_first_[b].size();
+    for (const Member& m : by_first_[b]) {
+      if (m.bytes.size() > 14 || m.seqnr > 255) return false;
+      AlphaMember am;
+      memset(&am, 0, sizeof am);
+      am.seqnr = (uint8_t)m.seqnr;
+      am.len = (uint8_t)m.bytes.size();
+      memcpy(am.bytes, m.bytes.data(), m.bytes.size());
+      members->push_back(am);
+    }
+  }
+  return true;
+}
+
 size_t Alphabet::encode_into(const char* s, size_t n, uint8_t* out, size_t cap) const {
   size_t count = 0, i = 0;
   const uint32_t unk = unk_symbol();

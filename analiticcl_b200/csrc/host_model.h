@@ -55,6 +55,8 @@ class Alphabet {
   // Encode into a fixed buffer; returns the number of symbols (may exceed cap; extra symbols dropped).
   size_t encode_into(const char* s, size_t n, uint8_t* out, size_t cap) const;
   const std::vector<std::vector<std::string>>& lines() const { return lines_; }
+  // Flat tables for the device encode kernel (device_types.h); false if a member does not fit.
+  bool export_tables(std::vector<AlphaMember>* members, std::vector<AlphaFirst>* first) const;
 
  private:
   struct Member {

@@ -71,6 +71,86 @@ __device__ __forceinline__ bool ccbit(const uint64_t* mask, uint32_t cc) {
 }
 
 // ================================================================================================
+// Kernel 0: query normalisation (normalize_to_alphabet, src/anahash.rs:50-80)
+// ================================================================================================
+// One thread per query: greedy matching of alphabet members at each character position, in alphabet-file
+// order (the members starting with the current byte are listed in (line, member) order); an unmatched
+// character becomes the UNK symbol.  Writes the encoded row (len, flags, symbols) the other kernels read.
+__device__ __forceinline__ uint32_t dev_u8len(uint32_t c) {
+  if (c < 0x80) return 1;
+  if ((c & 0xE0) == 0xC0) return 2;
+  if ((c & 0xF0) == 0xE0) return 3;
+  if ((c & 0xF8) == 0xF0) return 4;
+  return 1;
+}
+__global__ void __launch_bounds__(128)
+encode_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ qblob,
+              const uint32_t* __restrict__ qboff, uint32_t n, uint8_t* __restrict__ rows, uint8_t* __restrict__ status) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t b0 = qboff[q], len = qboff[q + 1] - b0;
+  const uint8_t* __restrict__ s = qblob + b0;
+  uint8_t* __restrict__ row = rows + (size_t)q * bp.query_stride;
+  const uint32_t cap = bp.query_stride - 2;
+  const AlphaMember* __restrict__ members = ix->alpha_members;
+  const uint32_t unk = ix->unk_symbol;
+  uint32_t count = 0, i = 0;
+  while (i < len) {
+    const uint32_t c = s[i];
+    const AlphaFirst af = ix->alpha_first[c];
+    uint32_t step = 0, sym = unk;
+    for (uint32_t m = af.first; m < (uint32_t)af.first + af.count; ++m) {
+      const uint32_t ml = members[m].len;
+      if (i + ml > len) continue;
+      bool eq = true;
+      for (uint32_t k = 1; k < ml && eq; ++k) eq = s[i + k] == members[m].bytes[k];
+      if (eq) {
+        step = ml;
+        sym = members[m].seqnr;
+        break;
+      }
+    }
+    if (step == 0) step = dev_u8len(c);
+    if (count < cap) row[2 + count] = (uint8_t)sym;
+    i += step;
+    ++count;
+  }
+  uint32_t flags = 0;
+  if (len > 0) {
+    // is the first character lowercase?  (src/lib.rs:1374)
+    const uint32_t c0 = s[0];
+    uint32_t cp = c0;
+    if (c0 >= 0x80) {
+      uint32_t l = dev_u8len(c0);
+      if (l > len) l = len;
+      cp = c0 & (0xFFu >> (l + 1));
+      for (uint32_t k = 1; k < l; ++k) cp = (cp << 6) | (s[k] & 0x3Fu);
+      // binary search in the inclusive [lo, hi] ranges
+      uint32_t lo = 0, hi = ix->n_lower_ranges;
+      const uint32_t* __restrict__ t = ix->lower_ranges;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (cp > t[2 * mid + 1]) lo = mid + 1; else hi = mid;
+      }
+      if (lo < ix->n_lower_ranges && cp >= t[2 * lo]) flags |= Q_FIRST_LOWER;
+    } else if (cp >= 'a' && cp <= 'z') {
+      flags |= Q_FIRST_LOWER;
+    }
+  }
+  uint8_t st = ENC_OK;
+  if (count > (uint32_t)ANL_MAX_SYMBOLS) {
+    // longer than the device rows hold.  If even after max_anagram_distance deletions the query is longer
+    // than the longest indexed entry, the result is empty (exact); otherwise it is outside the supported range
+    const uint32_t ka = apply_threshold(bp.max_anagram, count);
+    st = (count > ix->max_charcount + ka) ? ENC_TOO_LONG_EMPTY : ENC_TOO_LONG_UNSUPPORTED;
+    count = 0;
+  }
+  row[0] = (uint8_t)count;
+  row[1] = (uint8_t)flags;
+  status[q] = st;
+}
+
+// ================================================================================================
 // Kernel 1: candidate generation
 // ================================================================================================
 // Every node X = D + I' of the query's neighbourhood (D: a sub-multiset of the focus after d deletions,
@@ -1304,6 +1384,13 @@ cudaError_t configure_kernels() {
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_fn(), K1_WARPS * 32, sizeof(K1Shared));
   return e;
+}
+
+cudaError_t launch_encode(const DeviceIndex* d_ix, const BatchParams& bp, const uint8_t* qblob, const uint32_t* qboff, uint32_t n,
+                          uint8_t* rows, uint8_t* status, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  encode_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_ix, bp, qblob, qboff, n, rows, status);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,

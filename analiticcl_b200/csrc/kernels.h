@@ -26,6 +26,9 @@ struct LaunchBuffers {
   Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
 };
 
+// Query normalisation on the device (normalize_to_alphabet, src/anahash.rs:50-80): raw text -> encoded rows.
+cudaError_t launch_encode(const DeviceIndex* d_ix, const BatchParams& bp, const uint8_t* qblob, const uint32_t* qboff, uint32_t n,
+                          uint8_t* rows, uint8_t* status, cudaStream_t stream);
 // Candidate generation: deletion neighbourhood x insertion multisets -> Bloom -> table -> postings.
 cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
