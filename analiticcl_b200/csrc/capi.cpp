@@ -229,22 +229,34 @@ int64_t anl_shortest_edit_script(const char* src, size_t src_len, const char* ds
   return (int64_t)text.size();
 }
 int64_t anl_shortest_edit_script_fixed(const char* src, size_t src_len, const char* dst, size_t dst_len, char* out, size_t cap) {
-  // host build of the code the confusable kernel runs per thread (csrc/editscript_fixed.h)
-  for (size_t i = 0; i < src_len; ++i)
-    if ((unsigned char)src[i] >= 0x80) return -1;
-  for (size_t i = 0; i < dst_len; ++i)
-    if ((unsigned char)dst[i] >= 0x80) return -1;
-  if (src_len > (size_t)esf::MAXLEN || dst_len > (size_t)esf::MAXLEN) return -1;
-  esf::View v[esf::MAXSEG];
-  const uint8_t* a = reinterpret_cast<const uint8_t*>(src);
-  const uint8_t* b = reinterpret_cast<const uint8_t*>(dst);
-  const int nv = esf::shortest_edit_script(a, (int)src_len, b, (int)dst_len, v);
-  if (nv < 0) return -1;
+  // host builds of the fixed-capacity implementation (csrc/editscript_fixed.h): over bytes for pure-ASCII pairs
+  // (exactly what the confusable kernel runs per thread), over Unicode scalar values otherwise (what the host
+  // post-pass runs for the pairs the kernel declines)
+  bool ascii = true;
+  for (size_t i = 0; i < src_len; ++i) ascii = ascii && (unsigned char)src[i] < 0x80;
+  for (size_t i = 0; i < dst_len; ++i) ascii = ascii && (unsigned char)dst[i] < 0x80;
   std::string text;
-  for (int i = 0; i < nv; ++i) {
-    text += v[i].op == 0 ? "=[" : (v[i].op > 0 ? "+[" : "-[");
-    text.append(reinterpret_cast<const char*>((v[i].op > 0 ? b : a) + v[i].pos), v[i].len);
-    text += "]";
+  if (ascii) {
+    if (src_len > (size_t)esf::MAXLEN || dst_len > (size_t)esf::MAXLEN) return -1;
+    esf::View v[esf::MAXSEG];
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(src);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(dst);
+    const int nv = esf::shortest_edit_script(a, (int)src_len, b, (int)dst_len, v);
+    if (nv < 0) return -1;
+    for (int i = 0; i < nv; ++i) {
+      text += v[i].op == 0 ? "=[" : (v[i].op > 0 ? "+[" : "-[");
+      text.append(reinterpret_cast<const char*>((v[i].op > 0 ? b : a) + v[i].pos), v[i].len);
+      text += "]";
+    }
+  } else {
+    EditView v[64];
+    size_t nv = 0;
+    if (!edit_views_fixed(src, src_len, dst, dst_len, v, &nv)) return -1;
+    for (size_t i = 0; i < nv; ++i) {
+      text += v[i].op == 0 ? "=[" : (v[i].op > 0 ? "+[" : "-[");
+      text.append(v[i].p, v[i].n);
+      text += "]";
+    }
   }
   if (out && cap) {
     const size_t n = std::min(text.size(), cap - 1);

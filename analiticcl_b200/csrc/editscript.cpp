@@ -18,6 +18,10 @@
 #include "host_model.h"
 #include "unicode_tables.h"
 
+// the fixed-capacity implementation, instantiated here for Unicode scalar values (host only)
+#define ESF_FN inline
+#include "editscript_fixed.h"
+
 namespace anl {
 namespace {
 
@@ -583,6 +587,55 @@ bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>
   }
   for (size_t i = 0; i < ref.size(); ++i) v[i] = EditView{ref[i].op, ref[i].text.data(), ref[i].text.size()};
   return confusable_found_in_views(c, v, ref.size());
+}
+
+
+// The allocation-free route for short strings (what the host post-pass uses): edit script over Unicode
+// scalar values by the fixed-capacity implementation, returned as byte views into the two UTF-8 strings.
+// false = outside its limits (more than esf::MAXLEN scalars, internal capacity): use shortest_edit_script.
+namespace {
+struct UnicodeClass {
+  static bool alnum(uint32_t c) { return cp_alnum((char32_t)c); }
+  static bool space(uint32_t c) { return cp_space((char32_t)c); }
+};
+// decodes into scalars + the byte offset of each scalar (n + 1 entries); false if more than MAXLEN scalars
+bool decode_with_offsets(const char* s, size_t n, char32_t* out, uint16_t* off, int* count) {
+  int c = 0;
+  size_t i = 0;
+  while (i < n) {
+    if (c >= esf::MAXLEN) return false;
+    const unsigned char ch = (unsigned char)s[i];
+    unsigned l = ch < 0x80 ? 1 : ((ch & 0xE0) == 0xC0 ? 2 : ((ch & 0xF0) == 0xE0 ? 3 : ((ch & 0xF8) == 0xF0 ? 4 : 1)));
+    if (i + l > n) l = (unsigned)(n - i);
+    char32_t cp = l == 1 ? ch : (ch & (0xFFu >> (l + 1)));
+    for (unsigned k = 1; k < l; ++k) cp = (cp << 6) | ((unsigned char)s[i + k] & 0x3F);
+    off[c] = (uint16_t)i;
+    out[c++] = cp;
+    i += l;
+  }
+  off[c] = (uint16_t)n;
+  *count = c;
+  return true;
+}
+}  // namespace
+
+bool edit_views_fixed(const char* src, size_t src_len, const char* dst, size_t dst_len, EditView* out, size_t* nout) {
+  if (src_len > 4 * (size_t)esf::MAXLEN || dst_len > 4 * (size_t)esf::MAXLEN) return false;
+  char32_t a[esf::MAXLEN], b[esf::MAXLEN];
+  uint16_t oa[esf::MAXLEN + 1], ob[esf::MAXLEN + 1];
+  int na = 0, nb = 0;
+  if (!decode_with_offsets(src, src_len, a, oa, &na) || !decode_with_offsets(dst, dst_len, b, ob, &nb)) return false;
+  esf::View v[esf::MAXSEG];
+  const int nv = esf::shortest_edit_script_t<UnicodeClass, char32_t>(a, na, b, nb, v);
+  if (nv < 0) return false;
+  for (int i = 0; i < nv; ++i) {
+    const bool ins = v[i].op > 0;
+    const uint16_t* o = ins ? ob : oa;
+    const char* base = ins ? dst : src;
+    out[i] = EditView{v[i].op, base + o[v[i].pos], (size_t)(o[v[i].pos + v[i].len] - o[v[i].pos])};
+  }
+  *nout = (size_t)nv;
+  return true;
 }
 
 }  // namespace anl

@@ -18,10 +18,12 @@
 
 #include "device_types.h"
 
+#if !defined(ESF_FN)
 #if defined(__CUDACC__)
 #define ESF_FN __host__ __device__ inline
 #else
 #define ESF_FN inline
+#endif
 #endif
 
 namespace anl {
@@ -40,9 +42,10 @@ struct Frame {
   uint8_t alo, ahi, blo, bhi;  // stage 0: the sub-problem a[alo,ahi) x b[blo,bhi); stage 1: (alo, blo) = origin
   uint8_t start, suf, stage, pad;
 };
+template <class T>
 struct State {
-  const uint8_t* a;  // source
-  const uint8_t* b;  // destination
+  const T* a;  // source
+  const T* b;  // destination
   int nd;
   bool overflow;
   Seg d[MAXSEG];
@@ -57,7 +60,8 @@ struct View {  // one instruction of the final script: its text is (op == INS ? 
 ESF_FN int imin(int x, int y) { return x < y ? x : y; }
 ESF_FN int imax(int x, int y) { return x > y ? x : y; }
 
-ESF_FN void push(State& S, int8_t op, int len) {
+template <class T>
+ESF_FN void push(State<T>& S, int8_t op, int len) {
   if (S.nd >= MAXSEG) {
     S.overflow = true;
     return;
@@ -66,7 +70,8 @@ ESF_FN void push(State& S, int8_t op, int len) {
   S.d[S.nd].len = (uint8_t)len;
   ++S.nd;
 }
-ESF_FN void insert_at(State& S, int idx, int8_t op, int len) {
+template <class T>
+ESF_FN void insert_at(State<T>& S, int idx, int8_t op, int len) {
   if (S.nd >= MAXSEG) {
     S.overflow = true;
     return;
@@ -76,41 +81,48 @@ ESF_FN void insert_at(State& S, int idx, int8_t op, int len) {
   S.d[idx].len = (uint8_t)len;
   ++S.nd;
 }
-ESF_FN void erase(State& S, int idx, int cnt) {
+template <class T>
+ESF_FN void erase(State<T>& S, int idx, int cnt) {
   for (int k = idx; k + cnt < S.nd; ++k) S.d[k] = S.d[k + cnt];
   S.nd -= cnt;
 }
 
-ESF_FN int common_prefix(const uint8_t* x, int nx, const uint8_t* y, int ny) {
+template <class T>
+ESF_FN int common_prefix(const T* x, int nx, const T* y, int ny) {
   const int n = imin(nx, ny);
   int i = 0;
   while (i < n && x[i] == y[i]) ++i;
   return i;
 }
-ESF_FN int common_suffix(const uint8_t* x, int nx, const uint8_t* y, int ny) {
+template <class T>
+ESF_FN int common_suffix(const T* x, int nx, const T* y, int ny) {
   const int n = imin(nx, ny);
   int i = 0;
   while (i < n && x[nx - 1 - i] == y[ny - 1 - i]) ++i;
   return i;
 }
-ESF_FN bool same(const uint8_t* x, const uint8_t* y, int n) {
+template <class T>
+ESF_FN bool same(const T* x, const T* y, int n) {
   for (int i = 0; i < n; ++i)
     if (x[i] != y[i]) return false;
   return true;
 }
-ESF_FN int find_in(const uint8_t* hay, int nh, const uint8_t* needle, int nn) {
+template <class T>
+ESF_FN int find_in(const T* hay, int nh, const T* needle, int nn) {
   if (nn == 0) return 0;
   for (int i = 0; i + nn <= nh; ++i)
     if (same(hay + i, needle, nn)) return i;
   return -1;
 }
-ESF_FN int overlap_len(const uint8_t* x, int nx, const uint8_t* y, int ny) {
+template <class T>
+ESF_FN int overlap_len(const T* x, int nx, const T* y, int ny) {
   for (int l = imin(nx, ny); l >= 1; --l)
     if (same(x + nx - l, y, l)) return l;
   return 0;
 }
 // start positions (in a and b) of segment k of the sub-script that starts at index s0 / origin (a0, b0)
-ESF_FN void seg_pos(const State& S, int s0, int k, int a0, int b0, int* pa, int* pb) {
+template <class T>
+ESF_FN void seg_pos(const State<T>& S, int s0, int k, int a0, int b0, int* pa, int* pb) {
   for (int i = s0; i < k; ++i) {
     if (S.d[i].op != INS) a0 += S.d[i].len;
     if (S.d[i].op != DEL) b0 += S.d[i].len;
@@ -121,7 +133,8 @@ ESF_FN void seg_pos(const State& S, int s0, int k, int a0, int b0, int* pa, int*
 
 // Reorder and merge like edit sections, factor out common affixes, slide single edits -- on the
 // tail [s0, nd) of the segment array (cf. merge_pass in editscript.cpp).
-ESF_FN void merge_pass(State& S, int s0, int a0, int b0) {
+template <class T>
+ESF_FN void merge_pass(State<T>& S, int s0, int a0, int b0) {
   bool again = true;
   while (again && !S.overflow) {
     push(S, EQ, 0);
@@ -196,7 +209,7 @@ ESF_FN void merge_pass(State& S, int s0, int a0, int b0) {
       int ka, kb;
       seg_pos(S, s0, k, a0, b0, &ka, &kb);
       const bool del = S.d[k].op == DEL;
-      const uint8_t* base = del ? S.a : S.b;
+      const T* base = del ? S.a : S.b;
       const int pos = del ? ka : kb;
       const int len = S.d[k].len, lp = S.d[k - 1].len, ln = S.d[k + 1].len;
       if (len >= lp && same(base + pos + len - lp, base + pos - lp, lp)) {
@@ -214,7 +227,8 @@ ESF_FN void merge_pass(State& S, int s0, int a0, int b0) {
 
 // Myers O(ND) middle snake on a[alo,ahi) x b[blo,bhi): true + the split point (relative), or false
 // when the strings share nothing (cf. bisect in editscript.cpp).
-ESF_FN bool bisect_split(const State& S, int alo, int ahi, int blo, int bhi, int* sx, int* sy) {
+template <class T>
+ESF_FN bool bisect_split(const State<T>& S, int alo, int ahi, int blo, int bhi, int* sx, int* sy) {
   const int n = ahi - alo, m = bhi - blo;
   const int maxd = (n + m + 1) / 2, off = maxd, vlen = 2 * maxd;
   int8_t vf[MAXLEN * 2 + 4], vr[MAXLEN * 2 + 4];
@@ -224,8 +238,8 @@ ESF_FN bool bisect_split(const State& S, int alo, int ahi, int blo, int bhi, int
   const int delta = n - m;
   const bool odd = (delta % 2) != 0;
   int fs = 0, fe = 0, rs = 0, re = 0;
-  const uint8_t* a = S.a + alo;
-  const uint8_t* b = S.b + blo;
+  const T* a = S.a + alo;
+  const T* b = S.b + blo;
   for (int dd = 0; dd < maxd; ++dd) {
     for (int k = -dd + fs; k <= dd - fe; k += 2) {
       const int ko = off + k;
@@ -279,7 +293,8 @@ ESF_FN bool bisect_split(const State& S, int alo, int ahi, int blo, int bhi, int
 }
 
 // diff(a[0,na), b[0,nb)) with the nested clean-up passes of the recursive formulation.
-ESF_FN void diff_main(State& S, int na, int nb) {
+template <class T>
+ESF_FN void diff_main(State<T>& S, int na, int nb) {
   Frame st[MAXFRAME];
   int sp = 0;
   st[sp++] = Frame{0, (uint8_t)na, 0, (uint8_t)nb, 0, 0, 0, 0};
@@ -339,16 +354,21 @@ ESF_FN void diff_main(State& S, int na, int nb) {
   }
 }
 
-ESF_FN bool ascii_alnum(uint8_t c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
-ESF_FN bool ascii_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+// character classes of the boundary scores: ASCII bytes here (host + device); editscript.cpp supplies the
+// Unicode version for scalar values
+struct AsciiClass {
+  static ESF_FN bool alnum(uint32_t c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+  static ESF_FN bool space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+};
 
 // Boundary quality between two strings (6 = edge ... 0 = inside a word), ASCII restriction of
 // boundary_score in editscript.cpp.
-ESF_FN int boundary_score(const uint8_t* one, int n1, const uint8_t* two, int n2) {
+template <class CC, class T>
+ESF_FN int boundary_score(const T* one, int n1, const T* two, int n2) {
   if (n1 == 0 || n2 == 0) return 6;
-  const uint8_t c1 = one[n1 - 1], c2 = two[0];
-  const bool na1 = !ascii_alnum(c1), na2 = !ascii_alnum(c2);
-  const bool ws1 = na1 && ascii_space(c1), ws2 = na2 && ascii_space(c2);
+  const uint32_t c1 = one[n1 - 1], c2 = two[0];
+  const bool na1 = !CC::alnum(c1), na2 = !CC::alnum(c2);
+  const bool ws1 = na1 && CC::space(c1), ws2 = na2 && CC::space(c2);
   const bool lb1 = ws1 && (c1 == '\n' || c1 == '\r'), lb2 = ws2 && (c2 == '\n' || c2 == '\r');
   const bool tail_blank = (n1 >= 2 && one[n1 - 1] == '\n' && one[n1 - 2] == '\n') ||
                           (n1 >= 3 && one[n1 - 1] == '\n' && one[n1 - 2] == '\r' && one[n1 - 3] == '\n');
@@ -365,13 +385,14 @@ ESF_FN int boundary_score(const uint8_t* one, int n1, const uint8_t* two, int n2
   return 0;
 }
 
-ESF_FN void lossless_shift(State& S) {
+template <class CC, class T>
+ESF_FN void lossless_shift(State<T>& S) {
   for (int k = 1; k + 1 < S.nd; ++k) {
     if (S.d[k - 1].op != EQ || S.d[k + 1].op != EQ) continue;
     int ka, kb;
     seg_pos(S, 0, k, 0, 0, &ka, &kb);
     const bool del = S.d[k].op == DEL;
-    const uint8_t* base = del ? S.a : S.b;
+    const T* base = del ? S.a : S.b;
     int pos = del ? ka : kb;
     const int m = S.d[k].len;
     int l1 = S.d[k - 1].len, l2 = S.d[k + 1].len;
@@ -380,12 +401,12 @@ ESF_FN void lossless_shift(State& S) {
     l1 -= cs;
     l2 += cs;
     int best_l1 = l1, best_l2 = l2;
-    int best = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
+    int best = boundary_score<CC>(base + pos - l1, l1, base + pos, m) + boundary_score<CC>(base + pos, m, base + pos + m, l2);
     while (m > 0 && l2 > 0 && base[pos] == base[pos + m]) {
       ++pos;
       ++l1;
       --l2;
-      const int sc = boundary_score(base + pos - l1, l1, base + pos, m) + boundary_score(base + pos, m, base + pos + m, l2);
+      const int sc = boundary_score<CC>(base + pos - l1, l1, base + pos, m) + boundary_score<CC>(base + pos, m, base + pos + m, l2);
       if (sc >= best) {
         best = sc;
         best_l1 = l1;
@@ -411,7 +432,8 @@ ESF_FN void lossless_shift(State& S) {
   }
 }
 
-ESF_FN void semantic_pass(State& S) {
+template <class CC, class T>
+ESF_FN void semantic_pass(State<T>& S) {
   bool changed = false;
   uint8_t eqs[MAXSEG];
   int ne = 0;
@@ -450,14 +472,14 @@ ESF_FN void semantic_pass(State& S) {
   if (S.overflow) return;
   if (changed) merge_pass(S, 0, 0, 0);
   if (S.overflow) return;
-  lossless_shift(S);
+  lossless_shift<CC>(S);
   for (int k = 1; k < S.nd && !S.overflow; ++k) {
     if (S.d[k - 1].op == DEL && S.d[k].op == INS) {
       int ka, kb;
       seg_pos(S, 0, k - 1, 0, 0, &ka, &kb);
       const int dl = S.d[k - 1].len, il = S.d[k].len;
-      const uint8_t* del = S.a + ka;
-      const uint8_t* ins = S.b + kb;
+      const T* del = S.a + ka;
+      const T* ins = S.b + kb;
       const int o1 = overlap_len(del, dl, ins, il), o2 = overlap_len(ins, il, del, dl);
       if (o1 >= o2) {
         if (o1 * 2 >= dl || o1 * 2 >= il) {
@@ -483,16 +505,17 @@ ESF_FN void semantic_pass(State& S) {
 
 // The edit script of a -> b as views into the two strings.  Returns the number of instructions, or
 // -1 when the pair is outside this implementation's limits (caller falls back to the host).
-ESF_FN int shortest_edit_script(const uint8_t* a, int na, const uint8_t* b, int nb, View* out /* [MAXSEG] */) {
+template <class CC, class T>
+ESF_FN int shortest_edit_script_t(const T* a, int na, const T* b, int nb, View* out /* [MAXSEG] */) {
   if (na > MAXLEN || nb > MAXLEN) return -1;
-  State S;
+  State<T> S;
   S.a = a;
   S.b = b;
   S.nd = 0;
   S.overflow = false;
   diff_main(S, na, nb);
   if (S.overflow) return -1;
-  semantic_pass(S);
+  semantic_pass<CC>(S);
   if (S.overflow) return -1;
   merge_pass(S, 0, 0, 0);
   if (S.overflow) return -1;
@@ -510,6 +533,9 @@ ESF_FN int shortest_edit_script(const uint8_t* a, int na, const uint8_t* b, int 
     if (s.op != DEL) pb += s.len;
   }
   return nv;
+}
+ESF_FN int shortest_edit_script(const uint8_t* a, int na, const uint8_t* b, int nb, View* out /* [MAXSEG] */) {
+  return shortest_edit_script_t<AsciiClass, uint8_t>(a, na, b, nb, out);
 }
 
 // ---- confusable patterns as flat tables (built by Engine::ensure_confusable_table) --------------------

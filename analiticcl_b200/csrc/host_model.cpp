@@ -739,6 +739,15 @@ double HostModel::compute_confusable_weight(const char* input, size_t len, uint6
     }
   }
   if (g_cw_count) g_cw_full.fetch_add(1, std::memory_order_relaxed);
+  {
+    EditView v[64];
+    size_t nv = 0;
+    if (edit_views_fixed(input, len, cand.data(), cand.size(), v, &nv)) {
+      for (const Confusable& c : confusables)
+        if (confusable_found_in_views(c, v, nv)) weight *= c.weight;
+      return weight;
+    }
+  }
   const std::vector<EditInstruction> script = shortest_edit_script(std::string(input, len), cand);
   for (const Confusable& c : confusables)
     if (confusable_found_in(c, script)) weight *= c.weight;

@@ -159,6 +159,9 @@ struct EditView {  // non-owning form of an edit instruction
   size_t n;
 };
 bool confusable_found_in_views(const Confusable& c, const EditView* ref, size_t nref);
+// allocation-free edit script for strings of at most 64 scalars (csrc/editscript_fixed.h over Unicode scalar
+// values); out must hold 64 views; false = outside its limits
+bool edit_views_fixed(const char* src, size_t src_len, const char* dst, size_t dst_len, EditView* out, size_t* nout);
 std::vector<EditInstruction> shortest_edit_script(const std::string& src, const std::string& dst);
 bool parse_confusable(const std::string& editscript, double weight, Confusable* out);
 bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& script);  // src/confusables.rs:47-128
