@@ -58,7 +58,8 @@ class Match(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("queries", "deletion_keys", "probes", "filter_pass", "probe_steps", "postings", "anagram_hits",
-                 "instance_pairs", "dl_pairs", "dl_cells", "survivors", "results", "reruns")]
+                 "instance_pairs", "dl_pairs", "dl_cells", "survivors", "results", "reruns", "dp_pairs",
+                 "dp_cells")]
 
 
 class IndexStats(C.Structure):

@@ -249,7 +249,7 @@ static const uint32_t QF_UNSUPPORTED = 8;   // thresholded anagram distance > AN
 
 struct Counters {
   unsigned long long deletion_keys, probes, filter_pass, table_steps, postings, anagram_hits, instance_pairs, dl_pairs,
-      dl_cells, survivors, results;
+      dl_cells, survivors, results, dp_pairs, dp_cells;
 };
 
 }  // namespace anl

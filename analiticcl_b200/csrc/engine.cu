@@ -754,6 +754,8 @@ bool Engine::counters(DeviceBatch* b, anl_counters* out, std::string* err) {
   out->dl_cells = c.dl_cells;
   out->survivors = c.survivors;
   out->results = c.results;
+  out->dp_pairs = c.dp_pairs;
+  out->dp_cells = c.dp_cells;
   out->reruns = b->reruns;
   return true;
 }

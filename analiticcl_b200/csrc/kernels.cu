@@ -700,8 +700,9 @@ struct __align__(8) SurvRec {
 //   q[256]                         query symbols
 //   cell[(ML+1)][32] (uint32)      per column j, per lane: {t[j-1], lcs[j], lastrow[j], unused}
 //   ring[R][(ML+1)][32] (uint8)    the last R rows of the DL matrix, per lane
+//   pm[256] (uint32)               prefilter: bit j of pm[c] set iff query symbol j equals c
 __host__ __device__ inline size_t k2_warp_bytes(uint32_t ML, uint32_t R) {
-  return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32;
+  return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32 + 1024;
 }
 
 __device__ __forceinline__ double result_score(const BatchParams& bp, double dist, double freq) {
@@ -730,7 +731,9 @@ constexpr int CONF_SETTLED = 0, CONF_QUEUE = 1, CONF_HOST = 2;
 __device__ __forceinline__ int confusable_triage(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
                                                  const uint8_t* __restrict__ b, uint32_t nb) {
   uint32_t hibits = 0;
+#pragma unroll 1
   for (uint32_t i = 0; i < na; ++i) hibits |= a[i];
+#pragma unroll 1
   for (uint32_t i = 0; i < nb; ++i) hibits |= b[i];
   if (hibits & 0x80) return CONF_HOST;
   uint32_t p = 0;
@@ -739,14 +742,17 @@ __device__ __forceinline__ int confusable_triage(const DeviceIndex* ix, const ui
   uint32_t s = 0;
   while (s < m - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
   uint64_t alo = 0, ahi = 0, blo = 0, bhi = 0;
+#pragma unroll 1
   for (uint32_t i = p; i < na - s; ++i) {
     const uint32_t ch = a[i];
     if (ch < 64) alo |= 1ull << ch; else ahi |= 1ull << (ch - 64);
   }
+#pragma unroll 1
   for (uint32_t i = p; i < nb - s; ++i) {
     const uint32_t ch = b[i];
     if (ch < 64) blo |= 1ull << ch; else bhi |= 1ull << (ch - 64);
   }
+#pragma unroll 1
   for (uint32_t k = 0; k < ix->n_conf_pats; ++k) {
     const ConfPat pat = ix->conf_pats[k];
     bool possible = true;
@@ -817,6 +823,7 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
     for (uint32_t i = lane; i < nsurv; i += 32) {
       const SurvRec a = surv[i];
       uint32_t rank = 0;
+#pragma unroll 1
       for (uint32_t j = 0; j < nsurv; ++j) {
         const SurvRec b = surv[j];
         rank += (j != i) && ranks_before(bp, gather_order, b, a);
@@ -935,8 +942,8 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
-             ConfWork* __restrict__ conf_work, uint32_t nq, const uint32_t* __restrict__ hits,
-             const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
+             ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
+             uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
              unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -948,6 +955,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t cell_a = sbase + 256 + lane * 4;                    // + j * 128
   const uint32_t ring_a = sbase + 256 + (ML + 1) * 32 * 4 + lane;    // + slot * rowbytes + j * 32
   const uint32_t rowbytes = (ML + 1) * 32;
+  const uint32_t pm_a = sbase + 256 + (ML + 1) * 32 * 4 + R * rowbytes;  // + symbol * 4
+  for (uint32_t k = lane; k < 256; k += 32) sts_u32(pm_a + k * 4, 0);
+  __syncwarp();
 
   const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
   SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
@@ -957,7 +967,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t nstride = ix->norm_stride;
   const int have_freq = ix->have_freq;
   const uint32_t* __restrict__ gid_of = ix->inst_gid;
-  unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0;
+  unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0, c_dpp = 0, c_dpc = 0;
 
   for (;;) {
     uint32_t qi = 0;
@@ -982,9 +992,98 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     for (uint32_t i = lane; i < Lq; i += 32) sts_u8(sq_a + i, qrow[2 + i]);
     __syncwarp();
     const uint32_t ke = apply_threshold(bp.max_edit, Lq);
-    const uint32_t nh = hit_count[qi];
-    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    uint32_t nh = hit_count[qi];
+    uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
     const double Ld = (double)Lq;
+
+    // ---- prefilter: bit-parallel restricted (OSA) Damerau-Levenshtein distance ------------------------------
+    // Most candidates of the anagram neighbourhood are far beyond the edit-distance threshold.  Hyyro's
+    // bit-vector algorithm gives each lane the OSA distance of its candidate in ~30 instructions per candidate
+    // symbol (against ~30 per matrix CELL for the exact DP below).  OSA and the true (Lowrance-Wagner) distance
+    // DL differ only through transpositions with a gap: such an operation costs c >= 2 in DL and c + 1 when
+    // replaced by plain edits, so OSA <= DL + floor(DL / 2).  Hence OSA > ke + floor(ke / 2) implies DL > ke:
+    // the candidate is dropped here (exact); everything else goes through the exact DP.  Only used when it can
+    // save a whole batch of the DP (more than 32 candidates) and the query fits one 32-bit word.
+    const bool prefilter = Lq <= 32 && nh > 32;
+    uint32_t mysym = 256u + lane;
+    if (prefilter) {
+      if (lane < Lq) mysym = lds_u8(sq_a + lane);
+      const uint32_t mm = __match_any_sync(FULL, mysym);  // the lanes (= query positions) holding the same symbol
+      if (lane < Lq) sts_u32(pm_a + mysym * 4, mm);
+      __syncwarp();
+      const uint32_t top = 1u << (Lq - 1);
+      const uint32_t osa_max = ke + ke / 2;
+      uint32_t w = 0;
+      for (uint32_t hb = 0; hb < nh; hb += 32) {
+        const uint32_t hi = hb + lane;
+        bool valid = hi < nh;
+        uint32_t g = 0, Lc = 0;
+        const uint8_t* row = rows;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          g = hq[hi];
+          row = rows + (size_t)g * nstride;
+          v0 = __ldg(reinterpret_cast<const uint4*>(row));
+          Lc = v0.x & 0xFF;
+          const uint32_t diff = Lq > Lc ? Lq - Lc : Lc - Lq;
+          valid = diff <= ke;  // length pre-check of damerau_levenshtein (src/distance.rs:109-130)
+          if (valid) {
+            c_pairs += 1;
+            c_cells += (unsigned long long)Lq * Lc;
+          } else {
+            Lc = 0;
+          }
+        }
+        uint32_t Lcm = Lc;
+        for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
+        uint32_t D0 = 0, VP = 0xFFFFFFFFu, VN = 0, PMp = 0, sc = Lq;
+        const uint32_t nbytes = Lcm ? Lcm + 2 : 0;  // row bytes to walk: len, flags, symbols
+        for (uint32_t k0 = 0; k0 < nbytes; k0 += 16) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (k0 < Lc + 2 && Lc) v = (k0 == 0) ? v0 : __ldg(reinterpret_cast<const uint4*>(row + k0));
+          uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+          uint32_t pos = k0, steps = min(16u, nbytes - k0);
+          if (k0 == 0) {  // skip the length and flag bytes
+            x = __funnelshift_r(x, y, 16);
+            y = __funnelshift_r(y, z, 16);
+            z = __funnelshift_r(z, t, 16);
+            t >>= 16;
+            pos = 2;
+            steps -= 2;
+          }
+          for (uint32_t st = 0; st < steps; ++st, ++pos) {
+            const uint32_t c = x & 0xFFu;
+            x = __funnelshift_r(x, y, 8);
+            y = __funnelshift_r(y, z, 8);
+            z = __funnelshift_r(z, t, 8);
+            t >>= 8;
+            if (pos < Lc + 2) {  // this lane's candidate still has symbols (never for dropped lanes: Lc = 0)
+              const uint32_t PMj = lds_u32(pm_a + c * 4);
+              const uint32_t TR = ((~D0 & PMj) << 1) & PMp;  // adjacent transposition
+              D0 = TR | (((PMj & VP) + VP) ^ VP) | PMj | VN;
+              const uint32_t HP = VN | ~(D0 | VP);
+              const uint32_t HN = D0 & VP;
+              sc += (HP & top) ? 1u : 0u;
+              sc -= (HN & top) ? 1u : 0u;
+              const uint32_t X = (HP << 1) | 1u;
+              VP = (HN << 1) | ~(D0 | X);
+              VN = X & D0;
+              PMp = PMj;
+            }
+          }
+        }
+        const bool pass = valid && sc <= osa_max;
+        const uint32_t pmask = __ballot_sync(FULL, pass);
+        __syncwarp();  // every lane has read its entry of this batch: the compacted list may overwrite it
+        if (pass) hq[w + __popc(pmask & lanemask_lt())] = g;
+        w += __popc(pmask);
+      }
+      __syncwarp();
+      if (lane < Lq) sts_u32(pm_a + mysym * 4, 0);  // leave the table clean for the next query
+      nh = w;
+      if (lane == 0) hit_count[qi] = w;  // a re-run of this kernel (pool overflow) must see the filtered list
+      __syncwarp();
+    }
     // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
     // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
     const double quot_lane = __ddiv_rn((double)lane, Ld);
@@ -1022,14 +1121,18 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
               }
             }
           }
-          c_pairs += 1;
-          c_cells += (unsigned long long)Lq * Lc;
+          if (!prefilter) {  // (the prefilter pass counted them already)
+            c_pairs += 1;
+            c_cells += (unsigned long long)Lq * Lc;
+          }
         }
       }
       const uint32_t vmask = __ballot_sync(FULL, valid);
       if (vmask == 0) continue;
       uint32_t Lcm = valid ? Lc : 0;
       for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
+      c_dpp += valid ? 1 : 0;
+      c_dpc += (unsigned long long)Lq * Lcm;  // per lane: x 32 lanes in the sum = warp-cells of this batch
 
       // ---- true Damerau-Levenshtein, all lanes in lock-step over (i, j) -----------------------
       // Row i of the matrix lives in ring slot (i mod R), R = max edit distance + 2: only the last
@@ -1159,9 +1262,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   }
 
   if (counters) {
-    unsigned long long v[4] = {c_pairs, c_cells, c_surv, c_res};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    unsigned long long v[6] = {c_pairs, c_cells, c_surv, c_res, c_dpp, c_dpc};
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
       unsigned long long x = v[k];
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
       v[k] = x;
@@ -1171,6 +1274,8 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       atomicAdd(&counters->dl_cells, v[1]);
       atomicAdd(&counters->survivors, v[2]);
       atomicAdd(&counters->results, v[3]);
+      atomicAdd(&counters->dp_pairs, v[4]);
+      atomicAdd(&counters->dp_cells, v[5]);
     }
   }
 }

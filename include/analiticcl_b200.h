@@ -238,6 +238,8 @@ typedef struct anl_counters {
   uint64_t survivors;     /* pairs within max edit distance                                  */
   uint64_t results;       /* variants returned                                               */
   uint64_t reruns;        /* queries re-run because a fixed-capacity buffer overflowed       */
+  uint64_t dp_pairs;      /* pairs the exact DP actually processed (after the bit-parallel OSA prefilter) */
+  uint64_t dp_cells;      /* warp-cells of the exact DP: sum over batches of len_q * longest candidate * 32 lanes */
 } anl_counters;
 anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out);
 
