@@ -705,7 +705,7 @@ __host__ __device__ inline size_t k2_warp_bytes(uint32_t ML, uint32_t R) {
   return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32 + 1024;
 }
 
-__device__ __forceinline__ double result_score(const BatchParams& bp, double dist, double freq) {
+__device__ __noinline__ double result_score(const BatchParams& bp, double dist, double freq) {
   // VariantResult::score (src/types.rs:335-341), evaluated without FMA contraction
   if (!bp.freq_weight_nonzero) return dist;
   return __ddiv_rn(__dadd_rn(dist, __dmul_rn(bp.freq_weight64, freq)), __dadd_rn(1.0, bp.freq_weight64));
@@ -1034,8 +1034,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
             Lc = 0;
           }
         }
-        uint32_t Lcm = Lc;
-        for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
+        const uint32_t Lcm = __reduce_max_sync(FULL, Lc);
         uint32_t D0 = 0, VP = 0xFFFFFFFFu, VN = 0, PMp = 0, sc = Lq;
         const uint32_t nbytes = Lcm ? Lcm + 2 : 0;  // row bytes to walk: len, flags, symbols
         for (uint32_t k0 = 0; k0 < nbytes; k0 += 16) {
@@ -1110,15 +1109,19 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           // stage the candidate's symbols: cell[j].t = t[j-1]
           for (uint32_t j0 = 0; j0 < Lc + 2; j0 += 16) {
             const uint4 v = (j0 == 0) ? v0 : __ldg(reinterpret_cast<const uint4*>(row + j0));
-            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-              const uint32_t bytepos = j0 + b;  // byte in the row; symbol index = bytepos - 2
-              if (bytepos >= 2 && bytepos < Lc + 2) {
-                const uint32_t sym = (wds[b >> 2] >> ((b & 3) * 8)) & 0xFF;
-                // column j = bytepos - 1: {t, lcs = 0, lastrow = 0, D[0][j] = j}
-                sts_u32(cell_a + (bytepos - 1) * 128, sym | ((bytepos - 1) << 24));
-              }
+            // (a rolled loop over a shifting 128-bit window: staging runs once per batch, and the unrolled form
+            // cost far more instruction-cache footprint than it saved in issue slots)
+            uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+            const uint32_t jend = min(j0 + 16, Lc + 2);
+#pragma unroll 1
+            for (uint32_t bytepos = j0; bytepos < jend; ++bytepos) {  // byte in the row; symbol index = bytepos - 2
+              const uint32_t sym = x & 0xFFu;
+              x = __funnelshift_r(x, y, 8);
+              y = __funnelshift_r(y, z, 8);
+              z = __funnelshift_r(z, t, 8);
+              t >>= 8;
+              // column j = bytepos - 1: {t, lcs = 0, lastrow = 0, D[0][j] = j}
+              if (bytepos >= 2) sts_u32(cell_a + (bytepos - 1) * 128, sym | ((bytepos - 1) << 24));
             }
           }
           if (!prefilter) {  // (the prefilter pass counted them already)
@@ -1129,8 +1132,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       }
       const uint32_t vmask = __ballot_sync(FULL, valid);
       if (vmask == 0) continue;
-      uint32_t Lcm = valid ? Lc : 0;
-      for (int o = 16; o > 0; o >>= 1) Lcm = max(Lcm, __shfl_xor_sync(FULL, Lcm, o));
+      const uint32_t Lcm = __reduce_max_sync(FULL, valid ? Lc : 0u);
       c_dpp += valid ? 1 : 0;
       c_dpc += (unsigned long long)Lq * Lcm;  // per lane: x 32 lanes in the sum = warp-cells of this batch
 
