@@ -823,8 +823,8 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
     for (uint32_t i = lane; i < nsurv; i += 32) {
       const SurvRec a = surv[i];
       uint32_t rank = 0;
-#pragma unroll 1
-      for (uint32_t j = 0; j < nsurv; ++j) {
+#pragma unroll 4
+      for (uint32_t j = 0; j < nsurv; ++j) {  // (unrolled by 4: the loads from the scratch list overlap)
         const SurvRec b = surv[j];
         rank += (j != i) && ranks_before(bp, gather_order, b, a);
       }
