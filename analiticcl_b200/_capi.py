@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libanaliticcl_b200.so")
+SO_PATH = os.environ.get("ANL_LIB_PATH") or os.path.join(_HERE, "libanaliticcl_b200.so")  # ANL_LIB_PATH: developer override (A/B of builds)
 
 OK, ERR_INVALID, ERR_IO, ERR_NOT_BUILT, ERR_CUDA, ERR_UNSUPPORTED, ERR_EMPTY_INPUT = range(7)
 THRESHOLD_RATIO, THRESHOLD_RATIO_WITH_LIMIT, THRESHOLD_ABSOLUTE = 0, 1, 2

@@ -33,13 +33,14 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
+    extra = os.environ.get("ANL_NVCC_EXTRA", "").split()  # developer knob: extra nvcc flags (e.g. -DANL_K1_WARPS=4)
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for s in SOURCES:
         o = os.path.join(HERE, "build", s + ".o")
         objs.append(o)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose and s.endswith(".cu") else []) + \
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose and s.endswith(".cu") else []) + \
               ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False

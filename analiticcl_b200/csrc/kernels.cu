@@ -166,8 +166,17 @@ encode_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const ui
 // version stalled 57 % of the time on instruction fetch: 92 KB of SASS against a 32 KB L1.5 I-cache):
 // the exact stage is one non-inlined function, cold general-case code is kept out of line, and
 // per-symbol work runs in short loops over packed bytes instead of unrolled register arrays.
-constexpr int K1_WARPS = 8;
-constexpr int DCH = 64;  // deletion entries with insertion budget buffered per pass
+#ifndef ANL_K1_WARPS
+#define ANL_K1_WARPS 8
+#endif
+#ifndef ANL_K1_MIN_CTAS
+#define ANL_K1_MIN_CTAS 4
+#endif
+#ifndef ANL_K1_DCH
+#define ANL_K1_DCH 64
+#endif
+constexpr int K1_WARPS = ANL_K1_WARPS;
+constexpr int DCH = ANL_K1_DCH;  // deletion entries with insertion budget buffered per pass
 constexpr int SQ = 64;   // staging queue capacity (filter positives waiting for the exact lookup)
 
 // deleted symbols packed one per byte (ascending, unused bytes 0xFF), number of deletions in the top byte
@@ -199,7 +208,7 @@ struct K1Warp {
   uint64_t kF[3];      // exact key of the focus (valid iff kF_ok)
   uint32_t pfx[33];    // exact stage: exclusive prefix of posting counts (+ sentinel)
   uint32_t poff[32];   // exact stage: first posting of each staged node
-  uint32_t stat[6][32];  // lane-local work counters of the non-inlined stages: slots, postings, anagrams, instances, probes, passes
+  uint32_t stat[6];    // per-warp work counters of the non-inlined stages: slots, postings, anagrams, instances, probes, passes
   uint32_t binomL[8];  // C(L, d)
   uint32_t kF_ok, nhits, L, ka;
   uint32_t* hits_q;    // hit list of the current query
@@ -366,10 +375,16 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
       }
     }
   }
-  W.stat[0][lane] += c_steps;
-  W.stat[1][lane] += c_post;
-  W.stat[2][lane] += c_ana;
-  W.stat[3][lane] += c_inst;
+  {
+    const uint32_t r0 = __reduce_add_sync(FULL, c_steps), r1 = __reduce_add_sync(FULL, c_post);
+    const uint32_t r2 = __reduce_add_sync(FULL, c_ana), r3 = __reduce_add_sync(FULL, c_inst);
+    if (lane == 0) {
+      W.stat[0] += r0;
+      W.stat[1] += r1;
+      W.stat[2] += r2;
+      W.stat[3] += r3;
+    }
+  }
   __syncwarp();
 }
 
@@ -445,8 +460,13 @@ __device__ __noinline__ uint32_t insertion_nodes(K1Shared& S, K1Warp& W, uint32_
       }
     }
   }
-  W.stat[4][lane] += probes;
-  W.stat[5][lane] += passes;
+  {
+    const uint32_t r4 = __reduce_add_sync(FULL, probes), r5 = __reduce_add_sync(FULL, passes);
+    if (lane == 0) {
+      W.stat[4] += r4;
+      W.stat[5] += r5;
+    }
+  }
   return sqn;
 }
 
@@ -481,7 +501,7 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   if (threadIdx.x == 0) S.hit_cap = bp.hit_cap;
   const uint32_t lane = lane_id();
   K1Warp& W = S.w[threadIdx.x >> 5];
-  for (int k = 0; k < 6; ++k) W.stat[k][lane] = 0;
+  if (lane < 6) W.stat[lane] = 0;
   __syncthreads();
 
   uint32_t c_dkeys = 0, c_probes = 0, c_pass = 0;
@@ -652,15 +672,17 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   // flush the work counters (one atomic per counter per warp)
   if (counters) {
     // lane-local u32 counts (a warp handles far fewer than 2^32 units per launch)
-    W.stat[4][lane] += c_probes;
-    W.stat[5][lane] += c_pass;
     const uint32_t dk = __reduce_add_sync(FULL, c_dkeys);
-    if (lane == 0) atomicAdd(&counters->deletion_keys, (unsigned long long)dk);
-    const int order[6] = {4, 5, 0, 1, 2, 3};  // probes, filter_pass, table_steps, postings, anagram_hits, instance_pairs
-#pragma unroll 1
-    for (int k = 0; k < 6; ++k) {
-      const uint32_t x = __reduce_add_sync(FULL, W.stat[order[k]][lane]);
-      if (lane == 0) atomicAdd(&counters->probes + k, (unsigned long long)x);
+    const uint32_t pr = __reduce_add_sync(FULL, c_probes), pa = __reduce_add_sync(FULL, c_pass);
+    __syncwarp();
+    if (lane == 0) {
+      atomicAdd(&counters->deletion_keys, (unsigned long long)dk);
+      atomicAdd(&counters->probes, (unsigned long long)(pr + W.stat[4]));
+      atomicAdd(&counters->filter_pass, (unsigned long long)(pa + W.stat[5]));
+      atomicAdd(&counters->table_steps, (unsigned long long)W.stat[0]);
+      atomicAdd(&counters->postings, (unsigned long long)W.stat[1]);
+      atomicAdd(&counters->anagram_hits, (unsigned long long)W.stat[2]);
+      atomicAdd(&counters->instance_pairs, (unsigned long long)W.stat[3]);
     }
   }
 }
@@ -1473,7 +1495,7 @@ static int g_k1_ctas_per_sm = 0;
 static int g_k1_variant = 4;  // resident CTAs per SM the probe kernel is compiled for (register budget); ANL_K1_CTAS=3|4
 typedef void (*ProbeFn)(const DeviceIndex*, const BatchParams, const uint8_t*, const uint32_t*, uint32_t, uint32_t*, uint32_t*,
                         uint32_t*, unsigned int*, Counters*);
-static ProbeFn probe_fn() { return g_k1_variant == 3 ? probe_kernel<3> : probe_kernel<4>; }
+static ProbeFn probe_fn() { return g_k1_variant == 3 ? probe_kernel<3> : probe_kernel<ANL_K1_MIN_CTAS>; }
 
 static uint32_t ring_depth(const BatchParams& bp) {
   // rows needed = max edit distance + 2; thresholds are capped at 255 but anything beyond 14 is
