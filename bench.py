@@ -289,14 +289,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop()
-    launches += per_pass * e2e_steps * max(1, -(-n // (1 << 17)))  # the batch call works in chunks of 131072 queries
+    # the batch call works in chunks of 131072 queries; each chunk also launches the encode kernel
+    launches += (per_pass + 1) * e2e_steps * max(1, -(-n // (1 << 17)))
     ist = m.index_stats()
     max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
     stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
-    h2d = n * stride                       # encoded query rows
-    if spec["confusables"]:
-        h2d += len(blob) + 4 * (n + 1)     # raw query text + offsets for the device confusable stage
-    d2h = n * (16 + 4 + 4) + 16 * int(n_results) + 16  # per-query headers/flags/hit counts + packed 16-byte records
+    # the query text + u32 offsets go up (the rows are encoded on the device); headers, flags, hit counts,
+    # encode status and the packed 16-byte records come back
+    h2d = len(blob) + 4 * (n + 1)
+    d2h = n * (16 + 4 + 4 + 1) + 16 * int(n_results) + 16
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s, probe_ms, score_ms], dtype=torch.float64, device="cuda")
