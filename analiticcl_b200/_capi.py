@@ -115,6 +115,8 @@ SIGNATURES = {
     "anl_match_set_get": (_i32, [_vp, _u64, _P(Match)]),
     "anl_match_set_free": (None, [_vp]),
     "anl_match_set_lookup_counts": (None, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
+    "anl_debug_find_boundaries": (_i64, [_cp, _sz, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz]),
+    "anl_debug_segment_text": (_i64, [_cp, _sz, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32), _sz]),
     "anl_device_batch_create": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_device_batch_run": (_i32, [_vp, _vp, _vp]),
     "anl_device_batch_timings": (_i32, [_vp, _vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),

@@ -558,6 +558,33 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   *out = ms;
   return ANL_OK;
 }
+// ---- test hooks for the host-side producer (no model, no GPU needed) ------------------------------------------
+int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin, uint64_t* end, int32_t* strength, size_t cap) {
+  const std::string t(text ? text : "", len);
+  const std::vector<Boundary>& b = find_boundaries(t);
+  for (size_t i = 0; i < b.size() && i < cap; ++i) {
+    begin[i] = b[i].begin;
+    end[i] = b[i].end;
+    strength[i] = b[i].strength;
+  }
+  return (int64_t)b.size();
+}
+int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end, uint32_t* order,
+                               uint32_t* batch, size_t cap) {
+  const std::string t(text ? text : "", len);
+  SegmentedText st;
+  segment_text(t, max_ngram, &st);
+  const size_t nb = st.batch_first.size() - 1;
+  for (size_t b = 0; b < nb; ++b)
+    for (uint64_t k = st.batch_first[b]; k < st.batch_first[b + 1] && k < cap; ++k) {
+      begin[k] = st.segs[k].begin;
+      end[k] = st.segs[k].end;
+      order[k] = st.segs[k].n;
+      batch[k] = (uint32_t)b;
+    }
+  return (int64_t)st.segs.size();
+}
+
 uint64_t anl_match_set_len(const anl_match_set* ms) { return ms ? ms->matches.size() : 0; }
 anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out) {
   if (!ms || !out || i >= ms->matches.size()) return fail(ANL_ERR_INVALID, "match index out of range");

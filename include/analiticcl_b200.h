@@ -206,6 +206,14 @@ void anl_match_set_free(anl_match_set* ms);
  * producer de-duplicates identical segments inside a window). */
 void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_lookups, uint64_t* distinct_strings);
 
+/* Test hooks for the host-side batch producer of find_all_matches (no model or GPU needed): the boundaries
+ * (src/search.rs:190-258; strength 1 weak, 2 normal, 3 hard) and the n-gram segments per hard-delimited batch
+ * (src/search.rs:262-312, src/lib.rs:1822-1903) exactly as anl_find_all_matches produces them.  Both return
+ * the number of items (may exceed cap; only cap items are written). */
+int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin, uint64_t* end, int32_t* strength, size_t cap);
+int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end, uint32_t* order,
+                               uint32_t* batch, size_t cap);
+
 /* ---- device-resident path (what bench.py times as `value`; plumbing for multi-GPU hosts) ------ */
 typedef struct anl_device_batch anl_device_batch; /* encoded queries + result buffers in HBM */
 /* Encodes on the host (alphabet normalisation) and uploads; buffers are sized for n_queries. */
