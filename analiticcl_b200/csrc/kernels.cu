@@ -718,7 +718,7 @@ struct __align__(8) SurvRec {
   uint32_t pad;
 };
 
-// shared memory of one warp (dynamic; sized by the longest indexed entry ML and the ring depth R)
+// shared memory of one warp (dynamic; sized by the number of matrix columns `ML` a launch handles and the ring depth R)
 //   q[256]                         query symbols
 //   cell[(ML+1)][32] (uint32)      per column j, per lane: {t[j-1], lcs[j], lastrow[j], unused}
 //   ring[R][(ML+1)][32] (uint8)    the last R rows of the DL matrix, per lane
@@ -961,13 +961,13 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
   return (lane == 0 && fits) ? n : 0;
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 6)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
              ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
              uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
-             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R) {
+             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -980,6 +980,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t pm_a = sbase + 256 + (ML + 1) * 32 * 4 + R * rowbytes;  // + symbol * 4
   for (uint32_t k = lane; k < 256; k += 32) sts_u32(pm_a + k * 4, 0);
   __syncwarp();
+  const uint32_t max_len = ix->max_len;
 
   const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
   SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
@@ -997,7 +998,17 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= nq) break;
     const uint32_t flags = qflags[qi];
-    if (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
+    const bool skip = (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) != 0;
+    {
+      // Queries are split over launches by the number of matrix columns they can need (longest admissible
+      // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
+      // with a fraction of the shared memory, i.e. more resident warps.
+      const uint32_t q0 = qlist ? qlist[qi] : qi;
+      const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
+      const uint32_t need = skip ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
+      if (need < need_min || need > need_max) continue;
+    }
+    if (skip) {
       if (lane == 0) {
         OutHead h;
         h.max_freq = 0.0;
@@ -1547,13 +1558,6 @@ static int k2_ctas_per_sm(uint32_t R, size_t smem) {
   return n;
 }
 
-// The score kernel's grid is fixed per (model, params) so its scratch can be allocated once.
-static long long k2_grid(const DeviceIndex& h_ix, const BatchParams& bp, int sm_count) {
-  const uint32_t R = ring_depth(bp);
-  const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
-  return (long long)sm_count * k2_ctas_per_sm(R, smem);
-}
-
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries) {
   // one survivor list + one sorted copy per resident warp.  Upper bound on resident warps: 16 CTAs/SM
   // exceeds any smem-limited occupancy here; the launcher never starts more warps than queries.
@@ -1563,15 +1567,12 @@ size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queri
   return ctas * K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
 }
 
-cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
-                         int sm_count, cudaStream_t stream) {
-  if (lb.n == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // work counter, pool cursor, confusable queue
-  if (e != cudaSuccess) return e;
+static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
+                                      cudaStream_t stream, uint32_t cols, uint32_t need_min, uint32_t need_max, unsigned int* work) {
   const uint32_t R = ring_depth(bp);
-  const size_t smem = k2_warp_bytes(h_ix.max_len, R) * K2_WARPS;
+  const size_t smem = k2_warp_bytes(cols, R) * K2_WARPS;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  long long grid = k2_grid(h_ix, bp, sm_count);
+  long long grid = (long long)sm_count * k2_ctas_per_sm(R, smem);
   const long long cap = (long long)sm_count * 16;
   if (grid > cap) grid = cap;
   long long want = ((long long)lb.n + K2_WARPS - 1) / K2_WARPS;
@@ -1580,9 +1581,31 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
   score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.conf_work,
                                                                 lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
-                                                                lb.out_head, scratch, lb.work + 1, lb.work + 2, lb.counters,
-                                                                h_ix.max_len, R);
+                                                                lb.out_head, scratch, work, lb.work + 2, lb.counters, cols, R,
+                                                                need_min, need_max);
   return cudaGetLastError();
+}
+
+// Queries whose matrices fit K2_SHORT_COLS columns (nearly all of them) run in a launch with a small
+// shared-memory footprint and therefore more resident warps; the rest in a second launch sized by the
+// longest indexed entry.  Both launches walk the whole batch and skip the queries of the other class.
+constexpr uint32_t K2_SHORT_COLS = 24;
+
+cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
+                         int sm_count, cudaStream_t stream) {
+  if (lb.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // work counter, pool cursor, confusable queue
+  if (e != cudaSuccess) return e;
+  const uint32_t ML = h_ix.max_len;
+  if (ML <= K2_SHORT_COLS + 4) return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, 0, ML, lb.work + 1);
+  e = launch_score_class(d_ix, bp, lb, sm_count, stream, K2_SHORT_COLS, 0, K2_SHORT_COLS, lb.work + 1);
+  if (e != cudaSuccess) return e;
+  // the longest query of the batch bounds what the second class can need (a symbol takes at least one byte)
+  const uint32_t longest = bp.query_stride - 2, kmax = ring_depth(bp) - 2;
+  if (std::min<uint32_t>(ML, longest + kmax) <= K2_SHORT_COLS) return cudaSuccess;
+  e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
+  if (e != cudaSuccess) return e;
+  return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work);
 }
 
 // The device confusable stage: edit scripts of the queued pairs, then re-rank / crop / cut-off per query.
