@@ -245,6 +245,7 @@ struct __attribute__((aligned(16))) OutHead {
 static const uint32_t QF_EMPTY = 1;         // empty query
 static const uint32_t QF_HIT_OVERFLOW = 2;  // more instance hits than hit_cap: rerun with larger cap
 static const uint32_t QF_OUT_OVERFLOW = 4;  // the packed result pool was exhausted: rerun the score kernel with a larger pool
+static const uint32_t QF_PREFILTERED = 16;   // prefilter_kernel compacted this query's hit list (and counted its pairs)
 static const uint32_t QF_UNSUPPORTED = 8;   // thresholded anagram distance > ANL_MAX_K or enumeration too large
 
 struct Counters {

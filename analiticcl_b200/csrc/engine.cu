@@ -696,6 +696,7 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   CU_TRY(cudaEventRecord(ev[0], stream));
   CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[1], stream));
+  CU_TRY(launch_prefilter(d_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[2], stream));
   CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, stream));

@@ -722,9 +722,8 @@ struct __align__(8) SurvRec {
 //   q[256]                         query symbols
 //   cell[(ML+1)][32] (uint32)      per column j, per lane: {t[j-1], lcs[j], lastrow[j], unused}
 //   ring[R][(ML+1)][32] (uint8)    the last R rows of the DL matrix, per lane
-//   pm[256] (uint32)               prefilter: bit j of pm[c] set iff query symbol j equals c
 __host__ __device__ inline size_t k2_warp_bytes(uint32_t ML, uint32_t R) {
-  return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32 + 1024;
+  return 256 + (size_t)(ML + 1) * 32 * 4 + (size_t)R * (ML + 1) * 32;
 }
 
 __device__ __noinline__ double result_score(const BatchParams& bp, double dist, double freq) {
@@ -961,86 +960,50 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
   return (lane == 0 && fits) ? n : 0;
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32, 6)
-score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
-             const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
-             ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
-             uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
-             uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
-             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// ================================================================================================
+// Kernel 2a: prefilter -- bit-parallel restricted (OSA) Damerau-Levenshtein distance
+// ================================================================================================
+// Most candidates of the anagram neighbourhood are far beyond the edit-distance threshold.  Hyyro's
+// bit-vector algorithm gives each lane the OSA distance of its candidate in ~30 instructions per candidate
+// symbol (against ~30 per matrix CELL for the exact DP of the score kernel).  OSA and the true
+// (Lowrance-Wagner) distance DL differ only through transpositions with a gap: such an operation costs
+// c >= 2 in DL and c + 1 when replaced by plain edits, so OSA <= DL + floor(DL / 2).  Hence
+// OSA > ke + floor(ke / 2) implies DL > ke: the candidate is dropped here (exact) and the hit list is
+// compacted in place; everything else goes through the exact DP.  Only queries with more than one batch of
+// candidates (it can save a whole batch of the DP) and at most 32 symbols (one 32-bit word) are filtered;
+// they get QF_PREFILTERED.  A kernel of its own: a tiny loop and 1.3 KB of shared memory per warp, so it runs
+// at full occupancy instead of sharing the instruction cache and the occupancy of the score kernel.
+constexpr int KF_WARPS = 8;
+__global__ void __launch_bounds__(KF_WARPS * 32)
+prefilter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+                 const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* hits, uint32_t* hit_count, uint32_t* qflags,
+                 unsigned int* work, Counters* counters) {
+  __shared__ uint32_t pm_s[KF_WARPS][256];  // per warp: bit j of pm[c] set iff query symbol j equals c
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
-  // per-warp shared memory by shared-window address: sq (query symbols), cell[(ML+1)][32] words, ring[R][(ML+1)][32] bytes
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * (uint32_t)k2_warp_bytes(ML, R);
-  const uint32_t sq_a = sbase;
-  const uint32_t cell_a = sbase + 256 + lane * 4;                    // + j * 128
-  const uint32_t ring_a = sbase + 256 + (ML + 1) * 32 * 4 + lane;    // + slot * rowbytes + j * 32
-  const uint32_t rowbytes = (ML + 1) * 32;
-  const uint32_t pm_a = sbase + 256 + (ML + 1) * 32 * 4 + R * rowbytes;  // + symbol * 4
+  const uint32_t pm_a = (uint32_t)__cvta_generic_to_shared(&pm_s[warp][0]);
   for (uint32_t k = lane; k < 256; k += 32) sts_u32(pm_a + k * 4, 0);
   __syncwarp();
-  const uint32_t max_len = ix->max_len;
-
-  const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
-  SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
-  SurvRec* sorted = surv + bp.hit_cap;
-
   const uint8_t* __restrict__ rows = ix->inst_rows;
   const uint32_t nstride = ix->norm_stride;
-  const int have_freq = ix->have_freq;
-  const uint32_t* __restrict__ gid_of = ix->inst_gid;
-  unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0, c_dpp = 0, c_dpc = 0;
-
+  unsigned long long c_pairs = 0, c_cells = 0;
   for (;;) {
     uint32_t qi = 0;
     if (lane == 0) qi = atomicAdd(work, 1u);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= nq) break;
     const uint32_t flags = qflags[qi];
-    const bool skip = (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) != 0;
-    {
-      // Queries are split over launches by the number of matrix columns they can need (longest admissible
-      // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
-      // with a fraction of the shared memory, i.e. more resident warps.
-      const uint32_t q0 = qlist ? qlist[qi] : qi;
-      const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
-      const uint32_t need = skip ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
-      if (need < need_min || need > need_max) continue;
-    }
-    if (skip) {
-      if (lane == 0) {
-        OutHead h;
-        h.max_freq = 0.0;
-        h.offset = 0;
-        h.count = 0;
-        out_head[qi] = h;
-      }
-      continue;
-    }
+    if (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED | QF_PREFILTERED)) continue;
+    uint32_t nh = hit_count[qi];
     const uint32_t q = qlist ? qlist[qi] : qi;
     const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
     const uint32_t Lq = qrow[0];
-    const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
-    for (uint32_t i = lane; i < Lq; i += 32) sts_u8(sq_a + i, qrow[2 + i]);
-    __syncwarp();
+    if (Lq > 32 || nh <= 32) continue;
     const uint32_t ke = apply_threshold(bp.max_edit, Lq);
-    uint32_t nh = hit_count[qi];
     uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
-    const double Ld = (double)Lq;
-
-    // ---- prefilter: bit-parallel restricted (OSA) Damerau-Levenshtein distance ------------------------------
-    // Most candidates of the anagram neighbourhood are far beyond the edit-distance threshold.  Hyyro's
-    // bit-vector algorithm gives each lane the OSA distance of its candidate in ~30 instructions per candidate
-    // symbol (against ~30 per matrix CELL for the exact DP below).  OSA and the true (Lowrance-Wagner) distance
-    // DL differ only through transpositions with a gap: such an operation costs c >= 2 in DL and c + 1 when
-    // replaced by plain edits, so OSA <= DL + floor(DL / 2).  Hence OSA > ke + floor(ke / 2) implies DL > ke:
-    // the candidate is dropped here (exact); everything else goes through the exact DP.  Only used when it can
-    // save a whole batch of the DP (more than 32 candidates) and the query fits one 32-bit word.
-    const bool prefilter = Lq <= 32 && nh > 32;
-    uint32_t mysym = 256u + lane;
-    if (prefilter) {
-      if (lane < Lq) mysym = lds_u8(sq_a + lane);
+    uint32_t mysym = 256u + lane;  // (lanes beyond the query get unique values: they match nobody)
+    {
+      if (lane < Lq) mysym = qrow[2 + lane];
       const uint32_t mm = __match_any_sync(FULL, mysym);  // the lanes (= query positions) holding the same symbol
       if (lane < Lq) sts_u32(pm_a + mysym * 4, mm);
       __syncwarp();
@@ -1116,6 +1079,88 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       if (lane == 0) hit_count[qi] = w;  // a re-run of this kernel (pool overflow) must see the filtered list
       __syncwarp();
     }
+    if (lane == 0) qflags[qi] = flags | QF_PREFILTERED;
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      c_pairs += __shfl_xor_sync(FULL, c_pairs, o);
+      c_cells += __shfl_xor_sync(FULL, c_cells, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->dl_pairs, c_pairs);
+      atomicAdd(&counters->dl_cells, c_cells);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32, 6)
+score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+             const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+             ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
+             uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
+             uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
+             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  // per-warp shared memory by shared-window address: sq (query symbols), cell[(ML+1)][32] words, ring[R][(ML+1)][32] bytes
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * (uint32_t)k2_warp_bytes(ML, R);
+  const uint32_t sq_a = sbase;
+  const uint32_t cell_a = sbase + 256 + lane * 4;                    // + j * 128
+  const uint32_t ring_a = sbase + 256 + (ML + 1) * 32 * 4 + lane;    // + slot * rowbytes + j * 32
+  const uint32_t rowbytes = (ML + 1) * 32;
+  const uint32_t max_len = ix->max_len;
+
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
+  SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
+  SurvRec* sorted = surv + bp.hit_cap;
+
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  const int have_freq = ix->have_freq;
+  const uint32_t* __restrict__ gid_of = ix->inst_gid;
+  unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0, c_dpp = 0, c_dpc = 0;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t flags = qflags[qi];
+    const bool skip = (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) != 0;
+    {
+      // Queries are split over launches by the number of matrix columns they can need (longest admissible
+      // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
+      // with a fraction of the shared memory, i.e. more resident warps.
+      const uint32_t q0 = qlist ? qlist[qi] : qi;
+      const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
+      const uint32_t need = skip ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
+      if (need < need_min || need > need_max) continue;
+    }
+    if (skip) {
+      if (lane == 0) {
+        OutHead h;
+        h.max_freq = 0.0;
+        h.offset = 0;
+        h.count = 0;
+        out_head[qi] = h;
+      }
+      continue;
+    }
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t Lq = qrow[0];
+    const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
+    for (uint32_t i = lane; i < Lq; i += 32) sts_u8(sq_a + i, qrow[2 + i]);
+    __syncwarp();
+    const uint32_t ke = apply_threshold(bp.max_edit, Lq);
+    const uint32_t nh = hit_count[qi];
+    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    const double Ld = (double)Lq;
+
+    // (candidates far beyond the edit distance were already dropped by prefilter_kernel when the query has more
+    // than one batch of them; it also counted the pairs of those queries)
+    const bool prefilter = (flags & QF_PREFILTERED) != 0;
     // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
     // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
     const double quot_lane = __ddiv_rn((double)lane, Ld);
@@ -1565,6 +1610,20 @@ size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queri
   const size_t want = ((size_t)n_queries + K2_WARPS - 1) / K2_WARPS;
   if (want < ctas) ctas = std::max<size_t>(want, 1);
   return ctas * K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
+}
+
+cudaError_t launch_prefilter(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
+                             cudaStream_t stream) {
+  if (lb.n <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
+  if (e != cudaSuccess) return e;
+  long long grid = (long long)sm_count * 8;  // 64 warps per SM
+  const long long want = ((long long)lb.n + KF_WARPS - 1) / KF_WARPS;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  prefilter_kernel<<<(unsigned)grid, KF_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count, lb.qflags,
+                                                                 lb.work, lb.counters);
+  return cudaGetLastError();
 }
 
 static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,

@@ -32,6 +32,9 @@ cudaError_t launch_encode(const DeviceIndex* d_ix, const BatchParams& bp, const 
 // Candidate generation: deletion neighbourhood x insertion multisets -> Bloom -> table -> postings.
 cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
+// Bit-parallel OSA prefilter of the hit lists (exact rejection of candidates far beyond the edit distance);
+// optional, run between launch_probe and launch_score.
+cudaError_t launch_prefilter(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream);
 // Scoring (true Damerau-Levenshtein, LCS, prefix, suffix, case, f64 score) fused with ranking,
 // cropping and cut-off.
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
