@@ -113,6 +113,7 @@ SIGNATURES = {
     "anl_find_all_matches": (_i32, [_vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
     "anl_match_set_len": (_u64, [_vp]),
     "anl_match_set_get": (_i32, [_vp, _u64, _P(Match)]),
+    "anl_kernel_launches": (_u64, []),
     "anl_match_set_free": (None, [_vp]),
     "anl_match_set_lookup_counts": (None, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "anl_debug_find_boundaries": (_i64, [_cp, _sz, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz]),

@@ -40,6 +40,7 @@ static anl_status fail(anl_status code, const std::string& msg) {
 extern "C" {
 
 const char* anl_last_error(void) { return g_last_error.c_str(); }
+uint64_t anl_kernel_launches(void) { return kernel_launches(); }
 const char* anl_version(void) { return "analiticcl_b200 0.1 (reference: analiticcl 0.4.9; sm_100a)"; }
 
 void anl_weights_default(anl_weights* w) {

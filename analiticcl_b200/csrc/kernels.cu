@@ -23,6 +23,10 @@
 
 namespace anl {
 
+// process-wide count of kernel launches issued by this library (bench.py reports it as gpu_launches)
+static unsigned long long g_kernel_launches = 0;
+unsigned long long kernel_launches() { return g_kernel_launches; }
+
 long long merge_grid(int sm_count, uint32_t n);
 
 #define FULL 0xFFFFFFFFu
@@ -1532,6 +1536,7 @@ cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, c
                                                              qflags_in, qflags, out, out_head,
                                                              reinterpret_cast<SurvRec*>(scratch), scratch_cap, work + 1,
                                                              work + 2);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 long long merge_grid(int sm_count, uint32_t n) {
@@ -1575,6 +1580,7 @@ cudaError_t launch_encode(const DeviceIndex* d_ix, const BatchParams& bp, const 
                           uint8_t* rows, uint8_t* status, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   encode_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_ix, bp, qblob, qboff, n, rows, status);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 
@@ -1592,6 +1598,7 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (grid < 1) grid = 1;
   probe_fn()<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
                                                                             lb.hit_count, lb.qflags, lb.work, lb.counters);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 
@@ -1623,6 +1630,7 @@ cudaError_t launch_prefilter(const DeviceIndex* d_ix, const BatchParams& bp, con
   if (grid < 1) grid = 1;
   prefilter_kernel<<<(unsigned)grid, KF_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count, lb.qflags,
                                                                  lb.work, lb.counters);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 
@@ -1642,6 +1650,7 @@ static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams
                                                                 lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
                                                                 lb.out_head, scratch, work, lb.work + 2, lb.counters, cols, R,
                                                                 need_min, need_max);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 
@@ -1677,6 +1686,7 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
   unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
   if (blocks < 1) blocks = 1;
   confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream) {
@@ -1690,6 +1700,7 @@ cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm
   if (grid < 1) grid = 1;
   finish_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(bp, lb.n, lb.out, lb.out_head, reinterpret_cast<SurvRec*>(lb.scratch),
                                                               bp.hit_cap, lb.work);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 

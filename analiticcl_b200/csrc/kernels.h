@@ -47,6 +47,7 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream);
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
 cudaError_t configure_kernels();
+unsigned long long kernel_launches();  // process-wide count of kernel launches issued by this library
 // Lexicon-sharded mode: merge the all-gathered per-shard survivor lists (see merge_kernel).
 cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, const OutRec* recs_all,
                          const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,

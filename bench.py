@@ -255,6 +255,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
+    launches0 = L.anl_kernel_launches()
     ev0.record(stream)
     for _ in range(args.steps):
         check(L.anl_device_batch_run(m._h, batch, sh))
@@ -266,14 +267,13 @@ def run_ours(args):
     probe_ms, score_ms, rescore_ms = pm.value, sm_.value, xm.value
     ctr = _capi.Counters()
     check(L.anl_device_batch_counters(m._h, batch, C.byref(ctr)))
-    # kernels per pass: probe + score, plus confusable + finish when the model has confusables
-    per_pass = 4 if spec["confusables"] else 2
-    launches = per_pass * args.steps
+    launches = L.anl_kernel_launches() - launches0  # counted by the library: every kernel of the timed passes
 
     # ---- e2e: host buffers through the public C-ABI call ------------------------------------------------
     e2e_steps = min(args.steps, args.e2e_steps)  # 0 = skip (profiling runs)
     n_results = 0
     e2e_s = float("nan")
+    launches_e2e0 = 0
     if e2e_steps > 0:
         rs = C.c_void_p()
         check(L.anl_find_variants_batch(m._h, blob, offs_p, n, C.byref(sp.data), C.byref(rs)))  # warm-up
@@ -281,6 +281,7 @@ def run_ours(args):
         L.anl_result_set_free(rs)
         barrier()
         torch.cuda.synchronize()
+        launches_e2e0 = L.anl_kernel_launches()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             rs = C.c_void_p()
@@ -289,8 +290,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop()
-    # the batch call works in chunks of 131072 queries; each chunk also launches the encode kernel
-    launches += (per_pass + 1) * e2e_steps * max(1, -(-n // (1 << 17)))
+    if e2e_steps > 0:
+        launches += L.anl_kernel_launches() - launches_e2e0  # the batch call works in chunks of 131072 queries
     ist = m.index_stats()
     max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
     stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
@@ -402,6 +403,7 @@ def run_search(args):
         L.anl_match_set_free(ms)
     sampler = ClockSampler(0)
     sampler.start()
+    launches0 = L.anl_kernel_launches()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ms, n = once()
@@ -425,7 +427,7 @@ def run_search(args):
                                   "window, result assembly); query = one n-gram segment lookup"},
         "tokens_per_s": n_tokens / dt,
         "e2e": {"value": lookups / dt, "unit": "queries/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
-        "gpu_launches": None, "clocks": clocks,
+        "gpu_launches": L.anl_kernel_launches() - launches0, "clocks": clocks,
     }
     print(json.dumps(line))
 
@@ -502,6 +504,7 @@ def run_sharded(args):
     sampler.start()
     dist.barrier()
     torch.cuda.synchronize()
+    launches0 = L.anl_kernel_launches()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
@@ -527,7 +530,7 @@ def run_sharded(args):
             "kernels": {"probe_ms": probe_ms, "score_ms": score_ms,
                         "exchange_and_merge_ms": dt_max * 1e3 - probe_ms - score_ms,
                         "nvlink_bytes_received_per_rank": bytes_exchanged[0]},
-            "gpu_launches": 3 * args.steps, "clocks": clocks,
+            "gpu_launches": L.anl_kernel_launches() - launches0, "clocks": clocks,
         }
         print(json.dumps(line))
     L.anl_device_batch_free(m._h, batch)

@@ -114,6 +114,8 @@ void anl_vocab_params_default(anl_vocab_params* p);
 
 const char* anl_last_error(void);
 const char* anl_version(void);
+/* Number of CUDA kernels this library has launched in this process so far (all models). */
+uint64_t anl_kernel_launches(void);
 
 /* ---- model construction ------------------------------------------------------------------ */
 /* VariantModel::new (src/lib.rs:104): alphabet TSV file + weights. */
