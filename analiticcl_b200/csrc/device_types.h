@@ -143,6 +143,24 @@ struct AlphaFirst {
 // per-query result of the encode kernel
 static const uint8_t ENC_OK = 0, ENC_TOO_LONG_EMPTY = 1, ENC_TOO_LONG_UNSUPPORTED = 2;
 
+// ---- split probe path: staged nodes in a global queue between the Bloom stage and the exact stage --------
+// One node X = D + I' of some query's neighbourhood that passed the Bloom filter (40 bytes).
+struct __attribute__((aligned(8))) QEntry {
+  uint64_t h;       // mhash(X)
+  uint64_t dprod;   // product of the primes of the deleted symbols
+  uint64_t dd;      // deleted symbols, packed (count in the top byte)
+  uint32_t t;       // index of I' in the multiset table (unused when isz == 0)
+  uint32_t qi;      // query (position in the launch)
+  uint8_t isz, imax;
+  uint8_t pad[6];
+};
+// what the exact stage needs to know about a query
+struct __attribute__((aligned(16))) QCtx {
+  uint64_t kF[3];   // exact key of the focus
+  uint32_t L;       // symbols of the query
+  uint32_t ka_ok;   // max anagram distance | (key valid) << 8
+};
+
 // ---- per-model constant data ------------------------------------------------------------------------
 struct DeviceIndex {
   const Slot* table;

@@ -405,6 +405,8 @@ void Engine::destroy_batch(DeviceBatch* b) {
   if (b->d_qboff) cudaFree(b->d_qboff);
   if (b->d_conf_work) cudaFree(b->d_conf_work);
   if (b->d_enc_status) cudaFree(b->d_enc_status);
+  if (b->d_queue) cudaFree(b->d_queue);
+  if (b->d_qctx) cudaFree(b->d_qctx);
   if (b->h_enc_status) cudaFreeHost(b->h_enc_status);
   for (void* p : {(void*)b->d_rows, (void*)b->d_hits, (void*)b->d_hit_count, (void*)b->d_qflags, (void*)b->d_out,
                   (void*)b->d_gid, (void*)b->d_head, b->d_scratch, (void*)b->d_work, (void*)b->d_counters, (void*)b->rr_qlist,
@@ -471,8 +473,8 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
     b->cap_scratch = scratch;
   }
   if (!b->d_work) {
-    if (!dev_realloc(&b->d_work, 4, err)) return false;
-    if (!pinned_realloc(&b->h_work, 4, err)) return false;
+    if (!dev_realloc(&b->d_work, 8, err)) return false;
+    if (!pinned_realloc(&b->h_work, 8, err)) return false;
     if (!dev_realloc(&b->d_counters, 1, err)) return false;
   }
   return true;
@@ -546,6 +548,33 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, std::max<uint64_t>(1024, n * per_query));
   if (!ensure_capacity(b, (uint32_t)n, stride, bp.hit_cap, pool_cap, score_scratch_bytes(bp, sm_count_, (uint32_t)n), err)) return fail();
   bp.pool_cap = b->cap_pool;
+  {
+    // split probe path (Bloom stage -> global queue of staged nodes -> exact stage): capacity per query by the
+    // anagram distance; an overflow is detected after the run and answered by the fused kernel
+    static int split_on = -1;
+    if (split_on < 0) {
+      const char* e = getenv("ANL_SPLIT");
+      split_on = e ? (atoi(e) != 0) : 1;
+    }
+    b->split = split_on && !bp.stop_at_exact && n > 0;
+    if (b->split) {
+      const uint32_t kcap = threshold_cap(p.max_anagram_distance);
+      uint64_t per_query = kcap <= 3 ? 160 : (kcap == 4 ? 320 : 640);
+      if (const char* e = getenv("ANL_QUEUE_PER_QUERY")) per_query = (uint64_t)std::max(1, atoi(e));
+      const uint64_t want = std::min<uint64_t>(0x7FFFFFF0ull, n * per_query + 4096);
+      std::string e2;
+      bool okq = true;
+      if (want > b->cap_queue || !b->d_queue) {
+        okq = dev_realloc(&b->d_queue, (size_t)want, &e2);
+        b->cap_queue = okq ? (size_t)want : 0;
+      }
+      if (okq && (n > b->cap_qctx || !b->d_qctx)) {
+        okq = dev_realloc(&b->d_qctx, (size_t)n, &e2);
+        b->cap_qctx = okq ? (size_t)n : 0;
+      }
+      if (!okq) b->split = false;  // not enough memory for the queue: the fused kernel needs none
+    }
+  }
   b->sharded = hm_->index.n_shards > 1;
   b->merged = false;
   b->final_mode = hm_->confusables.empty() ? FINISH_FULL : (hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP);
@@ -665,6 +694,11 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   lb.qblob = b->has_qblob ? reinterpret_cast<const uint8_t*>(b->d_qblob) : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
   lb.conf_work = b->dev_conf ? b->d_conf_work : nullptr;
+  if (b->split) {
+    lb.queue = b->d_queue;
+    lb.queue_cap = (uint32_t)std::min<size_t>(b->cap_queue, 0x7FFFFFF0u);
+    lb.qctx = b->d_qctx;
+  }
   lb.n = b->n;
   lb.hits = b->d_hits;
   lb.hit_count = b->d_hit_count;
@@ -923,7 +957,7 @@ bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* e
   unsigned int total = 0;
   for (int attempt = 0;; ++attempt) {
     CU_TRY(cudaStreamWaitEvent(st, b->last_done, 0));
-    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     if (n) {
       CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -933,6 +967,22 @@ bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* e
     CU_TRY(cudaStreamSynchronize(st));
     if (b->dev_encode)
       for (uint32_t i = 0; i < n; ++i) b->host_flags[i] = b->h_enc_status[i];
+    if (b->split && n && b->h_work[4] > std::min<size_t>(b->cap_queue, 0x7FFFFFF0u)) {
+      // the staged-node queue was too small for this batch: run it again with the fused probe kernel
+      if (profile_enabled()) fprintf(stderr, "[anl profile] staged-node queue overflow (%u > %zu): fused rerun\n", b->h_work[4], b->cap_queue);
+      b->split = false;
+      LaunchBuffers lbq = launch_buffers(b);
+      lbq.counters = nullptr;
+      CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
+      CU_TRY(launch_prefilter(d_ix_, b->bp, lbq, sm_count_, st));
+      CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
+      CU_TRY(launch_confusables(d_ix_, b->bp, lbq, sm_count_, st));
+      CU_TRY(launch_finish(b->bp, lbq, sm_count_, st));
+      CU_TRY(cudaEventRecord(b->last_done, st));
+      b->reruns += 1;
+      --attempt;
+      continue;
+    }
     total = n ? b->h_work[2] : 0;
     if (total <= b->bp.pool_cap || b->merged) break;
     if (attempt >= 2) {

@@ -53,6 +53,10 @@ struct DeviceBatch {
   char* h_qblob = nullptr;      // pinned staging of the query text
   size_t cap_qblob = 0, cap_qboff = 0;
   bool has_qblob = false;
+  QEntry* d_queue = nullptr;        // split probe path: staged nodes between the Bloom stage and the exact stage
+  QCtx* d_qctx = nullptr;           //                   per-query context of the exact stage
+  size_t cap_queue = 0, cap_qctx = 0;
+  bool split = false;               // use the split probe path for this batch
   uint8_t* d_enc_status = nullptr;  // per query: ENC_* result of the encode kernel
   uint8_t* h_enc_status = nullptr;
   bool dev_encode = false;          // the rows of this batch were encoded on the device

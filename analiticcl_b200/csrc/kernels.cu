@@ -222,6 +222,11 @@ struct K1Shared {
   DeviceIndex ix;     // block-local copy of the model constants (pointers, masks, small tables)
   uint64_t rnd[256];  // class_rnd of every symbol
   uint32_t hit_cap;
+  // split path: staged nodes go to a global queue (exact_kernel consumes it) instead of the warp's own exact stage
+  QEntry* queue;
+  unsigned int* queue_cursor;
+  uint32_t queue_cap;
+  uint32_t cur_qi[K1_WARPS];  // the query each warp is working on
   K1Warp w[K1_WARPS];
 };
 
@@ -398,6 +403,25 @@ __device__ __forceinline__ void stage(K1Shared& S, K1Warp& W, uint32_t& sqn, boo
   const uint32_t ballot = __ballot_sync(FULL, pass);
   if (ballot == 0) return;
   const uint32_t lane = lane_id();
+  if (S.queue) {
+    // split path: one reservation per warp in the global queue
+    uint32_t pos = 0;
+    if (lane == 0) pos = atomicAdd(S.queue_cursor, (unsigned int)__popc(ballot));
+    pos = __shfl_sync(FULL, pos, 0) + __popc(ballot & lanemask_lt());
+    if (pass && pos < S.queue_cap) {
+      QEntry e;
+      e.h = h;
+      e.dprod = dprod;
+      e.dd = dd;
+      e.t = t;
+      e.qi = S.cur_qi[threadIdx.x >> 5];
+      e.isz = (uint8_t)isz;
+      e.imax = (uint8_t)imax;
+      for (int k = 0; k < 6; ++k) e.pad[k] = 0;
+      S.queue[pos] = e;
+    }
+    return;
+  }
   if (pass) {
     SEntry s;
     s.h = h;
@@ -493,9 +517,15 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(K1_WARPS * 32, MIN_CTAS)
 probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
-             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
+             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters, QEntry* queue, uint32_t queue_cap,
+             QCtx* __restrict__ qctx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K1Shared& S = *reinterpret_cast<K1Shared*>(smem_raw);
+  if (threadIdx.x == 0) {
+    S.queue = queue;
+    S.queue_cursor = work + 4;
+    S.queue_cap = queue_cap;
+  }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(ix);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.ix);
@@ -530,6 +560,7 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       W.L = L;
       W.ka = ka;
       W.hits_q = hits + (size_t)qi * bp.hit_cap;
+      S.cur_qi[threadIdx.x >> 5] = qi;
     }
     __syncwarp();
     if (L == 0) {
@@ -573,6 +604,15 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           W.kF[1] = k1;
           W.kF[2] = k2;
           W.kF_ok = ok ? 1u : 0u;
+          if (queue) {
+            QCtx c;
+            c.kF[0] = k0;
+            c.kF[1] = k1;
+            c.kF[2] = k2;
+            c.L = L;
+            c.ka_ok = ka | (ok ? 0x100u : 0u);
+            qctx[qi] = c;
+          }
         }
       }
       __syncwarp();
@@ -665,10 +705,15 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     }
     __syncwarp();
     if (lane == 0) {
-      const uint32_t n = W.nhits;
-      hit_count[qi] = n;
-      if (n > bp.hit_cap) flags |= QF_HIT_OVERFLOW;
-      qflags[qi] = flags;
+      if (queue) {
+        // split path: exact_kernel counts the hits (hit_count was zeroed) and raises QF_HIT_OVERFLOW itself
+        if (flags) atomicOr(qflags + qi, flags);
+      } else {
+        const uint32_t n = W.nhits;
+        hit_count[qi] = n;
+        if (n > bp.hit_cap) flags |= QF_HIT_OVERFLOW;
+        qflags[qi] = flags;
+      }
     }
     __syncwarp();
   }
@@ -687,6 +732,433 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       atomicAdd(&counters->postings, (unsigned long long)W.stat[1]);
       atomicAdd(&counters->anagram_hits, (unsigned long long)W.stat[2]);
       atomicAdd(&counters->instance_pairs, (unsigned long long)W.stat[3]);
+    }
+  }
+}
+
+// ================================================================================================
+// Kernel 1a (split probe path): the Bloom stage on its own
+// ================================================================================================
+// The same enumeration as probe_kernel (deletion sets in colex order, insertion multisets, one 64-bit add and
+// one Bloom word per node), but every node that passes the filter is appended to a global queue for
+// exact_kernel instead of being looked up by this warp.  Without the exact stage the kernel needs 2 KB of
+// shared memory per warp and few registers, so twice as many warps are resident: the stage is bound by the
+// latency of the Bloom word loads (ncu: long scoreboard), and more warps in flight is what hides it.
+constexpr int KB_WARPS = 8;
+#ifndef ANL_KB_MIN_CTAS
+#define ANL_KB_MIN_CTAS 6
+#endif
+struct KBWarp {
+  DEntry dch[DCH];
+  uint32_t binomL[8];
+  uint8_t sorted[256];
+};
+struct KBShared {
+  uint64_t rnd[256];
+  uint32_t prime_of[256];
+  uint64_t charcount_mask[4];
+  uint32_t mset_end[ANL_MAX_K + 1];
+  KBWarp w[KB_WARPS];
+};
+
+__device__ __forceinline__ void queue_push(QEntry* __restrict__ queue, uint32_t queue_cap, unsigned int* cursor, bool pass, uint64_t h,
+                                           uint64_t dprod, uint64_t dd, uint32_t t, uint32_t isz, uint32_t imax, uint32_t qi) {
+  const uint32_t ballot = __ballot_sync(FULL, pass);
+  if (ballot == 0) return;
+  uint32_t pos = 0;
+  if (lane_id() == 0) pos = atomicAdd(cursor, (unsigned int)__popc(ballot));
+  pos = __shfl_sync(FULL, pos, 0) + __popc(ballot & lanemask_lt());
+  if (pass && pos < queue_cap) {
+    QEntry e;
+    e.h = h;
+    e.dprod = dprod;
+    e.dd = dd;
+    e.t = t;
+    e.qi = qi;
+    e.isz = (uint8_t)isz;
+    e.imax = (uint8_t)imax;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) e.pad[k] = 0;
+    queue[pos] = e;
+  }
+}
+
+__global__ void __launch_bounds__(KB_WARPS * 32, ANL_KB_MIN_CTAS)
+bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+             const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters,
+             QEntry* __restrict__ queue, uint32_t queue_cap, QCtx* __restrict__ qctx) {
+  __shared__ KBShared S;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    S.rnd[i] = class_rnd(i);
+    S.prime_of[i] = ix->prime_of[i];
+  }
+  if (threadIdx.x < 4) S.charcount_mask[threadIdx.x] = ix->charcount_mask[threadIdx.x];
+  if (threadIdx.x <= (unsigned)ANL_MAX_K) S.mset_end[threadIdx.x] = ix->mset_end[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = lane_id();
+  KBWarp& W = S.w[threadIdx.x >> 5];
+  const uint64_t* __restrict__ bloom = ix->bloom;
+  const uint64_t bloom_wmask = ix->bloom_mask;
+  const MsetEntry* __restrict__ mset = ix->mset;
+  const uint32_t max_cc = ix->max_charcount;
+  const int sd = ix->sd;
+  const uint32_t* __restrict__ colex2 = ix->colex2;
+  const uint32_t* __restrict__ colex3 = ix->colex3;
+  const uint32_t* __restrict__ binom = ix->binom;
+  unsigned int* cursor = work + 4;
+  uint32_t c_dkeys = 0, c_probes = 0, c_pass = 0;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t L = qrow[0];
+    uint32_t flags = 0;
+    const uint32_t ka = L ? apply_threshold(bp.max_anagram, L) : 0;
+    if (L == 0) {
+      flags = QF_EMPTY;
+    } else if (ka > (uint32_t)ANL_MAX_K) {
+      flags = QF_UNSUPPORTED;
+    } else if (L <= max_cc + ka) {  // else every candidate would be longer than any indexed entry
+      // sort the query symbols (rank sort) so equal symbols are adjacent; mhash(F) on the way
+      uint64_t hF = 0;
+#pragma unroll 1
+      for (uint32_t i = lane; i < L; i += 32) {
+        const uint8_t v = qrow[2 + i];
+        uint32_t r = 0;
+#pragma unroll 1
+        for (uint32_t j = 0; j < L; ++j) {
+          const uint8_t u = qrow[2 + j];
+          r += (u < v) || (u == v && j < i);
+        }
+        W.sorted[r] = v;
+        hF += S.rnd[v];
+      }
+      for (int o = 16; o > 0; o >>= 1) hF += __shfl_xor_sync(FULL, hF, o);
+      const uint32_t dmax = min(ka, L - 1);
+      if (lane <= dmax) W.binomL[lane] = __ldg(binom + L * 8 + lane);
+      __syncwarp();
+      {
+        // exact key of the focus for the exact stage (every lane computes the same value; lane 0 publishes it)
+        uint64_t k0 = 1, k1 = 0, k2 = 0, pp = 1;
+        bool ok = true;
+#pragma unroll 1
+        for (uint32_t p = 0; p < L && ok; ++p) {
+          pp *= S.prime_of[W.sorted[p]];
+          if (pp >> 53) {
+            ok = mul192(k0, k1, k2, pp);
+            pp = 1;
+          }
+        }
+        if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+        if (lane == 0) {
+          QCtx c;
+          c.kF[0] = k0;
+          c.kF[1] = k1;
+          c.kF[2] = k2;
+          c.L = L;
+          c.ka_ok = ka | (ok ? 0x100u : 0u);
+          qctx[qi] = c;
+        }
+      }
+      uint64_t total64 = 0;
+#pragma unroll 1
+      for (uint32_t d = 0; d <= dmax; ++d) total64 += W.binomL[d];
+      if (total64 > 0x7FFFFFFFull) {
+        flags = QF_UNSUPPORTED;
+      } else {
+        const uint32_t total = (uint32_t)total64;
+        const bool fast = L <= (uint32_t)COLEX_N;
+        uint32_t nD = 0;
+        for (uint32_t base = 0; base < total; base += 32) {
+          const uint32_t t = base + lane;
+          bool ok = t < total;
+          uint32_t d = 0;
+          uint64_t h = hF, dprod = 1, dd = 0x00FFFFFFFFFFFFFFULL;
+          if (ok) {
+            uint32_t rem = t;
+            while (rem >= W.binomL[d]) {
+              rem -= W.binomL[d];
+              ++d;
+            }
+            uint64_t pk = rem;
+            if (fast && d == 2) pk = __ldg(colex2 + rem);
+            else if (fast && d == 3) pk = __ldg(colex3 + rem);
+            else if (d >= 2) pk = unrank_general(binom, L, d, rem);
+            uint32_t prev = 0xFFFFFFFFu;
+#pragma unroll 1
+            for (uint32_t i = 0; i < d; ++i) {
+              const uint32_t p = (uint32_t)(pk >> (8 * i)) & 0xFF;
+              const uint32_t sym = W.sorted[p];
+              if (p > 0 && W.sorted[p - 1] == sym && prev + 1 != p) ok = false;  // canonical: leading part of a run only
+              prev = p;
+              h -= S.rnd[sym];
+              dprod *= S.prime_of[sym];
+              dd = (dd & ~(0xFFULL << (8 * i))) | ((uint64_t)sym << (8 * i));
+            }
+            dd |= (uint64_t)d << 56;
+          }
+          c_dkeys += ok;
+          const uint32_t cx = L - d;
+          const bool probe = ok && (ccbit(S.charcount_mask, cx) || (sd == 1 && ka > d && ccbit(S.charcount_mask, cx + 1)));
+          bool pass = false;
+          if (probe) {
+            const uint64_t word = __ldg(bloom + fp_index(h, bloom_wmask));
+            const uint64_t m = bloom_mask(h);
+            pass = (word & m) == m;
+          }
+          c_probes += probe;
+          c_pass += pass;
+          queue_push(queue, queue_cap, cursor, pass, h, dprod, dd, 0, 0, 0, qi);
+          // entries with budget for insertions beyond the table's own depth are buffered for the insertion pass
+          const bool ins = ok && (int)ka - (int)d - sd >= 1;
+          const uint32_t ballot = __ballot_sync(FULL, ins);
+          if (ins) {
+            DEntry de;
+            de.h = h;
+            de.dprod = dprod;
+            de.dd = dd;
+            W.dch[nD + __popc(ballot & lanemask_lt())] = de;
+          }
+          nD += __popc(ballot);
+          __syncwarp();
+          if (nD > DCH - 32 || (base + 32 >= total && nD)) {
+            // the nodes X = D + I', |I'| >= 1, of the buffered entries; lanes stride over the multiset table
+            for (uint32_t e = 0; e < nD; ++e) {
+              const DEntry de = W.dch[e];  // warp-uniform broadcast
+              const uint32_t dn = dd_count(de.dd);
+              const int jmax = (int)ka - (int)dn - sd;
+              for (int j = 1; j <= jmax; ++j) {
+                const uint32_t cxj = L - dn + j;
+                const bool useful = (sd == 0) ? ccbit(S.charcount_mask, cxj) : ccbit(S.charcount_mask, cxj + 1);
+                if (!useful) continue;
+                const uint32_t lo = S.mset_end[j - 1], hi = S.mset_end[j];
+                for (uint32_t mb = lo; mb < hi; mb += 32) {
+                  const uint32_t mt = mb + lane;
+                  bool active = mt < hi;
+                  uint64_t hx = de.h;
+                  uint32_t imax = 0;
+                  if (active) {
+                    const ulonglong2 me = __ldg(reinterpret_cast<const ulonglong2*>(mset + mt));  // {hsum, cls[6] | j | maxcls}
+                    hx += me.x;
+                    imax = (uint32_t)(me.y >> 56);
+#pragma unroll 1
+                    for (uint32_t b = 0; b < dn; ++b) active = active && !has_byte6(me.y, (uint32_t)(de.dd >> (8 * b)) & 0xFF);
+                  }
+                  bool px = false;
+                  if (active) {
+                    const uint64_t word = __ldg(bloom + fp_index(hx, bloom_wmask));
+                    const uint64_t m = bloom_mask(hx);
+                    px = (word & m) == m;
+                  }
+                  c_probes += active;
+                  c_pass += px;
+                  queue_push(queue, queue_cap, cursor, px, hx, de.dprod, de.dd, mt, (uint32_t)j, imax, qi);
+                }
+              }
+            }
+            nD = 0;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (lane == 0 && flags) atomicOr(qflags + qi, flags);  // exact_kernel counts the hits and raises QF_HIT_OVERFLOW
+    __syncwarp();
+  }
+  if (counters) {
+    const uint32_t dk = __reduce_add_sync(FULL, c_dkeys);
+    const uint32_t pr = __reduce_add_sync(FULL, c_probes), pa = __reduce_add_sync(FULL, c_pass);
+    if (lane == 0) {
+      atomicAdd(&counters->deletion_keys, (unsigned long long)dk);
+      atomicAdd(&counters->probes, (unsigned long long)pr);
+      atomicAdd(&counters->filter_pass, (unsigned long long)pa);
+    }
+  }
+}
+
+// ================================================================================================
+// Kernel 1b (split probe path): the exact stage over the global queue of staged nodes
+// ================================================================================================
+// The same two steps as exact_stage -- slot lookup by fingerprint, then every posting verified against the
+// canonical-generation rules and the anagram's exact key -- but over the staged nodes of ALL queries, one node
+// per lane: every round has 32 busy lanes (inside probe_kernel a warp drains only its own query's nodes, often
+// a handful), the Bloom stage no longer carries this code through its instruction cache, and both kernels run
+// at the occupancy that suits them.  Hits are appended to the queries' hit lists with one atomic per anagram.
+constexpr int KX_WARPS = 8;
+struct KXWarp {
+  QEntry e[32];
+  uint64_t nprod[32];
+  uint32_t pfx[33];
+  uint32_t poff[32];
+};
+// General exact verification without the warp's sorted copy of the query (cold, cf. verify_general).
+__device__ __noinline__ bool verify_general_q(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qrow, uint32_t L,
+                                              const QEntry& s, uint32_t x, const Key192& ck) {
+  uint64_t k0 = 1, k1 = 0, k2 = 0, pp = 1;
+  bool ok = true;
+  const uint32_t d = dd_count(s.dd);
+  uint32_t used = 0;  // deleted symbols already dropped
+#pragma unroll 1
+  for (uint32_t p = 0; p < L && ok; ++p) {
+    const uint32_t sym = qrow[2 + p];
+    bool dropped = false;
+#pragma unroll 1
+    for (uint32_t b = 0; b < d && !dropped; ++b)
+      if (!((used >> b) & 1u) && ((s.dd >> (8 * b)) & 0xFF) == sym) {
+        used |= 1u << b;
+        dropped = true;
+      }
+    if (dropped) continue;
+    pp *= ix->prime_of[sym];
+    if (pp >> 53) {
+      ok = mul192(k0, k1, k2, pp);
+      pp = 1;
+    }
+  }
+  if (ok && s.isz) {
+    const uint64_t cls = __ldg(reinterpret_cast<const uint64_t*>(ix->mset + s.t) + 1);
+#pragma unroll 1
+    for (uint32_t a = 0; a < s.isz && ok; ++a) {
+      pp *= ix->prime_of[(cls >> (8 * a)) & 0xFF];
+      if (pp >> 53) {
+        ok = mul192(k0, k1, k2, pp);
+        pp = 1;
+      }
+    }
+  }
+  if (ok && x != POST_SELF) {
+    pp *= ix->prime_of[x];
+    if (pp >> 53) {
+      ok = mul192(k0, k1, k2, pp);
+      pp = 1;
+    }
+  }
+  if (ok && pp > 1) ok = mul192(k0, k1, k2, pp);
+  return ok && ck.w0 == k0 && ck.w1 == k1 && ck.w2 == k2;
+}
+
+__global__ void __launch_bounds__(KX_WARPS * 32)
+exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+             const uint32_t* __restrict__ qlist, const QEntry* __restrict__ queue, uint32_t queue_cap,
+             const QCtx* __restrict__ qctx, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
+             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
+  __shared__ KXWarp sm[KX_WARPS];
+  KXWarp& W = sm[threadIdx.x >> 5];
+  const uint32_t lane = lane_id();
+  const uint32_t total = min(work[4], queue_cap);
+  const Slot* __restrict__ table = ix->table;
+  const uint64_t table_mask = ix->table_mask;
+  const int sd = ix->sd;
+  uint32_t c_steps = 0, c_post = 0, c_ana = 0, c_inst = 0;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work + 5, 32u);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= total) break;
+    const uint32_t i = base + lane;
+    uint32_t poff = 0, pcnt = 0;
+    if (i < total) {
+      const QEntry e = queue[i];
+      W.e[lane] = e;
+      const uint64_t fp = e.h;
+      uint64_t idx = fp_index(fp, table_mask);
+      for (;;) {
+        const Slot sl = table[idx];
+        ++c_steps;
+        if (sl.post_cnt == 0) break;
+        if (sl.fp == fp) {
+          poff = sl.post_off;
+          pcnt = sl.post_cnt;
+          break;
+        }
+        idx = (idx + 1) & table_mask;
+      }
+      if (pcnt) {
+        uint64_t np = 1;
+        if (e.isz) {
+          const uint64_t cls = __ldg(reinterpret_cast<const uint64_t*>(ix->mset + e.t) + 1);  // cls[6] | j | maxcls
+#pragma unroll 1
+          for (uint32_t a = 0; a < e.isz; ++a) np = (np >> 53) ? 0 : np * ix->prime_of[(cls >> (8 * a)) & 0xFF];
+          if (np >> 53) np = 0;
+        }
+        W.nprod[lane] = np;
+      }
+    }
+    uint32_t incl = pcnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t npost = __shfl_sync(FULL, incl, 31);
+    W.pfx[lane] = incl - pcnt;
+    W.poff[lane] = poff;
+    __syncwarp();
+    for (uint32_t t0 = 0; t0 < npost; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      if (t < npost) {
+        uint32_t owner = 0;  // largest lane whose exclusive prefix is <= t
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (W.pfx[owner + step] <= t) owner += step;
+        const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
+        const QEntry& s = W.e[owner];
+        const uint32_t r = __ldg(ix->post_ana + p);
+        const uint32_t x = __ldg(ix->post_cls + p);
+        ++c_post;
+        const QCtx cx = qctx[s.qi];
+        const uint32_t ka = cx.ka_ok & 0xFFu;
+        const uint64_t dd = s.dd;
+        const uint32_t isz = s.isz;
+        bool ok;
+        if (x == POST_SELF) {
+          ok = (sd == 0) || (isz == 0);
+        } else {
+          // budget left for the last insertion; ascending insertion order; never re-insert a deleted class
+          ok = ka >= dd_count(dd) + isz + 1 && (isz == 0 || x >= s.imax) && !has_byte6(dd, x);
+        }
+        if (ok) {
+          const Key192 ck = ix->ana_key[r];
+          const uint64_t np = W.nprod[owner];
+          bool match;
+          if ((cx.ka_ok & 0x100u) && np != 0) {
+            const uint64_t n = (x == POST_SELF) ? np : np * ix->prime_of[x];
+            uint64_t a0, a1, a2, a3, b0, b1, b2, b3;
+            mul192x64(ck.w0, ck.w1, ck.w2, s.dprod, a0, a1, a2, a3);
+            mul192x64(cx.kF[0], cx.kF[1], cx.kF[2], n, b0, b1, b2, b3);
+            match = a0 == b0 && a1 == b1 && a2 == b2 && a3 == b3;
+          } else {
+            const uint32_t q = qlist ? qlist[s.qi] : s.qi;
+            match = verify_general_q(ix, queries + (size_t)q * bp.query_stride, cx.L, s, x, ck);
+          }
+          if (match) {  // else: fingerprint collision
+            const uint32_t io = __ldg(ix->ana_inst_off + r), ie = __ldg(ix->ana_inst_off + r + 1);
+            const uint32_t n = ie - io;
+            ++c_ana;
+            c_inst += n;
+            const uint32_t pos = atomicAdd(hit_count + s.qi, n);
+            uint32_t* hq = hits + (size_t)s.qi * bp.hit_cap;
+            for (uint32_t k = 0; k < n; ++k)
+              if (pos + k < bp.hit_cap) hq[pos + k] = io + k;
+            if (pos + n > bp.hit_cap) atomicOr(qflags + s.qi, QF_HIT_OVERFLOW);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (counters) {
+    const uint32_t r0 = __reduce_add_sync(FULL, c_steps), r1 = __reduce_add_sync(FULL, c_post);
+    const uint32_t r2 = __reduce_add_sync(FULL, c_ana), r3 = __reduce_add_sync(FULL, c_inst);
+    if (lane == 0) {
+      atomicAdd(&counters->table_steps, (unsigned long long)r0);
+      atomicAdd(&counters->postings, (unsigned long long)r1);
+      atomicAdd(&counters->anagram_hits, (unsigned long long)r2);
+      atomicAdd(&counters->instance_pairs, (unsigned long long)r3);
     }
   }
 }
@@ -1555,7 +2027,7 @@ size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap) {
 static int g_k1_ctas_per_sm = 0;
 static int g_k1_variant = 4;  // resident CTAs per SM the probe kernel is compiled for (register budget); ANL_K1_CTAS=3|4
 typedef void (*ProbeFn)(const DeviceIndex*, const BatchParams, const uint8_t*, const uint32_t*, uint32_t, uint32_t*, uint32_t*,
-                        uint32_t*, unsigned int*, Counters*);
+                        uint32_t*, unsigned int*, Counters*, QEntry*, uint32_t, QCtx*);
 static ProbeFn probe_fn() { return g_k1_variant == 3 ? probe_kernel<3> : probe_kernel<ANL_K1_MIN_CTAS>; }
 
 static uint32_t ring_depth(const BatchParams& bp) {
@@ -1588,16 +2060,48 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
                          int sm_count, cudaStream_t stream) {
   (void)h_ix;
   if (lb.n == 0) return cudaSuccess;
+  // the split path does not serve StopAtExactMatch (the enumeration depends on the exact stage's answer)
+  const bool split = lb.queue != nullptr && lb.queue_cap > 0 && lb.qctx != nullptr && !bp.stop_at_exact;
   cudaError_t e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  int per_sm = g_k1_ctas_per_sm > 0 ? g_k1_ctas_per_sm : 1;
-  // persistent grid: a whole number of CTAs per SM, no more warps than queries
-  long long want = ((long long)lb.n + K1_WARPS - 1) / K1_WARPS;
-  long long grid = (long long)sm_count * per_sm;
-  if (grid > want) grid = want;
-  if (grid < 1) grid = 1;
-  probe_fn()<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
-                                                                            lb.hit_count, lb.qflags, lb.work, lb.counters);
+  if (split) {
+    e = cudaMemsetAsync(lb.work + 4, 0, 2 * sizeof(unsigned int), stream);  // queue length, exact-stage work counter
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lb.hit_count, 0, (size_t)lb.n * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lb.qflags, 0, (size_t)lb.n * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (split) {
+    static int kb_ctas = 0;
+    if (kb_ctas == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kb_ctas, bloom_kernel, KB_WARPS * 32, 0) != cudaSuccess || kb_ctas < 1)
+        kb_ctas = 1;
+    }
+    long long want = ((long long)lb.n + KB_WARPS - 1) / KB_WARPS;
+    long long grid = (long long)sm_count * kb_ctas;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    bloom_kernel<<<(unsigned)grid, KB_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.qflags, lb.work, lb.counters,
+                                                               lb.queue, lb.queue_cap, lb.qctx);
+    ++g_kernel_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else {
+    int per_sm = g_k1_ctas_per_sm > 0 ? g_k1_ctas_per_sm : 1;
+    // persistent grid: a whole number of CTAs per SM, no more warps than queries
+    long long want = ((long long)lb.n + K1_WARPS - 1) / K1_WARPS;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    probe_fn()<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
+                                                                            lb.hit_count, lb.qflags, lb.work, lb.counters, nullptr, 0,
+                                                                            nullptr);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+  }
+  exact_kernel<<<(unsigned)sm_count * 8, KX_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.queue, lb.queue_cap, lb.qctx,
+                                                                     lb.hits, lb.hit_count, lb.qflags, lb.work, lb.counters);
   ++g_kernel_launches;
   return cudaGetLastError();
 }

@@ -22,7 +22,11 @@ struct LaunchBuffers {
   uint32_t* out_gid = nullptr;       // optional (sharded mode): global gather id per pool record
   OutHead* out_head = nullptr;       // [n] per-query header: offset / count into the pool, max_freq
   void* scratch = nullptr;           // score kernel scratch: score_scratch_bytes(...)
-  unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor, [3] confusable queue length (zeroed by the launchers)
+  unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor, [3] confusable queue length,
+                                     // [4] staged-node queue length, [5] exact-stage work counter (zeroed by the launchers)
+  QEntry* queue = nullptr;           // optional (split probe path): staged nodes of the whole launch, queue_cap entries
+  uint32_t queue_cap = 0;
+  QCtx* qctx = nullptr;              //          per-query context for the exact stage, [n]
   Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
 };
 
@@ -30,6 +34,9 @@ struct LaunchBuffers {
 cudaError_t launch_encode(const DeviceIndex* d_ix, const BatchParams& bp, const uint8_t* qblob, const uint32_t* qboff, uint32_t n,
                           uint8_t* rows, uint8_t* status, cudaStream_t stream);
 // Candidate generation: deletion neighbourhood x insertion multisets -> Bloom -> table -> postings.
+// With lb.queue set (and no stop-at-exact-match) the work is split over two kernels: the Bloom stage appends
+// the nodes that pass the filter to a global queue, and exact_kernel looks them up one node per lane.  The
+// caller must check work[4] <= queue_cap afterwards (else: run again without the queue).
 cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
 // Bit-parallel OSA prefilter of the hit lists (exact rejection of candidates far beyond the edit distance);

@@ -154,6 +154,17 @@ def test_capacity_overflow_rerun(A, eng_oracle, monkeypatch):
     assert_same(got, exp, qs, "overflow")
 
 
+@pytest.mark.parametrize("per_query", ["3", "100000"], ids=["queue overflow -> fused rerun", "roomy queue"])
+def test_split_probe_queue(A, eng, eng_oracle, monkeypatch, per_query):
+    """Split probe path (Bloom stage -> global queue of staged nodes -> exact stage): a queue that is too small is
+    detected after the run and answered by the fused probe kernel; either way the results are the oracle's."""
+    monkeypatch.setenv("ANL_QUEUE_PER_QUERY", per_query)
+    qs = workloads.misspellings(workloads.read_words("eng"), 700, 4321)
+    sp = A.SearchParameters()
+    assert_same(eng.find_variants_raw(qs, sp), eng_oracle.find_variants_batch(qs, to_orc_params(sp)), qs, "split queue")
+    monkeypatch.setenv("ANL_SPLIT", "0")  # (read once per process: only effective if this is the first batch)
+
+
 def test_nld_frequency_parity(A, nld_pair):
     m, o = nld_pair
     qs = workloads.ocr_noise(workloads.read_words("nld"), 1500, 2003)
