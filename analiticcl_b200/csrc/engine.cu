@@ -561,7 +561,8 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       const uint32_t kcap = threshold_cap(p.max_anagram_distance);
       uint64_t per_query = kcap <= 3 ? 160 : (kcap == 4 ? 320 : 640);
       if (const char* e = getenv("ANL_QUEUE_PER_QUERY")) per_query = (uint64_t)std::max(1, atoi(e));
-      const uint64_t want = std::min<uint64_t>(0x7FFFFFF0ull, n * per_query + 4096);
+      // (+ one reservation chunk per resident warp of the Bloom stage)
+      const uint64_t want = std::min<uint64_t>(0x7FFFFFF0ull, n * per_query + 4096 + 148ull * 64 * 128);
       std::string e2;
       bool okq = true;
       if (want > b->cap_queue || !b->d_queue) {

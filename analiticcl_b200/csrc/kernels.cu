@@ -761,25 +761,48 @@ struct KBShared {
   KBWarp w[KB_WARPS];
 };
 
-__device__ __forceinline__ void queue_push(QEntry* __restrict__ queue, uint32_t queue_cap, unsigned int* cursor, bool pass, uint64_t h,
-                                           uint64_t dprod, uint64_t dd, uint32_t t, uint32_t isz, uint32_t imax, uint32_t qi) {
+// Queue space is reserved in chunks of QCHUNK entries per warp: one global atomic per chunk instead of one per
+// push (with a single shared cursor the pushes ran at the same-address atomic rate of the L2 -- 24 % of the
+// kernel's stall samples).  A push that does not fit the current chunk spills its tail into a fresh chunk, so
+// chunks are filled completely; only a warp's last chunk keeps a hole, marked with QHOLE entries at exit.
+constexpr uint32_t QCHUNK = 128;
+constexpr uint32_t QHOLE = 0xFFFFFFFFu;  // QEntry.qi of an unused slot
+struct QCursor {
+  uint32_t pos, end;  // next free slot and end of this warp's current chunk (warp-uniform)
+};
+__device__ __forceinline__ void queue_push(QEntry* __restrict__ queue, uint32_t queue_cap, unsigned int* cursor, QCursor& qc, bool pass,
+                                           uint64_t h, uint64_t dprod, uint64_t dd, uint32_t t, uint32_t isz, uint32_t imax,
+                                           uint32_t qi) {
   const uint32_t ballot = __ballot_sync(FULL, pass);
   if (ballot == 0) return;
-  uint32_t pos = 0;
-  if (lane_id() == 0) pos = atomicAdd(cursor, (unsigned int)__popc(ballot));
-  pos = __shfl_sync(FULL, pos, 0) + __popc(ballot & lanemask_lt());
-  if (pass && pos < queue_cap) {
-    QEntry e;
-    e.h = h;
-    e.dprod = dprod;
-    e.dd = dd;
-    e.t = t;
-    e.qi = qi;
-    e.isz = (uint8_t)isz;
-    e.imax = (uint8_t)imax;
+  const uint32_t need = __popc(ballot), room = qc.end - qc.pos;
+  uint32_t fresh = 0;
+  if (need > room) {  // warp-uniform
+    if (lane_id() == 0) fresh = atomicAdd(cursor, QCHUNK);
+    fresh = __shfl_sync(FULL, fresh, 0);
+  }
+  if (pass) {
+    const uint32_t r = __popc(ballot & lanemask_lt());
+    const uint32_t pos = r < room ? qc.pos + r : fresh + (r - room);
+    if (pos < queue_cap) {
+      QEntry e;
+      e.h = h;
+      e.dprod = dprod;
+      e.dd = dd;
+      e.t = t;
+      e.qi = qi;
+      e.isz = (uint8_t)isz;
+      e.imax = (uint8_t)imax;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) e.pad[k] = 0;
-    queue[pos] = e;
+      for (int k = 0; k < 6; ++k) e.pad[k] = 0;
+      queue[pos] = e;
+    }
+  }
+  if (need > room) {
+    qc.pos = fresh + (need - room);
+    qc.end = fresh + QCHUNK;
+  } else {
+    qc.pos += need;
   }
 }
 
@@ -806,6 +829,8 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t* __restrict__ colex3 = ix->colex3;
   const uint32_t* __restrict__ binom = ix->binom;
   unsigned int* cursor = work + 4;
+  QCursor qc;
+  qc.pos = qc.end = 0;
   uint32_t c_dkeys = 0, c_probes = 0, c_pass = 0;
 
   for (;;) {
@@ -912,7 +937,7 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           }
           c_probes += probe;
           c_pass += pass;
-          queue_push(queue, queue_cap, cursor, pass, h, dprod, dd, 0, 0, 0, qi);
+          queue_push(queue, queue_cap, cursor, qc, pass, h, dprod, dd, 0, 0, 0, qi);
           // entries with budget for insertions beyond the table's own depth are buffered for the insertion pass
           const bool ins = ok && (int)ka - (int)d - sd >= 1;
           const uint32_t ballot = __ballot_sync(FULL, ins);
@@ -956,7 +981,7 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
                   }
                   c_probes += active;
                   c_pass += px;
-                  queue_push(queue, queue_cap, cursor, px, hx, de.dprod, de.dd, mt, (uint32_t)j, imax, qi);
+                  queue_push(queue, queue_cap, cursor, qc, px, hx, de.dprod, de.dd, mt, (uint32_t)j, imax, qi);
                 }
               }
             }
@@ -969,6 +994,18 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     if (lane == 0 && flags) atomicOr(qflags + qi, flags);  // exact_kernel counts the hits and raises QF_HIT_OVERFLOW
     __syncwarp();
   }
+  // mark the unused tail of this warp's last chunk
+  for (uint32_t p = qc.pos + lane; p < qc.end; p += 32)
+    if (p < queue_cap) {
+      QEntry e;
+      e.h = e.dprod = e.dd = 0;
+      e.t = 0;
+      e.qi = QHOLE;
+      e.isz = e.imax = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) e.pad[k] = 0;
+      queue[p] = e;
+    }
   if (counters) {
     const uint32_t dk = __reduce_add_sync(FULL, c_dkeys);
     const uint32_t pr = __reduce_add_sync(FULL, c_probes), pa = __reduce_add_sync(FULL, c_pass);
@@ -1061,7 +1098,7 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     if (base >= total) break;
     const uint32_t i = base + lane;
     uint32_t poff = 0, pcnt = 0;
-    if (i < total) {
+    if (i < total && queue[i].qi != QHOLE) {
       const QEntry e = queue[i];
       W.e[lane] = e;
       const uint64_t fp = e.h;
