@@ -222,11 +222,6 @@ struct K1Shared {
   DeviceIndex ix;     // block-local copy of the model constants (pointers, masks, small tables)
   uint64_t rnd[256];  // class_rnd of every symbol
   uint32_t hit_cap;
-  // split path: staged nodes go to a global queue (exact_kernel consumes it) instead of the warp's own exact stage
-  QEntry* queue;
-  unsigned int* queue_cursor;
-  uint32_t queue_cap;
-  uint32_t cur_qi[K1_WARPS];  // the query each warp is working on
   K1Warp w[K1_WARPS];
 };
 
@@ -403,25 +398,6 @@ __device__ __forceinline__ void stage(K1Shared& S, K1Warp& W, uint32_t& sqn, boo
   const uint32_t ballot = __ballot_sync(FULL, pass);
   if (ballot == 0) return;
   const uint32_t lane = lane_id();
-  if (S.queue) {
-    // split path: one reservation per warp in the global queue
-    uint32_t pos = 0;
-    if (lane == 0) pos = atomicAdd(S.queue_cursor, (unsigned int)__popc(ballot));
-    pos = __shfl_sync(FULL, pos, 0) + __popc(ballot & lanemask_lt());
-    if (pass && pos < S.queue_cap) {
-      QEntry e;
-      e.h = h;
-      e.dprod = dprod;
-      e.dd = dd;
-      e.t = t;
-      e.qi = S.cur_qi[threadIdx.x >> 5];
-      e.isz = (uint8_t)isz;
-      e.imax = (uint8_t)imax;
-      for (int k = 0; k < 6; ++k) e.pad[k] = 0;
-      S.queue[pos] = e;
-    }
-    return;
-  }
   if (pass) {
     SEntry s;
     s.h = h;
@@ -517,15 +493,9 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(K1_WARPS * 32, MIN_CTAS)
 probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
-             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters, QEntry* queue, uint32_t queue_cap,
-             QCtx* __restrict__ qctx) {
+             uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K1Shared& S = *reinterpret_cast<K1Shared*>(smem_raw);
-  if (threadIdx.x == 0) {
-    S.queue = queue;
-    S.queue_cursor = work + 4;
-    S.queue_cap = queue_cap;
-  }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(ix);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.ix);
@@ -560,7 +530,6 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       W.L = L;
       W.ka = ka;
       W.hits_q = hits + (size_t)qi * bp.hit_cap;
-      S.cur_qi[threadIdx.x >> 5] = qi;
     }
     __syncwarp();
     if (L == 0) {
@@ -604,15 +573,6 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           W.kF[1] = k1;
           W.kF[2] = k2;
           W.kF_ok = ok ? 1u : 0u;
-          if (queue) {
-            QCtx c;
-            c.kF[0] = k0;
-            c.kF[1] = k1;
-            c.kF[2] = k2;
-            c.L = L;
-            c.ka_ok = ka | (ok ? 0x100u : 0u);
-            qctx[qi] = c;
-          }
         }
       }
       __syncwarp();
@@ -705,15 +665,10 @@ probe_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     }
     __syncwarp();
     if (lane == 0) {
-      if (queue) {
-        // split path: exact_kernel counts the hits (hit_count was zeroed) and raises QF_HIT_OVERFLOW itself
-        if (flags) atomicOr(qflags + qi, flags);
-      } else {
-        const uint32_t n = W.nhits;
-        hit_count[qi] = n;
-        if (n > bp.hit_cap) flags |= QF_HIT_OVERFLOW;
-        qflags[qi] = flags;
-      }
+      const uint32_t n = W.nhits;
+      hit_count[qi] = n;
+      if (n > bp.hit_cap) flags |= QF_HIT_OVERFLOW;
+      qflags[qi] = flags;
     }
     __syncwarp();
   }
@@ -2064,7 +2019,7 @@ size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap) {
 static int g_k1_ctas_per_sm = 0;
 static int g_k1_variant = 4;  // resident CTAs per SM the probe kernel is compiled for (register budget); ANL_K1_CTAS=3|4
 typedef void (*ProbeFn)(const DeviceIndex*, const BatchParams, const uint8_t*, const uint32_t*, uint32_t, uint32_t*, uint32_t*,
-                        uint32_t*, unsigned int*, Counters*, QEntry*, uint32_t, QCtx*);
+                        uint32_t*, unsigned int*, Counters*);
 static ProbeFn probe_fn() { return g_k1_variant == 3 ? probe_kernel<3> : probe_kernel<ANL_K1_MIN_CTAS>; }
 
 static uint32_t ring_depth(const BatchParams& bp) {
@@ -2132,8 +2087,7 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     probe_fn()<<<(unsigned)grid, K1_WARPS * 32, sizeof(K1Shared), stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits,
-                                                                            lb.hit_count, lb.qflags, lb.work, lb.counters, nullptr, 0,
-                                                                            nullptr);
+                                                                            lb.hit_count, lb.qflags, lb.work, lb.counters);
     ++g_kernel_launches;
     return cudaGetLastError();
   }
