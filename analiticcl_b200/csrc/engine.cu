@@ -1,10 +1,11 @@
 // engine.cu -- device residency of the index and the batched lookup pipeline.
 //
 // Replaces the reference's per-query call chain find_variants -> find_nearest_anahashes ->
-// gather_instances -> score_and_rank (src/lib.rs:972-1027) with: host normalisation of a whole
-// batch, one H2D copy, probe kernel, score/rank kernel, one packed D2H copy, and a thin host
-// post-pass (late confusable rescoring + cut-off, src/lib.rs:1592-1622) that only exists when
-// confusables are loaded.  There is no CPU fallback: every failure of the CUDA path is an error.
+// gather_instances -> score_and_rank (src/lib.rs:972-1027) with: one H2D copy of a batch's raw text, the
+// kernels of kernels.cu (encode, Bloom stage, exact stage, prefilter, score/rank, confusables, finish), one
+// packed D2H copy, and a thin host pass that assembles the result arrays and finishes the few queries the
+// device declines (confusable pairs with non-ASCII or over-long text, src/lib.rs:1592-1622).  There is no CPU
+// fallback: every failure of the CUDA path is an error.
 #include "engine.h"
 
 #include <algorithm>

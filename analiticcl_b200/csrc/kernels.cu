@@ -1,16 +1,24 @@
-// kernels.cu -- the two hand-written sm_100a kernels of the variant-lookup hot path.
+// kernels.cu -- the hand-written sm_100a kernels of the variant-lookup hot path.
 //
-//   probe_kernel : candidate generation.  Replaces find_nearest_anahashes (src/lib.rs:1143-1308):
-//                  BFS over deletions (src/iterators.rs:153-187) + linear scan of
-//                  sortedindex[charcount] with a bignum modulo per test (src/lib.rs:1268-1281).
-//   score_kernel : candidate scoring + ranking.  Replaces gather_instances (src/lib.rs:1311-1402),
-//                  damerau_levenshtein / longest_common_substring_length / common_prefix_length /
-//                  common_suffix_length (src/distance.rs:101-231) and score_and_rank
-//                  (src/lib.rs:1405-1653) up to and including crop and cut-off.
+//   encode_kernel    : query normalisation (normalize_to_alphabet, src/anahash.rs:50-80).
+//   bloom_kernel     : candidate generation, stage 1.  Replaces the search side of find_nearest_anahashes
+//                      (src/lib.rs:1143-1308): BFS over deletions (src/iterators.rs:153-187) + linear scan of
+//                      sortedindex[charcount] with a bignum modulo per test (src/lib.rs:1268-1281) become a
+//                      canonical enumeration of the neighbourhood with one add + one Bloom word per node.
+//   exact_kernel     : candidate generation, stage 2: table slot, postings, exact 192-bit verification.
+//   probe_kernel     : both stages fused in one kernel (StopAtExactMatch, reruns, queue overflow).
+//   prefilter_kernel : bit-parallel OSA distance of every candidate; exact rejection of the far ones.
+//   score_kernel     : candidate scoring + ranking.  Replaces gather_instances (src/lib.rs:1311-1402),
+//                      damerau_levenshtein / longest_common_substring_length / common_prefix_length /
+//                      common_suffix_length (src/distance.rs:101-231) and score_and_rank
+//                      (src/lib.rs:1405-1653) up to and including crop and cut-off.
+//   confusable_kernel, finish_kernel : rescore_confusables (src/lib.rs:1656-1663) on the device, then
+//                      re-rank / crop / cut-off in place.
+//   merge_kernel     : lexicon-sharded mode, ranks the all-gathered per-shard survivors.
 //
-// One warp owns one query at a time (queries are independent, src/bin/analiticcl.rs:445-448);
-// warps pull queries from a global counter, so the grid is persistent: SMs x resident CTAs.
-// Integer / byte work only -- no tensor cores (see DESIGN.md for the rooflines).
+// One warp owns one query at a time in the per-query kernels (queries are independent,
+// src/bin/analiticcl.rs:445-448); warps pull queries from a global counter, so the grids are persistent:
+// SMs x resident CTAs.  Integer / byte work only -- no tensor cores (see DESIGN.md for the rooflines).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>

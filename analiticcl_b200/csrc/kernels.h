@@ -1,4 +1,4 @@
-// kernels.h -- launch interface of the two sm_100a kernels of the variant-lookup path.
+// kernels.h -- launch interface of the sm_100a kernels of the variant-lookup path (see kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
