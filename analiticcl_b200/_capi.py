@@ -121,6 +121,7 @@ SIGNATURES = {
     "anl_device_batch_create": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_device_batch_run": (_i32, [_vp, _vp, _vp]),
     "anl_device_batch_timings": (_i32, [_vp, _vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),
+    "anl_device_batch_stage_timings": (_i32, [_vp, _vp, _P(C.c_float)]),
     "anl_device_batch_fetch": (_i32, [_vp, _vp, _P(_vp)]),
     "anl_device_batch_free": (None, [_vp, _vp]),
     "anl_device_batch_counters": (_i32, [_vp, _vp, _P(Counters)]),

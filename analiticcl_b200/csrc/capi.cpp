@@ -618,7 +618,17 @@ anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream)
 anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms) {
   if (!m || !b || !probe_ms || !score_ms) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
-  if (!m->engine.timings(b->b, probe_ms, score_ms, rescore_ms, &err)) return fail(ANL_ERR_CUDA, err);
+  float st[6];
+  if (!m->engine.timings(b->b, st, &err)) return fail(ANL_ERR_CUDA, err);
+  *probe_ms = st[0] + st[1];
+  *score_ms = st[2] + st[3];
+  if (rescore_ms) *rescore_ms = st[4] + st[5];
+  return ANL_OK;
+}
+anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, float* stage_ms) {
+  if (!m || !b || !stage_ms) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.timings(b->b, stage_ms, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
 anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) {

@@ -730,42 +730,39 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   cudaEvent_t* ev = b->events.data() + (size_t)b->runs_recorded * EV_PER_RUN;
   CU_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(Counters), stream));
   CU_TRY(cudaEventRecord(ev[0], stream));
+  lb.ev_bloom_done = ev[1];
   CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
-  CU_TRY(cudaEventRecord(ev[1], stream));
-  CU_TRY(launch_prefilter(d_ix_, b->bp, lb, sm_count_, stream));
-  CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[2], stream));
-  CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, stream));
+  CU_TRY(launch_prefilter(d_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[3], stream));
-  CU_TRY(launch_finish(b->bp, lb, sm_count_, stream));
+  CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[4], stream));
-  b->last_done = ev[4];
+  CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, stream));
+  CU_TRY(cudaEventRecord(ev[5], stream));
+  CU_TRY(launch_finish(b->bp, lb, sm_count_, stream));
+  CU_TRY(cudaEventRecord(ev[6], stream));
+  b->last_done = ev[6];
   ++b->runs_recorded;
   b->ran = true;
   return true;
 }
 
-bool Engine::timings(DeviceBatch* b, float* probe_ms, float* score_ms, float* rescore_ms, std::string* err) {
+bool Engine::timings(DeviceBatch* b, float* stage_ms, std::string* err) {
   if (!b->ran) {
     *err = "batch has not been run";
     return false;
   }
   // averages over the runs since the previous call (CUDA events on the launching stream)
   CU_TRY(cudaEventSynchronize(b->last_done));
-  double p = 0, s = 0, x = 0;
-  for (uint32_t r = 0; r < b->runs_recorded; ++r) {
-    float a = 0, c = 0, d = 0;
-    CU_TRY(cudaEventElapsedTime(&a, b->events[r * EV_PER_RUN + 0], b->events[r * EV_PER_RUN + 1]));
-    CU_TRY(cudaEventElapsedTime(&c, b->events[r * EV_PER_RUN + 1], b->events[r * EV_PER_RUN + 2]));
-    CU_TRY(cudaEventElapsedTime(&d, b->events[r * EV_PER_RUN + 2], b->events[r * EV_PER_RUN + 4]));
-    p += a;
-    s += c;
-    x += d;
-  }
+  double acc[EV_PER_RUN - 1] = {0};
+  for (uint32_t r = 0; r < b->runs_recorded; ++r)
+    for (int k = 0; k + 1 < EV_PER_RUN; ++k) {
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, b->events[r * EV_PER_RUN + k], b->events[r * EV_PER_RUN + k + 1]));
+      acc[k] += ms;
+    }
   const uint32_t nr = std::max(1u, b->runs_recorded);
-  *probe_ms = (float)(p / nr);
-  *score_ms = (float)(s / nr);
-  if (rescore_ms) *rescore_ms = (float)(x / nr);
+  for (int k = 0; k + 1 < EV_PER_RUN; ++k) stage_ms[k] = (float)(acc[k] / nr);
   b->runs_recorded = 0;
   return true;
 }

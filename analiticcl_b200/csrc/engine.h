@@ -25,7 +25,7 @@ struct ResultSet {
 
 // Everything one pass over a batch of queries needs, on the device and in pinned host memory.
 // Buffers are capacity-based and recycled through Engine's cache: steady-state calls allocate nothing.
-static const int EV_PER_RUN = 5;
+static const int EV_PER_RUN = 7;
 struct DeviceBatch {
   // ---- capacities (what the buffers can hold) ----
   uint32_t cap_n = 0, cap_pool = 0;
@@ -82,7 +82,8 @@ struct DeviceBatch {
   size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;
   cudaStream_t stream = nullptr;    // this batch's own stream (copies + default launches)
   cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
-  // EV_PER_RUN events (start, after probe, after score, after confusables, after finish) per run since the last timings() call
+  // EV_PER_RUN events (start, after the Bloom stage, after probe, after prefilter, after score, after confusables,
+  // after finish) per run since the last timings() call
   std::vector<cudaEvent_t> events;
   uint32_t runs_recorded = 0;
   cudaEvent_t last_done = nullptr;  // end event of the most recent run
@@ -111,7 +112,9 @@ class Engine {
   // append: add this batch's queries after the ones already in `out` (pipelined chunks)
   bool fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status);
   void free_batch(DeviceBatch* b);  // returns the buffers to the cache
-  bool timings(DeviceBatch* b, float* probe_ms, float* score_ms, float* rescore_ms, std::string* err);
+  // stage_ms[6]: Bloom stage, exact stage (the whole fused probe kernel when the split path is off), prefilter,
+  // score/rank, confusables, finish
+  bool timings(DeviceBatch* b, float* stage_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);
 
   // lexicon-sharded mode (see include/analiticcl_b200.h)

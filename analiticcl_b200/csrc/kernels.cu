@@ -2087,7 +2087,9 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
     ++g_kernel_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (lb.ev_bloom_done && (e = cudaEventRecord(lb.ev_bloom_done, stream)) != cudaSuccess) return e;
   } else {
+    if (lb.ev_bloom_done && (e = cudaEventRecord(lb.ev_bloom_done, stream)) != cudaSuccess) return e;
     int per_sm = g_k1_ctas_per_sm > 0 ? g_k1_ctas_per_sm : 1;
     // persistent grid: a whole number of CTAs per SM, no more warps than queries
     long long want = ((long long)lb.n + K1_WARPS - 1) / K1_WARPS;

@@ -28,6 +28,7 @@ struct LaunchBuffers {
   uint32_t queue_cap = 0;
   QCtx* qctx = nullptr;              //          per-query context for the exact stage, [n]
   Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
+  cudaEvent_t ev_bloom_done = nullptr;  // optional: recorded by launch_probe between the Bloom and the exact stage
 };
 
 // Query normalisation on the device (normalize_to_alphabet, src/anahash.rs:50-80): raw text -> encoded rows.

@@ -228,6 +228,10 @@ anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream)
  * (events recorded on the launching stream); synchronises.  rescore_ms (may be NULL) = confusable
  * kernel + finish kernel, which only run when confusables are loaded. */
 anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms);
+/* The same window per kernel: stage_ms[6] = Bloom-stage kernel, exact-stage kernel (the whole fused probe
+ * kernel when the split path is off), prefilter kernel, score/rank kernel launches, confusable kernel,
+ * finish kernel.  Resets the window like anl_device_batch_timings. */
+anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, float* stage_ms);
 /* Downloads the results of the last run and finishes them on the host (same output as
  * anl_find_variants_batch). */
 anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out);

@@ -56,7 +56,7 @@ except (OSError, ValueError):
 md = [f"# ncu summary {tag}", "",
       "Source: `tools/profile.sh` under gpurun (1x B200, `--clock-control none`). Full `.ncu-rep` files stay in",
       "`gpurun_out/` (scratch); this file holds what the numbers in DESIGN.md / bench.py are read from.", ""]
-for name in ("probe", "score"):
+for name in ("bloom", "exact", "score"):
     rep = os.path.join(OUT, f"prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -104,6 +104,9 @@ if os.path.exists(launch):
         md.append(f"| {k} | {len(v)} | {med[k]:.0f} | {med[k] / s:.3f} |")
     md.append("")
 open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w").write("\n".join(md))
+if "bloom_kernel" in traffic and "exact_kernel" in traffic:
+    # candidate generation = Bloom stage + exact stage (bench.py's `roofline.traffic`)
+    traffic["probe"] = dict(traffic["bloom_kernel"], dram_bytes=traffic["bloom_kernel"]["dram_bytes"] + traffic["exact_kernel"]["dram_bytes"])
 if traffic and launch_info[1]:
     import json
     json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
