@@ -417,6 +417,9 @@ void Engine::destroy_batch(DeviceBatch* b) {
   for (auto& ev : b->events)
     if (ev) cudaEventDestroy(ev);
   if (b->uploaded) cudaEventDestroy(b->uploaded);
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->aux) cudaStreamDestroy(b->aux);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -523,6 +526,12 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   }
   if (!b->uploaded && cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming) != cudaSuccess) {
     *err = "cudaEventCreate failed";
+    return fail();
+  }
+  if (!b->aux && (cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+    *err = "cudaStreamCreate failed";
     return fail();
   }
   b->n = (uint32_t)n;
@@ -711,6 +720,10 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   lb.scratch = b->d_scratch;
   lb.work = b->d_work;
   lb.counters = b->d_counters;
+  lb.aux_stream = b->aux;
+  lb.ev_fork = b->ev_fork;
+  lb.ev_join = b->ev_join;
+  lb.scratch_bytes = b->cap_scratch;
   return lb;
 }
 

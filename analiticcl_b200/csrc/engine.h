@@ -82,6 +82,8 @@ struct DeviceBatch {
   size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;
   cudaStream_t stream = nullptr;    // this batch's own stream (copies + default launches)
   cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
+  cudaStream_t aux = nullptr;       // side stream: the long-query class of the score kernel runs beside the short one
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // EV_PER_RUN events (start, after the Bloom stage, after probe, after prefilter, after score, after confusables,
   // after finish) per run since the last timings() call
   std::vector<cudaEvent_t> events;

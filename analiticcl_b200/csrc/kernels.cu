@@ -1575,7 +1575,8 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
              ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
              uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
-             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max) {
+             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max,
+             uint32_t scratch_cta0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -1587,7 +1588,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t rowbytes = (ML + 1) * 32;
   const uint32_t max_len = ix->max_len;
 
-  const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
+  const uint32_t gwarp = (blockIdx.x + scratch_cta0) * K2_WARPS + warp;  // (scratch_cta0: first scratch slot of this launch)
   SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
   SurvRec* sorted = surv + bp.hit_cap;
 
@@ -1597,22 +1598,32 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   const uint32_t* __restrict__ gid_of = ix->inst_gid;
   unsigned long long c_pairs = 0, c_cells = 0, c_surv = 0, c_res = 0, c_dpp = 0, c_dpc = 0;
 
+  // Queries are split over launches by the number of matrix columns they can need (longest admissible
+  // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
+  // with a fraction of the shared memory, i.e. more resident warps.  The launch for the long ones takes 32
+  // queries per counter increment and tests their class one per lane (it skips nearly all of them).
+  const uint32_t grab = need_min > 0 ? 32u : 1u;
+  uint32_t gbase = 0, gmask = 0;
   for (;;) {
-    uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(work, 1u);
-    qi = __shfl_sync(FULL, qi, 0);
-    if (qi >= nq) break;
+    if (gmask == 0) {
+      if (lane == 0) gbase = atomicAdd(work, grab);
+      gbase = __shfl_sync(FULL, gbase, 0);
+      if (gbase >= nq) break;
+      bool mine = false;
+      if (lane < grab && gbase + lane < nq) {
+        const uint32_t f0 = qflags[gbase + lane];
+        const uint32_t q0 = qlist ? qlist[gbase + lane] : gbase + lane;
+        const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
+        const uint32_t need = (f0 & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
+        mine = need >= need_min && need <= need_max;
+      }
+      gmask = __ballot_sync(FULL, mine);
+      if (gmask == 0) continue;
+    }
+    const uint32_t qi = gbase + (uint32_t)__ffs(gmask) - 1;
+    gmask &= gmask - 1;
     const uint32_t flags = qflags[qi];
     const bool skip = (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) != 0;
-    {
-      // Queries are split over launches by the number of matrix columns they can need (longest admissible
-      // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
-      // with a fraction of the shared memory, i.e. more resident warps.
-      const uint32_t q0 = qlist ? qlist[qi] : qi;
-      const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
-      const uint32_t need = skip ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
-      if (need < need_min || need > need_max) continue;
-    }
     if (skip) {
       if (lane == 0) {
         OutHead h;
@@ -2139,22 +2150,31 @@ cudaError_t launch_prefilter(const DeviceIndex* d_ix, const BatchParams& bp, con
   return cudaGetLastError();
 }
 
-static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
-                                      cudaStream_t stream, uint32_t cols, uint32_t need_min, uint32_t need_max, unsigned int* work) {
+static long long score_class_grid(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, uint32_t cols) {
   const uint32_t R = ring_depth(bp);
   const size_t smem = k2_warp_bytes(cols, R) * K2_WARPS;
-  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  if (smem > 200 * 1024) return -1;
   long long grid = (long long)sm_count * k2_ctas_per_sm(R, smem);
   const long long cap = (long long)sm_count * 16;
   if (grid > cap) grid = cap;
   long long want = ((long long)lb.n + K2_WARPS - 1) / K2_WARPS;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
+  return grid;
+}
+
+static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
+                                      cudaStream_t stream, uint32_t cols, uint32_t need_min, uint32_t need_max, unsigned int* work,
+                                      long long grid, uint32_t scratch_cta0) {
+  const uint32_t R = ring_depth(bp);
+  const size_t smem = k2_warp_bytes(cols, R) * K2_WARPS;
+  if (grid < 1) return cudaErrorInvalidConfiguration;
+  (void)sm_count;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
   score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.conf_work,
                                                                 lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
                                                                 lb.out_head, scratch, work, lb.work + 2, lb.counters, cols, R,
-                                                                need_min, need_max);
+                                                                need_min, need_max, scratch_cta0);
   ++g_kernel_launches;
   return cudaGetLastError();
 }
@@ -2162,6 +2182,8 @@ static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams
 // Queries whose matrices fit K2_SHORT_COLS columns (nearly all of them) run in a launch with a small
 // shared-memory footprint and therefore more resident warps; the rest in a second launch sized by the
 // longest indexed entry.  Both launches walk the whole batch and skip the queries of the other class.
+// With a side stream the second launch (few queries, long dependent chains) runs beside the first on its own
+// scratch slots instead of after it.
 constexpr uint32_t K2_SHORT_COLS = 24;
 
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
@@ -2170,15 +2192,38 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // work counter, pool cursor, confusable queue
   if (e != cudaSuccess) return e;
   const uint32_t ML = h_ix.max_len;
-  if (ML <= K2_SHORT_COLS + 4) return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, 0, ML, lb.work + 1);
-  e = launch_score_class(d_ix, bp, lb, sm_count, stream, K2_SHORT_COLS, 0, K2_SHORT_COLS, lb.work + 1);
-  if (e != cudaSuccess) return e;
+  if (ML <= K2_SHORT_COLS + 4)
+    return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, 0, ML, lb.work + 1, score_class_grid(bp, lb, sm_count, ML), 0);
+  const long long grid_a = score_class_grid(bp, lb, sm_count, K2_SHORT_COLS);
   // the longest query of the batch bounds what the second class can need (a symbol takes at least one byte)
   const uint32_t longest = bp.query_stride - 2, kmax = ring_depth(bp) - 2;
-  if (std::min<uint32_t>(ML, longest + kmax) <= K2_SHORT_COLS) return cudaSuccess;
+  const bool second = std::min<uint32_t>(ML, longest + kmax) > K2_SHORT_COLS;
+  long long grid_b = second ? score_class_grid(bp, lb, sm_count, ML) : 0;
+  if (second && grid_b < 1) return cudaErrorInvalidConfiguration;
+  // side by side only when the scratch has slots for both grids (the long class then gets by with one CTA per SM)
+  bool beside = second && lb.aux_stream && lb.ev_fork && lb.ev_join && grid_a > 0;
+  if (beside) {
+    if (grid_b > sm_count) grid_b = sm_count;
+    const size_t slot = (size_t)K2_WARPS * 2 * bp.hit_cap * sizeof(SurvRec);
+    beside = (size_t)(grid_a + grid_b) * slot <= lb.scratch_bytes;
+    if (!beside) grid_b = score_class_grid(bp, lb, sm_count, ML);
+  }
+  if (beside) {
+    // fork: the memset above (pool cursor, queue length) precedes both launches
+    if ((e = cudaEventRecord(lb.ev_fork, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(lb.aux_stream, lb.ev_fork, 0)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), lb.aux_stream)) != cudaSuccess) return e;
+    e = launch_score_class(d_ix, bp, lb, sm_count, lb.aux_stream, ML, K2_SHORT_COLS + 1, ML, lb.work, grid_b, (uint32_t)grid_a);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(lb.ev_join, lb.aux_stream)) != cudaSuccess) return e;
+  }
+  e = launch_score_class(d_ix, bp, lb, sm_count, stream, K2_SHORT_COLS, 0, K2_SHORT_COLS, lb.work + 1, grid_a, 0);
+  if (e != cudaSuccess) return e;
+  if (beside) return cudaStreamWaitEvent(stream, lb.ev_join, 0);
+  if (!second) return cudaSuccess;
   e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
   if (e != cudaSuccess) return e;
-  return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work);
+  return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work, grid_b, 0);
 }
 
 // The device confusable stage: edit scripts of the queued pairs, then re-rank / crop / cut-off per query.

@@ -28,6 +28,9 @@ struct LaunchBuffers {
   uint32_t queue_cap = 0;
   QCtx* qctx = nullptr;              //          per-query context for the exact stage, [n]
   Counters* counters = nullptr;      // accumulated work counters (zeroed by the caller when wanted)
+  cudaStream_t aux_stream = nullptr;    // optional side stream (+ two events): launch_score runs the long-query class on it,
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // beside the short-query class, when `scratch` has room for both grids
+  size_t scratch_bytes = 0;             // size of `scratch` (only needed with aux_stream)
   cudaEvent_t ev_bloom_done = nullptr;  // optional: recorded by launch_probe between the Bloom and the exact stage
 };
 
