@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -420,13 +421,14 @@ void Engine::destroy_batch(DeviceBatch* b) {
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->aux) cudaStreamDestroy(b->aux);
+  if (b->rr_stream) cudaStreamDestroy(b->rr_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
 
 void Engine::free_batch(DeviceBatch* b) {
   if (!b) return;
-  if (cache_.size() < 2) {
+  if (cache_.size() < 6) {
     b->owned_blob.clear();
     b->owned_blob.shrink_to_fit();
     b->blob = nullptr;
@@ -537,6 +539,8 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   b->n = (uint32_t)n;
   b->params = p;
   b->reruns = 0;
+  b->fetch_begun = false;
+  b->rr_pending = false;
   b->results = 0;
   b->offsets.resize(n + 1);
   const uint64_t base = offsets[0];
@@ -880,9 +884,9 @@ void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs,
 
 // Queries with more instance hits than hit_cap: run both kernels again for just those queries with
 // an exact capacity.  Rare (needs > hit_cap candidate instances for one query).
-bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, std::vector<OutHead>* heads,
-                                std::vector<OutRec>* recs, std::string* err, int* status) {
+bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
+  const std::vector<uint32_t>& which = b->rr_which;
   const uint32_t m = (uint32_t)which.size();
   uint32_t cap = b->bp.hit_cap;
   for (uint32_t i : which) cap = std::max(cap, b->h_hitcnt[i]);
@@ -896,7 +900,7 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
   }
   bp.pool_cap = (uint32_t)pool64;
   // grow-only buffers kept with the batch: steady state allocates (and frees) nothing, which matters
-  // because cudaFree synchronises the device and would stall the other in-flight chunk
+  // because cudaFree synchronises the device and would stall the other in-flight chunks
   const size_t scratch = score_scratch_bytes(bp, sm_count_, m);
   if (m > b->rr_cap_m) {
     if (!dev_realloc(&b->rr_qlist, m, err) || !dev_realloc(&b->rr_hit_count, m, err) || !dev_realloc(&b->rr_qflags, m, err) ||
@@ -916,51 +920,61 @@ bool Engine::rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& whi
     if (!dev_realloc(&b->rr_scratch, scratch, err)) return false;
     b->rr_cap_scratch = scratch;
   }
-  uint32_t* d_qlist = b->rr_qlist;
-  uint32_t *d_hits = b->rr_hits, *d_hit_count = b->rr_hit_count, *d_qflags = b->rr_qflags;
-  OutHead* d_head = b->rr_head;
-  OutRec* d_out = b->rr_out;
-  uint8_t* d_scratch = b->rr_scratch;
-  auto cleanup = [&]() {};
-  bool ok = true;
-  auto body = [&]() -> bool {
-    CU_TRY(cudaMemcpyAsync(d_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
-    LaunchBuffers lb;
-    lb.queries = b->d_rows;
-    lb.qlist = d_qlist;
-    lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
-    lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
-    lb.n = m;
-    lb.hits = d_hits;
-    lb.hit_count = d_hit_count;
-    lb.qflags = d_qflags;
-    lb.out = d_out;
-    lb.out_head = d_head;
-    lb.scratch = d_scratch;
-    lb.work = b->d_work;
-    lb.counters = nullptr;
-    CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, b->stream));
-    CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, b->stream));
-    std::vector<uint32_t> fl(m);
-    heads->resize(m);
-    unsigned int total = 0;
-    CU_TRY(cudaMemcpyAsync(heads->data(), d_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaMemcpyAsync(fl.data(), d_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaStreamSynchronize(b->stream));
-    for (uint32_t i = 0; i < m; ++i)
-      if (fl[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW | QF_UNSUPPORTED)) {
-        *err = "internal error: overflow persisted after rerun";
-        return false;
-      }
-    recs->resize(total);
-    if (total) CU_TRY(cudaMemcpy(recs->data(), d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost));
-    return true;
-  };
-  ok = body();
-  cleanup();
-  if (ok) *status = ANL_OK;
-  return ok;
+  if (!b->rr_stream) {
+    // the re-run is a handful of warps with long dependent chains: let its blocks go first whenever an SM has
+    // room, instead of queueing behind the persistent grids of the other chunks
+    int lo = 0, hi = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU_TRY(cudaStreamCreateWithPriority(&b->rr_stream, cudaStreamNonBlocking, hi));
+  }
+  cudaStream_t st = b->rr_stream;  // (the batch's own run has completed: settle_pool synchronised)
+  CU_TRY(cudaMemcpyAsync(b->rr_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  LaunchBuffers lb;
+  lb.queries = b->d_rows;
+  lb.qlist = b->rr_qlist;
+  lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
+  lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
+  lb.n = m;
+  lb.hits = b->rr_hits;
+  lb.hit_count = b->rr_hit_count;
+  lb.qflags = b->rr_qflags;
+  lb.out = b->rr_out;
+  lb.out_head = b->rr_head;
+  lb.scratch = b->rr_scratch;
+  lb.work = b->d_work;
+  lb.counters = nullptr;
+  CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, st));
+  CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, st));
+  b->rr_bp = bp;
+  b->rr_pending = true;
+  *status = ANL_OK;
+  return true;
+}
+
+bool Engine::rerun_collect(DeviceBatch* b, std::string* err, int* status) {
+  *status = ANL_ERR_CUDA;
+  const uint32_t m = (uint32_t)b->rr_which.size();
+  cudaStream_t st = b->rr_stream;
+  b->rr_pending = false;
+  std::vector<uint32_t> fl(m);
+  b->rr_heads.resize(m);
+  unsigned int total = 0;
+  CU_TRY(cudaMemcpyAsync(b->rr_heads.data(), b->rr_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(fl.data(), b->rr_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; i < m; ++i)
+    if (fl[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW | QF_UNSUPPORTED)) {
+      *err = "internal error: overflow persisted after rerun";
+      return false;
+    }
+  b->rr_recs.resize(total);
+  if (total) {
+    CU_TRY(cudaMemcpyAsync(b->rr_recs.data(), b->rr_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  *status = ANL_OK;
+  return true;
 }
 
 bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* err) {
@@ -1116,7 +1130,7 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
   return ok;
 }
 
-bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
+bool Engine::fetch_begin(DeviceBatch* b, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!b->ran) {
     *err = "batch has not been run";
@@ -1136,11 +1150,13 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
   unsigned int total = 0;
   if (!settle_pool(b, &total, err)) return false;
   if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
-  pt.lap("fetch: sync+D2H");
+  pt.lap("fetch: sync");
 
   // queries whose hit list overflowed are run again with an exact capacity
-  std::vector<uint32_t> which;
+  b->rr_which.clear();
+  b->rr_index.clear();
+  b->rr_heads.clear();
+  b->rr_recs.clear();
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t f = b->h_flags[i];
     if (f & QF_UNSUPPORTED) {
@@ -1149,19 +1165,34 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
       *status = ANL_ERR_UNSUPPORTED;
       return false;
     }
-    if (f & QF_HIT_OVERFLOW) which.push_back(i);
+    if (f & QF_HIT_OVERFLOW) b->rr_which.push_back(i);
   }
-  std::vector<OutHead> rr_heads;
-  std::vector<OutRec> rr_recs;
-  std::vector<int32_t> rr_index;
-  if (!which.empty()) {
-    if (profile_enabled()) fprintf(stderr, "[anl profile] %zu queries overflowed hit_cap=%u\n", which.size(), b->bp.hit_cap);
-    if (!rerun_hit_overflow(b, which, &rr_heads, &rr_recs, err, status)) return false;
-    b->reruns += which.size();
-    rr_index.assign(n, -1);
-    for (size_t k = 0; k < which.size(); ++k) rr_index[which[k]] = (int32_t)k;
+  if (!b->rr_which.empty()) {
+    if (profile_enabled()) fprintf(stderr, "[anl profile] %zu queries overflowed hit_cap=%u\n", b->rr_which.size(), b->bp.hit_cap);
+    if (!rerun_launch(b, err, status)) return false;
+    b->reruns += b->rr_which.size();
+    b->rr_index.assign(n, -1);
+    for (size_t k = 0; k < b->rr_which.size(); ++k) b->rr_index[b->rr_which[k]] = (int32_t)k;
   }
-  pt.lap("fetch: hit-overflow reruns");
+  pt.lap("fetch: launch hit-overflow reruns");
+  b->fetch_begun = true;
+  *status = ANL_OK;
+  return true;
+}
+
+bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
+  if (!b->fetch_begun && !fetch_begin(b, err, status)) return false;
+  b->fetch_begun = false;
+  *status = ANL_ERR_CUDA;
+  const uint32_t n = b->n;
+  PhaseTimer pt;
+  CU_TRY(cudaStreamSynchronize(b->stream));  // the D2H copy of the results
+  if (b->rr_pending && !rerun_collect(b, err, status)) return false;
+  *status = ANL_ERR_CUDA;
+  const std::vector<OutHead>& rr_heads = b->rr_heads;
+  const std::vector<OutRec>& rr_recs = b->rr_recs;
+  const std::vector<int32_t>& rr_index = b->rr_index;
+  pt.lap("fetch: D2H + collect reruns");
 
   // host = the device did not (or could not) finish this query: confusable rescoring, re-rank, cut-off follow here
   const bool post_pass = b->bp.finish_mode != FINISH_FULL;
@@ -1272,9 +1303,10 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
 
 bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
                                  ResultSet* out, std::string* err, int* status) {
-  // Chunks are pipelined over two batches with their own streams: while the GPU works on chunk i,
-  // the host finishes chunk i-1 (D2H, confusable post-pass, assembly) and encodes chunk i+1.
-  uint64_t CHUNK = 1u << 17;
+  // Chunks are pipelined over up to four batches with their own streams: while the GPU works on chunks
+  // i .. i+2 (kernel tails of one chunk overlap the next chunk's kernels), the host finishes chunk i-1 (D2H,
+  // confusable post-pass, assembly) and stages chunk i+3.
+  uint64_t CHUNK = 1u << 16;
   if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
   out->offsets.assign(1, 0);
   out->variants.clear();
@@ -1284,8 +1316,42 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
     out->offsets.reserve((size_t)n + 1);
     out->flags.reserve((size_t)n);
   }
-  DeviceBatch* inflight = nullptr;
+  // Batches in flight, oldest first (each with its own streams).  Once DEPTH are queued the oldest is settled
+  // (fetch_begin: wait for its run, start the D2H copy, launch the re-run of overflowed queries) and the one
+  // settled in the previous round is finished on the host, so a re-run never has the host waiting for it.
+  size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
+  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(4, std::max(1, atoi(e)));
+  std::deque<DeviceBatch*> inflight;
+  DeviceBatch* settled = nullptr;
   bool ok = true;
+  auto fail_with = [&](const std::string& e2, int s2) {
+    if (ok) {
+      ok = false;
+      *err = e2;
+      *status = s2;
+    }
+  };
+  auto finish_settled = [&]() {
+    if (!settled) return;
+    std::string e2;
+    int s2 = ANL_OK;
+    if (ok && !fetch_batch(settled, out, true, &e2, &s2)) fail_with(e2, s2);
+    if (!ok) {
+      cudaStreamSynchronize(settled->stream);
+      if (settled->rr_stream) cudaStreamSynchronize(settled->rr_stream);
+    }
+    free_batch(settled);
+    settled = nullptr;
+  };
+  auto settle_oldest = [&]() {
+    DeviceBatch* f = inflight.front();
+    inflight.pop_front();
+    std::string e2;
+    int s2 = ANL_OK;
+    if (ok && !fetch_begin(f, &e2, &s2)) fail_with(e2, s2);
+    finish_settled();  // (the previous one: its re-run had this whole round to complete)
+    settled = f;
+  };
   for (uint64_t lo = 0; ok && (lo < n || (n == 0 && lo == 0)); lo += CHUNK) {
     const uint64_t m = std::min(CHUNK, n - lo);
     DeviceBatch* b = create_batch(blob, offsets + lo, m, p, false, false, err, status);
@@ -1294,30 +1360,15 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
       *status = ANL_ERR_CUDA;
       ok = false;
     }
-    if (inflight) {
-      std::string e2;
-      int s2 = ANL_OK;
-      if (!fetch_batch(inflight, out, true, &e2, &s2) && ok) {
-        ok = false;
-        *err = e2;
-        *status = s2;
-      }
-      free_batch(inflight);
-      inflight = nullptr;
-    }
-    if (ok)
-      inflight = b;
-    else if (b) {
-      cudaStreamSynchronize(b->stream);
-      free_batch(b);
-    }
+    if (b) inflight.push_back(b);
+    if (ok && inflight.size() >= DEPTH) settle_oldest();
     if (n == 0) break;
   }
-  if (inflight) {
-    if (ok) ok = fetch_batch(inflight, out, true, err, status);
-    else cudaStreamSynchronize(inflight->stream);
-    free_batch(inflight);
+  while (!inflight.empty()) {
+    if (!ok) cudaStreamSynchronize(inflight.front()->stream);
+    settle_oldest();
   }
+  finish_settled();
   if (ok) *status = ANL_OK;
   return ok;
 }

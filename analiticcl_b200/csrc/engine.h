@@ -95,6 +95,16 @@ struct DeviceBatch {
   int final_mode = FINISH_FULL;  // finish mode of the merged result (bp.finish_mode is FINISH_SHARD while scoring)
   uint64_t reruns = 0;
   uint64_t results = 0;
+  // fetch in two phases (fetch_begin / fetch_batch): queries whose hit list overflowed are run again on a
+  // high-priority stream between the two, while the host works on other chunks
+  bool fetch_begun = false;
+  bool rr_pending = false;
+  cudaStream_t rr_stream = nullptr;
+  BatchParams rr_bp;
+  std::vector<uint32_t> rr_which;
+  std::vector<OutHead> rr_heads;
+  std::vector<OutRec> rr_recs;
+  std::vector<int32_t> rr_index;
 };
 
 class Engine {
@@ -112,6 +122,9 @@ class Engine {
                             bool copy_blob, bool sync, std::string* err, int* status);
   bool run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err);
   // append: add this batch's queries after the ones already in `out` (pipelined chunks)
+  // first phase of a fetch (optional; fetch_batch runs it when the caller has not): waits for the run, starts the
+  // D2H copy of the results and launches the re-run of queries whose hit list overflowed, without waiting for it
+  bool fetch_begin(DeviceBatch* b, std::string* err, int* status);
   bool fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status);
   void free_batch(DeviceBatch* b);  // returns the buffers to the cache
   // stage_ms[6]: Bloom stage, exact stage (the whole fused probe kernel when the split path is off), prefilter,
@@ -138,8 +151,8 @@ class Engine {
   // post-pass of one query's device records -> final variants (confusables, re-sort, cut-off); appends to `out`
   void finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
                     std::vector<anl_variant>* out) const;
-  bool rerun_hit_overflow(DeviceBatch* b, const std::vector<uint32_t>& which, std::vector<OutHead>* heads,
-                          std::vector<OutRec>* recs, std::string* err, int* status);
+  bool rerun_launch(DeviceBatch* b, std::string* err, int* status);   // b->rr_which -> kernels on b->rr_stream
+  bool rerun_collect(DeviceBatch* b, std::string* err, int* status);  // sync; b->rr_heads / b->rr_recs
   bool ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
                        std::string* err);
   bool grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err);

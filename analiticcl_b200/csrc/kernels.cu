@@ -1655,6 +1655,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 
     uint32_t nsurv = 0;
     double maxfreq = 0.0;
+#ifdef ANL_ROUND_STATS
+    uint32_t nvalid_q = 0;
+#endif
 
     for (uint32_t hb = 0; hb < nh; hb += 32) {
       const uint32_t hi = hb + lane;
@@ -1698,8 +1701,12 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       const uint32_t vmask = __ballot_sync(FULL, valid);
       if (vmask == 0) continue;
       const uint32_t Lcm = __reduce_max_sync(FULL, valid ? Lc : 0u);
+#ifdef ANL_ROUND_STATS  // experiment: dp_pairs = DP rounds executed, dp_cells = rounds the within-distance candidates alone would need
+      c_dpp += lane == 0 ? 1 : 0;
+#else
       c_dpp += valid ? 1 : 0;
       c_dpc += (unsigned long long)Lq * Lcm;  // per lane: x 32 lanes in the sum = warp-cells of this batch
+#endif
 
       // ---- true Damerau-Levenshtein, all lanes in lock-step over (i, j) -----------------------
       // Row i of the matrix lives in ring slot (i mod R), R = max edit distance + 2: only the last
@@ -1797,6 +1804,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
       maxfreq = fmax(maxfreq, mf);
       c_surv += valid ? 1 : 0;
+#ifdef ANL_ROUND_STATS
+      nvalid_q += __popc(__ballot_sync(FULL, valid));
+#endif
       const bool keep = valid && score >= bp.score_threshold;
       const uint32_t kmask = __ballot_sync(FULL, keep);
       if (keep) {
@@ -1814,6 +1824,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
       __syncwarp();
     }
 
+#ifdef ANL_ROUND_STATS
+    c_dpc += lane == 0 ? (nvalid_q + 31) / 32 : 0;
+#endif
     ConfStage cs;
     if (qblob && ix->conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
       const uint32_t b0 = qboff[q], b1 = qboff[q + 1];

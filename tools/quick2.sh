@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 W=${W:-cfg2}
 for envs in "$@"; do
-  env $envs timeout 600 python bench.py --workload $W --steps 3 --warmup 3 --e2e-steps 1 --cpu-sample 64 > gpurun_out/ab.json 2> gpurun_out/ab.err
+  env $envs timeout 600 python bench.py --workload $W --steps 3 --warmup 3 --e2e-steps ${E2E:-1} --cpu-sample 64 > gpurun_out/ab.json 2> gpurun_out/ab.err
   python - <<PY
 import json
 try:
