@@ -388,7 +388,7 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
   else
     bp->finish_mode = hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP;
   if (hm_->index.n_shards > 1) bp->finish_mode = FINISH_SHARD;  // ranking happens after the exchange (shard_merge)
-  uint32_t hit_cap = 2048;
+  uint32_t hit_cap = 4096;
   if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = (uint32_t)std::max(1, atoi(e));
   bp->hit_cap = hit_cap;
   const uint32_t kcap = std::min<uint32_t>(threshold_cap(p.max_anagram_distance), ANL_MAX_K);
@@ -428,7 +428,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
 
 void Engine::free_batch(DeviceBatch* b) {
   if (!b) return;
-  if (cache_.size() < 6) {
+  if (cache_.size() < 8) {
     b->owned_blob.clear();
     b->owned_blob.shrink_to_fit();
     b->blob = nullptr;
@@ -944,6 +944,7 @@ bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
   lb.work = b->d_work;
   lb.counters = nullptr;
   CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, st));
+  CU_TRY(launch_prefilter(d_ix_, bp, lb, sm_count_, st));
   CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, st));
   b->rr_bp = bp;
   b->rr_pending = true;
@@ -1317,12 +1318,12 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
     out->flags.reserve((size_t)n);
   }
   // Batches in flight, oldest first (each with its own streams).  Once DEPTH are queued the oldest is settled
-  // (fetch_begin: wait for its run, start the D2H copy, launch the re-run of overflowed queries) and the one
-  // settled in the previous round is finished on the host, so a re-run never has the host waiting for it.
+  // (fetch_begin: wait for its run, start the D2H copy, launch the re-run of overflowed queries) and the ones
+  // settled in earlier rounds are finished on the host, so a re-run does not have the host waiting for it.
   size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
   if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(4, std::max(1, atoi(e)));
   std::deque<DeviceBatch*> inflight;
-  DeviceBatch* settled = nullptr;
+  std::deque<DeviceBatch*> settled;
   bool ok = true;
   auto fail_with = [&](const std::string& e2, int s2) {
     if (ok) {
@@ -1331,17 +1332,17 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
       *status = s2;
     }
   };
-  auto finish_settled = [&]() {
-    if (!settled) return;
+  auto finish_front = [&]() {
+    DeviceBatch* f = settled.front();
+    settled.pop_front();
     std::string e2;
     int s2 = ANL_OK;
-    if (ok && !fetch_batch(settled, out, true, &e2, &s2)) fail_with(e2, s2);
+    if (ok && !fetch_batch(f, out, true, &e2, &s2)) fail_with(e2, s2);
     if (!ok) {
-      cudaStreamSynchronize(settled->stream);
-      if (settled->rr_stream) cudaStreamSynchronize(settled->rr_stream);
+      cudaStreamSynchronize(f->stream);
+      if (f->rr_stream) cudaStreamSynchronize(f->rr_stream);
     }
-    free_batch(settled);
-    settled = nullptr;
+    free_batch(f);
   };
   auto settle_oldest = [&]() {
     DeviceBatch* f = inflight.front();
@@ -1349,8 +1350,9 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
     std::string e2;
     int s2 = ANL_OK;
     if (ok && !fetch_begin(f, &e2, &s2)) fail_with(e2, s2);
-    finish_settled();  // (the previous one: its re-run had this whole round to complete)
-    settled = f;
+    settled.push_back(f);
+    // a re-run is a few warps with long dependent chains (milliseconds): it gets three rounds to complete
+    while (!settled.empty() && settled.size() > (settled.front()->rr_pending ? 3u : 1u)) finish_front();
   };
   for (uint64_t lo = 0; ok && (lo < n || (n == 0 && lo == 0)); lo += CHUNK) {
     const uint64_t m = std::min(CHUNK, n - lo);
@@ -1368,7 +1370,7 @@ bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint
     if (!ok) cudaStreamSynchronize(inflight.front()->stream);
     settle_oldest();
   }
-  finish_settled();
+  while (!settled.empty()) finish_front();
   if (ok) *status = ANL_OK;
   return ok;
 }

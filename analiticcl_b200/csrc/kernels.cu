@@ -1041,7 +1041,10 @@ __device__ __noinline__ bool verify_general_q(const DeviceIndex* __restrict__ ix
   return ok && ck.w0 == k0 && ck.w1 == k1 && ck.w2 == k2;
 }
 
-__global__ void __launch_bounds__(KX_WARPS * 32)
+#ifndef ANL_KX_MIN_CTAS
+#define ANL_KX_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(KX_WARPS * 32, ANL_KX_MIN_CTAS)
 exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, const QEntry* __restrict__ queue, uint32_t queue_cap,
              const QCtx* __restrict__ qctx, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_count,
@@ -1569,7 +1572,10 @@ prefilter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const
   }
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32, 6)
+#ifndef ANL_K2_MIN_CTAS
+#define ANL_K2_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(K2_WARPS * 32, ANL_K2_MIN_CTAS)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
              ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,

@@ -56,7 +56,7 @@ except (OSError, ValueError):
 md = [f"# ncu summary {tag}", "",
       "Source: `tools/profile.sh` under gpurun (1x B200, `--clock-control none`). Full `.ncu-rep` files stay in",
       "`gpurun_out/` (scratch); this file holds what the numbers in DESIGN.md / bench.py are read from.", ""]
-for name in ("bloom", "exact", "score"):
+for name in ("bloom", "exact", "score", "confusable"):
     rep = os.path.join(OUT, f"prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
