@@ -419,6 +419,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
     if (ev) cudaEventDestroy(ev);
   if (b->uploaded) cudaEventDestroy(b->uploaded);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_merged) cudaEventDestroy(b->ev_merged);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->aux) cudaStreamDestroy(b->aux);
   if (b->rr_stream) cudaStreamDestroy(b->rr_stream);
@@ -1109,13 +1110,9 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
                       reinterpret_cast<const uint32_t*>(d_gids_all), (uint32_t)record_stride,
                       reinterpret_cast<const uint32_t*>(d_flags_all), b->d_qflags, b->d_out, b->d_head, b->d_scratch, cap,
                       b->d_work, sm_count_, st));
-  if (b->events.empty()) {
-    cudaEvent_t ev = nullptr;
-    CU_TRY(cudaEventCreate(&ev));
-    b->events.push_back(ev);
-  }
-  CU_TRY(cudaEventRecord(b->events[0], st));
-  b->last_done = b->events[0];
+  if (!b->ev_merged) CU_TRY(cudaEventCreateWithFlags(&b->ev_merged, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(b->ev_merged, st));  // (not one of the per-run timing events: timings() stays valid)
+  b->last_done = b->ev_merged;
   b->merged = true;
   b->bp.finish_mode = b->final_mode;  // the host post-pass of fetch_batch follows the final mode
   b->bp.pool_cap = b->cap_pool;

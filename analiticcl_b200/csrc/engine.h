@@ -84,6 +84,7 @@ struct DeviceBatch {
   cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
   cudaStream_t aux = nullptr;       // side stream: the long-query class of the score kernel runs beside the short one
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_merged = nullptr;  // end of shard_merge
   // EV_PER_RUN events (start, after the Bloom stage, after probe, after prefilter, after score, after confusables,
   // after finish) per run since the last timings() call
   std::vector<cudaEvent_t> events;

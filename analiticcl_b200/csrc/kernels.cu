@@ -769,6 +769,7 @@ __device__ __forceinline__ void queue_push(QEntry* __restrict__ queue, uint32_t 
   }
 }
 
+constexpr uint32_t KB_HEAVY_LEN = 16;  // queries at least this long are enumerated in the first phase
 __global__ void __launch_bounds__(KB_WARPS * 32, ANL_KB_MIN_CTAS)
 bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
              const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* __restrict__ qflags, unsigned int* work, Counters* counters,
@@ -796,11 +797,31 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   qc.pos = qc.end = 0;
   uint32_t c_dkeys = 0, c_probes = 0, c_pass = 0;
 
+  // Long queries first (their neighbourhood grows with C(L, k)): phase 0 walks the batch four queries per grab and
+  // takes the long ones, phase 1 (its own counter, work[6]) the rest -- see score_kernel for the reason.
+  uint32_t gbase = 0, gmask = 0, phase = 0;
   for (;;) {
-    uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(work, 1u);
-    qi = __shfl_sync(FULL, qi, 0);
-    if (qi >= nq) break;
+    if (gmask == 0) {
+      const uint32_t grab = phase == 0 ? 4u : 1u;  // (few per grab: a warp works its grab off serially)
+      if (lane == 0) gbase = atomicAdd(phase == 0 ? work : work + 6, grab);
+      gbase = __shfl_sync(FULL, gbase, 0);
+      if (gbase >= nq) {
+        if (phase == 0) {
+          phase = 1;
+          continue;
+        }
+        break;
+      }
+      bool mine = false;
+      if (lane < grab && gbase + lane < nq) {
+        const uint32_t q0 = qlist ? qlist[gbase + lane] : gbase + lane;
+        mine = (queries[(size_t)q0 * bp.query_stride] >= KB_HEAVY_LEN) == (phase == 0);
+      }
+      gmask = __ballot_sync(FULL, mine);
+      if (gmask == 0) continue;
+    }
+    const uint32_t qi = gbase + (uint32_t)__ffs(gmask) - 1;
+    gmask &= gmask - 1;
     const uint32_t q = qlist ? qlist[qi] : qi;
     const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
     const uint32_t L = qrow[0];
@@ -1572,6 +1593,7 @@ prefilter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const
   }
 }
 
+constexpr uint32_t K2_HEAVY_HITS = 64;  // more candidates than two rounds of 32: scored in the first phase
 #ifndef ANL_K2_MIN_CTAS
 #define ANL_K2_MIN_CTAS 6
 #endif
@@ -1581,8 +1603,8 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
              ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
              uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
-             unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min, uint32_t need_max,
-             uint32_t scratch_cta0) {
+             unsigned int* work_light, unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min,
+             uint32_t need_max, uint32_t scratch_cta0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -1608,20 +1630,32 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
   // candidate = min(longest entry, query length + max edit distance)): the launch for short queries gets by
   // with a fraction of the shared memory, i.e. more resident warps.  The launch for the long ones takes 32
   // queries per counter increment and tests their class one per lane (it skips nearly all of them).
-  const uint32_t grab = need_min > 0 ? 32u : 1u;
-  uint32_t gbase = 0, gmask = 0;
+  // Heavy queries first: a query is one warp's job from start to end, so the kernel cannot end before its
+  // heaviest query does; started last, a query with a thousand candidates is the whole tail of a 65 k-query
+  // chunk.  Phase 0 walks the batch four queries per grab and takes those with more than two rounds of
+  // candidates, phase 1 (its own counter) takes the rest one query per grab.
+  uint32_t gbase = 0, gmask = 0, phase = 0;
   for (;;) {
     if (gmask == 0) {
-      if (lane == 0) gbase = atomicAdd(work, grab);
+      const uint32_t grab = need_min > 0 ? 32u : (phase == 0 ? 4u : 1u);  // (few per grab: a warp works its grab off serially)
+      if (lane == 0) gbase = atomicAdd(phase == 0 ? work : work_light, grab);
       gbase = __shfl_sync(FULL, gbase, 0);
-      if (gbase >= nq) break;
+      if (gbase >= nq) {
+        if (phase == 0) {
+          phase = 1;
+          continue;
+        }
+        break;
+      }
       bool mine = false;
       if (lane < grab && gbase + lane < nq) {
         const uint32_t f0 = qflags[gbase + lane];
         const uint32_t q0 = qlist ? qlist[gbase + lane] : gbase + lane;
         const uint32_t L0 = queries[(size_t)q0 * bp.query_stride];
-        const uint32_t need = (f0 & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
-        mine = need >= need_min && need <= need_max;
+        const bool skip0 = (f0 & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) != 0;
+        const uint32_t need = skip0 ? 0u : min(max_len, L0 + apply_threshold(bp.max_edit, L0));
+        const bool heavy = !skip0 && hit_count[gbase + lane] > K2_HEAVY_HITS;
+        mine = need >= need_min && need <= need_max && heavy == (phase == 0);
       }
       gmask = __ballot_sync(FULL, mine);
       if (gmask == 0) continue;
@@ -2095,7 +2129,7 @@ cudaError_t launch_probe(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   cudaError_t e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   if (split) {
-    e = cudaMemsetAsync(lb.work + 4, 0, 2 * sizeof(unsigned int), stream);  // queue length, exact-stage work counter
+    e = cudaMemsetAsync(lb.work + 4, 0, 3 * sizeof(unsigned int), stream);  // queue length, exact-stage work counter, Bloom phase 1
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(lb.hit_count, 0, (size_t)lb.n * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -2184,7 +2218,7 @@ static long long score_class_grid(const BatchParams& bp, const LaunchBuffers& lb
 
 static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
                                       cudaStream_t stream, uint32_t cols, uint32_t need_min, uint32_t need_max, unsigned int* work,
-                                      long long grid, uint32_t scratch_cta0) {
+                                      unsigned int* work_light, long long grid, uint32_t scratch_cta0) {
   const uint32_t R = ring_depth(bp);
   const size_t smem = k2_warp_bytes(cols, R) * K2_WARPS;
   if (grid < 1) return cudaErrorInvalidConfiguration;
@@ -2192,8 +2226,8 @@ static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
   score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.conf_work,
                                                                 lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
-                                                                lb.out_head, scratch, work, lb.work + 2, lb.counters, cols, R,
-                                                                need_min, need_max, scratch_cta0);
+                                                                lb.out_head, scratch, work, work_light, lb.work + 2, lb.counters,
+                                                                cols, R, need_min, need_max, scratch_cta0);
   ++g_kernel_launches;
   return cudaGetLastError();
 }
@@ -2210,9 +2244,11 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   if (lb.n == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // work counter, pool cursor, confusable queue
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(lb.work + 6, 0, 2 * sizeof(unsigned int), stream);  // second-phase work counters of the two classes
+  if (e != cudaSuccess) return e;
   const uint32_t ML = h_ix.max_len;
   if (ML <= K2_SHORT_COLS + 4)
-    return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, 0, ML, lb.work + 1, score_class_grid(bp, lb, sm_count, ML), 0);
+    return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, 0, ML, lb.work + 1, lb.work + 6, score_class_grid(bp, lb, sm_count, ML), 0);
   const long long grid_a = score_class_grid(bp, lb, sm_count, K2_SHORT_COLS);
   // the longest query of the batch bounds what the second class can need (a symbol takes at least one byte)
   const uint32_t longest = bp.query_stride - 2, kmax = ring_depth(bp) - 2;
@@ -2232,17 +2268,17 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
     if ((e = cudaEventRecord(lb.ev_fork, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(lb.aux_stream, lb.ev_fork, 0)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), lb.aux_stream)) != cudaSuccess) return e;
-    e = launch_score_class(d_ix, bp, lb, sm_count, lb.aux_stream, ML, K2_SHORT_COLS + 1, ML, lb.work, grid_b, (uint32_t)grid_a);
+    e = launch_score_class(d_ix, bp, lb, sm_count, lb.aux_stream, ML, K2_SHORT_COLS + 1, ML, lb.work, lb.work + 7, grid_b, (uint32_t)grid_a);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(lb.ev_join, lb.aux_stream)) != cudaSuccess) return e;
   }
-  e = launch_score_class(d_ix, bp, lb, sm_count, stream, K2_SHORT_COLS, 0, K2_SHORT_COLS, lb.work + 1, grid_a, 0);
+  e = launch_score_class(d_ix, bp, lb, sm_count, stream, K2_SHORT_COLS, 0, K2_SHORT_COLS, lb.work + 1, lb.work + 6, grid_a, 0);
   if (e != cudaSuccess) return e;
   if (beside) return cudaStreamWaitEvent(stream, lb.ev_join, 0);
   if (!second) return cudaSuccess;
   e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
   if (e != cudaSuccess) return e;
-  return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work, grid_b, 0);
+  return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work, lb.work + 7, grid_b, 0);
 }
 
 // The device confusable stage: edit scripts of the queued pairs, then re-rank / crop / cut-off per query.
