@@ -154,6 +154,31 @@ def test_capacity_overflow_rerun(A, eng_oracle, monkeypatch):
     assert_same(got, exp, qs, "overflow")
 
 
+@pytest.mark.parametrize("inflight", ["1", "4"])
+def test_chunk_pipeline_with_reruns(A, eng_oracle, monkeypatch, inflight):
+    """The batch call cuts the queries into chunks with several batches in flight and fetches them in two phases;
+    chunks whose hit lists overflow get an asynchronous re-run that is collected rounds later.  Small chunks and a
+    small capacity make some chunks overflow and others not: the results must still be the oracle's, in order."""
+    monkeypatch.setenv("ANL_CHUNK", "1024")
+    monkeypatch.setenv("ANL_INFLIGHT", inflight)
+    monkeypatch.setenv("ANL_HIT_CAP", "96")
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path("eng"))
+    m.build()
+    words = workloads.read_words("eng")
+    # long words (few candidates: no overflow) and short ones (many candidates) in alternating stretches
+    long_q = workloads.misspellings(words, 6000, 7, min_len=12, max_len=24)
+    short_q = workloads.misspellings(words, 6000, 8, min_len=3, max_len=6)
+    qs = []
+    for k in range(0, 6000, 1500):
+        qs += long_q[k:k + 1500] + short_q[k:k + 1500]
+    qs = qs[:11000] + [""] + qs[11000:]
+    sp = A.SearchParameters()
+    got = m.find_variants_raw(qs, sp)
+    exp = eng_oracle.find_variants_batch(qs, to_orc_params(sp), threads=0)
+    assert_same(got, exp, qs, f"pipeline inflight={inflight}")
+
+
 @pytest.mark.parametrize("per_query", ["3", "100000"], ids=["queue overflow -> fused rerun", "roomy queue"])
 def test_split_probe_queue(A, eng, eng_oracle, monkeypatch, per_query):
     """Split probe path (Bloom stage -> global queue of staged nodes -> exact stage): a queue that is too small is
