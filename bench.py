@@ -380,7 +380,7 @@ def run_ours(args):
 
 def run_search(args):
     """--workload cfg3: search mode.  find_all_matches over synthetic running text with n-gram spans
-    (max_ngram = 3): host segmentation + two pipelined GPU batches per window; the FST consolidation
+    (max_ngram = 3): host segmentation + pipelined GPU batches per window; the FST consolidation
     stage is out of scope.  A "query" is one n-gram segment lookup."""
     import torch
     import analiticcl_b200 as A
@@ -428,7 +428,7 @@ def run_search(args):
         "config": {"workload": f"cfg3: find_all_matches over {n_tokens} tokens of synthetic running text, max_ngram=3, k=3 (eng)",
                    "segments": n, "segment_lookups": lookups, "looked_up_fraction": frac,
                    "distinct_strings_sent_to_gpu": distinct, "text_bytes": len(raw),
-                   "value_scope": "end to end through anl_find_all_matches (host segmentation, two pipelined GPU batches per "
+                   "value_scope": "end to end through anl_find_all_matches (host segmentation, pipelined GPU batches per "
                                   "window, result assembly); query = one n-gram segment lookup"},
         "tokens_per_s": n_tokens / dt,
         "e2e": {"value": lookups / dt, "unit": "queries/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
