@@ -12,8 +12,7 @@ echo "$W $Q" > gpurun_out/profile_launch.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --workload $W --queries $Q --steps 2 --warmup 3 --e2e-steps 0 --cpu-sample 64 > gpurun_out/launches_bench.json 2> gpurun_out/launches.err
 for K in bloom exact score confusable; do
-  S=3
-  [ $K = score ] && S=2  # two score launches per pass (24-column class first): capture the first class of pass 2
+  S=3  # (score: two launches per pass, the long-query class first on its side stream; 3 skipped = the short class of pass 2)
   ncu --set full --clock-control none --import-source on -k regex:${K}_kernel -s $S -c 1 -f -o gpurun_out/prof_$K \
       python bench.py --workload $W --queries $Q --steps 1 --warmup 3 --e2e-steps 0 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_$K.err
 done
