@@ -1108,13 +1108,18 @@ static bool confusable_found_in(const Confusable& c, const std::vector<EditInstr
 enum { VT_NONE = 0, VT_INDEXED = 1, VT_LM = 2, VT_TRANSPARENT = 4 };  // src/vocab.rs:31-49
 enum { FH_SUM = 0, FH_MAX = 1, FH_MIN = 2, FH_REPLACE = 3 };          // src/vocab.rs:100-106
 
-struct VocabValue {  // src/vocab.rs:7-29 (variants: out of scope)
+struct VocabValue {  // src/vocab.rs:7-29
   std::string text;
   NormString norm;
   uint32_t frequency;
   uint8_t tokencount;
   uint32_t lexindex;
   uint8_t vocabtype;
+  // `variants: Option<Vec<VariantReference>>` (src/vocab.rs:22, :52-61): the VariantOf entries in insertion order;
+  // has_variants = the Option is Some (it also is for an item that only holds ReferenceFor entries)
+  std::vector<std::pair<uint64_t, double>> variant_of;
+  std::vector<uint64_t> reference_for;
+  bool has_variants = false;
 };
 struct IndexNode {  // src/index.rs:8-12
   std::vector<uint64_t> instances;
@@ -1137,9 +1142,11 @@ struct Params {  // the subset of src/types.rs:110-168 that the path reads
   int32_t max_ngram;
   int32_t unicodeoffsets;
 };
-struct Result {  // src/types.rs:326-332 (via: out of scope, always none)
+static const uint64_t NO_VIA = ~0ull;
+struct Result {  // src/types.rs:326-332
   uint64_t vocab_id;
   double dist_score, freq_score;
+  uint64_t via;  // NO_VIA = None
 };
 struct Stats {
   uint64_t queries, modulo_tests, deletions, anagram_hits, dl_pairs, dl_cells, survivors;
@@ -1164,7 +1171,7 @@ struct Model {
   void init_vocab() {  // src/vocab.rs:150-181
     const char* names[3] = {"<bos>", "<eos>", "<unk>"};
     for (int i = 0; i < 3; ++i) {
-      decoder.push_back(VocabValue{names[i], {}, 0, 1, 0, VT_NONE});
+      decoder.push_back(VocabValue{names[i], {}, 0, 1, 0, VT_NONE, {}, {}, false});
       encoder[names[i]] = i;
     }
   }
@@ -1242,6 +1249,31 @@ struct Model {
     return id;
   }
 
+  // src/lib.rs:460-514 (add_variant + add_variant_by_id)
+  bool add_variant(uint64_t ref_id, const std::string& variant, double score, bool has_freq, uint32_t freq, int freq_handling,
+                   int vocab_type, int lex_index) {
+    const uint64_t variantid = add_to_vocabulary(variant, has_freq, freq, freq_handling, vocab_type, lex_index);
+    if (variantid == ref_id) return false;
+    {
+      VocabValue& r = decoder[ref_id];  // link reference to variant: only the first mention counts
+      r.has_variants = true;
+      if (std::find(r.reference_for.begin(), r.reference_for.end(), variantid) == r.reference_for.end())
+        r.reference_for.push_back(variantid);
+    }
+    {
+      VocabValue& v = decoder[variantid];  // link variant to reference
+      const bool had = v.has_variants;
+      v.has_variants = true;
+      // the reference compares the stored *target* with the variant's own id (:505-508), so a repeated
+      // (reference, variant) pair is stored again; only an entry pointing at the variant itself would block it
+      bool exists = false;
+      if (had)
+        for (auto& e : v.variant_of) exists = exists || e.first == variantid;
+      if (!exists) v.variant_of.push_back({ref_id, score});
+    }
+    return true;
+  }
+
   // src/lib.rs:519-568
   int read_vocabulary(const std::string& filename, int text_column, int freq_column, int freq_handling, int vocab_type) {
     std::ifstream f(filename, std::ios::binary);
@@ -1272,6 +1304,76 @@ struct Model {
         }
       }
       add_to_vocabulary(fields[text_column], true, frequency, freq_handling, vocab_type, lex_index);
+    }
+    lexicons.push_back(filename);
+    return 0;
+  }
+
+  // src/lib.rs:766-897: weighted variant list, TSV: reference [freq] (variant score [freq])*
+  static bool parse_u32_strict(const std::string& fs, uint32_t* out) {  // str::parse::<u32>()
+    if (fs.empty()) return false;
+    size_t i = fs[0] == '+' ? 1 : 0;
+    if (i >= fs.size()) return false;
+    unsigned long long v = 0;
+    for (; i < fs.size(); ++i) {
+      if (fs[i] < '0' || fs[i] > '9') return false;
+      v = v * 10 + (unsigned)(fs[i] - '0');
+      if (v > 0xFFFFFFFFULL) return false;
+    }
+    *out = (uint32_t)v;
+    return true;
+  }
+  int read_variants(const std::string& filename, int freq_handling, int vocab_type, bool transparent) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) return -1;
+    const int lex_index = (int)(lexicons.size() & 0xFF);
+    const int variant_type = transparent ? (vocab_type | VT_TRANSPARENT) : vocab_type;
+    int has_freq = -1;  // Option<bool>: -1 = not decided yet
+    std::string line;
+    while (std::getline(f, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty()) continue;
+      std::vector<std::string> fields;
+      size_t fp = 0;
+      for (;;) {
+        size_t tab = line.find('\t', fp);
+        fields.push_back(line.substr(fp, tab == std::string::npos ? std::string::npos : tab - fp));
+        if (tab == std::string::npos) break;
+        fp = tab + 1;
+      }
+      bool have = false;
+      uint32_t freq = 0;
+      if (has_freq < 0) {  // auto-detect (:815-830)
+        if (fields.size() < 2) return -2;  // reference: usize underflow panic
+        if ((fields.size() - 2) % 3 == 0) {
+          if (parse_u32_strict(fields[1], &freq)) {
+            has_freq = 1;
+            have = true;
+          }  // else: stays undecided, this line is read as (variant, score) pairs
+        } else {
+          has_freq = 0;
+        }
+      } else if (has_freq == 1) {
+        if (fields.size() < 2 || !parse_u32_strict(fields[1], &freq)) return -3;  // reference: expect() panic
+        have = true;
+      }
+      const uint64_t ref_id = add_to_vocabulary(fields[0], have, freq, freq_handling, vocab_type, lex_index);
+      if (has_freq == 1) {
+        for (size_t k = 2; k + 2 < fields.size(); k += 3) {
+          char* end = nullptr;
+          const double score = strtod(fields[k + 1].c_str(), &end);
+          uint32_t vf = 0;
+          if (fields[k + 1].empty() || *end != '\0' || !parse_u32_strict(fields[k + 2], &vf)) return -4;
+          add_variant(ref_id, fields[k], score, true, vf, freq_handling, variant_type, lex_index);
+        }
+      } else {
+        for (size_t k = 1; k + 1 < fields.size(); k += 2) {
+          char* end = nullptr;
+          const double score = strtod(fields[k + 1].c_str(), &end);
+          if (fields[k + 1].empty() || *end != '\0') return -4;
+          add_variant(ref_id, fields[k], score, false, 0, freq_handling, variant_type, lex_index);
+        }
+      }
     }
     lexicons.push_back(filename);
     return 0;
@@ -1460,6 +1562,7 @@ struct Model {
                                      const Params& p, Stats* st) const {
     std::vector<Result> results;
     double max_freq = 0.0;
+    bool has_expandable_variants = false;
     const double weights_sum = weights.ld + weights.lcs + weights.prefix + weights.suffix + weights.case_;
     const double L = (double)input_length;
     for (const Instance& in : instances) {
@@ -1479,14 +1582,36 @@ struct Model {
       double score = acc / weights_sum;
       double freq_score = have_freq ? (double)item.frequency : 1.0;
       if (freq_score > max_freq) max_freq = freq_score;
-      if (score >= p.score_threshold) results.push_back(Result{in.vocab_id, score, freq_score});
+      if (item.has_variants) has_expandable_variants = true;  // :1464 (before the score threshold)
+      if (score >= p.score_threshold) results.push_back(Result{in.vocab_id, score, freq_score, NO_VIA});
     }
     if (st) st->survivors += instances.size();
     if (!confusables.empty() && confusables_before_pruning)
       for (Result& r : results) r.dist_score *= compute_confusable_weight(input, r.vocab_id);
+    if (has_expandable_variants) {  // :1510-1518 + expand_variants :1677-1727
+      std::vector<Result> expanded;
+      expanded.reserve(results.size());
+      for (const Result& r : results) {
+        const VocabValue& item = decoder[r.vocab_id];
+        for (auto& vr : item.variant_of) {
+          const double target_freq = (double)decoder[vr.first].frequency;
+          // (the minimum of the target's frequency and this result's still absolute frequency score)
+          expanded.push_back(Result{vr.first, r.dist_score * vr.second, target_freq < r.freq_score ? target_freq : r.freq_score,
+                                    r.vocab_id});
+        }
+        if (!(item.vocabtype & VT_TRANSPARENT)) expanded.push_back(r);
+      }
+      results.swap(expanded);
+      for (const Result& r : results)
+        if (r.freq_score > max_freq) max_freq = r.freq_score;
+    }
     if (max_freq > 0.0)
       for (Result& r : results) r.freq_score = r.freq_score / max_freq;
     rank_results(results, p.freq_weight);
+    if (has_expandable_variants)  // :1530-1533 Vec::dedup_by_key: consecutive duplicates only, the first is kept
+      results.erase(std::unique(results.begin(), results.end(),
+                                [](const Result& a, const Result& b) { return a.vocab_id == b.vocab_id; }),
+                    results.end());
     const size_t max_matches = (size_t)p.max_matches;
     if (max_matches > 0 && results.size() > max_matches) {
       double last_score = result_score(results[max_matches - 1], p.freq_weight);
@@ -1705,6 +1830,16 @@ int32_t orc_read_vocabulary(void* h, const char* filename, int32_t text_column, 
 uint64_t orc_add_to_vocabulary(void* h, const char* text, int32_t has_freq, uint32_t freq, int32_t freq_handling,
                                int32_t vocab_type, int32_t lex_index) {
   return ((Model*)h)->add_to_vocabulary(text, has_freq != 0, freq, freq_handling, vocab_type, lex_index);
+}
+int32_t orc_add_variant(void* h, uint64_t ref_id, const char* variant, double score, int32_t has_freq, uint32_t freq,
+                        int32_t freq_handling, int32_t vocab_type, int32_t lex_index) {
+  Model* m = (Model*)h;
+  if (ref_id >= m->decoder.size()) return -1;
+  return m->add_variant(ref_id, variant, score, has_freq != 0, freq, freq_handling, vocab_type, lex_index) ? 1 : 0;
+}
+uint32_t orc_vocab_type(void* h, uint64_t id) { return ((Model*)h)->decoder[id].vocabtype; }
+int32_t orc_read_variants(void* h, const char* filename, int32_t freq_handling, int32_t vocab_type, int32_t transparent) {
+  return ((Model*)h)->read_variants(filename, freq_handling, vocab_type, transparent != 0);
 }
 void orc_set_have_freq(void* h, int32_t v) { ((Model*)h)->have_freq = v != 0; }
 int32_t orc_add_confusable(void* h, const char* script, double weight) {

@@ -38,7 +38,7 @@ class Params(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [("vocab_id", C.c_uint64), ("dist_score", C.c_double), ("freq_score", C.c_double)]
+    _fields_ = [("vocab_id", C.c_uint64), ("dist_score", C.c_double), ("freq_score", C.c_double), ("via", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -111,6 +111,9 @@ def lib():
         "orc_edit_script": (vp, [cp, cp]),
         "orc_confusable_found_in": (i32, [cp, cp, cp]),
         "orc_nearest": (vp, [vp, cp, u32, i32]),
+        "orc_add_variant": (i32, [vp, u64, cp, C.c_double, i32, u32, i32, i32, i32]),
+        "orc_read_variants": (i32, [vp, cp, i32, i32, i32]),
+        "orc_vocab_type": (u32, [vp, u64]),
         "orc_find_variants": (i64, [vp, cp, P(Params), P(Result), i64]),
         "orc_find_variants_batch": (i32, [vp, cp, P(u64), u64, P(Params), i32, P(u64), P(P(Result)), P(Stats)]),
         "orc_free_results": (None, [P(Result)]),
@@ -148,6 +151,7 @@ TEST_ALPHABET_TSV = "\n".join(
 """The 27-class alphabet of the reference's tests (src/test.rs:3-31)."""
 
 VT = {"NONE": 0, "INDEXED": 1, "LM": 2, "TRANSPARENT": 5}
+NO_VIA = (1 << 64) - 1
 FH = {"sum": 0, "max": 1, "min": 2, "replace": 3}
 
 
@@ -183,6 +187,19 @@ class OracleModel:
         return lib().orc_add_to_vocabulary(self.h, text.encode(), frequency is not None, frequency or 0,
                                            FH[freq_handling], VT[vocab_type], index)
 
+    def add_variant(self, ref_id, variant, score, frequency=None, freq_handling="max", vocab_type="INDEXED", index=0):
+        rc = lib().orc_add_variant(self.h, ref_id, variant.encode(), score, frequency is not None, frequency or 0,
+                                   FH[freq_handling], VT[vocab_type] if isinstance(vocab_type, str) else vocab_type, index)
+        if rc < 0:
+            raise ValueError("add_variant: unknown reference id")
+        return bool(rc)
+
+    def read_variants(self, filename, transparent=False, freq_handling="max", vocab_type="INDEXED"):
+        rc = lib().orc_read_variants(self.h, filename.encode(), FH[freq_handling], VT[vocab_type], int(transparent))
+        if rc != 0:
+            raise RuntimeError(f"oracle read_variants({filename}) failed: {rc}")
+        self.nlex += 1
+
     def add_to_confusables(self, script, weight):
         if lib().orc_add_confusable(self.h, script.encode(), weight) != 0:
             raise ValueError("bad confusable pattern " + script)
@@ -202,6 +219,12 @@ class OracleModel:
 
     def vocab_lexindex(self, vid):
         return lib().orc_vocab_lexindex(self.h, vid)
+
+    def vocab_freq(self, vid):
+        return lib().orc_vocab_freq(self.h, vid)
+
+    def vocab_type(self, vid):
+        return lib().orc_vocab_type(self.h, vid)
 
     def vocab_lookup(self, text):
         return lib().orc_vocab_lookup(self.h, text.encode())
@@ -231,16 +254,19 @@ class OracleModel:
         return [int(x) for x in s.split("\n") if x]
 
     # -- queries -----------------------------------------------------------------------------------
-    def find_variants(self, text, params):
+    def find_variants(self, text, params, with_via=False):
         cap = 4096
         while True:
             buf = (Result * cap)()
             n = lib().orc_find_variants(self.h, text.encode(), C.byref(params), buf, cap)
             if n <= cap:
+                if with_via:
+                    return [(buf[i].vocab_id, buf[i].dist_score, buf[i].freq_score, None if buf[i].via == NO_VIA else buf[i].via)
+                            for i in range(n)]
                 return [(buf[i].vocab_id, buf[i].dist_score, buf[i].freq_score) for i in range(n)]
             cap = n
 
-    def find_variants_batch(self, queries, params, threads=0, want_stats=False):
+    def find_variants_batch(self, queries, params, threads=0, want_stats=False, with_via=False):
         """queries: list[str] -> list[list[(vocab_id, dist, freq)]] (+ Stats)."""
         enc = [q.encode("utf-8") for q in queries]
         blob = b"".join(enc)
@@ -258,8 +284,12 @@ class OracleModel:
                                       C.byref(st) if want_stats else None)
         out = []
         for i in range(n):
-            out.append([(res[j].vocab_id, res[j].dist_score, res[j].freq_score)
-                        for j in range(out_offs[i], out_offs[i + 1])])
+            if with_via:
+                out.append([(res[j].vocab_id, res[j].dist_score, res[j].freq_score, None if res[j].via == NO_VIA else res[j].via)
+                            for j in range(out_offs[i], out_offs[i + 1])])
+            else:
+                out.append([(res[j].vocab_id, res[j].dist_score, res[j].freq_score)
+                            for j in range(out_offs[i], out_offs[i + 1])])
         lib().orc_free_results(res)
         return (out, st) if want_stats else out
 

@@ -315,3 +315,56 @@ def test_tutorial_find_all_matches(eng_oracle):
     uni = [s for s in segs if s["n"] == 1]
     assert [(s["text"], s["begin"], s["end"]) for s in uni] == [
         (mm["input"], mm["offset"]["begin"], mm["offset"]["end"]) for mm in GOLD["find_all_matches"]["We would like seperate beds"]]
+
+
+# ---- 0801 variant lists (T:1484-1510; src/lib.rs:460-514, 766-897, 1677-1727) ------------------------
+def test_expand_variants_transparent():
+    m = orc.OracleModel(alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    ref = m.add_to_vocabulary("afgescheid")
+    assert m.add_variant(ref, "afghescheydt", 1.0, vocab_type="TRANSPARENT")
+    m.build()
+    # very strict parameters: the reference form cannot match, the transparent variant can (T:1497-1499)
+    r = m.find_variants("afgheschaydt", orc.make_params(**dict(TEST_PARAMS, max_anagram_distance=2, max_edit_distance=2)),
+                        with_via=True)
+    assert len(r) == 1
+    assert m.vocab_text(r[0][0]) == "afgescheid"
+    assert m.vocab_text(r[0][3]) == "afghescheydt"  # via = the variant that matched
+
+
+def test_expand_variants_semantics(tmp_path):
+    """Non-transparent variants stay in the list next to their reference; the expanded score is dist * variant score;
+    the frequency score is min(reference frequency, the variant's own) before normalisation; consecutive duplicates
+    of one vocabulary id are dropped after ranking (src/lib.rs:1510-1533)."""
+    f = tmp_path / "variants.tsv"
+    f.write_text("separate\tseperate\t0.9\tseparete\t0.8\nhouse\thuose\t0.5\n")
+    m = orc.OracleModel(alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    m.add_to_vocabulary("separated")
+    m.read_variants(str(f), transparent=False)
+    m.build()
+    p = orc.make_params(**dict(TEST_PARAMS, max_anagram_distance=3, max_edit_distance=3))
+    r = m.find_variants("seperate", p, with_via=True)
+    got = [(m.vocab_text(v), round(d, 6), None if via is None else m.vocab_text(via)) for v, d, _, via in r]
+    # "seperate" matches itself exactly (1.0) -> expands to separate at 1.0 * 0.9 via seperate; the direct match of
+    # "separate" scores lower than 0.9, is ranked behind the expanded one and is NOT adjacent to it, so it stays
+    names = [g[0] for g in got]
+    assert got[0] == ("seperate", 1.0, None)
+    assert ("separate", 0.9, "seperate") in got
+    assert names.count("separate") >= 1 and "separete" in names
+    # transparent: the variants themselves disappear, only references remain
+    m2 = orc.OracleModel(alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    m2.add_to_vocabulary("separated")
+    m2.read_variants(str(f), transparent=True)
+    m2.build()
+    r2 = m2.find_variants("seperate", p, with_via=True)
+    names2 = [m2.vocab_text(v) for v, _, _, _ in r2]
+    assert "seperate" not in names2 and "separete" not in names2 and "separate" in names2
+    assert m2.vocab_type(m2.vocab_lookup("seperate")) & 4 and not (m2.vocab_type(m2.vocab_lookup("separate")) & 4)
+
+
+def test_read_variants_with_frequencies(tmp_path):
+    f = tmp_path / "variants_freq.tsv"
+    f.write_text("separate\t100\tseperate\t0.9\t7\nhouse\t50\thuose\t0.5\t2\n")
+    m = orc.OracleModel(alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    m.read_variants(str(f))
+    assert m.vocab_freq(m.vocab_lookup("separate")) == 100 and m.vocab_freq(m.vocab_lookup("seperate")) == 7
+    assert m.vocab_freq(m.vocab_lookup("huose")) == 2
