@@ -239,6 +239,20 @@ class VariantModel:
                                                   C.byref(p), C.byref(vid)))
         return vid.value
 
+    def add_variant(self, ref_id, variant, score, frequency=None, params=None):
+        """add_variant (src/lib.rs:460): link `variant` (added to the vocabulary with `params`) to the entry `ref_id`."""
+        p = (params or VocabParams()).data
+        raw = variant.encode("utf-8")
+        added = C.c_int32()
+        _check(_lib().anl_model_add_variant(self._h, int(ref_id), raw, len(raw), float(score), frequency is not None,
+                                            int(frequency or 0), C.byref(p), C.byref(added)))
+        return bool(added.value)
+
+    def read_variants(self, filename, transparent=False, params=None):
+        """read_variants (bindings/python/src/lib.rs:669-684): weighted variant list; transparent=True for an error list."""
+        p = (params or VocabParams()).data
+        _check(_lib().anl_model_read_variants(self._h, os.fsencode(filename), C.byref(p), int(bool(transparent))))
+
     def read_confusablelist(self, filename):
         _check(_lib().anl_model_read_confusablelist(self._h, os.fsencode(filename)))
 
@@ -250,9 +264,6 @@ class VariantModel:
 
     def read_lm(self, filename):
         raise NotImplementedError("language models are outside the variant-lookup hot path (see DESIGN.md)")
-
-    def read_variants(self, filename, transparent=False):
-        raise NotImplementedError("variant lists are outside the variant-lookup hot path (see DESIGN.md)")
 
     def read_contextrules(self, filename):
         raise NotImplementedError("context rules are outside the variant-lookup hot path (see DESIGN.md)")
@@ -322,13 +333,16 @@ class VariantModel:
         finally:
             _lib().anl_result_set_free(rs)
 
-    def find_variants_raw(self, inputs, params):
-        """Batch lookup returning plain tuples: [[(vocab_id, dist_score, freq_score), ...], ...]."""
+    def find_variants_raw(self, inputs, params, with_via=False):
+        """Batch lookup returning plain tuples: [[(vocab_id, dist_score, freq_score[, via or None]), ...], ...]."""
         rs = self._run(list(inputs), params)
         try:
             n = len(inputs)
             offs = _lib().anl_result_set_offsets(rs)
             var = _lib().anl_result_set_variants(rs)
+            if with_via:
+                return [[(var[j].vocab_id, var[j].dist_score, var[j].freq_score, None if var[j].via == _capi.NO_VIA else var[j].via)
+                         for j in range(offs[i], offs[i + 1])] for i in range(n)]
             return [[(var[j].vocab_id, var[j].dist_score, var[j].freq_score) for j in range(offs[i], offs[i + 1])]
                     for i in range(n)]
         finally:

@@ -83,6 +83,8 @@ SIGNATURES = {
     "anl_model_free": (None, [_vp]),
     "anl_model_read_vocabulary": (_i32, [_vp, _cp, _P(VocabParams)]),
     "anl_model_add_to_vocabulary": (_i32, [_vp, _cp, _sz, _i32, _u32, _P(VocabParams), _P(_u64)]),
+    "anl_model_add_variant": (_i32, [_vp, _u64, _cp, _sz, C.c_double, _i32, _u32, _P(VocabParams), _P(_i32)]),
+    "anl_model_read_variants": (_i32, [_vp, _cp, _P(VocabParams), _i32]),
     "anl_model_read_confusablelist": (_i32, [_vp, _cp]),
     "anl_model_add_to_confusables": (_i32, [_vp, _cp, C.c_double]),
     "anl_model_set_confusables_before_pruning": (None, [_vp]),

@@ -140,6 +140,20 @@ anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t le
   if (vocab_id) *vocab_id = id;
   return ANL_OK;
 }
+anl_status anl_model_add_variant(anl_model* m, uint64_t ref_id, const char* text, size_t len, double score, int32_t has_frequency,
+                                 uint32_t frequency, const anl_vocab_params* params, int32_t* added) {
+  if (!m || !text) return fail(ANL_ERR_INVALID, "null argument");
+  if (ref_id >= m->host.decoder.size()) return fail(ANL_ERR_INVALID, "add_variant: unknown reference id");
+  const bool ok = m->host.add_variant(ref_id, text, len, score, has_frequency != 0, frequency, to_vocab_params(params));
+  if (added) *added = ok ? 1 : 0;
+  return ANL_OK;
+}
+anl_status anl_model_read_variants(anl_model* m, const char* filename, const anl_vocab_params* params, int32_t transparent) {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.read_variants(filename, to_vocab_params(params), transparent != 0, &err)) return fail(ANL_ERR_IO, err);
+  return ANL_OK;
+}
 anl_status anl_model_read_confusablelist(anl_model* m, const char* filename) {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;

@@ -387,6 +387,8 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
     bp->finish_mode = FINISH_FULL;
   else
     bp->finish_mode = hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP;
+  // variant lists: every survivor goes to the host in gather order; expansion, ranking, crop and cut-off follow there
+  if (hm_->any_variants) bp->finish_mode = FINISH_GATHER;
   if (hm_->index.n_shards > 1) bp->finish_mode = FINISH_SHARD;  // ranking happens after the exchange (shard_merge)
   uint32_t hit_cap = 4096;
   if (const char* e = getenv("ANL_HIT_CAP")) hit_cap = (uint32_t)std::max(1, atoi(e));
@@ -594,6 +596,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   b->sharded = hm_->index.n_shards > 1;
   b->merged = false;
   b->final_mode = hm_->confusables.empty() ? FINISH_FULL : (hm_->confusables_before_pruning ? FINISH_GATHER : FINISH_CROP);
+  if (hm_->any_variants) b->final_mode = FINISH_GATHER;
   b->bp = bp;
   pt.lap("create: buffers");
 
@@ -681,7 +684,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     }
     b->has_qblob = true;
   }
-  b->dev_conf = conf_stage && b->has_qblob && b->d_conf_work != nullptr && !b->sharded;
+  b->dev_conf = conf_stage && b->has_qblob && b->d_conf_work != nullptr && !b->sharded && !hm_->any_variants;
   if (b->dev_encode && !b->has_qblob && n > 0) b->dev_encode = false;  // (cannot happen: the text was staged above)
   pt.lap("create: query text");
   if (b->dev_encode) {
@@ -851,8 +854,60 @@ static size_t cutoff_variants(const anl_variant* r, size_t n, double cutoff_thre
   return n;
 }
 
+// Host finish of a query of a model with variant lists (src/lib.rs:1504-1622 with expand_variants :1677-1727):
+// the device delivered every candidate that passed the score threshold, in gather order, with absolute frequencies.
+void Engine::finish_query_variants(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
+                                   std::vector<anl_variant>* out) const {
+  const size_t start = out->size();
+  if (count == 0) return;
+  const char* in = b.blob + b.offsets[qi];
+  const size_t inlen = (size_t)(b.offsets[qi + 1] - b.offsets[qi]);
+  const float fw = b.params.freq_weight;
+  const bool early = !hm_->confusables.empty() && hm_->confusables_before_pruning;
+  const bool late = !hm_->confusables.empty() && !hm_->confusables_before_pruning;
+  bool expand = false;
+  for (uint32_t i = 0; i < count; ++i) expand = expand || hm_->decoder[recs[i].vocab_id & ~OUT_SKIP_CONFUSABLES].has_variants;
+  for (uint32_t i = 0; i < count; ++i) {
+    const uint64_t id = recs[i].vocab_id & ~OUT_SKIP_CONFUSABLES;
+    const bool skip = (recs[i].vocab_id & OUT_SKIP_CONFUSABLES) != 0;
+    double dist = recs[i].dist_score;
+    if (early && !skip) dist *= hm_->compute_confusable_weight(in, inlen, id);
+    const double f = (double)recs[i].freq;
+    const VocabEntry& item = hm_->decoder[id];
+    if (expand) {
+      for (const auto& vr : item.variant_of) {
+        const double tf = (double)hm_->decoder[vr.first].frequency;  // the smaller of the two absolute frequencies
+        out->push_back(anl_variant{vr.first, dist * vr.second, tf < f ? tf : f, id});
+      }
+      if (item.vocabtype & VT_TRANSPARENT) continue;
+    }
+    out->push_back(anl_variant{id, dist, f, ANL_NO_VIA});
+  }
+  size_t n = out->size() - start;
+  anl_variant* v = out->data() + start;
+  if (expand)
+    for (size_t i = 0; i < n; ++i) max_freq = v[i].freq_score > max_freq ? v[i].freq_score : max_freq;
+  if (max_freq > 0.0)
+    for (size_t i = 0; i < n; ++i) v[i].freq_score = v[i].freq_score / max_freq;
+  rank_variants(v, v + n, fw);
+  if (expand) {  // Vec::dedup_by_key(|x| x.vocab_id): consecutive duplicates, the first one stays
+    size_t w = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (w == 0 || v[w - 1].vocab_id != v[i].vocab_id) v[w++] = v[i];
+    n = w;
+  }
+  n = crop_variants(v, n, (size_t)b.params.max_matches, fw);
+  if (late) {  // (every record, expanded ones against their target's text: the triage flags do not survive the expansion)
+    for (size_t i = 0; i < n; ++i) v[i].dist_score *= hm_->compute_confusable_weight(in, inlen, v[i].vocab_id);
+    rank_variants(v, v + n, fw);
+  }
+  n = cutoff_variants(v, n, b.params.cutoff_threshold, fw);
+  out->resize(start + n);
+}
+
 void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
                           std::vector<anl_variant>* out) const {
+  if (hm_->any_variants) return finish_query_variants(b, qi, recs, count, max_freq, out);
   const size_t start = out->size();
   for (uint32_t i = 0; i < count; ++i) {
     // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with

@@ -150,6 +150,8 @@ class Engine {
 
  private:
   // post-pass of one query's device records -> final variants (confusables, re-sort, cut-off); appends to `out`
+  void finish_query_variants(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
+                             std::vector<anl_variant>* out) const;
   void finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
                     std::vector<anl_variant>* out) const;
   bool rerun_launch(DeviceBatch* b, std::string* err, int* status);   // b->rr_which -> kernels on b->rr_stream

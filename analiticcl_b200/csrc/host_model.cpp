@@ -283,6 +283,91 @@ bool HostModel::read_vocabulary(const std::string& filename, const VocabParams& 
   return true;
 }
 
+// src/lib.rs:460-514: the variant is added to the vocabulary and linked with its reference in both directions.
+bool HostModel::add_variant(uint64_t ref_id, const char* text, size_t len, double score, bool has_freq, uint32_t freq,
+                            const VocabParams& p) {
+  const uint64_t vid = add_to_vocabulary(text, len, has_freq, freq, p);
+  if (vid == ref_id) return false;
+  VocabEntry& ref = decoder[ref_id];
+  ref.has_variants = true;  // (only the first mention of a variant counts)
+  if (std::find(ref.reference_for.begin(), ref.reference_for.end(), vid) == ref.reference_for.end()) ref.reference_for.push_back(vid);
+  VocabEntry& var = decoder[vid];
+  // The reference's duplicate check on this side compares the stored target with the variant's own id (:505-508),
+  // so repeating a (reference, variant) pair stores the link again; kept as is, it shows in the expanded results.
+  bool blocked = false;
+  if (var.has_variants)
+    for (const auto& e : var.variant_of) blocked = blocked || e.first == vid;
+  var.has_variants = true;
+  if (!blocked) var.variant_of.emplace_back(ref_id, score);
+  any_variants = true;
+  built = false;
+  return true;
+}
+
+// src/lib.rs:766-897.  TSV: reference (variant score)*, or with frequencies: reference freq (variant score freq)*;
+// which of the two is detected from the first line whose column count fits and whose second column is an integer.
+bool HostModel::read_variants(const std::string& filename, const VocabParams& p_in, bool transparent, std::string* err) {
+  std::ifstream f(filename, std::ios::binary);
+  if (!f) {
+    *err = "cannot open variant list " + filename;
+    return false;
+  }
+  VocabParams p = p_in;
+  p.index = (uint8_t)(lexicons.size() & 0xFF);
+  VocabParams pv = p;
+  if (transparent) pv.vocab_type |= VT_TRANSPARENT;
+  enum { UNDECIDED, WITH_FREQ, WITHOUT_FREQ } layout = UNDECIDED;
+  std::string line;
+  size_t lineno = 0;
+  std::vector<std::pair<size_t, size_t>> col;
+  auto field = [&](size_t k) { return std::string(line.data() + col[k].first, col[k].second); };
+  auto bad = [&](const char* what) {
+    *err = std::string(what) + " (line " + std::to_string(lineno) + " of " + filename + ")";
+    return false;
+  };
+  while (std::getline(f, line)) {
+    ++lineno;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    col.clear();
+    for (size_t b = 0;;) {
+      const size_t t = line.find('\t', b);
+      col.emplace_back(b, (t == std::string::npos ? line.size() : t) - b);
+      if (t == std::string::npos) break;
+      b = t + 1;
+    }
+    bool have = false;
+    uint32_t freq = 0;
+    if (layout == UNDECIDED) {
+      if (col.size() < 2) return bad("a variant list line needs at least a reference and one variant");
+      if ((col.size() - 2) % 3 == 0) {
+        if (parse_u32(field(1), &freq)) {
+          layout = WITH_FREQ;
+          have = true;
+        }
+      } else {
+        layout = WITHOUT_FREQ;
+      }
+    } else if (layout == WITH_FREQ) {
+      if (col.size() < 2 || !parse_u32(field(1), &freq)) return bad("frequency must be an integer");
+      have = true;
+    }
+    const uint64_t ref_id = add_to_vocabulary(line.data() + col[0].first, col[0].second, have, freq, p);
+    const size_t first = layout == WITH_FREQ ? 2 : 1, step = layout == WITH_FREQ ? 3 : 2;
+    for (size_t k = first; k + step <= col.size(); k += step) {
+      const std::string sc = field(k + 1);
+      char* end = nullptr;
+      const double score = strtod(sc.c_str(), &end);
+      if (sc.empty() || *end != '\0') return bad("variant scores must be floating point values");
+      uint32_t vf = 0;
+      if (layout == WITH_FREQ && !parse_u32(field(k + 2), &vf)) return bad("variant frequency must be an integer");
+      add_variant(ref_id, line.data() + col[k].first, col[k].second, score, layout == WITH_FREQ, vf, pv);
+    }
+  }
+  lexicons.push_back(filename);
+  return true;
+}
+
 bool HostModel::add_to_confusables(const std::string& editscript, double weight, std::string* err) {
   Confusable c;
   if (!parse_confusable(editscript, weight, &c)) {
@@ -381,6 +466,21 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   }
   ix.shard = shard;
   ix.n_shards = n_shards;
+  if (any_variants) {
+    // Results are expanded on the host from the candidates that pass the score threshold.  The reference decides
+    // *whether* to expand from every instance within the edit distance (src/lib.rs:1464); the two differ only for
+    // a transparent entry that holds no variant reference (it is dropped iff the list is expanded at all).
+    if (n_shards > 1) {
+      *err = "variant lists are not supported in the lexicon-sharded mode";
+      return false;
+    }
+    for (size_t id = 3; id < decoder.size(); ++id)
+      if ((decoder[id].vocabtype & VT_TRANSPARENT) && !decoder[id].has_variants) {
+        *err = "a transparent entry without variant references (" + decoder[id].text +
+               ") next to variant lists is not supported by the GPU path";
+        return false;
+      }
+  }
   if (alphabet.size() + 1 > 168) {
     *err = "alphabet has more classes than there are primes (168)";
     return false;

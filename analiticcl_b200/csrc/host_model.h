@@ -41,6 +41,10 @@ struct VocabEntry {  // src/vocab.rs:7-29
   uint8_t vocabtype = VT_NONE;
   bool first_lower = false;  // char::is_lowercase of the first char (src/lib.rs:1367-1374)
   bool ascii = false;        // text is pure ASCII (bytes == Unicode scalar values)
+  // variants: Option<Vec<VariantReference>> (src/vocab.rs:22, :52-61)
+  std::vector<std::pair<uint64_t, double>> variant_of;  // VariantOf(target id, score), insertion order
+  std::vector<uint64_t> reference_for;                  // ReferenceFor(variant id)
+  bool has_variants = false;                            // the Option is Some
 };
 
 // Greedy alphabet matcher (src/anahash.rs:16-80) with a first-byte dispatch table instead of
@@ -115,6 +119,9 @@ class HostModel {
   void read_alphabet_text(const std::string& tsv) { alphabet.load_tsv(tsv); }
   bool read_vocabulary(const std::string& filename, const VocabParams& p, std::string* err);
   uint64_t add_to_vocabulary(const char* text, size_t len, bool has_freq, uint32_t freq, const VocabParams& p);
+  // weighted variant lists (src/lib.rs:460-514, 766-897); ref_id must exist
+  bool add_variant(uint64_t ref_id, const char* text, size_t len, double score, bool has_freq, uint32_t freq, const VocabParams& p);
+  bool read_variants(const std::string& filename, const VocabParams& p, bool transparent, std::string* err);
   bool add_to_confusables(const std::string& editscript, double weight, std::string* err);
   bool read_confusablelist(const std::string& filename, std::string* err);
   // src/lib.rs:192-245: anagram values, grouping, ordering -> flat arrays (host side of build())
@@ -141,6 +148,7 @@ class HostModel {
   std::unordered_map<std::string, uint64_t> encoder;
   std::vector<std::string> lexicons;
   bool have_freq = false;
+  bool any_variants = false;  // some entry holds variant references: results are expanded on the host (expand_variants)
   std::vector<Confusable> confusables;
   bool confusables_before_pruning = false;
   bool all_confusables_simple = true;

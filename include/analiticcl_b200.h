@@ -93,7 +93,7 @@ typedef struct anl_variant {
   uint64_t vocab_id;
   double dist_score;
   double freq_score;
-  uint64_t via; /* ANL_NO_VIA = None (variant lists are out of scope, so always None) */
+  uint64_t via; /* ANL_NO_VIA = None; else the vocabulary id of the variant this result was reached through (variant lists) */
 } anl_variant;
 
 /* VocabValue, src/vocab.rs:7-29 (read-only view) */
@@ -127,6 +127,16 @@ void anl_model_free(anl_model* m);
 
 /* read_vocabulary (src/lib.rs:519) */
 anl_status anl_model_read_vocabulary(anl_model* m, const char* filename, const anl_vocab_params* params);
+/* add_variant (src/lib.rs:460-514): adds `text` to the vocabulary (with `params`; set ANL_VOCAB_TRANSPARENT for an
+ * error list whose entries should only lead to their reference) and links it to the existing entry `ref_id` with
+ * `score`.  *added = 0 when the variant is the reference itself.  Results of later lookups are expanded
+ * (expand_variants, src/lib.rs:1677-1727): a matched variant also yields its reference with dist_score * score and
+ * via = the variant's id. */
+anl_status anl_model_add_variant(anl_model* m, uint64_t ref_id, const char* text, size_t len, double score, int32_t has_frequency,
+                                 uint32_t frequency, const anl_vocab_params* params, int32_t* added);
+/* read_variants (src/lib.rs:766-897): TSV weighted variant list, `reference (variant score)*` or
+ * `reference freq (variant score freq)*` (auto-detected). */
+anl_status anl_model_read_variants(anl_model* m, const char* filename, const anl_vocab_params* params, int32_t transparent);
 /* add_to_vocabulary (src/lib.rs:900); has_frequency=0 means None */
 anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t len, int32_t has_frequency,
                                        uint32_t frequency, const anl_vocab_params* params, uint64_t* vocab_id);

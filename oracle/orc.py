@@ -220,6 +220,9 @@ class OracleModel:
     def vocab_lexindex(self, vid):
         return lib().orc_vocab_lexindex(self.h, vid)
 
+    def vocab_size(self):
+        return lib().orc_vocab_size(self.h)
+
     def vocab_freq(self, vid):
         return lib().orc_vocab_freq(self.h, vid)
 

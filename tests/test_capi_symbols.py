@@ -62,3 +62,33 @@ def test_search_parameters_surface():
     assert w.to_dict() == {"ld": 0.6, "lcs": 0.125, "prefix": 0.125, "suffix": 0.125, "case": 0.125}
     v = A.VocabParams(freq_column=2, vocabtype="TRANSPARENT", freqhandling="sum")
     assert v.freq_column == 2 and v.data.vocab_type == 5 and v.data.freq_handling == 0
+
+
+def test_variant_list_loading_matches_oracle(tmp_path):
+    """Host side of the variant lists (no GPU needed): read_variants / add_variant build the same vocabulary as the
+    oracle -- ids in order of first mention, frequencies, the TRANSPARENT flag -- for both file layouts."""
+    import ctypes as C
+    import analiticcl_b200 as A
+    from analiticcl_b200 import _capi
+    from oracle import orc
+    import workloads
+    plain = tmp_path / "v.tsv"
+    plain.write_text("separate\tseperate\t0.9\tseparete\t0.8\nhouse\thuose\t0.5\nseparate\tseperate\t0.7\nodd\todd\t1.0\n")
+    freq = tmp_path / "vf.tsv"
+    freq.write_text("separate\t100\tseperate\t0.9\t7\nhouse\t50\thuose\t0.5\t2\thuose\t0.4\t9\n")
+    for path, transparent in ((plain, False), (plain, True), (freq, True)):
+        m = A.VariantModel(workloads.ALPHABET, A.Weights())
+        o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+        rid = m.add_to_vocabulary("separated", 3)
+        assert rid == o.add_to_vocabulary("separated", 3)
+        m.read_variants(str(path), transparent=transparent)
+        o.read_variants(str(path), transparent=transparent)
+        assert m.add_variant(rid, "seperated", 0.6) and o.add_variant(rid, "seperated", 0.6, index=0)
+        assert not m.add_variant(rid, "separated", 1.0)  # a variant of itself is refused
+        n = _capi.lib().anl_model_vocab_size(m._h)
+        assert n == o.vocab_size()
+        for vid in range(3, n):
+            info = m._vocab(vid)
+            assert C.string_at(info.text, info.text_len).decode() == o.vocab_text(vid)
+            assert info.frequency == o.vocab_freq(vid), o.vocab_text(vid)
+            assert info.vocabtype == o.vocab_type(vid), o.vocab_text(vid)

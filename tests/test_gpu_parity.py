@@ -405,3 +405,65 @@ def test_find_all_matches_large_text_equals_piecewise(A, eng):
     assert len(whole) == len(exp)
     bad = [i for i, (g, e) in enumerate(zip(whole, exp)) if g != e]
     assert not bad, (len(bad), whole[bad[0]], exp[bad[0]])
+
+
+# ---- variant lists (SURVEY 8 "next" row f-4; src/lib.rs:460-514, 766-897, 1677-1727) ------------------------
+def _variant_list(words, path, seed, with_freq):
+    """A synthetic error list: ~3000 references from the lexicon, each with 1-3 misspelt variants and scores."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    refs = [words[int(i)] for i in rng.choice(len(words), size=3000, replace=False) if len(words[int(i)]) >= 5]
+    lines = []
+    for k, r in enumerate(refs):
+        vs = workloads.misspellings([r], int(rng.integers(1, 4)), seed + k, min_len=1, max_len=99)
+        cols = [r] + (["%d" % int(rng.integers(1, 1000))] if with_freq else [])
+        for v in vs:
+            cols += [v, "%.2f" % float(rng.uniform(0.3, 1.0))] + (["%d" % int(rng.integers(1, 50))] if with_freq else [])
+        lines.append("\t".join(cols))
+    lines.insert(5, lines[0])  # a repeated line: the (reference, variant) links are stored again (reference quirk)
+    path.write_text("\n".join(lines) + "\n")
+
+
+def assert_same_via(got, exp, queries, tag):
+    bad = []
+    for i, (g, e) in enumerate(zip(got, exp)):
+        if [(v, bits(d), bits(f), via) for v, d, f, via in g] != [(v, bits(d), bits(f), via) for v, d, f, via in e]:
+            bad.append((i, queries[i], g[:4], e[:4], len(g), len(e)))
+    assert len(got) == len(exp) and not bad, f"{tag}: {len(bad)} / {len(got)} queries differ, first: {bad[:3]}"
+
+
+@pytest.mark.parametrize("transparent,with_freq,confusables", [(False, False, None), (True, False, None), (True, True, "late"),
+                                                             (False, True, "early")])
+def test_variant_lists(A, tmp_path, transparent, with_freq, confusables):
+    words = workloads.read_words("eng")
+    f = tmp_path / "variants.tsv"
+    _variant_list(words, f, 17, with_freq)
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    lex = workloads.lexicon_path("eng")
+    if with_freq:
+        lex = workloads.nld_freq_lexicon()  # a lexicon with a frequency column (have_freq = true)
+        words = workloads.read_words("nld")
+        _variant_list(words, f, 17, with_freq)
+    m.read_lexicon(lex)
+    o.read_lexicon(lex)
+    m.read_variants(str(f), transparent=transparent)
+    o.read_variants(str(f), transparent=transparent)
+    if confusables:
+        for pat, wt in workloads.CFG2_CONFUSABLES:
+            m.add_to_confusables(pat, wt)
+            o.add_to_confusables(pat, wt)
+        if confusables == "early":
+            m.set_confusables_before_pruning()
+            o.set_confusables_before_pruning()
+    m.build()
+    o.build()
+    # queries: the variants themselves, further misspellings of them, and ordinary misspellings
+    listed = [c for ln in f.read_text().splitlines() for c in ln.split("\t")[(2 if with_freq else 1)::(3 if with_freq else 2)]]
+    qs = listed[:1500] + workloads.misspellings(listed, 1000, 5, min_len=1, max_len=99) + workloads.misspellings(words, 1000, 6)
+    for kw in (dict(), dict(max_matches=3, freq_weight=0.25), dict(max_matches=0, cutoff_threshold=1.5)):
+        sp = A.SearchParameters(**kw)
+        got = m.find_variants_raw(qs, sp, with_via=True)
+        exp = o.find_variants_batch(qs, to_orc_params(sp), threads=0, with_via=True)
+        assert_same_via(got, exp, qs, f"variants transparent={transparent} freq={with_freq} conf={confusables} {kw}")
+    assert any(via is not None for r in got for *_, via in r)
