@@ -93,7 +93,7 @@ inline unsigned host_threads() {
 }
 
 // Persistent worker pool for the host phases of a batch (encode, post-pass, assembly).  Three
-// parallel phases per 131072-query chunk used to mean ~48 thread creations per chunk; the pool's
+// parallel phases per chunk of the batch call used to mean ~48 thread creations per chunk; the pool's
 // workers sleep on a condition variable between phases instead.  One job at a time: a second caller
 // (another model / another host thread) that finds the pool busy runs its ranges on fresh threads.
 class HostPool {

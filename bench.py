@@ -293,7 +293,7 @@ def run_ours(args):
         e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop()
     if e2e_steps > 0:
-        launches += L.anl_kernel_launches() - launches_e2e0  # the batch call works in chunks of 131072 queries
+        launches += L.anl_kernel_launches() - launches_e2e0  # the batch call works in chunks of 65536 queries
     ist = m.index_stats()
     max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
     stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
