@@ -198,11 +198,12 @@ def _check(status):
 class VariantModel:
     """VariantModel(alphabet_file, weights, debug=0) -- bindings/python/src/lib.rs:548-812.
 
-    In scope: read_lexicon, read_vocabulary, add_to_vocabulary, read_confusablelist,
-    set_confusables_before_pruning, build, __contains__, find_variants, find_variants_par,
-    find_all_matches.  Out of scope (raise NotImplementedError): read_lm, read_variants,
-    read_contextrules, add_contextrule -- the language-model / FST stage is not part of the
-    variant-lookup hot path.
+    In scope: read_lexicon, read_vocabulary, add_to_vocabulary, read_variants, add_variant,
+    read_confusablelist, set_confusables_before_pruning, build, __contains__, find_variants,
+    find_variants_par, find_all_matches (with the variant-model part of the sequence consolidation).
+    Out of scope (raise NotImplementedError): read_lm, read_contextrules, add_contextrule -- the
+    language-model and context-rule terms of the sequence score are not part of the variant-lookup
+    hot path.
     """
 
     def __init__(self, alphabet_file, weights=None, debug=0, alphabet_tsv=None):
@@ -350,29 +351,39 @@ class VariantModel:
 
     def find_all_matches(self, text, params):
         """bindings/python/src/lib.rs:752-805: [{"input", "offset": {"begin","end"}, "variants": [...]}, ...]
-        with the selected variant first.  See the C header for the (documented) difference when
-        max_ngram > 1: no FST consolidation, every looked-up segment is returned."""
+        with the selected variant first.  With max_ngram > 1 the matches are the most likely sequence per
+        hard-delimited batch (most_likely_sequence, src/lib.rs:1912-1924, 2088-2495; variant-model scores only: no
+        LM, no context rules), like the reference.  `consolidate_matches=False` (which the reference's library
+        carries but never reads) returns the producer's view instead: every looked-up segment of every order."""
         raw = text.encode("utf-8")
         ms = C.c_void_p()
         _check(_lib().anl_find_all_matches(self._h, raw, len(raw), C.byref(params.data), C.byref(ms)))
         try:
-            lexnames = self._lexicon_names()
-            fw = params.data.freq_weight
-            cpmode = bool(params.data.unicodeoffsets)
-            out = []
-            m = _capi.Match()
-            for i in range(_lib().anl_match_set_len(ms)):
-                _check(_lib().anl_match_set_get(ms, i, C.byref(m)))
-                if not m.variants and params.data.max_ngram > 1 and m.n > 1:
-                    continue  # higher-order segment skipped as redundant: no lookup happened
-                seg = text[m.begin:m.end] if cpmode else raw[m.begin:m.end].decode("utf-8")
-                variants = [self._variant_dict(m.variants[j], fw, lexnames) for j in range(m.n_variants)]
-                if m.selected > 0:
-                    variants.insert(0, variants.pop(m.selected))
-                out.append({"input": seg, "offset": {"begin": int(m.begin), "end": int(m.end)}, "variants": variants})
-            return out
+            if params.data.max_ngram > 1 and params.data.consolidate_matches:
+                best = C.c_void_p()
+                _check(_lib().anl_match_set_consolidate(ms, raw, len(raw), C.byref(params.data), C.byref(best)))
+                _lib().anl_match_set_free(ms)
+                ms = best
+            return self._match_list(ms, text, raw, params)
         finally:
             _lib().anl_match_set_free(ms)
+
+    def _match_list(self, ms, text, raw, params):
+        lexnames = self._lexicon_names()
+        fw = params.data.freq_weight
+        cpmode = bool(params.data.unicodeoffsets)
+        out = []
+        m = _capi.Match()
+        for i in range(_lib().anl_match_set_len(ms)):
+            _check(_lib().anl_match_set_get(ms, i, C.byref(m)))
+            if not m.variants and params.data.max_ngram > 1 and m.n > 1:
+                continue  # higher-order segment skipped as redundant: no lookup happened
+            seg = text[m.begin:m.end] if cpmode else raw[m.begin:m.end].decode("utf-8")
+            variants = [self._variant_dict(m.variants[j], fw, lexnames) for j in range(m.n_variants)]
+            if m.selected > 0:
+                variants.insert(0, variants.pop(m.selected))
+            out.append({"input": seg, "offset": {"begin": int(m.begin), "end": int(m.end)}, "variants": variants})
+        return out
 
     # -- introspection used by tests / benchmarks -------------------------------------------------------
     def vocab_text(self, vid):

@@ -573,6 +573,105 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   *out = ms;
   return ANL_OK;
 }
+// most_likely_sequence per hard-delimited batch (src/lib.rs:1912-1924, 2088-2495): host post-pass over the
+// match set of anl_find_all_matches.  The segments are re-derived from the text (cheap next to the lookups) so
+// that the match set itself stays a flat list; batches are independent and run on all cores.
+anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
+                                     anl_match_set** out) {
+  if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  const std::string t(text ? text : "", len);
+  SegmentedText st;
+  segment_text(t, params->max_ngram, &st);
+  if (st.segs.size() != in->matches.size())
+    return fail(ANL_ERR_INVALID, "match set does not belong to this text / max_ngram (segment count differs)");
+  const std::vector<Boundary>& bounds = find_boundaries(t);
+  std::vector<BatchDesc> descs;
+  if (!t.empty()) list_batches(bounds, &descs);
+  const size_t nbatch = st.batch_first.size() - 1;
+  if (descs.size() != nbatch) return fail(ANL_ERR_INVALID, "match set does not belong to this text (batch count differs)");
+  const float fw = params->freq_weight;
+  const bool run_fst = params->max_ngram > 1;  // :1912 (no LM, no context rules in this build)
+  // per batch: the chosen (segment, variant) steps; thread-local lists keep the batch order
+  const unsigned nt_max = host_threads();
+  std::vector<std::vector<SequenceStep>> part(nt_max);
+  std::vector<std::vector<uint64_t>> part_count(nt_max);  // steps per batch
+  std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+  const unsigned used = parallel_ranges(nbatch, 64, [&](unsigned tid, uint64_t lo, uint64_t hi) {
+    range[tid] = {lo, hi};
+    std::vector<SequenceStep> steps;
+    std::vector<uint32_t> count;
+    std::vector<uint64_t> first;
+    std::vector<double> score;
+    for (uint64_t b = lo; b < hi; ++b) {
+      const uint64_t s0 = st.batch_first[b], s1 = st.batch_first[b + 1];
+      const size_t before = part[tid].size();
+      bool chosen = false;
+      if (run_fst) {
+        count.clear();
+        first.clear();
+        score.clear();
+        for (uint64_t k = s0; k < s1; ++k) {
+          const anl_match& mm = in->matches[k];
+          const uint32_t c = mm.variants ? (uint32_t)mm.n_variants : 0;
+          count.push_back(c);
+          first.push_back(score.size());
+          for (uint32_t j = 0; j < c; ++j) {  // VariantResult::score, src/types.rs:335-341
+            const anl_variant& v = mm.variants[j];
+            score.push_back(fw == 0.0f ? v.dist_score : (v.dist_score + ((double)fw * v.freq_score)) / (1.0 + (double)fw));
+          }
+        }
+        const BatchDesc& d = descs[b];
+        chosen = most_likely_sequence(bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, bounds[d.end_index].begin,
+                                      st.segs.data() + s0, s1 - s0, BatchVariants{count.data(), first.data(), score.data()},
+                                      &steps);
+        if (chosen)
+          part[tid].insert(part[tid].end(), steps.begin(), steps.end());
+      }
+      if (!chosen)  // unigram-only models (:1929-1932) and empty lattices (:2261-2267): every match as it is
+        for (uint64_t k = s0; k < s1; ++k) part[tid].push_back(SequenceStep{(uint32_t)(k - s0), in->matches[k].selected});
+      part_count[tid].push_back(part[tid].size() - before);
+    }
+  });
+  anl_match_set* ms = new anl_match_set();
+  ms->logical_lookups = in->logical_lookups;
+  ms->distinct_lookups = in->distinct_lookups;
+  uint64_t nout = 0, nvar = 0;
+  for (unsigned tid = 0; tid < used; ++tid) {
+    size_t pos = 0;
+    for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
+      const uint64_t c = part_count[tid][b - range[tid].first];
+      for (uint64_t i = 0; i < c; ++i, ++pos) {
+        const anl_match& mm = in->matches[st.batch_first[b] + part[tid][pos].seg];
+        if (mm.variants) nvar += mm.n_variants;
+      }
+      nout += c;
+    }
+  }
+  ms->matches.resize(nout);
+  ms->variants.reserve(nvar + 1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
+  ms->variants.resize(nvar);
+  uint64_t o = 0, v = 0;
+  for (unsigned tid = 0; tid < used; ++tid) {
+    size_t pos = 0;
+    for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
+      const uint64_t c = part_count[tid][b - range[tid].first];
+      for (uint64_t i = 0; i < c; ++i, ++pos) {
+        const SequenceStep& s = part[tid][pos];
+        anl_match mm = in->matches[st.batch_first[b] + s.seg];
+        mm.selected = s.variant < 0 ? -1 : s.variant;
+        if (mm.variants) {
+          if (mm.n_variants) memcpy(ms->variants.data() + v, mm.variants, (size_t)mm.n_variants * sizeof(anl_variant));
+          mm.variants = ms->variants.data() + v;
+          v += mm.n_variants;
+        }
+        ms->matches[o++] = mm;
+      }
+    }
+  }
+  *out = ms;
+  return ANL_OK;
+}
+
 // ---- test hooks for the host-side producer (no model, no GPU needed) ------------------------------------------
 int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin, uint64_t* end, int32_t* strength, size_t cap) {
   const std::string t(text ? text : "", len);
@@ -598,6 +697,38 @@ int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram,
       batch[k] = (uint32_t)b;
     }
   return (int64_t)st.segs.size();
+}
+
+// A match set as anl_find_all_matches assembles it, from caller-supplied variant lists (one per segment, in the
+// producer's order) instead of GPU lookups: lets the CPU tests drive anl_match_set_consolidate.
+anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_ngram, int32_t unicodeoffsets,
+                                     const uint8_t* looked, const uint64_t* offsets, const anl_variant* variants, uint64_t nseg,
+                                     anl_match_set** out) {
+  if (!out || (!text && len > 0) || (nseg && (!looked || !offsets))) return fail(ANL_ERR_INVALID, "null argument");
+  const std::string t(text ? text : "", len);
+  SegmentedText st;
+  segment_text(t, max_ngram, &st);
+  if (st.segs.size() != nseg) return fail(ANL_ERR_INVALID, "segment count differs from the producer's");
+  std::vector<uint64_t> cpmap;
+  if (unicodeoffsets) cpmap = byte_to_codepoint_map(t);
+  anl_match_set* ms = new anl_match_set();
+  ms->matches.resize(nseg);
+  ms->variants.reserve((nseg ? offsets[nseg] : 0) + 1);
+  ms->variants.resize(nseg ? offsets[nseg] : 0);
+  if (nseg && offsets[nseg]) memcpy(ms->variants.data(), variants, (size_t)offsets[nseg] * sizeof(anl_variant));
+  for (uint64_t k = 0; k < nseg; ++k) {
+    const SegmentSpan& sp = st.segs[k];
+    anl_match& mm = ms->matches[k];
+    const uint64_t cnt = looked[k] ? offsets[k + 1] - offsets[k] : 0;
+    mm.begin = unicodeoffsets ? cpmap[sp.begin] : sp.begin;
+    mm.end = unicodeoffsets ? cpmap[sp.end] : sp.end;
+    mm.n = sp.n;
+    mm.n_variants = cnt;
+    mm.selected = (looked[k] && cnt > 0) ? 0 : -1;
+    mm.variants = looked[k] ? ms->variants.data() + offsets[k] : nullptr;
+  }
+  *out = ms;
+  return ANL_OK;
 }
 
 uint64_t anl_match_set_len(const anl_match_set* ms) { return ms ? ms->matches.size() : 0; }

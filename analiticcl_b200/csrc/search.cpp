@@ -8,6 +8,7 @@
 #include "search.h"
 
 #include <algorithm>
+#include <limits>
 
 #include "hostpool.h"
 #include "unicode_tables.h"
@@ -118,6 +119,18 @@ void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t n
   }
 }
 
+// the batches: spans between hard boundaries (src/lib.rs:1822)
+void list_batches(const std::vector<Boundary>& bounds, std::vector<BatchDesc>* out) {
+  out->clear();
+  size_t begin = 0, begin_index = 0;
+  for (size_t i = 0; i < bounds.size(); ++i) {
+    if (bounds[i].strength != BOUNDARY_HARD || bounds[i].begin == begin) continue;
+    out->push_back(BatchDesc{begin, begin_index, i});
+    begin = bounds[i].end;
+    begin_index = i + 1;
+  }
+}
+
 void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp) {
   SegmentedText& st = *stp;
   st.segs.clear();
@@ -125,23 +138,10 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
   st.batch_first[0] = 0;
   if (text.empty()) return;
   const std::vector<Boundary>& bounds = find_boundaries(text);
-  // the batches: spans between hard boundaries (src/lib.rs:1822)
-  struct Desc {
-    size_t begin, begin_index, end_index;
-  };
   // (a lambda naming a thread_local would see the executing thread's instance: bind it to a local reference)
-  static thread_local std::vector<Desc> descs_tl;
-  std::vector<Desc>& descs = descs_tl;
-  descs.clear();
-  {
-    size_t begin = 0, begin_index = 0;
-    for (size_t i = 0; i < bounds.size(); ++i) {
-      if (bounds[i].strength != BOUNDARY_HARD || bounds[i].begin == begin) continue;
-      descs.push_back(Desc{begin, begin_index, i});
-      begin = bounds[i].end;
-      begin_index = i + 1;
-    }
-  }
+  static thread_local std::vector<BatchDesc> descs_tl;
+  std::vector<BatchDesc>& descs = descs_tl;
+  list_batches(bounds, &descs);
   const size_t nb = descs.size();
   const unsigned nt_max = host_threads();
   std::vector<std::vector<SegmentSpan>*> part(nt_max, nullptr);
@@ -156,7 +156,7 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
     std::vector<SegmentSpan>& out = scratch;
     if (hi > lo) out.reserve((descs[hi - 1].end_index - descs[lo].begin_index + 1) * (size_t)max_ngram + 16);
     for (uint64_t k = lo; k < hi; ++k) {
-      const Desc& d = descs[k];
+      const BatchDesc& d = descs[k];
       const size_t before = out.size();
       for (uint32_t order = 1; order <= max_ngram; ++order)
         find_match_ngrams(text, bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, order, d.begin,
@@ -172,6 +172,115 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
       if (part[t] && !part[t]->empty())
         std::copy(part[t]->begin(), part[t]->end(), st.segs.data() + st.batch_first[range[t].first]);
   });
+}
+
+// most_likely_sequence, src/lib.rs:2088-2495, without language model and context rules.
+//
+// The reference hands a weighted FST to rustfst (start state + one state per boundary of the batch; a transition
+// per (segment, variant) from the boundary before the segment to the boundary after it, cost n + (1 - score) in
+// f32 with n = tokens covered; cost n + 1 for a unigram without variants, copied from the input; cost 100 for
+// the epsilon fail-safe between neighbouring states) and, with nothing but the variant model to weigh, keeps the
+// cheapest of the n shortest paths.  States are ordered by position, every transition points forward, so the
+// cheapest path is a single sweep over the states: best[t] = min over incoming transitions of best[from] + cost,
+// accumulated in f32 from the start state like the path weight rustfst reports.  Transitions are bucketed by
+// their target state (counting sort) in (source state, segment, variant) order, and only a strictly lower cost
+// replaces the incumbent: among equal-cost paths the earliest source state, then the earliest transition wins
+// (rustfst's own choice among ties is not pinned by any reference test).
+bool most_likely_sequence(const Boundary* bounds, size_t nbounds, size_t end_offset, const SegmentSpan* segs, size_t nsegs,
+                          const BatchVariants& variants, std::vector<SequenceStep>* out) {
+  out->clear();
+  struct Arc {
+    uint32_t from, seg;
+    int32_t variant;  // -1 = out of vocabulary, -2 = epsilon
+    float cost;
+  };
+  const size_t nstates = nbounds + 1;  // 0 = start, 1 + i = boundary i
+  // boundary positions -> state: begin offsets and end offsets are both ascending, binary search replaces the
+  // reference's scan over all boundaries per match (:2142-2148; offsets are unique, so "last hit" = "the hit")
+  auto state_ending_at = [&](size_t pos) -> long {  // boundary whose end == pos
+    size_t lo = 0, hi = nbounds;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (bounds[mid].end < pos) lo = mid + 1; else hi = mid;
+    }
+    return (lo < nbounds && bounds[lo].end == pos) ? (long)lo : -1;
+  };
+  auto state_starting_at = [&](size_t pos) -> long {  // boundary whose begin == pos
+    size_t lo = 0, hi = nbounds;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (bounds[mid].begin < pos) lo = mid + 1; else hi = mid;
+    }
+    return (lo < nbounds && bounds[lo].begin == pos) ? (long)lo : -1;
+  };
+  static thread_local std::vector<Arc> arcs, by_target;
+  static thread_local std::vector<uint32_t> target, fill;
+  arcs.clear();
+  target.clear();
+  size_t labelled = 0;
+  for (size_t k = 0; k < nsegs; ++k) {
+    const long next = state_starting_at(segs[k].end);
+    if (next < 0) continue;  // cannot happen for producer segments (the reference would panic)
+    const long prev = state_ending_at(segs[k].begin);
+    const long n = prev >= 0 ? next - prev : next + 1;
+    const uint32_t from = prev >= 0 ? (uint32_t)prev + 1 : 0;
+    const uint32_t cnt = variants.count[k];
+    if (cnt > 0) {
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const float cost = (float)n + (1.0f - (float)variants.score[variants.first[k] + j]);  // :2203-2204
+        arcs.push_back(Arc{from, (uint32_t)k, (int32_t)j, cost});
+        target.push_back((uint32_t)next + 1);
+      }
+      labelled += cnt;
+    } else if (n == 1) {
+      arcs.push_back(Arc{from, (uint32_t)k, -1, (float)n + 1.0f});  // :2223
+      target.push_back((uint32_t)next + 1);
+      ++labelled;
+    }
+  }
+  if (labelled == 0) return false;
+  for (size_t i = 0; i < nbounds; ++i) {  // fail-safe, :2249-2259
+    arcs.push_back(Arc{(uint32_t)i, 0, -2, 100.0f});
+    target.push_back((uint32_t)i + 1);
+  }
+  // bucket by target state; inside a bucket order by source state (stable counting sort over the arc list, which
+  // is in (segment, variant) order) so that the sweep below sees candidates in (source, segment, variant) order
+  fill.assign(nstates + 1, 0);
+  for (uint32_t t : target) ++fill[t + 1];
+  for (size_t s = 0; s < nstates; ++s) fill[s + 1] += fill[s];
+  by_target.resize(arcs.size());
+  {
+    std::vector<uint32_t> order(arcs.size());
+    for (size_t a = 0; a < arcs.size(); ++a) order[a] = (uint32_t)a;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return arcs[x].from < arcs[y].from; });
+    std::vector<uint32_t> cursor(fill.begin(), fill.end() - 1);
+    for (uint32_t a : order) by_target[cursor[target[a]]++] = arcs[a];
+  }
+  const float INF = std::numeric_limits<float>::infinity();
+  std::vector<float> best(nstates, INF);
+  std::vector<int64_t> via(nstates, -1);  // index into by_target
+  best[0] = 0.0f;
+  for (size_t t = 1; t < nstates; ++t) {
+    for (uint32_t a = fill[t]; a < fill[t + 1]; ++a) {
+      const Arc& arc = by_target[a];
+      if (best[arc.from] == INF) continue;
+      const float c = best[arc.from] + arc.cost;
+      if (c < best[t]) {
+        best[t] = c;
+        via[t] = a;
+      }
+    }
+  }
+  long fin = -1;  // final states, :2119-2122
+  for (size_t i = 0; i < nbounds; ++i)
+    if ((bounds[i].begin == end_offset || bounds[i].end == end_offset) && (fin < 0 || best[i + 1] < best[fin])) fin = (long)i + 1;
+  if (fin < 0 || best[fin] == INF) return false;
+  for (size_t t = (size_t)fin; t != 0; t = by_target[via[t]].from) {
+    const Arc& arc = by_target[via[t]];
+    if (arc.variant != -2) out->push_back(SequenceStep{arc.seg, arc.variant});
+  }
+  std::reverse(out->begin(), out->end());
+  return true;
 }
 
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text) {

@@ -26,10 +26,36 @@ struct SegmentedText {
   PodBuffer<uint64_t> batch_first;  // index of each batch's first segment; n_batches + 1 entries
 };
 
+// A batch = the text between two hard boundaries (src/lib.rs:1822): it starts at byte `begin`, its boundaries are
+// bounds[begin_index .. end_index] and bounds[end_index] is the hard boundary that closes it.
+struct BatchDesc {
+  size_t begin, begin_index, end_index;
+};
+void list_batches(const std::vector<Boundary>& bounds, std::vector<BatchDesc>* out);
+
 const std::vector<Boundary>& find_boundaries(const std::string& text);  // valid until the calling thread's next call
 void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order, size_t begin, size_t end,
                        std::vector<SegmentSpan>* out);
 void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* out);
+
+// One step of the most likely sequence of a batch: segment `seg` (index into the batch's segments) rendered as its
+// variant `variant`, or copied from the input (out of vocabulary) when variant < 0.
+struct SequenceStep {
+  uint32_t seg;
+  int32_t variant;
+};
+// Per segment of the batch: how many variants its lookup returned (0 also for segments that were not looked up)
+// and the f64 score (VariantResult::score, src/types.rs:335-341) of variant j at score[first[seg] + j].
+struct BatchVariants {
+  const uint32_t* count;
+  const uint64_t* first;
+  const double* score;
+};
+// most_likely_sequence (src/lib.rs:2088-2495) for a model without language model and context rules: the
+// lowest-cost path through the batch's segment lattice.  Returns false when the lattice has no arcs (the
+// reference then returns the matches unchanged, :2261-2267).
+bool most_likely_sequence(const Boundary* bounds, size_t nbounds, size_t end_offset, const SegmentSpan* segs, size_t nsegs,
+                          const BatchVariants& variants, std::vector<SequenceStep>* out);
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text);
 
 }  // namespace anl

@@ -196,11 +196,11 @@ uint32_t anl_result_set_flags(const anl_result_set* rs, uint64_t i);
 void anl_result_set_free(anl_result_set* rs);
 
 /* find_all_matches (src/lib.rs:1790).  Host segmentation (boundaries, n-gram spans, redundant-match
- * pruning) feeding the batched GPU lookup.  The FST/LM consolidation stage
- * (most_likely_sequence, src/lib.rs:2088) is out of scope: with max_ngram == 1 and no LM/context
- * rules the reference does not run it either and results are identical; with max_ngram > 1 every
- * segment of every order is returned with its variant list and `selected` = 0 where it has variants
- * (i.e. the `consolidate_matches = false` view). */
+ * pruning) feeding the batched GPU lookup.  The call returns the producer's view: every segment of every
+ * order with its variant list and `selected` = 0 where it has variants.  With max_ngram == 1 (and no
+ * LM/context rules) that is the reference's result; with max_ngram > 1 the reference goes on to pick one
+ * segmentation per hard-delimited batch (most_likely_sequence, src/lib.rs:1912-1924, 2088-2495) --
+ * anl_match_set_consolidate below does that as a host post-pass over this match set. */
 anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, const anl_search_params* params,
                                 anl_match_set** out);
 typedef struct anl_match {
@@ -218,6 +218,17 @@ void anl_match_set_free(anl_match_set* ms);
  * producer de-duplicates identical segments inside a window). */
 void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_lookups, uint64_t* distinct_strings);
 
+/* most_likely_sequence (src/lib.rs:2088-2495) for a model without language model and context rules: per
+ * hard-delimited batch, the lowest-cost path through the lattice of looked-up segments (cost of a variant =
+ * tokens covered + 1 - score, f32; unigram without variants = copied from the input at cost 2; fail-safe
+ * epsilon at cost 100).  `in` must be the match set anl_find_all_matches returned for the same text and
+ * params->max_ngram; `*out` is a new, independent match set holding only the matches on the best path, in
+ * text order, with `selected` = the chosen variant (-1 = out of vocabulary).  With max_ngram == 1 the result is
+ * a copy of `in` (the reference skips the FST, :1929-1932).  The LM / context-rule terms of the reference's
+ * sequence score (:2336-2400) are not built; tie-breaking among equal-cost paths is documented in DESIGN.md. */
+anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
+                                     anl_match_set** out);
+
 /* Test hooks for the host-side batch producer of find_all_matches (no model or GPU needed): the boundaries
  * (src/search.rs:190-258; strength 1 weak, 2 normal, 3 hard) and the n-gram segments per hard-delimited batch
  * (src/search.rs:262-312, src/lib.rs:1822-1903) exactly as anl_find_all_matches produces them.  Both return
@@ -225,6 +236,13 @@ void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_look
 int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin, uint64_t* end, int32_t* strength, size_t cap);
 int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end, uint32_t* order,
                                uint32_t* batch, size_t cap);
+
+/* Test hook: a match set exactly as anl_find_all_matches assembles it, but from caller-supplied variant lists
+ * (CSR `offsets[nseg + 1]` into `variants`, `looked[k]` = segment k was looked up; segments in the order of
+ * anl_debug_segment_text) instead of GPU lookups -- drives anl_match_set_consolidate on a CPU-only box. */
+anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_ngram, int32_t unicodeoffsets,
+                                     const uint8_t* looked, const uint64_t* offsets, const anl_variant* variants, uint64_t nseg,
+                                     anl_match_set** out);
 
 /* ---- device-resident path (what bench.py times as `value`; plumbing for multi-GPU hosts) ------ */
 typedef struct anl_device_batch anl_device_batch; /* encoded queries + result buffers in HBM */

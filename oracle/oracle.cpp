@@ -23,6 +23,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <set>
 #include <string>
@@ -1724,6 +1725,7 @@ struct Segment {
   unsigned n;
   bool looked_up;
   std::vector<Result> variants;
+  int selected = -1;  // Match.selected (src/search.rs:55): index into variants, -1 = None
 };
 // src/search.rs:262-312 ; `bounds` is the slice of boundaries of the current batch
 static std::vector<Segment> find_match_ngrams(const std::string& text, const Span* bounds, size_t nbounds, unsigned order,
@@ -1769,14 +1771,102 @@ static bool redundant_match(const Segment& cand, const std::vector<Segment>& mat
   }
   return true;
 }
-// src/lib.rs:1790-1957 without the FST consolidation stage (out of scope): returns every segment
-// of every order with its variant list, in the reference's batch order.
-static std::vector<Segment> find_all_segments(const Model& m, const std::string& text, const Params& p, Stats* st) {
+// ---- src/lib.rs:2088-2495 most_likely_sequence, for a model without language model and context rules -----------
+// The reference builds a weighted FST (rustfst 1.1.2, tropical semiring over f32; third-party, not under
+// /root/reference): a start state plus one state per boundary of the batch, one transition per (match, variant)
+// with cost `n + (1 - score)` (n = tokens covered), an out-of-vocabulary transition of cost `n + 1` for a unigram
+// without variants, and an epsilon fail-safe of cost 100 between consecutive states.  It then asks rustfst for
+// the `max_seq` shortest paths and, with no LM and no context rules, keeps the one of lowest total cost
+// (`norm_variant_score = ln(best_cost / cost)` is maximal there, :2383-2400).  The lattice is a DAG whose states
+// are ordered by boundary index, so the lowest-cost path is restated here as one forward relaxation pass with
+// f32 accumulation along the path (tropical `times` = f32 addition).
+// PARITY UNPINNED for ties: which of several equal-cost paths rustfst enumerates first is not fixed by any
+// reference test; the rule here is "earliest source state, then earliest transition (match order, then variant
+// order)".  Single-boundary batches: the reference's initial `best_variant_cost` of 0 makes every score -inf and
+// it keeps the first enumerated path; restated as the lowest cost as well.
+struct Transition {
+  int to;
+  float cost;
+  long match_index;  // -1 = epsilon
+  int variant_index; // -1 = out of vocabulary (copied from the input)
+};
+static std::vector<Segment> most_likely_sequence(const std::vector<Segment>& matches, const Span* bounds, size_t nbounds,
+                                                 size_t end_offset, float freq_weight) {
+  const int nstates = (int)nbounds + 1;  // state 0 = start, state 1 + i = boundary i
+  std::vector<std::vector<Transition>> out(nstates);
+  size_t output_symbols = 1;  // symbol 0 is epsilon
+  for (size_t mi = 0; mi < matches.size(); ++mi) {
+    const Segment& m = matches[mi];
+    long prevb = -1, nextb = -1;
+    for (size_t i = 0; i < nbounds; ++i) {  // :2142-2148 (no break: the last boundary that fits wins)
+      if (m.begin == bounds[i].end)
+        prevb = (long)i;
+      else if (m.end == bounds[i].begin)
+        nextb = (long)i;
+    }
+    if (nextb < 0) continue;  // reference: expect("next boundary must exist") panics; cannot happen for producer segments
+    const long n = prevb >= 0 ? nextb - prevb : nextb + 1;
+    const int prevstate = prevb >= 0 ? (int)prevb + 1 : 0, nextstate = (int)nextb + 1;
+    if (m.looked_up && !m.variants.empty()) {
+      for (size_t vi = 0; vi < m.variants.size(); ++vi) {
+        const float cost = (float)n + (1.0f - (float)Model::result_score(m.variants[vi], freq_weight));  // :2203-2204
+        out[prevstate].push_back(Transition{nextstate, cost, (long)mi, (int)vi});
+        ++output_symbols;
+      }
+    } else if (n == 1) {
+      out[prevstate].push_back(Transition{nextstate, (float)n + 1.0f, (long)mi, -1});  // OOV emission, :2223
+      ++output_symbols;
+    }
+  }
+  for (size_t i = 0; i < nbounds; ++i) out[i].push_back(Transition{(int)i + 1, 100.0f, -1, -1});  // :2249-2259
+  if (output_symbols == 1) return matches;                                                        // :2261-2267
+  const float INF = std::numeric_limits<float>::infinity();
+  std::vector<float> dist(nstates, INF);
+  std::vector<std::pair<int, const Transition*>> back(nstates, {-1, nullptr});
+  dist[0] = 0.0f;
+  for (int s = 0; s < nstates; ++s) {
+    if (dist[s] == INF) continue;
+    for (const Transition& t : out[s]) {
+      const float d = dist[s] + t.cost;
+      if (d < dist[t.to]) {
+        dist[t.to] = d;
+        back[t.to] = {s, &t};
+      }
+    }
+  }
+  int fin = -1;
+  for (size_t i = 0; i < nbounds; ++i)  // final states, :2119-2122
+    if (bounds[i].begin == end_offset || bounds[i].end == end_offset)
+      if (fin < 0 || dist[i + 1] < dist[fin]) fin = (int)i + 1;
+  if (fin < 0 || dist[fin] == INF) return matches;  // reference: panic!("no final state found")
+  std::vector<const Transition*> path;
+  for (int s = fin; s != 0; s = back[s].first) path.push_back(back[s].second);
+  std::vector<Segment> best;
+  for (size_t k = path.size(); k-- > 0;) {
+    if (path[k]->match_index < 0) continue;  // epsilon: no output label
+    Segment m = matches[path[k]->match_index];
+    m.selected = path[k]->variant_index;  // :2472
+    best.push_back(std::move(m));
+  }
+  return best;
+}
+
+// src/lib.rs:1790-1957.  `consolidate` = false: every segment of every order with its variant list, in the
+// reference's batch order (the producer alone).  `consolidate` = true: the reference's result -- the most likely
+// sequence per batch when max_ngram > 1 (:1912-1924), else every unigram with selected = 0 (:1929-1932).
+// `pv` (tests only) supplies the variant lists per segment in producer order instead of looking them up.
+struct Provided {
+  const uint8_t* looked;
+  const uint64_t* offsets;
+  const Result* results;
+};
+static std::vector<Segment> run_search(const Model* m, const std::string& text, const Params& p, Stats* st, bool consolidate,
+                                       const Provided* pv) {
   std::vector<Segment> all;
-  if (text.empty() || m.index.empty()) return all;
+  if (text.empty() || (m && m->index.empty())) return all;
   auto boundaries = find_boundaries(text);
   auto strengths = classify_boundaries(text, boundaries);
-  size_t begin = 0, begin_index = 0;
+  size_t begin = 0, begin_index = 0, k = 0;
   for (size_t i = 0; i < boundaries.size(); ++i) {
     if (strengths[i] == B_HARD && boundaries[i].begin != begin) {
       std::vector<Segment> batch;
@@ -1784,12 +1874,24 @@ static std::vector<Segment> find_all_segments(const Model& m, const std::string&
         auto cur = find_match_ngrams(text, boundaries.data() + begin_index, i + 1 - begin_index, order, begin,
                                      boundaries[i].begin);
         for (Segment& seg : cur) {
-          if (order == 1 || !redundant_match(seg, batch)) {
-            seg.variants = m.find_variants(text.substr(seg.begin, seg.end - seg.begin), p, st);
+          if (pv) {
+            seg.looked_up = pv->looked[k] != 0;
+            seg.variants.assign(pv->results + pv->offsets[k], pv->results + pv->offsets[k + 1]);
+          } else if (order == 1 || !redundant_match(seg, batch)) {
+            seg.variants = m->find_variants(text.substr(seg.begin, seg.end - seg.begin), p, st);
             seg.looked_up = true;
           }
+          ++k;
         }
         batch.insert(batch.end(), cur.begin(), cur.end());
+      }
+      if (consolidate) {
+        if (p.max_ngram > 1) {
+          batch = most_likely_sequence(batch, boundaries.data() + begin_index, i + 1 - begin_index, boundaries[i].begin,
+                                       p.freq_weight);
+        } else {
+          for (Segment& seg : batch) seg.selected = 0;
+        }
       }
       all.insert(all.end(), batch.begin(), batch.end());
       begin = boundaries[i].end;
@@ -1797,6 +1899,9 @@ static std::vector<Segment> find_all_segments(const Model& m, const std::string&
     }
   }
   return all;
+}
+static std::vector<Segment> find_all_segments(const Model& m, const std::string& text, const Params& p, Stats* st) {
+  return run_search(&m, text, p, st, false, nullptr);
 }
 
 }  // namespace orc
@@ -2046,6 +2151,32 @@ int64_t orc_find_all_segments(void* h, const char* text, uint64_t len, const Par
       seg_end[i] = segs[i].end;
       seg_n[i] = segs[i].n;
       seg_looked[i] = segs[i].looked_up;
+      res_offsets[i] = r;
+    }
+    for (auto& v : segs[i].variants) {
+      if (r < res_cap) results[r] = v;
+      ++r;
+    }
+  }
+  if ((int64_t)segs.size() < seg_cap) res_offsets[segs.size()] = r;
+  return (int64_t)segs.size();
+}
+// find_all_matches with the sequence consolidation (src/lib.rs:1790-1957 + 2088-2495, no LM / context rules).
+// h == NULL: the variant lists come from (looked, prov_offsets, prov_results), one entry per segment in the
+// producer's order (orc_find_all_segments), so a test can hand the same lattice to the product's host code.
+int64_t orc_find_all_matches(void* h, const char* text, uint64_t len, const Params* p, const uint8_t* looked,
+                             const uint64_t* prov_offsets, const Result* prov_results, uint64_t* seg_begin, uint64_t* seg_end,
+                             uint32_t* seg_n, int32_t* seg_selected, uint64_t* res_offsets, int64_t seg_cap, Result* results,
+                             int64_t res_cap) {
+  Provided pv{looked, prov_offsets, prov_results};
+  auto segs = run_search((Model*)h, std::string(text, len), *p, nullptr, true, h ? nullptr : &pv);
+  int64_t r = 0;
+  for (size_t i = 0; i < segs.size(); ++i) {
+    if ((int64_t)i < seg_cap) {
+      seg_begin[i] = segs[i].begin;
+      seg_end[i] = segs[i].end;
+      seg_n[i] = segs[i].n;
+      seg_selected[i] = segs[i].selected;
       res_offsets[i] = r;
     }
     for (auto& v : segs[i].variants) {

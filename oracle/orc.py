@@ -120,6 +120,8 @@ def lib():
         "orc_max_threads": (i32, []),
         "orc_find_all_segments": (i64, [vp, cp, u64, P(Params), P(u64), P(u64), P(u32), P(C.c_uint8), P(u64), i64,
                                         P(Result), i64]),
+        "orc_find_all_matches": (i64, [vp, cp, u64, P(Params), P(C.c_uint8), P(u64), P(Result), P(u64), P(u64), P(u32),
+                                       P(i32), P(u64), i64, P(Result), i64]),
         "orc_find_boundaries": (i64, [cp, u64, P(u64), P(u64), P(i32), i64]),
         "orc_find_match_ngrams": (i64, [cp, u64, u32, P(u64), P(u64), i64]),
         "orc_is_alphabetic": (i32, [u32]),
@@ -329,6 +331,48 @@ class OracleModel:
                 "variants": [(rs[j].vocab_id, rs[j].dist_score, rs[j].freq_score) for j in range(ro[i], ro[i + 1])],
             })
         return out
+
+
+    def find_all_matches(self, text, params):
+        """find_all_matches with the sequence consolidation (src/lib.rs:1790-1957, 2088-2495; no LM / context rules)."""
+        return _find_all_matches(self.h, text, params, None)
+
+
+def consolidate(text, params, segments):
+    """The consolidation alone: `segments` = one dict per producer segment (find_all_segments order) with
+    "looked_up" and "variants" [(vocab_id, dist_score, freq_score)]; no model, no lookups."""
+    return _find_all_matches(None, text, params, segments)
+
+
+def _find_all_matches(h, text, params, segments):
+    raw = text.encode("utf-8")
+    looked = offs = prov = None
+    if segments is not None:
+        n = len(segments)
+        looked = (C.c_uint8 * max(1, n))(*[1 if s["looked_up"] else 0 for s in segments])
+        offs = (C.c_uint64 * (n + 1))()
+        flat = []
+        for i, s in enumerate(segments):
+            flat += list(s["variants"]) if s["looked_up"] else []
+            offs[i + 1] = len(flat)
+        prov = (Result * max(1, len(flat)))()
+        for j, v in enumerate(flat):
+            prov[j] = Result(int(v[0]), float(v[1]), float(v[2]), NO_VIA)
+    seg_cap, res_cap = 4096, 1 << 16
+    while True:
+        sb, se = (C.c_uint64 * seg_cap)(), (C.c_uint64 * seg_cap)()
+        sn, ss = (C.c_uint32 * seg_cap)(), (C.c_int32 * seg_cap)()
+        ro = (C.c_uint64 * (seg_cap + 1))()
+        rs = (Result * res_cap)()
+        n = lib().orc_find_all_matches(h, raw, len(raw), C.byref(params), looked, offs, prov, sb, se, sn, ss, ro, seg_cap,
+                                       rs, res_cap)
+        if n < seg_cap and ro[n] <= res_cap:
+            break
+        seg_cap = max(seg_cap, n + 1)
+        res_cap *= 4
+    return [{"begin": sb[i], "end": se[i], "n": sn[i], "selected": ss[i], "text": raw[sb[i]:se[i]].decode("utf-8"),
+             "variants": [(rs[j].vocab_id, rs[j].dist_score, rs[j].freq_score) for j in range(ro[i], ro[i + 1])]}
+            for i in range(n)]
 
 
 # -- free functions (primitives) --------------------------------------------------------------------
