@@ -579,9 +579,11 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
 anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
                                      anl_match_set** out) {
   if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  PhaseTimer pt;
   const std::string t(text ? text : "", len);
   SegmentedText st;
   segment_text(t, params->max_ngram, &st);
+  pt.lap("consolidate: segmentation");
   if (st.segs.size() != in->matches.size())
     return fail(ANL_ERR_INVALID, "match set does not belong to this text / max_ngram (segment count differs)");
   const std::vector<Boundary>& bounds = find_boundaries(t);
@@ -595,6 +597,7 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
   const unsigned nt_max = host_threads();
   std::vector<std::vector<SequenceStep>> part(nt_max);
   std::vector<std::vector<uint64_t>> part_count(nt_max);  // steps per batch
+  std::vector<uint64_t> part_nvar(nt_max, 0);             // variants held by the chosen matches
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
   const unsigned used = parallel_ranges(nbatch, 64, [&](unsigned tid, uint64_t lo, uint64_t hi) {
     range[tid] = {lo, hi};
@@ -630,44 +633,46 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
       if (!chosen)  // unigram-only models (:1929-1932) and empty lattices (:2261-2267): every match as it is
         for (uint64_t k = s0; k < s1; ++k) part[tid].push_back(SequenceStep{(uint32_t)(k - s0), in->matches[k].selected});
       part_count[tid].push_back(part[tid].size() - before);
+      for (size_t i = before; i < part[tid].size(); ++i) {
+        const anl_match& mm = in->matches[s0 + part[tid][i].seg];
+        if (mm.variants) part_nvar[tid] += mm.n_variants;
+      }
     }
   });
+  pt.lap("consolidate: lattices");
   anl_match_set* ms = new anl_match_set();
   ms->logical_lookups = in->logical_lookups;
   ms->distinct_lookups = in->distinct_lookups;
-  uint64_t nout = 0, nvar = 0;
+  // every thread copies the matches of its own batches behind those of the threads before it
+  std::vector<uint64_t> first_match(used + 1, 0), first_variant(used + 1, 0);
   for (unsigned tid = 0; tid < used; ++tid) {
-    size_t pos = 0;
-    for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
-      const uint64_t c = part_count[tid][b - range[tid].first];
-      for (uint64_t i = 0; i < c; ++i, ++pos) {
-        const anl_match& mm = in->matches[st.batch_first[b] + part[tid][pos].seg];
-        if (mm.variants) nvar += mm.n_variants;
-      }
-      nout += c;
-    }
+    first_match[tid + 1] = first_match[tid] + part[tid].size();
+    first_variant[tid + 1] = first_variant[tid] + part_nvar[tid];
   }
-  ms->matches.resize(nout);
-  ms->variants.reserve(nvar + 1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
-  ms->variants.resize(nvar);
-  uint64_t o = 0, v = 0;
-  for (unsigned tid = 0; tid < used; ++tid) {
-    size_t pos = 0;
-    for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
-      const uint64_t c = part_count[tid][b - range[tid].first];
-      for (uint64_t i = 0; i < c; ++i, ++pos) {
-        const SequenceStep& s = part[tid][pos];
-        anl_match mm = in->matches[st.batch_first[b] + s.seg];
-        mm.selected = s.variant < 0 ? -1 : s.variant;
-        if (mm.variants) {
-          if (mm.n_variants) memcpy(ms->variants.data() + v, mm.variants, (size_t)mm.n_variants * sizeof(anl_variant));
-          mm.variants = ms->variants.data() + v;
-          v += mm.n_variants;
+  ms->matches.resize(first_match[used]);
+  ms->variants.reserve(first_variant[used] + 1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
+  ms->variants.resize(first_variant[used]);
+  parallel_ranges(used, 1, [&](unsigned, uint64_t tlo, uint64_t thi) {
+    for (uint64_t tid = tlo; tid < thi; ++tid) {
+      uint64_t o = first_match[tid], v = first_variant[tid];
+      size_t pos = 0;
+      for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
+        const uint64_t c = part_count[tid][b - range[tid].first];
+        for (uint64_t i = 0; i < c; ++i, ++pos) {
+          const SequenceStep& s = part[tid][pos];
+          anl_match mm = in->matches[st.batch_first[b] + s.seg];
+          mm.selected = s.variant < 0 ? -1 : s.variant;
+          if (mm.variants) {
+            if (mm.n_variants) memcpy(ms->variants.data() + v, mm.variants, (size_t)mm.n_variants * sizeof(anl_variant));
+            mm.variants = ms->variants.data() + v;
+            v += mm.n_variants;
+          }
+          ms->matches[o++] = mm;
         }
-        ms->matches[o++] = mm;
       }
     }
-  }
+  });
+  pt.lap("consolidate: assemble");
   *out = ms;
   return ANL_OK;
 }

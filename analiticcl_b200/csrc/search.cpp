@@ -213,8 +213,11 @@ bool most_likely_sequence(const Boundary* bounds, size_t nbounds, size_t end_off
     }
     return (lo < nbounds && bounds[lo].begin == pos) ? (long)lo : -1;
   };
+  // (scratch kept per thread: a text has one lattice per sentence)
   static thread_local std::vector<Arc> arcs, by_target;
-  static thread_local std::vector<uint32_t> target, fill;
+  static thread_local std::vector<uint32_t> target, fill, order, cursor;
+  static thread_local std::vector<float> best;
+  static thread_local std::vector<int64_t> via;
   arcs.clear();
   target.clear();
   size_t labelled = 0;
@@ -250,15 +253,18 @@ bool most_likely_sequence(const Boundary* bounds, size_t nbounds, size_t end_off
   for (size_t s = 0; s < nstates; ++s) fill[s + 1] += fill[s];
   by_target.resize(arcs.size());
   {
-    std::vector<uint32_t> order(arcs.size());
-    for (size_t a = 0; a < arcs.size(); ++a) order[a] = (uint32_t)a;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return arcs[x].from < arcs[y].from; });
-    std::vector<uint32_t> cursor(fill.begin(), fill.end() - 1);
+    // counting sort by source state first (stable), then the stable scatter by target state
+    cursor.assign(nstates + 1, 0);
+    for (const Arc& a : arcs) ++cursor[a.from + 1];
+    for (size_t s = 0; s < nstates; ++s) cursor[s + 1] += cursor[s];
+    order.resize(arcs.size());
+    for (size_t a = 0; a < arcs.size(); ++a) order[cursor[arcs[a].from]++] = (uint32_t)a;
+    cursor.assign(fill.begin(), fill.end() - 1);
     for (uint32_t a : order) by_target[cursor[target[a]]++] = arcs[a];
   }
   const float INF = std::numeric_limits<float>::infinity();
-  std::vector<float> best(nstates, INF);
-  std::vector<int64_t> via(nstates, -1);  // index into by_target
+  best.assign(nstates, INF);
+  via.assign(nstates, -1);  // index into by_target
   best[0] = 0.0f;
   for (size_t t = 1; t < nstates; ++t) {
     for (uint32_t a = fill[t]; a < fill[t + 1]; ++a) {
