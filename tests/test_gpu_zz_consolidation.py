@@ -92,3 +92,19 @@ def test_consolidated_matches_equal_oracle(A, eng, eng_oracle, max_ngram, freq_w
     bad = [i for i, (g, e) in enumerate(zip(got, want)) if g != e]
     assert len(got) == len(want) and not bad, (len(got), len(want), bad[:3], got[bad[0]] if bad else None)
     assert any(s["n"] > 1 for s in exp) and any(s["selected"] < 0 for s in exp)
+
+
+def test_reference_0705_lm_disabled(A):
+    """tests/main.rs:1364-1429 as it stands: the model carries the test's LM entries, `lm_weight = 0.0` switches the
+    language model off, the sequence is decided by the variant-model cost alone."""
+    m = A.VariantModel(None, A.Weights(), alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    for w in ["I", "think", "sink", "you", "are", "right", "are right"]:
+        m.add_to_vocabulary(w, 2, A.VocabParams())
+    for w, f in [("<bos> I", 2), ("I think", 2), ("I sink", 1), ("you are", 2), ("right <eos>", 2)]:
+        m.add_to_vocabulary(w, f, A.VocabParams(vocabtype="LM"))
+    m.build()
+    sp = A.SearchParameters(max_anagram_distance=2, max_edit_distance=2, max_matches=10, score_threshold=0.0,
+                            cutoff_threshold=0.0, freq_weight=0.0, max_ngram=2, lm_weight=0.0, context_weight=0.5)
+    r = m.find_all_matches("I tink you are rihgt", sp)
+    assert [(x["input"], x["variants"][0]["text"]) for x in r] == \
+        [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right")]

@@ -22,10 +22,15 @@ def L():
     return _capi.lib()
 
 
-def small_model(words):
+LM_ENTRIES = [("<bos> I", 2), ("I think", 2), ("I sink", 1), ("you are", 2), ("right <eos>", 2)]  # T:1154-1193
+
+
+def small_model(words, lm=()):
     m = orc.OracleModel(alphabet_tsv=orc.TEST_ALPHABET_TSV)
     for w in words:
         m.add_to_vocabulary(w, 2)
+    for w, f in lm:
+        m.add_to_vocabulary(w, f, vocab_type="LM")
     m.build()
     return m
 
@@ -43,6 +48,24 @@ def test_oracle_reference_0702_0703():
     assert (r[1]["begin"], r[1]["end"]) == (2, 6)
     r = m.find_all_matches("I tink you are\nrihgt", p)
     assert rendered(m, r) == [("I", "I"), ("tink", "think"), ("you", "you"), ("are\nrihgt", "are right")]  # T:1243-1252
+
+
+def test_oracle_reference_0705_lm_disabled():
+    """tests/main.rs:1364-1429, the whole test: the model holds the LM entries but `lm_weight = 0.0` switches the
+    language model off (src/lib.rs:2336, 2392-2396), so the sequence is decided by the variant-model cost alone --
+    exactly the configuration restated here.  (LM-typed entries are not indexed and never show up as variants.)"""
+    m = small_model(["I", "think", "sink", "you", "are", "right", "are right"], LM_ENTRIES)
+    r = m.find_all_matches("I tink you are rihgt", orc.make_params(**TEST_PARAMS))
+    assert rendered(m, r) == [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right")]  # T:1420-1428
+
+
+def test_oracle_reference_0704_two_batches():
+    """tests/main.rs:1274-1361 without the language model's say: a double line break is a hard boundary, the two
+    sentences are consolidated independently."""
+    m = small_model(["I", "think", "sink", "you", "are", "right", "am", "sure", "are right"])
+    r = m.find_all_matches("I tink you are rihgt\n\nI am sur", orc.make_params(**TEST_PARAMS))
+    assert rendered(m, r) == [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right"),
+                              ("I", "I"), ("am", "am"), ("sur", "sure")]  # T:1346-1360
 
 
 def test_oracle_tutorial_golden(eng_oracle):
@@ -207,10 +230,12 @@ def test_python_mirror_consolidates_like_the_reference(L, monkeypatch):
     producer's view; the selected variant comes first."""
     import analiticcl_b200 as A
     words = ["I", "think", "sink", "you", "are", "right", "are right"]
-    o = small_model(words)
+    o = small_model(words, LM_ENTRIES)
     m = A.VariantModel(None, A.Weights(), alphabet_tsv=orc.TEST_ALPHABET_TSV)
     for w in words:
         m.add_to_vocabulary(w, 2, A.VocabParams())
+    for w, f in LM_ENTRIES:  # tests/main.rs:1364-1429 (lm_weight = 0: the entries are carried, the LM is off)
+        m.add_to_vocabulary(w, f, A.VocabParams(vocabtype="LM"))
 
     def fake_find_all_matches(h, raw, n, params_ref, out_ref):
         sp = params_ref._obj
@@ -231,7 +256,7 @@ def test_python_mirror_consolidates_like_the_reference(L, monkeypatch):
     real = L.anl_find_all_matches
     monkeypatch.setattr(L, "anl_find_all_matches", fake_find_all_matches, raising=False)
     try:
-        sp = A.SearchParameters(**TEST_PARAMS)
+        sp = A.SearchParameters(**TEST_PARAMS, lm_weight=0.0, context_weight=0.5)
         r = m.find_all_matches("I tink you are rihgt", sp)
         assert [(x["input"], x["variants"][0]["text"]) for x in r] == \
             [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right")]
