@@ -83,3 +83,18 @@ def test_large_text_equals_piecewise(L):
     arr = np.array([(bt, o) for _, _, o, bt in whole])
     same_batch = arr[1:, 0] == arr[:-1, 0]
     assert np.all(arr[1:, 1][same_batch] >= arr[:-1, 1][same_batch])
+
+
+def test_alphabetic_is_the_derived_property(L):
+    """char::is_alphabetic (src/search.rs:198,204) is the derived property Alphabetic, which includes Other_Alphabetic:
+    dependent vowel signs and similar marks are part of a word, they do not split it."""
+    for cp, alpha in ((0x093F, True), (0x0902, True), (0x0E31, True), (0x0345, True), (0x0301, False), (0x0030, False),
+                      (0x2160, True), (0x00AA, True), (0x3042, True), (0x2019, False)):
+        assert bool(orc.lib().orc_is_alphabetic(cp)) == alpha, hex(cp)
+    assert bool(orc.lib().orc_is_lowercase(0x10780)) and bool(orc.lib().orc_is_lowercase(0x00E9))
+    assert not orc.lib().orc_is_lowercase(0x00C9) and not orc.lib().orc_is_lowercase(0x4E00)
+    t = "हिंदी भाषा, ภาษาไทย"
+    raw = t.encode("utf-8")
+    got = boundaries(L, t)
+    assert got == [(b, e, s) for b, e, _, s in orc.find_boundaries(t)]
+    assert [raw[b:e].decode() for b, e, _ in got] == [" ", ", ", ""]
