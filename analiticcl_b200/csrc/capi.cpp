@@ -37,6 +37,24 @@ static anl_status fail(anl_status code, const std::string& msg) {
   return code;
 }
 
+// No exception crosses the C boundary: every entry point that can allocate or call into the engine is a function
+// try block ending here (std::bad_alloc from the result arrays is the realistic case).
+static anl_status on_exception() noexcept {
+  try {
+    try {
+      throw;
+    } catch (const std::bad_alloc&) {
+      return fail(ANL_ERR_INVALID, "out of memory");
+    } catch (const std::exception& e) {
+      return fail(ANL_ERR_INVALID, std::string("internal error: ") + e.what());
+    } catch (...) {
+      return fail(ANL_ERR_INVALID, "internal error: unknown exception");
+    }
+  } catch (...) {  // even the message could not be stored
+    return ANL_ERR_INVALID;
+  }
+}
+
 extern "C" {
 
 const char* anl_last_error(void) { return g_last_error.c_str(); }
@@ -102,7 +120,7 @@ static VocabParams to_vocab_params(const anl_vocab_params* p) {
   return r;
 }
 
-anl_status anl_model_new(const char* alphabet_file, const anl_weights* weights, int32_t debug, anl_model** out) {
+anl_status anl_model_new(const char* alphabet_file, const anl_weights* weights, int32_t debug, anl_model** out) try {
   if (!alphabet_file || !out) return fail(ANL_ERR_INVALID, "null argument");
   anl_model* m = new (std::nothrow) anl_model(to_weights(weights), debug);
   if (!m) return fail(ANL_ERR_INVALID, "out of memory");
@@ -114,9 +132,11 @@ anl_status anl_model_new(const char* alphabet_file, const anl_weights* weights, 
   m->host.init_vocab();
   *out = m;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 anl_status anl_model_new_from_tsv(const char* alphabet_tsv, size_t len, const anl_weights* weights, int32_t debug,
-                                  anl_model** out) {
+                                  anl_model** out) try {
   if (!alphabet_tsv || !out) return fail(ANL_ERR_INVALID, "null argument");
   anl_model* m = new (std::nothrow) anl_model(to_weights(weights), debug);
   if (!m) return fail(ANL_ERR_INVALID, "out of memory");
@@ -124,53 +144,67 @@ anl_status anl_model_new_from_tsv(const char* alphabet_tsv, size_t len, const an
   m->host.init_vocab();
   *out = m;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 void anl_model_free(anl_model* m) { delete m; }
 
-anl_status anl_model_read_vocabulary(anl_model* m, const char* filename, const anl_vocab_params* params) {
+anl_status anl_model_read_vocabulary(anl_model* m, const char* filename, const anl_vocab_params* params) try {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->host.read_vocabulary(filename, to_vocab_params(params), &err)) return fail(ANL_ERR_IO, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t len, int32_t has_frequency, uint32_t frequency,
-                                       const anl_vocab_params* params, uint64_t* vocab_id) {
+                                       const anl_vocab_params* params, uint64_t* vocab_id) try {
   if (!m || !text) return fail(ANL_ERR_INVALID, "null argument");
   uint64_t id = m->host.add_to_vocabulary(text, len, has_frequency != 0, frequency, to_vocab_params(params));
   if (vocab_id) *vocab_id = id;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 anl_status anl_model_add_variant(anl_model* m, uint64_t ref_id, const char* text, size_t len, double score, int32_t has_frequency,
-                                 uint32_t frequency, const anl_vocab_params* params, int32_t* added) {
+                                 uint32_t frequency, const anl_vocab_params* params, int32_t* added) try {
   if (!m || !text) return fail(ANL_ERR_INVALID, "null argument");
   if (ref_id >= m->host.decoder.size()) return fail(ANL_ERR_INVALID, "add_variant: unknown reference id");
   const bool ok = m->host.add_variant(ref_id, text, len, score, has_frequency != 0, frequency, to_vocab_params(params));
   if (added) *added = ok ? 1 : 0;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_model_read_variants(anl_model* m, const char* filename, const anl_vocab_params* params, int32_t transparent) {
+anl_status anl_model_read_variants(anl_model* m, const char* filename, const anl_vocab_params* params, int32_t transparent) try {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->host.read_variants(filename, to_vocab_params(params), transparent != 0, &err)) return fail(ANL_ERR_IO, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_model_read_confusablelist(anl_model* m, const char* filename) {
+anl_status anl_model_read_confusablelist(anl_model* m, const char* filename) try {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->host.read_confusablelist(filename, &err)) return fail(ANL_ERR_IO, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_model_add_to_confusables(anl_model* m, const char* editscript, double weight) {
+anl_status anl_model_add_to_confusables(anl_model* m, const char* editscript, double weight) try {
   if (!m || !editscript) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->host.add_to_confusables(editscript, weight, &err)) return fail(ANL_ERR_INVALID, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 void anl_model_set_confusables_before_pruning(anl_model* m) {
   if (m) m->host.confusables_before_pruning = true;
 }
 
-anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards) {
+anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards) try {
   if (!m) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int sd = 1;
@@ -178,13 +212,15 @@ anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard,
   if (!m->host.build_index(sd, shard, n_shards, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
   if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_model_build(anl_model* m, int32_t device) { return anl_model_build_sharded(m, device, 0, 1); }
+anl_status anl_model_build(anl_model* m, int32_t device) try { return anl_model_build_sharded(m, device, 0, 1); } catch (...) { return on_exception(); }
 
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len) { return m && m->host.has(text, len) ? 1 : 0; }
 int64_t anl_model_vocab_id(const anl_model* m, const char* text, size_t len) { return m ? m->host.vocab_id(text, len) : -1; }
 uint64_t anl_model_vocab_size(const anl_model* m) { return m ? m->host.decoder.size() : 0; }
-anl_status anl_model_get_vocab(const anl_model* m, uint64_t vocab_id, anl_vocab_info* out) {
+anl_status anl_model_get_vocab(const anl_model* m, uint64_t vocab_id, anl_vocab_info* out) try {
   if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
   if (vocab_id >= m->host.decoder.size()) return fail(ANL_ERR_INVALID, "vocabulary id out of range");
   const VocabEntry& e = m->host.decoder[vocab_id];
@@ -196,6 +232,8 @@ anl_status anl_model_get_vocab(const anl_model* m, uint64_t vocab_id, anl_vocab_
   out->tokencount = e.tokencount;
   out->norm_len = (uint32_t)e.syms.size();
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 uint32_t anl_model_lexicon_count(const anl_model* m) { return m ? (uint32_t)m->host.lexicons.size() : 0; }
 const char* anl_model_lexicon_name(const anl_model* m, uint32_t index) {
@@ -288,7 +326,7 @@ int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src
 
 // ---- lookup ------------------------------------------------------------------------------------------
 anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
-                                   const anl_search_params* params, anl_result_set** out) {
+                                   const anl_search_params* params, anl_result_set** out) try {
   if (!m || !offsets || !params || !out || (!blob && n_queries > 0)) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built || !m->engine.uploaded())
     return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_variants()");
@@ -301,6 +339,8 @@ anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_
   }
   *out = rs;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 uint64_t anl_result_set_len(const anl_result_set* rs) { return rs ? rs->rs.offsets.size() - 1 : 0; }
 const anl_variant* anl_result_set_get(const anl_result_set* rs, uint64_t i, uint64_t* count) {
@@ -323,7 +363,7 @@ void anl_result_set_free(anl_result_set* rs) { delete rs; }
 // window costs two pipelined GPU batches: all unigrams, then the higher-order segments that the
 // unigram results do not make redundant (src/search.rs:317-336).
 anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, const anl_search_params* params,
-                                anl_match_set** out) {
+                                anl_match_set** out) try {
   if (!m || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built || !m->engine.uploaded())
     return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_all_matches()");
@@ -572,12 +612,14 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   ms->distinct_lookups = distinct_lookups;
   *out = ms;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 // most_likely_sequence per hard-delimited batch (src/lib.rs:1912-1924, 2088-2495): host post-pass over the
 // match set of anl_find_all_matches.  The segments are re-derived from the text (cheap next to the lookups) so
 // that the match set itself stays a flat list; batches are independent and run on all cores.
 anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
-                                     anl_match_set** out) {
+                                     anl_match_set** out) try {
   if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   PhaseTimer pt;
   const std::string t(text ? text : "", len);
@@ -675,6 +717,8 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
   pt.lap("consolidate: assemble");
   *out = ms;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 
 // ---- test hooks for the host-side producer (no model, no GPU needed) ------------------------------------------
@@ -708,7 +752,7 @@ int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram,
 // producer's order) instead of GPU lookups: lets the CPU tests drive anl_match_set_consolidate.
 anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_ngram, int32_t unicodeoffsets,
                                      const uint8_t* looked, const uint64_t* offsets, const anl_variant* variants, uint64_t nseg,
-                                     anl_match_set** out) {
+                                     anl_match_set** out) try {
   if (!out || (!text && len > 0) || (nseg && (!looked || !offsets))) return fail(ANL_ERR_INVALID, "null argument");
   const std::string t(text ? text : "", len);
   SegmentedText st;
@@ -734,13 +778,17 @@ anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_
   }
   *out = ms;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 
 uint64_t anl_match_set_len(const anl_match_set* ms) { return ms ? ms->matches.size() : 0; }
-anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out) {
+anl_status anl_match_set_get(const anl_match_set* ms, uint64_t i, anl_match* out) try {
   if (!ms || !out || i >= ms->matches.size()) return fail(ANL_ERR_INVALID, "match index out of range");
   *out = ms->matches[i];
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 void anl_match_set_free(anl_match_set* ms) { delete ms; }
 void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_lookups, uint64_t* distinct_strings) {
@@ -750,7 +798,7 @@ void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_look
 
 // ---- device-resident path ---------------------------------------------------------------------------------
 anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
-                                   const anl_search_params* params, anl_device_batch** out) {
+                                   const anl_search_params* params, anl_device_batch** out) try {
   if (!m || !offsets || !params || !out) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int status = ANL_OK;
@@ -758,14 +806,18 @@ anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_
   if (!b) return fail(status ? status : ANL_ERR_CUDA, err);
   *out = new anl_device_batch{b};
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream) {
+anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream) try {
   if (!m || !b) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->engine.run_batch(b->b, reinterpret_cast<cudaStream_t>(stream), &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms) {
+anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms) try {
   if (!m || !b || !probe_ms || !score_ms) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   float st[6];
@@ -774,14 +826,18 @@ anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* pr
   *score_ms = st[2] + st[3];
   if (rescore_ms) *rescore_ms = st[4] + st[5];
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, float* stage_ms) {
+anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, float* stage_ms) try {
   if (!m || !b || !stage_ms) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->engine.timings(b->b, stage_ms, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) {
+anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) try {
   if (!m || !b || !out) return fail(ANL_ERR_INVALID, "null argument");
   anl_result_set* rs = new anl_result_set();
   std::string err;
@@ -792,35 +848,43 @@ anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_
   }
   *out = rs;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 void anl_device_batch_free(anl_model* m, anl_device_batch* b) {
   if (!b) return;
   if (m) m->engine.free_batch(b->b);
   delete b;
 }
-anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out) {
+anl_status anl_device_batch_counters(anl_model* m, anl_device_batch* b, anl_counters* out) try {
   if (!m || !b || !out) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->engine.counters(b->b, out, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 // ---- lexicon-sharded mode --------------------------------------------------------------------------------
-anl_status anl_shard_export_size(anl_model* m, anl_device_batch* b, uint64_t* n_records, uint32_t* max_per_query) {
+anl_status anl_shard_export_size(anl_model* m, anl_device_batch* b, uint64_t* n_records, uint32_t* max_per_query) try {
   if (!m || !b || !n_records) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int status = ANL_OK;
   if (!m->engine.shard_export_size(b->b, n_records, max_per_query, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
-anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags) {
+anl_status anl_shard_export(anl_model* m, anl_device_batch* b, void* d_heads, void* d_records, void* d_gids, void* d_flags) try {
   if (!m || !b || !d_heads || !d_records || !d_gids || !d_flags) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->engine.shard_export(b->b, d_heads, d_records, d_gids, d_flags, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards, const void* d_heads_all,
                            const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
-                           uint32_t max_survivors, anl_result_set** out) {
+                           uint32_t max_survivors, anl_result_set** out) try {
   if (!m || !b || !d_heads_all || !d_records_all || !d_gids_all || !d_flags_all)
     return fail(ANL_ERR_INVALID, "null argument");
   anl_result_set* rs = out ? new anl_result_set() : nullptr;
@@ -833,9 +897,11 @@ anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards,
   }
   if (out) *out = rs;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 
-anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) {
+anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) try {
   if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "model has not been built");
   const HostIndex& ix = m->host.index;
@@ -857,6 +923,8 @@ anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) {
   out->active_classes = (uint32_t)ix.active_classes.size();
   out->sd = (uint32_t)ix.sd;
   return ANL_OK;
+} catch (...) {
+  return on_exception();
 }
 
 }  // extern "C"

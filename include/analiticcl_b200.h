@@ -24,7 +24,7 @@ extern "C" {
 typedef int32_t anl_status;
 enum {
   ANL_OK = 0,
-  ANL_ERR_INVALID = 1,     /* bad argument */
+  ANL_ERR_INVALID = 1,     /* bad argument; also: out of memory / internal C++ exception (never propagated to the caller) */
   ANL_ERR_IO = 2,          /* file could not be read / parsed (reference: io::Error) */
   ANL_ERR_NOT_BUILT = 3,   /* lookup before build() (reference: stderr + empty result, src/lib.rs:973) */
   ANL_ERR_CUDA = 4,        /* CUDA runtime / kernel failure, or no device */

@@ -92,3 +92,15 @@ def test_variant_list_loading_matches_oracle(tmp_path):
             assert C.string_at(info.text, info.text_len).decode() == o.vocab_text(vid)
             assert info.frequency == o.vocab_freq(vid), o.vocab_text(vid)
             assert info.vocabtype == o.vocab_type(vid), o.vocab_text(vid)
+
+
+def test_no_exception_crosses_the_c_boundary(so):
+    """A C++ exception inside an entry point (here: std::bad_alloc from an absurd variant count) comes back as a
+    status code with a message, not as a terminate() in the caller's process."""
+    from analiticcl_b200 import _capi
+    L = _capi.lib()
+    looked = (ctypes.c_uint8 * 1)(1)
+    offs = (ctypes.c_uint64 * 2)(0, 1 << 57)
+    ms = ctypes.c_void_p()
+    rc = L.anl_debug_match_set_build(b"a", 1, 1, 0, looked, offs, None, 1, ctypes.byref(ms))
+    assert rc != 0 and b"out of memory" in L.anl_last_error()
