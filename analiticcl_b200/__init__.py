@@ -276,6 +276,15 @@ class VariantModel:
         """Build the anagram index and upload it to the GPU (`device` = CUDA ordinal, -1 = current)."""
         _check(_lib().anl_model_build(self._h, int(device)))
 
+    def save_index(self, filename):
+        """Write the built index to `filename` (not in the reference: its build takes seconds; see the C header)."""
+        _check(_lib().anl_model_save_index(self._h, os.fsencode(filename)))
+
+    def load_index(self, filename, device=-1):
+        """Instead of build(): read an index written by save_index for the same alphabet and vocabulary (same order)
+        and upload it to the GPU.  Raises RuntimeError on a foreign, mismatching or corrupt file."""
+        _check(_lib().anl_model_load_index(self._h, os.fsencode(filename), int(device)))
+
     def __contains__(self, text):
         raw = text.encode("utf-8")
         return bool(_lib().anl_model_has(self._h, raw, len(raw)))

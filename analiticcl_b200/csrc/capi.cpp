@@ -215,6 +215,24 @@ anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard,
 } catch (...) {
   return on_exception();
 }
+anl_status anl_model_save_index(const anl_model* m, const char* filename) try {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before save_index()");
+  std::string err;
+  if (!m->host.save_index(filename, &err)) return fail(ANL_ERR_IO, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+anl_status anl_model_load_index(anl_model* m, const char* filename, int32_t device) try {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.load_index(filename, &err)) return fail(ANL_ERR_IO, err);
+  if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
 anl_status anl_model_build(anl_model* m, int32_t device) try { return anl_model_build_sharded(m, device, 0, 1); } catch (...) { return on_exception(); }
 
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len) { return m && m->host.has(text, len) ? 1 : 0; }

@@ -656,6 +656,154 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   return true;
 }
 
+// ---- persistence of the built index -------------------------------------------------------------------------------
+namespace {
+const char kIndexMagic[8] = {'A', 'N', 'L', 'I', 'D', 'X', '0', '1'};
+struct IndexFileHeader {  // fixed-size, little-endian hosts only (x86-64 / aarch64)
+  char magic[8];
+  uint32_t header_bytes, slot_bytes, key_bytes, max_k;
+  uint64_t fingerprint;
+  uint32_t shard, n_shards, norm_stride, max_charcount, max_len, max_key_bits;
+  int32_t sd;
+  uint32_t reserved;
+  uint64_t table_keys;
+  uint64_t charcount_mask[4];
+  uint32_t prime_of[256];
+};
+template <class T>
+bool write_array(FILE* f, const std::vector<T>& v) {
+  const uint64_t n = v.size(), b = sizeof(T);
+  return fwrite(&n, 8, 1, f) == 1 && fwrite(&b, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T>
+bool read_array(FILE* f, std::vector<T>* v, uint64_t max_bytes) {
+  uint64_t n = 0, b = 0;
+  if (fread(&n, 8, 1, f) != 1 || fread(&b, 8, 1, f) != 1 || b != sizeof(T) || n > max_bytes / sizeof(T)) return false;
+  v->resize(n);
+  return n == 0 || fread(v->data(), sizeof(T), n, f) == n;
+}
+inline uint64_t fp_mix(uint64_t h, uint64_t x) {
+  h ^= x + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+  h *= 0xFF51AFD7ED558CCDULL;
+  return h ^ (h >> 32);
+}
+}  // namespace
+
+// Everything build_index reads: per vocabulary entry (in id order) its text, normalised symbols, frequency,
+// vocabulary type and case flag, plus the alphabet size.
+uint64_t HostModel::vocabulary_fingerprint() const {
+  uint64_t h = fp_mix(0x414E4C49ULL, alphabet.size());
+  for (const VocabEntry& v : decoder) {
+    h = fp_mix(h, v.text.size());
+    for (unsigned char c : v.text) h = fp_mix(h, c);
+    h = fp_mix(h, v.syms.size());
+    for (uint8_t s : v.syms) h = fp_mix(h, s);
+    h = fp_mix(h, ((uint64_t)v.frequency << 32) | ((uint64_t)v.vocabtype << 1) | (v.first_lower ? 1 : 0));
+  }
+  return h;
+}
+
+bool HostModel::save_index(const std::string& path, std::string* err) const {
+  if (!built) {
+    *err = "Model has not been built yet! Call build() before save_index()";
+    return false;
+  }
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) {
+    *err = "cannot open " + path + " for writing";
+    return false;
+  }
+  const HostIndex& ix = index;
+  IndexFileHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kIndexMagic, 8);
+  h.header_bytes = sizeof h;
+  h.slot_bytes = sizeof(Slot);
+  h.key_bytes = sizeof(Key192);
+  h.max_k = ANL_MAX_K;
+  h.fingerprint = vocabulary_fingerprint();
+  h.shard = ix.shard;
+  h.n_shards = ix.n_shards;
+  h.norm_stride = ix.norm_stride;
+  h.max_charcount = ix.max_charcount;
+  h.max_len = ix.max_len;
+  h.max_key_bits = ix.max_key_bits;
+  h.sd = ix.sd;
+  h.table_keys = ix.table_keys;
+  memcpy(h.charcount_mask, ix.charcount_mask, sizeof h.charcount_mask);
+  memcpy(h.prime_of, ix.prime_of, sizeof h.prime_of);
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  ok = ok && write_array(f, ix.ana_key) && write_array(f, ix.ana_inst_off) && write_array(f, ix.ana_charcount) &&
+       write_array(f, ix.inst_vocab) && write_array(f, ix.inst_freq) && write_array(f, ix.inst_gid) &&
+       write_array(f, ix.inst_rows) && write_array(f, ix.table) && write_array(f, ix.bloom) && write_array(f, ix.post_ana) &&
+       write_array(f, ix.post_cls) && write_array(f, ix.active_classes);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) *err = "short write to " + path;
+  return ok;
+}
+
+bool HostModel::load_index(const std::string& path, std::string* err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
+    *err = "cannot open " + path;
+    return false;
+  }
+  uint64_t file_bytes = 0;
+  if (fseek(f, 0, SEEK_END) == 0) {
+    const long end = ftell(f);
+    file_bytes = end > 0 ? (uint64_t)end : 0;
+  }
+  rewind(f);
+  IndexFileHeader h;
+  HostIndex ix;
+  auto bad = [&](const std::string& why) {
+    fclose(f);
+    *err = path + ": " + why;
+    return false;
+  };
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kIndexMagic, 8) != 0) return bad("not an analiticcl_b200 index file");
+  if (h.header_bytes != sizeof h || h.slot_bytes != sizeof(Slot) || h.key_bytes != sizeof(Key192) || h.max_k != ANL_MAX_K)
+    return bad("index file was written by a library with a different data layout");
+  if (h.fingerprint != vocabulary_fingerprint())
+    return bad("index file was built from a different vocabulary or alphabet (fingerprint mismatch)");
+  ix.shard = h.shard;
+  ix.n_shards = h.n_shards;
+  ix.norm_stride = h.norm_stride;
+  ix.max_charcount = h.max_charcount;
+  ix.max_len = h.max_len;
+  ix.max_key_bits = h.max_key_bits;
+  ix.sd = h.sd;
+  ix.table_keys = h.table_keys;
+  memcpy(ix.charcount_mask, h.charcount_mask, sizeof h.charcount_mask);
+  memcpy(ix.prime_of, h.prime_of, sizeof h.prime_of);
+  const bool read_ok = read_array(f, &ix.ana_key, file_bytes) && read_array(f, &ix.ana_inst_off, file_bytes) &&
+                       read_array(f, &ix.ana_charcount, file_bytes) && read_array(f, &ix.inst_vocab, file_bytes) &&
+                       read_array(f, &ix.inst_freq, file_bytes) && read_array(f, &ix.inst_gid, file_bytes) &&
+                       read_array(f, &ix.inst_rows, file_bytes) && read_array(f, &ix.table, file_bytes) &&
+                       read_array(f, &ix.bloom, file_bytes) && read_array(f, &ix.post_ana, file_bytes) &&
+                       read_array(f, &ix.post_cls, file_bytes) && read_array(f, &ix.active_classes, file_bytes);
+  if (!read_ok) return bad("truncated or corrupt index file");
+  // structural checks: everything the kernels index with must be in range
+  const size_t ninst = ix.inst_vocab.size(), nana = ix.ana_key.size();
+  auto pow2 = [](size_t n) { return n != 0 && (n & (n - 1)) == 0; };
+  bool sane = nana > 0 && ninst >= nana && ix.ana_inst_off.size() == nana + 1 && ix.ana_charcount.size() == nana &&
+              ix.inst_freq.size() == ninst && (ix.inst_gid.empty() || ix.inst_gid.size() == ninst) && ix.norm_stride >= 16 &&
+              ix.norm_stride % 16 == 0 && ix.inst_rows.size() == ninst * (size_t)ix.norm_stride && pow2(ix.table.size()) &&
+              pow2(ix.bloom.size()) && ix.post_cls.size() == ix.post_ana.size() && ix.n_shards >= 1 && ix.shard < ix.n_shards &&
+              ix.ana_inst_off[0] == 0 && ix.ana_inst_off[nana] == ninst && ix.max_len + 2 <= ix.norm_stride;
+  for (size_t r = 0; sane && r < nana; ++r) sane = ix.ana_inst_off[r] < ix.ana_inst_off[r + 1];
+  for (size_t g = 0; sane && g < ninst; ++g)
+    sane = ix.inst_vocab[g] < decoder.size() && ix.inst_rows[g * ix.norm_stride] <= ix.max_len;
+  for (size_t t = 0; sane && t < ix.post_ana.size(); ++t) sane = ix.post_ana[t] < nana;
+  for (size_t i = 0; sane && i < ix.table.size(); ++i)
+    sane = (uint64_t)ix.table[i].post_off + ix.table[i].post_cnt <= ix.post_ana.size();
+  if (!sane) return bad("index file is inconsistent");
+  fclose(f);
+  index = std::move(ix);
+  built = true;
+  return true;
+}
+
 bool HostModel::ensure_msets(uint32_t J, std::string* err) {
   if (J > (uint32_t)ANL_MAX_K) J = ANL_MAX_K;
   if (index.mset_built_j >= J && !(J == 0)) return true;

@@ -129,6 +129,13 @@ class HostModel {
   bool build_index(int sd, uint32_t shard, uint32_t n_shards, std::string* err);
   // builds the insertion-multiset table up to size J (idempotent)
   bool ensure_msets(uint32_t J, std::string* err);
+  // Persistence of the built index (the reference has no on-disk index, its nearest format is the
+  // TSV of `analiticcl index`, src/bin/analiticcl.rs:1190-1204): the flat arrays of HostIndex behind a header that
+  // pins the library's struct layout and a fingerprint of the vocabulary the index was built from.  load_index
+  // replaces build_index (same arrays, bit for bit) for a model that holds the same vocabulary in the same order.
+  uint64_t vocabulary_fingerprint() const;
+  bool save_index(const std::string& path, std::string* err) const;
+  bool load_index(const std::string& path, std::string* err);
 
   // -- queries against the host copy ---------------------------------------------------------------
   bool has(const char* text, size_t len) const;  // src/lib.rs:331-338

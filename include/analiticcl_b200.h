@@ -148,6 +148,13 @@ void anl_model_set_confusables_before_pruning(anl_model* m);
 
 /* build (src/lib.rs:192): anagram index on the host, then upload to `device` (-1 = current). */
 anl_status anl_model_build(anl_model* m, int32_t device);
+/* Persistence of the built index (the reference has no on-disk index -- its build takes seconds,
+ * the 10 M-entry lexicon of BASELINE config 5 takes 24 s here).  save_index writes the host copy of the index of a
+ * built model; load_index replaces anl_model_build for a model that holds the SAME alphabet and vocabulary in the
+ * same order (checked by a fingerprint; also checked: library data layout, array consistency): it reads the
+ * arrays and uploads them to `device`.  ANL_ERR_IO on a missing, foreign, mismatching or corrupt file. */
+anl_status anl_model_save_index(const anl_model* m, const char* filename);
+anl_status anl_model_load_index(anl_model* m, const char* filename, int32_t device);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len);          /* has(), src/lib.rs:331 */

@@ -1,0 +1,85 @@
+"""CPU-only: persistence of the built index (anl_model_save_index / anl_model_load_index).  Without a GPU build()
+and load_index() stop at the upload ("no CPU fallback"), but the host copy of the index is complete by then, so
+the file round trip, the validation of the file and the equality of a loaded and a built index can be checked
+here; tests/test_gpu_zz_consolidation.py checks that lookups on a loaded index equal those on a built one."""
+import os
+
+import pytest
+import torch
+
+import workloads
+
+pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="host-only variant of the persistence test")
+
+
+def model(A, lexicon="eng", extra=()):
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path(lexicon))
+    for w in extra:
+        m.add_to_vocabulary(w, 1, A.VocabParams())
+    return m
+
+
+def host_build(m):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.build()
+
+
+def stats(m):
+    return (m.index_size(), m.instance_count(), m.max_key_bits(), [m.anagram_count_of_length(i) for i in range(1, 30)])
+
+
+def test_index_file_round_trip(tmp_path):
+    import analiticcl_b200 as A
+    a = model(A)
+    with pytest.raises(RuntimeError, match="not been built"):
+        a.save_index(str(tmp_path / "x.idx"))
+    host_build(a)
+    f1, f2 = str(tmp_path / "eng.idx"), str(tmp_path / "eng2.idx")
+    a.save_index(f1)
+    assert os.path.getsize(f1) > 30_000_000  # table + Bloom words + postings + instance rows of eng
+    b = model(A)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # the file is accepted, only the upload is missing here
+        b.load_index(f1)
+    assert stats(b) == stats(a) and stats(a)[0] == 108802 and stats(a)[1] == 119773
+    b.save_index(f2)
+    assert open(f1, "rb").read() == open(f2, "rb").read()  # loaded index == built index, bit for bit
+
+
+def test_index_file_is_validated(tmp_path):
+    import analiticcl_b200 as A
+    a = model(A, "eng")
+    host_build(a)
+    good = str(tmp_path / "eng.idx")
+    a.save_index(good)
+    raw = open(good, "rb").read()
+    # another vocabulary (one more entry, or another lexicon): refused by the fingerprint
+    for other in (model(A, "eng", extra=["zzyzx"]), model(A, "nld")):
+        with pytest.raises(RuntimeError, match="different vocabulary"):
+            other.load_index(good)
+        assert other.index_size() == 0
+    fresh = lambda: model(A, "eng")  # noqa: E731
+    cases = {
+        "missing.idx": (None, "cannot open"),
+        "foreign.idx": (b"not an index" * 1000, "not an analiticcl_b200 index file"),
+        "truncated.idx": (raw[: len(raw) // 2], "truncated or corrupt"),
+        "layout.idx": (raw[:12] + b"\x11\x00\x00\x00" + raw[16:], "different data layout"),
+    }
+    for name, (content, msg) in cases.items():
+        path = str(tmp_path / name)
+        if content is not None:
+            open(path, "wb").write(content)
+        with pytest.raises(RuntimeError, match=msg):
+            fresh().load_index(path)
+    # a flipped posting (anagram rank out of range) is caught by the structural checks
+    bad = bytearray(raw)
+    m = fresh()
+    host_build(m)
+    n_ana = m.index_size()
+    import struct
+    hit = raw.rfind(struct.pack("<I", n_ana - 1))  # some u32 holding the last anagram rank (postings / offsets)
+    assert hit > 0
+    bad[hit:hit + 4] = struct.pack("<I", 0xFFFFFFF0)
+    open(str(tmp_path / "flipped.idx"), "wb").write(bytes(bad))
+    with pytest.raises(RuntimeError, match="inconsistent|truncated"):
+        fresh().load_index(str(tmp_path / "flipped.idx"))
