@@ -120,6 +120,7 @@ SIGNATURES = {
     "anl_match_set_lookup_counts": (None, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "anl_model_save_index": (_i32, [_vp, _cp]),
     "anl_model_load_index": (_i32, [_vp, _cp, _i32]),
+    "anl_model_shard": (None, [_vp, _P(_u32), _P(_u32)]),
     "anl_match_set_consolidate": (_i32, [_vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
     "anl_debug_match_set_build": (_i32, [_cp, _sz, C.c_uint32, C.c_int32, _P(C.c_uint8), _P(C.c_uint64), _P(Variant), _u64, _P(_vp)]),
     "anl_debug_find_boundaries": (_i64, [_cp, _sz, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz]),

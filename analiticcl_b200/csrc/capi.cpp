@@ -233,6 +233,10 @@ anl_status anl_model_load_index(anl_model* m, const char* filename, int32_t devi
 } catch (...) {
   return on_exception();
 }
+void anl_model_shard(const anl_model* m, uint32_t* shard, uint32_t* n_shards) {
+  if (shard) *shard = m && m->host.built ? m->host.index.shard : 0;
+  if (n_shards) *n_shards = m && m->host.built ? m->host.index.n_shards : 1;
+}
 anl_status anl_model_build(anl_model* m, int32_t device) try { return anl_model_build_sharded(m, device, 0, 1); } catch (...) { return on_exception(); }
 
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len) { return m && m->host.has(text, len) ? 1 : 0; }

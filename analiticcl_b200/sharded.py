@@ -34,6 +34,15 @@ class ShardedVariantModel(VariantModel):
         _check(_lib().anl_model_build_sharded(self._h, int(device), int(shard), int(n_shards)))
         self.shard, self.n_shards = int(shard), int(n_shards)
 
+    def load_index(self, filename, device=-1):
+        """Instead of build(): a shard's index file written by save_index; the shard coordinates come from the file."""
+        try:
+            super().load_index(filename, device)
+        finally:
+            s, n = C.c_uint32(), C.c_uint32()
+            _lib().anl_model_shard(self._h, C.byref(s), C.byref(n))
+            self.shard, self.n_shards = s.value, n.value
+
     # -- stage 1: score the whole batch against this shard ------------------------------------------
     def score(self, inputs, params, device):
         blob, offs = _capi.pack(list(inputs))

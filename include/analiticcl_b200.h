@@ -155,6 +155,8 @@ anl_status anl_model_build(anl_model* m, int32_t device);
  * arrays and uploads them to `device`.  ANL_ERR_IO on a missing, foreign, mismatching or corrupt file. */
 anl_status anl_model_save_index(const anl_model* m, const char* filename);
 anl_status anl_model_load_index(anl_model* m, const char* filename, int32_t device);
+/* Which lexicon shard the built / loaded index holds (0 of 1 = the whole lexicon; lexicon-sharded mode below). */
+void anl_model_shard(const anl_model* m, uint32_t* shard, uint32_t* n_shards);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 int32_t anl_model_has(const anl_model* m, const char* text, size_t len);          /* has(), src/lib.rs:331 */

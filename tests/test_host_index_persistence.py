@@ -83,3 +83,35 @@ def test_index_file_is_validated(tmp_path):
     open(str(tmp_path / "flipped.idx"), "wb").write(bytes(bad))
     with pytest.raises(RuntimeError, match="inconsistent|truncated"):
         fresh().load_index(str(tmp_path / "flipped.idx"))
+
+
+def test_sharded_index_round_trip(tmp_path):
+    """A lexicon shard (its own anagram subset + the global gather ids) survives the file as well, and a shard's
+    file is not mistaken for another shard's: the shard coordinates are part of the file."""
+    import analiticcl_b200 as A
+    from analiticcl_b200 import sharded
+
+    def shard_model(s, n):
+        m = sharded.ShardedVariantModel(workloads.ALPHABET, A.Weights())
+        m.read_lexicon(workloads.lexicon_path("eng"))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.build(shard=s, n_shards=n)
+        return m
+    parts = [shard_model(s, 3) for s in range(3)]
+    assert sum(p.index_size() for p in parts) == 108802 and sum(p.instance_count() for p in parts) == 119773
+    files = []
+    for s, p in enumerate(parts):
+        files.append(str(tmp_path / f"eng.{s}of3.idx"))
+        p.save_index(files[-1])
+    assert len({open(f, "rb").read() for f in files}) == 3
+    again = model(A)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        again.load_index(files[1])
+    assert (again.index_size(), again.instance_count()) == (parts[1].index_size(), parts[1].instance_count())
+    other = sharded.ShardedVariantModel(workloads.ALPHABET, A.Weights())
+    other.read_lexicon(workloads.lexicon_path("eng"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        other.load_index(files[2])
+    assert (other.shard, other.n_shards) == (2, 3)
+    again.save_index(str(tmp_path / "copy.idx"))
+    assert open(str(tmp_path / "copy.idx"), "rb").read() == open(files[1], "rb").read()
