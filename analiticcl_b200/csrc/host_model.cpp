@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 
+#include "hostpool.h"
 #include "unicode_tables.h"
 
 namespace anl {
@@ -22,6 +23,28 @@ const uint32_t kPrimes[168] = {
     631, 641, 643, 647, 653, 659, 661, 673, 677, 683, 691, 701, 709, 719, 727, 733, 739, 743, 751,
     757, 761, 769, 773, 787, 797, 809, 811, 821, 823, 827, 829, 839, 853, 857, 859, 863, 877, 881,
     883, 887, 907, 911, 919, 929, 937, 941, 947, 953, 967, 971, 977, 983, 991, 997};
+
+#if defined(__linux__)
+}  // namespace anl
+#include <sys/mman.h>
+namespace anl {
+static void advise_huge_pages(void* p, size_t bytes) {
+  const uintptr_t two_mb = (uintptr_t)2 << 20;
+  const uintptr_t lo = ((uintptr_t)p + two_mb - 1) & ~(two_mb - 1), hi = ((uintptr_t)p + bytes) & ~(two_mb - 1);
+  if (hi > lo) madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+}
+#else
+static void advise_huge_pages(void*, size_t) {}
+#endif
+// First touch of a large, freshly reserved block on all cores (page faults are the cost of a fresh allocation and
+// they scale with threads); the caller then initialises the already mapped memory as usual.
+static void prefault(void* p, size_t bytes) {
+  const size_t chunk = (size_t)2 << 20;
+  parallel_ranges((bytes + chunk - 1) / chunk, 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+    const size_t b = (size_t)lo * chunk, e = std::min(bytes, (size_t)hi * chunk);
+    if (e > b) memset((char*)p + b, 0, e - b);
+  });
+}
 
 // ---- UTF-8 ----------------------------------------------------------------------------------------
 static inline unsigned u8len(unsigned char c) {
@@ -458,6 +481,7 @@ std::vector<uint64_t> HostModel::anahash_limbs(const char* text, size_t len) con
 
 // ---- index build (src/lib.rs:192-245) ----------------------------------------------------------------------
 bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::string* err) {
+  PhaseTimer pt;
   HostIndex ix;
   ix.sd = sd;
   if (n_shards == 0 || shard >= n_shards) {
@@ -526,11 +550,13 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     *err = "vocabulary too large";
     return false;
   }
+  pt.lap("build: anagram keys");
   // instances in (key ascending, vocab id ascending) order = the reference's gather order
   std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
     if (!key_eq(a.key, b.key)) return key_less(a.key, b.key);
     return a.id < b.id;
   });
+  pt.lap("build: sort instances");
   ix.norm_stride = ((ix.max_len + 2) + 15) & ~15u;
   // lexicon-sharded mode: anagrams are partitioned by hash(key) mod n_shards (instances follow their
   // key); the position in the global (key, vocab id) order stays the tie-break key on every shard
@@ -585,6 +611,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   for (uint32_t s = 0; s < 256; ++s)
     if (class_seen[s]) ix.active_classes.push_back((uint8_t)s);
 
+  pt.lap("build: instance rows");
   // neighbour table: self postings, plus (sd = 1) one posting per distinct class of every anagram
   // The table is keyed by the linear multiset fingerprint mhash (device_types.h), not by the prime
   // product: mhash(C / p_x) = mhash(C) - class_rnd(x).
@@ -594,29 +621,66 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     uint8_t cls;
   };
   std::vector<Post> posts;
-  posts.reserve(ix.ana_key.size() * (sd ? 10 : 1));
-  for (uint32_t r = 0; r < ix.ana_key.size(); ++r) {
-    // symbols of this anagram from its first instance
-    const uint8_t* row = ix.inst_rows.data() + (size_t)ix.ana_inst_off[r] * ix.norm_stride;
-    uint64_t h = 0;
-    for (uint32_t i = 0; i < row[0]; ++i) h += class_rnd(row[2 + i]);
-    posts.push_back(Post{h, r, POST_SELF});
-    if (sd >= 1) {
-      bool seen[256] = {false};
-      for (uint32_t i = 0; i < row[0]; ++i) {
-        uint8_t x = row[2 + i];
-        if (seen[x]) continue;
-        seen[x] = true;
-        if (row[0] == 1) continue;  // the empty value is never a node (no empty leaves, src/iterators.rs:177)
-        posts.push_back(Post{h - class_rnd(x), r, x});
+  {
+    // generated on all cores, one list per thread; their concatenation order does not matter (sorted below)
+    std::vector<std::vector<Post>> part(host_threads());
+    const unsigned used = parallel_ranges(ix.ana_key.size(), 1u << 14, [&](unsigned tid, uint64_t lo, uint64_t hi) {
+      std::vector<Post>& mine = part[tid];
+      mine.reserve((hi - lo) * (sd ? 10 : 1));
+      for (uint64_t r = lo; r < hi; ++r) {
+        // symbols of this anagram from its first instance
+        const uint8_t* row = ix.inst_rows.data() + (size_t)ix.ana_inst_off[r] * ix.norm_stride;
+        uint64_t h = 0;
+        for (uint32_t i = 0; i < row[0]; ++i) h += class_rnd(row[2 + i]);
+        mine.push_back(Post{h, (uint32_t)r, POST_SELF});
+        if (sd >= 1) {
+          bool seen[256] = {false};
+          for (uint32_t i = 0; i < row[0]; ++i) {
+            uint8_t x = row[2 + i];
+            if (seen[x]) continue;
+            seen[x] = true;
+            if (row[0] == 1) continue;  // the empty value is never a node (no empty leaves, src/iterators.rs:177)
+            mine.push_back(Post{h - class_rnd(x), (uint32_t)r, x});
+          }
+        }
       }
+    });
+    size_t total = 0;
+    for (unsigned t = 0; t < used; ++t) total += part[t].size();
+    posts.reserve(total);
+    for (unsigned t = 0; t < used; ++t) posts.insert(posts.end(), part[t].begin(), part[t].end());
+  }
+  pt.lap("build: postings");
+  // Total order (fp, anagram, class).  fp is a hash, so its top byte splits the postings into 256 evenly filled
+  // buckets that are already in order among themselves: scatter, then sort the buckets on all cores.  (The order
+  // is total and equal postings are identical, so the result is the one a single std::sort gives.)
+  {
+    auto post_less = [](const Post& a, const Post& b) {
+      if (a.fp != b.fp) return a.fp < b.fp;
+      if (a.ana != b.ana) return a.ana < b.ana;
+      return a.cls < b.cls;
+    };
+    if (posts.size() < (1u << 16)) {
+      std::sort(posts.begin(), posts.end(), post_less);
+    } else {
+      std::vector<uint64_t> first(257, 0);
+      for (const Post& q : posts) ++first[(q.fp >> 56) + 1];
+      for (unsigned b = 0; b < 256; ++b) first[b + 1] += first[b];
+      std::vector<Post> sorted;
+      sorted.reserve(posts.size());
+      prefault(sorted.data(), posts.size() * sizeof(Post));
+      sorted.resize(posts.size());
+      {
+        std::vector<uint64_t> cursor(first.begin(), first.end() - 1);
+        for (const Post& q : posts) sorted[cursor[q.fp >> 56]++] = q;
+      }
+      parallel_ranges(256, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+        for (uint64_t b = lo; b < hi; ++b) std::sort(sorted.begin() + first[b], sorted.begin() + first[b + 1], post_less);
+      });
+      posts.swap(sorted);
     }
   }
-  std::sort(posts.begin(), posts.end(), [](const Post& a, const Post& b) {
-    if (a.fp != b.fp) return a.fp < b.fp;
-    if (a.ana != b.ana) return a.ana < b.ana;
-    return a.cls < b.cls;
-  });
+  pt.lap("build: sort postings");
   uint64_t groups = 0;
   for (size_t i = 0; i < posts.size(); ++i)
     if (i == 0 || posts[i].fp != posts[i - 1].fp) ++groups;
@@ -629,16 +693,31 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   // false positives (a wasted exact lookup each) for residency: up to ~8 keys per word (false positives
   // ~2-3 %) while the filter is larger than 128 MB.
   while (words * 8 > (128ull << 20) && words * 8 >= groups) words >>= 1;
+  // the table is written at random: ask for huge pages before the first touch (a 4 KB page per TLB entry makes
+  // every insertion a page walk once the table is hundreds of MB; harmless where THP is unavailable)
+  pt.lap("build: count keys");
+  ix.table.reserve(slots);
+  ix.bloom.reserve(words);
+  advise_huge_pages(ix.table.data(), slots * sizeof(Slot));
+  advise_huge_pages(ix.bloom.data(), words * sizeof(uint64_t));
+  prefault(ix.table.data(), slots * sizeof(Slot));
+  prefault(ix.bloom.data(), words * sizeof(uint64_t));
   ix.table.assign(slots, Slot{0, 0, 0, 0});
   ix.bloom.assign(words, 0);
   ix.post_ana.resize(posts.size());
   ix.post_cls.resize(posts.size());
+  pt.lap("build: allocate table");
   for (size_t i = 0; i < posts.size();) {
     size_t j = i;
     while (j < posts.size() && posts[j].fp == posts[i].fp) ++j;
     if (j - i > 0xFFFF) {
       *err = "posting list too long";
       return false;
+    }
+    if (i + 48 < posts.size()) {  // the home slot and Bloom word of a key a few dozen postings ahead: both are cache misses
+      const uint64_t ahead = posts[i + 48].fp;
+      __builtin_prefetch(&ix.table[fp_index(ahead, slots - 1)], 1);
+      __builtin_prefetch(&ix.bloom[fp_index(ahead, words - 1)], 1);
     }
     const uint64_t fp = posts[i].fp;
     uint64_t idx = fp_index(fp, slots - 1);
@@ -651,6 +730,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     }
     i = j;
   }
+  pt.lap("build: table + Bloom filter");
   index = std::move(ix);
   built = true;
   return true;
