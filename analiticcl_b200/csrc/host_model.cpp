@@ -620,12 +620,24 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     uint32_t ana;
     uint8_t cls;
   };
+  // Generated on all cores (one list per thread, a range of anagrams each), then brought into the total order
+  // (fp, anagram, class).  fp is a hash, so its top byte splits the postings into 256 evenly filled buckets that
+  // are already in order among themselves: every thread scatters its own list into the buckets (offsets from the
+  // per-thread bucket counts), then the buckets are sorted on all cores.  The order is total and equal postings
+  // are identical, so the result is the one a single std::sort over one list gives.
   std::vector<Post> posts;
   {
-    // generated on all cores, one list per thread; their concatenation order does not matter (sorted below)
-    std::vector<std::vector<Post>> part(host_threads());
+    auto post_less = [](const Post& a, const Post& b) {
+      if (a.fp != b.fp) return a.fp < b.fp;
+      if (a.ana != b.ana) return a.ana < b.ana;
+      return a.cls < b.cls;
+    };
+    const unsigned nt_max = host_threads();
+    std::vector<std::vector<Post>> part(nt_max);
+    std::vector<std::vector<uint64_t>> count(nt_max, std::vector<uint64_t>(256, 0));
     const unsigned used = parallel_ranges(ix.ana_key.size(), 1u << 14, [&](unsigned tid, uint64_t lo, uint64_t hi) {
       std::vector<Post>& mine = part[tid];
+      std::vector<uint64_t>& cnt = count[tid];
       mine.reserve((hi - lo) * (sd ? 10 : 1));
       for (uint64_t r = lo; r < hi; ++r) {
         // symbols of this anagram from its first instance
@@ -633,6 +645,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
         uint64_t h = 0;
         for (uint32_t i = 0; i < row[0]; ++i) h += class_rnd(row[2 + i]);
         mine.push_back(Post{h, (uint32_t)r, POST_SELF});
+        ++cnt[h >> 56];
         if (sd >= 1) {
           bool seen[256] = {false};
           for (uint32_t i = 0; i < row[0]; ++i) {
@@ -640,48 +653,39 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
             if (seen[x]) continue;
             seen[x] = true;
             if (row[0] == 1) continue;  // the empty value is never a node (no empty leaves, src/iterators.rs:177)
-            mine.push_back(Post{h - class_rnd(x), (uint32_t)r, x});
+            const uint64_t hx = h - class_rnd(x);
+            mine.push_back(Post{hx, (uint32_t)r, x});
+            ++cnt[hx >> 56];
           }
         }
       }
     });
-    size_t total = 0;
-    for (unsigned t = 0; t < used; ++t) total += part[t].size();
-    posts.reserve(total);
-    for (unsigned t = 0; t < used; ++t) {
-      posts.insert(posts.end(), part[t].begin(), part[t].end());
-      std::vector<Post>().swap(part[t]);  // (bounds the transient memory: 16 B per posting, ~10 postings per anagram)
-    }
-  }
-  pt.lap("build: postings");
-  // Total order (fp, anagram, class).  fp is a hash, so its top byte splits the postings into 256 evenly filled
-  // buckets that are already in order among themselves: scatter, then sort the buckets on all cores.  (The order
-  // is total and equal postings are identical, so the result is the one a single std::sort gives.)
-  {
-    auto post_less = [](const Post& a, const Post& b) {
-      if (a.fp != b.fp) return a.fp < b.fp;
-      if (a.ana != b.ana) return a.ana < b.ana;
-      return a.cls < b.cls;
-    };
-    if (posts.size() < (1u << 16)) {
-      std::sort(posts.begin(), posts.end(), post_less);
-    } else {
-      std::vector<uint64_t> first(257, 0);
-      for (const Post& q : posts) ++first[(q.fp >> 56) + 1];
-      for (unsigned b = 0; b < 256; ++b) first[b + 1] += first[b];
-      std::vector<Post> sorted;
-      sorted.reserve(posts.size());
-      prefault(sorted.data(), posts.size() * sizeof(Post));
-      sorted.resize(posts.size());
-      {
-        std::vector<uint64_t> cursor(first.begin(), first.end() - 1);
-        for (const Post& q : posts) sorted[cursor[q.fp >> 56]++] = q;
+    pt.lap("build: postings");
+    // bucket b holds [first[b], first[b + 1]); thread t writes its share of bucket b from offset[t][b] on
+    std::vector<uint64_t> first(257, 0);
+    for (unsigned b = 0; b < 256; ++b) {
+      uint64_t at = first[b];
+      for (unsigned t = 0; t < used; ++t) {
+        const uint64_t c = count[t][b];
+        count[t][b] = at;  // becomes the thread's write cursor for this bucket
+        at += c;
       }
-      parallel_ranges(256, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
-        for (uint64_t b = lo; b < hi; ++b) std::sort(sorted.begin() + first[b], sorted.begin() + first[b + 1], post_less);
-      });
-      posts.swap(sorted);
+      first[b + 1] = at;
     }
+    const uint64_t total = first[256];
+    posts.reserve(total);
+    prefault(posts.data(), total * sizeof(Post));
+    posts.resize(total);
+    parallel_ranges(used, 1, [&](unsigned, uint64_t tlo, uint64_t thi) {
+      for (uint64_t t = tlo; t < thi; ++t) {
+        std::vector<uint64_t>& cursor = count[t];
+        for (const Post& q : part[t]) posts[cursor[q.fp >> 56]++] = q;
+        std::vector<Post>().swap(part[t]);
+      }
+    });
+    parallel_ranges(256, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t b = lo; b < hi; ++b) std::sort(posts.begin() + first[b], posts.begin() + first[b + 1], post_less);
+    });
   }
   pt.lap("build: sort postings");
   uint64_t groups = 0;
