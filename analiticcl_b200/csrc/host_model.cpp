@@ -27,6 +27,7 @@ const uint32_t kPrimes[168] = {
 #if defined(__linux__)
 }  // namespace anl
 #include <sys/mman.h>
+#include <unistd.h>
 namespace anl {
 static void advise_huge_pages(void* p, size_t bytes) {
   const uintptr_t two_mb = (uintptr_t)2 << 20;
@@ -766,8 +767,33 @@ template <class T>
 bool read_array(FILE* f, std::vector<T>* v, uint64_t max_bytes) {
   uint64_t n = 0, b = 0;
   if (fread(&n, 8, 1, f) != 1 || fread(&b, 8, 1, f) != 1 || b != sizeof(T) || n > max_bytes / sizeof(T)) return false;
+  const size_t bytes = (size_t)n * sizeof(T);
+  if (bytes < ((size_t)8 << 20)) {
+    v->resize(n);
+    return n == 0 || fread(v->data(), sizeof(T), n, f) == n;
+  }
+  // large array: first touch and read on all cores (pread at this array's offset, 4 MB pieces)
+  v->reserve(n);
+  prefault(v->data(), bytes);
   v->resize(n);
-  return n == 0 || fread(v->data(), sizeof(T), n, f) == n;
+  const long at = ftell(f);
+  if (at < 0) return false;
+  const int fd = fileno(f);
+  const size_t piece = (size_t)4 << 20;
+  std::atomic<bool> ok{true};
+  parallel_ranges((bytes + piece - 1) / piece, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+    size_t pos = (size_t)lo * piece;
+    const size_t end = std::min(bytes, (size_t)hi * piece);
+    while (pos < end) {
+      const ssize_t got = pread(fd, (char*)v->data() + pos, end - pos, (off_t)at + (off_t)pos);
+      if (got <= 0) {
+        ok = false;
+        return;
+      }
+      pos += (size_t)got;
+    }
+  });
+  return ok && fseek(f, at + (long)bytes, SEEK_SET) == 0;
 }
 inline uint64_t fp_mix(uint64_t h, uint64_t x) {
   h ^= x + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
