@@ -47,6 +47,38 @@ static void prefault(void* p, size_t bytes) {
   });
 }
 
+// Sort under a TOTAL order (no two elements compare equal) on all cores: equal chunks sorted in parallel, then
+// merged pairwise in parallel rounds.  With a total order the result is the one std::sort gives.
+template <class T, class Less>
+static void parallel_sort(std::vector<T>& v, Less less) {
+  const size_t n = v.size();
+  unsigned parts = 1;
+  while (parts * 2 <= host_threads() && n / (parts * 2) >= (1u << 15)) parts *= 2;
+  if (parts == 1) {
+    std::sort(v.begin(), v.end(), less);
+    return;
+  }
+  std::vector<size_t> cut(parts + 1);
+  for (unsigned i = 0; i <= parts; ++i) cut[i] = n / parts * i;
+  cut[parts] = n;
+  parallel_ranges(parts, 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+    for (uint64_t q = lo; q < hi; ++q) std::sort(v.begin() + cut[q], v.begin() + cut[q + 1], less);
+  });
+  std::vector<T> other(n);
+  T* src = v.data();
+  T* dst = other.data();
+  for (unsigned width = 1; width < parts; width *= 2) {
+    parallel_ranges(parts / (2 * width), 1, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t q = lo; q < hi; ++q) {
+        const size_t a = cut[q * 2 * width], m = cut[q * 2 * width + width], e = cut[q * 2 * width + 2 * width];
+        std::merge(src + a, src + m, src + m, src + e, dst + a, less);
+      }
+    });
+    std::swap(src, dst);
+  }
+  if (src != v.data()) std::copy(src, src + n, v.data());
+}
+
 // ---- UTF-8 ----------------------------------------------------------------------------------------
 static inline unsigned u8len(unsigned char c) {
   if (c < 0x80) return 1;
@@ -517,31 +549,67 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     uint32_t id;
   };
   std::vector<Item> items;
-  items.reserve(decoder.size());
   bool class_seen[256] = {false};
-  for (size_t id = 0; id < decoder.size(); ++id) {
-    const VocabEntry& v = decoder[id];
-    if (!(v.vocabtype & VT_INDEXED)) continue;
-    if (v.syms.empty()) {
-      // reference: anahash of "" is 1 and the entry is indexed under it; it can never be returned
-      // (deletions never reach the empty value, src/iterators.rs:177) except as an exact match of an
-      // empty query, which the reference rejects (src/lib.rs:1420).  Not indexed here.
-      continue;
+  {
+    // keys on all cores, a range of vocabulary ids per thread; the lists are joined in id order, and the first
+    // offending entry (lowest id) is the one reported, as a serial pass would
+    struct Part {
+      std::vector<Item> items;
+      bool class_seen[256] = {false};
+      uint32_t max_len = 0, max_key_bits = 0;
+      size_t bad_id = SIZE_MAX;
+      int bad_kind = 0;  // 1 = too long, 2 = key overflow
+    };
+    std::vector<Part> part(host_threads());
+    const unsigned used = parallel_ranges(decoder.size(), 1u << 14, [&](unsigned tid, uint64_t lo, uint64_t hi) {
+      Part& mine = part[tid];
+      mine.items.reserve(hi - lo);
+      for (size_t id = lo; id < hi; ++id) {
+        const VocabEntry& v = decoder[id];
+        if (!(v.vocabtype & VT_INDEXED)) continue;
+        if (v.syms.empty()) {
+          // reference: anahash of "" is 1 and the entry is indexed under it; it can never be returned
+          // (deletions never reach the empty value, src/iterators.rs:177) except as an exact match of an
+          // empty query, which the reference rejects (src/lib.rs:1420).  Not indexed here.
+          continue;
+        }
+        if (v.syms.size() > (size_t)ANL_MAX_SYMBOLS) {
+          mine.bad_id = id;
+          mine.bad_kind = 1;
+          return;
+        }
+        Item it;
+        if (!key_of(v.syms.data(), v.syms.size(), &it.key)) {
+          mine.bad_id = id;
+          mine.bad_kind = 2;
+          return;
+        }
+        it.id = (uint32_t)id;
+        mine.items.push_back(it);
+        for (uint8_t s : v.syms) mine.class_seen[s] = true;
+        mine.max_len = std::max<uint32_t>(mine.max_len, (uint32_t)v.syms.size());
+        mine.max_key_bits = std::max(mine.max_key_bits, key_bits(it.key));
+      }
+    });
+    size_t total = 0;
+    for (unsigned t = 0; t < used; ++t) {  // ranges ascend with t: the first failing part holds the lowest failing id
+      if (part[t].bad_kind == 1) {
+        *err = "lexicon entry longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols: " + decoder[part[t].bad_id].text;
+        return false;
+      }
+      if (part[t].bad_kind == 2) {
+        *err = "anagram value of lexicon entry exceeds 192 bits: " + decoder[part[t].bad_id].text;
+        return false;
+      }
+      total += part[t].items.size();
     }
-    if (v.syms.size() > (size_t)ANL_MAX_SYMBOLS) {
-      *err = "lexicon entry longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols: " + v.text;
-      return false;
+    items.reserve(total);
+    for (unsigned t = 0; t < used; ++t) {
+      items.insert(items.end(), part[t].items.begin(), part[t].items.end());
+      for (int c = 0; c < 256; ++c) class_seen[c] = class_seen[c] || part[t].class_seen[c];
+      ix.max_len = std::max(ix.max_len, part[t].max_len);
+      ix.max_key_bits = std::max(ix.max_key_bits, part[t].max_key_bits);
     }
-    Item it;
-    if (!key_of(v.syms.data(), v.syms.size(), &it.key)) {
-      *err = "anagram value of lexicon entry exceeds 192 bits: " + v.text;
-      return false;
-    }
-    it.id = (uint32_t)id;
-    items.push_back(it);
-    for (uint8_t s : v.syms) class_seen[s] = true;
-    ix.max_len = std::max<uint32_t>(ix.max_len, (uint32_t)v.syms.size());
-    ix.max_key_bits = std::max(ix.max_key_bits, key_bits(it.key));
   }
   if (items.empty()) {
     *err = "no indexed vocabulary entries";
@@ -553,7 +621,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   }
   pt.lap("build: anagram keys");
   // instances in (key ascending, vocab id ascending) order = the reference's gather order
-  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+  parallel_sort(items, [](const Item& a, const Item& b) {
     if (!key_eq(a.key, b.key)) return key_less(a.key, b.key);
     return a.id < b.id;
   });

@@ -104,3 +104,22 @@ def test_no_exception_crosses_the_c_boundary(so):
     ms = ctypes.c_void_p()
     rc = L.anl_debug_match_set_build(b"a", 1, 1, 0, looked, offs, None, 1, ctypes.byref(ms))
     assert rc != 0 and b"out of memory" in L.anl_last_error()
+
+
+def test_build_limits_are_reported_for_the_first_offending_entry():
+    """The host index build rejects what the 192-bit device keys cannot hold; the keys are
+    computed on all cores and the entry reported is the first one in vocabulary order, as in a serial pass."""
+    import analiticcl_b200 as A
+    import workloads
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path("eng"))  # > 100 k entries: several threads
+    m.add_to_vocabulary("z" * 40, 1, A.VocabParams())
+    m.add_to_vocabulary("y" * 300, 1, A.VocabParams())
+    m.add_to_vocabulary("z" * 41, 1, A.VocabParams())
+    with pytest.raises(RuntimeError, match="exceeds 192 bits: z{40}$"):
+        m.build()
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.add_to_vocabulary("y" * 300, 1, A.VocabParams())
+    m.add_to_vocabulary("z" * 40, 1, A.VocabParams())
+    with pytest.raises(RuntimeError, match="longer than"):
+        m.build()
