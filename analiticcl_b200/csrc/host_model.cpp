@@ -656,25 +656,63 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     ix.norm_stride = ((ix.max_len + 2) + 15) & ~15u;
     ix.inst_gid = gids;
   }
-  ix.inst_rows.assign((size_t)items.size() * ix.norm_stride, 0);
-  ix.inst_vocab.resize(items.size());
-  ix.inst_freq.resize(items.size());
-  for (size_t g = 0; g < items.size(); ++g) {
-    const VocabEntry& v = decoder[items[g].id];
-    if (g == 0 || !key_eq(items[g].key, items[g - 1].key)) {
-      ix.ana_key.push_back(items[g].key);
-      ix.ana_inst_off.push_back((uint32_t)g);
-      ix.ana_charcount.push_back((uint16_t)v.syms.size());
-      const uint32_t cc = (uint32_t)v.syms.size();
-      ix.charcount_mask[cc >> 6] |= 1ull << (cc & 63);
-      ix.max_charcount = std::max(ix.max_charcount, cc);
+  {
+    // Instance rows and the anagram arrays on all cores: a range of instances per thread; an anagram starts where
+    // the key changes, so a thread first counts the anagrams that start in its range, the ranges' counts give
+    // every thread its first anagram rank, and the second pass fills rows and anagram entries in place.
+    const size_t ninst = items.size();
+    ix.inst_rows.reserve(ninst * ix.norm_stride);
+    prefault(ix.inst_rows.data(), ninst * ix.norm_stride);
+    ix.inst_rows.assign(ninst * ix.norm_stride, 0);
+    ix.inst_vocab.resize(ninst);
+    ix.inst_freq.resize(ninst);
+    auto starts_anagram = [&](size_t g) { return g == 0 || !key_eq(items[g].key, items[g - 1].key); };
+    const unsigned nt_max = host_threads();
+    std::vector<uint64_t> first_rank(nt_max + 1, 0);
+    std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+    const unsigned used = parallel_ranges(ninst, 1u << 14, [&](unsigned tid, uint64_t lo, uint64_t hi) {
+      range[tid] = {lo, hi};
+      uint64_t c = 0;
+      for (size_t g = lo; g < hi; ++g) c += starts_anagram(g) ? 1 : 0;
+      first_rank[tid + 1] = c;
+    });
+    for (unsigned t = 0; t < used; ++t) first_rank[t + 1] += first_rank[t];
+    const size_t nana = first_rank[used];
+    ix.ana_key.resize(nana);
+    ix.ana_inst_off.resize(nana);
+    ix.ana_charcount.resize(nana);
+    struct Seen {
+      uint64_t mask[4] = {0, 0, 0, 0};
+      uint32_t max_cc = 0;
+    };
+    std::vector<Seen> seen(nt_max);
+    parallel_ranges(used, 1, [&](unsigned, uint64_t tlo, uint64_t thi) {
+      for (uint64_t t = tlo; t < thi; ++t) {
+        uint64_t r = first_rank[t];
+        for (size_t g = range[t].first; g < range[t].second; ++g) {
+          const VocabEntry& v = decoder[items[g].id];
+          if (starts_anagram(g)) {
+            const uint32_t cc = (uint32_t)v.syms.size();
+            ix.ana_key[r] = items[g].key;
+            ix.ana_inst_off[r] = (uint32_t)g;
+            ix.ana_charcount[r] = (uint16_t)cc;
+            seen[t].mask[cc >> 6] |= 1ull << (cc & 63);
+            seen[t].max_cc = std::max(seen[t].max_cc, cc);
+            ++r;
+          }
+          uint8_t* row = ix.inst_rows.data() + g * ix.norm_stride;
+          row[0] = (uint8_t)v.syms.size();
+          row[1] = v.first_lower ? ROW_FIRST_LOWER : 0;
+          memcpy(row + 2, v.syms.data(), v.syms.size());
+          ix.inst_vocab[g] = items[g].id;
+          ix.inst_freq[g] = v.frequency;
+        }
+      }
+    });
+    for (unsigned t = 0; t < used; ++t) {
+      for (int w = 0; w < 4; ++w) ix.charcount_mask[w] |= seen[t].mask[w];
+      ix.max_charcount = std::max(ix.max_charcount, seen[t].max_cc);
     }
-    uint8_t* row = ix.inst_rows.data() + g * ix.norm_stride;
-    row[0] = (uint8_t)v.syms.size();
-    row[1] = v.first_lower ? ROW_FIRST_LOWER : 0;
-    memcpy(row + 2, v.syms.data(), v.syms.size());
-    ix.inst_vocab[g] = items[g].id;
-    ix.inst_freq[g] = v.frequency;
   }
   ix.ana_inst_off.push_back((uint32_t)items.size());
   for (uint32_t s = 0; s < 256; ++s)
