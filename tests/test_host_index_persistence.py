@@ -115,3 +115,25 @@ def test_sharded_index_round_trip(tmp_path):
     assert (other.shard, other.n_shards) == (2, 3)
     again.save_index(str(tmp_path / "copy.idx"))
     assert open(str(tmp_path / "copy.idx"), "rb").read() == open(files[1], "rb").read()
+
+
+def test_parallel_build_is_deterministic(tmp_path):
+    """The index build runs on all cores (keys, instance sort, rows, posting generation and sort); its output must
+    not depend on the number of threads: one thread (a plain serial pass) and three threads (uneven ranges) give
+    the file the default thread count gives."""
+    import subprocess
+    import sys
+    import analiticcl_b200 as A
+    m = model(A, "nld")
+    host_build(m)
+    ref = str(tmp_path / "nld.idx")
+    m.save_index(ref)
+    code = ("import sys; sys.path.insert(0, %r); import workloads, analiticcl_b200 as A\n"
+            "m = A.VariantModel(workloads.ALPHABET, A.Weights()); m.read_lexicon(workloads.lexicon_path('nld'))\n"
+            "try:\n    m.build()\nexcept RuntimeError:\n    pass\n"
+            "m.save_index(sys.argv[1])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for threads in ("1", "3"):
+        out = str(tmp_path / f"nld.t{threads}.idx")
+        env = dict(os.environ, ANL_HOST_THREADS=threads)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
+        assert open(out, "rb").read() == open(ref, "rb").read(), f"{threads} thread(s)"
