@@ -818,9 +818,28 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   prefault(ix.bloom.data(), words * sizeof(uint64_t));
   ix.table.assign(slots, Slot{0, 0, 0, 0});
   ix.bloom.assign(words, 0);
+  ix.post_ana.reserve(posts.size());
+  ix.post_cls.reserve(posts.size());
+  prefault(ix.post_ana.data(), posts.size() * sizeof(uint32_t));
+  prefault(ix.post_cls.data(), posts.size());
   ix.post_ana.resize(posts.size());
   ix.post_cls.resize(posts.size());
   pt.lap("build: allocate table");
+  // Everything that does not depend on the insertion order runs on all cores first: the posting arrays (a plain
+  // copy) and the Bloom words (OR is commutative; atomic because ranges share words).
+  parallel_ranges(posts.size(), 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+    for (uint64_t t = lo; t < hi; ++t) {
+      ix.post_ana[t] = posts[t].ana;
+      ix.post_cls[t] = posts[t].cls;
+      if (t == 0 || posts[t].fp != posts[t - 1].fp) {
+        const uint64_t fp = posts[t].fp;
+        __atomic_fetch_or(&ix.bloom[fp_index(fp, words - 1)], bloom_mask(fp), __ATOMIC_RELAXED);
+      }
+    }
+  });
+  pt.lap("build: postings arrays + Bloom filter");
+  // The table itself is filled in key order on one thread: with linear probing the slot of a colliding key depends
+  // on who came first, and the layout is kept reproducible.
   for (size_t i = 0; i < posts.size();) {
     size_t j = i;
     while (j < posts.size() && posts[j].fp == posts[i].fp) ++j;
@@ -828,23 +847,15 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
       *err = "posting list too long";
       return false;
     }
-    if (i + 48 < posts.size()) {  // the home slot and Bloom word of a key a few dozen postings ahead: both are cache misses
-      const uint64_t ahead = posts[i + 48].fp;
-      __builtin_prefetch(&ix.table[fp_index(ahead, slots - 1)], 1);
-      __builtin_prefetch(&ix.bloom[fp_index(ahead, words - 1)], 1);
-    }
+    if (i + 160 < posts.size())  // the home slot of a key some hundred postings ahead: a cache miss
+      __builtin_prefetch(&ix.table[fp_index(posts[i + 160].fp, slots - 1)], 1);
     const uint64_t fp = posts[i].fp;
     uint64_t idx = fp_index(fp, slots - 1);
     while (ix.table[idx].post_cnt != 0) idx = (idx + 1) & (slots - 1);
     ix.table[idx] = Slot{fp, (uint32_t)i, (uint16_t)(j - i), 0};
-    ix.bloom[fp_index(fp, words - 1)] |= bloom_mask(fp);
-    for (size_t t = i; t < j; ++t) {
-      ix.post_ana[t] = posts[t].ana;
-      ix.post_cls[t] = posts[t].cls;
-    }
     i = j;
   }
-  pt.lap("build: table + Bloom filter");
+  pt.lap("build: table");
   index = std::move(ix);
   built = true;
   return true;
