@@ -1,6 +1,7 @@
 // capi.cpp -- the extern "C" boundary declared in include/analiticcl_b200.h.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -352,14 +353,12 @@ anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_
   if (!m || !offsets || !params || !out || (!blob && n_queries > 0)) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built || !m->engine.uploaded())
     return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_variants()");
-  anl_result_set* rs = new anl_result_set();
+  std::unique_ptr<anl_result_set> rs(new anl_result_set());
   std::string err;
   int status = ANL_OK;
-  if (!m->engine.find_variants_batch(blob ? blob : "", offsets, n_queries, *params, &rs->rs, &err, &status)) {
-    delete rs;
+  if (!m->engine.find_variants_batch(blob ? blob : "", offsets, n_queries, *params, &rs->rs, &err, &status))
     return fail(status ? status : ANL_ERR_CUDA, err);
-  }
-  *out = rs;
+  *out = rs.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -394,7 +393,8 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   // results do not make redundant (redundant_match only reads unigram results, src/search.rs:317-336).
   PhaseTimer pt;
   const std::string t(text ? text : "", len);
-  anl_match_set* ms = new anl_match_set();
+  std::unique_ptr<anl_match_set> ms_owner(new anl_match_set());  // (released to *out on success only)
+  anl_match_set* ms = ms_owner.get();
   SegmentedText st;
   segment_text(t, params->max_ngram, &st);
   pt.lap("search: segmentation");
@@ -616,10 +616,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
     pt.lap("search: assemble matches");
     b0 = b1;
   }
-  if (!ok) {
-    delete ms;
-    return fail(status ? status : ANL_ERR_CUDA, err);
-  }
+  if (!ok) return fail(status ? status : ANL_ERR_CUDA, err);
   const anl_variant* vbase = ms->variants.data();
   parallel_ranges(nseg, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
     for (uint64_t k = lo; k < hi; ++k) {
@@ -632,7 +629,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
             (unsigned long long)logical_lookups, (unsigned long long)distinct_lookups);
   ms->logical_lookups = logical_lookups;
   ms->distinct_lookups = distinct_lookups;
-  *out = ms;
+  *out = ms_owner.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -704,7 +701,8 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
     }
   });
   pt.lap("consolidate: lattices");
-  anl_match_set* ms = new anl_match_set();
+  std::unique_ptr<anl_match_set> ms_owner(new anl_match_set());
+  anl_match_set* ms = ms_owner.get();
   ms->logical_lookups = in->logical_lookups;
   ms->distinct_lookups = in->distinct_lookups;
   // every thread copies the matches of its own batches behind those of the threads before it
@@ -737,7 +735,7 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
     }
   });
   pt.lap("consolidate: assemble");
-  *out = ms;
+  *out = ms_owner.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -782,7 +780,8 @@ anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_
   if (st.segs.size() != nseg) return fail(ANL_ERR_INVALID, "segment count differs from the producer's");
   std::vector<uint64_t> cpmap;
   if (unicodeoffsets) cpmap = byte_to_codepoint_map(t);
-  anl_match_set* ms = new anl_match_set();
+  std::unique_ptr<anl_match_set> ms_owner(new anl_match_set());
+  anl_match_set* ms = ms_owner.get();
   ms->matches.resize(nseg);
   ms->variants.reserve((nseg ? offsets[nseg] : 0) + 1);
   ms->variants.resize(nseg ? offsets[nseg] : 0);
@@ -798,7 +797,7 @@ anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_
     mm.selected = (looked[k] && cnt > 0) ? 0 : -1;
     mm.variants = looked[k] ? ms->variants.data() + offsets[k] : nullptr;
   }
-  *out = ms;
+  *out = ms_owner.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -861,14 +860,11 @@ anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, flo
 }
 anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_set** out) try {
   if (!m || !b || !out) return fail(ANL_ERR_INVALID, "null argument");
-  anl_result_set* rs = new anl_result_set();
+  std::unique_ptr<anl_result_set> rs(new anl_result_set());
   std::string err;
   int status = ANL_OK;
-  if (!m->engine.fetch_batch(b->b, &rs->rs, false, &err, &status)) {
-    delete rs;
-    return fail(status ? status : ANL_ERR_CUDA, err);
-  }
-  *out = rs;
+  if (!m->engine.fetch_batch(b->b, &rs->rs, false, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
+  *out = rs.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -909,15 +905,13 @@ anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards,
                            uint32_t max_survivors, anl_result_set** out) try {
   if (!m || !b || !d_heads_all || !d_records_all || !d_gids_all || !d_flags_all)
     return fail(ANL_ERR_INVALID, "null argument");
-  anl_result_set* rs = out ? new anl_result_set() : nullptr;
+  std::unique_ptr<anl_result_set> rs(out ? new anl_result_set() : nullptr);
   std::string err;
   int status = ANL_OK;
   if (!m->engine.shard_merge(b->b, n_shards, d_heads_all, d_records_all, d_gids_all, d_flags_all, record_stride, max_survivors,
-                             rs ? &rs->rs : nullptr, &err, &status)) {
-    delete rs;
+                             rs ? &rs->rs : nullptr, &err, &status))
     return fail(status ? status : ANL_ERR_CUDA, err);
-  }
-  if (out) *out = rs;
+  if (out) *out = rs.release();
   return ANL_OK;
 } catch (...) {
   return on_exception();

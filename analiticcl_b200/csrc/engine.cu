@@ -18,6 +18,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 
 #include "hostpool.h"
 #include "unicode_tables.h"
@@ -127,8 +128,9 @@ void Engine::release_index() {
   d_ix_ = nullptr;
 }
 
-template <class T>
-static bool upload_vec(const std::vector<T>& v, const T** out, std::vector<void*>* allocs, std::string* err) {
+template <class V, class T>
+static bool upload_vec(const V& v, const T** out, std::vector<void*>* allocs, std::string* err) {
+  static_assert(std::is_same<typename V::value_type, T>::value, "element type mismatch");
   void* p = nullptr;
   CU_TRY(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
   allocs->push_back(p);

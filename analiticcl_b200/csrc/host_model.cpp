@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <type_traits>
 
 #include "hostpool.h"
 #include "unicode_tables.h"
@@ -37,8 +38,8 @@ static void advise_huge_pages(void* p, size_t bytes) {
 #else
 static void advise_huge_pages(void*, size_t) {}
 #endif
-// First touch of a large, freshly reserved block on all cores (page faults are the cost of a fresh allocation and
-// they scale with threads); the caller then initialises the already mapped memory as usual.
+// First touch (zero fill) of a large, freshly sized RawVec on all cores: page faults are the cost of a fresh
+// allocation and they scale with threads.
 static void prefault(void* p, size_t bytes) {
   const size_t chunk = (size_t)2 << 20;
   parallel_ranges((bytes + chunk - 1) / chunk, 16, [&](unsigned, uint64_t lo, uint64_t hi) {
@@ -247,6 +248,8 @@ uint64_t HostModel::add_to_vocabulary(const char* text, size_t len, bool has_fre
   auto it = encoder.find(key);
   if (it != encoder.end()) {
     VocabEntry& item = decoder[it->second];
+    const uint32_t old_frequency = item.frequency;
+    const uint8_t old_type = item.vocabtype;
     switch (p.freq_handling) {
       case FH_SUM: item.frequency += frequency; break;
       case FH_MAX: if (frequency > item.frequency) item.frequency = frequency; break;
@@ -258,6 +261,9 @@ uint64_t HostModel::add_to_vocabulary(const char* text, size_t len, bool has_fre
     else if ((item.vocabtype & VT_TRANSPARENT) && !(p.vocab_type & VT_TRANSPARENT))
       item.vocabtype ^= VT_TRANSPARENT;
     item.lexindex |= 1u << (p.index & 31);
+    // the device index holds its own copy of the frequencies (the reference reads decoder[].frequency live in
+    // score_and_rank): a changed entry invalidates the built index instead of ranking with stale values
+    if (item.frequency != old_frequency || item.vocabtype != old_type) built = false;
     return it->second;
   }
   const uint64_t id = decoder.size();
@@ -512,6 +518,24 @@ std::vector<uint64_t> HostModel::anahash_limbs(const char* text, size_t len) con
   return v;
 }
 
+bool HostModel::check_variant_support(uint32_t n_shards, std::string* err) const {
+  if (!any_variants) return true;
+  // Results are expanded on the host from the candidates that pass the score threshold.  The reference decides
+  // *whether* to expand from every instance within the edit distance (src/lib.rs:1464); the two differ only for
+  // a transparent entry that holds no variant reference (it is dropped iff the list is expanded at all).
+  if (n_shards > 1) {
+    *err = "variant lists are not supported in the lexicon-sharded mode";
+    return false;
+  }
+  for (size_t id = 3; id < decoder.size(); ++id)
+    if ((decoder[id].vocabtype & VT_TRANSPARENT) && !decoder[id].has_variants) {
+      *err = "a transparent entry without variant references (" + decoder[id].text +
+             ") next to variant lists is not supported by the GPU path";
+      return false;
+    }
+  return true;
+}
+
 // ---- index build (src/lib.rs:192-245) ----------------------------------------------------------------------
 bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::string* err) {
   PhaseTimer pt;
@@ -523,21 +547,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   }
   ix.shard = shard;
   ix.n_shards = n_shards;
-  if (any_variants) {
-    // Results are expanded on the host from the candidates that pass the score threshold.  The reference decides
-    // *whether* to expand from every instance within the edit distance (src/lib.rs:1464); the two differ only for
-    // a transparent entry that holds no variant reference (it is dropped iff the list is expanded at all).
-    if (n_shards > 1) {
-      *err = "variant lists are not supported in the lexicon-sharded mode";
-      return false;
-    }
-    for (size_t id = 3; id < decoder.size(); ++id)
-      if ((decoder[id].vocabtype & VT_TRANSPARENT) && !decoder[id].has_variants) {
-        *err = "a transparent entry without variant references (" + decoder[id].text +
-               ") next to variant lists is not supported by the GPU path";
-        return false;
-      }
-  }
+  if (!check_variant_support(n_shards, err)) return false;
   if (alphabet.size() + 1 > 168) {
     *err = "alphabet has more classes than there are primes (168)";
     return false;
@@ -661,9 +671,8 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
     // the key changes, so a thread first counts the anagrams that start in its range, the ranges' counts give
     // every thread its first anagram rank, and the second pass fills rows and anagram entries in place.
     const size_t ninst = items.size();
-    ix.inst_rows.reserve(ninst * ix.norm_stride);
+    ix.inst_rows.resize(ninst * ix.norm_stride);
     prefault(ix.inst_rows.data(), ninst * ix.norm_stride);
-    ix.inst_rows.assign(ninst * ix.norm_stride, 0);
     ix.inst_vocab.resize(ninst);
     ix.inst_freq.resize(ninst);
     auto starts_anagram = [&](size_t g) { return g == 0 || !key_eq(items[g].key, items[g - 1].key); };
@@ -732,7 +741,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   // are already in order among themselves: every thread scatters its own list into the buckets (offsets from the
   // per-thread bucket counts), then the buckets are sorted on all cores.  The order is total and equal postings
   // are identical, so the result is the one a single std::sort over one list gives.
-  std::vector<Post> posts;
+  RawVec<Post> posts;
   {
     auto post_less = [](const Post& a, const Post& b) {
       if (a.fp != b.fp) return a.fp < b.fp;
@@ -780,9 +789,8 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
       first[b + 1] = at;
     }
     const uint64_t total = first[256];
-    posts.reserve(total);
-    prefault(posts.data(), total * sizeof(Post));
     posts.resize(total);
+    prefault(posts.data(), total * sizeof(Post));
     parallel_ranges(used, 1, [&](unsigned, uint64_t tlo, uint64_t thi) {
       for (uint64_t t = tlo; t < thi; ++t) {
         std::vector<uint64_t>& cursor = count[t];
@@ -810,20 +818,16 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   // the table is written at random: ask for huge pages before the first touch (a 4 KB page per TLB entry makes
   // every insertion a page walk once the table is hundreds of MB; harmless where THP is unavailable)
   pt.lap("build: count keys");
-  ix.table.reserve(slots);
-  ix.bloom.reserve(words);
+  ix.table.resize(slots);  // (RawVec: no fill; the parallel first touch below zeroes them = empty slots / words)
+  ix.bloom.resize(words);
   advise_huge_pages(ix.table.data(), slots * sizeof(Slot));
   advise_huge_pages(ix.bloom.data(), words * sizeof(uint64_t));
   prefault(ix.table.data(), slots * sizeof(Slot));
   prefault(ix.bloom.data(), words * sizeof(uint64_t));
-  ix.table.assign(slots, Slot{0, 0, 0, 0});
-  ix.bloom.assign(words, 0);
-  ix.post_ana.reserve(posts.size());
-  ix.post_cls.reserve(posts.size());
-  prefault(ix.post_ana.data(), posts.size() * sizeof(uint32_t));
-  prefault(ix.post_cls.data(), posts.size());
   ix.post_ana.resize(posts.size());
   ix.post_cls.resize(posts.size());
+  prefault(ix.post_ana.data(), posts.size() * sizeof(uint32_t));
+  prefault(ix.post_cls.data(), posts.size());
   pt.lap("build: allocate table");
   // Everything that does not depend on the insertion order runs on all cores first: the posting arrays (a plain
   // copy) and the Bloom words (OR is commutative; atomic because ranges share words).
@@ -863,7 +867,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
 
 // ---- persistence of the built index -------------------------------------------------------------------------------
 namespace {
-const char kIndexMagic[8] = {'A', 'N', 'L', 'I', 'D', 'X', '0', '1'};
+const char kIndexMagic[8] = {'A', 'N', 'L', 'I', 'D', 'X', '0', '2'};
 struct IndexFileHeader {  // fixed-size, little-endian hosts only (x86-64 / aarch64)
   char magic[8];
   uint32_t header_bytes, slot_bytes, key_bytes, max_k;
@@ -872,16 +876,76 @@ struct IndexFileHeader {  // fixed-size, little-endian hosts only (x86-64 / aarc
   int32_t sd;
   uint32_t reserved;
   uint64_t table_keys;
+  uint64_t checksum;  // content_checksum() of every array that follows the header
   uint64_t charcount_mask[4];
   uint32_t prime_of[256];
 };
-template <class T>
-bool write_array(FILE* f, const std::vector<T>& v) {
+// 64-bit checksum of a byte range on all cores: fixed 4 MB pieces hashed independently (8 bytes per step), the
+// piece hashes folded in piece order -- independent of the thread count.
+uint64_t fp_mix(uint64_t h, uint64_t x);
+uint64_t bytes_checksum(const void* data, size_t bytes) {
+  const size_t piece = (size_t)4 << 20;
+  const size_t np = (bytes + piece - 1) / piece;
+  std::vector<uint64_t> ph(np, 0);
+  parallel_ranges(np, 4, [&](unsigned, uint64_t lo, uint64_t hi) {
+    for (uint64_t q = lo; q < hi; ++q) {
+      const unsigned char* p = (const unsigned char*)data + (size_t)q * piece;
+      size_t n = std::min(piece, bytes - (size_t)q * piece);
+      uint64_t h0 = 0x9E3779B97F4A7C15ULL ^ n, h1 = 0xC2B2AE3D27D4EB4FULL, h2 = 0x165667B19E3779F9ULL, h3 = 0xD6E8FEB86659FD93ULL;
+      while (n >= 32) {  // four independent lanes: the multiplies pipeline
+        uint64_t w[4];
+        memcpy(w, p, 32);
+        h0 = (h0 ^ w[0]) * 0xFF51AFD7ED558CCDULL; h0 ^= h0 >> 29;
+        h1 = (h1 ^ w[1]) * 0xC4CEB9FE1A85EC53ULL; h1 ^= h1 >> 31;
+        h2 = (h2 ^ w[2]) * 0x9FB21C651E98DF25ULL; h2 ^= h2 >> 30;
+        h3 = (h3 ^ w[3]) * 0xD6E8FEB86659FD93ULL; h3 ^= h3 >> 28;
+        p += 32;
+        n -= 32;
+      }
+      while (n) {
+        const size_t k = std::min<size_t>(n, 8);
+        uint64_t w = 0;
+        memcpy(&w, p, k);
+        h0 = (h0 ^ w) * 0xFF51AFD7ED558CCDULL; h0 ^= h0 >> 29;
+        p += k;
+        n -= k;
+      }
+      ph[q] = fp_mix(fp_mix(fp_mix(h0, h1), h2), h3);
+    }
+  });
+  uint64_t h = 0x414E4C43ULL ^ bytes;
+  for (uint64_t v : ph) h = fp_mix(h, v);
+  return h;
+}
+template <class V>
+uint64_t array_checksum(uint64_t h, const V& v) {
+  return fp_mix(fp_mix(h, v.size()), bytes_checksum(v.data(), v.size() * sizeof(typename V::value_type)));
+}
+uint64_t content_checksum(const HostIndex& ix) {
+  uint64_t h = 0x414E4C58ULL;
+  h = array_checksum(h, ix.ana_key);
+  h = array_checksum(h, ix.ana_inst_off);
+  h = array_checksum(h, ix.ana_charcount);
+  h = array_checksum(h, ix.inst_vocab);
+  h = array_checksum(h, ix.inst_freq);
+  h = array_checksum(h, ix.inst_gid);
+  h = array_checksum(h, ix.inst_rows);
+  h = array_checksum(h, ix.table);
+  h = array_checksum(h, ix.bloom);
+  h = array_checksum(h, ix.post_ana);
+  h = array_checksum(h, ix.post_cls);
+  h = array_checksum(h, ix.active_classes);
+  return h;
+}
+template <class V>
+bool write_array(FILE* f, const V& v) {
+  typedef typename V::value_type T;
   const uint64_t n = v.size(), b = sizeof(T);
   return fwrite(&n, 8, 1, f) == 1 && fwrite(&b, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
 }
-template <class T>
-bool read_array(FILE* f, std::vector<T>* v, uint64_t max_bytes) {
+template <class V>
+bool read_array(FILE* f, V* v, uint64_t max_bytes) {
+  typedef typename V::value_type T;
   uint64_t n = 0, b = 0;
   if (fread(&n, 8, 1, f) != 1 || fread(&b, 8, 1, f) != 1 || b != sizeof(T) || n > max_bytes / sizeof(T)) return false;
   const size_t bytes = (size_t)n * sizeof(T);
@@ -890,9 +954,8 @@ bool read_array(FILE* f, std::vector<T>* v, uint64_t max_bytes) {
     return n == 0 || fread(v->data(), sizeof(T), n, f) == n;
   }
   // large array: first touch and read on all cores (pread at this array's offset, 4 MB pieces)
-  v->reserve(n);
-  prefault(v->data(), bytes);
   v->resize(n);
+  if (!std::is_same<V, std::vector<T>>::value) prefault(v->data(), bytes);  // (a plain vector was just zero-filled)
   const long at = ftell(f);
   if (at < 0) return false;
   const int fd = fileno(f);
@@ -912,7 +975,7 @@ bool read_array(FILE* f, std::vector<T>* v, uint64_t max_bytes) {
   });
   return ok && fseek(f, at + (long)bytes, SEEK_SET) == 0;
 }
-inline uint64_t fp_mix(uint64_t h, uint64_t x) {
+uint64_t fp_mix(uint64_t h, uint64_t x) {
   h ^= x + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
   h *= 0xFF51AFD7ED558CCDULL;
   return h ^ (h >> 32);
@@ -960,6 +1023,7 @@ bool HostModel::save_index(const std::string& path, std::string* err) const {
   h.max_key_bits = ix.max_key_bits;
   h.sd = ix.sd;
   h.table_keys = ix.table_keys;
+  h.checksum = content_checksum(ix);
   memcpy(h.charcount_mask, ix.charcount_mask, sizeof h.charcount_mask);
   memcpy(h.prime_of, ix.prime_of, sizeof h.prime_of);
   bool ok = fwrite(&h, sizeof h, 1, f) == 1;
@@ -996,6 +1060,14 @@ bool HostModel::load_index(const std::string& path, std::string* err) {
     return bad("index file was written by a library with a different data layout");
   if (h.fingerprint != vocabulary_fingerprint())
     return bad("index file was built from a different vocabulary or alphabet (fingerprint mismatch)");
+  // header fields the kernels size buffers and loops from
+  if (h.sd < 0 || h.sd > 1 || h.n_shards < 1 || h.shard >= h.n_shards || h.max_len == 0 || h.max_len > (uint32_t)ANL_MAX_SYMBOLS ||
+      h.max_charcount == 0 || h.max_charcount > h.max_len || h.max_key_bits == 0 || h.max_key_bits > 192 || h.norm_stride < 16 ||
+      h.norm_stride % 16 != 0 || h.max_len + 2 > h.norm_stride || h.norm_stride > 256)
+    return bad("index file is inconsistent (header fields out of range)");
+  if (alphabet.size() + 1 > 168) return bad("alphabet has more classes than there are primes (168)");
+  std::string verr;
+  if (!check_variant_support(h.n_shards, &verr)) return bad(verr);  // what build_index refuses, a file must not bypass
   ix.shard = h.shard;
   ix.n_shards = h.n_shards;
   ix.norm_stride = h.norm_stride;
@@ -1004,8 +1076,10 @@ bool HostModel::load_index(const std::string& path, std::string* err) {
   ix.max_key_bits = h.max_key_bits;
   ix.sd = h.sd;
   ix.table_keys = h.table_keys;
-  memcpy(ix.charcount_mask, h.charcount_mask, sizeof h.charcount_mask);
-  memcpy(ix.prime_of, h.prime_of, sizeof h.prime_of);
+  // derived tables are recomputed, not trusted: primes from the alphabet, the charcount mask from the anagrams below
+  const uint32_t n_classes = (uint32_t)alphabet.size() + 1;  // incl. UNK
+  for (uint32_t s = 0; s < n_classes; ++s) ix.prime_of[s] = kPrimes[s];
+  if (memcmp(ix.prime_of, h.prime_of, sizeof ix.prime_of) != 0) return bad("index file is inconsistent (prime table)");
   const bool read_ok = read_array(f, &ix.ana_key, file_bytes) && read_array(f, &ix.ana_inst_off, file_bytes) &&
                        read_array(f, &ix.ana_charcount, file_bytes) && read_array(f, &ix.inst_vocab, file_bytes) &&
                        read_array(f, &ix.inst_freq, file_bytes) && read_array(f, &ix.inst_gid, file_bytes) &&
@@ -1013,21 +1087,69 @@ bool HostModel::load_index(const std::string& path, std::string* err) {
                        read_array(f, &ix.bloom, file_bytes) && read_array(f, &ix.post_ana, file_bytes) &&
                        read_array(f, &ix.post_cls, file_bytes) && read_array(f, &ix.active_classes, file_bytes);
   if (!read_ok) return bad("truncated or corrupt index file");
-  // structural checks: everything the kernels index with must be in range
+  if (content_checksum(ix) != h.checksum) return bad("truncated or corrupt index file (content checksum mismatch)");
+  // structural checks: everything the kernels index with must be in range (a file with a valid checksum can still
+  // come from a buggy or hostile writer)
   const size_t ninst = ix.inst_vocab.size(), nana = ix.ana_key.size();
   auto pow2 = [](size_t n) { return n != 0 && (n & (n - 1)) == 0; };
   bool sane = nana > 0 && ninst >= nana && ix.ana_inst_off.size() == nana + 1 && ix.ana_charcount.size() == nana &&
-              ix.inst_freq.size() == ninst && (ix.inst_gid.empty() || ix.inst_gid.size() == ninst) && ix.norm_stride >= 16 &&
-              ix.norm_stride % 16 == 0 && ix.inst_rows.size() == ninst * (size_t)ix.norm_stride && pow2(ix.table.size()) &&
-              pow2(ix.bloom.size()) && ix.post_cls.size() == ix.post_ana.size() && ix.n_shards >= 1 && ix.shard < ix.n_shards &&
-              ix.ana_inst_off[0] == 0 && ix.ana_inst_off[nana] == ninst && ix.max_len + 2 <= ix.norm_stride;
-  for (size_t r = 0; sane && r < nana; ++r) sane = ix.ana_inst_off[r] < ix.ana_inst_off[r + 1];
-  for (size_t g = 0; sane && g < ninst; ++g)
-    sane = ix.inst_vocab[g] < decoder.size() && ix.inst_rows[g * ix.norm_stride] <= ix.max_len;
-  for (size_t t = 0; sane && t < ix.post_ana.size(); ++t) sane = ix.post_ana[t] < nana;
-  for (size_t i = 0; sane && i < ix.table.size(); ++i)
-    sane = (uint64_t)ix.table[i].post_off + ix.table[i].post_cnt <= ix.post_ana.size();
+              ix.inst_freq.size() == ninst && (ix.inst_gid.empty() == (ix.n_shards == 1)) &&
+              (ix.inst_gid.empty() || ix.inst_gid.size() == ninst) &&
+              ix.inst_rows.size() == ninst * (size_t)ix.norm_stride && pow2(ix.table.size()) &&
+              pow2(ix.bloom.size()) && ix.post_cls.size() == ix.post_ana.size() && ix.post_ana.size() < 0xFFFFFFF0ull &&
+              ix.ana_inst_off[0] == 0 && ix.ana_inst_off[nana] == ninst && !ix.active_classes.empty() &&
+              ix.active_classes.size() <= n_classes && ix.table_keys > 0 && ix.table_keys * 2 <= ix.table.size();
   if (!sane) return bad("index file is inconsistent");
+  std::atomic<bool> ok{true};
+  auto check = [&](uint64_t n, auto pred) {  // pred(i) for i in [0, n) on all cores
+    parallel_ranges(n, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
+      bool good = true;
+      for (uint64_t i = lo; i < hi && good; ++i) good = pred(i);
+      if (!good) ok = false;
+    });
+    return ok.load();
+  };
+  // active classes: ascending symbols of the alphabet
+  for (size_t i = 0; i < ix.active_classes.size(); ++i)
+    if (ix.active_classes[i] >= n_classes || (i && ix.active_classes[i] <= ix.active_classes[i - 1])) ok = false;
+  bool is_active[256] = {false};
+  for (uint8_t c : ix.active_classes) is_active[c] = true;
+  // anagrams: keys strictly ascending (has() binary-searches them), CSR offsets strictly ascending, charcounts in range
+  ok = ok && check(nana, [&](uint64_t r) {
+    return ix.ana_inst_off[r] < ix.ana_inst_off[r + 1] && ix.ana_inst_off[r + 1] <= ninst &&
+           (r == 0 || key_less(ix.ana_key[r - 1], ix.ana_key[r])) && ix.ana_charcount[r] >= 1 &&
+           ix.ana_charcount[r] <= ix.max_charcount && key_bits(ix.ana_key[r]) <= ix.max_key_bits;
+  });
+  // instances: vocabulary ids, row lengths and symbols; a shard's global gather ids ascend
+  ok = ok && check(ninst, [&](uint64_t g) {
+    const uint8_t* row = ix.inst_rows.data() + g * ix.norm_stride;
+    if (ix.inst_vocab[g] >= decoder.size() || row[0] == 0 || row[0] > ix.max_len || (row[1] & ~ROW_FIRST_LOWER)) return false;
+    for (uint32_t i = 0; i < row[0]; ++i)
+      if (!is_active[row[2 + i]]) return false;
+    return ix.inst_gid.empty() || g == 0 || ix.inst_gid[g - 1] < ix.inst_gid[g];
+  });
+  // every row of an anagram has that anagram's length
+  ok = ok && check(nana, [&](uint64_t r) {
+    for (uint32_t g = ix.ana_inst_off[r]; g < ix.ana_inst_off[r + 1]; ++g)
+      if (ix.inst_rows[(size_t)g * ix.norm_stride] != ix.ana_charcount[r]) return false;
+    return true;
+  });
+  // postings: anagram rank and class in range
+  ok = ok && check(ix.post_ana.size(), [&](uint64_t t) {
+    return ix.post_ana[t] < nana && (ix.post_cls[t] == POST_SELF || (ix.sd == 1 && is_active[ix.post_cls[t]]));
+  });
+  // table: posting ranges in range, occupancy as declared (a full table would make the linear probe spin forever)
+  std::atomic<uint64_t> occupied{0};
+  ok = ok && check(ix.table.size(), [&](uint64_t i) {
+    const Slot& sl = ix.table[i];
+    if (sl.post_cnt == 0) return true;
+    occupied.fetch_add(1, std::memory_order_relaxed);
+    return (uint64_t)sl.post_off + sl.post_cnt <= ix.post_ana.size();
+  });
+  if (!ok || occupied.load() != ix.table_keys) return bad("index file is inconsistent");
+  for (uint16_t cc : ix.ana_charcount) ix.charcount_mask[cc >> 6] |= 1ull << (cc & 63);
+  if (memcmp(ix.charcount_mask, h.charcount_mask, sizeof ix.charcount_mask) != 0)
+    return bad("index file is inconsistent (charcount mask)");
   fclose(f);
   index = std::move(ix);
   built = true;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "device_types.h"
+#include "hostpool.h"
 
 namespace anl {
 
@@ -93,12 +94,12 @@ struct HostIndex {
   std::vector<uint32_t> inst_freq;
   std::vector<uint32_t> inst_gid;    // lexicon-sharded index: global gather id per local one (empty = identity)
   uint32_t shard = 0, n_shards = 1;
-  std::vector<uint8_t> inst_rows;
+  RawVec<uint8_t> inst_rows;         // (RawVec: sized without a fill, then first-touched on all cores)
   uint32_t norm_stride = 0;
-  std::vector<Slot> table;
-  std::vector<uint64_t> bloom;
-  std::vector<uint32_t> post_ana;
-  std::vector<uint8_t> post_cls;
+  RawVec<Slot> table;
+  RawVec<uint64_t> bloom;
+  RawVec<uint32_t> post_ana;
+  RawVec<uint8_t> post_cls;
   std::vector<uint8_t> active_classes;  // symbols that occur in indexed entries, ascending
   std::vector<MsetEntry> mset;
   uint32_t mset_end[ANL_MAX_K + 1] = {0};
@@ -134,6 +135,8 @@ class HostModel {
   // pins the library's struct layout and a fingerprint of the vocabulary the index was built from.  load_index
   // replaces build_index (same arrays, bit for bit) for a model that holds the same vocabulary in the same order.
   uint64_t vocabulary_fingerprint() const;
+  // what build_index refuses about variant lists (also re-checked by load_index)
+  bool check_variant_support(uint32_t n_shards, std::string* err) const;
   bool save_index(const std::string& path, std::string* err) const;
   bool load_index(const std::string& path, std::string* err);
 

@@ -8,10 +8,13 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <functional>
 #include <mutex>
+#include <memory>
 #include <new>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace anl {
@@ -20,6 +23,30 @@ namespace anl {
 // a fresh mmap per call costs tens of ms of page faults, a recycled block is already mapped).
 void* big_block_take(size_t min_bytes, size_t* got_bytes);  // nullptr if nothing suitable is parked
 void big_block_give(void* p, size_t bytes);                 // parks or frees
+
+// std::vector whose resize() default-initialises (leaves PODs untouched) instead of zero-filling: the large index
+// arrays are sized first and then first-touched / zeroed on all cores (a plain vector would memset them on one
+// thread, and writing through data() beyond size() of a reserved vector is undefined behaviour).
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  DefaultInitAlloc() = default;
+  template <class U>
+  DefaultInitAlloc(const DefaultInitAlloc<U>&) noexcept {}
+  template <class U>
+  void construct(U* p) noexcept(noexcept(::new ((void*)p) U)) {
+    ::new ((void*)p) U;
+  }
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T>
+using RawVec = std::vector<T, DefaultInitAlloc<T>>;
 
 // Growable array of PODs that does not value-initialise on resize (a std::vector would memset
 // hundreds of MB that are overwritten immediately, on one thread).
@@ -102,33 +129,54 @@ class HostPool {
     static HostPool* p = new HostPool();  // leaked on purpose: workers outlive static destruction
     return *p;
   }
-  // runs fn(part) for part in [0, parts); the caller executes part 0
+  // runs fn(part) for part in [0, parts); the caller executes part 0.  An exception thrown by any part (std::bad_alloc
+  // from a per-thread vector is the realistic one) is caught where it is thrown, the remaining parts still run to
+  // completion, and the first exception is rethrown on the calling thread after the join -- so it reaches the
+  // function-try-blocks of capi.cpp instead of std::terminate on a worker.
   template <class F>
   void run(unsigned parts, F& fn) {
     if (parts <= 1) {
       fn(0u);
       return;
     }
+    std::exception_ptr first_error;
+    std::mutex error_m;
+    auto guarded = [&fn, &first_error, &error_m](unsigned t) noexcept {
+      try {
+        fn(t);
+      } catch (...) {
+        std::lock_guard<std::mutex> lk(error_m);
+        if (!first_error) first_error = std::current_exception();
+      }
+    };
     std::unique_lock<std::mutex> busy(run_m_, std::try_to_lock);
     if (!busy.owns_lock() || parts - 1 > workers_.size()) {
       std::vector<std::thread> th;
-      for (unsigned t = 1; t < parts; ++t) th.emplace_back([&fn, t]() { fn(t); });
-      fn(0u);
+      try {
+        for (unsigned t = 1; t < parts; ++t) th.emplace_back([&guarded, t]() { guarded(t); });
+      } catch (...) {  // thread creation failed: run the parts that got no thread here
+        for (unsigned t = 1 + (unsigned)th.size(); t < parts; ++t) guarded(t);
+      }
+      guarded(0u);
       for (auto& t : th) t.join();
+      if (first_error) std::rethrow_exception(first_error);
       return;
     }
     {
       std::lock_guard<std::mutex> lk(m_);
-      job_ = [&fn](unsigned t) { fn(t); };
+      job_ = [&guarded](unsigned t) { guarded(t); };
       parts_ = parts;
       pending_ = parts - 1;
       ++gen_;
     }
     cv_.notify_all();
-    fn(0u);
-    std::unique_lock<std::mutex> lk(m_);
-    done_.wait(lk, [this]() { return pending_ == 0; });
-    job_ = nullptr;
+    guarded(0u);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      done_.wait(lk, [this]() { return pending_ == 0; });
+      job_ = nullptr;
+    }
+    if (first_error) std::rethrow_exception(first_error);
   }
 
  private:

@@ -29,11 +29,16 @@ static inline uint32_t decode_at(const std::string& s, size_t i, unsigned* len) 
 // src/search.rs:190-235: a boundary is a maximal run of non-alphabetic characters; the text always
 // ends with a boundary (possibly of length zero).  The scan runs in parallel over byte ranges; a run
 // that crosses a range border is stitched back together afterwards.
-// (Scratch vectors are thread_local: the pool's workers are persistent, so after the first call their
-// capacity is already mapped and a 100 M-token stream does not page-fault hundreds of MB per call.)
+// (The per-part scratch vectors belong to the CALLING thread (thread_local arena indexed by part): after the
+// first call their capacity is already mapped, so a 100 M-token stream does not page-fault hundreds of MB per
+// call, and they outlive whichever thread ran the part -- when the pool is busy the parts run on short-lived
+// threads whose own thread_locals are gone by the time the results are read.)
 const std::vector<Boundary>& find_boundaries(const std::string& text) {
   const size_t n = text.size();
   const unsigned nt_max = host_threads();
+  static thread_local std::vector<std::vector<Boundary>> arena_tl;
+  std::vector<std::vector<Boundary>>& arena = arena_tl;  // (a lambda naming a thread_local would see the executing thread's)
+  if (arena.size() < nt_max) arena.resize(nt_max);
   std::vector<std::vector<Boundary>*> part(nt_max, nullptr);
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
   const unsigned used = parallel_ranges(n, 1u << 16, [&](unsigned t, uint64_t lo, uint64_t hi) {
@@ -41,10 +46,9 @@ const std::vector<Boundary>& find_boundaries(const std::string& text) {
     while (lo < n && lo > 0 && ((unsigned char)text[lo] & 0xC0) == 0x80) ++lo;
     while (hi < n && ((unsigned char)text[hi] & 0xC0) == 0x80) ++hi;
     range[t] = {lo, hi};
-    static thread_local std::vector<Boundary> scratch;
-    scratch.clear();
-    part[t] = &scratch;
-    std::vector<Boundary>& out = scratch;
+    std::vector<Boundary>& out = arena[t];
+    out.clear();
+    part[t] = &out;
     out.reserve((size_t)(hi - lo) / 5 + 16);
     bool open = false;
     size_t start = 0;
@@ -144,16 +148,18 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
   list_batches(bounds, &descs);
   const size_t nb = descs.size();
   const unsigned nt_max = host_threads();
+  static thread_local std::vector<std::vector<SegmentSpan>> arena_tl;  // per-part scratch owned by the calling thread
+  std::vector<std::vector<SegmentSpan>>& arena = arena_tl;
+  if (arena.size() < nt_max) arena.resize(nt_max);
   std::vector<std::vector<SegmentSpan>*> part(nt_max, nullptr);
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
   st.batch_first.resize(nb + 1);  // segments per batch first, then the exclusive prefix
   uint64_t* count = st.batch_first.data() + 1;
   const unsigned used = parallel_ranges(nb, 256, [&](unsigned t, uint64_t lo, uint64_t hi) {
     range[t] = {lo, hi};
-    static thread_local std::vector<SegmentSpan> scratch;
-    scratch.clear();
-    part[t] = &scratch;
-    std::vector<SegmentSpan>& out = scratch;
+    std::vector<SegmentSpan>& out = arena[t];
+    out.clear();
+    part[t] = &out;
     if (hi > lo) out.reserve((descs[hi - 1].end_index - descs[lo].begin_index + 1) * (size_t)max_ngram + 16);
     for (uint64_t k = lo; k < hi; ++k) {
       const BatchDesc& d = descs[k];

@@ -85,6 +85,66 @@ def test_index_file_is_validated(tmp_path):
         fresh().load_index(str(tmp_path / "flipped.idx"))
 
 
+def test_tampered_index_files_are_refused(tmp_path):
+    """Bit rot or a hostile writer must give an error, never a silently wrong (or spinning) lookup: header fields
+    the kernels size loops and shared arrays from are range-checked, derived tables (primes, charcount mask) are
+    recomputed instead of trusted, and every array byte is covered by the content checksum in the header."""
+    import struct
+    import analiticcl_b200 as A
+    a = model(A, "eng")
+    host_build(a)
+    good = str(tmp_path / "eng.idx")
+    a.save_index(good)
+    raw = open(good, "rb").read()
+    # header layout: magic 8 | header_bytes, slot_bytes, key_bytes, max_k | fingerprint 8 | shard, n_shards, norm_stride,
+    # max_charcount, max_len, max_key_bits | sd | reserved | table_keys 8 | checksum 8 | charcount_mask 32 | prime_of 1024
+    OFF = dict(shard=32, n_shards=36, norm_stride=40, max_charcount=44, max_len=48, max_key_bits=52, sd=56, table_keys=64,
+               checksum=72, charcount_mask=80, prime_of=112, arrays=112 + 1024)
+    assert struct.unpack_from("<i", raw, OFF["sd"])[0] == 1 and struct.unpack_from("<I", raw, OFF["max_len"])[0] == 24
+    assert struct.unpack_from("<I", raw, OFF["prime_of"])[0] == 2 and struct.unpack_from("<I", raw, OFF["prime_of"] + 4)[0] == 3
+
+    def patched(off, data):
+        b = bytearray(raw)
+        b[off:off + len(data)] = data
+        return bytes(b)
+    first_keys = OFF["arrays"] + 16  # ana_key array: count, element size, then the keys
+    cases = {
+        "sd7": patched(OFF["sd"], struct.pack("<i", 7)),
+        "maxcc": patched(OFF["max_charcount"], struct.pack("<I", 100000)),
+        "maxlen": patched(OFF["max_len"], struct.pack("<I", 250)),
+        "stride": patched(OFF["norm_stride"], struct.pack("<I", 4096)),
+        "shard": patched(OFF["n_shards"], struct.pack("<I", 0)),
+        "primes": patched(OFF["prime_of"], b"\0" * 1024),
+        "ccmask": patched(OFF["charcount_mask"], struct.pack("<Q", 0xFFFF)),
+        "tablekeys": patched(OFF["table_keys"], struct.pack("<Q", 1)),
+        "garbage_keys": patched(first_keys, os.urandom(100 * 24)),
+        "one_bit": patched(len(raw) - 4096, bytes([raw[len(raw) - 4096] ^ 0x10])),
+        "checksum": patched(OFF["checksum"], struct.pack("<Q", 12345)),
+    }
+    for name, content in cases.items():
+        path = str(tmp_path / (name + ".idx"))
+        open(path, "wb").write(content)
+        m = model(A, "eng")
+        with pytest.raises(RuntimeError, match="inconsistent|corrupt"):
+            m.load_index(path)
+        assert m.index_size() == 0, name
+
+
+def test_frequency_change_invalidates_the_built_index():
+    """The device holds its own copy of the frequencies; the reference reads decoder[].frequency live
+    (src/lib.rs:1456).  Changing an indexed entry's frequency after build() must not leave a stale index in use."""
+    import analiticcl_b200 as A
+    m = model(A, "eng")
+    host_build(m)
+    assert m.index_size() == 108802
+    m.add_to_vocabulary("separate", 1, A.VocabParams())      # Max(1, 1): nothing changes, the index stays valid
+    assert m.index_size() == 108802
+    m.add_to_vocabulary("separate", 500, A.VocabParams())    # frequency 1 -> 500
+    assert m.index_size() == 0
+    with pytest.raises(RuntimeError, match="not been built"):
+        m.find_variants("seperate", A.SearchParameters())
+
+
 def test_sharded_index_round_trip(tmp_path):
     """A lexicon shard (its own anagram subset + the global gather ids) survives the file as well, and a shard's
     file is not mistaken for another shard's: the shard coordinates are part of the file."""

@@ -98,3 +98,41 @@ def test_alphabetic_is_the_derived_property(L):
     got = boundaries(L, t)
     assert got == [(b, e, s) for b, e, _, s in orc.find_boundaries(t)]
     assert [raw[b:e].decode() for b, e, _ in got] == [" ", ", ", ""]
+
+
+def test_concurrent_callers_on_large_texts():
+    """Several host threads inside the producer at once (ctypes releases the GIL; the reference's find_all_matches is
+    &self and thread-safe): while one caller holds the worker pool the others run their parts on short-lived
+    threads, whose thread_locals are gone when the parts' results are read -- the per-part scratch must belong to
+    the caller.  Runs in a child process with 8 host threads so a crash cannot take the test session down."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, threading, ctypes as C\n"
+        "sys.path.insert(0, %r)\n"
+        "import workloads\n"
+        "from analiticcl_b200 import _capi\n"
+        "L = _capi.lib()\n"
+        "raw = workloads.cfg3_text(330000, 17).encode('utf-8')\n"
+        "assert len(raw) > 2_000_000\n"
+        "cap = 3 * (len(raw) // 4)\n"
+        "res = [None] * 4\n"
+        "def work(i):\n"
+        "    b, e = (C.c_uint64 * cap)(), (C.c_uint64 * cap)()\n"
+        "    o, bt = (C.c_uint32 * cap)(), (C.c_uint32 * cap)()\n"
+        "    out = []\n"
+        "    for _ in range(3):\n"
+        "        n = L.anl_debug_segment_text(raw, len(raw), 3, b, e, o, bt, cap)\n"
+        "        out.append((n, sum(b[k] for k in range(0, min(n, cap), 997)), sum(e[k] for k in range(0, min(n, cap), 991))))\n"
+        "    res[i] = out\n"
+        "th = [threading.Thread(target=work, args=(i,)) for i in range(4)]\n"
+        "[t.start() for t in th]; [t.join() for t in th]\n"
+        "assert all(r is not None and len(set(r)) == 1 for r in res), res\n"
+        "assert len({r[0] for r in res}) == 1, res\n"
+        "print('ok', res[0][0][0])\n") % root
+    env = dict(os.environ, ANL_HOST_THREADS="8")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.returncode, p.stderr[-2000:])
+    assert p.stdout.startswith("ok")
