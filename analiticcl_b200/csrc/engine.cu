@@ -642,14 +642,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
         row[1] = flags;
       }
     });
-    for (uint64_t i = 0; i < n; ++i) {
-      if (b->host_flags[i] == 2) {
-        *err = "query " + std::to_string(i) + " is longer than " + std::to_string(ANL_MAX_SYMBOLS) + " symbols";
-        *status = ANL_ERR_UNSUPPORTED;
-        free_batch(b);
-        return nullptr;
-      }
-    }
+    // (host_flags == 2: outside the supported range -- that query alone gets an empty list and flag bit 1)
   }
   pt.lap("create: encode");
   // raw query bytes for the device-side confusable stage (only when a confusable post-pass follows)
@@ -1140,9 +1133,9 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
   std::vector<uint32_t> flags_all((size_t)n * n_shards);
   if (n) CU_TRY(cudaMemcpy(flags_all.data(), d_flags_all, flags_all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < flags_all.size(); ++i) {
-    if (flags_all[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
+    if ((flags_all[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) {
       *err = "query " + std::to_string(i % std::max<uint32_t>(n, 1)) +
-             " exceeds the per-query candidate capacity (or the supported distance) on a shard; raise ANL_HIT_CAP";
+             " exceeds the per-query candidate capacity on a shard; raise ANL_HIT_CAP";
       *status = ANL_ERR_UNSUPPORTED;
       return false;
     }
@@ -1212,16 +1205,10 @@ bool Engine::fetch_begin(DeviceBatch* b, std::string* err, int* status) {
   b->rr_index.clear();
   b->rr_heads.clear();
   b->rr_recs.clear();
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t f = b->h_flags[i];
-    if (f & QF_UNSUPPORTED) {
-      *err = "query " + std::to_string(i) + ": max_anagram_distance after thresholding exceeds " +
-             std::to_string(ANL_MAX_K) + " (or its deletion neighbourhood is too large) -- unsupported by the GPU path";
-      *status = ANL_ERR_UNSUPPORTED;
-      return false;
-    }
-    if (f & QF_HIT_OVERFLOW) b->rr_which.push_back(i);
-  }
+  // (QF_UNSUPPORTED -- thresholded anagram distance above ANL_MAX_K, deletion neighbourhood beyond 2^31 -- is a
+  // property of that query alone: it comes back with an empty list and flag bit 1, the batch goes on)
+  for (uint32_t i = 0; i < n; ++i)
+    if ((b->h_flags[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) b->rr_which.push_back(i);
   if (!b->rr_which.empty()) {
     if (profile_enabled()) fprintf(stderr, "[anl profile] %zu queries overflowed hit_cap=%u\n", b->rr_which.size(), b->bp.hit_cap);
     if (!rerun_launch(b, err, status)) return false;
@@ -1276,8 +1263,10 @@ bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::strin
   out->offsets.resize(qbase + (size_t)n + 1);
   out->flags.resize(qbase + n, 0);
   uint64_t* offs = out->offsets.data() + qbase;
-  for (uint32_t i = 0; i < n; ++i)
-    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[qbase + i] |= 1;
+  for (uint32_t i = 0; i < n; ++i) {
+    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[qbase + i] |= ANL_QUERY_EMPTY;
+    if ((b->h_flags[i] & QF_UNSUPPORTED) || b->host_flags[i] == 2) out->flags[qbase + i] |= ANL_QUERY_UNSUPPORTED;
+  }
 
   // pass 1: queries the host must finish go through finish_query into per-thread side buffers; the
   // counts of all other queries are final as they come from the device

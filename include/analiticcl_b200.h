@@ -191,8 +191,15 @@ int32_t anl_confusable_found_in(const char* pattern, const char* src, size_t src
 /* find_variants over a batch (== find_variants_par, bindings/python/src/lib.rs:720).
  * `blob` holds the UTF-8 queries back to back, query i = blob[offsets[i] .. offsets[i+1]).
  * Results are final: ranked, cropped, confusable-rescored, cut off -- identical to what
- * VariantModel::find_variants returns for each query.  An empty query yields an empty list and
- * sets bit 0 of its flags (the reference panics on it). */
+ * VariantModel::find_variants returns for each query.  Failures are per query, never per batch (the reference
+ * answers every query on its own, src/lib.rs:972-1027): a query the path cannot answer yields an empty list and
+ * a flag bit in anl_result_set_flags():
+ *   ANL_QUERY_EMPTY        empty query (the reference panics on it, src/lib.rs:1420)
+ *   ANL_QUERY_UNSUPPORTED  outside the limits of the GPU path (DESIGN.md "Limits"): longer than 236 symbols while
+ *                          an indexed entry could still be within reach, thresholded anagram distance above 6, or
+ *                          a deletion neighbourhood beyond 2^31 nodes.  (A query longer than the longest indexed
+ *                          entry + max_anagram_distance has an empty result by construction: no flag.) */
+enum { ANL_QUERY_EMPTY = 1, ANL_QUERY_UNSUPPORTED = 2 };
 anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
                                    const anl_search_params* params, anl_result_set** out);
 uint64_t anl_result_set_len(const anl_result_set* rs);

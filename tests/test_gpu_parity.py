@@ -308,6 +308,32 @@ def test_python_binding_test(A):
         assert r["input"] == orig and r["variants"][0]["text"] == term and r["variants"][0]["lexicons"] == [lexicon]
 
 
+def test_python_binding_test_under_its_own_module_name(tmp_path, monkeypatch):
+    """The same test with the reference's import line (`from analiticcl import VariantModel, Weights,
+    SearchParameters`, bindings/python/tests/tests.py:3) and its relative paths, run from a directory laid out like
+    bindings/python/ (tests/*.tsv next to it, ../../examples/simple.alphabet.tsv above)."""
+    import shutil
+    from analiticcl import VariantModel, Weights, SearchParameters
+    py = tmp_path / "bindings" / "python"
+    (py / "tests").mkdir(parents=True)
+    (tmp_path / "examples").mkdir()
+    shutil.copy(workloads.AMPHIBIANS, py / "tests" / "amphibians.tsv")
+    shutil.copy(workloads.REPTILES, py / "tests" / "reptiles.tsv")
+    shutil.copy(workloads.ALPHABET, tmp_path / "examples" / "simple.alphabet.tsv")
+    monkeypatch.chdir(py)
+    model = VariantModel("../../examples/simple.alphabet.tsv", Weights(), debug=False)
+    model.read_lexicon("tests/amphibians.tsv")
+    model.read_lexicon("tests/reptiles.tsv")
+    model.build()
+    results = model.find_all_matches("Salamander lizard frog snake toad", SearchParameters(max_edit_distance=3, max_ngram=1))
+    assert len(results) == 5
+    for r, (orig, lexicon, term) in zip(results, [("Salamander", "tests/amphibians.tsv", "salamander"),
+                                                  ("lizard", "tests/reptiles.tsv", "lizard"), ("frog", "tests/amphibians.tsv", "frog"),
+                                                  ("snake", "tests/reptiles.tsv", "snake"), ("toad", "tests/amphibians.tsv", "toad")]):
+        assert r["input"] == orig and len(r["variants"]) > 0
+        assert r["variants"][0]["text"] == term and r["variants"][0]["lexicons"] == [lexicon]
+
+
 def test_weights_variants(A):
     """Features with weight <= 0 are skipped (src/lib.rs:1352-1377); non-default weights stay bit-exact."""
     words = workloads.read_words("eng")[:30000]
