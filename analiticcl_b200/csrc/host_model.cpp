@@ -814,7 +814,9 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   // A filter that outgrows the 126 MB L2 turns every probe into a DRAM sector read.  Large indexes trade
   // false positives (a wasted exact lookup each) for residency: up to ~8 keys per word (false positives
   // ~2-3 %) while the filter is larger than 128 MB.
-  while (words * 8 > (128ull << 20) && words * 8 >= groups) words >>= 1;
+  uint64_t bloom_max_bytes = 128ull << 20;
+  if (const char* e = getenv("ANL_BLOOM_MAX_MB")) bloom_max_bytes = (uint64_t)std::max(1, atoi(e)) << 20;  // (tests: the dense branch on a small lexicon)
+  while (words * 8 > bloom_max_bytes && words * 8 >= groups) words >>= 1;
   // the table is written at random: ask for huge pages before the first touch (a 4 KB page per TLB entry makes
   // every insertion a page walk once the table is hundreds of MB; harmless where THP is unavailable)
   pt.lap("build: count keys");

@@ -28,19 +28,22 @@ def cfg5():
     return lexicon, qs, exp
 
 
-def test_cfg5_dense_bloom_parity(cfg5):
+def test_cfg5_dense_bloom_parity(cfg5, monkeypatch):
     import analiticcl_b200 as A
     from test_gpu_parity import assert_same
     lexicon, qs, exp = cfg5
+    # The 10 M-entry lexicon of the bench caps its filter at 128 MB (~6.6 keys per 64-bit word); the same density on
+    # the 2 M-entry instance needs the cap lowered: 32 MB -> ~5.7 keys per word, percent-level false positives.
+    monkeypatch.setenv("ANL_BLOOM_MAX_MB", "32")
     m = A.VariantModel(workloads.ALPHABET, A.Weights())
     m.read_lexicon(lexicon)
     m.build()
     st = m.index_stats()
     assert st["instances"] > 1_990_000 and st["sd"] == 1
-    # the dense-Bloom branch of the index build: more than two keys per 64-bit filter word, table far beyond the L2
+    # the dense-Bloom branch of the index build: several keys per 64-bit filter word, table far beyond the L2
     keys_per_word = st["table_keys"] / (st["bloom_bytes"] / 8)
-    assert keys_per_word > 2.0, keys_per_word
-    assert st["table_bytes"] >= 512 << 20 and st["bloom_bytes"] <= 128 << 20
+    assert keys_per_word > 4.0, keys_per_word
+    assert st["table_bytes"] >= 512 << 20 and st["bloom_bytes"] <= 32 << 20
     for tag, (kw, want) in exp.items():
         got = m.find_variants_raw(qs, A.SearchParameters(**kw))
         assert_same(got, want, qs, "cfg5 " + tag)
