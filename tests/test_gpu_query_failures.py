@@ -57,21 +57,6 @@ def test_over_budget_queries_inside_a_10k_batch(eng_oracle):
     assert_same([got[i] for i in sample], exp, [qs[i] for i in sample], "batch with over-budget queries")
 
 
-def test_over_long_query_next_to_a_long_entry():
-    """A query longer than the 236 symbols a device row holds, while an indexed entry is still within reach: flagged
-    (with the eng lexicon the same query is simply empty: nothing that long is indexed)."""
-    import analiticcl_b200 as A
-    m = A.VariantModel(workloads.ALPHABET, A.Weights())
-    m.add_to_vocabulary("ab" * 118, 1, A.VocabParams())  # 236 symbols
-    for w in ("separate", "operate", "desperate"):
-        m.add_to_vocabulary(w, 1, A.VocabParams())
-    m.build()
-    sp = A.SearchParameters()
-    got, flags = run_with_flags(m, A, ["seperate", "ab" * 118 + "a", "ab" * 119, "x" * 300, "operate"], sp)
-    assert [len(g) > 0 for g in got] == [True, False, False, False, True]
-    assert flags == [0, QUERY_UNSUPPORTED, QUERY_UNSUPPORTED, 0, 0]
-
-
 def test_over_budget_token_inside_a_text(eng_oracle):
     import analiticcl_b200 as A
     m = A.VariantModel(workloads.ALPHABET, A.Weights())
