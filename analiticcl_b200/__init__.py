@@ -272,9 +272,18 @@ class VariantModel:
     def add_contextrule(self, pattern, score, tag, tagoffset):
         raise NotImplementedError("context rules are outside the variant-lookup hot path (see DESIGN.md)")
 
-    def build(self, device=-1):
-        """Build the anagram index and upload it to the GPU (`device` = CUDA ordinal, -1 = current)."""
-        _check(_lib().anl_model_build(self._h, int(device)))
+    def build(self, device=-1, devices=None):
+        """Build the anagram index and upload it to the GPU (`device` = CUDA ordinal, -1 = current).  With
+        `devices=[0, 1, ...]` every listed GPU of this process gets a replica and each lookup call is spread over
+        all of them (anl_model_build_multi)."""
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            _check(_lib().anl_model_build_multi(self._h, arr, len(devices)))
+        else:
+            _check(_lib().anl_model_build(self._h, int(device)))
+
+    def device_count(self):
+        return _lib().anl_model_device_count(self._h)
 
     def save_index(self, filename):
         """Write the built index to `filename` (not in the reference: its build takes seconds; see the C header)."""

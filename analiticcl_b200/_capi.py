@@ -89,6 +89,8 @@ SIGNATURES = {
     "anl_model_add_to_confusables": (_i32, [_vp, _cp, C.c_double]),
     "anl_model_set_confusables_before_pruning": (None, [_vp]),
     "anl_model_build": (_i32, [_vp, _i32]),
+    "anl_model_build_multi": (_i32, [_vp, _P(C.c_int32), _u32]),
+    "anl_model_device_count": (_u32, [_vp]),
     "anl_model_has": (_i32, [_vp, _cp, _sz]),
     "anl_model_vocab_id": (_i64, [_vp, _cp, _sz]),
     "anl_model_vocab_size": (_u64, [_vp]),

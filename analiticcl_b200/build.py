@@ -12,13 +12,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libanaliticcl_b200.so")
-SOURCES = ["kernels.cu", "engine.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "capi.cpp"]
-HEADERS = ["device_types.h", "editscript_fixed.h", "kernels.h", "engine.h", "host_model.h", "hostpool.h", "search.h", "unicode_tables.h",
+SOURCES = ["kernels.cu", "export.cu", "engine.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "capi.cpp"]
+HEADERS = ["device_types.h", "editscript_fixed.h", "kernel_common.cuh", "kernels.h", "engine.h", "host_model.h", "hostpool.h", "search.h", "unicode_tables.h",
            os.path.join("..", "..", "include", "analiticcl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-ccbin", "/usr/bin/g++",
-         "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function,-pthread",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function,-Wno-attributes,-pthread",
          "--cudart", "static"]
 
 

@@ -17,8 +17,23 @@ using namespace anl;
 
 struct anl_model {
   HostModel host;
-  Engine engine;
-  anl_model(const Weights& w, int debug) : host(w, debug), engine(&host) {}
+  // one Engine per device that holds a replica of the index (anl_model_build: one; anl_model_build_multi: several)
+  std::vector<std::unique_ptr<Engine>> engines;
+  Engine& engine;  // engines[0]: the device-batch API and the sharded mode work on the first device
+  anl_model(const Weights& w, int debug) : host(w, debug), engines(make_first(&host)), engine(*engines[0]) {}
+  std::vector<Engine*> replicas() const {
+    std::vector<Engine*> v;
+    for (const auto& e : engines)
+      if (e->uploaded()) v.push_back(e.get());
+    return v;
+  }
+
+ private:
+  static std::vector<std::unique_ptr<Engine>> make_first(HostModel* h) {
+    std::vector<std::unique_ptr<Engine>> v;
+    v.emplace_back(new Engine(h));
+    return v;
+  }
 };
 struct anl_result_set {
   ResultSet rs;
@@ -205,17 +220,40 @@ void anl_model_set_confusables_before_pruning(anl_model* m) {
   if (m) m->host.confusables_before_pruning = true;
 }
 
+// device side of build / load_index: one replica of the host index per listed device
+static anl_status upload_replicas(anl_model* m, const int32_t* devices, uint32_t n_devices) {
+  std::string err;
+  while (m->engines.size() > std::max<uint32_t>(n_devices, 1)) m->engines.pop_back();
+  while (m->engines.size() < n_devices) m->engines.emplace_back(new Engine(&m->host));
+  for (uint32_t i = 0; i < std::max<uint32_t>(n_devices, 1); ++i)
+    if (!m->engines[i]->upload(devices ? devices[i] : -1, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+}
 anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards) try {
   if (!m) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int sd = 1;
   if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
   if (!m->host.build_index(sd, shard, n_shards, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
-  if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
-  return ANL_OK;
+  return upload_replicas(m, &device, 1);
 } catch (...) {
   return on_exception();
 }
+anl_status anl_model_build_multi(anl_model* m, const int32_t* devices, uint32_t n_devices) try {
+  if (!m || (!devices && n_devices > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  if (n_devices == 0 || n_devices > 64) return fail(ANL_ERR_INVALID, "anl_model_build_multi: between 1 and 64 devices");
+  for (uint32_t i = 0; i < n_devices; ++i)
+    for (uint32_t j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(ANL_ERR_INVALID, "anl_model_build_multi: a device is listed twice");
+  std::string err;
+  int sd = 1;
+  if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
+  if (!m->host.build_index(sd, 0, 1, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  return upload_replicas(m, devices, n_devices);
+} catch (...) {
+  return on_exception();
+}
+uint32_t anl_model_device_count(const anl_model* m) { return m ? (uint32_t)m->replicas().size() : 0; }
 anl_status anl_model_save_index(const anl_model* m, const char* filename) try {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before save_index()");
@@ -229,8 +267,7 @@ anl_status anl_model_load_index(anl_model* m, const char* filename, int32_t devi
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   if (!m->host.load_index(filename, &err)) return fail(ANL_ERR_IO, err);
-  if (!m->engine.upload(device, &err)) return fail(ANL_ERR_CUDA, err);
-  return ANL_OK;
+  return upload_replicas(m, &device, 1);
 } catch (...) {
   return on_exception();
 }
@@ -356,7 +393,7 @@ anl_status anl_find_variants_batch(anl_model* m, const char* blob, const uint64_
   std::unique_ptr<anl_result_set> rs(new anl_result_set());
   std::string err;
   int status = ANL_OK;
-  if (!m->engine.find_variants_batch(blob ? blob : "", offsets, n_queries, *params, &rs->rs, &err, &status))
+  if (!find_variants_batch_multi(m->replicas(), blob ? blob : "", offsets, n_queries, *params, &rs->rs, &err, &status))
     return fail(status ? status : ANL_ERR_CUDA, err);
   *out = rs.release();
   return ANL_OK;
@@ -527,7 +564,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
     parallel_ranges(nu, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; ++i) memcpy(&blob[offs[i]], t.data() + st.segs[pick[uniq[i]]].begin, offs[i + 1] - offs[i]);
     });
-    if (!m->engine.find_variants_batch(blob.data(), offs.data(), nu, *params, &rs[pass], &err, &status)) return false;
+    if (!find_variants_batch_multi(m->replicas(), blob.data(), offs.data(), nu, *params, &rs[pass], &err, &status)) return false;
     parallel_ranges(np, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; ++i) {
         const uint64_t k = pick[i];
@@ -841,11 +878,11 @@ anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream)
 anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms) try {
   if (!m || !b || !probe_ms || !score_ms) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
-  float st[6];
+  float st[7];
   if (!m->engine.timings(b->b, st, &err)) return fail(ANL_ERR_CUDA, err);
   *probe_ms = st[0] + st[1];
   *score_ms = st[2] + st[3];
-  if (rescore_ms) *rescore_ms = st[4] + st[5];
+  if (rescore_ms) *rescore_ms = st[4] + st[5] + st[6];
   return ANL_OK;
 } catch (...) {
   return on_exception();
@@ -863,7 +900,7 @@ anl_status anl_device_batch_fetch(anl_model* m, anl_device_batch* b, anl_result_
   std::unique_ptr<anl_result_set> rs(new anl_result_set());
   std::string err;
   int status = ANL_OK;
-  if (!m->engine.fetch_batch(b->b, &rs->rs, false, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
+  if (!m->engine.fetch_batch(b->b, &rs->rs, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
   *out = rs.release();
   return ANL_OK;
 } catch (...) {

@@ -95,19 +95,24 @@ static const int ANL_MAX_SYMBOLS = 236;  // longest query / entry (symbols) the 
 
 // ---- confusables on the device ---------------------------------------------------------------------
 // Confusable rescoring (src/lib.rs:1656-1663,1733-1756) needs sesdiff's edit script of the raw strings.
-// Two device stages handle pure-ASCII pairs (bytes == Unicode scalar values):
-//  (1) prefilter, in the score kernel: a `-[..]` / `+[..]` instruction can only match characters of the
-//      input's / candidate's "middle" (what remains after stripping the common prefix and suffix; see
-//      DESIGN.md section 7).  Pairs that fail this necessary condition are settled with weight 1.
-//  (2) confusable kernel (confusables.cu): the full edit script + pattern matching, one pair per thread
+// Two device stages handle every pair whose text lies in the Basic Multilingual Plane (UTF-8 of at most three
+// bytes per character) and has at most 64 characters:
+//  (1) triage, in the score kernel: a `-[..]` / `+[..]` instruction can only match characters of the
+//      input's / candidate's "middle" (what remains after stripping the common prefix and suffix at character
+//      boundaries).  Pairs that fail this necessary condition are settled with weight 1.
+//      A pair whose middles share no character has the script =[prefix]-[middle a]+[middle b]=[suffix]; when the
+//      patterns are "simple" (insertions / deletions only, no anchors) its weight is computed on the spot.
+//  (2) confusable kernel: the full edit script over UTF-16 code units + pattern matching, one pair per thread
 //      (editscript_fixed.h), for the pairs that pass (1).
-// Only patterns an ASCII pair can satisfy are in the table (options with non-ASCII text are dropped; a
-// pattern with an instruction that has no ASCII option is dropped).  Whatever the device cannot settle
-// (non-ASCII text, very long strings) is left to the host post-pass.
+// Options with text outside the BMP are dropped from the table (they cannot match a BMP pair); a pattern with an
+// instruction that has no option left is dropped.  Whatever the device cannot settle (text outside the BMP, very long
+// strings, internal capacity) is left to the host post-pass.
 struct ConfOpt {
-  uint64_t lo, hi;     // characters the option needs: bit c of (lo | hi << 64)
-  uint32_t text_off;   // the option's text inside DeviceIndex::conf_text
+  uint64_t lo, hi;     // ASCII characters the option needs: bit c of (lo | hi << 64)
+  uint32_t text_off;   // the option's text inside DeviceIndex::conf_text (UTF-16 code units)
   uint32_t text_len;
+  uint32_t nonascii;   // the option also needs characters beyond ASCII
+  uint32_t pad;
 };
 struct ConfInstr {
   int8_t op;           // -1 deletion, +1 insertion, 0 identity
@@ -128,6 +133,8 @@ static const uint32_t HEAD_HOST_FINISH = 0x80000000u;
 struct ConfWork {
   uint32_t rec;    // record index in the result pool
   uint32_t query;  // query row (index into the batch's raw text offsets)
+  uint32_t cost;   // characters in the two middles: the kernel hands pairs of similar cost to the lanes of a warp
+  uint32_t pad;
 };
 
 // ---- alphabet on the device (query normalisation, src/anahash.rs:50-80) --------------------------------
@@ -187,9 +194,10 @@ struct DeviceIndex {
   const ConfPat* conf_pats;
   const ConfInstr* conf_instrs;
   const ConfOpt* conf_opts;
-  const uint8_t* conf_text;         // option texts of the patterns, back to back
+  const uint16_t* conf_text;        // option texts of the patterns (UTF-16 code units), back to back
   uint32_t n_conf_pats;
   int32_t conf_prefilter;           // 1: table valid, the kernel may set OUT_SKIP_CONFUSABLES
+  int32_t conf_all_simple;          // 1: every pattern consists of insertions / deletions only and has no anchor
   // alphabet tables for the encode kernel (device_encode = 0: the host normalises the queries)
   const AlphaMember* alpha_members;
   const AlphaFirst* alpha_first;    // [256]
@@ -265,6 +273,16 @@ static const uint32_t QF_HIT_OVERFLOW = 2;  // more instance hits than hit_cap: 
 static const uint32_t QF_OUT_OVERFLOW = 4;  // the packed result pool was exhausted: rerun the score kernel with a larger pool
 static const uint32_t QF_PREFILTERED = 16;   // prefilter_kernel compacted this query's hit list (and counted its pairs)
 static const uint32_t QF_UNSUPPORTED = 8;   // thresholded anagram distance > ANL_MAX_K or enumeration too large
+
+// ---- export of the final result arrays (export.cu) ---------------------------------------------------------
+static const uint32_t EXPORT_TILE = 1024;  // queries per CTA of the export stage
+// what the host needs to know about a finished pass before it touches any per-query array
+struct ExportSummary {
+  uint32_t total;          // records in the exported arrays
+  uint32_t n_rerun;        // queries whose hit list overflowed (they hold no records yet)
+  uint32_t n_host_finish;  // queries the device could not finish (HEAD_HOST_FINISH)
+  uint32_t pad;
+};
 
 struct Counters {
   unsigned long long deletion_keys, probes, filter_pass, table_steps, postings, anagram_hits, instance_pairs, dl_pairs,

@@ -543,16 +543,26 @@ struct PatTable {
   const ConfPat* pats;
   const ConfInstr* instrs;
   const ConfOpt* opts;
-  const uint8_t* text;  // option texts back to back
+  const uint16_t* text;  // option texts back to back (UTF-16 code units)
   uint32_t n_pats;
 };
 
-ESF_FN bool view_sfx(const uint8_t* p, uint32_t len, const uint8_t* t, uint32_t n) { return len >= n && same(p + len - n, t, (int)n); }
-ESF_FN bool view_pfx(const uint8_t* p, uint32_t len, const uint8_t* t, uint32_t n) { return len >= n && same(p, t, (int)n); }
-ESF_FN bool view_eq(const uint8_t* p, uint32_t len, const uint8_t* t, uint32_t n) { return len == n && same(p, t, (int)n); }
+template <class T>
+ESF_FN bool same_text(const T* x, const uint16_t* t, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i)
+    if ((uint32_t)x[i] != (uint32_t)t[i]) return false;
+  return true;
+}
+template <class T>
+ESF_FN bool view_sfx(const T* p, uint32_t len, const uint16_t* t, uint32_t n) { return len >= n && same_text(p + len - n, t, n); }
+template <class T>
+ESF_FN bool view_pfx(const T* p, uint32_t len, const uint16_t* t, uint32_t n) { return len >= n && same_text(p, t, n); }
+template <class T>
+ESF_FN bool view_eq(const T* p, uint32_t len, const uint16_t* t, uint32_t n) { return len == n && same_text(p, t, n); }
 
 // Confusable::found_in (src/confusables.rs:47-128) over the flat tables; `ref` is the script of a -> b
-ESF_FN bool found_in(const PatTable& T, const ConfPat& c, const uint8_t* a, const uint8_t* b, const View* ref, int nref) {
+template <class Ch>
+ESF_FN bool found_in(const PatTable& T, const ConfPat& c, const Ch* a, const Ch* b, const View* ref, int nref) {
   const int l = c.n_instr;
   int matches = 0;
   for (int i = 0; i < nref; ++i) {
@@ -562,8 +572,8 @@ ESF_FN bool found_in(const PatTable& T, const ConfPat& c, const uint8_t* a, cons
     if (ins.op == ref[i].op) {
       for (uint32_t o = 0; o < ins.n_opts && !found; ++o) {
         const ConfOpt opt = T.opts[ins.first_opt + o];
-        const uint8_t* t = T.text + opt.text_off;
-        const uint8_t* rp = (ref[i].op == INS ? b : a) + ref[i].pos;
+        const uint16_t* t = T.text + opt.text_off;
+        const Ch* rp = (ref[i].op == INS ? b : a) + ref[i].pos;
         const uint32_t rl = ref[i].len;
         bool ok;
         if (ins.op != 0)

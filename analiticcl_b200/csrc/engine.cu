@@ -73,6 +73,73 @@ void big_block_give(void* p, size_t bytes) {
   free(p);
 }
 
+// ---- DMA-able host blocks for the result arrays (hostpool.h) -------------------------------------------------
+namespace {
+struct DmaParked {
+  void* p;
+  size_t bytes;
+  bool pinned;
+};
+std::mutex g_dma_m;
+DmaParked g_dma_parked[12];
+}  // namespace
+void* dma_block_take(size_t min_bytes, size_t* got_bytes, bool* pinned) {
+  min_bytes = std::max<size_t>(min_bytes, 256);
+  {
+    std::lock_guard<std::mutex> lk(g_dma_m);
+    DmaParked* best = nullptr;
+    for (DmaParked& b : g_dma_parked)
+      if (b.p && b.bytes >= min_bytes && b.bytes <= std::max(4 * min_bytes, min_bytes + (4u << 20)) && (!best || b.bytes < best->bytes))
+        best = &b;
+    if (best) {
+      void* r = best->p;
+      *got_bytes = best->bytes;
+      *pinned = best->pinned;
+      best->p = nullptr;
+      best->bytes = 0;
+      return r;
+    }
+  }
+  const size_t two_mb = (size_t)2 << 20;
+  const size_t want = min_bytes >= two_mb ? (min_bytes + two_mb - 1) & ~(two_mb - 1) : (min_bytes + 4095) & ~(size_t)4095;
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess && p) {
+    *pinned = true;
+    *got_bytes = want;
+    return p;
+  }
+  cudaGetLastError();  // (no device / pinning limit reached: plain memory, the copies are then staged by the driver)
+  p = malloc(want);
+  *pinned = false;
+  *got_bytes = p ? want : 0;
+  return p;
+}
+void dma_block_give(void* p, size_t bytes, bool pinned) {
+  if (!p) return;
+  if (bytes <= kParkMax) {
+    std::lock_guard<std::mutex> lk(g_dma_m);
+    DmaParked* slot = nullptr;
+    for (DmaParked& b : g_dma_parked)
+      if (!b.p) slot = &b;
+    if (!slot) {  // replace the smallest parked block if this one is bigger
+      slot = &g_dma_parked[0];
+      for (DmaParked& b : g_dma_parked)
+        if (b.bytes < slot->bytes) slot = &b;
+      if (slot->bytes >= bytes) slot = nullptr;
+    }
+    if (slot) {
+      std::swap(p, slot->p);
+      std::swap(bytes, slot->bytes);
+      std::swap(pinned, slot->pinned);
+    }
+  }
+  if (!p) return;
+  if (pinned)
+    cudaFreeHost(p);
+  else
+    free(p);
+}
+
 // DistanceThreshold on the host (src/lib.rs:982-1012); the kernels carry their own copy.
 static uint32_t host_threshold(const anl_distance_threshold& t, size_t len) {
   auto sat = [](double v) -> uint32_t { return !(v == v) || v <= 0 ? 0u : (v >= 255 ? 255u : (uint32_t)v); };
@@ -268,11 +335,12 @@ bool Engine::ensure_confusable_table(std::string* err) {
   h_ix_.conf_text = nullptr;
   h_ix_.n_conf_pats = 0;
   h_ix_.conf_prefilter = 0;
+  h_ix_.conf_all_simple = 0;
   if (!cf.empty()) {
     std::vector<ConfPat> pats;
     std::vector<ConfInstr> instrs;
     std::vector<ConfOpt> opts;
-    std::vector<uint8_t> ctext;
+    std::vector<uint16_t> ctext;  // option texts as UTF-16 code units (BMP only: one unit per character)
     bool fits = true;
     for (const Confusable& c : cf) {
       ConfPat pat;
@@ -285,27 +353,29 @@ bool Engine::ensure_confusable_table(std::string* err) {
       bool viable = true;
       for (const ConfusableInstr& ins : c.script) {
         ConfInstr ci{(int8_t)ins.op, 0, (uint16_t)opts.size()};
-        for (const std::string& o : ins.options) {
-          ConfOpt m{0, 0, (uint32_t)ctext.size(), (uint32_t)o.size()};
-          bool ascii = true;
-          for (unsigned char ch : o) {
-            if (ch >= 0x80) {
-              ascii = false;
+        for (const std::u32string& o : ins.options32) {
+          ConfOpt m{0, 0, (uint32_t)ctext.size(), (uint32_t)o.size(), 0, 0};
+          bool bmp = true;
+          for (char32_t ch : o) {
+            if (ch > 0xFFFF) {
+              bmp = false;
               break;
             }
-            if (ch < 64) m.lo |= 1ull << ch; else m.hi |= 1ull << (ch - 64);
+            if (ch >= 0x80) m.nonascii = 1;
+            else if (ch < 64) m.lo |= 1ull << ch;
+            else m.hi |= 1ull << (ch - 64);
           }
-          if (!ascii) continue;  // cannot match the text of an ASCII pair
+          if (!bmp) continue;  // cannot match the text of a pair inside the BMP
           if (ci.n_opts < 255) {
             opts.push_back(m);
-            ctext.insert(ctext.end(), o.begin(), o.end());
+            for (char32_t ch : o) ctext.push_back((uint16_t)ch);
             ++ci.n_opts;
           } else {
             fits = false;
           }
         }
         if (ci.n_opts == 0) {
-          viable = false;  // every option needs a non-ASCII character: impossible for an ASCII pair
+          viable = false;  // every option needs a character outside the BMP: impossible for a BMP pair
           break;
         }
         instrs.push_back(ci);
@@ -342,6 +412,16 @@ bool Engine::ensure_confusable_table(std::string* err) {
         if (!upload_vec(ctext, &h_ix_.conf_text, &conf_allocs_, err)) return false;
         h_ix_.n_conf_pats = (uint32_t)pats.size();
         h_ix_.conf_prefilter = 1;
+        h_ix_.conf_all_simple = hm_->all_confusables_simple ? 1 : 0;
+        {
+          // character classes of the device edit script (lossless shift): the Alphabetic ranges, per device
+          std::vector<uint32_t> alpha(2 * (size_t)anl_unicode::kAlphabeticRanges_len);
+          for (unsigned i = 0; i < anl_unicode::kAlphabeticRanges_len; ++i) {
+            alpha[2 * i] = anl_unicode::kAlphabeticRanges[i][0];
+            alpha[2 * i + 1] = anl_unicode::kAlphabeticRanges[i][1];
+          }
+          CU_TRY(upload_alphabetic_ranges(alpha.data(), anl_unicode::kAlphabeticRanges_len));
+        }
       }
     }
   }
@@ -405,8 +485,11 @@ bool Engine::make_batch_params(const anl_search_params& p, BatchParams* bp, uint
 void Engine::destroy_batch(DeviceBatch* b) {
   if (!b) return;
   for (void* p : {(void*)b->h_rows, (void*)b->h_head, (void*)b->h_flags, (void*)b->h_hitcnt, (void*)b->h_out,
-                  (void*)b->h_work, (void*)b->h_qboff, (void*)b->h_qblob})
+                  (void*)b->h_work, (void*)b->h_qboff, (void*)b->h_qblob, (void*)b->h_summary})
     if (p) cudaFreeHost(p);
+  for (void* p : {(void*)b->d_final, (void*)b->d_loff, (void*)b->d_oflags, (void*)b->d_off64, (void*)b->d_tile_sum,
+                  (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work})
+    if (p) cudaFree(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
   if (b->d_conf_work) cudaFree(b->d_conf_work);
@@ -423,16 +506,16 @@ void Engine::destroy_batch(DeviceBatch* b) {
     if (ev) cudaEventDestroy(ev);
   if (b->uploaded) cudaEventDestroy(b->uploaded);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-  if (b->ev_merged) cudaEventDestroy(b->ev_merged);
+  if (b->ev_done) cudaEventDestroy(b->ev_done);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->aux) cudaStreamDestroy(b->aux);
-  if (b->rr_stream) cudaStreamDestroy(b->rr_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
 
 void Engine::free_batch(DeviceBatch* b) {
   if (!b) return;
+  std::unique_lock<std::mutex> lk(cache_m_);
   if (cache_.size() < 8) {
     b->owned_blob.clear();
     b->owned_blob.shrink_to_fit();
@@ -441,16 +524,27 @@ void Engine::free_batch(DeviceBatch* b) {
     b->runs_recorded = 0;
     cache_.push_back(b);
   } else {
+    lk.unlock();
     destroy_batch(b);
   }
 }
 
-bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err) {
+bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, bool keep_records, std::string* err) {
   const bool need_gid = hm_->index.n_shards > 1;
   const bool need_cw = h_ix_.conf_prefilter && !need_gid;  // the confusable queue can hold every pool record
-  if (pool_cap <= b->cap_pool && b->d_out && (!need_gid || b->d_gid) && (!need_cw || b->d_conf_work)) return true;
+  if (pool_cap <= b->cap_pool && b->d_out && b->d_final && (!need_gid || b->d_gid) && (!need_cw || b->d_conf_work)) return true;
   pool_cap = std::max(pool_cap, b->cap_pool);
-  if (!dev_realloc(&b->d_out, pool_cap, err)) return false;
+  if (keep_records && b->d_out && b->cap_pool) {
+    // (hit-overflow patch: the records already in the pool stay valid)
+    OutRec* bigger = nullptr;
+    if (!dev_realloc(&bigger, pool_cap, err)) return false;
+    CU_TRY(cudaMemcpy(bigger, b->d_out, (size_t)b->cap_pool * sizeof(OutRec), cudaMemcpyDeviceToDevice));
+    cudaFree(b->d_out);
+    b->d_out = bigger;
+  } else if (!dev_realloc(&b->d_out, pool_cap, err)) {
+    return false;
+  }
+  if (!dev_realloc(&b->d_final, pool_cap, err)) return false;
   if (need_gid && !dev_realloc(&b->d_gid, pool_cap, err)) return false;
   if (need_cw && !dev_realloc(&b->d_conf_work, pool_cap, err)) return false;
   if (!pinned_realloc(&b->h_out, pool_cap, err)) return false;
@@ -476,9 +570,13 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
     if (!pinned_realloc(&b->h_head, n, err)) return false;
     if (!pinned_realloc(&b->h_flags, n, err)) return false;
     if (!pinned_realloc(&b->h_hitcnt, n, err)) return false;
+    if (!dev_realloc(&b->d_enc_status, (size_t)n + 1, err) || !pinned_realloc(&b->h_enc_status, (size_t)n + 1, err)) return false;
+    if (!dev_realloc(&b->d_loff, (size_t)n + 1, err) || !dev_realloc(&b->d_oflags, n, err) || !dev_realloc(&b->d_off64, n, err) ||
+        !dev_realloc(&b->d_tile_sum, (size_t)export_tiles(n) + 1, err))
+      return false;
     b->cap_n = n;
   }
-  if (!grow_pool(b, pool_cap, err)) return false;
+  if (!grow_pool(b, pool_cap, false, err)) return false;
   if (scratch > b->cap_scratch || !b->d_scratch) {
     if (!dev_realloc(reinterpret_cast<uint8_t**>(&b->d_scratch), scratch, err)) return false;
     b->cap_scratch = scratch;
@@ -487,6 +585,7 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
     if (!dev_realloc(&b->d_work, 8, err)) return false;
     if (!pinned_realloc(&b->h_work, 8, err)) return false;
     if (!dev_realloc(&b->d_counters, 1, err)) return false;
+    if (!dev_realloc(&b->d_summary, 1, err) || !pinned_realloc(&b->h_summary, 1, err)) return false;
   }
   return true;
 }
@@ -504,31 +603,45 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
     *status = ANL_ERR_INVALID;
     return nullptr;
   }
-  BatchParams bp;
-  uint32_t needed_j = 0;
-  if (!make_batch_params(p, &bp, &needed_j, err) || !ensure_msets(needed_j, err)) {
-    *status = ANL_ERR_UNSUPPORTED;
+  if (cudaSetDevice(device_) != cudaSuccess) {  // (a dispatcher thread starts on device 0)
+    *err = "cudaSetDevice failed";
     return nullptr;
   }
-  if (!ensure_confusable_table(err)) return nullptr;
+  BatchParams bp;
+  uint32_t needed_j = 0;
+  {
+    static std::mutex setup_m;  // process-wide: the engines of one model share its host-side tables
+    std::lock_guard<std::mutex> lk(setup_m);  // (first use of a distance / confusable list builds and uploads tables)
+    if (!make_batch_params(p, &bp, &needed_j, err) || !ensure_msets(needed_j, err)) {
+      *status = ANL_ERR_UNSUPPORTED;
+      return nullptr;
+    }
+    if (!ensure_confusable_table(err)) return nullptr;
+  }
   if (cudaSetDevice(device_) != cudaSuccess) {
     *err = "cudaSetDevice failed";
     return nullptr;
   }
   PhaseTimer pt;
   DeviceBatch* b = nullptr;
-  if (!cache_.empty()) {
-    b = cache_.back();
-    cache_.pop_back();
-  } else {
-    b = new DeviceBatch();
+  {
+    std::lock_guard<std::mutex> lk(cache_m_);
+    if (!cache_.empty()) {
+      b = cache_.back();
+      cache_.pop_back();
+    }
   }
+  if (!b) b = new DeviceBatch();
   auto fail = [&]() -> DeviceBatch* {
     destroy_batch(b);
     return nullptr;
   };
   if (!b->stream && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
     *err = "cudaStreamCreate failed";
+    return fail();
+  }
+  if (!b->ev_done && cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+    *err = "cudaEventCreate failed";
     return fail();
   }
   if (!b->uploaded && cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming) != cudaSuccess) {
@@ -544,8 +657,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
   b->n = (uint32_t)n;
   b->params = p;
   b->reruns = 0;
-  b->fetch_begun = false;
-  b->rr_pending = false;
+  b->settled = false;
   b->results = 0;
   b->offsets.resize(n + 1);
   const uint64_t base = offsets[0];
@@ -658,8 +770,7 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       b->cap_qblob = okb ? want : 0;
     }
     if (okb && (n + 1 > b->cap_qboff || !b->d_qboff)) {
-      okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2) &&
-            dev_realloc(&b->d_enc_status, (size_t)n + 1, &e2) && pinned_realloc(&b->h_enc_status, (size_t)n + 1, &e2);
+      okb = dev_realloc(&b->d_qboff, (size_t)n + 1, &e2) && pinned_realloc(&b->h_qboff, (size_t)n + 1, &e2);
       b->cap_qboff = okb ? (size_t)n + 1 : 0;
     }
     if (!okb) {
@@ -688,9 +799,14 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
       *err = "encode kernel launch failed";
       return fail();
     }
-  } else if (n > 0 && cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
-    *err = "H2D copy failed";
-    return fail();
+  } else if (n > 0) {
+    // rows encoded on the host; the per-query encode status follows them (the export stage turns it into flags)
+    memcpy(b->h_enc_status, b->host_flags.data(), (size_t)n);
+    if (cudaMemcpyAsync(b->d_rows, rows, (size_t)n * stride, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+        cudaMemcpyAsync(b->d_enc_status, b->h_enc_status, (size_t)n, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
+      *err = "H2D copy failed";
+      return fail();
+    }
   }
   if (cudaEventRecord(b->uploaded, b->stream) != cudaSuccess || (sync && cudaStreamSynchronize(b->stream) != cudaSuccess)) {
     *err = "H2D sync failed";
@@ -730,6 +846,34 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   return lb;
 }
 
+bool Engine::launch_export_chain(DeviceBatch* b, cudaStream_t st, std::string* err) {
+  // export stage + the download of what the host needs to decide anything about this pass: pool cursor, staged-node
+  // queue length, and the summary (records, queries to re-run, queries to finish on the host)
+  if (b->bp.finish_mode != FINISH_SHARD) {  // (a shard's survivors are ranked after the exchange: nothing final yet)
+    ExportBuffers eb;
+    eb.n = b->n;
+    eb.head = b->d_head;
+    eb.qflags = b->d_qflags;
+    eb.enc_status = b->d_enc_status;
+    eb.pool = b->d_out;
+    eb.tile_sum = b->d_tile_sum;
+    eb.loff = b->d_loff;
+    eb.oflags = b->d_oflags;
+    eb.out = b->d_final;
+    eb.out_cap = b->cap_pool;
+    eb.summary = b->d_summary;
+    CU_TRY(launch_export(eb, st));
+  }
+  return true;
+}
+
+static bool download_summary(DeviceBatch* b, cudaStream_t st, std::string* err) {
+  CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(ExportSummary), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(b->ev_done, st));
+  return true;
+}
+
 bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   CU_TRY(cudaSetDevice(device_));
   if (!stream)
@@ -757,9 +901,13 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   CU_TRY(cudaEventRecord(ev[5], stream));
   CU_TRY(launch_finish(b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[6], stream));
-  b->last_done = ev[6];
+  if (!launch_export_chain(b, stream, err)) return false;
+  CU_TRY(cudaEventRecord(ev[7], stream));
+  if (!download_summary(b, stream, err)) return false;
+  b->last_done = ev[7];
   ++b->runs_recorded;
   b->ran = true;
+  b->settled = false;
   return true;
 }
 
@@ -933,14 +1081,27 @@ void Engine::finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs,
   out->resize(start + n);
 }
 
-// Queries with more instance hits than hit_cap: run both kernels again for just those queries with
-// an exact capacity.  Rare (needs > hit_cap candidate instances for one query).
-bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
+// ---- settling a pass --------------------------------------------------------------------------------------------
+// Hit-list overflows (a query with more than hit_cap candidate instances): those queries are run again with an exact
+// capacity into buffers of their own, the results are patched into the batch's pool and the export stage runs again.
+// Rare; the batch's stream simply carries the extra work.
+bool Engine::rerun_overflowed(DeviceBatch* b, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
-  const std::vector<uint32_t>& which = b->rr_which;
-  const uint32_t m = (uint32_t)which.size();
+  const uint32_t n = b->n;
+  cudaStream_t st = b->stream;
+  CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  std::vector<uint32_t> which;
   uint32_t cap = b->bp.hit_cap;
-  for (uint32_t i : which) cap = std::max(cap, b->h_hitcnt[i]);
+  for (uint32_t i = 0; i < n; ++i)
+    if ((b->h_flags[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) {
+      which.push_back(i);
+      cap = std::max(cap, b->h_hitcnt[i]);
+    }
+  const uint32_t m = (uint32_t)which.size();
+  if (m == 0) return true;
+  if (profile_enabled()) fprintf(stderr, "[anl profile] %u queries overflowed hit_cap=%u\n", m, b->bp.hit_cap);
   cap = (cap + 31) & ~31u;
   BatchParams bp = b->bp;
   bp.hit_cap = cap;
@@ -950,8 +1111,8 @@ bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
     return false;
   }
   bp.pool_cap = (uint32_t)pool64;
-  // grow-only buffers kept with the batch: steady state allocates (and frees) nothing, which matters
-  // because cudaFree synchronises the device and would stall the other in-flight chunks
+  // grow-only buffers kept with the batch: steady state allocates (and frees) nothing, which matters because
+  // cudaFree synchronises the device and would stall the other in-flight chunks
   const size_t scratch = score_scratch_bytes(bp, sm_count_, m);
   if (m > b->rr_cap_m) {
     if (!dev_realloc(&b->rr_qlist, m, err) || !dev_realloc(&b->rr_hit_count, m, err) || !dev_realloc(&b->rr_qflags, m, err) ||
@@ -965,26 +1126,22 @@ bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
   }
   if (bp.pool_cap > b->rr_cap_pool) {
     if (!dev_realloc(&b->rr_out, bp.pool_cap, err)) return false;
+    if (b->dev_conf && !dev_realloc(&b->rr_conf_work, bp.pool_cap, err)) return false;
     b->rr_cap_pool = bp.pool_cap;
   }
+  if (b->dev_conf && !b->rr_conf_work && !dev_realloc(&b->rr_conf_work, b->rr_cap_pool, err)) return false;
   if (scratch > b->rr_cap_scratch) {
     if (!dev_realloc(&b->rr_scratch, scratch, err)) return false;
     b->rr_cap_scratch = scratch;
   }
-  if (!b->rr_stream) {
-    // the re-run is a handful of warps with long dependent chains: let its blocks go first whenever an SM has
-    // room, instead of queueing behind the persistent grids of the other chunks
-    int lo = 0, hi = 0;
-    CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CU_TRY(cudaStreamCreateWithPriority(&b->rr_stream, cudaStreamNonBlocking, hi));
-  }
-  cudaStream_t st = b->rr_stream;  // (the batch's own run has completed: settle_pool synchronised)
+  if (!b->rr_work && !dev_realloc(&b->rr_work, 8, err)) return false;
   CU_TRY(cudaMemcpyAsync(b->rr_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   LaunchBuffers lb;
   lb.queries = b->d_rows;
   lb.qlist = b->rr_qlist;
   lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
+  lb.conf_work = b->dev_conf ? b->rr_conf_work : nullptr;
   lb.n = m;
   lb.hits = b->rr_hits;
   lb.hit_count = b->rr_hit_count;
@@ -992,63 +1149,71 @@ bool Engine::rerun_launch(DeviceBatch* b, std::string* err, int* status) {
   lb.out = b->rr_out;
   lb.out_head = b->rr_head;
   lb.scratch = b->rr_scratch;
-  lb.work = b->d_work;
+  lb.scratch_bytes = b->rr_cap_scratch;
+  lb.work = b->rr_work;
   lb.counters = nullptr;
-  CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, st));
+  CU_TRY(cudaMemsetAsync(b->rr_work, 0, 8 * sizeof(unsigned int), st));
+  CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, st));  // (no staged-node queue: the fused kernel)
   CU_TRY(launch_prefilter(d_ix_, bp, lb, sm_count_, st));
   CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, st));
-  b->rr_bp = bp;
-  b->rr_pending = true;
-  *status = ANL_OK;
-  return true;
-}
-
-bool Engine::rerun_collect(DeviceBatch* b, std::string* err, int* status) {
-  *status = ANL_ERR_CUDA;
-  const uint32_t m = (uint32_t)b->rr_which.size();
-  cudaStream_t st = b->rr_stream;
-  b->rr_pending = false;
+  CU_TRY(launch_confusables(d_ix_, bp, lb, sm_count_, st));
+  CU_TRY(launch_finish(bp, lb, sm_count_, st));
+  unsigned int rr_work[8];
   std::vector<uint32_t> fl(m);
-  b->rr_heads.resize(m);
-  unsigned int total = 0;
-  CU_TRY(cudaMemcpyAsync(b->rr_heads.data(), b->rr_head, m * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(rr_work, b->rr_work, sizeof rr_work, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaMemcpyAsync(fl.data(), b->rr_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(&total, b->d_work + 2, sizeof total, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < m; ++i)
     if (fl[i] & (QF_HIT_OVERFLOW | QF_OUT_OVERFLOW | QF_UNSUPPORTED)) {
       *err = "internal error: overflow persisted after rerun";
       return false;
     }
-  b->rr_recs.resize(total);
-  if (total) {
-    CU_TRY(cudaMemcpyAsync(b->rr_recs.data(), b->rr_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+  const uint32_t rr_total = rr_work[2], base = b->h_work[2];
+  if ((uint64_t)base + rr_total > 0xFFFFFF00ull) {
+    *err = "result pool too large; split the batch";
+    *status = ANL_ERR_UNSUPPORTED;
+    return false;
+  }
+  if (base + rr_total > b->cap_pool) {
+    if (!grow_pool(b, base + rr_total + 1024, true, err)) return false;
+    b->bp.pool_cap = b->cap_pool;
+  }
+  CU_TRY(launch_patch(m, b->rr_qlist, b->rr_head, b->rr_qflags, b->rr_out, b->d_head, b->d_qflags, b->d_out, base, b->cap_pool,
+                      b->d_work + 2, rr_total, st));
+  b->reruns += m;
+  if (!launch_export_chain(b, st, err) || !download_summary(b, st, err)) return false;
+  CU_TRY(cudaEventSynchronize(b->ev_done));
+  if (b->h_summary->n_rerun != 0) {
+    *err = "internal error: hit overflow persisted after the patch";
+    return false;
   }
   *status = ANL_OK;
   return true;
 }
 
-bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* err) {
+// Pool and staged-node queue overflows of a pass: run the affected stages again with larger buffers.
+static const char* kPoolPersisted = "internal error: result pool overflow persisted";
+bool Engine::settle(DeviceBatch* b, std::string* err, int* status) {
+  *status = ANL_ERR_CUDA;
+  if (!b->ran) {
+    *err = "batch has not been run";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  if (b->settled) {
+    *status = ANL_OK;
+    return true;
+  }
+  CU_TRY(cudaSetDevice(device_));
   const uint32_t n = b->n;
   cudaStream_t st = b->stream;
-  unsigned int total = 0;
   for (int attempt = 0;; ++attempt) {
-    CU_TRY(cudaStreamWaitEvent(st, b->last_done, 0));
-    CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    if (n) {
-      CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaMemcpyAsync(b->h_hitcnt, b->d_hit_count, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      if (b->dev_encode) CU_TRY(cudaMemcpyAsync(b->h_enc_status, b->d_enc_status, (size_t)n, cudaMemcpyDeviceToHost, st));
-    }
-    CU_TRY(cudaStreamSynchronize(st));
-    if (b->dev_encode)
-      for (uint32_t i = 0; i < n; ++i) b->host_flags[i] = b->h_enc_status[i];
+    CU_TRY(cudaEventSynchronize(b->ev_done));
     if (b->split && n && b->h_work[4] > std::min<size_t>(b->cap_queue, 0x7FFFFFF0u)) {
       // the staged-node queue was too small for this batch: run it again with the fused probe kernel
       if (profile_enabled()) fprintf(stderr, "[anl profile] staged-node queue overflow (%u > %zu): fused rerun\n", b->h_work[4], b->cap_queue);
       b->split = false;
+      CU_TRY(cudaStreamWaitEvent(st, b->ev_done, 0));
       LaunchBuffers lbq = launch_buffers(b);
       lbq.counters = nullptr;
       CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
@@ -1056,32 +1221,196 @@ bool Engine::settle_pool(DeviceBatch* b, unsigned int* total_out, std::string* e
       CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
       CU_TRY(launch_confusables(d_ix_, b->bp, lbq, sm_count_, st));
       CU_TRY(launch_finish(b->bp, lbq, sm_count_, st));
-      CU_TRY(cudaEventRecord(b->last_done, st));
+      if (!launch_export_chain(b, st, err) || !download_summary(b, st, err)) return false;
       b->reruns += 1;
       --attempt;
       continue;
     }
-    total = n ? b->h_work[2] : 0;
-    if (total <= b->bp.pool_cap || b->merged) break;
+    const unsigned int used = n ? b->h_work[2] : 0;
+    if (used <= b->bp.pool_cap || b->merged) break;
     if (attempt >= 2) {
-      *err = "internal error: result pool overflow persisted";
+      *err = kPoolPersisted;
       return false;
     }
-    // the cursor counted every query's results, so `total` is the exact requirement
-    if (!grow_pool(b, (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, (uint64_t)total + 1024), err)) return false;
+    // the cursor counted every query's results, so `used` is the exact requirement
+    if (!grow_pool(b, (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, (uint64_t)used + 1024), false, err)) return false;
     b->bp.pool_cap = b->cap_pool;
+    CU_TRY(cudaStreamWaitEvent(st, b->ev_done, 0));
     LaunchBuffers lb = launch_buffers(b);
     lb.counters = nullptr;
     CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, st));
     CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, st));
     CU_TRY(launch_finish(b->bp, lb, sm_count_, st));
-    CU_TRY(cudaEventRecord(b->last_done, st));
+    if (!launch_export_chain(b, st, err) || !download_summary(b, st, err)) return false;
     b->reruns += 1;
   }
-  *total_out = total;
+  if (b->bp.finish_mode != FINISH_SHARD && b->h_summary->n_rerun && !rerun_overflowed(b, err, status)) return false;
+  b->settled = true;
+  *status = ANL_OK;
   return true;
 }
 
+// Does the host have to touch this batch's records?  Yes when a confusable / variant-list post-pass follows that the
+// device did not run, or when the device flagged queries it could not finish.
+bool Engine::needs_host_finish(const DeviceBatch* b) const {
+  if (b->bp.finish_mode == FINISH_FULL) return false;
+  if (hm_->any_variants || !b->dev_conf) return true;
+  return b->h_summary->n_host_finish != 0;
+}
+
+bool Engine::issue_download(DeviceBatch* b, ResultSet* out, uint64_t qbase, uint64_t vbase, std::string* err) {
+  CU_TRY(cudaSetDevice(device_));
+  const uint32_t n = b->n, total = b->h_summary->total;
+  cudaStream_t st = b->stream;
+  if (n) {
+    CU_TRY(launch_offsets(n, b->d_loff, vbase, b->d_off64, st));
+    CU_TRY(cudaMemcpyAsync(out->offsets.data() + qbase, b->d_off64, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->flags.data() + qbase, b->d_oflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (total)
+    CU_TRY(cudaMemcpyAsync(out->variants.data() + vbase, b->d_final, (size_t)total * sizeof(anl_variant), cudaMemcpyDeviceToHost, st));
+  b->results = total;
+  return true;
+}
+
+bool Engine::wait_download(DeviceBatch* b, std::string* err) {
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return true;
+}
+
+// Slow path of a batch: the 16-byte records come to the host, the queries the device could not finish go through
+// finish_query (confusable rescoring, variant expansion, re-rank, crop, cut-off: src/lib.rs:1504-1622), everything
+// is assembled into the batch's part of `out`.  The caller guarantees that no download into `out` is in flight
+// (its variants array may move).
+bool Engine::finish_on_host(DeviceBatch* b, ResultSet* out, uint64_t qbase, uint64_t vbase, uint64_t* written, std::string* err,
+                            int* status) {
+  *status = ANL_ERR_CUDA;
+  CU_TRY(cudaSetDevice(device_));
+  const uint32_t n = b->n;
+  cudaStream_t st = b->stream;
+  PhaseTimer pt;
+  const unsigned int used = n ? std::min<unsigned int>(b->h_work[2], b->cap_pool) : 0;
+  if (n) {
+    CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(b->h_flags, b->d_qflags, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(b->h_enc_status, b->d_enc_status, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  if (used) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)used * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  pt.lap("host finish: D2H");
+  const bool post_pass = b->bp.finish_mode != FINISH_FULL;
+  auto locate = [&](uint32_t i, const OutRec** recs, uint32_t* count, double* maxf, bool* host) {
+    const OutHead& h = b->h_head[i];
+    const bool none = (b->h_flags[i] & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED | QF_OUT_OVERFLOW)) != 0;
+    *recs = b->h_out + h.offset;
+    *count = none ? 0 : (h.count & ~HEAD_HOST_FINISH);
+    *maxf = h.max_freq;
+    *host = post_pass && (hm_->any_variants || !b->dev_conf || (h.count & HEAD_HOST_FINISH));
+  };
+  uint64_t* offs = out->offsets.data() + qbase;
+  uint32_t* flags = out->flags.data() + qbase;
+  // pass 1: queries the host must finish go through finish_query into per-thread side buffers; the
+  // counts of all other queries are final as they come from the device
+  const unsigned maxt = host_threads();
+  std::vector<std::vector<anl_variant>> part(post_pass ? maxt : 0);
+  std::vector<uint32_t> counts(n, 0), side_pos(post_pass ? n : 0, 0);
+  uint64_t host_queries = 0;
+  std::vector<uint64_t> hq(maxt, 0);
+  parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i) {
+      const OutRec* r;
+      uint32_t c;
+      double mf;
+      bool host;
+      locate((uint32_t)i, &r, &c, &mf, &host);
+      uint32_t of = 0;
+      if ((b->h_flags[i] & QF_EMPTY) && b->h_enc_status[i] == ENC_OK) of |= ANL_QUERY_EMPTY;
+      if ((b->h_flags[i] & QF_UNSUPPORTED) || b->h_enc_status[i] == ENC_TOO_LONG_UNSUPPORTED) of |= ANL_QUERY_UNSUPPORTED;
+      flags[i] = of;
+      if (!host) {
+        counts[i] = c;
+        continue;
+      }
+      std::vector<anl_variant>& buf = part[t];
+      const size_t before = buf.size();
+      finish_query(*b, i, r, c, mf, &buf);
+      side_pos[i] = (uint32_t)before;
+      counts[i] = (uint32_t)(buf.size() - before);
+      ++hq[t];
+    }
+  });
+  for (uint64_t v : hq) host_queries += v;
+  uint64_t tot = vbase;
+  for (uint32_t i = 0; i < n; ++i) {
+    offs[i] = tot;
+    tot += counts[i];
+  }
+  if (tot > out->variants.capacity()) out->variants.reserve(std::max<size_t>(tot, out->variants.capacity() + out->variants.capacity() / 2));
+  // pass 2: convert / copy straight into place (same thread ranges as pass 1)
+  anl_variant* vout = out->variants.data();
+  parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i) {
+      const OutRec* r;
+      uint32_t c;
+      double mf;
+      bool host;
+      locate((uint32_t)i, &r, &c, &mf, &host);
+      anl_variant* dst = vout + offs[i];
+      if (host) {
+        if (counts[i]) memcpy(dst, part[t].data() + side_pos[i], (size_t)counts[i] * sizeof(anl_variant));
+        continue;
+      }
+      for (uint32_t k = 0; k < c; ++k) {
+        // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with
+        const double f = (double)r[k].freq;
+        dst[k] = anl_variant{r[k].vocab_id & ~OUT_SKIP_CONFUSABLES, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
+      }
+    }
+  });
+  b->results = tot - vbase;
+  *written = tot - vbase;
+  pt.lap("host finish: post-pass+assemble");
+  if (profile_enabled()) {
+    uint64_t v[4];
+    confusable_stats(v);
+    fprintf(stderr, "[anl profile] %llu of %u queries finished on the host (device confusables: %s)\n",
+            (unsigned long long)host_queries, n, b->dev_conf ? "on" : "off");
+    fprintf(stderr, "[anl profile] confusable checks %llu, prefilter pass %llu (ascii), single-edit fast %llu, full script %llu\n",
+            (unsigned long long)v[0], (unsigned long long)v[1], (unsigned long long)v[2], (unsigned long long)v[3]);
+  }
+  *status = ANL_OK;
+  return true;
+}
+
+// One batch -> a fresh result set (device-batch API, sharded merge).
+bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* status) {
+  if (b->sharded && !b->merged) {
+    *err = "this model holds a lexicon shard: use the shard export / merge calls";
+    *status = ANL_ERR_INVALID;
+    return false;
+  }
+  if (!settle(b, err, status)) return false;
+  *status = ANL_ERR_CUDA;
+  const uint32_t n = b->n;
+  out->offsets.resize((size_t)n + 1);
+  out->flags.resize(std::max<size_t>(n, 1));
+  out->flags.resize(n);
+  uint64_t total = 0;
+  if (needs_host_finish(b)) {
+    out->variants.reserve(std::max<size_t>(b->h_summary->total, 16));
+    if (!finish_on_host(b, out, 0, 0, &total, err, status)) return false;
+  } else {
+    total = b->h_summary->total;
+    out->variants.reserve(std::max<size_t>(total, 16));
+    if (!issue_download(b, out, 0, 0, err) || !wait_download(b, err)) return false;
+  }
+  out->offsets[n] = total;
+  out->variants.resize(total);
+  *status = ANL_OK;
+  return true;
+}
+
+// ---- lexicon-sharded mode ---------------------------------------------------------------------------------------
 bool Engine::shard_export_size(DeviceBatch* b, uint64_t* n_records, uint32_t* max_per_query, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!b->ran || !b->sharded) {
@@ -1089,12 +1418,16 @@ bool Engine::shard_export_size(DeviceBatch* b, uint64_t* n_records, uint32_t* ma
     *status = ANL_ERR_INVALID;
     return false;
   }
-  CU_TRY(cudaSetDevice(device_));
-  unsigned int total = 0;
-  if (!settle_pool(b, &total, err)) return false;
+  if (!settle(b, err, status)) return false;  // (pool / queue overflows; a shard's hit overflow is reported at the merge)
+  *status = ANL_ERR_CUDA;
+  const uint32_t n = b->n;
+  if (n) {
+    CU_TRY(cudaMemcpyAsync(b->h_head, b->d_head, (size_t)n * sizeof(OutHead), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+  }
   uint32_t mx = 0;
-  for (uint32_t i = 0; i < b->n; ++i) mx = std::max(mx, b->h_head[i].count);
-  *n_records = total;
+  for (uint32_t i = 0; i < n; ++i) mx = std::max(mx, b->h_head[i].count);
+  *n_records = n ? b->h_work[2] : 0;
   if (max_per_query) *max_per_query = mx;
   *status = ANL_OK;
   return true;
@@ -1146,7 +1479,7 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
     *status = ANL_ERR_UNSUPPORTED;
     return false;
   }
-  if (!grow_pool(b, (uint32_t)pool64, err)) return false;
+  if (!grow_pool(b, (uint32_t)pool64, false, err)) return false;
   const uint32_t cap = std::max<uint32_t>(32, (max_survivors + 31) & ~31u);
   const size_t scratch = merge_scratch_bytes(sm_count_, n, cap);
   if (scratch > b->cap_scratch || !b->d_scratch) {
@@ -1160,262 +1493,245 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
                       reinterpret_cast<const uint32_t*>(d_gids_all), (uint32_t)record_stride,
                       reinterpret_cast<const uint32_t*>(d_flags_all), b->d_qflags, b->d_out, b->d_head, b->d_scratch, cap,
                       b->d_work, sm_count_, st));
-  if (!b->ev_merged) CU_TRY(cudaEventCreateWithFlags(&b->ev_merged, cudaEventDisableTiming));
-  CU_TRY(cudaEventRecord(b->ev_merged, st));  // (not one of the per-run timing events: timings() stays valid)
-  b->last_done = b->ev_merged;
+  // the merged lists are final: the host post-pass / export stage follow the final mode
   b->merged = true;
-  b->bp.finish_mode = b->final_mode;  // the host post-pass of fetch_batch follows the final mode
+  b->bp.finish_mode = b->final_mode;
   b->bp.pool_cap = b->cap_pool;
-  bool ok = true;
-  if (out) {
-    ok = fetch_batch(b, out, false, err, status);
-  } else {
-    CU_TRY(cudaStreamSynchronize(st));  // device-only merge: ranked lists stay in the batch's pool
-    *status = ANL_OK;
+  b->settled = false;
+  bool ok = launch_export_chain(b, st, err) && download_summary(b, st, err);
+  if (ok) {
+    if (out) {
+      ok = fetch_batch(b, out, err, status);
+    } else {
+      ok = settle(b, err, status);  // device-only merge: ranked lists (and their exported form) stay in the batch's buffers
+    }
   }
   b->bp.finish_mode = FINISH_SHARD;
   b->merged = false;
-  return ok;
-}
-
-bool Engine::fetch_begin(DeviceBatch* b, std::string* err, int* status) {
-  *status = ANL_ERR_CUDA;
-  if (!b->ran) {
-    *err = "batch has not been run";
-    *status = ANL_ERR_INVALID;
-    return false;
-  }
-  if (b->sharded && !b->merged) {
-    *err = "this model holds a lexicon shard: use the shard export / merge calls";
-    *status = ANL_ERR_INVALID;
-    return false;
-  }
-  CU_TRY(cudaSetDevice(device_));
-  const uint32_t n = b->n;
-  cudaStream_t st = b->stream;
-  PhaseTimer pt;
-  // headers + pool cursor first; grow the pool and re-run the score kernel if it overflowed
-  unsigned int total = 0;
-  if (!settle_pool(b, &total, err)) return false;
-  if (total) CU_TRY(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)total * sizeof(OutRec), cudaMemcpyDeviceToHost, st));
-  pt.lap("fetch: sync");
-
-  // queries whose hit list overflowed are run again with an exact capacity
-  b->rr_which.clear();
-  b->rr_index.clear();
-  b->rr_heads.clear();
-  b->rr_recs.clear();
-  // (QF_UNSUPPORTED -- thresholded anagram distance above ANL_MAX_K, deletion neighbourhood beyond 2^31 -- is a
-  // property of that query alone: it comes back with an empty list and flag bit 1, the batch goes on)
-  for (uint32_t i = 0; i < n; ++i)
-    if ((b->h_flags[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) b->rr_which.push_back(i);
-  if (!b->rr_which.empty()) {
-    if (profile_enabled()) fprintf(stderr, "[anl profile] %zu queries overflowed hit_cap=%u\n", b->rr_which.size(), b->bp.hit_cap);
-    if (!rerun_launch(b, err, status)) return false;
-    b->reruns += b->rr_which.size();
-    b->rr_index.assign(n, -1);
-    for (size_t k = 0; k < b->rr_which.size(); ++k) b->rr_index[b->rr_which[k]] = (int32_t)k;
-  }
-  pt.lap("fetch: launch hit-overflow reruns");
-  b->fetch_begun = true;
-  *status = ANL_OK;
-  return true;
-}
-
-bool Engine::fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status) {
-  if (!b->fetch_begun && !fetch_begin(b, err, status)) return false;
-  b->fetch_begun = false;
-  *status = ANL_ERR_CUDA;
-  const uint32_t n = b->n;
-  PhaseTimer pt;
-  CU_TRY(cudaStreamSynchronize(b->stream));  // the D2H copy of the results
-  if (b->rr_pending && !rerun_collect(b, err, status)) return false;
-  *status = ANL_ERR_CUDA;
-  const std::vector<OutHead>& rr_heads = b->rr_heads;
-  const std::vector<OutRec>& rr_recs = b->rr_recs;
-  const std::vector<int32_t>& rr_index = b->rr_index;
-  pt.lap("fetch: D2H + collect reruns");
-
-  // host = the device did not (or could not) finish this query: confusable rescoring, re-rank, cut-off follow here
-  const bool post_pass = b->bp.finish_mode != FINISH_FULL;
-  auto locate = [&](uint32_t i, const OutRec** recs, uint32_t* count, double* maxf, bool* host) {
-    if (!rr_index.empty() && rr_index[i] >= 0) {
-      const OutHead& h = rr_heads[rr_index[i]];
-      *recs = rr_recs.data() + h.offset;
-      *count = h.count & ~HEAD_HOST_FINISH;
-      *maxf = h.max_freq;
-      *host = post_pass;  // reruns skip the device confusable stage
-    } else {
-      const OutHead& h = b->h_head[i];
-      *recs = b->h_out + h.offset;
-      *count = h.count & ~HEAD_HOST_FINISH;
-      *maxf = h.max_freq;
-      *host = post_pass && (!b->dev_conf || (h.count & HEAD_HOST_FINISH));
-    }
-  };
-  if (!append || out->offsets.empty()) {
-    out->offsets.assign(1, 0);
-    out->variants.clear();
-    out->flags.clear();
-  }
-  const size_t qbase = out->flags.size();      // queries already in `out`
-  const uint64_t vbase = out->variants.size();  // variants already in `out`
-  out->offsets.resize(qbase + (size_t)n + 1);
-  out->flags.resize(qbase + n, 0);
-  uint64_t* offs = out->offsets.data() + qbase;
-  for (uint32_t i = 0; i < n; ++i) {
-    if ((b->h_flags[i] & QF_EMPTY) && b->host_flags[i] == 0) out->flags[qbase + i] |= ANL_QUERY_EMPTY;
-    if ((b->h_flags[i] & QF_UNSUPPORTED) || b->host_flags[i] == 2) out->flags[qbase + i] |= ANL_QUERY_UNSUPPORTED;
-  }
-
-  // pass 1: queries the host must finish go through finish_query into per-thread side buffers; the
-  // counts of all other queries are final as they come from the device
-  const unsigned maxt = host_threads();
-  std::vector<std::vector<anl_variant>> part(post_pass ? maxt : 0);
-  std::vector<uint32_t> counts(n, 0), side_pos(post_pass ? n : 0, 0);
-  uint64_t host_queries = 0;
-  if (post_pass) {
-    std::vector<uint64_t> hq(maxt, 0);
-    parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
-      std::vector<anl_variant>& buf = part[t];
-      for (uint64_t i = lo; i < hi; ++i) {
-        const OutRec* r;
-        uint32_t c;
-        double mf;
-        bool host;
-        locate((uint32_t)i, &r, &c, &mf, &host);
-        if (!host) {
-          counts[i] = c;
-          continue;
-        }
-        const size_t before = buf.size();
-        finish_query(*b, i, r, c, mf, &buf);
-        side_pos[i] = (uint32_t)before;
-        counts[i] = (uint32_t)(buf.size() - before);
-        ++hq[t];
-      }
-    });
-    for (uint64_t v : hq) host_queries += v;
-  } else {
-    for (uint32_t i = 0; i < n; ++i) {
-      const OutRec* r;
-      double mf;
-      bool host;
-      locate(i, &r, &counts[i], &mf, &host);
-    }
-  }
-  uint64_t tot = vbase;
-  for (uint32_t i = 0; i < n; ++i) {
-    offs[i] = tot;
-    tot += counts[i];
-  }
-  offs[n] = tot;
-  out->variants.resize(tot);
-  // pass 2: convert / copy straight into place (same thread ranges as pass 1)
-  parallel_ranges(n, 512, [&](unsigned t, uint64_t lo, uint64_t hi) {
-    for (uint64_t i = lo; i < hi; ++i) {
-      const OutRec* r;
-      uint32_t c;
-      double mf;
-      bool host;
-      locate((uint32_t)i, &r, &c, &mf, &host);
-      anl_variant* dst = out->variants.data() + offs[i];
-      if (host) {
-        if (counts[i]) memcpy(dst, part[t].data() + side_pos[i], (size_t)counts[i] * sizeof(anl_variant));
-        continue;
-      }
-      for (uint32_t k = 0; k < c; ++k) {
-        // frequency normalisation (src/lib.rs:1521-1525): the same IEEE division the device ranked with
-        const double f = (double)r[k].freq;
-        dst[k] = anl_variant{r[k].vocab_id & ~OUT_SKIP_CONFUSABLES, r[k].dist_score, mf > 0.0 ? f / mf : f, ANL_NO_VIA};
-      }
-    }
-  });
-  b->results = tot - vbase;
-  pt.lap("fetch: post-pass+assemble");
-  if (profile_enabled() && b->bp.finish_mode != FINISH_FULL) {
-    uint64_t v[4];
-    confusable_stats(v);
-    fprintf(stderr, "[anl profile] %llu of %u queries finished on the host (device confusables: %s)\n",
-            (unsigned long long)host_queries, n, b->dev_conf ? "on" : "off");
-    fprintf(stderr, "[anl profile] confusable checks %llu, prefilter pass %llu (ascii), single-edit fast %llu, full script %llu\n",
-            (unsigned long long)v[0], (unsigned long long)v[1], (unsigned long long)v[2], (unsigned long long)v[3]);
-  }
-  *status = ANL_OK;
-  return true;
-}
-
-bool Engine::find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
-                                 ResultSet* out, std::string* err, int* status) {
-  // Chunks are pipelined over up to four batches with their own streams: while the GPU works on chunks
-  // i .. i+2 (kernel tails of one chunk overlap the next chunk's kernels), the host finishes chunk i-1 (D2H,
-  // confusable post-pass, assembly) and stages chunk i+3.
-  uint64_t CHUNK = 1u << 16;
-  if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
-  out->offsets.assign(1, 0);
-  out->variants.clear();
-  out->flags.clear();
-  if (n > CHUNK) {
-    out->variants.reserve((size_t)n * 8);
-    out->offsets.reserve((size_t)n + 1);
-    out->flags.reserve((size_t)n);
-  }
-  // Batches in flight, oldest first (each with its own streams).  Once DEPTH are queued the oldest is settled
-  // (fetch_begin: wait for its run, start the D2H copy, launch the re-run of overflowed queries) and the ones
-  // settled in earlier rounds are finished on the host, so a re-run does not have the host waiting for it.
-  size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
-  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(4, std::max(1, atoi(e)));
-  std::deque<DeviceBatch*> inflight;
-  std::deque<DeviceBatch*> settled;
-  bool ok = true;
-  auto fail_with = [&](const std::string& e2, int s2) {
-    if (ok) {
-      ok = false;
-      *err = e2;
-      *status = s2;
-    }
-  };
-  auto finish_front = [&]() {
-    DeviceBatch* f = settled.front();
-    settled.pop_front();
-    std::string e2;
-    int s2 = ANL_OK;
-    if (ok && !fetch_batch(f, out, true, &e2, &s2)) fail_with(e2, s2);
-    if (!ok) {
-      cudaStreamSynchronize(f->stream);
-      if (f->rr_stream) cudaStreamSynchronize(f->rr_stream);
-    }
-    free_batch(f);
-  };
-  auto settle_oldest = [&]() {
-    DeviceBatch* f = inflight.front();
-    inflight.pop_front();
-    std::string e2;
-    int s2 = ANL_OK;
-    if (ok && !fetch_begin(f, &e2, &s2)) fail_with(e2, s2);
-    settled.push_back(f);
-    // a re-run is a few warps with long dependent chains (milliseconds): it gets three rounds to complete
-    while (!settled.empty() && settled.size() > (settled.front()->rr_pending ? 3u : 1u)) finish_front();
-  };
-  for (uint64_t lo = 0; ok && (lo < n || (n == 0 && lo == 0)); lo += CHUNK) {
-    const uint64_t m = std::min(CHUNK, n - lo);
-    DeviceBatch* b = create_batch(blob, offsets + lo, m, p, false, false, err, status);
-    ok = b != nullptr;
-    if (ok && !run_batch(b, nullptr, err)) {
-      *status = ANL_ERR_CUDA;
-      ok = false;
-    }
-    if (b) inflight.push_back(b);
-    if (ok && inflight.size() >= DEPTH) settle_oldest();
-    if (n == 0) break;
-  }
-  while (!inflight.empty()) {
-    if (!ok) cudaStreamSynchronize(inflight.front()->stream);
-    settle_oldest();
-  }
-  while (!settled.empty()) finish_front();
+  b->settled = false;
   if (ok) *status = ANL_OK;
   return ok;
+}
+
+// ---- the batch call: chunks pipelined over one or more devices -------------------------------------------------
+namespace {
+struct CallShared {
+  ResultSet* out = nullptr;
+  uint64_t n_total = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  uint64_t next_chunk = 0;  // the chunk whose turn it is to take its place in `out`
+  uint64_t vbase = 0;       // variants placed so far
+  bool failed = false;
+  std::string err;
+  int status = ANL_OK;
+  std::vector<cudaStream_t> streams;  // every stream that has copied into `out`: synchronised before `out` moves
+};
+struct InFlight {
+  uint64_t chunk, q0;
+  DeviceBatch* b;
+};
+
+void fail_call(CallShared& S, const std::string& e, int status) {  // (S.m held)
+  if (!S.failed) {
+    S.failed = true;
+    S.err = e;
+    S.status = status ? status : ANL_ERR_CUDA;
+  }
+}
+
+// room for `need` variants in S.out; `hint` = what the whole call is expected to need (S.m held)
+bool reserve_variants(CallShared& S, uint64_t need, uint64_t hint) {
+  if (need <= S.out->variants.capacity()) return true;
+  for (cudaStream_t st : S.streams)
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+  S.out->variants.resize(S.vbase);  // (what reserve has to preserve)
+  S.out->variants.reserve(std::max<uint64_t>(need, hint));
+  return true;
+}
+
+// One device's share of the call: chunks d, d + D, d + 2D, ... with up to DEPTH of them in flight, each on its own
+// stream, so the kernel tails of one chunk overlap the next chunk's kernels and the downloads overlap both.
+// Every chunk index takes its turn exactly once -- also after a failure or an exception -- so no other device's
+// thread waits for a turn that never comes.
+void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const char* blob, const uint64_t* offsets, uint64_t n,
+                      const anl_search_params& p, uint64_t CHUNK, size_t DEPTH, uint64_t nchunks, uint64_t* next_turn,
+                      std::deque<InFlight>& running, std::deque<InFlight>& copying) {
+  auto finish_copy = [&]() {
+    InFlight f = copying.front();
+    copying.pop_front();
+    std::string e2;
+    if (!e->wait_download(f.b, &e2)) {
+      std::lock_guard<std::mutex> lk(S.m);
+      fail_call(S, e2, ANL_ERR_CUDA);
+    }
+    e->free_batch(f.b);
+  };
+  // settle the chunk, then -- when it is its turn -- give it its place in `out` and start the download
+  auto place = [&](InFlight f) {
+    std::string e2;
+    int s2 = ANL_OK;
+    bool ok = f.b != nullptr;
+    if (ok) {
+      bool skip;
+      {
+        std::lock_guard<std::mutex> lk(S.m);
+        skip = S.failed;
+      }
+      ok = !skip && e->settle(f.b, &e2, &s2);
+    }
+    std::unique_lock<std::mutex> lk(S.m);
+    S.cv.wait(lk, [&]() { return S.next_chunk == f.chunk; });
+    struct Advance {  // the turn passes on however this scope is left
+      CallShared& S;
+      std::unique_lock<std::mutex>& lk;
+      uint64_t* next_turn;
+      unsigned D;
+      ~Advance() {
+        if (!lk.owns_lock()) lk.lock();
+        ++S.next_chunk;
+        *next_turn += D;
+        lk.unlock();
+        S.cv.notify_all();
+      }
+    } advance{S, lk, next_turn, D};
+    if (ok && !S.failed) {
+      const uint32_t total = e->export_total(f.b);
+      // size the variants array from the first chunk's density (+ slack): later chunks then rarely move it
+      const uint64_t hint = f.b->n ? (uint64_t)((double)std::max<uint32_t>(total, 1) / f.b->n * (double)S.n_total * 1.15) + 65536 : 0;
+      if (e->needs_host_finish(f.b)) {
+        for (cudaStream_t st : S.streams) cudaStreamSynchronize(st);  // its variants may move
+        uint64_t written = 0;
+        ok = reserve_variants(S, S.vbase + total, hint) && e->finish_on_host(f.b, S.out, f.q0, S.vbase, &written, &e2, &s2);
+        if (ok) S.vbase += written;
+        S.out->variants.resize(S.vbase);
+      } else {
+        ok = reserve_variants(S, S.vbase + total, hint) && e->issue_download(f.b, S.out, f.q0, S.vbase, &e2);
+        if (ok) {
+          if (std::find(S.streams.begin(), S.streams.end(), f.b->stream) == S.streams.end()) S.streams.push_back(f.b->stream);
+          S.vbase += total;
+        }
+      }
+      if (!ok && e2.empty()) e2 = "out of memory for the result arrays";
+    }
+    if (!ok && f.b && !e2.empty()) fail_call(S, e2, s2);
+  };
+  auto place_front = [&]() {
+    InFlight f = running.front();
+    running.pop_front();
+    if (f.b) copying.push_back(f);  // (owned by `copying` from here on, whatever happens in place())
+    place(f);
+    while (copying.size() > 1) finish_copy();
+  };
+  for (uint64_t c = d; c < nchunks; c += D) {
+    const uint64_t lo = c * CHUNK, m = std::min(CHUNK, n - lo);
+    bool skip;
+    {
+      std::lock_guard<std::mutex> lk(S.m);
+      skip = S.failed;
+    }
+    DeviceBatch* b = nullptr;
+    if (!skip) {
+      std::string e2;
+      int s2 = ANL_OK;
+      b = e->create_batch(blob, offsets + lo, m, p, false, false, &e2, &s2);
+      if (b && !e->run_batch(b, nullptr, &e2)) {
+        s2 = ANL_ERR_CUDA;
+        cudaStreamSynchronize(b->stream);
+        e->free_batch(b);
+        b = nullptr;
+      }
+      if (!b) {
+        std::lock_guard<std::mutex> lk(S.m);
+        fail_call(S, e2, s2);
+      }
+    }
+    running.push_back(InFlight{c, lo, b});
+    while (running.size() >= DEPTH) place_front();
+  }
+  while (!running.empty()) place_front();
+  while (!copying.empty()) finish_copy();
+}
+
+void device_loop(Engine* e, unsigned d, unsigned D, CallShared& S, const char* blob, const uint64_t* offsets, uint64_t n,
+                 const anl_search_params& p, uint64_t CHUNK, size_t DEPTH) {
+  const uint64_t nchunks = n == 0 ? 1 : (n + CHUNK - 1) / CHUNK;
+  uint64_t next_turn = d;  // the next chunk of this device that has not taken its turn yet
+  std::deque<InFlight> running, copying;
+  try {
+    device_loop_body(e, d, D, S, blob, offsets, n, p, CHUNK, DEPTH, nchunks, &next_turn, running, copying);
+  } catch (const std::exception& ex) {
+    std::lock_guard<std::mutex> lk(S.m);
+    fail_call(S, std::string("internal error: ") + ex.what(), ANL_ERR_INVALID);
+  } catch (...) {
+    std::lock_guard<std::mutex> lk(S.m);
+    fail_call(S, "internal error: unknown exception", ANL_ERR_INVALID);
+  }
+  // after an exception: pass on the turns this device still owes, release what is in flight
+  for (uint64_t c = next_turn; c < nchunks; c += D) {
+    std::unique_lock<std::mutex> lk(S.m);
+    S.cv.wait(lk, [&]() { return S.next_chunk == c; });
+    ++S.next_chunk;
+    lk.unlock();
+    S.cv.notify_all();
+  }
+  for (std::deque<InFlight>* q : {&running, &copying})
+    for (InFlight& f : *q)
+      if (f.b) {
+        cudaStreamSynchronize(f.b->stream);
+        e->free_batch(f.b);
+      }
+}
+}  // namespace
+
+bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* blob, const uint64_t* offsets, uint64_t n,
+                               const anl_search_params& p, ResultSet* out, std::string* err, int* status) {
+  const unsigned D = (unsigned)engines.size();
+  if (D == 0) {
+    *err = "model has not been built";
+    *status = ANL_ERR_NOT_BUILT;
+    return false;
+  }
+  // Chunks of 65536 queries: large enough for the persistent grids to fill the device, small enough that several are
+  // in flight per device and the first results come back early.
+  uint64_t CHUNK = 1u << 16;
+  if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
+  size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
+  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(8, std::max(1, atoi(e)));
+  CallShared S;
+  S.out = out;
+  S.n_total = n;
+  out->offsets.resize((size_t)n + 1);
+  out->flags.resize(std::max<uint64_t>(n, 1));
+  out->flags.resize(n);
+  out->variants.clear();
+  const uint64_t nchunks = n == 0 ? 1 : (n + CHUNK - 1) / CHUNK;
+  const unsigned used = (unsigned)std::min<uint64_t>(D, nchunks);
+  if (used <= 1) {
+    device_loop(engines[0], 0, 1, S, blob, offsets, n, p, CHUNK, DEPTH);
+  } else {
+    // one dispatcher thread per device (their host phases run inline: the shared pool serves one job at a time)
+    std::vector<std::thread> th;
+    for (unsigned d = 1; d < used; ++d)
+      th.emplace_back([&, d]() {
+        serial_ranges_flag() = true;
+        device_loop(engines[d], d, used, S, blob, offsets, n, p, CHUNK, DEPTH);
+      });
+    const bool was = serial_ranges_flag();
+    serial_ranges_flag() = true;
+    device_loop(engines[0], 0, used, S, blob, offsets, n, p, CHUNK, DEPTH);
+    serial_ranges_flag() = was;
+    for (auto& t : th) t.join();
+  }
+  if (S.failed) {
+    *err = S.err;
+    *status = S.status;
+    return false;
+  }
+  out->offsets[n] = S.vbase;
+  out->variants.resize(S.vbase);
+  *status = ANL_OK;
+  return true;
 }
 
 }  // namespace anl

@@ -1,10 +1,11 @@
-// engine.h -- device residency and the batched lookup pipeline (H2D, two kernels, D2H, host post-pass).
+// engine.h -- device residency of the index and the batched lookup pipeline (H2D, kernels, export, D2H).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -17,15 +18,16 @@
 
 namespace anl {
 
+// Vec<Vec<VariantResult>> as a CSR in DMA-able host memory: the export stage's arrays land here by D2H copy.
 struct ResultSet {
-  std::vector<uint64_t> offsets;  // n + 1
-  PodBuffer<anl_variant> variants;
-  std::vector<uint32_t> flags;  // per query: bit 0 = empty input
+  DmaBuffer<uint64_t> offsets;  // n + 1
+  DmaBuffer<anl_variant> variants;
+  DmaBuffer<uint32_t> flags;  // per query: ANL_QUERY_* bits
 };
 
 // Everything one pass over a batch of queries needs, on the device and in pinned host memory.
 // Buffers are capacity-based and recycled through Engine's cache: steady-state calls allocate nothing.
-static const int EV_PER_RUN = 7;
+static const int EV_PER_RUN = 8;
 struct DeviceBatch {
   // ---- capacities (what the buffers can hold) ----
   uint32_t cap_n = 0, cap_pool = 0;
@@ -37,14 +39,15 @@ struct DeviceBatch {
   const char* blob = nullptr;  // raw queries (borrowed for the duration of the call, or owned_blob)
   std::string owned_blob;
   std::vector<uint64_t> offsets;    // n + 1, relative to blob
-  std::vector<uint8_t> host_flags;  // per query: 1 = resolved on the host as empty, 2 = unsupported length
+  std::vector<uint8_t> host_flags;  // per query: ENC_* (1 = too long, empty by construction; 2 = too long, unsupported)
   // pinned host buffers
   uint8_t* h_rows = nullptr;   // [cap_n][cap_stride]
   OutHead* h_head = nullptr;   // [cap_n]
   uint32_t* h_flags = nullptr; // [cap_n]
   uint32_t* h_hitcnt = nullptr;// [cap_n]
   OutRec* h_out = nullptr;     // [cap_pool]
-  unsigned int* h_work = nullptr;  // [4]
+  unsigned int* h_work = nullptr;  // [8]
+  ExportSummary* h_summary = nullptr;
   // device buffers
   uint8_t* d_rows = nullptr;
   uint8_t* d_qblob = nullptr;   // raw query bytes (encode kernel, confusable stage), grow-only
@@ -57,7 +60,7 @@ struct DeviceBatch {
   QCtx* d_qctx = nullptr;           //                   per-query context of the exact stage
   size_t cap_queue = 0, cap_qctx = 0;
   bool split = false;               // use the split probe path for this batch
-  uint8_t* d_enc_status = nullptr;  // per query: ENC_* result of the encode kernel
+  uint8_t* d_enc_status = nullptr;  // per query: ENC_* result of the encode kernel (or of the host encoder)
   uint8_t* h_enc_status = nullptr;
   bool dev_encode = false;          // the rows of this batch were encoded on the device
   ConfWork* d_conf_work = nullptr;  // queue of (record, query) pairs for the confusable kernel, sized like d_out
@@ -71,6 +74,13 @@ struct DeviceBatch {
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
   Counters* d_counters = nullptr;
+  // export stage (export.cu): final arrays of this batch, in query order
+  anl_variant* d_final = nullptr;   // [cap_pool]
+  uint32_t* d_loff = nullptr;       // [cap_n + 1] batch-local CSR offsets
+  uint32_t* d_oflags = nullptr;     // [cap_n]
+  uint64_t* d_off64 = nullptr;      // [cap_n] call-wide offsets (written when the batch's base is known)
+  uint32_t* d_tile_sum = nullptr;   // [export_tiles(cap_n)]
+  ExportSummary* d_summary = nullptr;
   // buffers of the hit-overflow rerun (queries with more than hit_cap candidate instances), grow-only
   uint32_t* rr_qlist = nullptr;
   uint32_t* rr_hits = nullptr;
@@ -78,34 +88,27 @@ struct DeviceBatch {
   uint32_t* rr_qflags = nullptr;
   OutHead* rr_head = nullptr;
   OutRec* rr_out = nullptr;
+  ConfWork* rr_conf_work = nullptr;
   uint8_t* rr_scratch = nullptr;
+  unsigned int* rr_work = nullptr;  // [8] the rerun's own counters (the batch's hold its pool cursor)
   size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;
   cudaStream_t stream = nullptr;    // this batch's own stream (copies + default launches)
   cudaEvent_t uploaded = nullptr;   // recorded after the H2D copy of the query rows
   cudaStream_t aux = nullptr;       // side stream: the long-query class of the score kernel runs beside the short one
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_merged = nullptr;  // end of shard_merge
+  cudaEvent_t ev_done = nullptr;    // end of the most recent chain that is not one of the per-run timing events
   // EV_PER_RUN events (start, after the Bloom stage, after probe, after prefilter, after score, after confusables,
-  // after finish) per run since the last timings() call
+  // after finish, after export) per run since the last timings() call
   std::vector<cudaEvent_t> events;
   uint32_t runs_recorded = 0;
   cudaEvent_t last_done = nullptr;  // end event of the most recent run
   bool ran = false;
+  bool settled = false;        // the summary of the last run has been read and every exception it reported is dealt with
   bool sharded = false;        // built against a lexicon shard: results come from shard_export / shard_merge
   bool merged = false;         // shard_merge has produced the final lists in d_out / d_head
   int final_mode = FINISH_FULL;  // finish mode of the merged result (bp.finish_mode is FINISH_SHARD while scoring)
   uint64_t reruns = 0;
   uint64_t results = 0;
-  // fetch in two phases (fetch_begin / fetch_batch): queries whose hit list overflowed are run again on a
-  // high-priority stream between the two, while the host works on other chunks
-  bool fetch_begun = false;
-  bool rr_pending = false;
-  cudaStream_t rr_stream = nullptr;
-  BatchParams rr_bp;
-  std::vector<uint32_t> rr_which;
-  std::vector<OutHead> rr_heads;
-  std::vector<OutRec> rr_recs;
-  std::vector<int32_t> rr_index;
 };
 
 class Engine {
@@ -121,15 +124,26 @@ class Engine {
   // sync: wait for the H2D copy before returning (otherwise it is ordered before the kernels by an event)
   DeviceBatch* create_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p,
                             bool copy_blob, bool sync, std::string* err, int* status);
+  // one pass: probe, prefilter, score, confusables, finish, export -- ends with the (async) download of the summary
   bool run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err);
-  // append: add this batch's queries after the ones already in `out` (pipelined chunks)
-  // first phase of a fetch (optional; fetch_batch runs it when the caller has not): waits for the run, starts the
-  // D2H copy of the results and launches the re-run of queries whose hit list overflowed, without waiting for it
-  bool fetch_begin(DeviceBatch* b, std::string* err, int* status);
-  bool fetch_batch(DeviceBatch* b, ResultSet* out, bool append, std::string* err, int* status);
+  // Waits for the run and deals with everything its summary reports: result pool / staged-node queue overflows
+  // (re-run with larger buffers) and hit-list overflows (those queries are run again with an exact capacity and
+  // patched into the pool).  Afterwards the export arrays of the batch are final unless needs_host_finish().
+  bool settle(DeviceBatch* b, std::string* err, int* status);
+  bool needs_host_finish(const DeviceBatch* b) const;
+  uint32_t export_total(const DeviceBatch* b) const { return b->h_summary->total; }
+  // fast path: D2H of the export arrays into out[qbase ..] / variants[vbase ..] on the batch's stream (no wait)
+  bool issue_download(DeviceBatch* b, ResultSet* out, uint64_t qbase, uint64_t vbase, std::string* err);
+  // slow path: queries the device could not finish go through the host post-pass; writes the batch's part of `out`
+  // (whose variants may grow) and returns the number of variants written
+  bool finish_on_host(DeviceBatch* b, ResultSet* out, uint64_t qbase, uint64_t vbase, uint64_t* written, std::string* err,
+                      int* status);
+  bool wait_download(DeviceBatch* b, std::string* err);
+  // settle + download + wait into a fresh result set (device-batch API, sharded merge)
+  bool fetch_batch(DeviceBatch* b, ResultSet* out, std::string* err, int* status);
   void free_batch(DeviceBatch* b);  // returns the buffers to the cache
-  // stage_ms[6]: Bloom stage, exact stage (the whole fused probe kernel when the split path is off), prefilter,
-  // score/rank, confusables, finish
+  // stage_ms[7]: Bloom stage, exact stage (the whole fused probe kernel when the split path is off), prefilter,
+  // score/rank, confusables, finish, export
   bool timings(DeviceBatch* b, float* stage_ms, std::string* err);
   bool counters(DeviceBatch* b, anl_counters* out, std::string* err);
 
@@ -140,13 +154,11 @@ class Engine {
                    const void* d_gids_all, const void* d_flags_all, uint64_t record_stride, uint32_t max_survivors,
                    ResultSet* out, std::string* err, int* status);
 
-  // whole pipeline with internal chunking
-  bool find_variants_batch(const char* blob, const uint64_t* offsets, uint64_t n, const anl_search_params& p, ResultSet* out,
-                           std::string* err, int* status);
-
   const DeviceIndex& host_view() const { return h_ix_; }
   bool uploaded() const { return d_ix_ != nullptr; }
   cudaStream_t stream() const { return stream_; }
+  int device() const { return device_; }
+  HostModel* host_model() const { return hm_; }
 
  private:
   // post-pass of one query's device records -> final variants (confusables, re-sort, cut-off); appends to `out`
@@ -154,12 +166,11 @@ class Engine {
                              std::vector<anl_variant>* out) const;
   void finish_query(const DeviceBatch& b, uint64_t qi, const OutRec* recs, uint32_t count, double max_freq,
                     std::vector<anl_variant>* out) const;
-  bool rerun_launch(DeviceBatch* b, std::string* err, int* status);   // b->rr_which -> kernels on b->rr_stream
-  bool rerun_collect(DeviceBatch* b, std::string* err, int* status);  // sync; b->rr_heads / b->rr_recs
+  bool rerun_overflowed(DeviceBatch* b, std::string* err, int* status);  // hit-list overflows: re-run, patch, re-export
+  bool launch_export_chain(DeviceBatch* b, cudaStream_t st, std::string* err);
   bool ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
                        std::string* err);
-  bool grow_pool(DeviceBatch* b, uint32_t pool_cap, std::string* err);
-  bool settle_pool(DeviceBatch* b, unsigned int* total, std::string* err);  // sync; grow + re-score on pool overflow
+  bool grow_pool(DeviceBatch* b, uint32_t pool_cap, bool keep_records, std::string* err);
   void destroy_batch(DeviceBatch* b);
   void release_index();
 
@@ -174,7 +185,15 @@ class Engine {
   std::vector<void*> conf_allocs_;
   size_t conf_uploaded_ = (size_t)-1;  // number of confusables the device table was built from
   size_t conf_vocab_ = 0;              // vocabulary size the device text blob was built from
+  std::mutex cache_m_;
   std::vector<DeviceBatch*> cache_;  // idle batches whose buffers can be reused
 };
+
+// anl_find_variants_batch over one or more replicas of the index (one Engine per device): the batch is cut into chunks
+// that go round-robin to the devices, every device is driven by its own host thread with several chunks in flight,
+// and the chunks' result arrays land in `out` in query order.  src/bin/analiticcl.rs:418-482 (process_par) is the
+// reference's counterpart: rayon over the queries of one process.
+bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* blob, const uint64_t* offsets, uint64_t n,
+                               const anl_search_params& p, ResultSet* out, std::string* err, int* status);
 
 }  // namespace anl

@@ -8,6 +8,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <functional>
 #include <mutex>
@@ -93,6 +94,63 @@ class PodBuffer {
   size_t n_ = 0, cap_ = 0;
 };
 
+
+// Result arrays the GPU writes by DMA (anl_result_set): page-locked blocks from a process-wide recycler (pinning
+// hundreds of MB costs tens of ms; a recycled block is pinned already).  Falls back to plain memory when the
+// CUDA runtime cannot pin (then the copies are staged by the driver: slower, still correct).  engine.cu.
+void* dma_block_take(size_t min_bytes, size_t* got_bytes, bool* pinned);
+void dma_block_give(void* p, size_t bytes, bool pinned);
+
+// Growable POD array in DMA-able host memory.  resize() keeps the contents and never initialises new elements.
+template <class T>
+class DmaBuffer {
+ public:
+  DmaBuffer() = default;
+  DmaBuffer(const DmaBuffer&) = delete;
+  DmaBuffer& operator=(const DmaBuffer&) = delete;
+  ~DmaBuffer() { release(); }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+  size_t capacity() const { return cap_; }
+  bool empty() const { return n_ == 0; }
+  void clear() { n_ = 0; }
+  void release() {
+    if (p_) dma_block_give(p_, cap_ * sizeof(T), pinned_);
+    p_ = nullptr;
+    n_ = cap_ = 0;
+  }
+  // NOTE: moves the block when it grows -- the caller makes sure no DMA into the old block is in flight
+  void reserve(size_t c) {
+    if (c <= cap_) return;
+    size_t got = 0;
+    bool pinned = false;
+    T* q = static_cast<T*>(dma_block_take(c * sizeof(T), &got, &pinned));
+    if (!q) throw std::bad_alloc();
+    if (p_) {
+      if (n_) memcpy(q, p_, n_ * sizeof(T));
+      dma_block_give(p_, cap_ * sizeof(T), pinned_);
+    }
+    p_ = q;
+    cap_ = got / sizeof(T);
+    pinned_ = pinned;
+  }
+  void resize(size_t n) {
+    if (n > cap_) reserve(std::max(n, cap_ + cap_ / 2));
+    n_ = n;
+  }
+  void assign(size_t n, const T& v) {
+    resize(n);
+    for (size_t i = 0; i < n; ++i) p_[i] = v;
+  }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+  bool pinned_ = false;
+};
 
 inline bool profile_enabled() {
   static int v = -1;
@@ -212,10 +270,17 @@ class HostPool {
   uint64_t gen_ = 0;
 };
 
+// A dispatcher thread of a multi-device call sets this: its host phases run inline (every device has its own
+// thread already; the shared pool serves one job at a time).
+inline bool& serial_ranges_flag() {
+  static thread_local bool f = false;
+  return f;
+}
+
 // fn(thread index, lo, hi) over [0, n) split into contiguous ranges, one per thread
 template <class F>
 inline unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F fn) {
-  unsigned nt = host_threads();
+  unsigned nt = serial_ranges_flag() ? 1u : host_threads();
   const uint64_t mp = std::max<uint64_t>(1, min_per_thread);
   if (n / mp < nt) nt = (unsigned)std::max<uint64_t>(1, n / mp);
   if (nt <= 1) {

@@ -25,29 +25,26 @@
 
 #include <algorithm>
 
+#include <atomic>
+
 #include "device_types.h"
 #include "editscript_fixed.h"
+#include "kernel_common.cuh"
 #include "kernels.h"
 
 namespace anl {
 
-// process-wide count of kernel launches issued by this library (bench.py reports it as gpu_launches)
-static unsigned long long g_kernel_launches = 0;
-unsigned long long kernel_launches() { return g_kernel_launches; }
+// process-wide count of kernel launches issued by this library (bench.py reports it as gpu_launches); atomic: with
+// several devices every device has its own dispatcher thread
+static std::atomic<unsigned long long> g_kernel_launches{0};
+unsigned long long kernel_launches() { return g_kernel_launches.load(std::memory_order_relaxed); }
+void count_launch(unsigned n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 long long merge_grid(int sm_count, uint32_t n);
-
-#define FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ uint32_t lanemask_lt() {
-  uint32_t m;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
 
 // DistanceThreshold -> absolute distance for an input of `len` symbols (src/lib.rs:982-1012).
 __device__ __forceinline__ uint32_t apply_threshold(const Threshold& t, uint32_t len) {
@@ -1245,51 +1242,133 @@ __device__ __forceinline__ bool ranks_before(const BatchParams& bp, bool gather_
 }
 
 // Triage of one (input a, candidate b) pair for confusable rescoring.
-//   CONF_SETTLED : provably no pattern can match (necessary condition on the pair's "middle") -> weight 1
+//   CONF_SETTLED : the weight is known -- no pattern can match (necessary condition on the pair's "middle"), or the
+//                  middles share no character and the patterns are simple, so the script is =[p]-[ma]+[mb]=[s]
 //   CONF_QUEUE   : a pattern may match -> the confusable kernel computes the edit script
-//   CONF_HOST    : non-ASCII text or longer than the device edit script handles -> host post-pass
+//   CONF_HOST    : text outside the BMP or longer than the device edit script handles -> host post-pass
 constexpr int CONF_SETTLED = 0, CONF_QUEUE = 1, CONF_HOST = 2;
-__device__ __forceinline__ int confusable_triage(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
-                                                 const uint8_t* __restrict__ b, uint32_t nb) {
-  uint32_t hibits = 0;
+constexpr uint32_t CONF_FAST_MAX = 8;  // longest middle (characters) the on-the-spot path decodes
+
+__device__ __forceinline__ bool u8_cont(uint32_t byte) { return (byte & 0xC0u) == 0x80u; }
+// decodes the BMP characters of s[0, n) (valid UTF-8 of at most three bytes per character) into out[0, cap)
+__device__ __forceinline__ uint32_t u8_decode_bmp(const uint8_t* __restrict__ s, uint32_t n, uint16_t* out, uint32_t cap) {
+  uint32_t c = 0, i = 0;
+  while (i < n && c < cap) {
+    const uint32_t b0 = s[i];
+    uint32_t cp = b0, l = 1;
+    if (b0 >= 0xE0) {
+      l = 3;
+      cp = b0 & 0x0F;
+    } else if (b0 >= 0xC0) {
+      l = 2;
+      cp = b0 & 0x1F;
+    }
+    for (uint32_t k = 1; k < l && i + k < n; ++k) cp = (cp << 6) | (s[i + k] & 0x3Fu);
+    out[c++] = (uint16_t)cp;
+    i += l;
+  }
+  return c;
+}
+
+__device__ __noinline__ int confusable_triage(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
+                                              const uint8_t* __restrict__ b, uint32_t nb, double* weight, uint32_t* cost) {
+  *weight = 1.0;
+  *cost = 0;
+  // characters per string; a four-byte sequence (lead byte >= 0xF0) lies outside the BMP
+  uint32_t ca = 0, cb = 0, big = 0;
 #pragma unroll 1
-  for (uint32_t i = 0; i < na; ++i) hibits |= a[i];
+  for (uint32_t i = 0; i < na; ++i) {
+    const uint32_t ch = a[i];
+    ca += !u8_cont(ch);
+    big |= ch >= 0xF0;
+  }
 #pragma unroll 1
-  for (uint32_t i = 0; i < nb; ++i) hibits |= b[i];
-  if (hibits & 0x80) return CONF_HOST;
+  for (uint32_t i = 0; i < nb; ++i) {
+    const uint32_t ch = b[i];
+    cb += !u8_cont(ch);
+    big |= ch >= 0xF0;
+  }
+  if (big) return CONF_HOST;
+  // common prefix / suffix in bytes, moved back to character boundaries (the strings agree up to there, so a
+  // boundary of one is a boundary of the other)
   uint32_t p = 0;
   const uint32_t m = min(na, nb);
   while (p < m && a[p] == b[p]) ++p;
+  while (p > 0 && ((p < na && u8_cont(a[p])) || (p < nb && u8_cont(b[p])))) --p;
   uint32_t s = 0;
   while (s < m - p && a[na - 1 - s] == b[nb - 1 - s]) ++s;
+  while (s > 0 && u8_cont(a[na - s])) --s;
+  const uint32_t ea = na - s, eb = nb - s;  // the middles: a[p, ea), b[p, eb)
   uint64_t alo = 0, ahi = 0, blo = 0, bhi = 0;
+  uint32_t la = 0, lb = 0, wide_a = 0, wide_b = 0;
 #pragma unroll 1
-  for (uint32_t i = p; i < na - s; ++i) {
+  for (uint32_t i = p; i < ea; ++i) {
     const uint32_t ch = a[i];
-    if (ch < 64) alo |= 1ull << ch; else ahi |= 1ull << (ch - 64);
+    la += !u8_cont(ch);
+    if (ch >= 0x80) wide_a = 1;
+    else if (ch < 64) alo |= 1ull << ch;
+    else ahi |= 1ull << (ch - 64);
   }
 #pragma unroll 1
-  for (uint32_t i = p; i < nb - s; ++i) {
+  for (uint32_t i = p; i < eb; ++i) {
     const uint32_t ch = b[i];
-    if (ch < 64) blo |= 1ull << ch; else bhi |= 1ull << (ch - 64);
+    lb += !u8_cont(ch);
+    if (ch >= 0x80) wide_b = 1;
+    else if (ch < 64) blo |= 1ull << ch;
+    else bhi |= 1ull << (ch - 64);
   }
+  bool possible = false;
 #pragma unroll 1
-  for (uint32_t k = 0; k < ix->n_conf_pats; ++k) {
+  for (uint32_t k = 0; k < ix->n_conf_pats && !possible; ++k) {
     const ConfPat pat = ix->conf_pats[k];
-    bool possible = true;
-    for (uint32_t q = 0; q < pat.n_instr && possible; ++q) {
+    bool can = true;
+    for (uint32_t q = 0; q < pat.n_instr && can; ++q) {
       const ConfInstr ins = ix->conf_instrs[pat.first_instr + q];
       if (ins.op == 0) continue;  // identities impose nothing on the middle
       const uint64_t slo = ins.op < 0 ? alo : blo, shi = ins.op < 0 ? ahi : bhi;
+      const uint32_t swide = ins.op < 0 ? wide_a : wide_b;
       bool any = false;
       for (uint32_t o = 0; o < ins.n_opts && !any; ++o) {
         const ConfOpt opt = ix->conf_opts[ins.first_opt + o];
-        any = ((opt.lo & ~slo) | (opt.hi & ~shi)) == 0;
+        any = ((opt.lo & ~slo) | (opt.hi & ~shi)) == 0 && (!opt.nonascii || swide);
       }
-      possible = any;
+      can = any;
     }
-    if (possible) return (na > (uint32_t)esf::MAXLEN || nb > (uint32_t)esf::MAXLEN) ? CONF_HOST : CONF_QUEUE;
+    possible = can;
   }
+  if (!possible) return CONF_SETTLED;
+  if (ca > (uint32_t)esf::MAXLEN || cb > (uint32_t)esf::MAXLEN) return CONF_HOST;
+  *cost = la + lb;
+  // On the spot: middles without a common character (a lone insertion / deletion only when it is one character: a
+  // longer one may be slid over equal neighbours by the clean-up passes, which rotates its text).
+  if (!ix->conf_all_simple || la > CONF_FAST_MAX || lb > CONF_FAST_MAX || (la == 0 && lb != 1) || (lb == 0 && la != 1))
+    return CONF_QUEUE;
+  uint16_t ma[CONF_FAST_MAX], mb[CONF_FAST_MAX];
+  u8_decode_bmp(a + p, ea - p, ma, CONF_FAST_MAX);
+  u8_decode_bmp(b + p, eb - p, mb, CONF_FAST_MAX);
+  for (uint32_t i = 0; i < la; ++i)
+    for (uint32_t j = 0; j < lb; ++j)
+      if (ma[i] == mb[j]) return CONF_QUEUE;
+  // the script: [=prefix] [-ma] [+mb] [=suffix]; simple patterns never look at the text of an identity
+  esf::View v[4];
+  int nv = 0;
+  if (p) v[nv++] = esf::View{esf::EQ, 1, 0, 0};
+  if (la) v[nv++] = esf::View{esf::DEL, (uint8_t)la, 0, 0};
+  if (lb) v[nv++] = esf::View{esf::INS, (uint8_t)lb, 0, 0};
+  if (s) v[nv++] = esf::View{esf::EQ, 1, 0, 0};
+  esf::PatTable T;
+  T.pats = ix->conf_pats;
+  T.instrs = ix->conf_instrs;
+  T.opts = ix->conf_opts;
+  T.text = ix->conf_text;
+  T.n_pats = ix->n_conf_pats;
+  double w = 1.0;
+#pragma unroll 1
+  for (uint32_t k = 0; k < T.n_pats; ++k) {
+    const ConfPat pat = T.pats[k];
+    if (esf::found_in(T, pat, ma, mb, v, nv)) w = __dmul_rn(w, pat.weight);
+  }
+  *weight = w;
   return CONF_SETTLED;
 }
 
@@ -1415,16 +1494,21 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
       const uint32_t i = i0 + lane;
       bool queue = false;
+      uint32_t cost = 0;
       if (i < n) {
         const SurvRec r = sorted[i];
         OutRec o;
         o.dist_score = r.dist;
         o.vocab_id = r.vocab;
         if (cs.qraw) {
-          // confusable triage: settle the pairs no pattern can match, queue the rest for the confusable kernel
+          // confusable triage: settle the pairs whose weight is known here, queue the rest for the confusable kernel
           const uint32_t t0 = __ldg(cs.ix->vocab_text_off + r.vocab), t1 = __ldg(cs.ix->vocab_text_off + r.vocab + 1);
-          const int tri = confusable_triage(cs.ix, cs.qraw, cs.qraw_len, cs.ix->vocab_text + t0, t1 - t0);
-          if (tri == CONF_SETTLED) o.vocab_id |= OUT_SKIP_CONFUSABLES;
+          double w;
+          const int tri = confusable_triage(cs.ix, cs.qraw, cs.qraw_len, cs.ix->vocab_text + t0, t1 - t0, &w, &cost);
+          if (tri == CONF_SETTLED) {
+            o.vocab_id |= OUT_SKIP_CONFUSABLES;
+            if (w != 1.0) o.dist_score = __dmul_rn(r.dist, w);  // src/lib.rs:1660
+          }
           queue = tri == CONF_QUEUE;
         }
         o.freq = r.raw;
@@ -1441,6 +1525,8 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
             ConfWork w;
             w.rec = off + i;
             w.query = cs.qrow;
+            w.cost = cost;
+            w.pad = 0;
             cs.worklist[wbase + __popc(qm & lanemask_lt())] = w;  // capacity = pool capacity >= records emitted
           }
         }
@@ -1969,13 +2055,46 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
 // Kernels 4 + 5 (only with confusables): device-side rescoring of the ranked lists
 // ================================================================================================
 // confusable_kernel: one queued (input, candidate) pair per thread.  Computes the edit script of the raw
-// strings and the product of the weights of all patterns found in it (rescore_confusables /
-// compute_confusable_weight, src/lib.rs:1656-1663,1733-1756), multiplies the record's distance score and
-// marks it settled.  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
-__global__ void __launch_bounds__(64)
+// strings (as UTF-16 code units: every character of the Basic Multilingual Plane is one unit) and the product of the
+// weights of all patterns found in it (rescore_confusables / compute_confusable_weight, src/lib.rs:1656-1663,
+// 1733-1756), multiplies the record's distance score and marks it settled.  Pairs outside the limits of
+// editscript_fixed.h stay unsettled (host post-pass).
+//
+// The diff's loops are data dependent: lanes of a warp that hold pairs of very different size idle most of the time
+// (ncu, round 1: 4.5 of 32 lanes active).  A CTA therefore takes a tile of CK_TILE queued pairs, sorts them by the
+// size of their middles (the triage stored it) in shared memory, and hands neighbours in that order to the lanes.
+constexpr int CK_THREADS = 128;
+constexpr int CK_TILE = 512;
+// Unicode Alphabetic ranges (boundary scores of the diff clean-up, cf. UnicodeClass in editscript.cpp)
+__constant__ uint32_t c_alpha_ranges[2 * 800];
+__constant__ uint32_t c_n_alpha_ranges;
+struct DeviceCharClass {
+  static __device__ __forceinline__ bool alnum(uint32_t c) {
+    if (c < 0x80) return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+    uint32_t lo = 0, hi = c_n_alpha_ranges;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (c > c_alpha_ranges[2 * mid + 1]) lo = mid + 1; else hi = mid;
+    }
+    return lo < c_n_alpha_ranges && c >= c_alpha_ranges[2 * lo];
+  }
+  static __device__ __forceinline__ bool space(uint32_t c) {
+    return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+           c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+  }
+};
+cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n) {
+  if (n > 800) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbol(c_alpha_ranges, ranges, (size_t)n * 2 * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_n_alpha_ranges, &n, sizeof n);
+}
+
+__global__ void __launch_bounds__(CK_THREADS)
 confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
                   const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
                   OutRec* __restrict__ out) {
+  __shared__ uint32_t keys[CK_TILE];
   const uint32_t total = min(*work_count, work_cap);
   esf::PatTable T;
   T.pats = ix->conf_pats;
@@ -1985,30 +2104,53 @@ confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict_
   T.n_pats = ix->n_conf_pats;
   const uint8_t* __restrict__ vtext = ix->vocab_text;
   const uint32_t* __restrict__ voff = ix->vocab_text_off;
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-    const ConfWork it = worklist[w];
-    const OutRec r = out[it.rec];
-    const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
-    const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
-    const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
-    // private copies: the diff touches every character many times
-    uint8_t a[esf::MAXLEN], b[esf::MAXLEN];
-    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
-    if (na > esf::MAXLEN || nb > esf::MAXLEN) continue;
-    for (int i = 0; i < na; ++i) a[i] = qblob[a0 + i];
-    for (int i = 0; i < nb; ++i) b[i] = vtext[b0 + i];
-    esf::View v[esf::MAXSEG];
-    const int nv = esf::shortest_edit_script(a, na, b, nb, v);
-    if (nv < 0) continue;
-    double weight = 1.0;
-    for (uint32_t k = 0; k < T.n_pats; ++k) {
-      const ConfPat pat = T.pats[k];
-      if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
+  for (uint32_t t0 = blockIdx.x * CK_TILE; t0 < total; t0 += gridDim.x * CK_TILE) {
+    // key = cost << 9 | position in the tile; slots beyond the queue sort to the end
+    for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE; k += CK_THREADS) {
+      const uint32_t w = t0 + k;
+      keys[k] = w < total ? (min(worklist[w].cost, 0x3FFFFFu) << 9) | k : 0xFFFFFFFFu;
     }
-    OutRec o = r;
-    if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
-    o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
-    out[it.rec] = o;
+    __syncthreads();
+    for (uint32_t size = 2; size <= (uint32_t)CK_TILE; size <<= 1)
+      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE / 2; k += CK_THREADS) {
+          const uint32_t lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const uint32_t x = keys[lo], y = keys[hi];
+          if ((x > y) == up) {
+            keys[lo] = y;
+            keys[hi] = x;
+          }
+        }
+        __syncthreads();
+      }
+    for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE; k += CK_THREADS) {
+      const uint32_t key = keys[k];
+      if (key == 0xFFFFFFFFu) continue;
+      const ConfWork it = worklist[t0 + (key & 511u)];
+      const OutRec r = out[it.rec];
+      const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
+      const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
+      const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
+      // private copies: the diff touches every character many times
+      uint16_t a[esf::MAXLEN], b[esf::MAXLEN];
+      if (a1 - a0 > 3u * esf::MAXLEN || b1 - b0 > 3u * esf::MAXLEN) continue;  // (the triage checked the character counts)
+      const int na = (int)u8_decode_bmp(qblob + a0, a1 - a0, a, esf::MAXLEN);
+      const int nb = (int)u8_decode_bmp(vtext + b0, b1 - b0, b, esf::MAXLEN);
+      esf::View v[esf::MAXSEG];
+      const int nv = esf::shortest_edit_script_t<DeviceCharClass, uint16_t>(a, na, b, nb, v);
+      if (nv < 0) continue;
+      double weight = 1.0;
+      for (uint32_t p = 0; p < T.n_pats; ++p) {
+        const ConfPat pat = T.pats[p];
+        if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
+      }
+      OutRec o = r;
+      if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
+      o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
+      out[it.rec] = o;
+    }
+    __syncthreads();  // (the keys are overwritten by the next tile)
   }
 }
 
@@ -2286,11 +2428,10 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
                                cudaStream_t stream) {
   if (lb.n == 0 || !lb.conf_work) return cudaSuccess;
-  // one thread per possible work item (the queue length is only known on the device): threads beyond the
-  // queue exit at once, and the long, divergent per-pair work is balanced by the block scheduler
-  unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
+  // the queue length is only known on the device: a grid that covers the device walks the queue tile by tile
+  unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + CK_TILE - 1) / CK_TILE, (uint64_t)sm_count * 8);
   if (blocks < 1) blocks = 1;
-  confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
+  confusable_kernel<<<blocks, CK_THREADS, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
   ++g_kernel_launches;
   return cudaGetLastError();
 }

@@ -58,6 +58,8 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream);
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
 cudaError_t configure_kernels();
+// Unicode Alphabetic ranges ([n][2], inclusive) for the character classes of the device edit script; per device
+cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n);
 unsigned long long kernel_launches();  // process-wide count of kernel launches issued by this library
 // Lexicon-sharded mode: merge the all-gathered per-shard survivor lists (see merge_kernel).
 cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, const OutRec* recs_all,
@@ -65,5 +67,28 @@ cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, c
                          OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,
                          cudaStream_t stream);
 size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap);
+
+// Export stage (export.cu): packed pool + headers -> the caller-visible arrays in query order.
+struct ExportBuffers {
+  uint32_t n = 0;
+  const OutHead* head = nullptr;        // [n]
+  const uint32_t* qflags = nullptr;     // [n] QF_*
+  const uint8_t* enc_status = nullptr;  // optional [n] ENC_* of the encode kernel
+  const OutRec* pool = nullptr;
+  uint32_t* tile_sum = nullptr;         // [export_tiles(n)]
+  uint32_t* loff = nullptr;             // [n + 1] batch-local CSR offsets
+  uint32_t* oflags = nullptr;           // [n] ANL_QUERY_* flags
+  void* out = nullptr;                  // anl_variant[out_cap]
+  uint32_t out_cap = 0;
+  ExportSummary* summary = nullptr;
+};
+uint32_t export_tiles(uint32_t n);
+cudaError_t launch_export(const ExportBuffers& eb, cudaStream_t stream);
+// results of re-run queries -> the batch's pool (records behind `base`, headers and flags replaced)
+cudaError_t launch_patch(uint32_t m, const uint32_t* qlist, const OutHead* rr_head, const uint32_t* rr_qflags, const OutRec* rr_out,
+                         OutHead* head, uint32_t* qflags, OutRec* pool, uint32_t base, uint32_t pool_cap, unsigned int* pool_cursor,
+                         uint32_t rr_total, cudaStream_t stream);
+// off64[i] = base + loff[i], i < n: the batch's slice of the call-wide u64 offsets
+cudaError_t launch_offsets(uint32_t n, const uint32_t* loff, uint64_t base, uint64_t* off64, cudaStream_t stream);
 
 }  // namespace anl

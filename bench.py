@@ -222,8 +222,14 @@ def run_ours(args):
     m.read_lexicon(spec["lexicon"])
     for pat, w in spec["confusables"]:
         m.add_to_confusables(pat, w)
+    # `--gpus N` without torchrun: ONE process, one model with a replica on each of the N GPUs (anl_model_build_multi);
+    # the e2e call is then spread over all of them by the library.  `value` stays the device-resident pass on GPU 0.
+    single_process_gpus = args.gpus if (world == 1 and args.gpus > 1) else 1
     t0 = time.perf_counter()
-    m.build(device=dev)
+    if single_process_gpus > 1:
+        m.build(devices=list(range(single_process_gpus)))
+    else:
+        m.build(device=dev)
     build_s = time.perf_counter() - t0
     n = args.queries or spec["n"]
     queries = spec["queries"](n)
@@ -263,20 +269,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    stage = (C.c_float * 6)()
+    stage = (C.c_float * 7)()
     check(L.anl_device_batch_stage_timings(m._h, batch, stage))
-    bloom_ms, exact_ms, prefilter_ms, rank_ms, conf_ms, finish_ms = (float(v) for v in stage)
+    bloom_ms, exact_ms, prefilter_ms, rank_ms, conf_ms, finish_ms, export_ms = (float(v) for v in stage)
     probe_ms, score_ms, rescore_ms = bloom_ms + exact_ms, prefilter_ms + rank_ms, conf_ms + finish_ms
     ctr = _capi.Counters()
     check(L.anl_device_batch_counters(m._h, batch, C.byref(ctr)))
     launches = L.anl_kernel_launches() - launches0  # counted by the library: every kernel of the timed passes
 
     # ---- e2e: host buffers through the public C-ABI call ------------------------------------------------
-    e2e_steps = min(args.steps, args.e2e_steps)  # 0 = skip (profiling runs)
+    e2e_steps = args.e2e_steps  # 0 = skip (profiling runs)
     n_results = 0
     e2e_s = float("nan")
     launches_e2e0 = 0
+    e2e_n = n
+    if single_process_gpus > 1:  # every GPU gets a batch of its own size: weak scaling inside one call
+        e2e_queries = []
+        for g in range(single_process_gpus):
+            e2e_queries += workload_spec(args.workload, g)["queries"](n)
+        blob, offs = _capi.pack(e2e_queries)
+        offs_p = _capi.u64ptr(offs)
+        e2e_n = len(e2e_queries)
+    n_e2e_call = e2e_n
     if e2e_steps > 0:
+        n = n_e2e_call
         rs = C.c_void_p()
         check(L.anl_find_variants_batch(m._h, blob, offs_p, n, C.byref(sp.data), C.byref(rs)))  # warm-up
         n_results = L.anl_result_set_offsets(rs)[n]
@@ -291,16 +307,17 @@ def run_ours(args):
             L.anl_result_set_free(rs)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        n = args.queries or spec["n"]
     clocks = sampler.stop()
     if e2e_steps > 0:
         launches += L.anl_kernel_launches() - launches_e2e0  # the batch call works in chunks of 65536 queries
     ist = m.index_stats()
     max_q_bytes = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
     stride = (min(max_q_bytes, 254) + 2 + 15) & ~15
-    # the query text + u32 offsets go up (the rows are encoded on the device); headers, flags, hit counts,
-    # encode status and the packed 16-byte records come back
-    h2d = len(blob) + 4 * (n + 1)
-    d2h = n * (16 + 4 + 4 + 1) + 16 * int(n_results) + 16
+    # the query text + u32 offsets go up (the rows are encoded on the device); the final arrays come back: u64 offsets,
+    # u32 flags, 32-byte variant records (+ 48 bytes of summary per 65536-query chunk)
+    h2d = len(blob) + 4 * (n_e2e_call + 1)
+    d2h = n_e2e_call * (8 + 4) + 32 * int(n_results) + 48 * ((n_e2e_call + 65535) // 65536)
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s, probe_ms, score_ms], dtype=torch.float64, device="cuda")
@@ -351,8 +368,9 @@ def run_ours(args):
             "dp_gcups_of_step": total_cells * 1e-9 / (step_ms / 1000.0),
             "kernels": {"probe_ms": probe_ms, "score_ms": score_ms, "rescore_ms": rescore_ms,
                         "stages_ms": {"bloom_kernel": bloom_ms, "exact_kernel": exact_ms, "prefilter_kernel": prefilter_ms,
-                                      "score_kernel": rank_ms, "confusable_kernel": conf_ms, "finish_kernel": finish_ms},
-                        "probe_share": probe_ms / (probe_ms + score_ms + rescore_ms),
+                                      "score_kernel": rank_ms, "confusable_kernel": conf_ms, "finish_kernel": finish_ms,
+                                      "export_kernels": export_ms},
+                        "probe_share": probe_ms / (probe_ms + score_ms + rescore_ms + export_ms),
                         "probe_algorithmic_bytes": probe_bytes, "score_algorithmic_bytes": score_bytes,
                         "probe_gbs": probe_bytes / (probe_ms / 1e3) / 1e9, "score_gbs": score_bytes / (score_ms / 1e3) / 1e9,
                         "probes_per_s": ctr.probes / (probe_ms / 1e3)},
@@ -367,8 +385,9 @@ def run_ours(args):
                    "cells_per_launch": ctr.dl_cells, "ms": score_ms,
                    "bound": "integer issue (u8 DP cells in shared memory, no tensor cores); see profiles/ for issue utilisation"},
             "cpu_baseline": cpu,
-            "e2e": ({"value": total_q / e2e_s_max, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                     "steps": e2e_steps, "results_per_step": int(n_results)} if e2e_steps > 0 else None),
+            "e2e": ({"value": (n_e2e_call if single_process_gpus > 1 else total_q) / e2e_s_max, "unit": "queries/s",
+                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "results_per_step": int(n_results),
+                     "gpus_in_one_process": single_process_gpus, "queries_per_call": int(n_e2e_call)} if e2e_steps > 0 else None),
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -568,7 +587,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--queries", type=int, default=0, help="override the batch size (default: the config's)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--sharded", action="store_true", help="lexicon-sharded mode (needs torchrun with N > 1)")

@@ -148,6 +148,15 @@ void anl_model_set_confusables_before_pruning(anl_model* m);
 
 /* build (src/lib.rs:192): anagram index on the host, then upload to `device` (-1 = current). */
 anl_status anl_model_build(anl_model* m, int32_t device);
+/* build with one replica of the index on each of `n_devices` CUDA devices of this process.  Lookups
+ * (anl_find_variants_batch, anl_find_all_matches) then spread every call over all of them: the batch is cut into
+ * chunks that go round-robin to the devices, each device is driven by its own host thread, and the results come back
+ * in query order as from one device.  This is the single-process counterpart of the reference's rayon loop over the
+ * queries (src/bin/analiticcl.rs:418-482, process_par): one VariantModel, all GPUs of the box.  The device-batch and
+ * lexicon-sharded entry points below work on the first listed device. */
+anl_status anl_model_build_multi(anl_model* m, const int32_t* devices, uint32_t n_devices);
+/* number of devices that hold a replica of the built index (0 before build) */
+uint32_t anl_model_device_count(const anl_model* m);
 /* Persistence of the built index (the reference has no on-disk index -- its build takes seconds,
  * the 10 M-entry lexicon of BASELINE config 5 takes 24 s here).  save_index writes the host copy of the index of a
  * built model; load_index replaces anl_model_build for a model that holds the SAME alphabet and vocabulary in the
@@ -265,16 +274,18 @@ typedef struct anl_device_batch anl_device_batch; /* encoded queries + result bu
 /* Encodes on the host (alphabet normalisation) and uploads; buffers are sized for n_queries. */
 anl_status anl_device_batch_create(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
                                    const anl_search_params* params, anl_device_batch** out);
-/* One pass of the hot path over the resident batch: probe kernel + score/rank kernel (+ confusable and
- * finish kernels when confusables are loaded) on the model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
+/* One pass of the hot path over the resident batch: probe kernels + score/rank kernels (+ confusable and
+ * finish kernels when confusables are loaded) + the export kernels that leave the final result arrays (u64 offsets,
+ * 32-byte variant records in query order, per-query flags) in HBM, on the model's stream.  `stream` is a cudaStream_t (0 = the model's own stream).  Does not synchronise. */
 anl_status anl_device_batch_run(anl_model* m, anl_device_batch* b, void* stream);
 /* Device-side cudaEvent timings (ms) of the kernels, averaged over the runs since the previous call
  * (events recorded on the launching stream); synchronises.  rescore_ms (may be NULL) = confusable
  * kernel + finish kernel, which only run when confusables are loaded. */
 anl_status anl_device_batch_timings(anl_model* m, anl_device_batch* b, float* probe_ms, float* score_ms, float* rescore_ms);
-/* The same window per kernel: stage_ms[6] = Bloom-stage kernel, exact-stage kernel (the whole fused probe
+/* The same window per kernel: stage_ms[7] = Bloom-stage kernel, exact-stage kernel (the whole fused probe
  * kernel when the split path is off), prefilter kernel, score/rank kernel launches, confusable kernel,
- * finish kernel.  Resets the window like anl_device_batch_timings. */
+ * finish kernel, export kernels (final result arrays in query order).  Resets the window like
+ * anl_device_batch_timings. */
 anl_status anl_device_batch_stage_timings(anl_model* m, anl_device_batch* b, float* stage_ms);
 /* Downloads the results of the last run and finishes them on the host (same output as
  * anl_find_variants_batch). */

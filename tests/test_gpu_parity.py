@@ -154,6 +154,27 @@ def test_capacity_overflow_rerun(A, eng_oracle, monkeypatch):
     assert_same(got, exp, qs, "overflow")
 
 
+def test_pool_overflow_and_reruns_with_confusables(A, nld_pair, monkeypatch):
+    """A result pool that is too small (the score stage runs again with the exact size) together with hit-list
+    overflows (re-run, patched into the pool, exported again) on a model with device-side confusables."""
+    monkeypatch.setenv("ANL_POOL_PER_QUERY", "1")
+    monkeypatch.setenv("ANL_HIT_CAP", "64")
+    monkeypatch.setenv("ANL_CHUNK", "4096")
+    _, o = nld_pair
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.nld_freq_lexicon())
+    o2 = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    o2.read_lexicon(workloads.nld_freq_lexicon())
+    for pat, w in workloads.CFG2_CONFUSABLES:
+        m.add_to_confusables(pat, w)
+        o2.add_to_confusables(pat, w)
+    m.build()
+    o2.build()
+    qs = workloads.ocr_noise(workloads.read_words("nld"), 9000, 4711)
+    sp = A.SearchParameters(freq_weight=0.25)
+    assert_same(m.find_variants_raw(qs, sp), o2.find_variants_batch(qs, to_orc_params(sp)), qs, "pool overflow + reruns + confusables")
+
+
 @pytest.mark.parametrize("inflight", ["1", "4"])
 def test_chunk_pipeline_with_reruns(A, eng_oracle, monkeypatch, inflight):
     """The batch call cuts the queries into chunks with several batches in flight and fetches them in two phases;
