@@ -488,7 +488,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
                   (void*)b->h_work, (void*)b->h_qboff, (void*)b->h_qblob, (void*)b->h_summary})
     if (p) cudaFreeHost(p);
   for (void* p : {(void*)b->d_final, (void*)b->d_loff, (void*)b->d_oflags, (void*)b->d_off64, (void*)b->d_tile_sum,
-                  (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work})
+                  (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work, (void*)b->d_rec_query, (void*)b->rr_rec_query})
     if (p) cudaFree(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
@@ -532,7 +532,10 @@ void Engine::free_batch(DeviceBatch* b) {
 bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, bool keep_records, std::string* err) {
   const bool need_gid = hm_->index.n_shards > 1;
   const bool need_cw = h_ix_.conf_prefilter && !need_gid;  // the confusable queue can hold every pool record
-  if (pool_cap <= b->cap_pool && b->d_out && b->d_final && (!need_gid || b->d_gid) && (!need_cw || b->d_conf_work)) return true;
+  const bool need_rq = h_ix_.conf_prefilter != 0;  // the triage runs whenever the model has confusables
+  if (pool_cap <= b->cap_pool && b->d_out && b->d_final && (!need_gid || b->d_gid) && (!need_cw || b->d_conf_work) &&
+      (!need_rq || b->d_rec_query))
+    return true;
   pool_cap = std::max(pool_cap, b->cap_pool);
   if (keep_records && b->d_out && b->cap_pool) {
     // (hit-overflow patch: the records already in the pool stay valid)
@@ -547,6 +550,7 @@ bool Engine::grow_pool(DeviceBatch* b, uint32_t pool_cap, bool keep_records, std
   if (!dev_realloc(&b->d_final, pool_cap, err)) return false;
   if (need_gid && !dev_realloc(&b->d_gid, pool_cap, err)) return false;
   if (need_cw && !dev_realloc(&b->d_conf_work, pool_cap, err)) return false;
+  if (need_rq && !dev_realloc(&b->d_rec_query, pool_cap, err)) return false;
   if (!pinned_realloc(&b->h_out, pool_cap, err)) return false;
   b->cap_pool = pool_cap;
   return true;
@@ -823,6 +827,7 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   lb.qlist = nullptr;
   lb.qblob = b->has_qblob ? reinterpret_cast<const uint8_t*>(b->d_qblob) : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
+  lb.rec_query = b->has_qblob ? b->d_rec_query : nullptr;  // (allocated iff the model has a confusable table)
   lb.conf_work = b->dev_conf ? b->d_conf_work : nullptr;
   if (b->split) {
     lb.queue = b->d_queue;
@@ -1124,12 +1129,15 @@ bool Engine::rerun_overflowed(DeviceBatch* b, std::string* err, int* status) {
     if (!dev_realloc(&b->rr_hits, (size_t)m * cap, err)) return false;
     b->rr_cap_hits = (size_t)m * cap;
   }
+  const bool triage = b->has_qblob && h_ix_.conf_prefilter;
   if (bp.pool_cap > b->rr_cap_pool) {
     if (!dev_realloc(&b->rr_out, bp.pool_cap, err)) return false;
     if (b->dev_conf && !dev_realloc(&b->rr_conf_work, bp.pool_cap, err)) return false;
+    if (triage && !dev_realloc(&b->rr_rec_query, bp.pool_cap, err)) return false;
     b->rr_cap_pool = bp.pool_cap;
   }
   if (b->dev_conf && !b->rr_conf_work && !dev_realloc(&b->rr_conf_work, b->rr_cap_pool, err)) return false;
+  if (triage && !b->rr_rec_query && !dev_realloc(&b->rr_rec_query, b->rr_cap_pool, err)) return false;
   if (scratch > b->rr_cap_scratch) {
     if (!dev_realloc(&b->rr_scratch, scratch, err)) return false;
     b->rr_cap_scratch = scratch;
@@ -1141,6 +1149,7 @@ bool Engine::rerun_overflowed(DeviceBatch* b, std::string* err, int* status) {
   lb.qlist = b->rr_qlist;
   lb.qblob = b->has_qblob ? b->d_qblob : nullptr;
   lb.qboff = b->has_qblob ? b->d_qboff : nullptr;
+  lb.rec_query = triage ? b->rr_rec_query : nullptr;
   lb.conf_work = b->dev_conf ? b->rr_conf_work : nullptr;
   lb.n = m;
   lb.hits = b->rr_hits;

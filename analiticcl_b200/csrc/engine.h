@@ -63,6 +63,7 @@ struct DeviceBatch {
   uint8_t* d_enc_status = nullptr;  // per query: ENC_* result of the encode kernel (or of the host encoder)
   uint8_t* h_enc_status = nullptr;
   bool dev_encode = false;          // the rows of this batch were encoded on the device
+  uint32_t* d_rec_query = nullptr;  // per pool record: the row of its query (confusable triage), sized like d_out
   ConfWork* d_conf_work = nullptr;  // queue of (record, query) pairs for the confusable kernel, sized like d_out
   bool dev_conf = false;            // this batch's confusables are rescored on the device (HEAD_HOST_FINISH marks the rest)
   uint32_t* d_hits = nullptr;
@@ -89,6 +90,7 @@ struct DeviceBatch {
   OutHead* rr_head = nullptr;
   OutRec* rr_out = nullptr;
   ConfWork* rr_conf_work = nullptr;
+  uint32_t* rr_rec_query = nullptr;
   uint8_t* rr_scratch = nullptr;
   unsigned int* rr_work = nullptr;  // [8] the rerun's own counters (the batch's hold its pool cursor)
   size_t rr_cap_m = 0, rr_cap_hits = 0, rr_cap_pool = 0, rr_cap_scratch = 0;

@@ -1386,14 +1386,11 @@ __host__ __device__ inline uint32_t rce_mode(int finish_mode) {
     default: return 0;  // FINISH_SHARD: survivors pass through unranked
   }
 }
-// the confusable stage of a launch (all null when the model has no confusables or the mode has no post-pass)
+// the confusable stage of a launch (null when the model has no confusables or the mode has no post-pass): the
+// emitted records remember their query, triage_kernel and confusable_kernel take it from there
 struct ConfStage {
-  const DeviceIndex* ix = nullptr;
-  const uint8_t* qraw = nullptr;  // raw text of the current query
-  uint32_t qraw_len = 0;
-  uint32_t qrow = 0;              // the query's row in the batch (indexes the raw-text offsets)
-  ConfWork* worklist = nullptr;
-  unsigned int* work_cursor = nullptr;
+  uint32_t* rec_query = nullptr;  // per pool record: the query's row in the batch (indexes the raw-text offsets)
+  uint32_t qrow = 0;
 };
 
 // The tail shared by score_kernel and merge_kernel: frequency normalisation, ranking, crop, cut-off and
@@ -1493,43 +1490,15 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
   if (fits) {
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
       const uint32_t i = i0 + lane;
-      bool queue = false;
-      uint32_t cost = 0;
       if (i < n) {
         const SurvRec r = sorted[i];
         OutRec o;
         o.dist_score = r.dist;
         o.vocab_id = r.vocab;
-        if (cs.qraw) {
-          // confusable triage: settle the pairs whose weight is known here, queue the rest for the confusable kernel
-          const uint32_t t0 = __ldg(cs.ix->vocab_text_off + r.vocab), t1 = __ldg(cs.ix->vocab_text_off + r.vocab + 1);
-          double w;
-          const int tri = confusable_triage(cs.ix, cs.qraw, cs.qraw_len, cs.ix->vocab_text + t0, t1 - t0, &w, &cost);
-          if (tri == CONF_SETTLED) {
-            o.vocab_id |= OUT_SKIP_CONFUSABLES;
-            if (w != 1.0) o.dist_score = __dmul_rn(r.dist, w);  // src/lib.rs:1660
-          }
-          queue = tri == CONF_QUEUE;
-        }
         o.freq = r.raw;
         out[off + i] = o;
         if (out_gid) out_gid[off + i] = r.g;
-      }
-      if (cs.worklist) {
-        const uint32_t qm = __ballot_sync(FULL, queue);
-        if (qm) {
-          uint32_t wbase = 0;
-          if (lane == 0) wbase = atomicAdd(cs.work_cursor, (unsigned int)__popc(qm));
-          wbase = __shfl_sync(FULL, wbase, 0);
-          if (queue) {
-            ConfWork w;
-            w.rec = off + i;
-            w.query = cs.qrow;
-            w.cost = cost;
-            w.pad = 0;
-            cs.worklist[wbase + __popc(qm & lanemask_lt())] = w;  // capacity = pool capacity >= records emitted
-          }
-        }
+        if (cs.rec_query) cs.rec_query[off + i] = cs.qrow;
       }
     }
   }
@@ -1685,8 +1654,7 @@ constexpr uint32_t K2_HEAVY_HITS = 64;  // more candidates than two rounds of 32
 #endif
 __global__ void __launch_bounds__(K2_WARPS * 32, ANL_K2_MIN_CTAS)
 score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
-             const uint32_t* __restrict__ qlist, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
-             ConfWork* __restrict__ conf_work, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
+             const uint32_t* __restrict__ qlist, uint32_t* __restrict__ rec_query, uint32_t nq, uint32_t* hits, uint32_t* hit_count,
              uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              uint32_t* __restrict__ out_gid, OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work,
              unsigned int* work_light, unsigned int* pool_cursor, Counters* counters, uint32_t ML, uint32_t R, uint32_t need_min,
@@ -1954,14 +1922,9 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     c_dpc += lane == 0 ? (nvalid_q + 31) / 32 : 0;
 #endif
     ConfStage cs;
-    if (qblob && ix->conf_prefilter && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
-      const uint32_t b0 = qboff[q], b1 = qboff[q + 1];
-      cs.ix = ix;
-      cs.qraw = qblob + b0;
-      cs.qraw_len = b1 - b0;
+    if (rec_query && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
+      cs.rec_query = rec_query;
       cs.qrow = q;
-      cs.worklist = conf_work;
-      cs.work_cursor = pool_cursor + 1;
     }
     c_res += rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags,
                             qflags, pool_cursor, 0, cs);
@@ -2054,17 +2017,62 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
 // ================================================================================================
 // Kernels 4 + 5 (only with confusables): device-side rescoring of the ranked lists
 // ================================================================================================
+// triage_kernel: one pool record per thread (the score kernel left each record's query in rec_query).  Settles the
+// pairs whose confusable weight is known without an edit script and queues the rest for confusable_kernel.  A kernel
+// of its own: inside the score kernel the triage ran on the few lanes that hold a query's results (6 of 32 on
+// cfg 2) and walked the candidate's text byte by byte at that occupancy; here every lane has a record.
+__global__ void __launch_bounds__(256)
+triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+              const uint32_t* __restrict__ rec_query, OutRec* __restrict__ out, const unsigned int* __restrict__ pool_cursor,
+              uint32_t pool_cap, ConfWork* __restrict__ worklist, unsigned int* work_cursor) {
+  const uint32_t used = *pool_cursor;
+  if (used > pool_cap) return;  // pool overflow: the score stage runs again with a larger pool
+  const uint8_t* __restrict__ vtext = ix->vocab_text;
+  const uint32_t* __restrict__ voff = ix->vocab_text_off;
+  const uint32_t lane = lane_id();
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < used; base += gridDim.x * blockDim.x) {
+    const uint32_t rec = base + lane;
+    bool queue = false;
+    uint32_t cost = 0, query = 0;
+    if (rec < used) {
+      OutRec r = out[rec];
+      query = rec_query[rec];
+      const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
+      const uint32_t a0 = qboff[query], a1 = qboff[query + 1];
+      const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
+      double w;
+      const int tri = confusable_triage(ix, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &w, &cost);
+      if (tri == CONF_SETTLED) {
+        r.vocab_id |= OUT_SKIP_CONFUSABLES;
+        if (w != 1.0) r.dist_score = __dmul_rn(r.dist_score, w);  // src/lib.rs:1660
+        out[rec] = r;
+      }
+      queue = tri == CONF_QUEUE;
+    }
+    if (worklist) {
+      const uint32_t qm = __ballot_sync(FULL, queue);
+      if (qm) {
+        uint32_t wbase = 0;
+        if (lane == 0) wbase = atomicAdd(work_cursor, (unsigned int)__popc(qm));
+        wbase = __shfl_sync(FULL, wbase, 0);
+        if (queue) {
+          ConfWork w;
+          w.rec = rec;
+          w.query = query;
+          w.cost = cost;
+          w.pad = 0;
+          worklist[wbase + __popc(qm & lanemask_lt())] = w;  // capacity = pool capacity >= records emitted
+        }
+      }
+    }
+  }
+}
+
 // confusable_kernel: one queued (input, candidate) pair per thread.  Computes the edit script of the raw
-// strings (as UTF-16 code units: every character of the Basic Multilingual Plane is one unit) and the product of the
-// weights of all patterns found in it (rescore_confusables / compute_confusable_weight, src/lib.rs:1656-1663,
-// 1733-1756), multiplies the record's distance score and marks it settled.  Pairs outside the limits of
-// editscript_fixed.h stay unsettled (host post-pass).
-//
-// The diff's loops are data dependent: lanes of a warp that hold pairs of very different size idle most of the time
-// (ncu, round 1: 4.5 of 32 lanes active).  A CTA therefore takes a tile of CK_TILE queued pairs, sorts them by the
-// size of their middles (the triage stored it) in shared memory, and hands neighbours in that order to the lanes.
-constexpr int CK_THREADS = 128;
-constexpr int CK_TILE = 512;
+// strings and the product of the weights of all patterns found in it (rescore_confusables /
+// compute_confusable_weight, src/lib.rs:1656-1663, 1733-1756), multiplies the record's distance score and marks it
+// settled.  Pure-ASCII pairs run over bytes; pairs with other BMP characters over UTF-16 code units (one unit per
+// character).  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
 // Unicode Alphabetic ranges (boundary scores of the diff clean-up, cf. UnicodeClass in editscript.cpp)
 __constant__ uint32_t c_alpha_ranges[2 * 800];
 __constant__ uint32_t c_n_alpha_ranges;
@@ -2090,11 +2098,29 @@ cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n) {
   return cudaMemcpyToSymbol(c_n_alpha_ranges, &n, sizeof n);
 }
 
-__global__ void __launch_bounds__(CK_THREADS)
+// the wide-character variant of one pair, out of line: rare, and it keeps the byte path's code small
+__device__ __noinline__ bool confusable_weight_wide(const esf::PatTable& T, const uint8_t* __restrict__ sa, uint32_t la,
+                                                    const uint8_t* __restrict__ sb, uint32_t lb, double* weight) {
+  uint16_t a[esf::MAXLEN], b[esf::MAXLEN];
+  if (la > 3u * esf::MAXLEN || lb > 3u * esf::MAXLEN) return false;  // (the triage checked the character counts)
+  const int na = (int)u8_decode_bmp(sa, la, a, esf::MAXLEN);
+  const int nb = (int)u8_decode_bmp(sb, lb, b, esf::MAXLEN);
+  esf::View v[esf::MAXSEG];
+  const int nv = esf::shortest_edit_script_t<DeviceCharClass, uint16_t>(a, na, b, nb, v);
+  if (nv < 0) return false;
+  double w = 1.0;
+  for (uint32_t k = 0; k < T.n_pats; ++k) {
+    const ConfPat pat = T.pats[k];
+    if (esf::found_in(T, pat, a, b, v, nv)) w = __dmul_rn(w, pat.weight);
+  }
+  *weight = w;
+  return true;
+}
+
+__global__ void __launch_bounds__(64)
 confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
                   const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
                   OutRec* __restrict__ out) {
-  __shared__ uint32_t keys[CK_TILE];
   const uint32_t total = min(*work_count, work_cap);
   esf::PatTable T;
   T.pats = ix->conf_pats;
@@ -2104,53 +2130,38 @@ confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict_
   T.n_pats = ix->n_conf_pats;
   const uint8_t* __restrict__ vtext = ix->vocab_text;
   const uint32_t* __restrict__ voff = ix->vocab_text_off;
-  for (uint32_t t0 = blockIdx.x * CK_TILE; t0 < total; t0 += gridDim.x * CK_TILE) {
-    // key = cost << 9 | position in the tile; slots beyond the queue sort to the end
-    for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE; k += CK_THREADS) {
-      const uint32_t w = t0 + k;
-      keys[k] = w < total ? (min(worklist[w].cost, 0x3FFFFFu) << 9) | k : 0xFFFFFFFFu;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const ConfWork it = worklist[w];
+    const OutRec r = out[it.rec];
+    const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
+    const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
+    const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
+    // private copies: the diff touches every character many times
+    uint8_t a[esf::MAXLEN], b[esf::MAXLEN];
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    uint32_t hibits = 0;
+    if (na <= esf::MAXLEN && nb <= esf::MAXLEN) {
+      for (int i = 0; i < na; ++i) hibits |= (a[i] = qblob[a0 + i]);
+      for (int i = 0; i < nb; ++i) hibits |= (b[i] = vtext[b0 + i]);
+    } else {
+      hibits = 0x80;  // more bytes than the byte path holds: characters beyond ASCII (the triage bounded the characters)
     }
-    __syncthreads();
-    for (uint32_t size = 2; size <= (uint32_t)CK_TILE; size <<= 1)
-      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-        for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE / 2; k += CK_THREADS) {
-          const uint32_t lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
-          const bool up = (lo & size) == 0;
-          const uint32_t x = keys[lo], y = keys[hi];
-          if ((x > y) == up) {
-            keys[lo] = y;
-            keys[hi] = x;
-          }
-        }
-        __syncthreads();
-      }
-    for (uint32_t k = threadIdx.x; k < (uint32_t)CK_TILE; k += CK_THREADS) {
-      const uint32_t key = keys[k];
-      if (key == 0xFFFFFFFFu) continue;
-      const ConfWork it = worklist[t0 + (key & 511u)];
-      const OutRec r = out[it.rec];
-      const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
-      const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
-      const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
-      // private copies: the diff touches every character many times
-      uint16_t a[esf::MAXLEN], b[esf::MAXLEN];
-      if (a1 - a0 > 3u * esf::MAXLEN || b1 - b0 > 3u * esf::MAXLEN) continue;  // (the triage checked the character counts)
-      const int na = (int)u8_decode_bmp(qblob + a0, a1 - a0, a, esf::MAXLEN);
-      const int nb = (int)u8_decode_bmp(vtext + b0, b1 - b0, b, esf::MAXLEN);
+    double weight = 1.0;
+    if (hibits & 0x80) {
+      if (!confusable_weight_wide(T, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &weight)) continue;
+    } else {
       esf::View v[esf::MAXSEG];
-      const int nv = esf::shortest_edit_script_t<DeviceCharClass, uint16_t>(a, na, b, nb, v);
+      const int nv = esf::shortest_edit_script(a, na, b, nb, v);
       if (nv < 0) continue;
-      double weight = 1.0;
-      for (uint32_t p = 0; p < T.n_pats; ++p) {
-        const ConfPat pat = T.pats[p];
+      for (uint32_t k = 0; k < T.n_pats; ++k) {
+        const ConfPat pat = T.pats[k];
         if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
       }
-      OutRec o = r;
-      if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
-      o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
-      out[it.rec] = o;
     }
-    __syncthreads();  // (the keys are overwritten by the next tile)
+    OutRec o = r;
+    if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
+    o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
+    out[it.rec] = o;
   }
 }
 
@@ -2366,7 +2377,7 @@ static cudaError_t launch_score_class(const DeviceIndex* d_ix, const BatchParams
   if (grid < 1) return cudaErrorInvalidConfiguration;
   (void)sm_count;
   SurvRec* scratch = reinterpret_cast<SurvRec*>(lb.scratch);
-  score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.qblob, lb.qboff, lb.conf_work,
+  score_kernel<<<(unsigned)grid, K2_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.rec_query,
                                                                 lb.n, lb.hits, lb.hit_count, lb.qflags, lb.out, lb.out_gid,
                                                                 lb.out_head, scratch, work, work_light, lb.work + 2, lb.counters,
                                                                 cols, R, need_min, need_max, scratch_cta0);
@@ -2423,15 +2434,27 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work, lb.work + 7, grid_b, 0);
 }
 
-// The device confusable stage: edit scripts of the queued pairs, then re-rank / crop / cut-off per query.
-// Only launched when the score kernel filled a work list (lb.conf_work).
+// The device confusable stage: triage of every emitted record, edit scripts of the queued pairs; launch_finish then
+// re-ranks / crops / cuts off per query.  Only launched when the score kernel recorded the records' queries
+// (lb.rec_query); without lb.conf_work the triage only marks the settled records for the host post-pass.
 cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, const LaunchBuffers& lb, int sm_count,
                                cudaStream_t stream) {
-  if (lb.n == 0 || !lb.conf_work) return cudaSuccess;
-  // the queue length is only known on the device: a grid that covers the device walks the queue tile by tile
-  unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + CK_TILE - 1) / CK_TILE, (uint64_t)sm_count * 8);
+  if (lb.n == 0 || !lb.rec_query || !lb.qblob || !(bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER))
+    return cudaSuccess;
+  {
+    unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 255) / 256, (uint64_t)sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    triage_kernel<<<blocks, 256, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.rec_query, lb.out, lb.work + 2, bp.pool_cap, lb.conf_work,
+                                              lb.work + 3);
+    ++g_kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !lb.conf_work) return e;
+  }
+  // one thread per possible work item (the queue length is only known on the device): threads beyond the
+  // queue exit at once, and the long, divergent per-pair work is balanced by the block scheduler
+  unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
   if (blocks < 1) blocks = 1;
-  confusable_kernel<<<blocks, CK_THREADS, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
+  confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
   ++g_kernel_launches;
   return cudaGetLastError();
 }

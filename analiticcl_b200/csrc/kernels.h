@@ -13,6 +13,7 @@ struct LaunchBuffers {
   const uint32_t* qlist = nullptr;   // optional: indices into `queries` (rerun of selected queries); nullptr = identity
   const uint8_t* qblob = nullptr;    // optional: raw UTF-8 of the queries (confusable triage + edit scripts)
   const uint32_t* qboff = nullptr;   //           byte offsets into qblob, n_total + 1 entries
+  uint32_t* rec_query = nullptr;     // optional (confusables): per pool record the row of its query, bp.pool_cap entries
   ConfWork* conf_work = nullptr;     // optional: queue of (record, query) pairs for the confusable kernel, bp.pool_cap entries
   uint32_t n = 0;                    // number of queries in this launch
   uint32_t* hits = nullptr;          // [n][hit_cap] gather ids of candidate instances
