@@ -488,7 +488,9 @@ void Engine::destroy_batch(DeviceBatch* b) {
                   (void*)b->h_work, (void*)b->h_qboff, (void*)b->h_qblob, (void*)b->h_summary})
     if (p) cudaFreeHost(p);
   for (void* p : {(void*)b->d_final, (void*)b->d_loff, (void*)b->d_oflags, (void*)b->d_off64, (void*)b->d_tile_sum,
-                  (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work, (void*)b->d_rec_query, (void*)b->rr_rec_query})
+                  (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work, (void*)b->d_rec_query, (void*)b->rr_rec_query,
+                  (void*)b->d_qbase, (void*)b->d_pair_q, (void*)b->d_pair_g, (void*)b->d_pair_d, (void*)b->d_pair_res,
+                  (void*)b->d_pair_tab})
     if (p) cudaFree(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
   if (b->d_qboff) cudaFree(b->d_qboff);
@@ -576,7 +578,7 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
     if (!pinned_realloc(&b->h_hitcnt, n, err)) return false;
     if (!dev_realloc(&b->d_enc_status, (size_t)n + 1, err) || !pinned_realloc(&b->h_enc_status, (size_t)n + 1, err)) return false;
     if (!dev_realloc(&b->d_loff, (size_t)n + 1, err) || !dev_realloc(&b->d_oflags, n, err) || !dev_realloc(&b->d_off64, n, err) ||
-        !dev_realloc(&b->d_tile_sum, (size_t)export_tiles(n) + 1, err))
+        !dev_realloc(&b->d_tile_sum, (size_t)export_tiles(n) + 1, err) || !dev_realloc(&b->d_qbase, n, err))
       return false;
     b->cap_n = n;
   }
@@ -586,11 +588,24 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
     b->cap_scratch = scratch;
   }
   if (!b->d_work) {
-    if (!dev_realloc(&b->d_work, 8, err)) return false;
-    if (!pinned_realloc(&b->h_work, 8, err)) return false;
+    if (!dev_realloc(&b->d_work, WORK_SLOTS, err)) return false;
+    if (!pinned_realloc(&b->h_work, WORK_SLOTS, err)) return false;
+    CU_TRY(cudaMemset(b->d_work, 0, WORK_SLOTS * sizeof(unsigned int)));
     if (!dev_realloc(&b->d_counters, 1, err)) return false;
     if (!dev_realloc(&b->d_summary, 1, err) || !pinned_realloc(&b->h_summary, 1, err)) return false;
+    CU_TRY(cudaMemset(b->d_summary, 0, sizeof(ExportSummary)));
+    if (!dev_realloc(&b->d_pair_tab, 3 * (size_t)PAIR_TABLE, err)) return false;
   }
+  return true;
+}
+
+bool Engine::grow_pairs(DeviceBatch* b, size_t pair_cap, std::string* err) {
+  if (pair_cap <= b->cap_pairs && b->d_pair_q) return true;
+  pair_cap = std::min<size_t>(std::max(pair_cap, b->cap_pairs), 0xFFFFFF00u);
+  if (!dev_realloc(&b->d_pair_q, pair_cap, err) || !dev_realloc(&b->d_pair_g, pair_cap, err) ||
+      !dev_realloc(&b->d_pair_d, pair_cap, err) || !dev_realloc(&b->d_pair_res, pair_cap, err))
+    return false;
+  b->cap_pairs = pair_cap;
   return true;
 }
 
@@ -709,6 +724,23 @@ DeviceBatch* Engine::create_batch(const char* blob, const uint64_t* offsets, uin
         b->cap_qctx = okq ? (size_t)n : 0;
       }
       if (!okq) b->split = false;  // not enough memory for the queue: the fused kernel needs none
+    }
+  }
+  {
+    // pair-list score stage: room for the pairs that survive the length check and the OSA filter; an overflow is
+    // detected after the run and answered by running the stage again with the exact size
+    static int pairs_on = -1;
+    if (pairs_on < 0) {
+      const char* e = getenv("ANL_PAIRS");
+      pairs_on = e ? (atoi(e) != 0) : 1;
+    }
+    b->use_pairs = pairs_on && n > 0;
+    if (b->use_pairs) {
+      const uint32_t kcap = std::max(threshold_cap(p.max_anagram_distance), threshold_cap(p.max_edit_distance));
+      uint64_t per_query = kcap <= 2 ? 96 : (kcap == 3 ? 160 : (kcap == 4 ? 512 : 1024));
+      if (const char* e = getenv("ANL_PAIRS_PER_QUERY")) per_query = (uint64_t)std::max(1, atoi(e));
+      std::string e2;
+      if (!grow_pairs(b, (size_t)std::min<uint64_t>(0xFFFFFF00ull, n * per_query + 4096), &e2)) b->use_pairs = false;
     }
   }
   b->sharded = hm_->index.n_shards > 1;
@@ -834,6 +866,17 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
     lb.queue_cap = (uint32_t)std::min<size_t>(b->cap_queue, 0x7FFFFFF0u);
     lb.qctx = b->d_qctx;
   }
+  if (b->use_pairs) {
+    lb.qbase = b->d_qbase;
+    lb.pair_q = b->d_pair_q;
+    lb.pair_g = b->d_pair_g;
+    lb.pair_d = b->d_pair_d;
+    lb.pair_res = b->d_pair_res;
+    lb.pair_cap = (uint32_t)b->cap_pairs;
+    lb.pair_hist = b->d_pair_tab;
+    lb.pair_first = b->d_pair_tab + PAIR_TABLE;
+    lb.pair_cursor = b->d_pair_tab + 2 * PAIR_TABLE;
+  }
   lb.n = b->n;
   lb.hits = b->d_hits;
   lb.hit_count = b->d_hit_count;
@@ -873,10 +916,33 @@ bool Engine::launch_export_chain(DeviceBatch* b, cudaStream_t st, std::string* e
 }
 
 static bool download_summary(DeviceBatch* b, cudaStream_t st, std::string* err) {
-  CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(b->h_work, b->d_work, WORK_SLOTS * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(ExportSummary), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaEventRecord(b->ev_done, st));
   return true;
+}
+
+// prefilter + score: over the shape-sorted pair list, or query by query (ANL_PAIRS=0, re-runs of overflowed queries)
+bool Engine::launch_score_stage(DeviceBatch* b, const LaunchBuffers& lb, cudaStream_t st, cudaEvent_t ev_filter, std::string* err) {
+  if (b->use_pairs && lb.pair_q) {
+    CU_TRY(launch_score_pairs(d_ix_, h_ix_, b->bp, lb, sm_count_, st, ev_filter));
+    return true;
+  }
+  CU_TRY(launch_prefilter(d_ix_, b->bp, lb, sm_count_, st));
+  if (ev_filter) CU_TRY(cudaEventRecord(ev_filter, st));
+  CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, st));
+  return true;
+}
+
+bool Engine::relaunch_from_score(DeviceBatch* b, std::string* err) {
+  cudaStream_t st = b->stream;
+  CU_TRY(cudaStreamWaitEvent(st, b->ev_done, 0));
+  LaunchBuffers lb = launch_buffers(b);
+  lb.counters = nullptr;
+  if (!launch_score_stage(b, lb, st, nullptr, err)) return false;
+  CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, st));
+  CU_TRY(launch_finish(b->bp, lb, sm_count_, st));
+  return launch_export_chain(b, st, err) && download_summary(b, st, err);
 }
 
 bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
@@ -898,9 +964,7 @@ bool Engine::run_batch(DeviceBatch* b, cudaStream_t stream, std::string* err) {
   lb.ev_bloom_done = ev[1];
   CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[2], stream));
-  CU_TRY(launch_prefilter(d_ix_, b->bp, lb, sm_count_, stream));
-  CU_TRY(cudaEventRecord(ev[3], stream));
-  CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, stream));
+  if (!launch_score_stage(b, lb, stream, ev[3], err)) return false;
   CU_TRY(cudaEventRecord(ev[4], stream));
   CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, stream));
   CU_TRY(cudaEventRecord(ev[5], stream));
@@ -1142,7 +1206,7 @@ bool Engine::rerun_overflowed(DeviceBatch* b, std::string* err, int* status) {
     if (!dev_realloc(&b->rr_scratch, scratch, err)) return false;
     b->rr_cap_scratch = scratch;
   }
-  if (!b->rr_work && !dev_realloc(&b->rr_work, 8, err)) return false;
+  if (!b->rr_work && !dev_realloc(&b->rr_work, WORK_SLOTS, err)) return false;
   CU_TRY(cudaMemcpyAsync(b->rr_qlist, which.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   LaunchBuffers lb;
   lb.queries = b->d_rows;
@@ -1161,13 +1225,13 @@ bool Engine::rerun_overflowed(DeviceBatch* b, std::string* err, int* status) {
   lb.scratch_bytes = b->rr_cap_scratch;
   lb.work = b->rr_work;
   lb.counters = nullptr;
-  CU_TRY(cudaMemsetAsync(b->rr_work, 0, 8 * sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(b->rr_work, 0, WORK_SLOTS * sizeof(unsigned int), st));
   CU_TRY(launch_probe(d_ix_, h_ix_, bp, lb, sm_count_, st));  // (no staged-node queue: the fused kernel)
-  CU_TRY(launch_prefilter(d_ix_, bp, lb, sm_count_, st));
+  CU_TRY(launch_prefilter(d_ix_, bp, lb, sm_count_, st));         // (and the per-query score kernels: a handful of queries)
   CU_TRY(launch_score(d_ix_, h_ix_, bp, lb, sm_count_, st));
   CU_TRY(launch_confusables(d_ix_, bp, lb, sm_count_, st));
   CU_TRY(launch_finish(bp, lb, sm_count_, st));
-  unsigned int rr_work[8];
+  unsigned int rr_work[WORK_SLOTS];
   std::vector<uint32_t> fl(m);
   CU_TRY(cudaMemcpyAsync(rr_work, b->rr_work, sizeof rr_work, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaMemcpyAsync(fl.data(), b->rr_qflags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1226,11 +1290,15 @@ bool Engine::settle(DeviceBatch* b, std::string* err, int* status) {
       LaunchBuffers lbq = launch_buffers(b);
       lbq.counters = nullptr;
       CU_TRY(launch_probe(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
-      CU_TRY(launch_prefilter(d_ix_, b->bp, lbq, sm_count_, st));
-      CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lbq, sm_count_, st));
-      CU_TRY(launch_confusables(d_ix_, b->bp, lbq, sm_count_, st));
-      CU_TRY(launch_finish(b->bp, lbq, sm_count_, st));
-      if (!launch_export_chain(b, st, err) || !download_summary(b, st, err)) return false;
+      if (!relaunch_from_score(b, err)) return false;
+      b->reruns += 1;
+      --attempt;
+      continue;
+    }
+    if (b->use_pairs && n && b->h_work[WORK_PAIR_TOTAL] > b->cap_pairs) {
+      // more pairs survived the filter than the pair list holds: the counter is the exact requirement
+      if (profile_enabled()) fprintf(stderr, "[anl profile] pair list overflow (%u > %zu): score stage again\n", b->h_work[WORK_PAIR_TOTAL], b->cap_pairs);
+      if (!grow_pairs(b, (size_t)b->h_work[WORK_PAIR_TOTAL] + 4096, err) || !relaunch_from_score(b, err)) return false;
       b->reruns += 1;
       --attempt;
       continue;
@@ -1244,13 +1312,7 @@ bool Engine::settle(DeviceBatch* b, std::string* err, int* status) {
     // the cursor counted every query's results, so `used` is the exact requirement
     if (!grow_pool(b, (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, (uint64_t)used + 1024), false, err)) return false;
     b->bp.pool_cap = b->cap_pool;
-    CU_TRY(cudaStreamWaitEvent(st, b->ev_done, 0));
-    LaunchBuffers lb = launch_buffers(b);
-    lb.counters = nullptr;
-    CU_TRY(launch_score(d_ix_, h_ix_, b->bp, lb, sm_count_, st));
-    CU_TRY(launch_confusables(d_ix_, b->bp, lb, sm_count_, st));
-    CU_TRY(launch_finish(b->bp, lb, sm_count_, st));
-    if (!launch_export_chain(b, st, err) || !download_summary(b, st, err)) return false;
+    if (!relaunch_from_score(b, err)) return false;
     b->reruns += 1;
   }
   if (b->bp.finish_mode != FINISH_SHARD && b->h_summary->n_rerun && !rerun_overflowed(b, err, status)) return false;

@@ -46,7 +46,7 @@ struct DeviceBatch {
   uint32_t* h_flags = nullptr; // [cap_n]
   uint32_t* h_hitcnt = nullptr;// [cap_n]
   OutRec* h_out = nullptr;     // [cap_pool]
-  unsigned int* h_work = nullptr;  // [8]
+  unsigned int* h_work = nullptr;  // [WORK_SLOTS]
   ExportSummary* h_summary = nullptr;
   // device buffers
   uint8_t* d_rows = nullptr;
@@ -75,6 +75,15 @@ struct DeviceBatch {
   void* d_scratch = nullptr;
   unsigned int* d_work = nullptr;
   Counters* d_counters = nullptr;
+  // pair-list score stage (kernels.cu "Kernels 2p"): dense slot base per query, shape-sorted pair list, packed features
+  bool use_pairs = false;
+  uint32_t* d_qbase = nullptr;      // [cap_n]
+  uint32_t* d_pair_q = nullptr;     // [cap_pairs] each
+  uint32_t* d_pair_g = nullptr;
+  uint32_t* d_pair_d = nullptr;
+  uint32_t* d_pair_res = nullptr;
+  uint32_t* d_pair_tab = nullptr;   // [3][PAIR_TABLE]: histogram, first position, cursor per shape
+  size_t cap_pairs = 0;
   // export stage (export.cu): final arrays of this batch, in query order
   anl_variant* d_final = nullptr;   // [cap_pool]
   uint32_t* d_loff = nullptr;       // [cap_n + 1] batch-local CSR offsets
@@ -173,6 +182,9 @@ class Engine {
   bool ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32_t hit_cap, uint32_t pool_cap, size_t scratch,
                        std::string* err);
   bool grow_pool(DeviceBatch* b, uint32_t pool_cap, bool keep_records, std::string* err);
+  bool grow_pairs(DeviceBatch* b, size_t pair_cap, std::string* err);
+  bool launch_score_stage(DeviceBatch* b, const LaunchBuffers& lb, cudaStream_t st, cudaEvent_t ev_filter, std::string* err);
+  bool relaunch_from_score(DeviceBatch* b, std::string* err);  // score stage .. export + summary download, on the batch's stream
   void destroy_batch(DeviceBatch* b);
   void release_index();
 

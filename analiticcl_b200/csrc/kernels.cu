@@ -2042,7 +2042,9 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
       const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
       double w;
       const int tri = confusable_triage(ix, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &w, &cost);
-      if (tri == CONF_SETTLED) {
+      // Without a work list the host runs the post-pass (variant lists, sharded mode): it only wants to know which
+      // records provably keep their score -- a weight found on the spot is left for it to apply.
+      if (tri == CONF_SETTLED && (w == 1.0 || worklist)) {
         r.vocab_id |= OUT_SKIP_CONFUSABLES;
         if (w != 1.0) r.dist_score = __dmul_rn(r.dist_score, w);  // src/lib.rs:1660
         out[rec] = r;
@@ -2239,6 +2241,574 @@ size_t merge_scratch_bytes(int sm_count, uint32_t n, uint32_t scratch_cap) {
 }
 
 // ================================================================================================
+// Kernels 2p: scoring over a global, shape-sorted list of (query, candidate) pairs
+// ================================================================================================
+// score_kernel keeps a query's candidates together: one warp, rounds of 32 lanes, every lane walking a matrix as
+// large as the longest candidate of its round.  On cfg 2 that ran 19.6 useful lanes per round and 2.4 matrix cells
+// per useful cell (ncu, round 1) -- and one query with thousands of candidates was one warp's job.  Here the pairs of
+// ALL queries are sorted by matrix shape (query length, candidate length) first, so that the 32 lanes of a warp hold
+// 32 pairs of the same shape whatever queries they belong to:
+//   pairfilter_kernel : per query (one warp): length check + bit-parallel OSA rejection (as prefilter_kernel), hit
+//                       list compacted in place, a dense slot range reserved for the survivors, shape histogram
+//   pairscan_kernel   : exclusive scan of the histogram -> first position of every shape; long shapes go last,
+//                       starting at a tile boundary, so every tile of 32 positions belongs to one launch class
+//   pairscatter_kernel: per query: every surviving candidate takes the next position of its shape
+//   dp_kernel         : per tile of 32 pairs (one warp): true Damerau-Levenshtein + LCS + prefix + suffix in lock step,
+//                       no padding lanes, no padding columns; the packed features go to the pair's dense slot
+//   rank_kernel       : per query (one warp): features -> f64 score, max frequency, threshold, rank, crop, cut-off
+constexpr uint32_t PAIR_SHORT_MAX = 24;     // longest side of a "short" shape (the DP's small shared-memory class)
+constexpr uint32_t PAIR_SHORT_KEYS = 640;   // short shapes: Lq * 25 + Lc (625 used); long shapes follow:
+constexpr uint32_t PAIR_BUCKETS = PAIR_TABLE;  // min(Lq, 63) << 6 | min(Lc, 63) behind the short ones (4736 used of 5120)
+constexpr uint32_t PAIR_HOLE = 0xFFFFFFFFu;  // pair_q of an unused position (padding before the long class)
+constexpr uint32_t RES_REJECT = 0xFFFFFFFFu;  // packed features of a candidate beyond the edit distance
+__device__ __forceinline__ uint32_t pair_bucket(uint32_t Lq, uint32_t Lc) {
+  if (max(Lq, Lc) <= PAIR_SHORT_MAX) return Lq * (PAIR_SHORT_MAX + 1) + Lc;
+  return PAIR_SHORT_KEYS + ((min(Lq, 63u) << 6) | min(Lc, 63u));
+}
+static_assert(PAIR_SHORT_KEYS >= (PAIR_SHORT_MAX + 1) * (PAIR_SHORT_MAX + 1) && PAIR_SHORT_KEYS + 4096 <= PAIR_TABLE, "shape table");
+static_assert(PAIR_TABLE % 1024 == 0 && PAIR_SHORT_KEYS % (PAIR_TABLE / 1024) == 0, "pairscan_kernel splits the table over 1024 threads");
+// work[] slots of the pair path (the launchers zero them)
+constexpr int PW_TOTAL = 8;      // dense slots reserved = pairs that passed the filter
+constexpr int PW_TILES_A = 9;    // tiles of the short class
+constexpr int PW_TILES_ALL = 10; // all tiles
+constexpr int PW_NPOS = 17;      // positions of the sorted pair list (pairs + padding)
+constexpr int PW_DP_A = 11;      // work counters: dp short class, dp long class, rank (two phases), scatter, filter
+constexpr int PW_DP_B = 12;
+constexpr int PW_RANK = 13;
+constexpr int PW_SCATTER = 15;
+constexpr int PW_FILTER = 16;
+
+constexpr int PF_WARPS = 8;
+__global__ void __launch_bounds__(PF_WARPS * 32)
+pairfilter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+                  const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t* hits, uint32_t* hit_count, uint32_t* qflags,
+                  uint32_t* __restrict__ qbase, uint32_t* __restrict__ hist, unsigned int* work, Counters* counters) {
+  __shared__ uint32_t pm_s[PF_WARPS][256];  // per warp: bit j of pm[c] set iff query symbol j equals c
+  __shared__ uint32_t hist_s[PAIR_BUCKETS];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t pm_a = (uint32_t)__cvta_generic_to_shared(&pm_s[warp][0]);
+  for (uint32_t k = lane; k < 256; k += 32) sts_u32(pm_a + k * 4, 0);
+  for (uint32_t k = threadIdx.x; k < PAIR_BUCKETS; k += blockDim.x) hist_s[k] = 0;
+  __syncthreads();
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  unsigned long long c_pairs = 0, c_cells = 0;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work + PW_FILTER, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t flags = qflags[qi];
+    if (flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) {
+      if (lane == 0) qbase[qi] = 0;
+      continue;
+    }
+    const uint32_t nh = hit_count[qi];
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t Lq = qrow[0];
+    uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    uint32_t w = 0;
+    if (flags & QF_PREFILTERED) {
+      // a re-run of the score stage (pool or pair-list overflow): the list is filtered already, only the shapes
+      // are counted again
+      for (uint32_t hb = 0; hb < nh; hb += 32) {
+        const uint32_t hi = hb + lane;
+        if (hi < nh) atomicAdd(&hist_s[pair_bucket(Lq, __ldg(rows + (size_t)hq[hi] * nstride))], 1u);
+      }
+      w = nh;
+    } else {
+      const uint32_t ke = apply_threshold(bp.max_edit, Lq);
+      const bool osa = Lq <= 32;  // the bit-parallel distance holds the query in one 32-bit word
+      uint32_t mysym = 256u + lane;  // (lanes beyond the query get unique values: they match nobody)
+      if (osa) {
+        if (lane < Lq) mysym = qrow[2 + lane];
+        const uint32_t mm = __match_any_sync(FULL, mysym);  // the lanes (= query positions) holding the same symbol
+        if (lane < Lq) sts_u32(pm_a + mysym * 4, mm);
+        __syncwarp();
+      }
+      const uint32_t top = 1u << ((Lq - 1) & 31);
+      const uint32_t osa_max = ke + ke / 2;
+      for (uint32_t hb = 0; hb < nh; hb += 32) {
+        const uint32_t hi = hb + lane;
+        bool valid = hi < nh;
+        uint32_t g = 0, Lc = 0;
+        const uint8_t* row = rows;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          g = hq[hi];
+          row = rows + (size_t)g * nstride;
+          v0 = __ldg(reinterpret_cast<const uint4*>(row));
+          Lc = v0.x & 0xFF;
+          const uint32_t diff = Lq > Lc ? Lq - Lc : Lc - Lq;
+          valid = diff <= ke;  // length pre-check of damerau_levenshtein (src/distance.rs:109-130)
+          if (valid) {
+            c_pairs += 1;
+            c_cells += (unsigned long long)Lq * Lc;
+          }
+        }
+        const uint32_t Lreal = Lc;
+        if (!valid) Lc = 0;
+        bool pass = valid;
+        if (osa) {
+          const uint32_t Lcm = __reduce_max_sync(FULL, Lc);
+          uint32_t D0 = 0, VP = 0xFFFFFFFFu, VN = 0, PMp = 0, sc = Lq;
+          const uint32_t nbytes = Lcm ? Lcm + 2 : 0;  // row bytes to walk: len, flags, symbols
+          for (uint32_t k0 = 0; k0 < nbytes; k0 += 16) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (k0 < Lc + 2 && Lc) v = (k0 == 0) ? v0 : __ldg(reinterpret_cast<const uint4*>(row + k0));
+            uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+            uint32_t pos = k0, steps = min(16u, nbytes - k0);
+            if (k0 == 0) {  // skip the length and flag bytes
+              x = __funnelshift_r(x, y, 16);
+              y = __funnelshift_r(y, z, 16);
+              z = __funnelshift_r(z, t, 16);
+              t >>= 16;
+              pos = 2;
+              steps -= 2;
+            }
+            for (uint32_t st = 0; st < steps; ++st, ++pos) {
+              const uint32_t c = x & 0xFFu;
+              x = __funnelshift_r(x, y, 8);
+              y = __funnelshift_r(y, z, 8);
+              z = __funnelshift_r(z, t, 8);
+              t >>= 8;
+              if (pos < Lc + 2) {  // this lane's candidate still has symbols (never for dropped lanes: Lc = 0)
+                const uint32_t PMj = lds_u32(pm_a + c * 4);
+                const uint32_t TR = ((~D0 & PMj) << 1) & PMp;  // adjacent transposition
+                D0 = TR | (((PMj & VP) + VP) ^ VP) | PMj | VN;
+                const uint32_t HP = VN | ~(D0 | VP);
+                const uint32_t HN = D0 & VP;
+                sc += (HP & top) ? 1u : 0u;
+                sc -= (HN & top) ? 1u : 0u;
+                const uint32_t X = (HP << 1) | 1u;
+                VP = (HN << 1) | ~(D0 | X);
+                VN = X & D0;
+                PMp = PMj;
+              }
+            }
+          }
+          pass = valid && sc <= osa_max;
+        }
+        const uint32_t pmask = __ballot_sync(FULL, pass);
+        __syncwarp();  // every lane has read its entry of this batch: the compacted list may overwrite it
+        if (pass) {
+          hq[w + __popc(pmask & lanemask_lt())] = g;
+          atomicAdd(&hist_s[pair_bucket(Lq, Lreal)], 1u);
+        }
+        w += __popc(pmask);
+      }
+      __syncwarp();
+      if (osa && lane < Lq) sts_u32(pm_a + mysym * 4, 0);  // leave the table clean for the next query
+    }
+    if (lane == 0) {
+      hit_count[qi] = w;
+      qflags[qi] = flags | QF_PREFILTERED;
+      qbase[qi] = w ? atomicAdd(work + PW_TOTAL, w) : 0;  // the query's dense slot range
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < PAIR_BUCKETS; k += blockDim.x) {
+    const uint32_t v = hist_s[k];
+    if (v) atomicAdd(hist + k, v);
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      c_pairs += __shfl_xor_sync(FULL, c_pairs, o);
+      c_cells += __shfl_xor_sync(FULL, c_cells, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->dl_pairs, c_pairs);
+      atomicAdd(&counters->dl_cells, c_cells);
+    }
+  }
+}
+
+// hist[PAIR_BUCKETS] -> first[PAIR_BUCKETS] (exclusive scan; the long class starts at a multiple of 32), cursors zeroed,
+// tile counts published.  One CTA.
+__global__ void __launch_bounds__(1024)
+pairscan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first, uint32_t* __restrict__ cursor,
+                uint32_t* __restrict__ pair_q, uint32_t pair_cap, unsigned int* work) {
+  __shared__ uint32_t s_part[1024];
+  __shared__ uint32_t s_short;
+  constexpr uint32_t PER = PAIR_BUCKETS / 1024;
+  const uint32_t t = threadIdx.x;
+  uint32_t v[PER], sum = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < PER; ++k) {
+    v[k] = hist[t * PER + k];
+    sum += v[k];
+    cursor[t * PER + k] = 0;
+  }
+  s_part[t] = sum;
+  __syncthreads();
+  // inclusive scan of the 1024 partial sums (Hillis-Steele in shared memory)
+  for (uint32_t o = 1; o < 1024; o <<= 1) {
+    const uint32_t add = t >= o ? s_part[t - o] : 0;
+    __syncthreads();
+    s_part[t] += add;
+    __syncthreads();
+  }
+  if (t == PAIR_SHORT_KEYS / PER - 1) s_short = s_part[t];  // pairs of the short class
+  __syncthreads();
+  const uint32_t n_short = s_short, pad = ((n_short + 31) & ~31u) - n_short;
+  uint32_t run = s_part[t] - sum + (t * PER >= PAIR_SHORT_KEYS ? pad : 0);
+#pragma unroll
+  for (uint32_t k = 0; k < PER; ++k) {
+    first[t * PER + k] = run;
+    run += v[k];
+  }
+  if (t < pad && n_short + t < pair_cap) pair_q[n_short + t] = PAIR_HOLE;  // the padding positions hold no pair
+  if (t == 1023) {
+    const uint32_t n_all = s_part[1023] + pad;  // positions incl. the padding between the classes
+    work[PW_TILES_A] = (n_short + 31) / 32;
+    work[PW_TILES_ALL] = (n_all + 31) / 32;
+    work[PW_NPOS] = n_all;
+  }
+}
+
+// every surviving candidate takes the next position of its shape
+constexpr int PS_WARPS = 8;
+__global__ void __launch_bounds__(PS_WARPS * 32)
+pairscatter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+                   const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
+                   const uint32_t* __restrict__ hit_count, const uint32_t* __restrict__ qflags, const uint32_t* __restrict__ qbase,
+                   const uint32_t* __restrict__ first, uint32_t* __restrict__ cursor, uint32_t* __restrict__ pair_q,
+                   uint32_t* __restrict__ pair_g, uint32_t* __restrict__ pair_d, uint32_t pair_cap, unsigned int* work) {
+  const uint32_t lane = lane_id();
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work + PW_SCATTER, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    if (qflags[qi] & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) continue;
+    const uint32_t nh = hit_count[qi];
+    if (nh == 0) continue;
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint32_t Lq = queries[(size_t)q * bp.query_stride];
+    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    const uint32_t base = qbase[qi];
+    for (uint32_t hb = 0; hb < nh; hb += 32) {
+      const uint32_t k = hb + lane;
+      const bool valid = k < nh;
+      uint32_t g = 0, bucket = PAIR_BUCKETS + lane;  // (idle lanes: unique keys, they match nobody)
+      if (valid) {
+        g = hq[k];
+        bucket = pair_bucket(Lq, __ldg(rows + (size_t)g * nstride));
+      }
+      const uint32_t peers = __match_any_sync(FULL, bucket);
+      if (valid) {
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if (lane == leader) pos = atomicAdd(cursor + bucket, (uint32_t)__popc(peers));
+        pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt()) + first[bucket];
+        const uint32_t d = base + k;
+        if (pos < pair_cap && d < pair_cap) {
+          pair_q[pos] = qi;
+          pair_g[pos] = g;
+          pair_d[pos] = d;
+        }
+      }
+    }
+  }
+}
+
+// ---- the DP over tiles of 32 same-shape pairs -------------------------------------------------------------------------
+// shared memory of one warp (dynamic; sized by the launch class: MQ query rows, MC candidate columns, ring depth R)
+//   qs[MQ][32] (uint8)             query symbols, per lane
+//   cell[(MC+1)][32] (uint32)      per column j, per lane: {t[j-1], lcs[j], lastrow[j], D[i-1][j]}
+//   ring[R][(MC+1)][32] (uint8)    the last R rows of the DL matrix, per lane
+__host__ __device__ inline size_t dp_warp_bytes(uint32_t MQ, uint32_t MC, uint32_t R) {
+  return (size_t)MQ * 32 + (size_t)(MC + 1) * 32 * 4 + (size_t)R * (MC + 1) * 32;
+}
+constexpr int DP_WARPS = 4;
+#ifndef ANL_DP_MIN_CTAS
+#define ANL_DP_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(DP_WARPS * 32, ANL_DP_MIN_CTAS)
+dp_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+          const uint32_t* __restrict__ qlist, const uint32_t* __restrict__ pair_q, const uint32_t* __restrict__ pair_g,
+          const uint32_t* __restrict__ pair_d, uint32_t pair_cap, uint32_t* __restrict__ res, unsigned int* work, int cls,
+          Counters* counters, uint32_t MQ, uint32_t MC, uint32_t R) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * (uint32_t)dp_warp_bytes(MQ, MC, R);
+  const uint32_t qs_a = sbase + lane;                                        // + i * 32
+  const uint32_t cell_a = sbase + MQ * 32 + lane * 4;                        // + j * 128
+  const uint32_t ring_a = sbase + MQ * 32 + (MC + 1) * 32 * 4 + lane;        // + slot * rowbytes + j * 32
+  const uint32_t rowbytes = (MC + 1) * 32;
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  // tiles [t_lo, t_hi) of this launch class; positions beyond n_pos hold nothing
+  const uint32_t tiles_a = work[PW_TILES_A], tiles_all = work[PW_TILES_ALL];
+  const uint32_t t_lo = cls == 0 ? 0u : tiles_a, t_hi = cls == 0 ? tiles_a : tiles_all;
+  const uint32_t n_pos = min(work[PW_NPOS], pair_cap);
+  unsigned int* counter = work + (cls == 0 ? PW_DP_A : PW_DP_B);
+  const uint32_t S = R;  // shift of row / column numbers: "no previous occurrence" (0) fails the reach test
+  unsigned long long c_dpp = 0, c_dpc = 0;
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = t_lo + atomicAdd(counter, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= t_hi) break;
+    const uint32_t p = tile * 32 + lane;
+    uint32_t qi = PAIR_HOLE, g = 0, d = 0;
+    if (p < n_pos) {
+      qi = pair_q[p];
+      g = pair_g[p];
+      d = pair_d[p];
+    }
+    const bool valid = qi != PAIR_HOLE;
+    uint32_t Lq = 0, Lc = 0, ke = 0;
+    if (valid) {
+      // stage the query's and the candidate's symbols, one per shared-memory row / column of this lane
+      const uint32_t q = qlist ? qlist[qi] : qi;
+      const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+      const uint8_t* row = rows + (size_t)g * nstride;
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(qrow));
+      const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(row));
+      Lq = min(q0.x & 0xFF, MQ);  // (the class bounds hold by construction of the tiles; the clamp guards the arrays)
+      Lc = min(c0.x & 0xFF, MC);
+      ke = apply_threshold(bp.max_edit, q0.x & 0xFF);
+      for (uint32_t j0 = 0; j0 < Lq + 2; j0 += 16) {
+        const uint4 v = (j0 == 0) ? q0 : __ldg(reinterpret_cast<const uint4*>(qrow + j0));
+        uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+        const uint32_t jend = min(j0 + 16, Lq + 2);
+#pragma unroll 1
+        for (uint32_t bytepos = j0; bytepos < jend; ++bytepos) {
+          const uint32_t sym = x & 0xFFu;
+          x = __funnelshift_r(x, y, 8);
+          y = __funnelshift_r(y, z, 8);
+          z = __funnelshift_r(z, t, 8);
+          t >>= 8;
+          if (bytepos >= 2) sts_u8(qs_a + (bytepos - 2) * 32, sym);
+        }
+      }
+      for (uint32_t j0 = 0; j0 < Lc + 2; j0 += 16) {
+        const uint4 v = (j0 == 0) ? c0 : __ldg(reinterpret_cast<const uint4*>(row + j0));
+        uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+        const uint32_t jend = min(j0 + 16, Lc + 2);
+#pragma unroll 1
+        for (uint32_t bytepos = j0; bytepos < jend; ++bytepos) {
+          const uint32_t sym = x & 0xFFu;
+          x = __funnelshift_r(x, y, 8);
+          y = __funnelshift_r(y, z, 8);
+          z = __funnelshift_r(z, t, 8);
+          t >>= 8;
+          // column j = bytepos - 1: {t, lcs = 0, lastrow = 0, D[0][j] = j}
+          if (bytepos >= 2) sts_u32(cell_a + (bytepos - 1) * 128, sym | ((bytepos - 1) << 24));
+        }
+      }
+    }
+    const uint32_t Lqm = __reduce_max_sync(FULL, Lq), Lcm = __reduce_max_sync(FULL, Lc);
+    // (tiles are same-shape except where two shapes meet: shorter strings are padded with symbols that match nothing)
+    for (uint32_t i = Lq; i < Lqm; ++i) sts_u8(qs_a + i * 32, 0xFEu);
+    for (uint32_t j = Lc + 1; j <= Lcm; ++j) sts_u32(cell_a + j * 128, 0xFFu | (j << 24));
+    for (uint32_t j = 0; j <= Lcm; ++j) sts_u8(ring_a + j * 32, j);  // row 0 in slot 0
+    c_dpp += valid ? 1 : 0;
+    c_dpc += (unsigned long long)Lqm * Lcm;  // per lane: x 32 lanes in the sum = warp-cells of this tile
+
+    // ---- true Damerau-Levenshtein, all lanes in lock-step over (i, j); see score_kernel for the recurrence -------
+    uint32_t lcs_best = 0, ld = 255;
+    uint32_t slot = 0;  // ring slot of row i - 1
+    for (uint32_t i = 1; i <= Lqm; ++i) {
+      const uint32_t sc = lds_u8(qs_a + (i - 1) * 32);
+      slot = slot + 1 == R ? 0 : slot + 1;
+      const uint32_t cur_a = ring_a + slot * rowbytes;
+      const uint32_t is = i + S;  // shifted row number
+      uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
+      sts_u8(cur_a, i);
+      for (uint32_t j = 1; j <= Lcm; ++j) {
+        const uint32_t cw = lds_u32(cell_a + j * 128);
+        const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF, up = cw >> 24;
+        const bool same = tc == sc;
+        const uint32_t js = j + S;
+        uint32_t v = min(min(left, up) + 1, diag + (same ? 0u : 1u));
+        // transposition (src/distance.rs:160-165): mat[last][db] + (i-last-1) + 1 + (j-db-1); a term that
+        // reaches back more than ke + 1 in total cannot be <= ke and is skipped (exact)
+        const uint32_t reach = (is - last) + (js - db);
+        if (reach <= ke + 1) {
+          const uint32_t back = is - last + 1;  // rows between row i and row last-1
+          const uint32_t ts = slot >= back ? slot - back : slot + R - back;
+          const uint32_t tv = lds_u8(ring_a + ts * rowbytes + (db - S - 1) * 32) + reach - 1;
+          v = min(v, tv);
+        }
+        sts_u8(cur_a + j * 32, v);  // (a distance never exceeds the longer side: it fits the byte)
+        const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
+        lcs_best = max(lcs_best, lcs_new);
+        sts_u32(cell_a + j * 128, tc | (lcs_new << 8) | ((same ? is : last) << 16) | (v << 24));
+        if (same) db = js;
+        lcs_diag = lcs_up;
+        diag = up;
+        left = v;
+      }
+      if (i == Lq) ld = lds_u8(cur_a + Lc * 32);  // this lane's own matrix ends here
+    }
+    // ---- prefix / suffix (src/distance.rs:208-231) ------------------------------------------------
+    uint32_t pre = 0, suf = 0;
+    const bool within = valid && ld <= ke;
+    {
+      const uint32_t lim = min(Lqm, Lcm);
+      bool pgo = within, sgo = within;
+      for (uint32_t i = 0; i < lim; ++i) {
+        if (within && i < Lc && i < Lq) {
+          const uint32_t a = lds_u32(cell_a + (i + 1) * 128) & 0xFF;
+          pgo = pgo && (a == lds_u8(qs_a + i * 32));
+          pre += pgo;
+          const uint32_t b = lds_u32(cell_a + (Lc - i) * 128) & 0xFF;
+          sgo = sgo && (b == lds_u8(qs_a + (Lq - 1 - i) * 32));
+          suf += sgo;
+        }
+      }
+    }
+    if (valid && d < pair_cap) res[d] = within ? (ld | (lcs_best << 8) | (pre << 16) | (suf << 24)) : RES_REJECT;
+    __syncwarp();
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      c_dpp += __shfl_xor_sync(FULL, c_dpp, o);
+      c_dpc += __shfl_xor_sync(FULL, c_dpc, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->dp_pairs, c_dpp);
+      atomicAdd(&counters->dp_cells, c_dpc);
+    }
+  }
+}
+
+// ---- per query: features -> score -> rank / crop / cut-off -------------------------------------------------------------
+__global__ void __launch_bounds__(K2_WARPS * 32)
+rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+            const uint32_t* __restrict__ qlist, uint32_t* __restrict__ rec_query, uint32_t nq, const uint32_t* __restrict__ hits,
+            const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, const uint32_t* __restrict__ qbase,
+            const uint32_t* __restrict__ res, uint32_t pair_cap, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
+            OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters) {
+  const uint32_t lane = lane_id();
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+  SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
+  SurvRec* sorted = surv + bp.hit_cap;
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  const int have_freq = ix->have_freq;
+  const uint32_t* __restrict__ gid_of = ix->inst_gid;
+  unsigned long long c_surv = 0, c_res = 0;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(work + PW_RANK, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
+    const uint32_t flags = qflags[qi];
+    const uint32_t nh = hit_count[qi];
+    const uint32_t base = qbase[qi];
+    if ((flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) || (unsigned long long)base + nh > pair_cap) {
+      // (a query beyond the pair-list capacity: the host runs the score stage again with a larger list)
+      if (lane == 0) {
+        OutHead h;
+        h.max_freq = 0.0;
+        h.offset = 0;
+        h.count = 0;
+        out_head[qi] = h;
+      }
+      continue;
+    }
+    const uint32_t q = qlist ? qlist[qi] : qi;
+    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
+    const uint32_t Lq = qrow[0];
+    const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
+    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+    const double Ld = (double)Lq;
+    // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
+    // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
+    const double quot_lane = __ddiv_rn((double)lane, Ld);
+    const bool quot_ok = Lq <= 31;
+    uint32_t nsurv = 0;
+    double maxfreq = 0.0;
+    for (uint32_t hb = 0; hb < nh; hb += 32) {
+      const uint32_t k = hb + lane;
+      uint32_t r = RES_REJECT, g = 0;
+      if (k < nh) {
+        r = res[base + k];
+        g = hq[k];
+      }
+      const bool valid = r != RES_REJECT;
+      const uint32_t ld = r & 0xFF;
+      bool c_lower = false;
+      if (valid) c_lower = (__ldg(rows + (size_t)g * nstride + 1) & ROW_FIRST_LOWER) != 0;
+      // features are skipped (0 / true) when their weight is <= 0 (src/lib.rs:1352-1377)
+      const uint32_t f_lcs = (valid && bp.w_lcs > 0.0) ? (r >> 8) & 0xFF : 0;
+      const uint32_t f_pre = (valid && bp.w_prefix > 0.0) ? (r >> 16) & 0xFF : 0;
+      const uint32_t f_suf = (valid && bp.w_suffix > 0.0) ? r >> 24 : 0;
+      const bool samecase = bp.w_case > 0.0 ? (c_lower == q_lower) : true;
+      // ---- f64 score, left to right, no FMA (src/lib.rs:1433-1452) -----------------------------------
+      double q_ld, q_lcs, q_pre, q_suf;
+      if (quot_ok) {  // warp-uniform; all four indices are <= Lq <= 31 (ld is clamped: it only matters when <= Lq)
+        q_ld = __shfl_sync(FULL, quot_lane, min(ld, 31u));
+        q_lcs = __shfl_sync(FULL, quot_lane, f_lcs);
+        q_pre = __shfl_sync(FULL, quot_lane, f_pre);
+        q_suf = __shfl_sync(FULL, quot_lane, f_suf);
+      } else {
+        q_ld = __ddiv_rn((double)ld, Ld);
+        q_lcs = __ddiv_rn((double)f_lcs, Ld);
+        q_pre = __ddiv_rn((double)f_pre, Ld);
+        q_suf = __ddiv_rn((double)f_suf, Ld);
+      }
+      const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, q_ld);
+      double acc = __dmul_rn(bp.w_ld, ds);
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, q_lcs));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, q_pre));
+      acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, q_suf));
+      acc = __dadd_rn(acc, samecase ? bp.w_case : 0.0);
+      const double score = __ddiv_rn(acc, bp.w_sum);
+      double freq = 1.0;
+      if (valid && have_freq) freq = (double)__ldg(ix->inst_freq + g);
+      // max_freq is taken over every instance within the edit distance, before the score threshold
+      double mf = valid ? freq : 0.0;
+      for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
+      maxfreq = fmax(maxfreq, mf);
+      c_surv += valid ? 1 : 0;
+      const bool keep = valid && score >= bp.score_threshold;
+      const uint32_t kmask = __ballot_sync(FULL, keep);
+      if (keep) {
+        SurvRec s;
+        s.dist = score;
+        s.freq = freq;
+        s.key = 0.0;
+        s.g = gid_of ? __ldg(gid_of + g) : g;  // sharded index: global gather id
+        s.raw = (uint32_t)freq;               // raw frequency (exact: u32 or 1.0)
+        s.vocab = __ldg(ix->inst_vocab + g);
+        s.pad = 0;
+        surv[nsurv + __popc(kmask & lanemask_lt())] = s;
+      }
+      nsurv += __popc(kmask);
+      __syncwarp();
+    }
+    ConfStage cs;
+    if (rec_query && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
+      cs.rec_query = rec_query;
+      cs.qrow = q;
+    }
+    c_res += rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags,
+                            qflags, work + 2, 0, cs);
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      c_surv += __shfl_xor_sync(FULL, c_surv, o);
+      c_res += __shfl_xor_sync(FULL, c_res, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->survivors, c_surv);
+      atomicAdd(&counters->results, c_res);
+    }
+  }
+}
+
+
+// ================================================================================================
 // launchers
 // ================================================================================================
 static int g_k1_ctas_per_sm = 0;
@@ -2260,6 +2830,8 @@ cudaError_t configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(probe_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_fn(), K1_WARPS * 32, sizeof(K1Shared));
   return e;
@@ -2432,6 +3004,72 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
   e = cudaMemsetAsync(lb.work, 0, sizeof(unsigned int), stream);  // the probe kernel's counter is free again
   if (e != cudaSuccess) return e;
   return launch_score_class(d_ix, bp, lb, sm_count, stream, ML, K2_SHORT_COLS + 1, ML, lb.work, lb.work + 7, grid_b, 0);
+}
+
+// The pair-list score stage: filter + shape histogram, scan, scatter, DP per shape class, rank.  work[8..17] are its
+// counters (zeroed here); the caller checks work[PW_TOTAL] <= lb.pair_cap afterwards (else: run the stage again with a
+// larger pair list).
+static int dp_ctas_per_sm(size_t smem) {
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dp_kernel, DP_WARPS * 32, smem);
+  if (e != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
+                               int sm_count, cudaStream_t stream, cudaEvent_t ev_filter_done) {
+  if (lb.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(lb.work + 1, 0, 3 * sizeof(unsigned int), stream);  // (unused), pool cursor, confusable queue
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(lb.work + 8, 0, 10 * sizeof(unsigned int), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(lb.pair_hist, 0, PAIR_BUCKETS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  auto grid_for = [&](int warps_per_cta, int ctas_per_sm) {
+    long long grid = (long long)sm_count * ctas_per_sm;
+    const long long want = ((long long)lb.n + warps_per_cta - 1) / warps_per_cta;
+    if (grid > want) grid = want;
+    return (unsigned)(grid < 1 ? 1 : grid);
+  };
+  pairfilter_kernel<<<grid_for(PF_WARPS, 6), PF_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
+                                                                        lb.qflags, lb.qbase, lb.pair_hist, lb.work, lb.counters);
+  pairscan_kernel<<<1, 1024, 0, stream>>>(lb.pair_hist, lb.pair_first, lb.pair_cursor, lb.pair_q, lb.pair_cap, lb.work);
+  pairscatter_kernel<<<grid_for(PS_WARPS, 8), PS_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
+                                                                          lb.qflags, lb.qbase, lb.pair_first, lb.pair_cursor,
+                                                                          lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap, lb.work);
+  g_kernel_launches += 3;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (ev_filter_done && (e = cudaEventRecord(ev_filter_done, stream)) != cudaSuccess) return e;
+  const uint32_t R = ring_depth(bp);
+  // short shapes: both sides <= PAIR_SHORT_MAX (nearly all pairs); long shapes: sized by the longest entry / query
+  const uint32_t longest_q = std::min<uint32_t>(bp.query_stride - 2, (uint32_t)ANL_MAX_SYMBOLS);
+  {
+    const uint32_t MQ = std::min(PAIR_SHORT_MAX, longest_q), MC = std::min(PAIR_SHORT_MAX, h_ix.max_len);
+    const size_t smem = dp_warp_bytes(MQ, MC, R) * DP_WARPS;
+    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * dp_ctas_per_sm(smem), (long long)sm_count * 16);
+    dp_kernel<<<grid, DP_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap,
+                                                     lb.pair_res, lb.work, 0, lb.counters, MQ, MC, R);
+    ++g_kernel_launches;
+  }
+  if (std::max(longest_q, h_ix.max_len) > PAIR_SHORT_MAX) {
+    const uint32_t MQ = longest_q, MC = h_ix.max_len;
+    const size_t smem = dp_warp_bytes(MQ, MC, R) * DP_WARPS;
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * dp_ctas_per_sm(smem), (long long)sm_count * 2);
+    dp_kernel<<<grid, DP_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap,
+                                                     lb.pair_res, lb.work, 1, lb.counters, MQ, MC, R);
+    ++g_kernel_launches;
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  {
+    long long grid = (long long)sm_count * 8;
+    const long long want = ((long long)lb.n + K2_WARPS - 1) / K2_WARPS;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    rank_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.rec_query, lb.n, lb.hits, lb.hit_count,
+                                                              lb.qflags, lb.qbase, lb.pair_res, lb.pair_cap, lb.out, lb.out_gid,
+                                                              lb.out_head, reinterpret_cast<SurvRec*>(lb.scratch), lb.work,
+                                                              lb.counters);
+    ++g_kernel_launches;
+  }
+  return cudaGetLastError();
 }
 
 // The device confusable stage: triage of every emitted record, edit scripts of the queued pairs; launch_finish then

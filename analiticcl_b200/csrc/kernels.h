@@ -24,7 +24,18 @@ struct LaunchBuffers {
   OutHead* out_head = nullptr;       // [n] per-query header: offset / count into the pool, max_freq
   void* scratch = nullptr;           // score kernel scratch: score_scratch_bytes(...)
   unsigned int* work = nullptr;      // [0],[1] work-stealing counters, [2] pool cursor, [3] confusable queue length,
-                                     // [4] staged-node queue length, [5] exact-stage work counter (zeroed by the launchers)
+                                     // [4] staged-node queue length, [5] exact-stage work counter, [8..17] pair-list path
+                                     // (zeroed by the launchers); WORK_SLOTS entries
+  // pair-list score stage (launch_score_pairs): dense slot base per query, the shape-sorted pair list, packed features
+  uint32_t* qbase = nullptr;         // [n]
+  uint32_t* pair_q = nullptr;        // [pair_cap] query of the pair at a sorted position (0xFFFFFFFF = no pair)
+  uint32_t* pair_g = nullptr;        // [pair_cap] candidate (gather id)
+  uint32_t* pair_d = nullptr;        // [pair_cap] dense slot of the pair (qbase[query] + position in its hit list)
+  uint32_t* pair_res = nullptr;      // [pair_cap] by dense slot: ld | lcs << 8 | prefix << 16 | suffix << 24, or 0xFFFFFFFF
+  uint32_t pair_cap = 0;
+  uint32_t* pair_hist = nullptr;     // [PAIR_TABLE] pairs per shape
+  uint32_t* pair_first = nullptr;    // [PAIR_TABLE] first sorted position of a shape
+  uint32_t* pair_cursor = nullptr;   // [PAIR_TABLE]
   QEntry* queue = nullptr;           // optional (split probe path): staged nodes of the whole launch, queue_cap entries
   uint32_t queue_cap = 0;
   QCtx* qctx = nullptr;              //          per-query context for the exact stage, [n]
@@ -51,6 +62,14 @@ cudaError_t launch_prefilter(const DeviceIndex* d_ix, const BatchParams& bp, con
 // cropping and cut-off.
 cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                          int sm_count, cudaStream_t stream);
+// The same stage (prefilter + score) over a global, shape-sorted pair list: every lane of the DP holds a pair of the
+// same matrix shape, whatever query it belongs to.  ev_filter_done (optional) is recorded after the filter / sort
+// kernels.  The caller checks work[WORK_PAIR_TOTAL] <= lb.pair_cap afterwards.
+cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
+                               int sm_count, cudaStream_t stream, cudaEvent_t ev_filter_done);
+static const int WORK_SLOTS = 24;       // entries of LaunchBuffers::work
+static const int WORK_PAIR_TOTAL = 8;   // pairs that passed the filter = dense slots needed
+static const uint32_t PAIR_TABLE = 5120;  // entries of the per-shape tables
 // Confusable rescoring on the device (only when launch_score filled lb.conf_work): edit script + pattern
 // matching per queued pair, then re-rank / crop / cut-off per query in place.  Queries the device cannot
 // settle get HEAD_HOST_FINISH in their header.
