@@ -489,7 +489,7 @@ void Engine::destroy_batch(DeviceBatch* b) {
     if (p) cudaFreeHost(p);
   for (void* p : {(void*)b->d_final, (void*)b->d_loff, (void*)b->d_oflags, (void*)b->d_off64, (void*)b->d_tile_sum,
                   (void*)b->d_summary, (void*)b->rr_conf_work, (void*)b->rr_work, (void*)b->d_rec_query, (void*)b->rr_rec_query,
-                  (void*)b->d_qbase, (void*)b->d_pair_q, (void*)b->d_pair_g, (void*)b->d_pair_d, (void*)b->d_pair_res,
+                  (void*)b->d_qbase, (void*)b->d_pairs, (void*)b->d_pair_res,
                   (void*)b->d_pair_tab})
     if (p) cudaFree(p);
   if (b->d_qblob) cudaFree(b->d_qblob);
@@ -600,11 +600,9 @@ bool Engine::ensure_capacity(DeviceBatch* b, uint32_t n, uint32_t stride, uint32
 }
 
 bool Engine::grow_pairs(DeviceBatch* b, size_t pair_cap, std::string* err) {
-  if (pair_cap <= b->cap_pairs && b->d_pair_q) return true;
+  if (pair_cap <= b->cap_pairs && b->d_pairs) return true;
   pair_cap = std::min<size_t>(std::max(pair_cap, b->cap_pairs), 0xFFFFFF00u);
-  if (!dev_realloc(&b->d_pair_q, pair_cap, err) || !dev_realloc(&b->d_pair_g, pair_cap, err) ||
-      !dev_realloc(&b->d_pair_d, pair_cap, err) || !dev_realloc(&b->d_pair_res, pair_cap, err))
-    return false;
+  if (!dev_realloc(&b->d_pairs, pair_cap, err) || !dev_realloc(&b->d_pair_res, pair_cap, err)) return false;
   b->cap_pairs = pair_cap;
   return true;
 }
@@ -868,9 +866,7 @@ static LaunchBuffers launch_buffers(const DeviceBatch* b) {
   }
   if (b->use_pairs) {
     lb.qbase = b->d_qbase;
-    lb.pair_q = b->d_pair_q;
-    lb.pair_g = b->d_pair_g;
-    lb.pair_d = b->d_pair_d;
+    lb.pairs = b->d_pairs;
     lb.pair_res = b->d_pair_res;
     lb.pair_cap = (uint32_t)b->cap_pairs;
     lb.pair_hist = b->d_pair_tab;
@@ -924,7 +920,7 @@ static bool download_summary(DeviceBatch* b, cudaStream_t st, std::string* err) 
 
 // prefilter + score: over the shape-sorted pair list, or query by query (ANL_PAIRS=0, re-runs of overflowed queries)
 bool Engine::launch_score_stage(DeviceBatch* b, const LaunchBuffers& lb, cudaStream_t st, cudaEvent_t ev_filter, std::string* err) {
-  if (b->use_pairs && lb.pair_q) {
+  if (b->use_pairs && lb.pairs) {
     CU_TRY(launch_score_pairs(d_ix_, h_ix_, b->bp, lb, sm_count_, st, ev_filter));
     return true;
   }

@@ -78,10 +78,8 @@ struct DeviceBatch {
   // pair-list score stage (kernels.cu "Kernels 2p"): dense slot base per query, shape-sorted pair list, packed features
   bool use_pairs = false;
   uint32_t* d_qbase = nullptr;      // [cap_n]
-  uint32_t* d_pair_q = nullptr;     // [cap_pairs] each
-  uint32_t* d_pair_g = nullptr;
-  uint32_t* d_pair_d = nullptr;
-  uint32_t* d_pair_res = nullptr;
+  uint4* d_pairs = nullptr;         // [cap_pairs]
+  uint32_t* d_pair_res = nullptr;   // [cap_pairs]
   uint32_t* d_pair_tab = nullptr;   // [3][PAIR_TABLE]: histogram, first position, cursor per shape
   size_t cap_pairs = 0;
   // export stage (export.cu): final arrays of this batch, in query order

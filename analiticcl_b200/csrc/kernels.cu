@@ -1271,23 +1271,27 @@ __device__ __forceinline__ uint32_t u8_decode_bmp(const uint8_t* __restrict__ s,
 }
 
 __device__ __noinline__ int confusable_triage(const DeviceIndex* ix, const uint8_t* __restrict__ a, uint32_t na,
-                                              const uint8_t* __restrict__ b, uint32_t nb, double* weight, uint32_t* cost) {
+                                              const uint8_t* __restrict__ b, uint32_t nb, double* weight, uint32_t* cost,
+                                              bool* wide) {
   *weight = 1.0;
   *cost = 0;
   // characters per string; a four-byte sequence (lead byte >= 0xF0) lies outside the BMP
-  uint32_t ca = 0, cb = 0, big = 0;
+  uint32_t ca = 0, cb = 0, big = 0, hibits = 0;
 #pragma unroll 1
   for (uint32_t i = 0; i < na; ++i) {
     const uint32_t ch = a[i];
     ca += !u8_cont(ch);
     big |= ch >= 0xF0;
+    hibits |= ch;
   }
 #pragma unroll 1
   for (uint32_t i = 0; i < nb; ++i) {
     const uint32_t ch = b[i];
     cb += !u8_cont(ch);
     big |= ch >= 0xF0;
+    hibits |= ch;
   }
+  *wide = (hibits & 0x80) != 0;
   if (big) return CONF_HOST;
   // common prefix / suffix in bytes, moved back to character boundaries (the strings agree up to there, so a
   // boundary of one is a boundary of the other)
@@ -2017,14 +2021,16 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
 // ================================================================================================
 // Kernels 4 + 5 (only with confusables): device-side rescoring of the ranked lists
 // ================================================================================================
-// triage_kernel: one pool record per thread (the score kernel left each record's query in rec_query).  Settles the
-// pairs whose confusable weight is known without an edit script and queues the rest for confusable_kernel.  A kernel
-// of its own: inside the score kernel the triage ran on the few lanes that hold a query's results (6 of 32 on
-// cfg 2) and walked the candidate's text byte by byte at that occupancy; here every lane has a record.
+// triage_kernel: one pool record per thread (the score stage left each record's query in rec_query).  Settles the
+// pairs whose confusable weight is known without an edit script and queues the rest: pure-ASCII pairs from the front
+// of the work list (confusable_kernel, over bytes), pairs with other BMP characters from its back
+// (confusable_wide_kernel, over UTF-16 code units).  A kernel of its own: inside the score kernel the triage ran on
+// the few lanes that hold a query's results (6 of 32 on cfg 2) and walked the candidate's text byte by byte at that
+// occupancy; here every lane has a record.
 __global__ void __launch_bounds__(256)
 triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
               const uint32_t* __restrict__ rec_query, OutRec* __restrict__ out, const unsigned int* __restrict__ pool_cursor,
-              uint32_t pool_cap, ConfWork* __restrict__ worklist, unsigned int* work_cursor) {
+              uint32_t pool_cap, ConfWork* __restrict__ worklist, unsigned int* work_cursor, unsigned int* wide_cursor) {
   const uint32_t used = *pool_cursor;
   if (used > pool_cap) return;  // pool overflow: the score stage runs again with a larger pool
   const uint8_t* __restrict__ vtext = ix->vocab_text;
@@ -2032,7 +2038,7 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
   const uint32_t lane = lane_id();
   for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < used; base += gridDim.x * blockDim.x) {
     const uint32_t rec = base + lane;
-    bool queue = false;
+    bool queue = false, wide = false;
     uint32_t cost = 0, query = 0;
     if (rec < used) {
       OutRec r = out[rec];
@@ -2041,7 +2047,7 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
       const uint32_t a0 = qboff[query], a1 = qboff[query + 1];
       const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
       double w;
-      const int tri = confusable_triage(ix, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &w, &cost);
+      const int tri = confusable_triage(ix, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &w, &cost, &wide);
       // Without a work list the host runs the post-pass (variant lists, sharded mode): it only wants to know which
       // records provably keep their score -- a weight found on the spot is left for it to apply.
       if (tri == CONF_SETTLED && (w == 1.0 || worklist)) {
@@ -2052,10 +2058,15 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
       queue = tri == CONF_QUEUE;
     }
     if (worklist) {
-      const uint32_t qm = __ballot_sync(FULL, queue);
-      if (qm) {
-        uint32_t wbase = 0;
-        if (lane == 0) wbase = atomicAdd(work_cursor, (unsigned int)__popc(qm));
+      // the two queues share the array (capacity = pool capacity >= records emitted): bytes from the front, wide from the back
+      const uint32_t qa = __ballot_sync(FULL, queue && !wide), qw = __ballot_sync(FULL, queue && wide);
+      if (qa | qw) {
+        uint32_t abase = 0, wbase = 0;
+        if (lane == 0) {
+          if (qa) abase = atomicAdd(work_cursor, (unsigned int)__popc(qa));
+          if (qw) wbase = atomicAdd(wide_cursor, (unsigned int)__popc(qw));
+        }
+        abase = __shfl_sync(FULL, abase, 0);
         wbase = __shfl_sync(FULL, wbase, 0);
         if (queue) {
           ConfWork w;
@@ -2063,7 +2074,8 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
           w.query = query;
           w.cost = cost;
           w.pad = 0;
-          worklist[wbase + __popc(qm & lanemask_lt())] = w;  // capacity = pool capacity >= records emitted
+          const uint32_t pos = wide ? pool_cap - 1 - (wbase + __popc(qw & lanemask_lt())) : abase + __popc(qa & lanemask_lt());
+          worklist[pos] = w;
         }
       }
     }
@@ -2073,9 +2085,50 @@ triage_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qb
 // confusable_kernel: one queued (input, candidate) pair per thread.  Computes the edit script of the raw
 // strings and the product of the weights of all patterns found in it (rescore_confusables /
 // compute_confusable_weight, src/lib.rs:1656-1663, 1733-1756), multiplies the record's distance score and marks it
-// settled.  Pure-ASCII pairs run over bytes; pairs with other BMP characters over UTF-16 code units (one unit per
-// character).  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
-// Unicode Alphabetic ranges (boundary scores of the diff clean-up, cf. UnicodeClass in editscript.cpp)
+// settled.  Pairs outside the limits of editscript_fixed.h stay unsettled (host post-pass).
+__global__ void __launch_bounds__(64)
+confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+                  const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
+                  OutRec* __restrict__ out) {
+  const uint32_t total = min(*work_count, work_cap);
+  esf::PatTable T;
+  T.pats = ix->conf_pats;
+  T.instrs = ix->conf_instrs;
+  T.opts = ix->conf_opts;
+  T.text = ix->conf_text;
+  T.n_pats = ix->n_conf_pats;
+  const uint8_t* __restrict__ vtext = ix->vocab_text;
+  const uint32_t* __restrict__ voff = ix->vocab_text_off;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const ConfWork it = worklist[w];
+    const OutRec r = out[it.rec];
+    const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
+    const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
+    const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
+    // private copies: the diff touches every character many times
+    uint8_t a[esf::MAXLEN], b[esf::MAXLEN];
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    if (na > esf::MAXLEN || nb > esf::MAXLEN) continue;
+    for (int i = 0; i < na; ++i) a[i] = qblob[a0 + i];
+    for (int i = 0; i < nb; ++i) b[i] = vtext[b0 + i];
+    esf::View v[esf::MAXSEG];
+    const int nv = esf::shortest_edit_script(a, na, b, nb, v);
+    if (nv < 0) continue;
+    double weight = 1.0;
+    for (uint32_t k = 0; k < T.n_pats; ++k) {
+      const ConfPat pat = T.pats[k];
+      if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
+    }
+    OutRec o = r;
+    if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
+    o.vocab_id = r.vocab_id | OUT_SKIP_CONFUSABLES;
+    out[it.rec] = o;
+  }
+}
+
+// The same for the pairs with characters beyond ASCII (the back of the work list): strings decoded to UTF-16 code
+// units -- every character of the Basic Multilingual Plane is one unit -- and the Unicode Alphabetic ranges for the
+// boundary scores of the diff clean-up (cf. UnicodeClass in editscript.cpp).
 __constant__ uint32_t c_alpha_ranges[2 * 800];
 __constant__ uint32_t c_n_alpha_ranges;
 struct DeviceCharClass {
@@ -2099,31 +2152,11 @@ cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n) {
   if (e != cudaSuccess) return e;
   return cudaMemcpyToSymbol(c_n_alpha_ranges, &n, sizeof n);
 }
-
-// the wide-character variant of one pair, out of line: rare, and it keeps the byte path's code small
-__device__ __noinline__ bool confusable_weight_wide(const esf::PatTable& T, const uint8_t* __restrict__ sa, uint32_t la,
-                                                    const uint8_t* __restrict__ sb, uint32_t lb, double* weight) {
-  uint16_t a[esf::MAXLEN], b[esf::MAXLEN];
-  if (la > 3u * esf::MAXLEN || lb > 3u * esf::MAXLEN) return false;  // (the triage checked the character counts)
-  const int na = (int)u8_decode_bmp(sa, la, a, esf::MAXLEN);
-  const int nb = (int)u8_decode_bmp(sb, lb, b, esf::MAXLEN);
-  esf::View v[esf::MAXSEG];
-  const int nv = esf::shortest_edit_script_t<DeviceCharClass, uint16_t>(a, na, b, nb, v);
-  if (nv < 0) return false;
-  double w = 1.0;
-  for (uint32_t k = 0; k < T.n_pats; ++k) {
-    const ConfPat pat = T.pats[k];
-    if (esf::found_in(T, pat, a, b, v, nv)) w = __dmul_rn(w, pat.weight);
-  }
-  *weight = w;
-  return true;
-}
-
 __global__ void __launch_bounds__(64)
-confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
-                  const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ work_count, uint32_t work_cap,
-                  OutRec* __restrict__ out) {
-  const uint32_t total = min(*work_count, work_cap);
+confusable_wide_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qblob, const uint32_t* __restrict__ qboff,
+                       const ConfWork* __restrict__ worklist, const unsigned int* __restrict__ wide_count, uint32_t work_cap,
+                       OutRec* __restrict__ out) {
+  const uint32_t total = min(*wide_count, work_cap);
   esf::PatTable T;
   T.pats = ix->conf_pats;
   T.instrs = ix->conf_instrs;
@@ -2133,32 +2166,22 @@ confusable_kernel(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict_
   const uint8_t* __restrict__ vtext = ix->vocab_text;
   const uint32_t* __restrict__ voff = ix->vocab_text_off;
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-    const ConfWork it = worklist[w];
+    const ConfWork it = worklist[work_cap - 1 - w];
     const OutRec r = out[it.rec];
     const uint32_t vocab = r.vocab_id & ~OUT_SKIP_CONFUSABLES;
     const uint32_t a0 = qboff[it.query], a1 = qboff[it.query + 1];
     const uint32_t b0 = __ldg(voff + vocab), b1 = __ldg(voff + vocab + 1);
-    // private copies: the diff touches every character many times
-    uint8_t a[esf::MAXLEN], b[esf::MAXLEN];
-    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
-    uint32_t hibits = 0;
-    if (na <= esf::MAXLEN && nb <= esf::MAXLEN) {
-      for (int i = 0; i < na; ++i) hibits |= (a[i] = qblob[a0 + i]);
-      for (int i = 0; i < nb; ++i) hibits |= (b[i] = vtext[b0 + i]);
-    } else {
-      hibits = 0x80;  // more bytes than the byte path holds: characters beyond ASCII (the triage bounded the characters)
-    }
+    if (a1 - a0 > 3u * esf::MAXLEN || b1 - b0 > 3u * esf::MAXLEN) continue;  // (the triage checked the character counts)
+    uint16_t a[esf::MAXLEN], b[esf::MAXLEN];
+    const int na = (int)u8_decode_bmp(qblob + a0, a1 - a0, a, esf::MAXLEN);
+    const int nb = (int)u8_decode_bmp(vtext + b0, b1 - b0, b, esf::MAXLEN);
+    esf::View v[esf::MAXSEG];
+    const int nv = esf::shortest_edit_script_t<DeviceCharClass, uint16_t>(a, na, b, nb, v);
+    if (nv < 0) continue;
     double weight = 1.0;
-    if (hibits & 0x80) {
-      if (!confusable_weight_wide(T, qblob + a0, a1 - a0, vtext + b0, b1 - b0, &weight)) continue;
-    } else {
-      esf::View v[esf::MAXSEG];
-      const int nv = esf::shortest_edit_script(a, na, b, nb, v);
-      if (nv < 0) continue;
-      for (uint32_t k = 0; k < T.n_pats; ++k) {
-        const ConfPat pat = T.pats[k];
-        if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
-      }
+    for (uint32_t k = 0; k < T.n_pats; ++k) {
+      const ConfPat pat = T.pats[k];
+      if (esf::found_in(T, pat, a, b, v, nv)) weight = __dmul_rn(weight, pat.weight);
     }
     OutRec o = r;
     if (weight != 1.0) o.dist_score = __dmul_rn(r.dist_score, weight);
@@ -2430,7 +2453,7 @@ pairfilter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, cons
 // tile counts published.  One CTA.
 __global__ void __launch_bounds__(1024)
 pairscan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first, uint32_t* __restrict__ cursor,
-                uint32_t* __restrict__ pair_q, uint32_t pair_cap, unsigned int* work) {
+                uint4* __restrict__ pairs, uint32_t pair_cap, unsigned int* work) {
   __shared__ uint32_t s_part[1024];
   __shared__ uint32_t s_short;
   constexpr uint32_t PER = PAIR_BUCKETS / 1024;
@@ -2460,7 +2483,7 @@ pairscan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
     first[t * PER + k] = run;
     run += v[k];
   }
-  if (t < pad && n_short + t < pair_cap) pair_q[n_short + t] = PAIR_HOLE;  // the padding positions hold no pair
+  if (t < pad && n_short + t < pair_cap) pairs[n_short + t] = make_uint4(PAIR_HOLE, 0, 0, 0);  // the padding positions hold no pair
   if (t == 1023) {
     const uint32_t n_all = s_part[1023] + pad;  // positions incl. the padding between the classes
     work[PW_TILES_A] = (n_short + 31) / 32;
@@ -2475,8 +2498,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32)
 pairscatter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
                    const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ hits,
                    const uint32_t* __restrict__ hit_count, const uint32_t* __restrict__ qflags, const uint32_t* __restrict__ qbase,
-                   const uint32_t* __restrict__ first, uint32_t* __restrict__ cursor, uint32_t* __restrict__ pair_q,
-                   uint32_t* __restrict__ pair_g, uint32_t* __restrict__ pair_d, uint32_t pair_cap, unsigned int* work) {
+                   const uint32_t* __restrict__ first, uint32_t* __restrict__ cursor, uint4* __restrict__ pairs,
+                   uint32_t pair_cap, unsigned int* work) {
   const uint32_t lane = lane_id();
   const uint8_t* __restrict__ rows = ix->inst_rows;
   const uint32_t nstride = ix->norm_stride;
@@ -2507,11 +2530,7 @@ pairscatter_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, con
         if (lane == leader) pos = atomicAdd(cursor + bucket, (uint32_t)__popc(peers));
         pos = __shfl_sync(peers, pos, leader) + __popc(peers & lanemask_lt()) + first[bucket];
         const uint32_t d = base + k;
-        if (pos < pair_cap && d < pair_cap) {
-          pair_q[pos] = qi;
-          pair_g[pos] = g;
-          pair_d[pos] = d;
-        }
+        if (pos < pair_cap && d < pair_cap) pairs[pos] = make_uint4(qi, g, d, 0);  // one 16-byte record per pair
       }
     }
   }
@@ -2531,9 +2550,8 @@ constexpr int DP_WARPS = 4;
 #endif
 __global__ void __launch_bounds__(DP_WARPS * 32, ANL_DP_MIN_CTAS)
 dp_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
-          const uint32_t* __restrict__ qlist, const uint32_t* __restrict__ pair_q, const uint32_t* __restrict__ pair_g,
-          const uint32_t* __restrict__ pair_d, uint32_t pair_cap, uint32_t* __restrict__ res, unsigned int* work, int cls,
-          Counters* counters, uint32_t MQ, uint32_t MC, uint32_t R) {
+          const uint32_t* __restrict__ qlist, const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ res,
+          unsigned int* work, int cls, Counters* counters, uint32_t MQ, uint32_t MC, uint32_t R) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -2559,9 +2577,10 @@ dp_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_
     const uint32_t p = tile * 32 + lane;
     uint32_t qi = PAIR_HOLE, g = 0, d = 0;
     if (p < n_pos) {
-      qi = pair_q[p];
-      g = pair_g[p];
-      d = pair_d[p];
+      const uint4 pr = pairs[p];
+      qi = pr.x;
+      g = pr.y;
+      d = pr.z;
     }
     const bool valid = qi != PAIR_HOLE;
     uint32_t Lq = 0, Lc = 0, ke = 0;
@@ -2681,119 +2700,380 @@ dp_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_
   }
 }
 
+// ---- the same DP with the rows of the NEXT tile brought in by the TMA engine while this tile is computed ----------------
+// dp_kernel loads a tile's 32 query rows and 32 candidate rows with ordinary vector loads and only then starts the
+// matrix: every tile begins with a global-memory round trip.  Here a lane issues two 1-D bulk copies
+// (cp.async.bulk global -> shared, completion on an mbarrier of the warp) for the rows of tile t + 1 as soon as the
+// staging buffer of tile t has been unpacked, and the pair records of tile t + 2 are already on their way into
+// registers: the loads leave the issue stream, and their latency hides behind the ~3000 instructions of a tile's DP.
+// Rows are fixed-stride (norm_stride / query_stride, multiples of 16 bytes, 16-byte aligned): exactly what a 1-D bulk
+// copy needs.  Staging layout: [lane][row bytes], rows 48 bytes apart (not 32: a 128-bit shared load serves 8 lanes
+// per pass, and 8 rows 48 bytes apart fall into 8 different bank groups).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__host__ __device__ inline uint32_t dp_stage_stride(uint32_t row_bytes) { return (row_bytes % 32 == 0) ? row_bytes + 16 : row_bytes; }
+// per warp: the arrays of dp_kernel + staging for 32 query rows and 32 candidate rows + one mbarrier
+__host__ __device__ inline size_t dp_tma_warp_bytes(uint32_t MQ, uint32_t MC, uint32_t R, uint32_t qb, uint32_t cb) {
+  const size_t dp = (dp_warp_bytes(MQ, MC, R) + 15) & ~(size_t)15;
+  return dp + 32 * (size_t)(dp_stage_stride(qb) + dp_stage_stride(cb)) + 16;
+}
+__global__ void __launch_bounds__(DP_WARPS * 32, ANL_DP_MIN_CTAS)
+dp_tma_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
+              const uint32_t* __restrict__ qlist, const uint4* __restrict__ pairs, uint32_t pair_cap, uint32_t* __restrict__ res,
+              unsigned int* work, int cls, Counters* counters, uint32_t MQ, uint32_t MC, uint32_t R, uint32_t qb, uint32_t cb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t lane = lane_id();
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t wbytes = (uint32_t)dp_tma_warp_bytes(MQ, MC, R, qb, cb);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * wbytes;
+  const uint32_t qs_a = sbase + lane;                                        // + i * 32
+  const uint32_t cell_a = sbase + MQ * 32 + lane * 4;                        // + j * 128
+  const uint32_t ring_a = sbase + MQ * 32 + (MC + 1) * 32 * 4 + lane;        // + slot * rowbytes + j * 32
+  const uint32_t rowbytes = (MC + 1) * 32;
+  const uint32_t qstride = dp_stage_stride(qb), cstride = dp_stage_stride(cb);
+  const uint32_t stage_q = sbase + (((uint32_t)dp_warp_bytes(MQ, MC, R) + 15) & ~15u) + lane * qstride;
+  const uint32_t stage_c = sbase + (((uint32_t)dp_warp_bytes(MQ, MC, R) + 15) & ~15u) + 32 * qstride + lane * cstride;
+  const uint32_t bar = sbase + wbytes - 16;
+  const uint8_t* __restrict__ rows = ix->inst_rows;
+  const uint32_t nstride = ix->norm_stride;
+  const uint32_t tiles_a = work[PW_TILES_A], tiles_all = work[PW_TILES_ALL];
+  const uint32_t t_lo = cls == 0 ? 0u : tiles_a, t_hi = cls == 0 ? tiles_a : tiles_all;
+  const uint32_t n_pos = min(work[PW_NPOS], pair_cap);
+  unsigned int* counter = work + (cls == 0 ? PW_DP_A : PW_DP_B);
+  const uint32_t S = R;
+  unsigned long long c_dpp = 0, c_dpc = 0;
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t parity = 0;
+  auto grab = [&]() {
+    uint32_t t = 0;
+    if (lane == 0) t = t_lo + atomicAdd(counter, 1u);
+    return __shfl_sync(FULL, t, 0);
+  };
+  struct Pair {
+    uint32_t qi, g, d;
+  };
+  auto load_pair = [&](uint32_t tile) {
+    Pair pr{PAIR_HOLE, 0, 0};
+    const uint32_t p = tile * 32 + lane;
+    if (tile < t_hi && p < n_pos) {
+      const uint4 v = pairs[p];
+      pr.qi = v.x;
+      pr.g = v.y;
+      pr.d = v.z;
+    }
+    return pr;
+  };
+  // rows of a tile -> the staging buffer (the previous tile's rows have been unpacked: the buffer is free)
+  auto issue_rows = [&](const Pair& pr) {
+    const bool v = pr.qi != PAIR_HOLE;
+    const uint32_t nv = __popc(__ballot_sync(FULL, v));
+    fence_proxy_async_smem();  // the generic-proxy reads of the buffer precede the async-proxy writes
+    if (lane == 0) mbar_arrive_expect_tx(bar, nv * (qb + cb));
+    __syncwarp();
+    if (v) {
+      const uint32_t q = qlist ? qlist[pr.qi] : pr.qi;
+      bulk_copy_g2s(stage_q, queries + (size_t)q * bp.query_stride, qb, bar);
+      bulk_copy_g2s(stage_c, rows + (size_t)pr.g * nstride, cb, bar);
+    }
+  };
+  uint32_t tile = grab();
+  Pair cur = load_pair(tile);
+  uint32_t tile1 = grab();
+  Pair nxt = load_pair(tile1);
+  if (tile < t_hi) issue_rows(cur);
+  while (tile < t_hi) {
+    // ---- wait for this tile's rows, unpack them into the DP's column layout --------------------------------------
+    {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();  // (a lost copy would otherwise hang the device)
+      }
+      parity ^= 1;
+    }
+    const bool valid = cur.qi != PAIR_HOLE;
+    uint32_t Lq = 0, Lc = 0, ke = 0;
+    if (valid) {
+      const uint4 q0 = lds_u128(stage_q), c0 = lds_u128(stage_c);
+      Lq = min(q0.x & 0xFF, min(MQ, qb - 2));
+      Lc = min(c0.x & 0xFF, min(MC, cb - 2));
+      ke = apply_threshold(bp.max_edit, q0.x & 0xFF);
+      for (uint32_t j0 = 0; j0 < Lq + 2; j0 += 16) {
+        const uint4 v = (j0 == 0) ? q0 : lds_u128(stage_q + j0);
+        uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+        const uint32_t jend = min(j0 + 16, Lq + 2);
+#pragma unroll 1
+        for (uint32_t bytepos = j0; bytepos < jend; ++bytepos) {
+          const uint32_t sym = x & 0xFFu;
+          x = __funnelshift_r(x, y, 8);
+          y = __funnelshift_r(y, z, 8);
+          z = __funnelshift_r(z, t, 8);
+          t >>= 8;
+          if (bytepos >= 2) sts_u8(qs_a + (bytepos - 2) * 32, sym);
+        }
+      }
+      for (uint32_t j0 = 0; j0 < Lc + 2; j0 += 16) {
+        const uint4 v = (j0 == 0) ? c0 : lds_u128(stage_c + j0);
+        uint32_t x = v.x, y = v.y, z = v.z, t = v.w;
+        const uint32_t jend = min(j0 + 16, Lc + 2);
+#pragma unroll 1
+        for (uint32_t bytepos = j0; bytepos < jend; ++bytepos) {
+          const uint32_t sym = x & 0xFFu;
+          x = __funnelshift_r(x, y, 8);
+          y = __funnelshift_r(y, z, 8);
+          z = __funnelshift_r(z, t, 8);
+          t >>= 8;
+          if (bytepos >= 2) sts_u32(cell_a + (bytepos - 1) * 128, sym | ((bytepos - 1) << 24));
+        }
+      }
+    }
+    __syncwarp();
+    // ---- the staging buffer is free: the next tile's rows start their trip, the tile after that its pair records ----
+    const uint32_t tile2 = grab();
+    if (tile1 < t_hi) issue_rows(nxt);
+    const Pair nxt2 = load_pair(tile2);
+
+    const uint32_t Lqm = __reduce_max_sync(FULL, Lq), Lcm = __reduce_max_sync(FULL, Lc);
+    for (uint32_t i = Lq; i < Lqm; ++i) sts_u8(qs_a + i * 32, 0xFEu);
+    for (uint32_t j = Lc + 1; j <= Lcm; ++j) sts_u32(cell_a + j * 128, 0xFFu | (j << 24));
+    for (uint32_t j = 0; j <= Lcm; ++j) sts_u8(ring_a + j * 32, j);  // row 0 in slot 0
+    c_dpp += valid ? 1 : 0;
+    c_dpc += (unsigned long long)Lqm * Lcm;
+    uint32_t lcs_best = 0, ld = 255;
+    uint32_t slot = 0;
+    for (uint32_t i = 1; i <= Lqm; ++i) {
+      const uint32_t sc = lds_u8(qs_a + (i - 1) * 32);
+      slot = slot + 1 == R ? 0 : slot + 1;
+      const uint32_t cur_a = ring_a + slot * rowbytes;
+      const uint32_t is = i + S;
+      uint32_t left = i, diag = i - 1, db = 0, lcs_diag = 0;
+      sts_u8(cur_a, i);
+      for (uint32_t j = 1; j <= Lcm; ++j) {
+        const uint32_t cw = lds_u32(cell_a + j * 128);
+        const uint32_t tc = cw & 0xFF, lcs_up = (cw >> 8) & 0xFF, last = (cw >> 16) & 0xFF, up = cw >> 24;
+        const bool same = tc == sc;
+        const uint32_t js = j + S;
+        uint32_t v = min(min(left, up) + 1, diag + (same ? 0u : 1u));
+        const uint32_t reach = (is - last) + (js - db);
+        if (reach <= ke + 1) {
+          const uint32_t back = is - last + 1;
+          const uint32_t ts = slot >= back ? slot - back : slot + R - back;
+          const uint32_t tv = lds_u8(ring_a + ts * rowbytes + (db - S - 1) * 32) + reach - 1;
+          v = min(v, tv);
+        }
+        sts_u8(cur_a + j * 32, v);
+        const uint32_t lcs_new = same ? lcs_diag + 1 : 0;
+        lcs_best = max(lcs_best, lcs_new);
+        sts_u32(cell_a + j * 128, tc | (lcs_new << 8) | ((same ? is : last) << 16) | (v << 24));
+        if (same) db = js;
+        lcs_diag = lcs_up;
+        diag = up;
+        left = v;
+      }
+      if (i == Lq) ld = lds_u8(cur_a + Lc * 32);
+    }
+    uint32_t pre = 0, suf = 0;
+    const bool within = valid && ld <= ke;
+    {
+      const uint32_t lim = min(Lqm, Lcm);
+      bool pgo = within, sgo = within;
+      for (uint32_t i = 0; i < lim; ++i) {
+        if (within && i < Lc && i < Lq) {
+          const uint32_t a = lds_u32(cell_a + (i + 1) * 128) & 0xFF;
+          pgo = pgo && (a == lds_u8(qs_a + i * 32));
+          pre += pgo;
+          const uint32_t b = lds_u32(cell_a + (Lc - i) * 128) & 0xFF;
+          sgo = sgo && (b == lds_u8(qs_a + (Lq - 1 - i) * 32));
+          suf += sgo;
+        }
+      }
+    }
+    if (valid && cur.d < pair_cap) res[cur.d] = within ? (ld | (lcs_best << 8) | (pre << 16) | (suf << 24)) : RES_REJECT;
+    __syncwarp();
+    tile = tile1;
+    cur = nxt;
+    tile1 = tile2;
+    nxt = nxt2;
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      c_dpp += __shfl_xor_sync(FULL, c_dpp, o);
+      c_dpc += __shfl_xor_sync(FULL, c_dpc, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&counters->dp_pairs, c_dpp);
+      atomicAdd(&counters->dp_cells, c_dpc);
+    }
+  }
+}
+
 // ---- per query: features -> score -> rank / crop / cut-off -------------------------------------------------------------
+// One warp per query, but the per-query latency chain is kept short: a warp takes 32 queries per counter increment and
+// its lanes fetch their headers (flags, candidate count, dense base, length, case flag) side by side; queries with at
+// most 32 candidates (nearly all) keep their survivor lists in shared memory instead of the global scratch.
+constexpr uint32_t RK_SMEM_SURV = 32;
 __global__ void __launch_bounds__(K2_WARPS * 32)
 rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
             const uint32_t* __restrict__ qlist, uint32_t* __restrict__ rec_query, uint32_t nq, const uint32_t* __restrict__ hits,
             const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, const uint32_t* __restrict__ qbase,
             const uint32_t* __restrict__ res, uint32_t pair_cap, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
             OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters) {
+  __shared__ SurvRec s_scr[K2_WARPS][2 * RK_SMEM_SURV];
   const uint32_t lane = lane_id();
-  const uint32_t gwarp = blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
-  SurvRec* surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy
-  SurvRec* sorted = surv + bp.hit_cap;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t gwarp = blockIdx.x * K2_WARPS + warp;
+  SurvRec* g_surv = scratch + (size_t)gwarp * 2 * bp.hit_cap;  // survivors, then the sorted copy (long lists)
   const uint8_t* __restrict__ rows = ix->inst_rows;
   const uint32_t nstride = ix->norm_stride;
   const int have_freq = ix->have_freq;
   const uint32_t* __restrict__ gid_of = ix->inst_gid;
   unsigned long long c_surv = 0, c_res = 0;
   for (;;) {
-    uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(work + PW_RANK, 1u);
-    qi = __shfl_sync(FULL, qi, 0);
-    if (qi >= nq) break;
-    const uint32_t flags = qflags[qi];
-    const uint32_t nh = hit_count[qi];
-    const uint32_t base = qbase[qi];
-    if ((flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) || (unsigned long long)base + nh > pair_cap) {
-      // (a query beyond the pair-list capacity: the host runs the score stage again with a larger list)
-      if (lane == 0) {
-        OutHead h;
-        h.max_freq = 0.0;
-        h.offset = 0;
-        h.count = 0;
-        out_head[qi] = h;
-      }
-      continue;
+    uint32_t q0 = 0;
+    if (lane == 0) q0 = atomicAdd(work + PW_RANK, 32u);
+    q0 = __shfl_sync(FULL, q0, 0);
+    if (q0 >= nq) break;
+    // headers of the 32 queries, one per lane
+    uint32_t m_flags = QF_EMPTY, m_nh = 0, m_base = 0, m_q = 0, m_len = 0;
+    if (q0 + lane < nq) {
+      const uint32_t qi = q0 + lane;
+      m_flags = qflags[qi];
+      m_nh = hit_count[qi];
+      m_base = qbase[qi];
+      m_q = qlist ? qlist[qi] : qi;
+      m_len = *reinterpret_cast<const uint16_t*>(queries + (size_t)m_q * bp.query_stride);  // length | flags << 8
     }
-    const uint32_t q = qlist ? qlist[qi] : qi;
-    const uint8_t* qrow = queries + (size_t)q * bp.query_stride;
-    const uint32_t Lq = qrow[0];
-    const bool q_lower = (qrow[1] & Q_FIRST_LOWER) != 0;
-    const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
-    const double Ld = (double)Lq;
-    // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
-    // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
-    const double quot_lane = __ddiv_rn((double)lane, Ld);
-    const bool quot_ok = Lq <= 31;
-    uint32_t nsurv = 0;
-    double maxfreq = 0.0;
-    for (uint32_t hb = 0; hb < nh; hb += 32) {
-      const uint32_t k = hb + lane;
-      uint32_t r = RES_REJECT, g = 0;
-      if (k < nh) {
-        r = res[base + k];
-        g = hq[k];
+    const uint32_t nblock = min(32u, nq - q0);
+    for (uint32_t t = 0; t < nblock; ++t) {
+      const uint32_t qi = q0 + t;
+      const uint32_t flags = __shfl_sync(FULL, m_flags, t);
+      const uint32_t nh = __shfl_sync(FULL, m_nh, t);
+      const uint32_t base = __shfl_sync(FULL, m_base, t);
+      const uint32_t q = __shfl_sync(FULL, m_q, t);
+      const uint32_t len = __shfl_sync(FULL, m_len, t);
+      if ((flags & (QF_EMPTY | QF_HIT_OVERFLOW | QF_UNSUPPORTED)) || (unsigned long long)base + nh > pair_cap) {
+        // (a query beyond the pair-list capacity: the host runs the score stage again with a larger list)
+        if (lane == 0) {
+          OutHead h;
+          h.max_freq = 0.0;
+          h.offset = 0;
+          h.count = 0;
+          out_head[qi] = h;
+        }
+        continue;
       }
-      const bool valid = r != RES_REJECT;
-      const uint32_t ld = r & 0xFF;
-      bool c_lower = false;
-      if (valid) c_lower = (__ldg(rows + (size_t)g * nstride + 1) & ROW_FIRST_LOWER) != 0;
-      // features are skipped (0 / true) when their weight is <= 0 (src/lib.rs:1352-1377)
-      const uint32_t f_lcs = (valid && bp.w_lcs > 0.0) ? (r >> 8) & 0xFF : 0;
-      const uint32_t f_pre = (valid && bp.w_prefix > 0.0) ? (r >> 16) & 0xFF : 0;
-      const uint32_t f_suf = (valid && bp.w_suffix > 0.0) ? r >> 24 : 0;
-      const bool samecase = bp.w_case > 0.0 ? (c_lower == q_lower) : true;
-      // ---- f64 score, left to right, no FMA (src/lib.rs:1433-1452) -----------------------------------
-      double q_ld, q_lcs, q_pre, q_suf;
-      if (quot_ok) {  // warp-uniform; all four indices are <= Lq <= 31 (ld is clamped: it only matters when <= Lq)
-        q_ld = __shfl_sync(FULL, quot_lane, min(ld, 31u));
-        q_lcs = __shfl_sync(FULL, quot_lane, f_lcs);
-        q_pre = __shfl_sync(FULL, quot_lane, f_pre);
-        q_suf = __shfl_sync(FULL, quot_lane, f_suf);
-      } else {
-        q_ld = __ddiv_rn((double)ld, Ld);
-        q_lcs = __ddiv_rn((double)f_lcs, Ld);
-        q_pre = __ddiv_rn((double)f_pre, Ld);
-        q_suf = __ddiv_rn((double)f_suf, Ld);
+      const uint32_t Lq = len & 0xFF;
+      const bool q_lower = ((len >> 8) & Q_FIRST_LOWER) != 0;
+      const uint32_t* hq = hits + (size_t)qi * bp.hit_cap;
+      SurvRec* surv = nh <= RK_SMEM_SURV ? &s_scr[warp][0] : g_surv;
+      SurvRec* sorted = nh <= RK_SMEM_SURV ? &s_scr[warp][RK_SMEM_SURV] : g_surv + bp.hit_cap;
+      const double Ld = (double)Lq;
+      // every feature of the score is a small integer divided by the query length: lane v holds v / Ld once per
+      // query and the per-candidate quotients are fetched by shuffle (same IEEE division, so the bits are the same)
+      const double quot_lane = __ddiv_rn((double)lane, Ld);
+      const bool quot_ok = Lq <= 31;
+      uint32_t nsurv = 0;
+      double maxfreq = 0.0;
+      for (uint32_t hb = 0; hb < nh; hb += 32) {
+        const uint32_t k = hb + lane;
+        uint32_t r = RES_REJECT, g = 0;
+        if (k < nh) {
+          r = res[base + k];
+          g = hq[k];
+        }
+        const bool valid = r != RES_REJECT;
+        const uint32_t ld = r & 0xFF;
+        bool c_lower = false;
+        uint32_t vocab = 0;
+        double freq = 1.0;
+        if (valid) {
+          c_lower = (__ldg(rows + (size_t)g * nstride + 1) & ROW_FIRST_LOWER) != 0;
+          vocab = __ldg(ix->inst_vocab + g);
+          if (have_freq) freq = (double)__ldg(ix->inst_freq + g);
+        }
+        // features are skipped (0 / true) when their weight is <= 0 (src/lib.rs:1352-1377)
+        const uint32_t f_lcs = (valid && bp.w_lcs > 0.0) ? (r >> 8) & 0xFF : 0;
+        const uint32_t f_pre = (valid && bp.w_prefix > 0.0) ? (r >> 16) & 0xFF : 0;
+        const uint32_t f_suf = (valid && bp.w_suffix > 0.0) ? r >> 24 : 0;
+        const bool samecase = bp.w_case > 0.0 ? (c_lower == q_lower) : true;
+        // ---- f64 score, left to right, no FMA (src/lib.rs:1433-1452) -----------------------------------
+        double q_ld, q_lcs, q_pre, q_suf;
+        if (quot_ok) {  // warp-uniform; all four indices are <= Lq <= 31 (ld is clamped: it only matters when <= Lq)
+          q_ld = __shfl_sync(FULL, quot_lane, min(ld, 31u));
+          q_lcs = __shfl_sync(FULL, quot_lane, f_lcs);
+          q_pre = __shfl_sync(FULL, quot_lane, f_pre);
+          q_suf = __shfl_sync(FULL, quot_lane, f_suf);
+        } else {
+          q_ld = __ddiv_rn((double)ld, Ld);
+          q_lcs = __ddiv_rn((double)f_lcs, Ld);
+          q_pre = __ddiv_rn((double)f_pre, Ld);
+          q_suf = __ddiv_rn((double)f_suf, Ld);
+        }
+        const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, q_ld);
+        double acc = __dmul_rn(bp.w_ld, ds);
+        acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, q_lcs));
+        acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, q_pre));
+        acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, q_suf));
+        acc = __dadd_rn(acc, samecase ? bp.w_case : 0.0);
+        const double score = __ddiv_rn(acc, bp.w_sum);
+        // max_freq is taken over every instance within the edit distance, before the score threshold
+        double mf = valid ? freq : 0.0;
+        for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
+        maxfreq = fmax(maxfreq, mf);
+        c_surv += valid ? 1 : 0;
+        const bool keep = valid && score >= bp.score_threshold;
+        const uint32_t kmask = __ballot_sync(FULL, keep);
+        if (keep) {
+          SurvRec sr;
+          sr.dist = score;
+          sr.freq = freq;
+          sr.key = 0.0;
+          sr.g = gid_of ? __ldg(gid_of + g) : g;  // sharded index: global gather id
+          sr.raw = (uint32_t)freq;               // raw frequency (exact: u32 or 1.0)
+          sr.vocab = vocab;
+          sr.pad = 0;
+          surv[nsurv + __popc(kmask & lanemask_lt())] = sr;
+        }
+        nsurv += __popc(kmask);
+        __syncwarp();
       }
-      const double ds = ld > Lq ? 0.0 : __dsub_rn(1.0, q_ld);
-      double acc = __dmul_rn(bp.w_ld, ds);
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_lcs, q_lcs));
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_prefix, q_pre));
-      acc = __dadd_rn(acc, __dmul_rn(bp.w_suffix, q_suf));
-      acc = __dadd_rn(acc, samecase ? bp.w_case : 0.0);
-      const double score = __ddiv_rn(acc, bp.w_sum);
-      double freq = 1.0;
-      if (valid && have_freq) freq = (double)__ldg(ix->inst_freq + g);
-      // max_freq is taken over every instance within the edit distance, before the score threshold
-      double mf = valid ? freq : 0.0;
-      for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
-      maxfreq = fmax(maxfreq, mf);
-      c_surv += valid ? 1 : 0;
-      const bool keep = valid && score >= bp.score_threshold;
-      const uint32_t kmask = __ballot_sync(FULL, keep);
-      if (keep) {
-        SurvRec s;
-        s.dist = score;
-        s.freq = freq;
-        s.key = 0.0;
-        s.g = gid_of ? __ldg(gid_of + g) : g;  // sharded index: global gather id
-        s.raw = (uint32_t)freq;               // raw frequency (exact: u32 or 1.0)
-        s.vocab = __ldg(ix->inst_vocab + g);
-        s.pad = 0;
-        surv[nsurv + __popc(kmask & lanemask_lt())] = s;
+      ConfStage cs;
+      if (rec_query && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
+        cs.rec_query = rec_query;
+        cs.qrow = q;
       }
-      nsurv += __popc(kmask);
-      __syncwarp();
+      c_res += rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags,
+                              qflags, work + 2, 0, cs);
     }
-    ConfStage cs;
-    if (rec_query && (bp.finish_mode == FINISH_CROP || bp.finish_mode == FINISH_GATHER)) {
-      cs.rec_query = rec_query;
-      cs.qrow = q;
-    }
-    c_res += rank_crop_emit(bp, rce_mode(bp.finish_mode), surv, sorted, nsurv, maxfreq, out, out_gid, out_head, qi, flags,
-                            qflags, work + 2, 0, cs);
   }
   if (counters) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -2806,7 +3086,6 @@ rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint
     }
   }
 }
-
 
 // ================================================================================================
 // launchers
@@ -2832,6 +3111,8 @@ cudaError_t configure_kernels() {
   e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_k1_ctas_per_sm, probe_fn(), K1_WARPS * 32, sizeof(K1Shared));
   return e;
@@ -3009,12 +3290,6 @@ cudaError_t launch_score(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const
 // The pair-list score stage: filter + shape histogram, scan, scatter, DP per shape class, rank.  work[8..17] are its
 // counters (zeroed here); the caller checks work[PW_TOTAL] <= lb.pair_cap afterwards (else: run the stage again with a
 // larger pair list).
-static int dp_ctas_per_sm(size_t smem) {
-  int n = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dp_kernel, DP_WARPS * 32, smem);
-  if (e != cudaSuccess || n < 1) n = 1;
-  return n;
-}
 cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix, const BatchParams& bp, const LaunchBuffers& lb,
                                int sm_count, cudaStream_t stream, cudaEvent_t ev_filter_done) {
   if (lb.n == 0) return cudaSuccess;
@@ -3030,31 +3305,47 @@ cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix,
   };
   pairfilter_kernel<<<grid_for(PF_WARPS, 6), PF_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
                                                                         lb.qflags, lb.qbase, lb.pair_hist, lb.work, lb.counters);
-  pairscan_kernel<<<1, 1024, 0, stream>>>(lb.pair_hist, lb.pair_first, lb.pair_cursor, lb.pair_q, lb.pair_cap, lb.work);
+  pairscan_kernel<<<1, 1024, 0, stream>>>(lb.pair_hist, lb.pair_first, lb.pair_cursor, lb.pairs, lb.pair_cap, lb.work);
   pairscatter_kernel<<<grid_for(PS_WARPS, 8), PS_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.n, lb.hits, lb.hit_count,
                                                                           lb.qflags, lb.qbase, lb.pair_first, lb.pair_cursor,
-                                                                          lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap, lb.work);
+                                                                          lb.pairs, lb.pair_cap, lb.work);
   g_kernel_launches += 3;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (ev_filter_done && (e = cudaEventRecord(ev_filter_done, stream)) != cudaSuccess) return e;
   const uint32_t R = ring_depth(bp);
-  // short shapes: both sides <= PAIR_SHORT_MAX (nearly all pairs); long shapes: sized by the longest entry / query
-  const uint32_t longest_q = std::min<uint32_t>(bp.query_stride - 2, (uint32_t)ANL_MAX_SYMBOLS);
-  {
-    const uint32_t MQ = std::min(PAIR_SHORT_MAX, longest_q), MC = std::min(PAIR_SHORT_MAX, h_ix.max_len);
-    const size_t smem = dp_warp_bytes(MQ, MC, R) * DP_WARPS;
-    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * dp_ctas_per_sm(smem), (long long)sm_count * 16);
-    dp_kernel<<<grid, DP_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap,
-                                                     lb.pair_res, lb.work, 0, lb.counters, MQ, MC, R);
-    ++g_kernel_launches;
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* v = getenv("ANL_DP_TMA");
+    use_tma = v ? (atoi(v) != 0) : 1;
   }
-  if (std::max(longest_q, h_ix.max_len) > PAIR_SHORT_MAX) {
-    const uint32_t MQ = longest_q, MC = h_ix.max_len;
-    const size_t smem = dp_warp_bytes(MQ, MC, R) * DP_WARPS;
+  // short shapes: both sides <= PAIR_SHORT_MAX (nearly all pairs); long shapes: sized by the longest entry and by the
+  // longest query that can still have a candidate (length check: |Lq - Lc| <= max edit distance)
+  const uint32_t longest_q = std::min<uint32_t>(std::min<uint32_t>(bp.query_stride - 2, (uint32_t)ANL_MAX_SYMBOLS), h_ix.max_len + (R - 2));
+  for (int cls = 0; cls < 2; ++cls) {
+    if (cls == 1 && std::max(longest_q, h_ix.max_len) <= PAIR_SHORT_MAX) break;
+    const uint32_t MQ = cls == 0 ? std::min(PAIR_SHORT_MAX, longest_q) : longest_q;
+    const uint32_t MC = cls == 0 ? std::min(PAIR_SHORT_MAX, h_ix.max_len) : h_ix.max_len;
+    // bytes of a row the DP can need: length + flags + symbols, in 16-byte units (what a bulk copy moves)
+    const uint32_t qb = std::min<uint32_t>(bp.query_stride, (MQ + 2 + 15) & ~15u), cb = std::min<uint32_t>(h_ix.norm_stride, (MC + 2 + 15) & ~15u);
+    const size_t per_warp = use_tma ? dp_tma_warp_bytes(MQ, MC, R, qb, cb) : dp_warp_bytes(MQ, MC, R);
+    int warps = DP_WARPS;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * dp_ctas_per_sm(smem), (long long)sm_count * 2);
-    dp_kernel<<<grid, DP_WARPS * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pair_q, lb.pair_g, lb.pair_d, lb.pair_cap,
-                                                     lb.pair_res, lb.work, 1, lb.counters, MQ, MC, R);
+    int ctas = 0;
+    if (use_tma)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_tma_kernel, warps * 32, smem);
+    else
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dp_kernel, warps * 32, smem);
+    if (e != cudaSuccess || ctas < 1) ctas = 1;
+    if (cls == 1) ctas = std::min(ctas, 2);  // (few tiles, long dependent chains)
+    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * ctas, (long long)sm_count * 16);
+    if (use_tma)
+      dp_tma_kernel<<<grid, warps * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pairs, lb.pair_cap, lb.pair_res, lb.work, cls,
+                                                        lb.counters, MQ, MC, R, qb, cb);
+    else
+      dp_kernel<<<grid, warps * 32, smem, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.pairs, lb.pair_cap, lb.pair_res, lb.work, cls,
+                                                    lb.counters, MQ, MC, R);
     ++g_kernel_launches;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -3082,10 +3373,12 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
   {
     unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 255) / 256, (uint64_t)sm_count * 8);
     if (blocks < 1) blocks = 1;
+    cudaError_t e = cudaMemsetAsync(lb.work + 7, 0, sizeof(unsigned int), stream);  // length of the wide queue
+    if (e != cudaSuccess) return e;
     triage_kernel<<<blocks, 256, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.rec_query, lb.out, lb.work + 2, bp.pool_cap, lb.conf_work,
-                                              lb.work + 3);
+                                              lb.work + 3, lb.work + 7);
     ++g_kernel_launches;
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess || !lb.conf_work) return e;
   }
   // one thread per possible work item (the queue length is only known on the device): threads beyond the
@@ -3093,7 +3386,10 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
   unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
   if (blocks < 1) blocks = 1;
   confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
-  ++g_kernel_launches;
+  // (few pairs hold characters beyond ASCII: a small grid walks that queue)
+  confusable_wide_kernel<<<(unsigned)sm_count * 4, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 7, bp.pool_cap,
+                                                                    lb.out);
+  g_kernel_launches += 2;
   return cudaGetLastError();
 }
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream) {

@@ -28,9 +28,8 @@ struct LaunchBuffers {
                                      // (zeroed by the launchers); WORK_SLOTS entries
   // pair-list score stage (launch_score_pairs): dense slot base per query, the shape-sorted pair list, packed features
   uint32_t* qbase = nullptr;         // [n]
-  uint32_t* pair_q = nullptr;        // [pair_cap] query of the pair at a sorted position (0xFFFFFFFF = no pair)
-  uint32_t* pair_g = nullptr;        // [pair_cap] candidate (gather id)
-  uint32_t* pair_d = nullptr;        // [pair_cap] dense slot of the pair (qbase[query] + position in its hit list)
+  uint4* pairs = nullptr;            // [pair_cap] by sorted position: {query (0xFFFFFFFF = no pair), candidate (gather id),
+                                     //             dense slot = qbase[query] + position in its hit list, 0}
   uint32_t* pair_res = nullptr;      // [pair_cap] by dense slot: ld | lcs << 8 | prefix << 16 | suffix << 24, or 0xFFFFFFFF
   uint32_t pair_cap = 0;
   uint32_t* pair_hist = nullptr;     // [PAIR_TABLE] pairs per shape
