@@ -2941,6 +2941,7 @@ dp_tma_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const ui
 // its lanes fetch their headers (flags, candidate count, dense base, length, case flag) side by side; queries with at
 // most 32 candidates (nearly all) keep their survivor lists in shared memory instead of the global scratch.
 constexpr uint32_t RK_SMEM_SURV = 32;
+constexpr uint32_t RK_GRAB = 8;  // queries per counter increment (few: a warp works its grab off serially)
 __global__ void __launch_bounds__(K2_WARPS * 32)
 rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
             const uint32_t* __restrict__ qlist, uint32_t* __restrict__ rec_query, uint32_t nq, const uint32_t* __restrict__ hits,
@@ -2959,12 +2960,12 @@ rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint
   unsigned long long c_surv = 0, c_res = 0;
   for (;;) {
     uint32_t q0 = 0;
-    if (lane == 0) q0 = atomicAdd(work + PW_RANK, 32u);
+    if (lane == 0) q0 = atomicAdd(work + PW_RANK, RK_GRAB);
     q0 = __shfl_sync(FULL, q0, 0);
     if (q0 >= nq) break;
-    // headers of the 32 queries, one per lane
+    // headers of the grabbed queries, one per lane
     uint32_t m_flags = QF_EMPTY, m_nh = 0, m_base = 0, m_q = 0, m_len = 0;
-    if (q0 + lane < nq) {
+    if (lane < RK_GRAB && q0 + lane < nq) {
       const uint32_t qi = q0 + lane;
       m_flags = qflags[qi];
       m_nh = hit_count[qi];
@@ -2972,7 +2973,7 @@ rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint
       m_q = qlist ? qlist[qi] : qi;
       m_len = *reinterpret_cast<const uint16_t*>(queries + (size_t)m_q * bp.query_stride);  // length | flags << 8
     }
-    const uint32_t nblock = min(32u, nq - q0);
+    const uint32_t nblock = min(RK_GRAB, nq - q0);
     for (uint32_t t = 0; t < nblock; ++t) {
       const uint32_t qi = q0 + t;
       const uint32_t flags = __shfl_sync(FULL, m_flags, t);
@@ -3316,7 +3317,7 @@ cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix,
   static int use_tma = -1;
   if (use_tma < 0) {
     const char* v = getenv("ANL_DP_TMA");
-    use_tma = v ? (atoi(v) != 0) : 1;
+    use_tma = v ? (atoi(v) != 0) : 0;  // (measured, profiles/r02d: the staged variant is 30 % slower -- see DESIGN.md)
   }
   // short shapes: both sides <= PAIR_SHORT_MAX (nearly all pairs); long shapes: sized by the longest entry and by the
   // longest query that can still have a candidate (length check: |Lq - Lc| <= max edit distance)
