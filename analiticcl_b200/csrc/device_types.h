@@ -64,11 +64,20 @@ __host__ __device__ __forceinline__ uint64_t fp_index(uint64_t h, uint64_t mask)
 // A slot stores mhash(X) as a fingerprint, not X.
 struct __attribute__((aligned(16))) Slot {
   uint64_t fp;        // mhash(X)
-  uint32_t post_off;  // first posting
+  uint32_t post_off;  // first posting (device copy, SLOT_INLINE set: the anagram rank of the slot's only posting)
   uint16_t post_cnt;  // number of postings; 0 = empty slot
-  uint16_t pad;
+  uint16_t pad;       // device copy: SLOT_INLINE | class of the only posting (most keys have one: no posting read)
 };
 static const uint8_t POST_SELF = 0xFF;
+static const uint16_t SLOT_INLINE = 0x8000;
+// Everything the exact stage needs about an anagram in one 32-byte sector (device only; built at upload from
+// ana_key / ana_inst_off): with the table and the postings HBM-resident every separate array is another random
+// DRAM access per verified posting.
+struct __attribute__((aligned(32))) AnaRec {
+  Key192 key;         // exact prime-product key
+  uint32_t inst_off;  // first gather id
+  uint32_t inst_cnt;  // instances
+};
 
 // Blocked Bloom filter in front of the table: one 64-bit word per key, BLOOM_BITS bits inside it.
 // A miss (the overwhelmingly common case) costs one 8-byte load.
@@ -177,9 +186,8 @@ struct DeviceIndex {
   const uint32_t* post_ana;  // posting -> anagram rank
   const uint8_t* post_cls;   // posting -> class x (or POST_SELF)
   int32_t sd;                // symmetric-delete depth of the table (0 or 1)
-  // anagrams in ascending key order (rank = position): key, first gather id (n_anagrams + 1 entries)
-  const Key192* ana_key;
-  const uint32_t* ana_inst_off;
+  // anagrams in ascending key order (rank = position): key, first gather id, instance count
+  const AnaRec* ana_rec;
   // instances in gather order: (anagram key ascending, vocab id ascending) == the order in which
   // gather_instances (src/lib.rs:1327-1391) visits them, so "gather id ascending" reproduces the
   // reference's stable-sort tie order.

@@ -239,8 +239,30 @@ bool Engine::upload(int device, std::string* err) {
   if (!upload_vec(hx.post_ana, &ix.post_ana, &index_allocs_, err)) return false;
   if (!upload_vec(hx.post_cls, &ix.post_cls, &index_allocs_, err)) return false;
   ix.sd = hx.sd;
-  if (!upload_vec(hx.ana_key, &ix.ana_key, &index_allocs_, err)) return false;
-  if (!upload_vec(hx.ana_inst_off, &ix.ana_inst_off, &index_allocs_, err)) return false;
+  {
+    // keys + instance offsets -> 32-byte anagram records, single postings -> their slots (device-only forms)
+    const Key192* d_key = nullptr;
+    const uint32_t* d_off = nullptr;
+    std::vector<void*> tmp;
+    bool ok = upload_vec(hx.ana_key, &d_key, &tmp, err) && upload_vec(hx.ana_inst_off, &d_off, &tmp, err);
+    void* rec = nullptr;
+    if (ok && cudaMalloc(&rec, std::max<size_t>(hx.ana_key.size(), 1) * sizeof(AnaRec)) != cudaSuccess) {
+      *err = "out of device memory for the anagram records";
+      ok = false;
+    }
+    if (ok) {
+      index_allocs_.push_back(rec);
+      ix.ana_rec = reinterpret_cast<const AnaRec*>(rec);
+      const cudaError_t ce2 = finish_device_index(d_key, d_off, (uint32_t)hx.ana_key.size(), reinterpret_cast<AnaRec*>(rec),
+                                                  const_cast<Slot*>(ix.table), hx.table.size(), ix.post_ana, ix.post_cls, stream_);
+      if (ce2 != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) {
+        *err = std::string("index finishing kernels failed: ") + cudaGetErrorString(ce2 != cudaSuccess ? ce2 : cudaGetLastError());
+        ok = false;
+      }
+    }
+    for (void* p : tmp) cudaFree(p);
+    if (!ok) return false;
+  }
   if (!upload_vec(hx.inst_rows, &ix.inst_rows, &index_allocs_, err)) return false;
   ix.norm_stride = hx.norm_stride;
   if (!upload_vec(hx.inst_vocab, &ix.inst_vocab, &index_allocs_, err)) return false;
@@ -1761,10 +1783,12 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
   }
   // Chunks of 65536 queries: large enough for the persistent grids to fill the device, small enough that several are
   // in flight per device and the first results come back early.
-  uint64_t CHUNK = 1u << 16;
+  // (measured on cfg 2, 1 M queries, profiles/r02e_sweep.txt: 65536 -> 32.5, 131072 -> 35.4, 262144 -> 34.5 M q/s:
+  // larger chunks have fewer kernel tails, smaller ones a shorter ramp; calls that span few chunks stay at 65536)
+  uint64_t CHUNK = n >= ((uint64_t)D << 19) ? (1u << 17) : (1u << 16);
   if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
   size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
-  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(8, std::max(1, atoi(e)));
+  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(4, std::max(1, atoi(e)));
   CallShared S;
   S.out = out;
   S.n_total = n;

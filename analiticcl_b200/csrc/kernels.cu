@@ -160,6 +160,40 @@ encode_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const ui
 }
 
 // ================================================================================================
+// Upload-time transformations of the index (device only)
+// ================================================================================================
+// The host index keeps keys, instance offsets, slots and postings as separate arrays (and so does its file format).
+// On the device every separate array is another random access per verified posting, so the upload folds them:
+// anagram records {key, first instance, count} in one 32-byte sector, and the only posting of a slot into the slot.
+__global__ void ana_rec_kernel(const Key192* __restrict__ key, const uint32_t* __restrict__ inst_off, uint32_t n, AnaRec* __restrict__ rec) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  AnaRec a;
+  a.key = key[r];
+  a.inst_off = inst_off[r];
+  a.inst_cnt = inst_off[r + 1] - inst_off[r];
+  rec[r] = a;
+}
+__global__ void inline_slots_kernel(Slot* __restrict__ table, uint64_t slots, const uint32_t* __restrict__ post_ana,
+                                    const uint8_t* __restrict__ post_cls) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= slots) return;
+  Slot s = table[i];
+  if (s.post_cnt == 1 && !(s.pad & SLOT_INLINE)) {
+    s.pad = (uint16_t)(SLOT_INLINE | post_cls[s.post_off]);
+    s.post_off = post_ana[s.post_off];
+    table[i] = s;
+  }
+}
+cudaError_t finish_device_index(const Key192* ana_key, const uint32_t* ana_inst_off, uint32_t n_anagrams, AnaRec* ana_rec, Slot* table,
+                                uint64_t slots, const uint32_t* post_ana, const uint8_t* post_cls, cudaStream_t stream) {
+  if (n_anagrams) ana_rec_kernel<<<(n_anagrams + 255) / 256, 256, 0, stream>>>(ana_key, ana_inst_off, n_anagrams, ana_rec);
+  if (slots) inline_slots_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(table, slots, post_ana, post_cls);
+  g_kernel_launches += 2;
+  return cudaGetLastError();
+}
+
+// ================================================================================================
 // Kernel 1: candidate generation
 // ================================================================================================
 // Every node X = D + I' of the query's neighbourhood (D: a sub-multiset of the focus after d deletions,
@@ -216,7 +250,8 @@ struct K1Warp {
   uint64_t nprod[32];  // exact stage: product of the primes of I' per staged node (0 = does not fit: general path)
   uint64_t kF[3];      // exact key of the focus (valid iff kF_ok)
   uint32_t pfx[33];    // exact stage: exclusive prefix of posting counts (+ sentinel)
-  uint32_t poff[32];   // exact stage: first posting of each staged node
+  uint32_t poff[32];   // exact stage: first posting of each staged node (inline slot: the anagram rank)
+  uint32_t pinl[32];   // exact stage: 0xFFFFFFFF, or the class of the slot's inline posting
   uint32_t stat[6];    // per-warp work counters of the non-inlined stages: slots, postings, anagrams, instances, probes, passes
   uint32_t binomL[8];  // C(L, d)
   uint32_t kF_ok, nhits, L, ka;
@@ -297,7 +332,7 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
   const uint32_t lane = lane_id();
   const DeviceIndex& ix = S.ix;
   uint32_t c_steps = 0, c_post = 0, c_ana = 0, c_inst = 0;
-  uint32_t poff = 0, pcnt = 0;
+  uint32_t poff = 0, pcnt = 0, pinl = 0xFFFFFFFFu;
   if (lane < cnt) {
     const uint64_t fp = W.sq[lane].h;
     uint64_t idx = fp_index(fp, ix.table_mask);
@@ -308,6 +343,7 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
       if (sl.fp == fp) {
         poff = sl.post_off;
         pcnt = sl.post_cnt;
+        if (sl.pad & SLOT_INLINE) pinl = sl.pad & 0xFFu;
         break;
       }
       idx = (idx + 1) & ix.table_mask;
@@ -333,6 +369,7 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
   const uint32_t total = __shfl_sync(FULL, incl, 31);
   W.pfx[lane] = incl - pcnt;
   W.poff[lane] = poff;
+  W.pinl[lane] = pinl;
   __syncwarp();
   const uint32_t ka = W.ka;
   const int sd = ix.sd;
@@ -346,8 +383,9 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
         if (W.pfx[owner + step] <= t) owner += step;
       const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
       const SEntry& s = W.sq[owner];
-      const uint32_t r = __ldg(ix.post_ana + p);
-      const uint32_t x = __ldg(ix.post_cls + p);
+      const uint32_t inl = W.pinl[owner];
+      const uint32_t r = inl != 0xFFFFFFFFu ? p : __ldg(ix.post_ana + p);
+      const uint32_t x = inl != 0xFFFFFFFFu ? inl : __ldg(ix.post_cls + p);
       ++c_post;
       const uint64_t dd = s.dd;
       const uint32_t isz = s.isz;
@@ -359,7 +397,8 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
         ok = ka >= dd_count(dd) + isz + 1 && (isz == 0 || x >= s.imax) && !has_byte6(dd, x);
       }
       if (ok) {
-        const Key192 ck = ix.ana_key[r];
+        const AnaRec ar = ix.ana_rec[r];
+        const Key192 ck = ar.key;
         const uint64_t np = W.nprod[owner];
         bool match;
         if (kF_ok && np != 0) {
@@ -372,8 +411,7 @@ __device__ __noinline__ void exact_stage(K1Shared& S, K1Warp& W, uint32_t cnt) {
           match = verify_general(S, W, s, x, ck);
         }
         if (match) {  // else: fingerprint collision
-          const uint32_t io = __ldg(ix.ana_inst_off + r), ie = __ldg(ix.ana_inst_off + r + 1);
-          const uint32_t n = ie - io;
+          const uint32_t io = ar.inst_off, n = ar.inst_cnt;
           ++c_ana;
           c_inst += n;
           const uint32_t pos = atomicAdd(&W.nhits, n);
@@ -1012,6 +1050,7 @@ struct KXWarp {
   uint64_t nprod[32];
   uint32_t pfx[33];
   uint32_t poff[32];
+  uint32_t pinl[32];  // 0xFFFFFFFF, or the class of the slot's inline posting (poff is then the anagram rank)
 };
 // General exact verification without the warp's sorted copy of the query (cold, cf. verify_general).
 __device__ __noinline__ bool verify_general_q(const DeviceIndex* __restrict__ ix, const uint8_t* __restrict__ qrow, uint32_t L,
@@ -1081,7 +1120,7 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     base = __shfl_sync(FULL, base, 0);
     if (base >= total) break;
     const uint32_t i = base + lane;
-    uint32_t poff = 0, pcnt = 0;
+    uint32_t poff = 0, pcnt = 0, pinl = 0xFFFFFFFFu;
     if (i < total && queue[i].qi != QHOLE) {
       const QEntry e = queue[i];
       W.e[lane] = e;
@@ -1094,6 +1133,7 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
         if (sl.fp == fp) {
           poff = sl.post_off;
           pcnt = sl.post_cnt;
+          if (sl.pad & SLOT_INLINE) pinl = sl.pad & 0xFFu;
           break;
         }
         idx = (idx + 1) & table_mask;
@@ -1118,6 +1158,7 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
     const uint32_t npost = __shfl_sync(FULL, incl, 31);
     W.pfx[lane] = incl - pcnt;
     W.poff[lane] = poff;
+    W.pinl[lane] = pinl;
     __syncwarp();
     for (uint32_t t0 = 0; t0 < npost; t0 += 32) {
       const uint32_t t = t0 + lane;
@@ -1128,8 +1169,9 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           if (W.pfx[owner + step] <= t) owner += step;
         const uint32_t p = W.poff[owner] + (t - W.pfx[owner]);
         const QEntry& s = W.e[owner];
-        const uint32_t r = __ldg(ix->post_ana + p);
-        const uint32_t x = __ldg(ix->post_cls + p);
+        const uint32_t inl = W.pinl[owner];
+        const uint32_t r = inl != 0xFFFFFFFFu ? p : __ldg(ix->post_ana + p);
+        const uint32_t x = inl != 0xFFFFFFFFu ? inl : __ldg(ix->post_cls + p);
         ++c_post;
         const QCtx cx = qctx[s.qi];
         const uint32_t ka = cx.ka_ok & 0xFFu;
@@ -1143,7 +1185,8 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           ok = ka >= dd_count(dd) + isz + 1 && (isz == 0 || x >= s.imax) && !has_byte6(dd, x);
         }
         if (ok) {
-          const Key192 ck = ix->ana_key[r];
+          const AnaRec ar = ix->ana_rec[r];
+          const Key192 ck = ar.key;
           const uint64_t np = W.nprod[owner];
           bool match;
           if ((cx.ka_ok & 0x100u) && np != 0) {
@@ -1157,8 +1200,7 @@ exact_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
             match = verify_general_q(ix, queries + (size_t)q * bp.query_stride, cx.L, s, x, ck);
           }
           if (match) {  // else: fingerprint collision
-            const uint32_t io = __ldg(ix->ana_inst_off + r), ie = __ldg(ix->ana_inst_off + r + 1);
-            const uint32_t n = ie - io;
+            const uint32_t io = ar.inst_off, n = ar.inst_cnt;
             ++c_ana;
             c_inst += n;
             const uint32_t pos = atomicAdd(hit_count + s.qi, n);

@@ -76,6 +76,9 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
                                cudaStream_t stream);
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream);
 size_t score_scratch_bytes(const BatchParams& bp, int sm_count, uint32_t n_queries);
+// device-only forms of the index, built once at upload: 32-byte anagram records; single postings folded into their slots
+cudaError_t finish_device_index(const Key192* ana_key, const uint32_t* ana_inst_off, uint32_t n_anagrams, AnaRec* ana_rec, Slot* table,
+                                uint64_t slots, const uint32_t* post_ana, const uint8_t* post_cls, cudaStream_t stream);
 cudaError_t configure_kernels();
 // Unicode Alphabetic ranges ([n][2], inclusive) for the character classes of the device edit script; per device
 cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n);
