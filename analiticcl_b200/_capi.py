@@ -62,6 +62,11 @@ class Counters(C.Structure):
                  "dp_cells")]
 
 
+class ShardStepStats(C.Structure):
+    _fields_ = [("score_ms", C.c_float), ("exchange_ms", C.c_float), ("merge_ms", C.c_float), ("bytes_received", C.c_uint64),
+                ("records_local", C.c_uint64), ("records_total", C.c_uint64)]
+
+
 class IndexStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("table_slots", "table_bytes", "slot_bytes", "table_keys", "bloom_bytes", "postings", "anagrams",
@@ -139,6 +144,11 @@ SIGNATURES = {
     "anl_shard_export_size": (_i32, [_vp, _vp, _P(_u64), _P(_u32)]),
     "anl_shard_export": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "anl_shard_merge": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u64, _u32, _P(_vp)]),
+    "anl_shard_comm_id": (_i32, [_P(C.c_uint8)]),
+    "anl_shard_comm_init": (_i32, [_vp, _P(C.c_uint8), _i32, _i32]),
+    "anl_shard_comm_free": (None, [_vp]),
+    "anl_shard_batch_step": (_i32, [_vp, _vp, _P(ShardStepStats), _P(_vp)]),
+    "anl_shard_find_variants_batch": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
 }
 
 _lib = None

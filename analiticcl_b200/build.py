@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libanaliticcl_b200.so")
-SOURCES = ["kernels.cu", "export.cu", "engine.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "capi.cpp"]
-HEADERS = ["device_types.h", "editscript_fixed.h", "kernel_common.cuh", "kernels.h", "engine.h", "host_model.h", "hostpool.h", "search.h", "unicode_tables.h",
+SOURCES = ["kernels.cu", "export.cu", "engine.cu", "shard_comm.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "capi.cpp"]
+HEADERS = ["shard_comm.cu", "device_types.h", "editscript_fixed.h", "kernel_common.cuh", "kernels.h", "engine.h", "host_model.h", "hostpool.h", "search.h", "unicode_tables.h",
            os.path.join("..", "..", "include", "analiticcl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["--cudart", "static", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-pthread"]
-    subprocess.check_call(cmd)
+    subprocess.check_call(cmd + ["-ldl"])
     return OUT
 
 

@@ -954,6 +954,64 @@ anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards,
   return on_exception();
 }
 
+anl_status anl_shard_comm_id(uint8_t id[ANL_SHARD_ID_BYTES]) try {
+  if (!id) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!shard_unique_id(id, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+anl_status anl_shard_comm_init(anl_model* m, const uint8_t id[ANL_SHARD_ID_BYTES], int32_t rank, int32_t n_ranks) try {
+  if (!m || !id) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->engine.shard_comm_init(id, rank, n_ranks, &err)) return fail(ANL_ERR_CUDA, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+void anl_shard_comm_free(anl_model* m) {
+  if (m) m->engine.shard_comm_free();
+}
+anl_status anl_shard_batch_step(anl_model* m, anl_device_batch* b, anl_shard_step_stats* stats, anl_result_set** out) try {
+  if (!m || !b) return fail(ANL_ERR_INVALID, "null argument");
+  std::unique_ptr<anl_result_set> rs(out ? new anl_result_set() : nullptr);
+  std::string err;
+  int status = ANL_OK;
+  ShardStepStats st;
+  if (!m->engine.shard_step(b->b, rs ? &rs->rs : nullptr, &st, &err, &status)) return fail(status ? status : ANL_ERR_CUDA, err);
+  if (stats) {
+    stats->score_ms = st.score_ms;
+    stats->exchange_ms = st.exchange_ms;
+    stats->merge_ms = st.merge_ms;
+    stats->bytes_received = st.bytes_received;
+    stats->records_local = st.records_local;
+    stats->records_total = st.records_total;
+  }
+  if (out) *out = rs.release();
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+anl_status anl_shard_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                         const anl_search_params* params, anl_result_set** out) try {
+  if (!m || !offsets || !params || !out || (!blob && n_queries > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built || !m->engine.uploaded())
+    return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_variants()");
+  std::string err;
+  int status = ANL_OK;
+  DeviceBatch* b = m->engine.create_batch(blob ? blob : "", offsets, n_queries, *params, false, true, &err, &status);
+  if (!b) return fail(status ? status : ANL_ERR_CUDA, err);
+  std::unique_ptr<anl_result_set> rs(new anl_result_set());
+  const bool ok = m->engine.shard_step(b, &rs->rs, nullptr, &err, &status);
+  m->engine.free_batch(b);
+  if (!ok) return fail(status ? status : ANL_ERR_CUDA, err);
+  *out = rs.release();
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+
 anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) try {
   if (!m || !out) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "model has not been built");

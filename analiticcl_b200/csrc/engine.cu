@@ -177,6 +177,7 @@ static bool pinned_realloc(T** p, size_t count, std::string* err) {
 }
 
 Engine::~Engine() {
+  shard_comm_free();
   for (DeviceBatch* b : cache_) destroy_batch(b);
   cache_.clear();
   release_index();
@@ -1542,6 +1543,14 @@ bool Engine::shard_export(DeviceBatch* b, void* d_heads, void* d_records, void* 
 bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_all, const void* d_records_all,
                          const void* d_gids_all, const void* d_flags_all, uint64_t record_stride, uint32_t max_survivors,
                          ResultSet* out, std::string* err, int* status) {
+  return shard_merge_strided(b, n_shards, d_heads_all, d_records_all, d_gids_all, d_flags_all, b->n, record_stride, max_survivors, out,
+                             err, status);
+}
+
+// heads / flags of shard r at r * query_stride, records / gather ids at r * record_stride
+bool Engine::shard_merge_strided(DeviceBatch* b, uint32_t n_shards, const void* d_heads_all, const void* d_records_all,
+                                 const void* d_gids_all, const void* d_flags_all, uint64_t query_stride, uint64_t record_stride,
+                                 uint32_t max_survivors, ResultSet* out, std::string* err, int* status) {
   *status = ANL_ERR_CUDA;
   if (!b->sharded) {
     *err = "not a sharded batch";
@@ -1553,7 +1562,9 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
   cudaStream_t st = b->stream;
   // a hit-list overflow on any shard cannot be repaired after the exchange: fail on every rank alike
   std::vector<uint32_t> flags_all((size_t)n * n_shards);
-  if (n) CU_TRY(cudaMemcpy(flags_all.data(), d_flags_all, flags_all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (n)
+    CU_TRY(cudaMemcpy2D(flags_all.data(), (size_t)n * sizeof(uint32_t), d_flags_all, (size_t)query_stride * sizeof(uint32_t),
+                        (size_t)n * sizeof(uint32_t), n_shards, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < flags_all.size(); ++i) {
     if ((flags_all[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) {
       *err = "query " + std::to_string(i % std::max<uint32_t>(n, 1)) +
@@ -1578,8 +1589,8 @@ bool Engine::shard_merge(DeviceBatch* b, uint32_t n_shards, const void* d_heads_
   BatchParams bp = b->bp;
   bp.finish_mode = b->final_mode;
   bp.pool_cap = b->cap_pool;
-  CU_TRY(launch_merge(bp, n, n_shards, reinterpret_cast<const OutHead*>(d_heads_all), reinterpret_cast<const OutRec*>(d_records_all),
-                      reinterpret_cast<const uint32_t*>(d_gids_all), (uint32_t)record_stride,
+  CU_TRY(launch_merge(bp, n, n_shards, reinterpret_cast<const OutHead*>(d_heads_all), (uint32_t)query_stride,
+                      reinterpret_cast<const OutRec*>(d_records_all), reinterpret_cast<const uint32_t*>(d_gids_all), (uint32_t)record_stride,
                       reinterpret_cast<const uint32_t*>(d_flags_all), b->d_qflags, b->d_out, b->d_head, b->d_scratch, cap,
                       b->d_work, sm_count_, st));
   // the merged lists are final: the host post-pass / export stage follow the final mode

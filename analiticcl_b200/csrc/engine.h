@@ -120,6 +120,13 @@ struct DeviceBatch {
   uint64_t results = 0;
 };
 
+struct ShardComm;  // shard_comm.cu: NCCL communicator + receive buffers of the lexicon-sharded mode
+struct ShardStepStats {
+  float score_ms, exchange_ms, merge_ms;
+  uint64_t bytes_received, records_local, records_total;
+};
+bool shard_unique_id(uint8_t* id128, std::string* err);
+
 class Engine {
  public:
   explicit Engine(HostModel* hm) : hm_(hm) {}
@@ -163,6 +170,15 @@ class Engine {
                    const void* d_gids_all, const void* d_flags_all, uint64_t record_stride, uint32_t max_survivors,
                    ResultSet* out, std::string* err, int* status);
 
+  // the same with the exchange inside the library (shard_comm.cu): NCCL communicator over the shards' ranks, then per
+  // batch: score against the shard, exchange all shards' survivors, merge.  out == nullptr: results stay on the device.
+  bool shard_comm_init(const uint8_t* id128, int rank, int n_ranks, std::string* err);
+  void shard_comm_free();
+  bool shard_step(DeviceBatch* b, ResultSet* out, ShardStepStats* stats, std::string* err, int* status);
+  bool shard_merge_strided(DeviceBatch* b, uint32_t n_shards, const void* d_heads_all, const void* d_records_all,
+                           const void* d_gids_all, const void* d_flags_all, uint64_t query_stride, uint64_t record_stride,
+                           uint32_t max_survivors, ResultSet* out, std::string* err, int* status);
+
   const DeviceIndex& host_view() const { return h_ix_; }
   bool uploaded() const { return d_ix_ != nullptr; }
   cudaStream_t stream() const { return stream_; }
@@ -199,6 +215,7 @@ class Engine {
   size_t conf_vocab_ = 0;              // vocabulary size the device text blob was built from
   std::mutex cache_m_;
   std::vector<DeviceBatch*> cache_;  // idle batches whose buffers can be reused
+  ShardComm* shard_comm_ = nullptr;
 };
 
 // anl_find_variants_batch over one or more replicas of the index (one Engine per device): the batch is cut into chunks

@@ -2005,7 +2005,7 @@ score_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
 // G lists, takes the global max_freq (frequency normalisation is global, src/lib.rs:1460,1521-1525)
 // and runs the same rank / crop / cut-off tail as the unsharded kernel.
 __global__ void __launch_bounds__(K2_WARPS * 32)
-merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead* __restrict__ heads_all,
+merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead* __restrict__ heads_all, uint32_t head_stride,
              const OutRec* __restrict__ recs_all, const uint32_t* __restrict__ gids_all, uint32_t rec_stride,
              const uint32_t* __restrict__ qflags_in, uint32_t* __restrict__ qflags, OutRec* __restrict__ out,
              OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, uint32_t scratch_cap, unsigned int* work,
@@ -2023,7 +2023,7 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
     double maxfreq = 0.0;
     const uint32_t flags = qflags_in[qi];
     for (uint32_t r = 0; r < n_shards; ++r) {
-      const OutHead h = heads_all[(size_t)r * nq + qi];
+      const OutHead h = heads_all[(size_t)r * head_stride + qi];
       maxfreq = fmax(maxfreq, h.max_freq);
       const OutRec* recs = recs_all + (size_t)r * rec_stride + h.offset;
       const uint32_t* gids = gids_all + (size_t)r * rec_stride + h.offset;
@@ -2280,15 +2280,15 @@ finish_kernel(const BatchParams bp, uint32_t nq, OutRec* __restrict__ out, OutHe
   }
 }
 
-cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, const OutRec* recs_all,
-                         const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
+cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, uint32_t head_stride,
+                         const OutRec* recs_all, const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
                          OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,
                          cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(work, 0, 4 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   long long grid = merge_grid(sm_count, n);
-  merge_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(bp, n, n_shards, heads_all, recs_all, gids_all, rec_stride,
+  merge_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(bp, n, n_shards, heads_all, head_stride, recs_all, gids_all, rec_stride,
                                                              qflags_in, qflags, out, out_head,
                                                              reinterpret_cast<SurvRec*>(scratch), scratch_cap, work + 1,
                                                              work + 2);

@@ -76,8 +76,42 @@ class ShardedVariantModel(VariantModel):
                 _lib().anl_result_set_free(rs)
             _lib().anl_device_batch_free(self._h, batch)
 
-    # -- the whole exchange over torch.distributed (NCCL) ------------------------------------------------
+    # -- the exchange inside the library (csrc/shard_comm.cu): NCCL communicator over the shards' ranks ----------
+    def init_comm(self, group=None):
+        """Collective over the ranks that hold the shards: rank 0 draws an NCCL id, torch.distributed carries it to
+        the others (plumbing), every rank joins the library's own communicator with its shard coordinates."""
+        rank = dist.get_rank(group)
+        world = dist.get_world_size(group)
+        assert world == self.n_shards and rank == self.shard, "one rank per shard, rank == shard"
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(_lib().anl_shard_comm_id(ident))
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        _check(_lib().anl_shard_comm_init(self._h, ident, rank, world))
+        self._comm = True
+
     def find_variants_raw(self, inputs, params, device=None, group=None):
+        """All ranks call this with the same inputs; every rank returns the full, merged result lists.  One call
+        into the library: score against the shard, exchange every shard's survivors over NCCL, merge."""
+        inputs = list(inputs)
+        if not getattr(self, "_comm", False):
+            self.init_comm(group)
+        blob, offs = _capi.pack(inputs)
+        rs = C.c_void_p()
+        _check(_lib().anl_shard_find_variants_batch(self._h, blob, _capi.u64ptr(offs), len(inputs), C.byref(params.data),
+                                                    C.byref(rs)))
+        try:
+            o = _lib().anl_result_set_offsets(rs)
+            var = _lib().anl_result_set_variants(rs)
+            return [[(var[j].vocab_id, var[j].dist_score, var[j].freq_score) for j in range(o[i], o[i + 1])]
+                    for i in range(len(inputs))]
+        finally:
+            _lib().anl_result_set_free(rs)
+
+    # -- the same exchange with torch.distributed collectives (kept as a cross-check of the library's own) --------
+    def find_variants_raw_torch(self, inputs, params, device=None, group=None):
         """All ranks call this with the same inputs; every rank returns the full, merged result lists."""
         inputs = list(inputs)
         device = torch.cuda.current_device() if device is None else device

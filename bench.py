@@ -469,9 +469,10 @@ def run_search(args):
 
 
 def run_sharded(args):
-    """--sharded: lexicon-sharded mode (SURVEY 8e mode 2).  Every rank holds 1/N of the anagram keys, scores
-    the WHOLE batch against its shard, the survivor lists are exchanged with NCCL all-gathers and merged
-    on every rank.  A step = score kernels + export + 4 all-gathers + merge kernel, batch resident in HBM."""
+    """--sharded: lexicon-sharded mode (SURVEY 8e mode 2).  Every rank holds 1/N of the anagram keys, scores the WHOLE
+    batch against its shard; the library exchanges the survivor lists over NCCL (one 8-byte all-gather of sizes + ONE
+    grouped collective with exact sizes, csrc/shard_comm.cu) and merges on every rank.  A step = anl_shard_batch_step:
+    score kernels + exchange + merge kernel + export kernels, batch resident in HBM; CUDA events per part."""
     import torch
     import torch.distributed as dist
     import analiticcl_b200 as A
@@ -493,6 +494,7 @@ def run_sharded(args):
     t0 = time.perf_counter()
     m.build(device=local_rank, shard=rank, n_shards=world)
     build_s = time.perf_counter() - t0
+    m.init_comm()  # the library's own NCCL communicator (torch.distributed only carries the id)
     n = args.queries or spec["n"]
     queries = spec["queries"](n)
     sp = A.SearchParameters(**spec["params"])
@@ -505,34 +507,10 @@ def run_sharded(args):
     blob, offs = _capi.pack(queries)
     batch = C.c_void_p()
     check(L.anl_device_batch_create(m._h, blob, _capi.u64ptr(offs), n, C.byref(sp.data), C.byref(batch)))
-    bytes_exchanged = [0]
+    stats = _capi.ShardStepStats()
 
     def step():
-        check(L.anl_device_batch_run(m._h, batch, None))
-        n_rec, mx = C.c_uint64(), C.c_uint32()
-        check(L.anl_shard_export_size(m._h, batch, C.byref(n_rec), C.byref(mx)))
-        sizes = torch.tensor([n_rec.value, mx.value], dtype=torch.int64, device=dev)
-        all_sizes = torch.empty((world, 2), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_sizes, sizes)
-        stride = max(1, int(all_sizes[:, 0].max().item()))
-        max_surv = int(all_sizes[:, 1].sum().item())
-        heads = torch.empty((n, 2), dtype=torch.int64, device=dev)
-        recs = torch.zeros((stride, 2), dtype=torch.int64, device=dev)
-        gids = torch.zeros((stride,), dtype=torch.int32, device=dev)
-        flags = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(L.anl_shard_export(m._h, batch, heads.data_ptr(), recs.data_ptr(), gids.data_ptr(), flags.data_ptr()))
-        heads_all = torch.empty((world * n, 2), dtype=torch.int64, device=dev)
-        recs_all = torch.empty((world * stride, 2), dtype=torch.int64, device=dev)
-        gids_all = torch.empty((world * stride,), dtype=torch.int32, device=dev)
-        flags_all = torch.empty((world * n,), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(heads_all, heads)
-        dist.all_gather_into_tensor(recs_all, recs)
-        dist.all_gather_into_tensor(gids_all, gids)
-        dist.all_gather_into_tensor(flags_all, flags)
-        torch.cuda.synchronize(dev)
-        bytes_exchanged[0] = (world - 1) * (n * 20 + stride * 20)
-        check(L.anl_shard_merge(m._h, batch, world, heads_all.data_ptr(), recs_all.data_ptr(), gids_all.data_ptr(),
-                                flags_all.data_ptr(), stride, max_surv, None))
+        check(L.anl_shard_batch_step(m._h, batch, C.byref(stats), None))
 
     for _ in range(args.warmup):
         step()
@@ -541,35 +519,41 @@ def run_sharded(args):
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = L.anl_kernel_launches()
+    acc = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+        acc[0] += stats.score_ms
+        acc[1] += stats.exchange_ms
+        acc[2] += stats.merge_ms
     torch.cuda.synchronize()
     dist.barrier()
     dt = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
-    pm, sm_ = C.c_float(), C.c_float()
-    check(L.anl_device_batch_timings(m._h, batch, C.byref(pm), C.byref(sm_), None))
-    t = torch.tensor([dt, pm.value, sm_.value], dtype=torch.float64, device=dev)
+    t = torch.tensor([dt] + [a / args.steps for a in acc], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt_max, probe_ms, score_ms = t.tolist()
+    dt_max, score_ms, exchange_ms, merge_ms = t.tolist()
     if rank == 0:
         line = {
             "metric": METRIC, "value": n / dt_max, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt_max * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 multi-limb integer / u8 DP / f64 score", "data": "synthetic",
             "config": {"workload": spec["label"], "batch_queries": n,
-                       "parallelism": f"lexicon-sharded x{world} (hash(key) mod N) + NCCL all-gather merge",
+                       "parallelism": f"lexicon-sharded x{world} (hash(key) mod N) + NCCL exchange inside the library + merge",
                        "index": m.index_stats(), "build_seconds": build_s,
-                       "value_scope": "score kernels on the shard + survivor export + 4 NCCL all-gathers + merge kernel; "
-                                      "batch resident in HBM, host wall clock with device synchronisation (max over ranks)"},
-            "kernels": {"probe_ms": probe_ms, "score_ms": score_ms,
-                        "exchange_and_merge_ms": dt_max * 1e3 - probe_ms - score_ms,
-                        "nvlink_bytes_received_per_rank": bytes_exchanged[0]},
+                       "value_scope": "per step: score kernels on the shard, 8-byte all-gather of sizes, one grouped NCCL collective "
+                                      "with every shard's survivors (exact sizes), merge kernel, export kernels; batch resident in HBM; "
+                                      "host wall clock over the steps (max over ranks), parts by CUDA events"},
+            "kernels": {"score_ms": score_ms, "exchange_ms": exchange_ms, "merge_and_export_ms": merge_ms,
+                        "exchange_and_merge_ms": exchange_ms + merge_ms,
+                        "nvlink_bytes_received_per_rank": int(stats.bytes_received),
+                        "nvlink_gbs_received": stats.bytes_received / (exchange_ms / 1e3) / 1e9 if exchange_ms > 0 else None,
+                        "survivor_records_this_rank": int(stats.records_local), "survivor_records_all_ranks": int(stats.records_total)},
             "gpu_launches": L.anl_kernel_launches() - launches0, "clocks": clocks,
         }
         print(json.dumps(line))
     L.anl_device_batch_free(m._h, batch)
+    L.anl_shard_comm_free(m._h)
     dist.destroy_process_group()
 
 

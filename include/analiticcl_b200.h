@@ -334,6 +334,27 @@ anl_status anl_shard_merge(anl_model* m, anl_device_batch* b, uint32_t n_shards,
                            const void* d_records_all, const void* d_gids_all, const void* d_flags_all, uint64_t record_stride,
                            uint32_t max_survivors, anl_result_set** out);
 
+/* The same mode with the exchange inside the library: an NCCL communicator over the ranks that hold the shards
+ * (one process per GPU; NCCL is bound at run time, in a torch process it is the copy torch loaded).  Rank 0 obtains
+ * an id with anl_shard_comm_id and hands it to the other ranks by any host-side means (torch.distributed broadcast,
+ * MPI, a file); every rank then calls anl_shard_comm_init with its shard coordinates.  Per batch (all ranks, same
+ * queries): score against the shard, one 8-byte all-gather of sizes, ONE grouped collective that moves every shard's
+ * survivors with exact sizes over NVLink, merge kernel with the global max frequency, export stage. */
+#define ANL_SHARD_ID_BYTES 128
+anl_status anl_shard_comm_id(uint8_t id[ANL_SHARD_ID_BYTES]);
+anl_status anl_shard_comm_init(anl_model* m, const uint8_t id[ANL_SHARD_ID_BYTES], int32_t rank, int32_t n_ranks);
+void anl_shard_comm_free(anl_model* m);
+typedef struct anl_shard_step_stats {
+  float score_ms, exchange_ms, merge_ms;                         /* CUDA events on the batch's stream */
+  uint64_t bytes_received, records_local, records_total;         /* NVLink bytes this rank received; survivor records */
+} anl_shard_step_stats;
+/* One pass over a resident batch (anl_device_batch_create on a sharded model): score, exchange, merge.  stats and out
+ * may be NULL (out == NULL: the merged, exported results stay on the device). */
+anl_status anl_shard_batch_step(anl_model* m, anl_device_batch* b, anl_shard_step_stats* stats, anl_result_set** out);
+/* anl_find_variants_batch for a sharded model: every rank passes the same queries and receives the full result. */
+anl_status anl_shard_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
+                                         const anl_search_params* params, anl_result_set** out);
+
 /* Size of the device-resident index (bytes per component) for roofline accounting. */
 typedef struct anl_index_stats {
   uint64_t table_slots, table_bytes, slot_bytes, table_keys;

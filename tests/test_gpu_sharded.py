@@ -68,9 +68,11 @@ def _worker(rank, world, port, queries, q):
     m = sharded.ShardedVariantModel(workloads.ALPHABET, A.Weights())
     m.read_lexicon(workloads.lexicon_path("eng"))
     m.build(device=rank, shard=rank, n_shards=world)
-    res = m.find_variants_raw(queries, A.SearchParameters(), device=rank)
+    res = m.find_variants_raw(queries, A.SearchParameters(), device=rank)  # the library's own NCCL exchange
+    res_torch = m.find_variants_raw_torch(queries, A.SearchParameters(), device=rank)  # cross-check: torch collectives
+    again = m.find_variants_raw(queries[:700], A.SearchParameters(freq_weight=0.2, max_matches=5), device=rank)
     if rank == 0:
-        q.put(res)
+        q.put((res, res_torch, again))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -88,8 +90,12 @@ def test_sharded_nccl_two_gpus(eng_oracle):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, qs, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got, got_torch, again = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert_same(got, eng_oracle.find_variants_batch(qs, orc.make_params()), qs, "nccl sharded")
+    exp = eng_oracle.find_variants_batch(qs, orc.make_params())
+    assert_same(got, exp, qs, "nccl sharded (library exchange)")
+    assert_same(got_torch, exp, qs, "nccl sharded (torch collectives)")
+    assert_same(again, eng_oracle.find_variants_batch(qs[:700], orc.make_params(freq_weight=0.2, max_matches=5)), qs[:700],
+                "nccl sharded, second batch on the same communicator")
