@@ -272,13 +272,16 @@ class VariantModel:
     def add_contextrule(self, pattern, score, tag, tagoffset):
         raise NotImplementedError("context rules are outside the variant-lookup hot path (see DESIGN.md)")
 
-    def build(self, device=-1, devices=None):
+    def build(self, device=-1, devices=None, gpu_build=None):
         """Build the anagram index and upload it to the GPU (`device` = CUDA ordinal, -1 = current).  With
         `devices=[0, 1, ...]` every listed GPU of this process gets a replica and each lookup call is spread over
-        all of them (anl_model_build_multi)."""
+        all of them (anl_model_build_multi).  `gpu_build=True/False` forces the index construction onto the device /
+        the host cores (default: the device for lexicons of a million entries and more)."""
         if devices is not None:
             arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
             _check(_lib().anl_model_build_multi(self._h, arr, len(devices)))
+        elif gpu_build is not None:
+            _check(_lib().anl_model_build_on(self._h, int(device), int(bool(gpu_build))))
         else:
             _check(_lib().anl_model_build(self._h, int(device)))
 

@@ -95,6 +95,8 @@ SIGNATURES = {
     "anl_model_set_confusables_before_pruning": (None, [_vp]),
     "anl_model_build": (_i32, [_vp, _i32]),
     "anl_model_build_multi": (_i32, [_vp, _P(C.c_int32), _u32]),
+    "anl_model_build_on": (_i32, [_vp, _i32, _i32]),
+    "anl_debug_index_digest": (None, [_vp, _P(_u64), _sz]),
     "anl_model_device_count": (_u32, [_vp]),
     "anl_model_has": (_i32, [_vp, _cp, _sz]),
     "anl_model_vocab_id": (_i64, [_vp, _cp, _sz]),

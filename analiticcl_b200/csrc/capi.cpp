@@ -229,12 +229,33 @@ static anl_status upload_replicas(anl_model* m, const int32_t* devices, uint32_t
     if (!m->engines[i]->upload(devices ? devices[i] : -1, &err)) return fail(ANL_ERR_CUDA, err);
   return ANL_OK;
 }
+// Which build?  ANL_GPU_BUILD=1 / 0 forces the device / host build; by default lexicons of a million entries and more
+// are built on the device (seconds instead of tens of seconds), smaller ones on the host (the fixed cost of the device
+// pipeline -- allocations, a dozen launches, the download -- is what a small host build takes in total).
+static bool build_any(anl_model* m, int sd, uint32_t shard, uint32_t n_shards, int32_t device, int32_t where, std::string* err) {
+  int use_gpu = where;  // -1 = choose
+  if (use_gpu < 0) {
+    if (const char* e = getenv("ANL_GPU_BUILD")) use_gpu = atoi(e) ? 1 : 0;
+  }
+  if (use_gpu < 0) use_gpu = m->host.decoder.size() >= 1000000 ? 1 : 0;
+  return use_gpu ? gpu_build_index(&m->host, sd, shard, n_shards, device, err) : m->host.build_index(sd, shard, n_shards, err);
+}
 anl_status anl_model_build_sharded(anl_model* m, int32_t device, uint32_t shard, uint32_t n_shards) try {
   if (!m) return fail(ANL_ERR_INVALID, "null argument");
   std::string err;
   int sd = 1;
   if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
-  if (!m->host.build_index(sd, shard, n_shards, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  if (!build_any(m, sd, shard, n_shards, device, -1, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  return upload_replicas(m, &device, 1);
+} catch (...) {
+  return on_exception();
+}
+anl_status anl_model_build_on(anl_model* m, int32_t device, int32_t build_on_device) try {
+  if (!m) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  int sd = 1;
+  if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
+  if (!build_any(m, sd, 0, 1, device, build_on_device ? 1 : 0, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
   return upload_replicas(m, &device, 1);
 } catch (...) {
   return on_exception();
@@ -248,7 +269,7 @@ anl_status anl_model_build_multi(anl_model* m, const int32_t* devices, uint32_t 
   std::string err;
   int sd = 1;
   if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
-  if (!m->host.build_index(sd, 0, 1, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+  if (!build_any(m, sd, 0, 1, devices[0], -1, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
   return upload_replicas(m, devices, n_devices);
 } catch (...) {
   return on_exception();
@@ -1010,6 +1031,10 @@ anl_status anl_shard_find_variants_batch(anl_model* m, const char* blob, const u
   return ANL_OK;
 } catch (...) {
   return on_exception();
+}
+
+void anl_debug_index_digest(const anl_model* m, uint64_t* out, size_t cap) {
+  if (m && out) m->host.index_digest(out, cap);
 }
 
 anl_status anl_model_index_stats(const anl_model* m, anl_index_stats* out) try {

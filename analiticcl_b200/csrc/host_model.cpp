@@ -984,6 +984,46 @@ uint64_t fp_mix(uint64_t h, uint64_t x) {
 }
 }  // namespace
 
+// Test hook: per-array checksums of the built index (in file order), an order-independent digest of the table's
+// slots and whether every slot is reachable by linear probing from its home position.
+void HostModel::index_digest(uint64_t* out, size_t cap) const {
+  uint64_t v[16] = {0};
+  const HostIndex& ix = index;
+  if (built) {
+    v[0] = array_checksum(1, ix.ana_key);
+    v[1] = array_checksum(1, ix.ana_inst_off);
+    v[2] = array_checksum(1, ix.ana_charcount);
+    v[3] = array_checksum(1, ix.inst_vocab);
+    v[4] = array_checksum(1, ix.inst_freq);
+    v[5] = array_checksum(1, ix.inst_gid);
+    v[6] = array_checksum(1, ix.inst_rows);
+    v[7] = array_checksum(1, ix.table);
+    v[8] = array_checksum(1, ix.bloom);
+    v[9] = array_checksum(1, ix.post_ana);
+    v[10] = array_checksum(1, ix.post_cls);
+    v[11] = array_checksum(1, ix.active_classes);
+    const size_t slots = ix.table.size();
+    uint64_t sum = 0, occupied = 0;
+    bool reachable = true;
+    for (size_t i = 0; i < slots; ++i) {
+      const Slot& sl = ix.table[i];
+      if (sl.post_cnt == 0) continue;
+      ++occupied;
+      sum += fp_mix(fp_mix(sl.fp, sl.post_off), sl.post_cnt);
+      for (size_t j = fp_index(sl.fp, slots - 1); j != i; j = (j + 1) & (slots - 1))
+        if (ix.table[j].post_cnt == 0) {
+          reachable = false;  // an empty slot between the home position and the key: a probe would stop there
+          break;
+        }
+    }
+    v[12] = sum;
+    v[13] = reachable ? 1 : 0;
+    v[14] = occupied;
+    v[15] = fp_mix(fp_mix(fp_mix(ix.norm_stride, ix.max_len), ix.max_charcount), fp_mix(ix.max_key_bits, ix.charcount_mask[0] ^ ix.charcount_mask[1]));
+  }
+  for (size_t i = 0; i < cap && i < 16; ++i) out[i] = v[i];
+}
+
 // Everything build_index reads: per vocabulary entry (in id order) its text, normalised symbols, frequency,
 // vocabulary type and case flag, plus the alphabet size.
 uint64_t HostModel::vocabulary_fingerprint() const {

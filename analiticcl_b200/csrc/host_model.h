@@ -135,6 +135,7 @@ class HostModel {
   // pins the library's struct layout and a fingerprint of the vocabulary the index was built from.  load_index
   // replaces build_index (same arrays, bit for bit) for a model that holds the same vocabulary in the same order.
   uint64_t vocabulary_fingerprint() const;
+  void index_digest(uint64_t* out, size_t cap) const;  // test hook (see anl_debug_index_digest)
   // what build_index refuses about variant lists (also re-checked by load_index)
   bool check_variant_support(uint32_t n_shards, std::string* err) const;
   bool save_index(const std::string& path, std::string* err) const;
@@ -185,5 +186,8 @@ bool parse_confusable(const std::string& editscript, double weight, Confusable* 
 bool confusable_found_in(const Confusable& c, const std::vector<EditInstruction>& script);  // src/confusables.rs:47-128
 
 extern const uint32_t kPrimes[168];  // src/types.rs:20-30
+
+// The same build on the GPU (gpu_build.cu): fills hm->index like HostModel::build_index.
+bool gpu_build_index(HostModel* hm, int sd, uint32_t shard, uint32_t n_shards, int device, std::string* err);
 
 }  // namespace anl

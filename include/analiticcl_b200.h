@@ -148,6 +148,11 @@ void anl_model_set_confusables_before_pruning(anl_model* m);
 
 /* build (src/lib.rs:192): anagram index on the host, then upload to `device` (-1 = current). */
 anl_status anl_model_build(anl_model* m, int32_t device);
+/* build with the index construction itself forced onto the device (build_on_device = 1: anagram values, sorts,
+ * postings, Bloom filter and table as kernels, csrc/gpu_build.cu) or onto the host cores (0).  anl_model_build chooses:
+ * the device for lexicons of a million entries and more (ANL_GPU_BUILD=0/1 overrides).  Both builds produce the same
+ * index arrays; only the slot order inside the open-addressing table differs (both are valid probe layouts). */
+anl_status anl_model_build_on(anl_model* m, int32_t device, int32_t build_on_device);
 /* build with one replica of the index on each of `n_devices` CUDA devices of this process.  Lookups
  * (anl_find_variants_batch, anl_find_all_matches) then spread every call over all of them: the batch is cut into
  * chunks that go round-robin to the devices, each device is driven by its own host thread, and the results come back
@@ -354,6 +359,13 @@ anl_status anl_shard_batch_step(anl_model* m, anl_device_batch* b, anl_shard_ste
 /* anl_find_variants_batch for a sharded model: every rank passes the same queries and receives the full result. */
 anl_status anl_shard_find_variants_batch(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_queries,
                                          const anl_search_params* params, anl_result_set** out);
+
+/* Test hook: out[0..11] = checksums of the index arrays in file order (anagram keys, instance offsets, charcounts,
+ * vocabulary ids, frequencies, global gather ids, instance rows, table, Bloom words, posting anagrams, posting classes,
+ * active classes); out[12] = order-independent digest of the occupied slots; out[13] = 1 iff every slot is reachable by
+ * linear probing from its home position; out[14] = occupied slots; out[15] = digest of the scalar fields.  The host
+ * build and the device build must agree on everything but out[7] (the slot order inside the table). */
+void anl_debug_index_digest(const anl_model* m, uint64_t* out, size_t cap);
 
 /* Size of the device-resident index (bytes per component) for roofline accounting. */
 typedef struct anl_index_stats {
