@@ -134,6 +134,8 @@ SIGNATURES = {
     "anl_debug_match_set_build": (_i32, [_cp, _sz, C.c_uint32, C.c_int32, _P(C.c_uint8), _P(C.c_uint64), _P(Variant), _u64, _P(_vp)]),
     "anl_debug_find_boundaries": (_i64, [_cp, _sz, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz]),
     "anl_debug_segment_text": (_i64, [_cp, _sz, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32), _sz]),
+    "anl_debug_segment_text_device": (_i64, [C.c_int32, _cp, _sz, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32), _sz,
+                                             _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz, _P(C.c_uint64)]),
     "anl_device_batch_create": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _P(_vp)]),
     "anl_device_batch_run": (_i32, [_vp, _vp, _vp]),
     "anl_device_batch_timings": (_i32, [_vp, _vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),

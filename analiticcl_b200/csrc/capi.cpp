@@ -42,6 +42,7 @@ struct anl_match_set {
   uint64_t logical_lookups = 0, distinct_lookups = 0;
   PodBuffer<anl_match> matches;
   PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
+  std::shared_ptr<Segmentation> seg;  // the producer's segmentation (anl_find_all_matches), reused by the consolidation
 };
 struct anl_device_batch {
   DeviceBatch* b;
@@ -453,8 +454,11 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   const std::string t(text ? text : "", len);
   std::unique_ptr<anl_match_set> ms_owner(new anl_match_set());  // (released to *out on success only)
   anl_match_set* ms = ms_owner.get();
-  SegmentedText st;
-  segment_text(t, params->max_ngram, &st);
+  std::string err;
+  ms->seg = std::make_shared<Segmentation>();
+  // the batch producer: on the device for running text, the host loop for short strings (search.h segment_on_device)
+  if (!segment_any(m->replicas()[0]->device(), t, params->max_ngram, ms->seg.get(), &err)) return fail(ANL_ERR_CUDA, err);
+  SegmentedText& st = ms->seg->st;
   pt.lap("search: segmentation");
   std::vector<uint64_t> cpmap;
   if (params->unicodeoffsets) cpmap = byte_to_codepoint_map(t);  // src/lib.rs:1949-1956
@@ -469,7 +473,6 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   off.resize(nseg + 1);
   dst.resize(nseg + 1);
   ms->matches.resize(nseg);
-  std::string err;
   int status = ANL_OK;
   size_t WINDOW = 1u << 20;  // unigram segments per window
   if (const char* e = getenv("ANL_SEARCH_WINDOW")) WINDOW = (size_t)std::max(1, atoi(e));
@@ -700,14 +703,19 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
   if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   PhaseTimer pt;
   const std::string t(text ? text : "", len);
-  SegmentedText st;
-  segment_text(t, params->max_ngram, &st);
+  // the producer's own segmentation when the match set still carries it (anl_find_all_matches), else re-derived
+  std::shared_ptr<Segmentation> seg = in->seg;
+  if (!seg || seg->text_len != len || seg->max_ngram != params->max_ngram) {
+    seg = std::make_shared<Segmentation>();
+    std::string err;
+    segment_any(-1, t, params->max_ngram, seg.get(), &err);
+  }
+  const SegmentedText& st = seg->st;
   pt.lap("consolidate: segmentation");
   if (st.segs.size() != in->matches.size())
     return fail(ANL_ERR_INVALID, "match set does not belong to this text / max_ngram (segment count differs)");
-  const std::vector<Boundary>& bounds = find_boundaries(t);
-  std::vector<BatchDesc> descs;
-  if (!t.empty()) list_batches(bounds, &descs);
+  const std::vector<Boundary>& bounds = seg->bounds;
+  const std::vector<BatchDesc>& descs = seg->batches;
   const size_t nbatch = st.batch_first.size() - 1;
   if (descs.size() != nbatch) return fail(ANL_ERR_INVALID, "match set does not belong to this text (batch count differs)");
   const float fw = params->freq_weight;
@@ -812,9 +820,31 @@ int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin,
 }
 int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end, uint32_t* order,
                                uint32_t* batch, size_t cap) {
+  return anl_debug_segment_text_device(-1, text, len, max_ngram, begin, end, order, batch, cap, nullptr, nullptr, nullptr, 0, nullptr);
+}
+int64_t anl_debug_segment_text_device(int32_t device, const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end,
+                                      uint32_t* order, uint32_t* batch, size_t cap, uint64_t* bound_begin, uint64_t* bound_end,
+                                      int32_t* bound_strength, size_t bound_cap, uint64_t* n_bounds) try {
   const std::string t(text ? text : "", len);
-  SegmentedText st;
-  segment_text(t, max_ngram, &st);
+  Segmentation sg;
+  std::string err;
+  if (device >= 0) {
+    sg.text_len = len;
+    sg.max_ngram = max_ngram;
+    if (!segment_text_device(device, t, max_ngram, &sg.st, &err, &sg.bounds, &sg.batches)) {
+      fail(ANL_ERR_CUDA, err);
+      return -1;
+    }
+  } else {
+    segment_any(-1, t, max_ngram, &sg, &err);
+  }
+  const SegmentedText& st = sg.st;
+  if (n_bounds) *n_bounds = sg.bounds.size();
+  for (size_t i = 0; i < sg.bounds.size() && i < bound_cap; ++i) {
+    if (bound_begin) bound_begin[i] = sg.bounds[i].begin;
+    if (bound_end) bound_end[i] = sg.bounds[i].end;
+    if (bound_strength) bound_strength[i] = sg.bounds[i].strength;
+  }
   const size_t nb = st.batch_first.size() - 1;
   for (size_t b = 0; b < nb; ++b)
     for (uint64_t k = st.batch_first[b]; k < st.batch_first[b + 1] && k < cap; ++k) {
@@ -824,6 +854,9 @@ int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram,
       batch[k] = (uint32_t)b;
     }
   return (int64_t)st.segs.size();
+} catch (...) {
+  on_exception();
+  return -1;
 }
 
 // A match set as anl_find_all_matches assembles it, from caller-supplied variant lists (one per segment, in the

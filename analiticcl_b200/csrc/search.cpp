@@ -8,6 +8,7 @@
 #include "search.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "hostpool.h"
@@ -135,11 +136,34 @@ void list_batches(const std::vector<Boundary>& bounds, std::vector<BatchDesc>* o
   }
 }
 
-void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp) {
+bool segment_on_device(size_t len) {
+  if (const char* e = getenv("ANL_SEGMENT")) {
+    if (e[0] == 'h') return false;
+    if (e[0] == 'd') return len > 0 && len < 0x7FFFFFF0ull;
+  }
+  if (len == 0) return false;
+  size_t min_len = 1u << 16;
+  if (const char* e = getenv("ANL_SEGMENT_DEVICE_MIN")) min_len = (size_t)std::max(0ll, atoll(e));
+  return len >= min_len && len < 0x7FFFFFF0ull;
+}
+
+bool segment_any(int device, const std::string& text, uint32_t max_ngram, Segmentation* out, std::string* err) {
+  out->text_len = text.size();
+  out->max_ngram = max_ngram;
+  if (device >= 0 && segment_on_device(text.size()))
+    return segment_text_device(device, text, max_ngram, &out->st, err, &out->bounds, &out->batches);
+  segment_text(text, max_ngram, &out->st, &out->bounds, &out->batches);
+  return true;
+}
+
+void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp, std::vector<Boundary>* bounds_out,
+                  std::vector<BatchDesc>* batches_out) {
   SegmentedText& st = *stp;
   st.segs.clear();
   st.batch_first.resize(1);
   st.batch_first[0] = 0;
+  if (bounds_out) bounds_out->clear();
+  if (batches_out) batches_out->clear();
   if (text.empty()) return;
   const std::vector<Boundary>& bounds = find_boundaries(text);
   // (a lambda naming a thread_local would see the executing thread's instance: bind it to a local reference)
@@ -178,6 +202,8 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
       if (part[t] && !part[t]->empty())
         std::copy(part[t]->begin(), part[t]->end(), st.segs.data() + st.batch_first[range[t].first]);
   });
+  if (bounds_out) *bounds_out = bounds;
+  if (batches_out) *batches_out = descs;
 }
 
 // most_likely_sequence, src/lib.rs:2088-2495, without language model and context rules.

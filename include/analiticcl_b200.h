@@ -266,6 +266,12 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
 int64_t anl_debug_find_boundaries(const char* text, size_t len, uint64_t* begin, uint64_t* end, int32_t* strength, size_t cap);
 int64_t anl_debug_segment_text(const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end, uint32_t* order,
                                uint32_t* batch, size_t cap);
+/* The same producer run as kernels on CUDA device `device` (what anl_find_all_matches uses for running text; device < 0
+ * = the host loop): segments as above plus, optionally, the boundaries they were cut from (at most bound_cap are
+ * written, *n_bounds = how many there are).  Returns the number of segments, -1 on a CUDA error (anl_last_error). */
+int64_t anl_debug_segment_text_device(int32_t device, const char* text, size_t len, uint32_t max_ngram, uint64_t* begin, uint64_t* end,
+                                      uint32_t* order, uint32_t* batch, size_t cap, uint64_t* bound_begin, uint64_t* bound_end,
+                                      int32_t* bound_strength, size_t bound_cap, uint64_t* n_bounds);
 
 /* Test hook: a match set exactly as anl_find_all_matches assembles it, but from caller-supplied variant lists
  * (CSR `offsets[nseg + 1]` into `variants`, `looked[k]` = segment k was looked up; segments in the order of

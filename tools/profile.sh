@@ -9,12 +9,13 @@ mkdir -p gpurun_out
 Q=${Q:-1000000}
 W=${W:-cfg2}
 echo "$W $Q" > gpurun_out/profile_launch.txt
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
     python bench.py --workload $W --queries $Q --steps 2 --warmup 3 --e2e-steps 0 --cpu-sample 64 > gpurun_out/launches_bench.json 2> gpurun_out/launches.err
-for K in bloom exact score confusable; do
-  S=3  # (score: two launches per pass, the long-query class first on its side stream; 3 skipped = the short class of pass 2)
-  ncu --set full --clock-control none --import-source on -k regex:${K}_kernel -s $S -c 1 -f -o gpurun_out/prof_$K \
+KERNELS=${KERNELS:-"bloom exact pairfilter dp rank confusable"}
+for K in $KERNELS; do
+  S=3  # three warm-up passes skipped: the capture is the launch of the timed pass
+  ncu --set full --clock-control none --import-source on -k regex:^${K}_kernel -s $S -c 1 -f -o gpurun_out/prof_$K \
       python bench.py --workload $W --queries $Q --steps 1 --warmup 3 --e2e-steps 0 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_$K.err
 done
 ls -la gpurun_out
-tail -n 3 gpurun_out/launches.err gpurun_out/prof_bloom.err gpurun_out/prof_exact.err gpurun_out/prof_score.err gpurun_out/prof_confusable.err
+tail -n 2 gpurun_out/launches.err gpurun_out/prof_*.err

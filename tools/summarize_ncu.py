@@ -19,7 +19,7 @@ WANT = [
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "lts__t_sectors_op_read.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -56,7 +56,7 @@ except (OSError, ValueError):
 md = [f"# ncu summary {tag}", "",
       "Source: `tools/profile.sh` under gpurun (1x B200, `--clock-control none`). Full `.ncu-rep` files stay in",
       "`gpurun_out/` (scratch); this file holds what the numbers in DESIGN.md / bench.py are read from.", ""]
-for name in ("bloom", "exact", "score", "confusable"):
+for name in ("bloom", "exact", "pairfilter", "dp", "rank", "score", "confusable"):
     rep = os.path.join(OUT, f"prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -67,6 +67,15 @@ for name in ("bloom", "exact", "score", "confusable"):
         traffic[f"{name}_kernel"] = {"dram_bytes": float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]],
                                      "workload": launch_info[0], "queries": launch_info[1],
                                      "source": f"profiles/{tag}_ncu_summary.md (ncu --set full, one launch)"}
+        for key, metric in (("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            ("lanes_per_instruction", "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                            ("warp_instructions", "smsp__inst_executed.sum"), ("lts_sectors_read", "lts__t_sectors_op_read.sum"),
+                            ("l2_hit_pct", "lts__t_sector_hit_rate.pct"), ("dram_throughput_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")):
+            if metric in m:
+                try:
+                    traffic[f"{name}_kernel"][key] = float(m[metric][0].replace(",", ""))
+                except ValueError:
+                    pass
     except (KeyError, ValueError):
         pass
     md.append(f"## {name}_kernel (`ncu --set full`, one launch of {launch_info[1]} {launch_info[0]} queries)")
@@ -110,5 +119,14 @@ if "bloom_kernel" in traffic and "exact_kernel" in traffic:
     traffic["probe"] = dict(traffic["bloom_kernel"], dram_bytes=traffic["bloom_kernel"]["dram_bytes"] + traffic["exact_kernel"]["dram_bytes"])
 if traffic and launch_info[1]:
     import json
-    json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+    # one entry per workload: profiles/traffic.json = {workload: {kernel: {...}}}
+    path = os.path.join(PROF, "traffic.json")
+    try:
+        allw = json.load(open(path))
+        if "probe" in allw:  # round-1 layout (a single workload at the top level)
+            allw = {allw["probe"].get("workload", "cfg2"): allw}
+    except (OSError, ValueError):
+        allw = {}
+    allw[launch_info[0]] = traffic
+    json.dump(allw, open(path, "w"), indent=1)
 print("wrote", os.path.join(PROF, f"{tag}_ncu_summary.md"))
