@@ -53,10 +53,72 @@ def ncu_traffic(kernel, workload, n):
         d = json.load(open(p))
     except (OSError, ValueError):
         return None, None
-    e = d.get(kernel)
-    if not e or e.get("workload") != workload or int(e.get("queries", -1)) != int(n):
+    if "probe" in d and "workload" in d.get("probe", {}):  # round-1 layout: one workload at the top level
+        d = {d["probe"]["workload"]: d}
+    e = d.get(workload, {}).get(kernel)
+    if not e or int(e.get("queries", -1)) != int(n):
         return None, None
     return float(e["dram_bytes"]), e.get("source")
+
+
+def ncu_entry(kernel, workload):
+    """The whole profiles/traffic.json entry of one kernel on one workload (issue utilisation, lanes per instruction,
+    L2 sectors...), or {}."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        return {}
+    if "probe" in d and "workload" in d.get("probe", {}):
+        d = {d["probe"]["workload"]: d}
+    return d.get(workload, {}).get(kernel, {})
+
+
+def random_read_peak(footprint_bytes, width):
+    """Measured random-read rate of this GPU (G reads/s) for independent `width`-byte loads spread over a footprint of
+    that many bytes: tools/micro/randread.cu, table committed as profiles/r02d_randread.txt (log-interpolated)."""
+    rows = []
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", "r02d_randread.txt")):
+            f = ln.split()
+            if len(f) == 5 and f[0].isdigit():
+                rows.append((float(f[0]) * 2 ** 20, {8: float(f[1]), 16: float(f[2]), 32: float(f[3])}[width]))
+    except OSError:
+        return None
+    if not rows:
+        return None
+    if footprint_bytes <= rows[0][0]:
+        return rows[0][1]
+    for (b0, r0), (b1, r1) in zip(rows, rows[1:]):
+        if footprint_bytes <= b1:
+            t = (np.log(footprint_bytes) - np.log(b0)) / (np.log(b1) - np.log(b0))
+            return float(np.exp(np.log(r0) + t * (np.log(r1) - np.log(r0))))
+    return rows[-1][1]
+
+
+def survey_probe_keys(spec, queries, k, sample=400):
+    """SURVEY.md 8(d)'s P: distinct neighbourhood keys per query under canonical generation WITHOUT the
+    symmetric-delete level, P(q,k) = sum over distinct non-empty sub-multisets D (d <= k deletions) of
+    sum_{j <= k-d} C(a_D + j - 1, j), a_D = alphabet_size - (distinct classes deleted).  Mean over a sample."""
+    from math import comb
+    from itertools import combinations
+    from oracle import orc
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    asize = 32
+    tot = 0
+    qs = queries[:sample]
+    for q in qs:
+        f = sorted(o.normalize(q))
+        n = len(f)
+        seen = set()
+        for d in range(0, min(k, n - 1) + 1):
+            for pos in combinations(range(n), d):
+                rest = tuple(f[i] for i in range(n) if i not in pos)
+                if not rest or (d, rest) in seen:
+                    continue
+                seen.add((d, rest))
+                a = asize - len({f[i] for i in pos})
+                tot += sum(comb(a + j - 1, j) for j in range(0, k - d + 1))
+    return tot / max(1, len(qs))
 
 
 def workload_spec(name, rank=0):
@@ -70,6 +132,11 @@ def workload_spec(name, rank=0):
         return dict(label="cfg1: eng.aspell.lexicon, 10k synthetic misspellings, k=2",
                     lexicon=workloads.lexicon_path("eng"), queries=lambda n: workloads.cfg1_queries(n, 1001 + rank),
                     n=10_000, params=dict(max_anagram_distance=2, max_edit_distance=2), confusables=[])
+    if name == "eng3":
+        # the north-star target sentence: English aspell, query mode, max edit distance 3
+        return dict(label="eng3: eng.aspell.lexicon, 1M synthetic misspellings (cfg1 generator), k=3",
+                    lexicon=workloads.lexicon_path("eng"), queries=lambda n: workloads.cfg1_queries(n, 1003 + rank),
+                    n=1_000_000, params=dict(max_anagram_distance=3, max_edit_distance=3), confusables=[])
     if name == "cfg4":
         return dict(label="cfg4: eng.aspell.lexicon, 1M misspellings (len>=8, 2-4 edits), k=4",
                     lexicon=workloads.lexicon_path("eng"), queries=lambda n: workloads.cfg4_queries(n, 4001 + rank),
@@ -340,10 +407,62 @@ def run_ours(args):
         # the probe kernel is the memory-system-bound one and is reported against the measured HBM
         # peak; the score kernel is integer-issue bound and is reported as DP GCUPS (`dp` object below).
         achieved = probe_bytes / (probe_ms / 1000.0) / 1e9
-        traffic, traffic_src = ncu_traffic("probe", args.workload, n)
-        time_dominant = max((("bloom_kernel", bloom_ms), ("exact_kernel", exact_ms), ("prefilter_kernel", prefilter_ms),
-                             ("score_kernel", rank_ms), ("confusable_kernel", conf_ms), ("finish_kernel", finish_ms)),
-                            key=lambda kv: kv[1])[0]
+        wl_key = args.workload
+        traffic, traffic_src = ncu_traffic("probe", wl_key, n)
+        stage_list = (("bloom_kernel", bloom_ms), ("exact_kernel", exact_ms), ("pair_list_kernels", prefilter_ms),
+                      ("dp_kernel+rank_kernel", rank_ms), ("confusable_kernels", conf_ms), ("finish_kernel", finish_ms))
+        time_dominant = max(stage_list, key=lambda kv: kv[1])[0]
+        index_bytes = ist["table_bytes"] + ist["bloom_bytes"] + 5 * ist["postings"] + 32 * ist["anagrams"] + ist["instance_bytes"]
+        hbm_resident = index_bytes > 100e6  # beyond the 126 MB L2 (two 63 MB halves)
+        # one line per kernel (group), each against the limit that binds IT:
+        #  * Bloom stage: one independent 8-byte read per neighbourhood node over the Bloom filter's footprint -> measured
+        #    random-read rate of this GPU at that footprint (tools/micro/randread.cu); also instruction-issue bound (ncu)
+        #  * exact stage: one 16-byte slot read per probe step over the table's footprint -> random-read rate, same source
+        #  * DP: u8 cells, integer-issue bound -> GCUPS against SURVEY 8(d)'s nominal 148 SM x 128 lanes x f / 12 ops per cell
+        sm_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+        dp_peak = 148 * 128 * sm_ghz / 12.0  # GCUPS
+        kr = []
+        rr8 = random_read_peak(ist["bloom_bytes"], 8)
+        if rr8 and bloom_ms > 0:
+            e = ncu_entry("bloom_kernel", wl_key)
+            kr.append({"kernel": "bloom_kernel", "ms": bloom_ms, "bound": "random 8-byte reads (Bloom words) / instruction issue",
+                       "achieved": ctr.probes / (bloom_ms / 1e3) / 1e9, "peak": rr8, "unit": "G reads/s",
+                       "frac": ctr.probes / (bloom_ms / 1e3) / 1e9 / rr8, "footprint_bytes": ist["bloom_bytes"],
+                       "peak_source": "profiles/r02d_randread.txt (measured on this pool's B200, independent loads)",
+                       "issue_active_pct": e.get("issue_active_pct"), "lanes_per_instruction": e.get("lanes_per_instruction")})
+        rr16 = random_read_peak(ist["table_bytes"], 16)
+        if rr16 and exact_ms > 0:
+            e = ncu_entry("exact_kernel", wl_key)
+            kr.append({"kernel": "exact_kernel", "ms": exact_ms, "bound": "random 16-byte reads (table slots, then postings / anagram records)",
+                       "achieved": ctr.probe_steps / (exact_ms / 1e3) / 1e9, "peak": rr16, "unit": "G reads/s",
+                       "frac": ctr.probe_steps / (exact_ms / 1e3) / 1e9 / rr16, "footprint_bytes": ist["table_bytes"],
+                       "peak_source": "profiles/r02d_randread.txt",
+                       "issue_active_pct": e.get("issue_active_pct"), "lanes_per_instruction": e.get("lanes_per_instruction")})
+        if score_ms > 0:
+            e = ncu_entry("dp_kernel", wl_key)
+            gc = total_cells * 1e-9 / (score_ms_max / 1000.0)
+            kr.append({"kernel": "pair_list_kernels + dp_kernel + rank_kernel (score stage)", "ms": score_ms, "bound": "integer issue (u8 DP cells)",
+                       "achieved": gc, "peak": dp_peak, "unit": "GCUPS", "frac": gc / dp_peak,
+                       "peak_source": "nominal: 148 SMs x 128 lanes x %.3f GHz / 12 integer operations per cell (SURVEY 8d)" % sm_ghz,
+                       "cells": "reference cells (len_q x len_c of every pair that passes the length check); the DP itself runs "
+                                "only on the pairs the bit-parallel prefilter cannot reject (counters.dp_cells)",
+                       "issue_active_pct": e.get("issue_active_pct"), "lanes_per_instruction": e.get("lanes_per_instruction")})
+        dominant_frac = None
+        for r_ in kr:
+            if r_["kernel"].startswith(time_dominant.split("+")[0].split("_kernels")[0]):
+                dominant_frac = r_["frac"]
+        try:
+            survey_p = survey_probe_keys(spec, queries, int(spec["params"]["max_anagram_distance"]))
+        except Exception:
+            survey_p = None
+        if hbm_resident:
+            note = ("algorithmic bytes = exact per-launch counters (B_probe, the design's own byte model: DESIGN.md section 5); the "
+                    "index of this lexicon (%.1f GB) is HBM-resident: the probes are random 8/16/32-byte reads, so the binding limit is "
+                    "the GPU's random-read rate at that footprint (kernel_rooflines), not streaming bandwidth" % (index_bytes / 1e9))
+        else:
+            note = ("algorithmic bytes = exact per-launch counters (B_probe, the design's own byte model: DESIGN.md section 5); the "
+                    "index of this lexicon (%.0f MB: Bloom words, table, postings) is L2-resident, so DRAM traffic is far below the "
+                    "algorithmic bytes and the binding limit is instruction issue / L2 random-read rate, not HBM" % (index_bytes / 1e6))
         cpu = None
         if world == 1:
             # bounded CPU baseline on rank 0's host cores (N=1 only): the oracle port, all threads
@@ -360,8 +479,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 multi-limb integer / u8 DP / f64 score", "data": "synthetic",
             "config": {"workload": spec["label"], "batch_queries_per_gpu": n, "parallelism": f"query-partitioned replicas x{world}",
-                       "l2": "per-step working set (query rows + hit lists + results ~ GBs) exceeds the 126 MB L2; "
-                             "the index is L2-resident by design", "index": ist, "build_seconds": build_s,
+                       "l2": "per-step working set (query rows + hit lists + staged nodes + results ~ GBs) exceeds the 126 MB L2; "
+                             + ("the index is HBM-resident" if hbm_resident else "the index is L2-resident by design"),
+                       "index": ist, "index_bytes": index_bytes, "build_seconds": build_s,
                        "value_scope": "probe + score/rank (+ confusable + finish) kernels, encoded batch resident in HBM, "
                                       "results left in HBM"},
             "dp_gcups": total_cells * 1e-9 / (score_ms_max / 1000.0),
@@ -370,6 +490,8 @@ def run_ours(args):
                         "stages_ms": {"bloom_kernel": bloom_ms, "exact_kernel": exact_ms, "prefilter_kernel": prefilter_ms,
                                       "score_kernel": rank_ms, "confusable_kernel": conf_ms, "finish_kernel": finish_ms,
                                       "export_kernels": export_ms},
+                        "stage_kernels": {"prefilter_kernel": "pairfilter_kernel + pairscan_kernel + pairscatter_kernel (shape-sorted pair list)",
+                                          "score_kernel": "dp_kernel + rank_kernel", "confusable_kernel": "triage_kernel + confusable_kernel + confusable_wide_kernel"},
                         "probe_share": probe_ms / (probe_ms + score_ms + rescore_ms + export_ms),
                         "probe_algorithmic_bytes": probe_bytes, "score_algorithmic_bytes": score_bytes,
                         "probe_gbs": probe_bytes / (probe_ms / 1e3) / 1e9, "score_gbs": score_bytes / (score_ms / 1e3) / 1e9,
@@ -377,11 +499,17 @@ def run_ours(args):
             "counters": {f: getattr(ctr, f) for f, _ in ctr._fields_},
             "roofline": {"bound": "hbm", "kernel": "bloom_kernel + exact_kernel (candidate generation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "time_dominant_kernel": time_dominant,
-                         "note": "algorithmic bytes = exact per-launch counters (DESIGN.md section 5); the index (Bloom words, "
-                                 "table, postings) of this lexicon is L2-resident, so DRAM traffic is far below the algorithmic "
-                                 "bytes and the binding limit is load latency / instruction issue, not HBM"},
-            "dp": {"kernel": "score_kernel", "gcups": total_cells * 1e-9 / (score_ms_max / 1000.0), "unit": "GCUPS",
+                         "time_dominant_kernel": time_dominant, "time_dominant_frac": dominant_frac,
+                         "byte_model": {"B_probe_per_query": probe_bytes / n, "nodes_per_query": ctr.probes / n,
+                                        "survey_8d_P_per_query": survey_p,
+                                        "survey_8d_bytes_per_query": (survey_p * 32 + (ctr.anagram_hits * 8 + 4 * ctr.instance_pairs) / n)
+                                        if survey_p else None,
+                                        "why": "symmetric-delete depth 1 removes the last insertion level, so the kernels test "
+                                               "`nodes_per_query` keys where SURVEY 8(d)'s canonical generation would test P"},
+                         "note": note},
+            "kernel_rooflines": kr,
+            "dp": {"kernel": "pair list + dp_kernel + rank_kernel", "gcups": total_cells * 1e-9 / (score_ms_max / 1000.0), "unit": "GCUPS",
+                   "peak": dp_peak, "frac": total_cells * 1e-9 / (score_ms_max / 1000.0) / dp_peak,
                    "cells_per_launch": ctr.dl_cells, "ms": score_ms,
                    "bound": "integer issue (u8 DP cells in shared memory, no tensor cores); see profiles/ for issue utilisation"},
             "cpu_baseline": cpu,
