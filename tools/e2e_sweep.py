@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """e2e throughput of anl_find_variants_batch (cfg2) for a few chunk sizes / pipeline depths; one process per setting
-(the knobs are read once per process).  Usage: python tools/e2e_sweep.py [chunk:inflight ...]"""
+(the knobs are read once per process).  Usage: python tools/e2e_sweep.py [chunk:inflight[:host_threads] ...]"""
 import ctypes as C
 import os
 import subprocess
@@ -46,6 +46,8 @@ if __name__ == "__main__":
         child()
     else:
         for spec in (sys.argv[1:] or ["65536:4", "131072:4", "262144:4", "65536:8", "131072:2"]):
-            chunk, inflight = spec.split(":")
+            chunk, inflight, *threads = spec.split(":")
             env = dict(os.environ, ANL_SWEEP_CHILD="1", ANL_CHUNK=chunk, ANL_INFLIGHT=inflight)
+            if threads:
+                env["ANL_HOST_THREADS"] = threads[0]
             subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)

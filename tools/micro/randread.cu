@@ -30,8 +30,14 @@ __global__ void latency(const uint64_t* __restrict__ buf, uint64_t words_mask, i
   for (int i = 0; i < iters; ++i) s = mix(s + __ldg(buf + (s & words_mask)));
   if (s == 0x1234567) *sink = s;
 }
-int main() {
+int main(int argc, char** argv) {
   cudaSetDevice(0);
+  if (argc > 1) {  // L2 fetch granularity hint in bytes (32, 64 or 128; the default is the driver's)
+    const cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1]));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("cudaLimitMaxL2FetchGranularity requested %s -> %s, now %zu\n", argv[1], cudaGetErrorString(e), got);
+  }
   const size_t maxbytes = (size_t)16 << 30;
   uint64_t* buf; uint64_t* sink;
   if (cudaMalloc(&buf, maxbytes) != cudaSuccess) { printf("alloc failed\n"); return 1; }

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 Q=${Q:-1000000}
 W=${W:-cfg2}
 echo "$W $Q" > gpurun_out/profile_launch.txt
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(encode|probe|bloom|exact|pairfilter|pairscan|pairscatter|dp|dp_tma|rank|triage|confusable|confusable_wide|finish|count|export|offsets|patch|merge)_kernel' -c 120 --csv --log-file gpurun_out/launches.csv \
     python bench.py --workload $W --queries $Q --steps 2 --warmup 3 --e2e-steps 0 --cpu-sample 64 > gpurun_out/launches_bench.json 2> gpurun_out/launches.err
 KERNELS=${KERNELS:-"bloom exact pairfilter dp rank confusable"}
 for K in $KERNELS; do
