@@ -1142,6 +1142,9 @@ struct Params {  // the subset of src/types.rs:110-168 that the path reads
   float freq_weight;
   int32_t max_ngram;
   int32_t unicodeoffsets;
+  // most_likely_sequence (src/types.rs:139-156): number of shortest paths kept, weights of the three score terms
+  int32_t max_seq;
+  float lm_weight, variantmodel_weight, contextrules_weight;
 };
 static const uint64_t NO_VIA = ~0ull;
 struct Result {  // src/types.rs:326-332
@@ -1151,6 +1154,59 @@ struct Result {  // src/types.rs:326-332
 };
 struct Stats {
   uint64_t queries, modulo_tests, deletions, anagram_hits, dl_pairs, dl_cells, survivors;
+};
+
+// src/search.rs:338-365: one position of a context rule
+struct PatternMatch {
+  enum Kind { VOCAB, ANY, NOLEXICON, FROMLEXICON, NOT, DISJUNCTION } kind = ANY;
+  uint64_t vocab_id = 0;
+  unsigned lexicon = 0;
+  std::vector<PatternMatch> sub;  // NOT: one element; DISJUNCTION: the alternatives
+  // src/search.rs:374-419
+  bool matches(const std::vector<std::pair<uint64_t, uint32_t>>& seq, size_t index) const {
+    switch (kind) {
+      case ANY: return true;
+      case NOLEXICON: return index < seq.size() && (seq[index].second == 0 || seq[index].first == 0);
+      case VOCAB: return index < seq.size() && seq[index].first == vocab_id;
+      case FROMLEXICON: return index < seq.size() && (seq[index].second & (1u << lexicon)) == (1u << lexicon);
+      case NOT: return !sub[0].matches(seq, index);
+      case DISJUNCTION:
+        for (const PatternMatch& pm : sub)
+          if (pm.matches(seq, index)) return true;
+        return false;
+    }
+    return false;
+  }
+};
+struct PatternMatchResult {  // src/search.rs:367-372
+  float score;
+  int tag;  // -1 = None
+  uint8_t seqnr;
+};
+struct ContextRule {  // src/search.rs:354-365
+  std::vector<PatternMatch> pattern;
+  float score;
+  std::vector<uint16_t> tag;
+  std::vector<std::pair<uint8_t, uint8_t>> tagoffset;  // begin, length
+  // src/search.rs:474-523
+  bool matches(const std::vector<std::pair<uint64_t, uint32_t>>& seq, size_t begin,
+               std::vector<std::vector<PatternMatchResult>>& results) const {
+    if (begin + pattern.size() > seq.size()) return false;
+    for (size_t cursor = 0; cursor < pattern.size(); ++cursor)
+      if (!results[begin + cursor].empty() || !pattern[cursor].matches(seq, begin + cursor)) return false;
+    for (size_t cursor = 0; cursor < pattern.size(); ++cursor) {
+      std::vector<PatternMatchResult> r;
+      if (tag.empty()) {
+        r.push_back(PatternMatchResult{score, -1, (uint8_t)cursor});
+      } else {
+        for (size_t k = 0; k < tag.size() && k < tagoffset.size(); ++k)  // zip
+          if ((uint8_t)cursor >= tagoffset[k].first && (unsigned)(uint8_t)cursor < (unsigned)tagoffset[k].first + tagoffset[k].second)
+            r.push_back(PatternMatchResult{score, (int)tag[k], (uint8_t)((uint8_t)cursor - tagoffset[k].first)});
+      }
+      results[begin + cursor] = r;  // (may be empty: the position then still counts as uncovered)
+    }
+    return true;
+  }
 };
 
 struct Model {
@@ -1166,6 +1222,11 @@ struct Model {
   std::vector<std::string> lexicons;
   std::vector<Confusable> confusables;
   bool confusables_before_pruning = false;
+  // language model (src/lib.rs:75-79): n-gram (1..5 vocabulary ids) -> count
+  std::map<std::vector<uint64_t>, uint32_t> ngrams;
+  bool have_lm = false;
+  std::vector<ContextRule> context_rules;  // src/lib.rs:82
+  std::vector<std::string> tags;           // src/lib.rs:85
 
   unsigned alphabet_size() const { return (unsigned)((alphabet.size() + 1) & 0xFF); }  // src/lib.rs:163
 
@@ -1406,6 +1467,187 @@ struct Model {
     if (all_compact)
       for (auto& kv : sortedindex)
         for (const Big& b : kv.second) sortedcompact[kv.first].push_back(to_compact(b));
+    // "Constructing Language Model", src/lib.rs:246-295.  (into_ngram always encodes with use_unk = true, so the
+    // reference's `unseen_parts` stays empty: parts outside the vocabulary count as <unk>.)
+    ngrams.clear();
+    for (size_t id = 0; id < decoder.size(); ++id) {
+      if (!(decoder[id].vocabtype & VT_LM)) continue;
+      std::vector<uint64_t> ngram;
+      if (into_ngram(id, &ngram)) ngrams[ngram] += decoder[id].frequency;  // add_ngram, :2677-2685
+    }
+    have_lm = !ngrams.empty();
+  }
+
+  // src/lib.rs:2688-2751: the entry's text split on single spaces, each part looked up in the vocabulary (else UNK = 2);
+  // false for more than five parts
+  bool into_ngram(uint64_t id, std::vector<uint64_t>* out) const {
+    const VocabValue& v = decoder[id];
+    out->clear();
+    if (v.tokencount > 5) return false;
+    size_t pos = 0;
+    for (unsigned k = 0; k < v.tokencount; ++k) {
+      const size_t sp = v.text.find(' ', pos);
+      const std::string part = v.text.substr(pos, sp == std::string::npos ? std::string::npos : sp - pos);
+      auto it = encoder.find(part);
+      out->push_back(it != encoder.end() ? it->second : 2);
+      pos = sp == std::string::npos ? v.text.size() : sp + 1;
+    }
+    return true;
+  }
+
+  // src/search.rs:421-470 PatternMatch::parse
+  bool parse_pattern(const std::string& raw, PatternMatch* out, std::string* err) const {
+    const std::string t = trim(raw);
+    if (t == "?") {
+      out->kind = PatternMatch::ANY;
+    } else if (t == "^") {
+      out->kind = PatternMatch::NOLEXICON;
+    } else if (t.size() >= 3 && t.compare(0, 2, "!(") == 0 && t.back() == ')') {
+      out->kind = PatternMatch::NOT;
+      out->sub.resize(1);
+      return parse_pattern(t.substr(2, t.size() - 3), &out->sub[0], err);
+    } else if (t.find('|') != std::string::npos) {
+      out->kind = PatternMatch::DISJUNCTION;
+      size_t pos = 0;
+      for (;;) {
+        const size_t bar = t.find('|', pos);
+        PatternMatch pm;
+        if (!parse_pattern(t.substr(pos, bar == std::string::npos ? std::string::npos : bar - pos), &pm, err)) return false;
+        out->sub.push_back(pm);
+        if (bar == std::string::npos) break;
+        pos = bar + 1;
+      }
+    } else if (!t.empty() && t[0] == '!') {
+      out->kind = PatternMatch::NOT;
+      out->sub.resize(1);
+      return parse_pattern(t.substr(1), &out->sub[0], err);
+    } else if (!t.empty() && t[0] == '@') {
+      const std::string source = t.substr(1), rel = "/" + source;
+      for (size_t i = 0; i < lexicons.size(); ++i) {
+        const std::string& lx = lexicons[i];
+        if (source == lx || (lx.size() >= rel.size() && lx.compare(lx.size() - rel.size(), rel.size(), rel) == 0)) {
+          out->kind = PatternMatch::FROMLEXICON;
+          out->lexicon = (unsigned)(i & 0xFF);
+          return true;
+        }
+      }
+      *err = "Context rule references lexicon or variant list '" + source + "' but this source was not loaded";
+      return false;
+    } else {
+      auto it = encoder.find(t);
+      if (it == encoder.end()) {
+        *err = "Context rule references word '" + t + "' but this word does not occur in any lexicon";
+        return false;
+      }
+      out->kind = PatternMatch::VOCAB;
+      out->vocab_id = it->second;
+    }
+    return true;
+  }
+  static bool parse_u8(const std::string& f, uint8_t* out) {  // str::parse::<u8>()
+    uint32_t v = 0;
+    if (!parse_u32_strict(f, &v) || v > 255) return false;
+    *out = (uint8_t)v;
+    return true;
+  }
+  // src/lib.rs:658-765.  0 = ok, < 0 = the reference returns an Err.
+  int add_contextrule(const std::string& pattern_s, float score, const std::vector<std::string>& tag_s,
+                      const std::vector<std::string>& tagoffset_s, std::string* err) {
+    std::vector<PatternMatch> pattern;
+    size_t pos = 0;
+    for (;;) {
+      const size_t semi = pattern_s.find(';', pos);
+      PatternMatch pm;
+      if (!parse_pattern(pattern_s.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos), &pm, err)) return -1;
+      pattern.push_back(pm);
+      if (semi == std::string::npos) break;
+      pos = semi + 1;
+    }
+    bool empty_tag = false;
+    std::vector<uint16_t> tag;
+    for (const std::string& t : tag_s) {
+      if (t.empty()) empty_tag = true;
+      auto it = std::find(tags.begin(), tags.end(), t);
+      if (it == tags.end()) {
+        tags.push_back(t);
+        tag.push_back((uint16_t)(tags.size() - 1));
+      } else {
+        tag.push_back((uint16_t)(it - tags.begin()));
+      }
+    }
+    if (empty_tag) {
+      *err = "tag is empty";
+      return -2;
+    }
+    std::vector<std::pair<uint8_t, uint8_t>> tagoffset;
+    const char* bad = nullptr;
+    for (const std::string& t : tagoffset_s) {
+      const size_t colon = t.find(':');
+      const std::string f0 = t.substr(0, colon);
+      uint8_t b = 0, l = 0;
+      if (!f0.empty() && !parse_u8(f0, &b)) bad = "tag offset should be an integer";
+      if (colon == std::string::npos) {
+        l = (uint8_t)((uint8_t)pattern.size() - b);
+      } else {
+        const size_t colon2 = t.find(':', colon + 1);
+        const std::string f1 = t.substr(colon + 1, colon2 == std::string::npos ? std::string::npos : colon2 - colon - 1);
+        if (f1.empty())
+          l = (uint8_t)((uint8_t)pattern.size() - b);
+        else if (!parse_u8(f1, &l))
+          bad = "tag length should be an integer";
+      }
+      tagoffset.push_back({b, l});
+    }
+    if (bad) {
+      *err = bad;
+      return -3;
+    }
+    while (tagoffset.size() < tag.size()) tagoffset.push_back({0, (uint8_t)pattern.size()});
+    if (!pattern.empty()) context_rules.push_back(ContextRule{pattern, score, tag, tagoffset});
+    return 0;
+  }
+  // src/lib.rs:570-656: TSV pattern, score[, tags ';'-separated[, tag offsets ';'-separated]]
+  int read_contextrules(const std::string& filename, std::string* err) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) return -1;
+    std::string line;
+    auto split_trim = [](const std::string& s) {
+      std::vector<std::string> out;
+      size_t pos = 0;
+      for (;;) {
+        const size_t semi = s.find(';', pos);
+        const std::string w = trim(s.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos));
+        if (!w.empty()) out.push_back(w);
+        if (semi == std::string::npos) break;
+        pos = semi + 1;
+      }
+      return out;
+    };
+    while (std::getline(f, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty() || line[0] == '#') continue;
+      std::vector<std::string> fields;
+      size_t fp = 0;
+      for (;;) {
+        size_t tab = line.find('\t', fp);
+        fields.push_back(line.substr(fp, tab == std::string::npos ? std::string::npos : tab - fp));
+        if (tab == std::string::npos) break;
+        fp = tab + 1;
+      }
+      if (fields.size() < 2) return -2;
+      if (fields[0].empty()) continue;
+      char* end = nullptr;
+      const float score = strtof(fields[1].c_str(), &end);
+      if (fields[1].empty() || *end != '\0') return -3;
+      std::vector<std::string> tag = fields.size() > 2 ? split_trim(fields[2]) : std::vector<std::string>();
+      std::vector<std::string> tagoffset = fields.size() > 3 ? split_trim(fields[3]) : std::vector<std::string>();
+      if (tag.size() == 1 && tagoffset.empty())
+        tagoffset.push_back("0:");
+      else if (tag.size() != tagoffset.size())
+        return -4;
+      if (add_contextrule(fields[0], score, tag, tagoffset, err) != 0) return -5;
+    }
+    return 0;
   }
 
   bool has(const std::string& text) const {  // src/lib.rs:331-338
@@ -1726,6 +1968,8 @@ struct Segment {
   bool looked_up;
   std::vector<Result> variants;
   int selected = -1;  // Match.selected (src/search.rs:55): index into variants, -1 = None
+  std::vector<uint16_t> tag;   // Match.tag / Match.seqnr (src/search.rs:57-60), set by context rules
+  std::vector<uint8_t> seqnr;
 };
 // src/search.rs:262-312 ; `bounds` is the slice of boundaries of the current batch
 static std::vector<Segment> find_match_ngrams(const std::string& text, const Span* bounds, size_t nbounds, unsigned order,
@@ -1771,29 +2015,225 @@ static bool redundant_match(const Segment& cand, const std::vector<Segment>& mat
   }
   return true;
 }
-// ---- src/lib.rs:2088-2495 most_likely_sequence, for a model without language model and context rules -----------
+// ---- src/lib.rs:2088-2495 most_likely_sequence ----------------------------------------------------------------
 // The reference builds a weighted FST (rustfst 1.1.2, tropical semiring over f32; third-party, not under
 // /root/reference): a start state plus one state per boundary of the batch, one transition per (match, variant)
 // with cost `n + (1 - score)` (n = tokens covered), an out-of-vocabulary transition of cost `n + 1` for a unigram
-// without variants, and an epsilon fail-safe of cost 100 between consecutive states.  It then asks rustfst for
-// the `max_seq` shortest paths and, with no LM and no context rules, keeps the one of lowest total cost
-// (`norm_variant_score = ln(best_cost / cost)` is maximal there, :2383-2400).  The lattice is a DAG whose states
-// are ordered by boundary index, so the lowest-cost path is restated here as one forward relaxation pass with
-// f32 accumulation along the path (tropical `times` = f32 addition).
-// PARITY UNPINNED for ties: which of several equal-cost paths rustfst enumerates first is not fixed by any
-// reference test; the rule here is "earliest source state, then earliest transition (match order, then variant
-// order)".  Single-boundary batches: the reference's initial `best_variant_cost` of 0 makes every score -inf and
-// it keeps the first enumerated path; restated as the lowest cost as well.
+// without variants, and an epsilon fail-safe of cost 100 between consecutive states.  It asks rustfst for the
+// `max_seq` shortest paths, scores every one of them with the language model (lm_score, :2570-2674) and the context
+// rules (test_context_rules, :2501-2566), normalises the three terms against the best value seen, and keeps the
+// sequence with the highest weighted sum (:2383-2425; the first one wins a tie).
+//
+// rustfst's n-shortest-paths is restated from its published behaviour: the `max_seq` paths of lowest total weight,
+// each path's weight accumulated in f32 from the start state (tropical `times` = f32 addition).
+// PARITY UNPINNED for ties: (a) which of several equal-cost paths make the cut at `max_seq`, (b) the order in which
+// rustfst's paths_iter yields the paths -- it decides between sequences of equal final score -- are not fixed by any
+// reference test.  The rule here: paths are ordered by (cost, final state, then from the last arc backwards: source
+// state, arc in insertion order (match order, then variant order; fail-safe arcs last), then the prefixes by the same
+// rule); the first `max_seq` are scored in that order.  Single-boundary batches: the reference's initial
+// `best_variant_cost` of 0 makes every score -inf (or NaN) and it keeps the first path it enumerates; with the order
+// above that is the cheapest path.
 struct Transition {
-  int to;
+  int from, to;
   float cost;
-  long match_index;  // -1 = epsilon
-  int variant_index; // -1 = out of vocabulary (copied from the input)
+  long match_index;   // -1 = epsilon
+  int variant_index;  // -1 = out of vocabulary (copied from the input)
+  int boundary_index; // next boundary (batch-local), OutputSymbol.boundary_index
 };
-static std::vector<Segment> most_likely_sequence(const std::vector<Segment>& matches, const Span* bounds, size_t nbounds,
-                                                 size_t end_offset, float freq_weight) {
+struct FstPath {
+  std::vector<int> arcs;        // indices into the transition list, start -> final
+  std::vector<float> prefix;    // cost after each arc (f32, accumulated from the start)
+  int end_state = 0;
+  float cost() const { return prefix.empty() ? 0.0f : prefix.back(); }
+};
+// the order described above; < 0: a first
+static int path_cmp(const std::vector<Transition>& tr, const FstPath& a, const FstPath& b) {
+  if (a.cost() != b.cost()) return a.cost() < b.cost() ? -1 : 1;
+  if (a.end_state != b.end_state) return a.end_state < b.end_state ? -1 : 1;
+  size_t i = a.arcs.size(), j = b.arcs.size();
+  while (i > 0 && j > 0) {
+    --i;
+    --j;
+    if (a.prefix[i] != b.prefix[j]) return a.prefix[i] < b.prefix[j] ? -1 : 1;
+    const Transition &x = tr[a.arcs[i]], &y = tr[b.arcs[j]];
+    if (x.from != y.from) return x.from < y.from ? -1 : 1;
+    if (a.arcs[i] != b.arcs[j]) return a.arcs[i] < b.arcs[j] ? -1 : 1;
+  }
+  return (i > 0) - (j > 0);
+}
+static uint64_t g_bruteforce_limit = 200000;  // lattices with more paths than this use the per-state lists below
+// every path start -> final state, by exhaustive enumeration; false when there are more than `limit`
+static bool all_paths(const std::vector<Transition>& tr, const std::vector<std::vector<int>>& out, const std::vector<char>& is_final,
+                      uint64_t limit, std::vector<FstPath>* paths) {
+  FstPath cur;
+  std::vector<std::pair<int, size_t>> stack;  // (state, next out-arc to try)
+  stack.push_back({0, 0});
+  if (is_final[0]) paths->push_back(cur);
+  while (!stack.empty()) {
+    auto& top = stack.back();
+    if (top.second >= out[top.first].size()) {
+      stack.pop_back();
+      if (!cur.arcs.empty()) {
+        cur.arcs.pop_back();
+        cur.prefix.pop_back();
+      }
+      continue;
+    }
+    const int a = out[top.first][top.second++];
+    cur.arcs.push_back(a);
+    cur.prefix.push_back((cur.prefix.empty() ? 0.0f : cur.prefix.back()) + tr[a].cost);
+    if (is_final[tr[a].to]) {
+      cur.end_state = tr[a].to;
+      paths->push_back(cur);
+      if (paths->size() > limit) return false;
+    }
+    stack.push_back({tr[a].to, 0});
+  }
+  return true;
+}
+// the same first `k` paths from per-state lists of the k best partial paths (states are ordered by position and every
+// transition points forward; the order above is preserved by appending an arc, so a best path only has best prefixes)
+static std::vector<FstPath> kbest_paths(const std::vector<Transition>& tr, int nstates, const std::vector<char>& is_final, size_t k) {
+  struct Entry {
+    float cost;
+    int arc, rank;  // last arc, rank of the prefix in the list of the arc's source state (-1, -1 = the empty path)
+  };
+  std::vector<std::vector<int>> in(nstates);
+  for (size_t a = 0; a < tr.size(); ++a) in[tr[a].to].push_back((int)a);
+  std::vector<std::vector<Entry>> best(nstates);
+  best[0].push_back(Entry{0.0f, -1, -1});
+  for (int t = 1; t < nstates; ++t) {
+    std::vector<Entry> cand;
+    for (int a : in[t])
+      for (size_t r = 0; r < best[tr[a].from].size(); ++r) cand.push_back(Entry{best[tr[a].from][r].cost + tr[a].cost, a, (int)r});
+    std::sort(cand.begin(), cand.end(), [&](const Entry& x, const Entry& y) {
+      if (x.cost != y.cost) return x.cost < y.cost;
+      if (tr[x.arc].from != tr[y.arc].from) return tr[x.arc].from < tr[y.arc].from;
+      if (x.arc != y.arc) return x.arc < y.arc;
+      return x.rank < y.rank;
+    });
+    if (cand.size() > k) cand.resize(k);
+    best[t] = cand;
+  }
+  struct Fin {
+    float cost;
+    int state, rank;
+  };
+  std::vector<Fin> fins;
+  for (int t = 0; t < nstates; ++t)
+    if (is_final[t])
+      for (size_t r = 0; r < best[t].size(); ++r) fins.push_back(Fin{best[t][r].cost, t, (int)r});
+  std::sort(fins.begin(), fins.end(), [](const Fin& x, const Fin& y) {
+    if (x.cost != y.cost) return x.cost < y.cost;
+    if (x.state != y.state) return x.state < y.state;
+    return x.rank < y.rank;
+  });
+  if (fins.size() > k) fins.resize(k);
+  std::vector<FstPath> paths;
+  for (const Fin& f : fins) {
+    FstPath p;
+    p.end_state = f.state;
+    int st = f.state, rank = f.rank;
+    while (st != 0) {
+      const Entry& e = best[st][rank];
+      p.arcs.push_back(e.arc);
+      p.prefix.push_back(e.cost);
+      st = tr[e.arc].from;
+      rank = e.rank;
+    }
+    std::reverse(p.arcs.begin(), p.arcs.end());
+    std::reverse(p.prefix.begin(), p.prefix.end());
+    paths.push_back(p);
+  }
+  return paths;
+}
+static bool use_lm_weighted(const Model* m, const Params& p) { return m && m->have_lm && p.lm_weight != 0.0f; }  // :2399
+struct OutputSymbol {  // src/search.rs:132-149
+  uint64_t vocab_id;   // 0 = out of vocabulary, copied from the input
+  long match_index;
+  int variant_index;   // -1 = None
+  int boundary_index;
+};
+static const float TRANSITION_SMOOTHING_LOGPROB = -13.815510557964274f;  // src/search.rs:4
+
+// src/lib.rs:2643-2674 lm_score_tokens; token < 0 = out of vocabulary
+static void lm_score_tokens(const Model& m, const std::vector<long long>& tokens, float* logprob_out, double* perplexity) {
+  float logprob = 0.0f;
+  long n = 0;
+  for (size_t i = 1; i + 1 <= tokens.size(); ++i) {
+    if (tokens[i - 1] >= 0 && tokens[i] >= 0) {
+      uint32_t priorcount = 1;
+      auto pit = m.ngrams.find(std::vector<uint64_t>{(uint64_t)tokens[i - 1]});
+      if (pit != m.ngrams.end()) priorcount = pit->second;
+      auto jit = m.ngrams.find(std::vector<uint64_t>{(uint64_t)tokens[i - 1], (uint64_t)tokens[i]});
+      if (jit != m.ngrams.end()) {
+        if (priorcount < jit->second)
+          logprob += logf((float)jit->second);
+        else
+          logprob += logf((float)jit->second / (float)priorcount);
+      } else {
+        logprob += TRANSITION_SMOOTHING_LOGPROB;
+      }
+      ++n;
+    } else {
+      ++n;
+      logprob += TRANSITION_SMOOTHING_LOGPROB;
+    }
+  }
+  *logprob_out = logprob;
+  *perplexity = -1.0 / (double)n * (double)logprob;
+}
+// src/lib.rs:2570-2640 lm_score
+static void lm_score(const Model& m, const std::string& text, const std::vector<OutputSymbol>& seq, const Span* bounds, float* logprob,
+                     double* perplexity) {
+  std::vector<long long> tokens;
+  tokens.push_back(0);  // BOS
+  std::vector<uint64_t> ngram;
+  for (const OutputSymbol& os : seq) {
+    if (os.vocab_id == 0) {
+      tokens.push_back(-1);
+    } else if (m.into_ngram(os.vocab_id, &ngram)) {
+      for (uint64_t t : ngram) tokens.push_back((long long)t);
+    }
+    const Span& nb = bounds[os.boundary_index];
+    const std::string btext = Model::trim(text.substr(nb.begin, nb.end - nb.begin));
+    if (!btext.empty()) {
+      auto it = m.encoder.find(btext);
+      if (it != m.encoder.end()) {
+        if (m.into_ngram(it->second, &ngram))
+          for (uint64_t t : ngram) tokens.push_back((long long)t);
+      } else {
+        tokens.push_back(-1);
+      }
+    }
+  }
+  tokens.push_back(1);  // EOS
+  lm_score_tokens(m, tokens, logprob, perplexity);
+}
+// src/lib.rs:2501-2566 test_context_rules
+static double test_context_rules(const Model& m, const std::vector<OutputSymbol>& seq, std::vector<std::vector<PatternMatchResult>>* results) {
+  std::vector<std::pair<uint64_t, uint32_t>> sequence;
+  for (const OutputSymbol& os : seq)
+    sequence.push_back({os.vocab_id, os.vocab_id == 0 || os.vocab_id >= m.decoder.size() ? 0u : m.decoder[os.vocab_id].lexindex});
+  results->assign(sequence.size(), {});
+  bool found = false;
+  for (size_t begin = 0; begin < sequence.size(); ++begin)
+    for (const ContextRule& rule : m.context_rules)
+      if (rule.matches(sequence, begin, *results)) found = true;
+  if (!found) return 1.0;
+  float sum = 0.0f;
+  for (const auto& x : *results) sum += x.empty() ? 1.0f : x[0].score;
+  return (double)sum / (double)sequence.size();
+}
+
+static std::vector<Segment> most_likely_sequence(const Model* model, const std::string& text, const std::vector<Segment>& matches,
+                                                 const Span* bounds, size_t nbounds, size_t end_offset, const Params& p) {
   const int nstates = (int)nbounds + 1;  // state 0 = start, state 1 + i = boundary i
-  std::vector<std::vector<Transition>> out(nstates);
+  std::vector<Transition> tr;
+  std::vector<char> is_final(nstates, 0);
+  bool final_found = false;
+  for (size_t i = 0; i < nbounds; ++i)  // :2113-2124
+    if (bounds[i].begin == end_offset || bounds[i].end == end_offset) is_final[i + 1] = 1, final_found = true;
   size_t output_symbols = 1;  // symbol 0 is epsilon
   for (size_t mi = 0; mi < matches.size(); ++mi) {
     const Segment& m = matches[mi];
@@ -1809,46 +2249,105 @@ static std::vector<Segment> most_likely_sequence(const std::vector<Segment>& mat
     const int prevstate = prevb >= 0 ? (int)prevb + 1 : 0, nextstate = (int)nextb + 1;
     if (m.looked_up && !m.variants.empty()) {
       for (size_t vi = 0; vi < m.variants.size(); ++vi) {
-        const float cost = (float)n + (1.0f - (float)Model::result_score(m.variants[vi], freq_weight));  // :2203-2204
-        out[prevstate].push_back(Transition{nextstate, cost, (long)mi, (int)vi});
+        const float cost = (float)n + (1.0f - (float)Model::result_score(m.variants[vi], p.freq_weight));  // :2203-2204
+        tr.push_back(Transition{prevstate, nextstate, cost, (long)mi, (int)vi, (int)nextb});
         ++output_symbols;
       }
     } else if (n == 1) {
-      out[prevstate].push_back(Transition{nextstate, (float)n + 1.0f, (long)mi, -1});  // OOV emission, :2223
+      tr.push_back(Transition{prevstate, nextstate, (float)n + 1.0f, (long)mi, -1, (int)nextb});  // OOV emission, :2223
       ++output_symbols;
     }
   }
-  for (size_t i = 0; i < nbounds; ++i) out[i].push_back(Transition{(int)i + 1, 100.0f, -1, -1});  // :2249-2259
-  if (output_symbols == 1) return matches;                                                        // :2261-2267
-  const float INF = std::numeric_limits<float>::infinity();
-  std::vector<float> dist(nstates, INF);
-  std::vector<std::pair<int, const Transition*>> back(nstates, {-1, nullptr});
-  dist[0] = 0.0f;
-  for (int s = 0; s < nstates; ++s) {
-    if (dist[s] == INF) continue;
-    for (const Transition& t : out[s]) {
-      const float d = dist[s] + t.cost;
-      if (d < dist[t.to]) {
-        dist[t.to] = d;
-        back[t.to] = {s, &t};
-      }
+  for (size_t i = 0; i < nbounds; ++i) tr.push_back(Transition{(int)i, (int)i + 1, 100.0f, -1, -1, (int)i});  // :2249-2259
+  if (output_symbols == 1) return matches;                                                                  // :2261-2267
+  if (!final_found) return matches;  // reference: panic!("no final state found")
+  const bool use_lm = model && model->have_lm && p.lm_weight > 0.0f;
+  const bool use_rules = model && !model->context_rules.empty();
+  // with nothing but the variant model to weigh, the best of the max_seq shortest paths is the shortest path
+  const size_t k = (use_lm || use_rules) ? (size_t)std::max(p.max_seq, 0) : 1;
+  std::vector<FstPath> paths;
+  {
+    std::vector<std::vector<int>> out(nstates);
+    for (size_t a = 0; a < tr.size(); ++a) out[tr[a].from].push_back((int)a);
+    std::vector<FstPath> all;
+    if (all_paths(tr, out, is_final, g_bruteforce_limit, &all)) {
+      std::stable_sort(all.begin(), all.end(), [&](const FstPath& a, const FstPath& b) { return path_cmp(tr, a, b) < 0; });
+      if (all.size() > k) all.resize(k);
+      paths = std::move(all);
+    } else {
+      paths = kbest_paths(tr, nstates, is_final, k);
     }
   }
-  int fin = -1;
-  for (size_t i = 0; i < nbounds; ++i)  // final states, :2119-2122
-    if (bounds[i].begin == end_offset || bounds[i].end == end_offset)
-      if (fin < 0 || dist[i + 1] < dist[fin]) fin = (int)i + 1;
-  if (fin < 0 || dist[fin] == INF) return matches;  // reference: panic!("no final state found")
-  std::vector<const Transition*> path;
-  for (int s = fin; s != 0; s = back[s].first) path.push_back(back[s].second);
-  std::vector<Segment> best;
-  for (size_t k = path.size(); k-- > 0;) {
-    if (path[k]->match_index < 0) continue;  // epsilon: no output label
-    Segment m = matches[path[k]->match_index];
-    m.selected = path[k]->variant_index;  // :2472
-    best.push_back(std::move(m));
+  if (paths.empty()) return matches;  // (max_seq = 0: rustfst returns an empty FST and the reference panics on "best sequence")
+  struct Sequence {  // src/search.rs:153-172
+    std::vector<OutputSymbol> output_symbols;
+    float variant_cost;
+    float lm_logprob = 0.0f;
+    double perplexity = 0.0, context_score = 1.0;
+    std::vector<std::vector<std::pair<uint16_t, uint8_t>>> tags;
+  };
+  std::vector<Sequence> sequences;
+  double best_lm_perplexity = 999999.0, best_context_score = 0.0;  // :2322-2324
+  float best_variant_cost = (float)(nbounds - 1) * 2.0f;
+  for (const FstPath& path : paths) {
+    Sequence sq;
+    sq.variant_cost = path.cost();
+    for (int a : path.arcs) {
+      const Transition& t = tr[a];
+      if (t.match_index < 0) continue;  // epsilon: no output label
+      const uint64_t vid = t.variant_index >= 0 ? matches[t.match_index].variants[t.variant_index].vocab_id : 0;
+      sq.output_symbols.push_back(OutputSymbol{vid, t.match_index, t.variant_index, t.boundary_index});
+    }
+    if (use_lm) {  // :2336-2344
+      lm_score(*model, text, sq.output_symbols, bounds, &sq.lm_logprob, &sq.perplexity);
+      if (sq.perplexity < best_lm_perplexity) best_lm_perplexity = sq.perplexity;
+    }
+    if (use_rules) {  // :2345-2367
+      std::vector<std::vector<PatternMatchResult>> res;
+      sq.context_score = test_context_rules(*model, sq.output_symbols, &res);
+      for (const auto& v : res) {
+        std::vector<std::pair<uint16_t, uint8_t>> tg;
+        for (const PatternMatchResult& pm : v)
+          if (pm.tag >= 0) tg.push_back({(uint16_t)pm.tag, pm.seqnr});
+        sq.tags.push_back(tg);
+      }
+    }
+    if (sq.variant_cost < best_variant_cost) best_variant_cost = sq.variant_cost;
+    if (sq.context_score > best_context_score) best_context_score = sq.context_score;
+    sequences.push_back(std::move(sq));
   }
-  return best;
+  double best_score = -99999999.0;  // :2381-2425
+  const Sequence* best = nullptr;
+  const bool shortcut = !use_lm_weighted(model, p) && (!use_rules || p.contextrules_weight == 0.0f);
+  for (const Sequence& sq : sequences) {
+    const double norm_lm = use_lm ? std::log(best_lm_perplexity / sq.perplexity) : 0.0;
+    const double norm_variant = std::log((double)best_variant_cost / (double)sq.variant_cost);
+    const double norm_context = std::log(sq.context_score / best_context_score);
+    const double score = shortcut ? norm_variant
+                                  : ((double)p.lm_weight * norm_lm + (double)p.variantmodel_weight * norm_variant +
+                                     (double)p.contextrules_weight * norm_context) /
+                                        ((double)p.lm_weight + (double)p.variantmodel_weight + (double)p.contextrules_weight);
+    if (score > best_score || !best) {
+      best_score = score;
+      best = &sq;
+    }
+  }
+  std::vector<Segment> out;
+  for (size_t i = 0; i < best->output_symbols.size(); ++i) {  // :2476-2495
+    const OutputSymbol& os = best->output_symbols[i];
+    Segment m = matches[os.match_index];
+    m.selected = os.variant_index;
+    if (!best->tags.empty() && i < best->tags.size()) {
+      m.tag.clear();
+      m.seqnr.clear();
+      for (const auto& ts : best->tags[i]) {
+        m.tag.push_back(ts.first);
+        m.seqnr.push_back(ts.second);
+      }
+    }
+    out.push_back(std::move(m));
+  }
+  return out;
 }
 
 // src/lib.rs:1790-1957.  `consolidate` = false: every segment of every order with its variant list, in the
@@ -1886,9 +2385,8 @@ static std::vector<Segment> run_search(const Model* m, const std::string& text, 
         batch.insert(batch.end(), cur.begin(), cur.end());
       }
       if (consolidate) {
-        if (p.max_ngram > 1) {
-          batch = most_likely_sequence(batch, boundaries.data() + begin_index, i + 1 - begin_index, boundaries[i].begin,
-                                       p.freq_weight);
+        if (p.max_ngram > 1 || (m && (m->have_lm || !m->context_rules.empty()))) {  // :1912
+          batch = most_likely_sequence(m, text, batch, boundaries.data() + begin_index, i + 1 - begin_index, boundaries[i].begin, p);
         } else {
           for (Segment& seg : batch) seg.selected = 0;
         }
@@ -2167,10 +2665,10 @@ int64_t orc_find_all_segments(void* h, const char* text, uint64_t len, const Par
 int64_t orc_find_all_matches(void* h, const char* text, uint64_t len, const Params* p, const uint8_t* looked,
                              const uint64_t* prov_offsets, const Result* prov_results, uint64_t* seg_begin, uint64_t* seg_end,
                              uint32_t* seg_n, int32_t* seg_selected, uint64_t* res_offsets, int64_t seg_cap, Result* results,
-                             int64_t res_cap) {
+                             int64_t res_cap, uint64_t* tag_offsets, uint16_t* tags, uint8_t* seqnrs, int64_t tag_cap) {
   Provided pv{looked, prov_offsets, prov_results};
-  auto segs = run_search((Model*)h, std::string(text, len), *p, nullptr, true, h ? nullptr : &pv);
-  int64_t r = 0;
+  auto segs = run_search((Model*)h, std::string(text, len), *p, nullptr, true, looked ? &pv : nullptr);
+  int64_t r = 0, t = 0;
   for (size_t i = 0; i < segs.size(); ++i) {
     if ((int64_t)i < seg_cap) {
       seg_begin[i] = segs[i].begin;
@@ -2178,14 +2676,62 @@ int64_t orc_find_all_matches(void* h, const char* text, uint64_t len, const Para
       seg_n[i] = segs[i].n;
       seg_selected[i] = segs[i].selected;
       res_offsets[i] = r;
+      if (tag_offsets) tag_offsets[i] = t;
     }
     for (auto& v : segs[i].variants) {
       if (r < res_cap) results[r] = v;
       ++r;
     }
+    for (size_t k = 0; k < segs[i].tag.size(); ++k) {
+      if (tags && t < tag_cap) {
+        tags[t] = segs[i].tag[k];
+        seqnrs[t] = segs[i].seqnr[k];
+      }
+      ++t;
+    }
   }
-  if ((int64_t)segs.size() < seg_cap) res_offsets[segs.size()] = r;
+  if ((int64_t)segs.size() < seg_cap) {
+    res_offsets[segs.size()] = r;
+    if (tag_offsets) tag_offsets[segs.size()] = t;
+  }
   return (int64_t)segs.size();
+}
+// language model / context rules (src/lib.rs:246-295, 570-765)
+int32_t orc_have_lm(void* h) { return ((Model*)h)->have_lm ? 1 : 0; }
+uint64_t orc_ngram_count(void* h) { return ((Model*)h)->ngrams.size(); }
+// tags / tagoffsets: '\n'-separated lists (empty string = none)
+static std::vector<std::string> split_lines(const char* s) {
+  std::vector<std::string> out;
+  if (!s || !*s) return out;
+  std::string t(s);
+  size_t pos = 0;
+  for (;;) {
+    const size_t nl = t.find('\n', pos);
+    out.push_back(t.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos));
+    if (nl == std::string::npos) break;
+    pos = nl + 1;
+  }
+  return out;
+}
+static std::string g_rule_error;
+int32_t orc_add_contextrule(void* h, const char* pattern, float score, const char* tags, const char* tagoffsets) {
+  g_rule_error.clear();
+  return ((Model*)h)->add_contextrule(pattern, score, split_lines(tags), split_lines(tagoffsets), &g_rule_error);
+}
+int32_t orc_read_contextrules(void* h, const char* filename) {
+  g_rule_error.clear();
+  return ((Model*)h)->read_contextrules(filename, &g_rule_error);
+}
+const char* orc_rule_error() { return g_rule_error.c_str(); }
+uint64_t orc_contextrule_count(void* h) { return ((Model*)h)->context_rules.size(); }
+uint64_t orc_tag_count(void* h) { return ((Model*)h)->tags.size(); }
+const char* orc_tag_name(void* h, uint64_t i) { return ((Model*)h)->tags[i].c_str(); }
+// test hook: lattices with more paths than this are ranked from per-state lists instead of exhaustive enumeration
+void orc_set_bruteforce_limit(uint64_t n) { g_bruteforce_limit = n; }
+// lm_score_tokens on explicit tokens (-1 = out of vocabulary)
+void orc_lm_score_tokens(void* h, const int64_t* tokens, uint64_t n, float* logprob, double* perplexity) {
+  std::vector<long long> t(tokens, tokens + n);
+  lm_score_tokens(*(Model*)h, t, logprob, perplexity);
 }
 // boundaries as begin,end pairs + strength
 int64_t orc_find_boundaries(const char* text, uint64_t len, uint64_t* begins, uint64_t* ends, int32_t* strengths, int64_t cap) {

@@ -34,6 +34,10 @@ class Params(C.Structure):
         ("freq_weight", C.c_float),
         ("max_ngram", C.c_int32),
         ("unicodeoffsets", C.c_int32),
+        ("max_seq", C.c_int32),
+        ("lm_weight", C.c_float),
+        ("variantmodel_weight", C.c_float),
+        ("contextrules_weight", C.c_float),
     ]
 
 
@@ -59,10 +63,11 @@ def _threshold(v):
 
 def make_params(max_anagram_distance=3, max_edit_distance=3, max_matches=20, score_threshold=0.25,
                 cutoff_threshold=2.0, stop_at_exact_match=False, freq_weight=0.0, max_ngram=3,
-                unicodeoffsets=False):
+                unicodeoffsets=False, max_seq=250, lm_weight=1.0, variantmodel_weight=3.0, contextrules_weight=1.0):
     """Defaults = SearchParameters::default() (src/types.rs:170-192)."""
     return Params(_threshold(max_anagram_distance), _threshold(max_edit_distance), max_matches, score_threshold,
-                  cutoff_threshold, int(stop_at_exact_match), freq_weight, max_ngram, int(unicodeoffsets))
+                  cutoff_threshold, int(stop_at_exact_match), freq_weight, max_ngram, int(unicodeoffsets),
+                  max_seq, lm_weight, variantmodel_weight, contextrules_weight)
 
 
 _lib = None
@@ -121,7 +126,17 @@ def lib():
         "orc_find_all_segments": (i64, [vp, cp, u64, P(Params), P(u64), P(u64), P(u32), P(C.c_uint8), P(u64), i64,
                                         P(Result), i64]),
         "orc_find_all_matches": (i64, [vp, cp, u64, P(Params), P(C.c_uint8), P(u64), P(Result), P(u64), P(u64), P(u32),
-                                       P(i32), P(u64), i64, P(Result), i64]),
+                                       P(i32), P(u64), i64, P(Result), i64, P(u64), P(C.c_uint16), P(C.c_uint8), i64]),
+        "orc_have_lm": (i32, [vp]),
+        "orc_ngram_count": (u64, [vp]),
+        "orc_add_contextrule": (i32, [vp, cp, C.c_float, cp, cp]),
+        "orc_read_contextrules": (i32, [vp, cp]),
+        "orc_rule_error": (cp, []),
+        "orc_contextrule_count": (u64, [vp]),
+        "orc_tag_count": (u64, [vp]),
+        "orc_tag_name": (cp, [vp, u64]),
+        "orc_set_bruteforce_limit": (None, [u64]),
+        "orc_lm_score_tokens": (None, [vp, P(i64), u64, P(C.c_float), P(C.c_double)]),
         "orc_find_boundaries": (i64, [cp, u64, P(u64), P(u64), P(i32), i64]),
         "orc_find_match_ngrams": (i64, [cp, u64, u32, P(u64), P(u64), i64]),
         "orc_is_alphabetic": (i32, [u32]),
@@ -201,6 +216,36 @@ class OracleModel:
         if rc != 0:
             raise RuntimeError(f"oracle read_variants({filename}) failed: {rc}")
         self.nlex += 1
+
+    def read_lm(self, filename):
+        """bindings/python/src/lib.rs:659-667: read_vocabulary with VocabType::LM."""
+        self.read_vocabulary(filename, vocab_type="LM")
+
+    def add_contextrule(self, pattern, score, tag=(), tagoffset=()):
+        rc = lib().orc_add_contextrule(self.h, pattern.encode(), score, "\n".join(tag).encode(), "\n".join(tagoffset).encode())
+        if rc != 0:
+            raise RuntimeError("Error parsing context rule: " + lib().orc_rule_error().decode())
+
+    def read_contextrules(self, filename):
+        rc = lib().orc_read_contextrules(self.h, filename.encode())
+        if rc != 0:
+            raise RuntimeError(f"oracle read_contextrules({filename}) failed: {rc} {lib().orc_rule_error().decode()}")
+
+    def have_lm(self):
+        return bool(lib().orc_have_lm(self.h))
+
+    def ngram_count(self):
+        return lib().orc_ngram_count(self.h)
+
+    def tags(self):
+        return [lib().orc_tag_name(self.h, i).decode() for i in range(lib().orc_tag_count(self.h))]
+
+    def lm_score_tokens(self, tokens):
+        """tokens: vocabulary ids, None = out of vocabulary -> (logprob f32, perplexity f64)."""
+        arr = (C.c_int64 * len(tokens))(*[-1 if t is None else t for t in tokens])
+        lp, pp = C.c_float(), C.c_double()
+        lib().orc_lm_score_tokens(self.h, arr, len(tokens), C.byref(lp), C.byref(pp))
+        return lp.value, pp.value
 
     def add_to_confusables(self, script, weight):
         if lib().orc_add_confusable(self.h, script.encode(), weight) != 0:
@@ -333,14 +378,16 @@ class OracleModel:
         return out
 
 
-    def find_all_matches(self, text, params):
-        """find_all_matches with the sequence consolidation (src/lib.rs:1790-1957, 2088-2495; no LM / context rules)."""
-        return _find_all_matches(self.h, text, params, None)
+    def find_all_matches(self, text, params, segments=None):
+        """find_all_matches with the sequence consolidation (src/lib.rs:1790-1957, 2088-2495) incl. the language model
+        and context rules of this model.  `segments` (optional): the variant lists per producer segment instead of
+        lookups (see consolidate)."""
+        return _find_all_matches(self.h, text, params, segments)
 
 
 def consolidate(text, params, segments):
     """The consolidation alone: `segments` = one dict per producer segment (find_all_segments order) with
-    "looked_up" and "variants" [(vocab_id, dist_score, freq_score)]; no model, no lookups."""
+    "looked_up" and "variants" [(vocab_id, dist_score, freq_score)]; no model (hence no LM, no context rules), no lookups."""
     return _find_all_matches(None, text, params, segments)
 
 
@@ -364,14 +411,17 @@ def _find_all_matches(h, text, params, segments):
         sn, ss = (C.c_uint32 * seg_cap)(), (C.c_int32 * seg_cap)()
         ro = (C.c_uint64 * (seg_cap + 1))()
         rs = (Result * res_cap)()
+        to = (C.c_uint64 * (seg_cap + 1))()
+        tg, sq = (C.c_uint16 * res_cap)(), (C.c_uint8 * res_cap)()
         n = lib().orc_find_all_matches(h, raw, len(raw), C.byref(params), looked, offs, prov, sb, se, sn, ss, ro, seg_cap,
-                                       rs, res_cap)
-        if n < seg_cap and ro[n] <= res_cap:
+                                       rs, res_cap, to, tg, sq, res_cap)
+        if n < seg_cap and ro[n] <= res_cap and to[n] <= res_cap:
             break
         seg_cap = max(seg_cap, n + 1)
         res_cap *= 4
     return [{"begin": sb[i], "end": se[i], "n": sn[i], "selected": ss[i], "text": raw[sb[i]:se[i]].decode("utf-8"),
-             "variants": [(rs[j].vocab_id, rs[j].dist_score, rs[j].freq_score) for j in range(ro[i], ro[i + 1])]}
+             "variants": [(rs[j].vocab_id, rs[j].dist_score, rs[j].freq_score) for j in range(ro[i], ro[i + 1])],
+             "tag": [tg[j] for j in range(to[i], to[i + 1])], "seqnr": [sq[j] for j in range(to[i], to[i + 1])]}
             for i in range(n)]
 
 

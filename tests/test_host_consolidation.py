@@ -55,7 +55,7 @@ def test_oracle_reference_0705_lm_disabled():
     language model off (src/lib.rs:2336, 2392-2396), so the sequence is decided by the variant-model cost alone --
     exactly the configuration restated here.  (LM-typed entries are not indexed and never show up as variants.)"""
     m = small_model(["I", "think", "sink", "you", "are", "right", "are right"], LM_ENTRIES)
-    r = m.find_all_matches("I tink you are rihgt", orc.make_params(**TEST_PARAMS))
+    r = m.find_all_matches("I tink you are rihgt", orc.make_params(**TEST_PARAMS, lm_weight=0.0))
     assert rendered(m, r) == [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right")]  # T:1420-1428
 
 
