@@ -132,6 +132,16 @@ SIGNATURES = {
     "anl_model_shard": (None, [_vp, _P(_u32), _P(_u32)]),
     "anl_match_set_consolidate": (_i32, [_vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
     "anl_debug_match_set_build": (_i32, [_cp, _sz, C.c_uint32, C.c_int32, _P(C.c_uint8), _P(C.c_uint64), _P(Variant), _u64, _P(_vp)]),
+    "anl_model_consolidate": (_i32, [_vp, _vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
+    "anl_match_set_tags": (_u64, [_vp, _u64, _P(_P(C.c_uint16)), _P(_P(C.c_uint8))]),
+    "anl_model_have_lm": (_i32, [_vp]),
+    "anl_model_ngram_count": (_u64, [_vp]),
+    "anl_model_read_contextrules": (_i32, [_vp, _cp]),
+    "anl_model_add_contextrule": (_i32, [_vp, _cp, C.c_float, _P(_cp), C.c_uint32, _P(_cp), C.c_uint32]),
+    "anl_model_contextrule_count": (C.c_uint32, [_vp]),
+    "anl_model_tag_count": (C.c_uint32, [_vp]),
+    "anl_model_tag_name": (_cp, [_vp, C.c_uint32]),
+    "anl_debug_lm_score_tokens": (None, [_vp, _P(C.c_int64), _u64, _P(C.c_float), _P(C.c_double)]),
     "anl_debug_find_boundaries": (_i64, [_cp, _sz, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int32), _sz]),
     "anl_debug_segment_text": (_i64, [_cp, _sz, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32), _sz]),
     "anl_debug_segment_text_device": (_i64, [C.c_int32, _cp, _sz, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint32), _sz,

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libanaliticcl_b200.so")
-SOURCES = ["kernels.cu", "export.cu", "engine.cu", "shard_comm.cu", "gpu_build.cu", "gpu_segment.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "capi.cpp"]
+SOURCES = ["kernels.cu", "export.cu", "engine.cu", "shard_comm.cu", "gpu_build.cu", "gpu_segment.cu", "host_model.cpp", "editscript.cpp", "search.cpp", "sequence.cpp", "capi.cpp"]
 HEADERS = ["shard_comm.cu", "device_types.h", "editscript_fixed.h", "kernel_common.cuh", "kernels.h", "engine.h", "host_model.h", "hostpool.h", "search.h", "unicode_tables.h",
            os.path.join("..", "..", "include", "analiticcl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

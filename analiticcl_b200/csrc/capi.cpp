@@ -43,6 +43,10 @@ struct anl_match_set {
   PodBuffer<anl_match> matches;
   PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
   std::shared_ptr<Segmentation> seg;  // the producer's segmentation (anl_find_all_matches), reused by the consolidation
+  // tags assigned by context rules (Match.tag / Match.seqnr, src/search.rs:57-60): CSR over the matches; empty = none
+  std::vector<uint64_t> tag_first;
+  std::vector<uint16_t> tag;
+  std::vector<uint8_t> seqnr;
 };
 struct anl_device_batch {
   DeviceBatch* b;
@@ -698,8 +702,8 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
 // most_likely_sequence per hard-delimited batch (src/lib.rs:1912-1924, 2088-2495): host post-pass over the
 // match set of anl_find_all_matches.  The segments are re-derived from the text (cheap next to the lookups) so
 // that the match set itself stays a flat list; batches are independent and run on all cores.
-anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
-                                     anl_match_set** out) try {
+static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in, const char* text, size_t len,
+                                   const anl_search_params* params, anl_match_set** out) {
   if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   PhaseTimer pt;
   const std::string t(text ? text : "", len);
@@ -719,18 +723,27 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
   const size_t nbatch = st.batch_first.size() - 1;
   if (descs.size() != nbatch) return fail(ANL_ERR_INVALID, "match set does not belong to this text (batch count differs)");
   const float fw = params->freq_weight;
-  const bool run_fst = params->max_ngram > 1;  // :1912 (no LM, no context rules in this build)
+  const bool scored = hm && (hm->have_lm() || !hm->context_rules.empty());
+  const bool run_fst = params->max_ngram > 1 || scored;  // :1912
+  SequenceWeights sw;
+  sw.max_seq = params->max_seq;
+  sw.lm_weight = params->lm_weight;
+  sw.variantmodel_weight = params->variantmodel_weight;
+  sw.contextrules_weight = params->contextrules_weight;
   // per batch: the chosen (segment, variant) steps; thread-local lists keep the batch order
   const unsigned nt_max = host_threads();
   std::vector<std::vector<SequenceStep>> part(nt_max);
+  std::vector<std::vector<StepTags>> part_tags(nt_max);   // parallel to `part` when context rules are loaded
   std::vector<std::vector<uint64_t>> part_count(nt_max);  // steps per batch
   std::vector<uint64_t> part_nvar(nt_max, 0);             // variants held by the chosen matches
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+  const bool want_tags = hm && !hm->context_rules.empty();
   const unsigned used = parallel_ranges(nbatch, 64, [&](unsigned tid, uint64_t lo, uint64_t hi) {
     range[tid] = {lo, hi};
     std::vector<SequenceStep> steps;
+    std::vector<StepTags> tags;
     std::vector<uint32_t> count;
-    std::vector<uint64_t> first;
+    std::vector<uint64_t> first, vids;
     std::vector<double> score;
     for (uint64_t b = lo; b < hi; ++b) {
       const uint64_t s0 = st.batch_first[b], s1 = st.batch_first[b + 1];
@@ -740,6 +753,7 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
         count.clear();
         first.clear();
         score.clear();
+        vids.clear();
         for (uint64_t k = s0; k < s1; ++k) {
           const anl_match& mm = in->matches[k];
           const uint32_t c = mm.variants ? (uint32_t)mm.n_variants : 0;
@@ -748,17 +762,30 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
           for (uint32_t j = 0; j < c; ++j) {  // VariantResult::score, src/types.rs:335-341
             const anl_variant& v = mm.variants[j];
             score.push_back(fw == 0.0f ? v.dist_score : (v.dist_score + ((double)fw * v.freq_score)) / (1.0 + (double)fw));
+            if (scored) vids.push_back(v.vocab_id);
           }
         }
         const BatchDesc& d = descs[b];
-        chosen = most_likely_sequence(bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, bounds[d.end_index].begin,
-                                      st.segs.data() + s0, s1 - s0, BatchVariants{count.data(), first.data(), score.data()},
-                                      &steps);
-        if (chosen)
+        BatchVariants bv{count.data(), first.data(), score.data(), scored ? vids.data() : nullptr};
+        tags.clear();
+        if (scored)
+          chosen = most_likely_sequence_full(hm, t, bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, bounds[d.end_index].begin,
+                                             st.segs.data() + s0, s1 - s0, bv, sw, &steps, want_tags ? &tags : nullptr);
+        else
+          chosen = most_likely_sequence(bounds.data() + d.begin_index, d.end_index + 1 - d.begin_index, bounds[d.end_index].begin,
+                                        st.segs.data() + s0, s1 - s0, bv, &steps);
+        if (chosen) {
           part[tid].insert(part[tid].end(), steps.begin(), steps.end());
+          if (want_tags) {
+            tags.resize(steps.size());
+            part_tags[tid].insert(part_tags[tid].end(), tags.begin(), tags.end());
+          }
+        }
       }
-      if (!chosen)  // unigram-only models (:1929-1932) and empty lattices (:2261-2267): every match as it is
+      if (!chosen) {  // unigram-only models (:1929-1932) and empty lattices (:2261-2267): every match as it is
         for (uint64_t k = s0; k < s1; ++k) part[tid].push_back(SequenceStep{(uint32_t)(k - s0), in->matches[k].selected});
+        if (want_tags) part_tags[tid].resize(part[tid].size());
+      }
       part_count[tid].push_back(part[tid].size() - before);
       for (size_t i = before; i < part[tid].size(); ++i) {
         const anl_match& mm = in->matches[s0 + part[tid][i].seg];
@@ -800,11 +827,71 @@ anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, 
       }
     }
   });
+  if (want_tags) {  // Match.tag / Match.seqnr of the chosen sequence (:2476-2492)
+    ms->tag_first.assign(1, 0);
+    for (unsigned tid = 0; tid < used; ++tid)
+      for (const StepTags& stg : part_tags[tid]) {
+        ms->tag.insert(ms->tag.end(), stg.tag.begin(), stg.tag.end());
+        ms->seqnr.insert(ms->seqnr.end(), stg.seqnr.begin(), stg.seqnr.end());
+        ms->tag_first.push_back(ms->tag.size());
+      }
+    if (ms->tag_first.size() != ms->matches.size() + 1) return fail(ANL_ERR_INVALID, "internal error: tag list out of step");
+  }
   pt.lap("consolidate: assemble");
   *out = ms_owner.release();
   return ANL_OK;
+}
+anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
+                                     anl_match_set** out) try {
+  return consolidate_impl(nullptr, in, text, len, params, out);
 } catch (...) {
   return on_exception();
+}
+anl_status anl_model_consolidate(const anl_model* m, const anl_match_set* in, const char* text, size_t len,
+                                 const anl_search_params* params, anl_match_set** out) try {
+  if (!m) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before find_all_matches()");
+  return consolidate_impl(&m->host, in, text, len, params, out);
+} catch (...) {
+  return on_exception();
+}
+uint64_t anl_match_set_tags(const anl_match_set* ms, uint64_t i, const uint16_t** tags, const uint8_t** seqnr) {
+  if (tags) *tags = nullptr;
+  if (seqnr) *seqnr = nullptr;
+  if (!ms || ms->tag_first.empty() || i + 1 >= ms->tag_first.size()) return 0;
+  const uint64_t a = ms->tag_first[i], b = ms->tag_first[i + 1];
+  if (tags) *tags = ms->tag.data() + a;
+  if (seqnr) *seqnr = ms->seqnr.data() + a;
+  return b - a;
+}
+// ---- language model / context rules of the model ----------------------------------------------------------------------
+anl_status anl_model_read_contextrules(anl_model* m, const char* filename) try {
+  if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
+  std::string err;
+  if (!m->host.read_contextrules(filename, &err)) return fail(ANL_ERR_IO, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+anl_status anl_model_add_contextrule(anl_model* m, const char* pattern, float score, const char* const* tags, uint32_t n_tags,
+                                     const char* const* tagoffsets, uint32_t n_tagoffsets) try {
+  if (!m || !pattern || (n_tags && !tags) || (n_tagoffsets && !tagoffsets)) return fail(ANL_ERR_INVALID, "null argument");
+  std::vector<std::string> tg, to;
+  for (uint32_t i = 0; i < n_tags; ++i) tg.push_back(tags[i] ? tags[i] : "");
+  for (uint32_t i = 0; i < n_tagoffsets; ++i) to.push_back(tagoffsets[i] ? tagoffsets[i] : "");
+  std::string err;
+  if (!m->host.add_contextrule(pattern, score, tg, to, &err)) return fail(ANL_ERR_INVALID, err);
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+int32_t anl_model_have_lm(const anl_model* m) { return m && m->host.built && m->host.have_lm() ? 1 : 0; }
+uint64_t anl_model_ngram_count(const anl_model* m) { return m && m->host.built ? m->host.lm_ngrams : 0; }
+uint32_t anl_model_contextrule_count(const anl_model* m) { return m ? (uint32_t)m->host.context_rules.size() : 0; }
+uint32_t anl_model_tag_count(const anl_model* m) { return m ? (uint32_t)m->host.tags.size() : 0; }
+const char* anl_model_tag_name(const anl_model* m, uint32_t i) { return m && i < m->host.tags.size() ? m->host.tags[i].c_str() : nullptr; }
+void anl_debug_lm_score_tokens(const anl_model* m, const int64_t* tokens, uint64_t n, float* logprob, double* perplexity) {
+  if (m && tokens && n && logprob && perplexity) m->host.lm_score_tokens(tokens, n, logprob, perplexity);
 }
 
 // ---- test hooks for the host-side producer (no model, no GPU needed) ------------------------------------------

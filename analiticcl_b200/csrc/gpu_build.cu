@@ -622,6 +622,7 @@ bool gpu_build_index(HostModel* hm, int sd, uint32_t shard, uint32_t n_shards, i
   }
   pt.lap("gpu build: download");
   hm->index = std::move(ix);
+  hm->build_language_model();
   hm->built = true;
   return true;
 }

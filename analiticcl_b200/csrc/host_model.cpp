@@ -102,7 +102,7 @@ static bool is_unicode_space(uint32_t c) {
   return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
          c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
 }
-static std::string trim_unicode(const std::string& s) {
+std::string trim_unicode(const std::string& s) {
   size_t a = 0, b = s.size();
   while (a < b) {
     unsigned l;
@@ -863,6 +863,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
   }
   pt.lap("build: table");
   index = std::move(ix);
+  build_language_model();
   built = true;
   return true;
 }
@@ -1194,6 +1195,7 @@ bool HostModel::load_index(const std::string& path, std::string* err) {
     return bad("index file is inconsistent (charcount mask)");
   fclose(f);
   index = std::move(ix);
+  build_language_model();
   built = true;
   return true;
 }

@@ -10,6 +10,7 @@
 
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "device_types.h"
@@ -85,6 +86,23 @@ struct Confusable {  // src/confusables.rs:5-11
   bool simple = false;  // only insertions / deletions, no anchors: matching depends on edit chunks alone
 };
 
+// One context rule (src/search.rs:354-365).  The pattern (PatternMatch, :338-352) of every position is a prefix program:
+// an operator followed by its operands (NOT: one expression, OR: n expressions).
+struct RuleOp {
+  uint8_t kind;     // sequence.cpp: any, no-lexicon, vocabulary id, from-lexicon, not, or
+  uint8_t lexicon;  // from-lexicon: the lexicon's index
+  uint16_t n;       // or: number of alternatives
+  uint64_t vocab_id;
+};
+struct ContextRule {
+  std::vector<RuleOp> code;
+  std::vector<uint32_t> start;  // per pattern position: where its expression begins in `code`
+  float score = 1.0f;           // > 1 bonus, < 1 penalty
+  std::vector<uint16_t> tag;
+  std::vector<std::pair<uint8_t, uint8_t>> tagoffset;  // begin, length (in pattern positions)
+};
+std::string trim_unicode(const std::string& s);  // str::trim (Unicode White_Space)
+
 // Host copy of the built index (used for has(), statistics and to size device buffers).
 struct HostIndex {
   std::vector<Key192> ana_key;         // ascending
@@ -152,6 +170,15 @@ class HostModel {
   // -- host post-pass ---------------------------------------------------------------------------------
   double compute_confusable_weight(const char* input, size_t len, uint64_t candidate) const;  // src/lib.rs:1733-1756
 
+  // -- language model and context rules of the sequence consolidation (sequence.cpp) ------------------
+  void build_language_model();  // src/lib.rs:246-295, part of build()
+  bool have_lm() const { return lm_ngrams > 0; }
+  bool entry_tokens(uint64_t id, uint32_t* out, unsigned* n) const;  // into_ngram, src/lib.rs:2688-2751 (out holds 5)
+  void lm_score_tokens(const int64_t* tokens, size_t n, float* logprob, double* perplexity) const;  // src/lib.rs:2643-2674
+  bool add_contextrule(const std::string& pattern, float score, const std::vector<std::string>& tags,
+                       const std::vector<std::string>& tagoffsets, std::string* err);  // src/lib.rs:658-765
+  bool read_contextrules(const std::string& filename, std::string* err);               // src/lib.rs:570-656
+
   Weights weights;
   int debug;
   Alphabet alphabet;
@@ -165,6 +192,13 @@ class HostModel {
   bool all_confusables_simple = true;
   bool built = false;
   HostIndex index;
+  // n-gram counts keyed by vocabulary ids (unigram: id; bigram: first << 32 | second), src/lib.rs:75-79
+  std::unordered_map<uint32_t, uint32_t> lm_unigram;
+  std::unordered_map<uint64_t, uint32_t> lm_bigram;
+  std::unordered_set<std::string> lm_higher;  // scratch of build_language_model
+  uint64_t lm_ngrams = 0;
+  std::vector<ContextRule> context_rules;  // src/lib.rs:82
+  std::vector<std::string> tags;           // src/lib.rs:85
 };
 
 // sesdiff::shortest_edit_script(src, dst, false, false, false) -- see editscript.cpp

@@ -71,12 +71,30 @@ struct BatchVariants {
   const uint32_t* count;
   const uint64_t* first;
   const double* score;
+  const uint64_t* vocab_id = nullptr;  // per variant, parallel to score (needed by the language model / context rules)
 };
 // most_likely_sequence (src/lib.rs:2088-2495) for a model without language model and context rules: the
 // lowest-cost path through the batch's segment lattice.  Returns false when the lattice has no arcs (the
 // reference then returns the matches unchanged, :2261-2267).
 bool most_likely_sequence(const Boundary* bounds, size_t nbounds, size_t end_offset, const SegmentSpan* segs, size_t nsegs,
                           const BatchVariants& variants, std::vector<SequenceStep>* out);
+// The whole of most_likely_sequence (sequence.cpp): the max_seq shortest paths, each scored by the model's language
+// model (lm_score, src/lib.rs:2570-2674) and context rules (test_context_rules, :2501-2566), best weighted sum kept
+// (:2381-2425).  `text` is the whole input (boundary tokens are read from it).  out_tags (optional): per step the tags
+// and sequence numbers its context rules assign (Match.tag / Match.seqnr).  Falls back to the single cheapest path when
+// the model has neither (or hm == nullptr).
+class HostModel;
+struct SequenceWeights {  // src/types.rs:139-156
+  uint64_t max_seq = 250;
+  float lm_weight = 1.0f, variantmodel_weight = 3.0f, contextrules_weight = 1.0f;
+};
+struct StepTags {
+  std::vector<uint16_t> tag;
+  std::vector<uint8_t> seqnr;
+};
+bool most_likely_sequence_full(const HostModel* hm, const std::string& text, const Boundary* bounds, size_t nbounds, size_t end_offset,
+                               const SegmentSpan* segs, size_t nsegs, const BatchVariants& variants, const SequenceWeights& w,
+                               std::vector<SequenceStep>* out, std::vector<StepTags>* out_tags);
 std::vector<uint64_t> byte_to_codepoint_map(const std::string& text);
 
 }  // namespace anl

@@ -52,8 +52,8 @@ typedef struct anl_distance_threshold {
 /* StopCriterion, src/types.rs:307-313 */
 enum { ANL_STOP_EXHAUSTIVE = 0, ANL_STOP_AT_EXACT_MATCH = 1 };
 
-/* SearchParameters, src/types.rs:110-168, field for field (fields only used by the out-of-scope
- * FST/LM stage are carried so a caller can pass its struct through unchanged). */
+/* SearchParameters, src/types.rs:110-168, field for field (the sequence fields -- max_seq and the three
+ * weights -- are read by anl_model_consolidate; lm_order, context_weight and single_thread are carried unread, as in the reference). */
 typedef struct anl_search_params {
   anl_distance_threshold max_anagram_distance;
   anl_distance_threshold max_edit_distance;
@@ -254,10 +254,40 @@ void anl_match_set_lookup_counts(const anl_match_set* ms, uint64_t* segment_look
  * epsilon at cost 100).  `in` must be the match set anl_find_all_matches returned for the same text and
  * params->max_ngram; `*out` is a new, independent match set holding only the matches on the best path, in
  * text order, with `selected` = the chosen variant (-1 = out of vocabulary).  With max_ngram == 1 the result is
- * a copy of `in` (the reference skips the FST, :1929-1932).  The LM / context-rule terms of the reference's
- * sequence score (:2336-2400) are not built; tie-breaking among equal-cost paths is documented in DESIGN.md. */
+ * a copy of `in` (the reference skips the FST, :1929-1932).  This entry point knows no model, hence no language
+ * model and no context rules (anl_model_consolidate below); tie-breaking among equal-cost paths is documented in
+ * DESIGN.md. */
 anl_status anl_match_set_consolidate(const anl_match_set* in, const char* text, size_t len, const anl_search_params* params,
                                      anl_match_set** out);
+/* The whole of most_likely_sequence (src/lib.rs:2088-2495) with the model's language model and context rules: the
+ * params->max_seq shortest paths per batch, each scored by lm_score (bigram model over the output tokens and the
+ * boundaries between them, :2570-2674) and test_context_rules (:2501-2566), the three normalised terms weighted by
+ * params->lm_weight / variantmodel_weight / contextrules_weight (:2381-2425).  Runs also for max_ngram == 1 when the
+ * model holds a language model or context rules (:1912).  Matches of the result carry the tags their context rules
+ * assign (anl_match_set_tags). */
+anl_status anl_model_consolidate(const anl_model* m, const anl_match_set* in, const char* text, size_t len,
+                                 const anl_search_params* params, anl_match_set** out);
+/* Match.tag / Match.seqnr (src/search.rs:57-60) of match i: returns how many tags it has; *tags = indices into the model's
+ * tag names (anl_model_tag_name), *seqnr = position of the match inside each tagged sequence. */
+uint64_t anl_match_set_tags(const anl_match_set* ms, uint64_t i, const uint16_t** tags, const uint8_t** seqnr);
+
+/* Language model: entries read with vocab_type = ANL_VOCAB_LM (read_lm of the Python binding = read_vocabulary with that
+ * type, bindings/python/src/lib.rs:659-667) are n-grams "w1 w2 .." with their frequency as count; build() collects
+ * them (src/lib.rs:246-295). */
+int32_t anl_model_have_lm(const anl_model* m);
+uint64_t anl_model_ngram_count(const anl_model* m);
+/* read_contextrules (src/lib.rs:570-656): TSV `pattern <TAB> score [<TAB> tag;tag.. [<TAB> begin:length;..]]`;
+ * add_contextrule (src/lib.rs:658-765): pattern = ';'-separated positions, each a word of the vocabulary, `?` (any),
+ * `^` (in no lexicon), `@lexicon`, `!x` / `!(x|y)` (negation) or `x|y` (disjunction).  Call after the lexicons the
+ * rules refer to are loaded. */
+anl_status anl_model_read_contextrules(anl_model* m, const char* filename);
+anl_status anl_model_add_contextrule(anl_model* m, const char* pattern, float score, const char* const* tags, uint32_t n_tags,
+                                     const char* const* tagoffsets, uint32_t n_tagoffsets);
+uint32_t anl_model_contextrule_count(const anl_model* m);
+uint32_t anl_model_tag_count(const anl_model* m);
+const char* anl_model_tag_name(const anl_model* m, uint32_t i);
+/* Test hook: lm_score_tokens (src/lib.rs:2643-2674) on explicit vocabulary ids (-1 = out of vocabulary). */
+void anl_debug_lm_score_tokens(const anl_model* m, const int64_t* tokens, uint64_t n, float* logprob, double* perplexity);
 
 /* Test hooks for the host-side batch producer of find_all_matches (no model or GPU needed): the boundaries
  * (src/search.rs:190-258; strength 1 weak, 2 normal, 3 hard) and the n-gram segments per hard-delimited batch
