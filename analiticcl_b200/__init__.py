@@ -264,13 +264,27 @@ class VariantModel:
         _lib().anl_model_set_confusables_before_pruning(self._h)
 
     def read_lm(self, filename):
-        raise NotImplementedError("language models are outside the variant-lookup hot path (see DESIGN.md)")
+        """bindings/python/src/lib.rs:659-667: read_vocabulary with VocabType::LM -- n-grams `w1 w2 ..<TAB>count` for
+        the language-model term of find_all_matches (collected by build())."""
+        self.read_vocabulary(filename, VocabParams(vocabtype="LM"))
 
     def read_contextrules(self, filename):
-        raise NotImplementedError("context rules are outside the variant-lookup hot path (see DESIGN.md)")
+        """bindings/python/src/lib.rs:691-696 (src/lib.rs:570-656)."""
+        _check(_lib().anl_model_read_contextrules(self._h, os.fsencode(filename)))
 
-    def add_contextrule(self, pattern, score, tag, tagoffset):
-        raise NotImplementedError("context rules are outside the variant-lookup hot path (see DESIGN.md)")
+    def add_contextrule(self, pattern, score, tag=(), tagoffset=()):
+        """bindings/python/src/lib.rs:630-643 (src/lib.rs:658-765)."""
+        tg = [t.encode("utf-8") for t in tag]
+        to = [t.encode("utf-8") for t in tagoffset]
+        a = (C.c_char_p * max(1, len(tg)))(*tg)
+        b = (C.c_char_p * max(1, len(to)))(*to)
+        _check(_lib().anl_model_add_contextrule(self._h, pattern.encode("utf-8"), float(score), a, len(tg), b, len(to)))
+
+    def have_lm(self):
+        return bool(_lib().anl_model_have_lm(self._h))
+
+    def tags(self):
+        return [_lib().anl_model_tag_name(self._h, i).decode("utf-8") for i in range(_lib().anl_model_tag_count(self._h))]
 
     def build(self, device=-1, devices=None, gpu_build=None):
         """Build the anagram index and upload it to the GPU (`device` = CUDA ordinal, -1 = current).  With
@@ -372,17 +386,19 @@ class VariantModel:
 
     def find_all_matches(self, text, params):
         """bindings/python/src/lib.rs:752-805: [{"input", "offset": {"begin","end"}, "variants": [...]}, ...]
-        with the selected variant first.  With max_ngram > 1 the matches are the most likely sequence per
-        hard-delimited batch (most_likely_sequence, src/lib.rs:1912-1924, 2088-2495; variant-model scores only: no
-        LM, no context rules), like the reference.  `consolidate_matches=False` (which the reference's library
-        carries but never reads) returns the producer's view instead: every looked-up segment of every order."""
+        with the selected variant first (+ "tag" / "seqnr" where context rules tagged the match).  With max_ngram > 1, a
+        language model or context rules the matches are the most likely sequence per hard-delimited batch
+        (most_likely_sequence, src/lib.rs:1912-1924, 2088-2495), like the reference.  `consolidate_matches=False` (which
+        the reference's library carries but never reads) returns the producer's view instead: every looked-up segment
+        of every order."""
         raw = text.encode("utf-8")
         ms = C.c_void_p()
         _check(_lib().anl_find_all_matches(self._h, raw, len(raw), C.byref(params.data), C.byref(ms)))
         try:
-            if params.data.max_ngram > 1 and params.data.consolidate_matches:
+            sequence = params.data.max_ngram > 1 or self.have_lm() or _lib().anl_model_contextrule_count(self._h) > 0  # :1912
+            if sequence and params.data.consolidate_matches:
                 best = C.c_void_p()
-                _check(_lib().anl_match_set_consolidate(ms, raw, len(raw), C.byref(params.data), C.byref(best)))
+                _check(_lib().anl_model_consolidate(self._h, ms, raw, len(raw), C.byref(params.data), C.byref(best)))
                 _lib().anl_match_set_free(ms)
                 ms = best
             return self._match_list(ms, text, raw, params)
@@ -395,6 +411,8 @@ class VariantModel:
         cpmode = bool(params.data.unicodeoffsets)
         out = []
         m = _capi.Match()
+        tagnames = self.tags()
+        tg, sq = C.POINTER(C.c_uint16)(), C.POINTER(C.c_uint8)()
         for i in range(_lib().anl_match_set_len(ms)):
             _check(_lib().anl_match_set_get(ms, i, C.byref(m)))
             if not m.variants and params.data.max_ngram > 1 and m.n > 1:
@@ -403,7 +421,13 @@ class VariantModel:
             variants = [self._variant_dict(m.variants[j], fw, lexnames) for j in range(m.n_variants)]
             if m.selected > 0:
                 variants.insert(0, variants.pop(m.selected))
-            out.append({"input": seg, "offset": {"begin": int(m.begin), "end": int(m.end)}, "variants": variants})
+            d = {"input": seg, "offset": {"begin": int(m.begin), "end": int(m.end)}}
+            nt = _lib().anl_match_set_tags(ms, i, C.byref(tg), C.byref(sq)) if tagnames else 0
+            if nt:  # bindings/python/src/lib.rs:768-783
+                d["tag"] = [tagnames[tg[k]] for k in range(nt)]
+                d["seqnr"] = [int(sq[k]) for k in range(nt)]
+            d["variants"] = variants
+            out.append(d)
         return out
 
     # -- introspection used by tests / benchmarks -------------------------------------------------------

@@ -880,7 +880,7 @@ anl_status anl_model_add_contextrule(anl_model* m, const char* pattern, float sc
   for (uint32_t i = 0; i < n_tags; ++i) tg.push_back(tags[i] ? tags[i] : "");
   for (uint32_t i = 0; i < n_tagoffsets; ++i) to.push_back(tagoffsets[i] ? tagoffsets[i] : "");
   std::string err;
-  if (!m->host.add_contextrule(pattern, score, tg, to, &err)) return fail(ANL_ERR_INVALID, err);
+  if (!m->host.add_contextrule(pattern, score, tg, to, &err)) return fail(ANL_ERR_IO, err);  // (the reference returns an io::Error)
   return ANL_OK;
 } catch (...) {
   return on_exception();

@@ -322,9 +322,12 @@ bool most_likely_sequence_full(const HostModel* hm, const std::string& text, con
                                std::vector<SequenceStep>* out, std::vector<StepTags>* out_tags) {
   out->clear();
   if (out_tags) out_tags->clear();
-  const bool use_lm = hm && hm->have_lm() && w.lm_weight > 0.0f && variants.vocab_id;  // :2336
-  const bool use_rules = hm && !hm->context_rules.empty() && variants.vocab_id;        // :2345
-  if (!use_lm && !use_rules) {
+  const bool use_lm = hm && hm->have_lm() && w.lm_weight > 0.0f;  // :2336
+  const bool use_rules = hm && !hm->context_rules.empty();        // :2345
+  bool ids_missing = false;  // (a batch without a single variant needs no ids)
+  if (!variants.vocab_id)
+    for (size_t k = 0; k < nsegs; ++k) ids_missing = ids_missing || variants.count[k] > 0;
+  if ((!use_lm && !use_rules) || ids_missing) {
     // nothing but the variant model to weigh: the best of the max_seq shortest paths is the shortest path
     return most_likely_sequence(bounds, nbounds, end_offset, segs, nsegs, variants, out);
   }

@@ -108,3 +108,93 @@ def test_reference_0705_lm_disabled(A):
     r = m.find_all_matches("I tink you are rihgt", sp)
     assert [(x["input"], x["variants"][0]["text"]) for x in r] == \
         [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right")]
+
+
+# ---- language model and context rules: the reference's own tests through the Python mirror with GPU lookups ----------
+WORDS = ["I", "think", "sink", "you", "are", "right"]
+LM_ENTRIES = [("<bos> I", 2), ("I think", 2), ("I sink", 1), ("you are", 2), ("right <eos>", 2)]
+TEST_SP = dict(max_anagram_distance=2, max_edit_distance=2, max_matches=10, score_threshold=0.0, cutoff_threshold=0.0,
+               freq_weight=0.0, max_ngram=2)  # get_test_searchparams(), src/test.rs:48-68
+
+
+def small(A, words, lm=()):
+    m = A.VariantModel(None, A.Weights(), alphabet_tsv=orc.TEST_ALPHABET_TSV)
+    for w in words:
+        m.add_to_vocabulary(w, 2, A.VocabParams())
+    for w, f in lm:
+        m.add_to_vocabulary(w, f, A.VocabParams(vocabtype="LM"))
+    m.build()
+    return m
+
+
+def test_reference_0702_0704_with_language_model(A):
+    """tests/main.rs:1143-1361 as they stand (LM entries loaded, lm_weight = 1)."""
+    m = small(A, WORDS + ["are right"], LM_ENTRIES)
+    assert m.have_lm()
+    sp = A.SearchParameters(**TEST_SP)
+    for text, last in (("I tink you are rihgt", "are rihgt"), ("I tink you are\nrihgt", "are\nrihgt")):
+        r = m.find_all_matches(text, sp)
+        assert [(x["input"], x["variants"][0]["text"]) for x in r] == [("I", "I"), ("tink", "think"), ("you", "you"), (last, "are right")]
+    m = small(A, WORDS + ["am", "sure", "are right"], LM_ENTRIES + [("I am", 2), ("sure <eos>", 2)])
+    r = m.find_all_matches("I tink you are rihgt\n\nI am sur", sp)
+    assert [(x["input"], x["variants"][0]["text"]) for x in r] == \
+        [("I", "I"), ("tink", "think"), ("you", "you"), ("are rihgt", "are right"), ("I", "I"), ("am", "am"), ("sur", "sure")]
+
+
+def test_reference_0902_0905_context_rules(A):
+    """tests/main.rs:1575-1728: bonus + tag, penalty, single-word rules sharing a tag, two tags on one rule."""
+    sp = A.SearchParameters(**{**TEST_SP, "max_ngram": 1}, lm_weight=0.0)
+    text = "I tink you are rihgt"
+    m = small(A, WORDS)
+    m.add_contextrule("I; think", 1.1, ["testtag"], [])
+    r = m.find_all_matches(text, sp)
+    assert [(x["input"], x["variants"][0]["text"]) for x in r] == [("I", "I"), ("tink", "think"), ("you", "you"), ("are", "are"), ("rihgt", "right")]
+    assert (r[0]["tag"], r[0]["seqnr"], r[1]["tag"], r[1]["seqnr"]) == (["testtag"], [0], ["testtag"], [1])
+    assert all("tag" not in x for x in r[2:])
+    m = small(A, WORDS)
+    m.add_contextrule("I; think", 0.9, [], [])
+    r = m.find_all_matches(text, sp)
+    assert [x["variants"][0]["text"] for x in r] == ["I", "sink", "you", "are", "right"]
+    m = small(A, WORDS)
+    for w in ("think", "are", "right"):
+        m.add_contextrule(w, 1.0, ["testtag"], [])
+    r = m.find_all_matches(text, sp)
+    assert [(x.get("tag"), x.get("seqnr")) for x in r] == [(None, None), (["testtag"], [0]), (None, None), (["testtag"], [0]), (["testtag"], [0])]
+    m = small(A, WORDS)
+    m.add_contextrule("I; think", 1.1, ["testtag", "testtag2"], [])
+    r = m.find_all_matches(text, sp)
+    assert (r[0]["tag"], r[0]["seqnr"], r[1]["tag"], r[1]["seqnr"]) == (["testtag", "testtag2"], [0, 0], ["testtag", "testtag2"], [1, 1])
+    assert [x["variants"][0]["text"] for x in r] == ["I", "think", "you", "are", "right"]
+
+
+def test_language_model_and_rules_equal_oracle_on_running_text(A, eng, eng_oracle, tmp_path):
+    """A bigram model counted from the text itself + two rules, on the eng lexicon: GPU lookups + host sequence stage
+    against the oracle end to end (the eng fixtures are shared: the LM is loaded into fresh models)."""
+    text = workloads.cfg3_text(400, 77) + " We would like sep arate beds to gether."
+    toks = [t for t in text.replace(".", " ").split() if t]
+    counts = {}
+    for a, b in zip(toks, toks[1:]):
+        counts[a + " " + b] = counts.get(a + " " + b, 0) + 1
+    lmf = tmp_path / "lm.tsv"
+    lmf.write_text("".join(f"{k}\t{v}\n" for k, v in sorted(counts.items())[:300]), encoding="utf-8")
+    o = orc.OracleModel(alphabet_file=workloads.ALPHABET)
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    for mm in (o, m):
+        mm.read_lexicon(workloads.lexicon_path("eng"))
+        mm.read_lm(str(lmf))
+        mm.build()
+        mm.add_contextrule("would; like", 1.1, ["modal"], [])
+        mm.add_contextrule("^; ?", 0.95, [], [])
+    assert m.have_lm() and o.have_lm()
+    for kw in (dict(max_ngram=2), dict(max_ngram=3, max_seq=20, lm_weight=2.0), dict(max_ngram=1, contextrules_weight=0.5)):
+        sp = A.SearchParameters(max_anagram_distance=2, max_edit_distance=2, **kw)
+        op = orc.make_params(max_anagram_distance=2, max_edit_distance=2, **kw)
+        exp = o.find_all_matches(text, op)
+        got = m.find_all_matches(text, sp)
+        assert [(x["input"], x["offset"]["begin"], x["offset"]["end"]) for x in got] == [(s["text"], s["begin"], s["end"]) for s in exp]
+        for g, s in zip(got, exp):
+            ev = [o.vocab_text(v[0]) for v in s["variants"]]
+            if s["selected"] > 0:
+                ev.insert(0, ev.pop(s["selected"]))
+            assert [v["text"] for v in g["variants"]] == ev
+            assert g.get("tag", []) == [o.tags()[t] for t in s["tag"]] and g.get("seqnr", []) == s["seqnr"]

@@ -236,6 +236,10 @@ def test_python_mirror_consolidates_like_the_reference(L, monkeypatch):
         m.add_to_vocabulary(w, 2, A.VocabParams())
     for w, f in LM_ENTRIES:  # tests/main.rs:1364-1429 (lm_weight = 0: the entries are carried, the LM is off)
         m.add_to_vocabulary(w, f, A.VocabParams(vocabtype="LM"))
+    try:
+        m.build()  # host side of build() (index arrays, language model); the upload needs a GPU
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
 
     def fake_find_all_matches(h, raw, n, params_ref, out_ref):
         sp = params_ref._obj
