@@ -198,12 +198,10 @@ def _check(status):
 class VariantModel:
     """VariantModel(alphabet_file, weights, debug=0) -- bindings/python/src/lib.rs:548-812.
 
-    In scope: read_lexicon, read_vocabulary, add_to_vocabulary, read_variants, add_variant,
-    read_confusablelist, set_confusables_before_pruning, build, __contains__, find_variants,
-    find_variants_par, find_all_matches (with the variant-model part of the sequence consolidation).
-    Out of scope (raise NotImplementedError): read_lm, read_contextrules, add_contextrule -- the
-    language-model and context-rule terms of the sequence score are not part of the variant-lookup
-    hot path.
+    read_lexicon, read_vocabulary, read_lm, add_to_vocabulary, read_variants, add_variant, read_confusablelist,
+    set_confusables_before_pruning, read_contextrules, add_contextrule, build, __contains__, find_variants,
+    find_variants_par, find_all_matches (with the whole sequence stage: variant model, language model, context rules),
+    plus learn_variants, which the reference's library has and its binding lacks.
     """
 
     def __init__(self, alphabet_file, weights=None, debug=0, alphabet_tsv=None):
@@ -262,6 +260,26 @@ class VariantModel:
 
     def set_confusables_before_pruning(self):
         _lib().anl_model_set_confusables_before_pruning(self._h)
+
+    def learn_variants(self, inputs, params, strict=True, auto_build=True):
+        """VariantModel::learn_variants (src/lib.rs:1062-1139; the reference's Python binding does not expose it): look
+        the inputs up and store the found variants in the model.  Returns the number of variant links added."""
+        blob, offs = _capi.pack(list(inputs))
+        count = C.c_uint64()
+        _check(_lib().anl_model_learn_variants(self._h, blob, _capi.u64ptr(offs), len(offs) - 1, C.byref(params.data),
+                                               int(bool(strict)), int(bool(auto_build)), C.byref(count)))
+        return count.value
+
+    def _vocab_size(self):
+        return _lib().anl_model_vocab_size(self._h)
+
+    def vocab_links(self, vid):
+        """([(reference id, score), ...] this entry is a variant of, [variant ids this entry is the reference for])."""
+        ids, sc = (C.c_uint64 * 256)(), (C.c_double * 256)()
+        n = _lib().anl_debug_vocab_links(self._h, vid, 0, ids, sc, 256)
+        of = [(ids[i], sc[i]) for i in range(n)]
+        n = _lib().anl_debug_vocab_links(self._h, vid, 1, ids, sc, 256)
+        return of, [ids[i] for i in range(n)]
 
     def read_lm(self, filename):
         """bindings/python/src/lib.rs:659-667: read_vocabulary with VocabType::LM -- n-grams `w1 w2 ..<TAB>count` for

@@ -132,6 +132,9 @@ SIGNATURES = {
     "anl_model_shard": (None, [_vp, _P(_u32), _P(_u32)]),
     "anl_match_set_consolidate": (_i32, [_vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
     "anl_debug_match_set_build": (_i32, [_cp, _sz, C.c_uint32, C.c_int32, _P(C.c_uint8), _P(C.c_uint64), _P(Variant), _u64, _P(_vp)]),
+    "anl_model_learn_variants": (_i32, [_vp, _cp, _P(_u64), _u64, _P(SearchParams), _i32, _i32, _P(_u64)]),
+    "anl_debug_learn_apply": (_i32, [_vp, _cp, _P(_u64), _u64, _P(_u64), _P(C.c_double), _P(_u64)]),
+    "anl_debug_vocab_links": (_i64, [_vp, _u64, _i32, _P(_u64), _P(C.c_double), _sz]),
     "anl_model_consolidate": (_i32, [_vp, _vp, _cp, _sz, _P(SearchParams), _P(_vp)]),
     "anl_match_set_tags": (_u64, [_vp, _u64, _P(_P(C.c_uint16)), _P(_P(C.c_uint8))]),
     "anl_model_have_lm": (_i32, [_vp]),

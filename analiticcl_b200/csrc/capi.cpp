@@ -280,6 +280,99 @@ anl_status anl_model_build_multi(anl_model* m, const int32_t* devices, uint32_t 
   return on_exception();
 }
 uint32_t anl_model_device_count(const anl_model* m) { return m ? (uint32_t)m->replicas().size() : 0; }
+
+static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in, const char* text, size_t len,
+                                   const anl_search_params* params, anl_match_set** out);
+// learn_variants (src/lib.rs:1062-1139).  The lookups are the model's own batched GPU lookups: strict mode is ONE
+// anl_find_variants_batch over all inputs (the reference's par_iter over find_variants, :1083-1088), else
+// find_all_matches + the sequence stage per input; the found (input, variant) pairs are then stored in order.
+anl_status anl_model_learn_variants(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_inputs,
+                                    const anl_search_params* params, int32_t strict, int32_t auto_build, uint64_t* count) try {
+  if (!m || !offsets || !params || (!blob && n_inputs > 0)) return fail(ANL_ERR_INVALID, "null argument");
+  if (!m->host.built || !m->engine.uploaded())
+    return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before learn_variants()");
+  if (m->host.index.n_shards > 1) return fail(ANL_ERR_UNSUPPORTED, "learn_variants is not available on a lexicon shard");
+  std::vector<HostModel::LearnedVariant> items;
+  std::string err;
+  int status = ANL_OK;
+  if (strict) {
+    ResultSet rs;
+    if (!find_variants_batch_multi(m->replicas(), blob ? blob : "", offsets, n_inputs, *params, &rs, &err, &status))
+      return fail(status ? status : ANL_ERR_CUDA, err);
+    for (uint64_t i = 0; i < n_inputs; ++i)
+      for (uint64_t j = rs.offsets[i]; j < rs.offsets[i + 1]; ++j)
+        items.push_back({std::string(blob + offsets[i], offsets[i + 1] - offsets[i]), rs.variants[j].vocab_id, rs.variants[j].dist_score});
+  } else {
+    const bool sequence = params->max_ngram > 1 || m->host.have_lm() || !m->host.context_rules.empty();  // :1912
+    for (uint64_t i = 0; i < n_inputs; ++i) {
+      const char* text = blob + offsets[i];
+      const size_t len = offsets[i + 1] - offsets[i];
+      anl_match_set* all = nullptr;
+      anl_status st = anl_find_all_matches(m, text, len, params, &all);
+      if (st != ANL_OK) return st;
+      std::unique_ptr<anl_match_set> owner(all), best;
+      const anl_match_set* use = all;
+      if (sequence) {
+        anl_match_set* b = nullptr;
+        st = consolidate_impl(&m->host, all, text, len, params, &b);
+        if (st != ANL_OK) return st;
+        best.reset(b);
+        use = b;
+      }
+      std::vector<uint64_t> cp2byte;
+      if (params->unicodeoffsets) {  // match offsets are code points then: back to bytes for the text slice
+        const std::vector<uint64_t> map = byte_to_codepoint_map(std::string(text, len));
+        cp2byte.assign(map.back() + 1, 0);
+        for (size_t b = len + 1; b-- > 0;) cp2byte[map[b]] = b;
+      }
+      for (size_t k = 0; k < use->matches.size(); ++k) {
+        const anl_match& mm = use->matches[k];
+        if (!mm.variants || mm.selected < 0 || (uint64_t)mm.selected >= mm.n_variants) continue;
+        const uint64_t b = params->unicodeoffsets ? cp2byte[mm.begin] : mm.begin, e = params->unicodeoffsets ? cp2byte[mm.end] : mm.end;
+        items.push_back({std::string(text + b, e - b), mm.variants[mm.selected].vocab_id, mm.variants[mm.selected].dist_score});
+      }
+    }
+  }
+  const uint64_t added = m->host.learn_apply(items);
+  if (count) *count = added;
+  if (auto_build) {  // (re)build on the devices that hold the index now
+    std::vector<int32_t> devices;
+    for (Engine* e : m->replicas()) devices.push_back(e->device());
+    int sd = 1;
+    if (const char* e = getenv("ANL_SD")) sd = atoi(e) ? 1 : 0;
+    if (!build_any(m, sd, 0, 1, devices[0], -1, &err)) return fail(ANL_ERR_UNSUPPORTED, err);
+    return upload_replicas(m, devices.data(), (uint32_t)devices.size());
+  }
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+// Test hooks: the bookkeeping half of learn_variants on explicit (input, result id, score) triples, and an entry's links.
+anl_status anl_debug_learn_apply(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n, const uint64_t* vocab_ids,
+                                 const double* scores, uint64_t* count) try {
+  if (!m || !offsets || (n && (!blob || !vocab_ids || !scores))) return fail(ANL_ERR_INVALID, "null argument");
+  std::vector<HostModel::LearnedVariant> items;
+  for (uint64_t i = 0; i < n; ++i) items.push_back({std::string(blob + offsets[i], offsets[i + 1] - offsets[i]), vocab_ids[i], scores[i]});
+  const uint64_t added = m->host.learn_apply(items);
+  if (count) *count = added;
+  return ANL_OK;
+} catch (...) {
+  return on_exception();
+}
+int64_t anl_debug_vocab_links(const anl_model* m, uint64_t id, int32_t kind, uint64_t* ids, double* scores, size_t cap) {
+  if (!m || id >= m->host.decoder.size()) return -1;
+  const VocabEntry& v = m->host.decoder[id];
+  if (kind == 0) {
+    for (size_t i = 0; i < v.variant_of.size() && i < cap; ++i) {
+      if (ids) ids[i] = v.variant_of[i].first;
+      if (scores) scores[i] = v.variant_of[i].second;
+    }
+    return (int64_t)v.variant_of.size();
+  }
+  for (size_t i = 0; i < v.reference_for.size() && i < cap; ++i)
+    if (ids) ids[i] = v.reference_for[i];
+  return (int64_t)v.reference_for.size();
+}
 anl_status anl_model_save_index(const anl_model* m, const char* filename) try {
   if (!m || !filename) return fail(ANL_ERR_INVALID, "null argument");
   if (!m->host.built) return fail(ANL_ERR_NOT_BUILT, "Model has not been built yet! Call build() before save_index()");

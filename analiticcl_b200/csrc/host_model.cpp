@@ -348,7 +348,38 @@ bool HostModel::read_vocabulary(const std::string& filename, const VocabParams& 
 // src/lib.rs:460-514: the variant is added to the vocabulary and linked with its reference in both directions.
 bool HostModel::add_variant(uint64_t ref_id, const char* text, size_t len, double score, bool has_freq, uint32_t freq,
                             const VocabParams& p) {
-  const uint64_t vid = add_to_vocabulary(text, len, has_freq, freq, p);
+  return add_variant_by_id(ref_id, add_to_vocabulary(text, len, has_freq, freq, p), score);
+}
+
+// src/lib.rs:1106-1130, the bookkeeping half of learn_variants: every (input text, found variant) pair, in order.  An
+// input that is already in the vocabulary gains one occurrence per consecutive run of pairs; a new one is added as a
+// TRANSPARENT entry (that type alone: it is linked to its reference but -- like in the reference -- not indexed); the
+// input then becomes a variant of what was found for it, weighted by the distance score.
+uint64_t HostModel::learn_apply(const std::vector<LearnedVariant>& items) {
+  uint64_t count = 0;
+  VocabParams p;
+  p.vocab_type = VT_TRANSPARENT;
+  p.freq_handling = FH_MAX;
+  const LearnedVariant* prev = nullptr;
+  for (const LearnedVariant& it : items) {
+    uint64_t id;
+    auto e = encoder.find(it.input);
+    if (e != encoder.end()) {
+      id = e->second;
+      if (!prev || prev->input != it.input) {
+        decoder[id].frequency += 1;
+        built = false;  // (the device index holds its own copy of the frequencies)
+      }
+    } else {
+      id = add_to_vocabulary(it.input.data(), it.input.size(), true, 1, p);
+    }
+    if (it.vocab_id != id && it.vocab_id < decoder.size() && add_variant_by_id(it.vocab_id, id, it.dist_score)) ++count;
+    prev = &it;
+  }
+  return count;
+}
+
+bool HostModel::add_variant_by_id(uint64_t ref_id, uint64_t vid, double score) {  // src/lib.rs:478-514
   if (vid == ref_id) return false;
   VocabEntry& ref = decoder[ref_id];
   ref.has_variants = true;  // (only the first mention of a variant counts)

@@ -140,7 +140,15 @@ class HostModel {
   uint64_t add_to_vocabulary(const char* text, size_t len, bool has_freq, uint32_t freq, const VocabParams& p);
   // weighted variant lists (src/lib.rs:460-514, 766-897); ref_id must exist
   bool add_variant(uint64_t ref_id, const char* text, size_t len, double score, bool has_freq, uint32_t freq, const VocabParams& p);
+  bool add_variant_by_id(uint64_t ref_id, uint64_t variant_id, double score);
   bool read_variants(const std::string& filename, const VocabParams& p, bool transparent, std::string* err);
+  // learn_variants (src/lib.rs:1062-1139), second half: stores (input, found variant) pairs; returns how many links were added
+  struct LearnedVariant {
+    std::string input;
+    uint64_t vocab_id;
+    double dist_score;
+  };
+  uint64_t learn_apply(const std::vector<LearnedVariant>& items);
   bool add_to_confusables(const std::string& editscript, double weight, std::string* err);
   bool read_confusablelist(const std::string& filename, std::string* err);
   // src/lib.rs:192-245: anagram values, grouping, ordering -> flat arrays (host side of build())

@@ -140,6 +140,20 @@ anl_status anl_model_read_variants(anl_model* m, const char* filename, const anl
 /* add_to_vocabulary (src/lib.rs:900); has_frequency=0 means None */
 anl_status anl_model_add_to_vocabulary(anl_model* m, const char* text, size_t len, int32_t has_frequency,
                                        uint32_t frequency, const anl_vocab_params* params, uint64_t* vocab_id);
+/* learn_variants (src/lib.rs:1062-1139): looks the inputs up (strict = 1: every input as a whole, find_variants -- one
+ * batched GPU call over all inputs; strict = 0: every input as running text, the selected variants of find_all_matches)
+ * and stores what was found in the model instead of returning it: an input gains a frequency count (a new input becomes
+ * a TRANSPARENT entry) and is linked as a variant of every result, weighted by its distance score.  *count = links
+ * added.  auto_build = 1 rebuilds the index and uploads it to the model's devices again (the reference's `build()`).
+ * Inputs: UTF-8 blob + offsets[n_inputs + 1], as for anl_find_variants_batch. */
+anl_status anl_model_learn_variants(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n_inputs,
+                                    const anl_search_params* params, int32_t strict, int32_t auto_build, uint64_t* count);
+/* Test hooks: the bookkeeping half of learn_variants on explicit (input text, result vocabulary id, dist_score)
+ * triples (host only), and the variant links of an entry (kind 0: VariantOf targets + scores, 1: ReferenceFor ids;
+ * returns their number, -1 for an unknown id). */
+anl_status anl_debug_learn_apply(anl_model* m, const char* blob, const uint64_t* offsets, uint64_t n, const uint64_t* vocab_ids,
+                                 const double* scores, uint64_t* count);
+int64_t anl_debug_vocab_links(const anl_model* m, uint64_t id, int32_t kind, uint64_t* ids, double* scores, size_t cap);
 /* read_confusablelist (src/lib.rs:414), add_to_confusables (src/lib.rs:444) */
 anl_status anl_model_read_confusablelist(anl_model* m, const char* filename);
 anl_status anl_model_add_to_confusables(anl_model* m, const char* editscript, double weight);

@@ -1315,6 +1315,32 @@ struct Model {
   bool add_variant(uint64_t ref_id, const std::string& variant, double score, bool has_freq, uint32_t freq, int freq_handling,
                    int vocab_type, int lex_index) {
     const uint64_t variantid = add_to_vocabulary(variant, has_freq, freq, freq_handling, vocab_type, lex_index);
+    return add_variant_by_id(ref_id, variantid, score);
+  }
+  // the second half of learn_variants, src/lib.rs:1106-1130: (input text, result) pairs in order
+  struct Learned {
+    std::string input;
+    uint64_t vocab_id;
+    double dist_score;
+  };
+  uint64_t learn_apply(const std::vector<Learned>& items) {
+    uint64_t count = 0;
+    const std::string* prev = nullptr;
+    for (const Learned& it : items) {
+      uint64_t vocab_id;
+      auto e = encoder.find(it.input);
+      if (e != encoder.end()) {
+        if (!prev || *prev != it.input) decoder[e->second].frequency += 1;  // first of a consecutive run
+        vocab_id = e->second;
+      } else {
+        vocab_id = add_to_vocabulary(it.input, true, 1, FH_MAX, VT_TRANSPARENT, 0);  // (TRANSPARENT alone: not INDEXED)
+      }
+      if (it.vocab_id != vocab_id && add_variant_by_id(it.vocab_id, vocab_id, it.dist_score)) ++count;
+      prev = &it.input;
+    }
+    return count;
+  }
+  bool add_variant_by_id(uint64_t ref_id, uint64_t variantid, double score) {  // :478-514
     if (variantid == ref_id) return false;
     {
       VocabValue& r = decoder[ref_id];  // link reference to variant: only the first mention counts
@@ -2445,6 +2471,45 @@ int32_t orc_read_variants(void* h, const char* filename, int32_t freq_handling, 
   return ((Model*)h)->read_variants(filename, freq_handling, vocab_type, transparent != 0);
 }
 void orc_set_have_freq(void* h, int32_t v) { ((Model*)h)->have_freq = v != 0; }
+// learn_variants, src/lib.rs:1028-1139: strict = find_variants per input, else the selected variants of find_all_matches
+// per input; the found (input, variant) pairs are then stored in the model.  Returns the number of variants added.
+uint64_t orc_learn_variants(void* h, const char* blob, const uint64_t* offsets, uint64_t n, const Params* p, int32_t strict,
+                            int32_t auto_build) {
+  Model* m = (Model*)h;
+  std::vector<Model::Learned> items;
+  for (uint64_t i = 0; i < n; ++i) {
+    const std::string input(blob + offsets[i], offsets[i + 1] - offsets[i]);
+    if (strict) {
+      if (input.empty()) continue;  // (the reference would panic on an empty input, :1420)
+      for (const Result& r : m->find_variants(input, *p, nullptr)) items.push_back({input, r.vocab_id, r.dist_score});
+    } else {
+      for (const Segment& sg : run_search(m, input, *p, nullptr, true, nullptr))
+        if (sg.looked_up && sg.selected >= 0 && (size_t)sg.selected < sg.variants.size())
+          items.push_back({input.substr(sg.begin, sg.end - sg.begin), sg.variants[sg.selected].vocab_id, sg.variants[sg.selected].dist_score});
+    }
+  }
+  const uint64_t count = m->learn_apply(items);
+  if (auto_build) m->build();
+  return count;
+}
+uint64_t orc_learn_apply(void* h, const char* blob, const uint64_t* offsets, uint64_t n, const uint64_t* vocab_ids, const double* scores) {
+  std::vector<Model::Learned> items;
+  for (uint64_t i = 0; i < n; ++i) items.push_back({std::string(blob + offsets[i], offsets[i + 1] - offsets[i]), vocab_ids[i], scores[i]});
+  return ((Model*)h)->learn_apply(items);
+}
+// variant links of an entry: kind 0 = VariantOf (targets + scores), 1 = ReferenceFor (variant ids); returns the count
+int64_t orc_vocab_links(void* h, uint64_t id, int32_t kind, uint64_t* ids, double* scores, int64_t cap) {
+  const VocabValue& v = ((Model*)h)->decoder[id];
+  if (kind == 0) {
+    for (size_t i = 0; i < v.variant_of.size() && (int64_t)i < cap; ++i) {
+      ids[i] = v.variant_of[i].first;
+      scores[i] = v.variant_of[i].second;
+    }
+    return (int64_t)v.variant_of.size();
+  }
+  for (size_t i = 0; i < v.reference_for.size() && (int64_t)i < cap; ++i) ids[i] = v.reference_for[i];
+  return (int64_t)v.reference_for.size();
+}
 int32_t orc_add_confusable(void* h, const char* script, double weight) {
   Confusable c;
   if (!confusable_new(script, weight, &c)) return -1;

@@ -127,6 +127,9 @@ def lib():
                                         P(Result), i64]),
         "orc_find_all_matches": (i64, [vp, cp, u64, P(Params), P(C.c_uint8), P(u64), P(Result), P(u64), P(u64), P(u32),
                                        P(i32), P(u64), i64, P(Result), i64, P(u64), P(C.c_uint16), P(C.c_uint8), i64]),
+        "orc_learn_variants": (u64, [vp, cp, P(u64), u64, P(Params), i32, i32]),
+        "orc_learn_apply": (u64, [vp, cp, P(u64), u64, P(u64), P(C.c_double)]),
+        "orc_vocab_links": (i64, [vp, u64, i32, P(u64), P(C.c_double), i64]),
         "orc_have_lm": (i32, [vp]),
         "orc_ngram_count": (u64, [vp]),
         "orc_add_contextrule": (i32, [vp, cp, C.c_float, cp, cp]),
@@ -216,6 +219,32 @@ class OracleModel:
         if rc != 0:
             raise RuntimeError(f"oracle read_variants({filename}) failed: {rc}")
         self.nlex += 1
+
+    def learn_variants(self, inputs, params, strict=True, auto_build=True):
+        """src/lib.rs:1062-1139 -> number of variants added."""
+        raw = [t.encode("utf-8") for t in inputs]
+        offs = (C.c_uint64 * (len(raw) + 1))()
+        for i, r in enumerate(raw):
+            offs[i + 1] = offs[i] + len(r)
+        return lib().orc_learn_variants(self.h, b"".join(raw), offs, len(raw), C.byref(params), int(strict), int(auto_build))
+
+    def learn_apply(self, items):
+        """The bookkeeping half of learn_variants on explicit (input text, result vocab id, dist_score) triples."""
+        raw = [t.encode("utf-8") for t, _, _ in items]
+        offs = (C.c_uint64 * (len(raw) + 1))()
+        for i, r in enumerate(raw):
+            offs[i + 1] = offs[i] + len(r)
+        ids = (C.c_uint64 * max(1, len(items)))(*[int(v) for _, v, _ in items])
+        sc = (C.c_double * max(1, len(items)))(*[float(d) for _, _, d in items])
+        return lib().orc_learn_apply(self.h, b"".join(raw), offs, len(raw), ids, sc)
+
+    def vocab_links(self, vid):
+        """-> ([(target id, score)...] VariantOf, [variant id...] ReferenceFor)"""
+        ids, sc = (C.c_uint64 * 256)(), (C.c_double * 256)()
+        n = lib().orc_vocab_links(self.h, vid, 0, ids, sc, 256)
+        of = [(ids[i], sc[i]) for i in range(n)]
+        n = lib().orc_vocab_links(self.h, vid, 1, ids, sc, 256)
+        return of, [ids[i] for i in range(n)]
 
     def read_lm(self, filename):
         """bindings/python/src/lib.rs:659-667: read_vocabulary with VocabType::LM."""
