@@ -1560,15 +1560,15 @@ bool Engine::shard_merge_strided(DeviceBatch* b, uint32_t n_shards, const void* 
   CU_TRY(cudaSetDevice(device_));
   const uint32_t n = b->n;
   cudaStream_t st = b->stream;
-  // a hit-list overflow on any shard cannot be repaired after the exchange: fail on every rank alike
-  std::vector<uint32_t> flags_all((size_t)n * n_shards);
-  if (n)
-    CU_TRY(cudaMemcpy2D(flags_all.data(), (size_t)n * sizeof(uint32_t), d_flags_all, (size_t)query_stride * sizeof(uint32_t),
-                        (size_t)n * sizeof(uint32_t), n_shards, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < flags_all.size(); ++i) {
-    if ((flags_all[i] & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) {
-      *err = "query " + std::to_string(i % std::max<uint32_t>(n, 1)) +
-             " exceeds the per-query candidate capacity on a shard; raise ANL_HIT_CAP";
+  // a hit-list overflow on any shard cannot be repaired after the exchange: fail on every rank alike.  Checked on the
+  // device (8 bytes come back): downloading the n_shards x n flags cost more than the merge itself at 8 shards.
+  {
+    unsigned int* res = b->d_work + 20;  // (two free work slots; the launchers of the merge / export stage do not touch them)
+    CU_TRY(launch_shard_flagcheck(reinterpret_cast<const uint32_t*>(d_flags_all), n, n_shards, query_stride, res, sm_count_, st));
+    CU_TRY(cudaMemcpyAsync(b->h_work + 20, res, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (b->h_work[20]) {
+      *err = "query " + std::to_string(b->h_work[21]) + " exceeds the per-query candidate capacity on a shard; raise ANL_HIT_CAP";
       *status = ANL_ERR_UNSUPPORTED;
       return false;
     }

@@ -2280,6 +2280,30 @@ finish_kernel(const BatchParams bp, uint32_t nq, OutRec* __restrict__ out, OutHe
   }
 }
 
+// Lexicon-sharded mode: a hit-list overflow on any shard cannot be repaired after the exchange.  res[0] = 1 if some
+// (shard, query) carries QF_HIT_OVERFLOW without QF_UNSUPPORTED, res[1] = the smallest such query (pre-set to ~0).
+__global__ void shard_flagcheck_kernel(const uint32_t* __restrict__ flags_all, uint32_t n, uint32_t n_shards, uint64_t stride,
+                                       unsigned int* res) {
+  const uint64_t total = (uint64_t)n * n_shards;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(i / n), q = (uint32_t)(i % n);
+    const uint32_t f = flags_all[(size_t)r * stride + q];
+    if ((f & (QF_HIT_OVERFLOW | QF_UNSUPPORTED)) == QF_HIT_OVERFLOW) {
+      atomicOr(res, 1u);
+      atomicMin(res + 1, q);
+    }
+  }
+}
+cudaError_t launch_shard_flagcheck(const uint32_t* flags_all, uint32_t n, uint32_t n_shards, uint64_t stride, unsigned int* res,
+                                   int sm_count, cudaStream_t stream) {
+  static const unsigned int init[2] = {0u, 0xFFFFFFFFu};
+  cudaError_t e = cudaMemcpyAsync(res, init, sizeof init, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess || n == 0) return e;
+  shard_flagcheck_kernel<<<(unsigned)sm_count * 8, 256, 0, stream>>>(flags_all, n, n_shards, stride, res);
+  ++g_kernel_launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, uint32_t head_stride,
                          const OutRec* recs_all, const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
                          OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,

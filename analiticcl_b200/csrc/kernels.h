@@ -84,6 +84,8 @@ cudaError_t configure_kernels();
 cudaError_t upload_alphabetic_ranges(const uint32_t* ranges, uint32_t n);
 unsigned long long kernel_launches();  // process-wide count of kernel launches issued by this library
 // Lexicon-sharded mode: merge the all-gathered per-shard survivor lists (see merge_kernel).
+cudaError_t launch_shard_flagcheck(const uint32_t* flags_all, uint32_t n, uint32_t n_shards, uint64_t stride, unsigned int* res,
+                                   int sm_count, cudaStream_t stream);
 cudaError_t launch_merge(const BatchParams& bp, uint32_t n, uint32_t n_shards, const OutHead* heads_all, uint32_t head_stride,
                          const OutRec* recs_all, const uint32_t* gids_all, uint32_t rec_stride, const uint32_t* qflags_in, uint32_t* qflags,
                          OutRec* out, OutHead* out_head, void* scratch, uint32_t scratch_cap, unsigned int* work, int sm_count,

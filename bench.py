@@ -431,12 +431,18 @@ def run_ours(args):
                        "peak_source": "profiles/r02d_randread.txt (measured on this pool's B200, independent loads)",
                        "issue_active_pct": e.get("issue_active_pct"), "lanes_per_instruction": e.get("lanes_per_instruction")})
         rr16 = random_read_peak(ist["table_bytes"], 16)
-        if rr16 and exact_ms > 0:
+        rr32 = random_read_peak(32 * ist["anagrams"], 32)
+        if rr16 and rr32 and exact_ms > 0:
+            # two dependent random reads dominate a staged node: the 16-byte table slot(s) by fingerprint, then the 32-byte
+            # anagram record of every posting that is verified (posting-array reads of multi-posting slots and the staged-node
+            # queue itself are not counted).  Roof = the time those reads take at the measured random-read rates of their footprints.
             e = ncu_entry("exact_kernel", wl_key)
-            kr.append({"kernel": "exact_kernel", "ms": exact_ms, "bound": "random 16-byte reads (table slots, then postings / anagram records)",
-                       "achieved": ctr.probe_steps / (exact_ms / 1e3) / 1e9, "peak": rr16, "unit": "G reads/s",
-                       "frac": ctr.probe_steps / (exact_ms / 1e3) / 1e9 / rr16, "footprint_bytes": ist["table_bytes"],
-                       "peak_source": "profiles/r02d_randread.txt",
+            t_min_ms = (ctr.probe_steps / rr16 + ctr.postings / rr32) / 1e6
+            kr.append({"kernel": "exact_kernel", "ms": exact_ms, "bound": "random 16-byte reads (table slots) + random 32-byte reads (anagram records)",
+                       "achieved": (ctr.probe_steps + ctr.postings) / (exact_ms / 1e3) / 1e9,
+                       "peak": (ctr.probe_steps + ctr.postings) / (t_min_ms / 1e3) / 1e9, "unit": "G reads/s",
+                       "frac": t_min_ms / exact_ms, "footprint_bytes": [ist["table_bytes"], 32 * ist["anagrams"]],
+                       "peak_source": "profiles/r02d_randread.txt (16-byte reads at the table's footprint, 32-byte reads at the anagram records')",
                        "issue_active_pct": e.get("issue_active_pct"), "lanes_per_instruction": e.get("lanes_per_instruction")})
         if score_ms > 0:
             e = ncu_entry("dp_kernel", wl_key)
