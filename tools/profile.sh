@@ -14,6 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(encode|pro
 KERNELS=${KERNELS:-"bloom exact pairfilter dp rank confusable"}
 for K in $KERNELS; do
   S=3  # three warm-up passes skipped: the capture is the launch of the timed pass
+  if [ "$K" = dp ]; then S=6; fi  # (two launches per pass: the short class -- the main one -- then the long class)
   ncu --set full --clock-control none --import-source on -k regex:^${K}_kernel -s $S -c 1 -f -o gpurun_out/prof_$K \
       python bench.py --workload $W --queries $Q --steps 1 --warmup 3 --e2e-steps 0 --cpu-sample 64 > /dev/null 2> gpurun_out/prof_$K.err
 done
