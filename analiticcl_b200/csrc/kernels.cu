@@ -2022,26 +2022,37 @@ merge_kernel(const BatchParams bp, uint32_t nq, uint32_t n_shards, const OutHead
     uint32_t nsurv = 0;
     double maxfreq = 0.0;
     const uint32_t flags = qflags_in[qi];
-    for (uint32_t r = 0; r < n_shards; ++r) {
-      const OutHead h = heads_all[(size_t)r * head_stride + qi];
-      maxfreq = fmax(maxfreq, h.max_freq);
-      const OutRec* recs = recs_all + (size_t)r * rec_stride + h.offset;
-      const uint32_t* gids = gids_all + (size_t)r * rec_stride + h.offset;
-      for (uint32_t i = lane; i < h.count; i += 32) {
-        if (nsurv + i < scratch_cap) {
-          const OutRec o = recs[i];
-          SurvRec s;
-          s.dist = o.dist_score;
-          s.freq = (double)o.freq;
-          s.key = 0.0;
-          s.g = gids[i];
-          s.raw = o.freq;
-          s.vocab = o.vocab_id;
-          s.pad = 0;
-          surv[nsurv + i] = s;
+    // the shards' headers in one go (lane r holds shard r's; 32 shards per round), then the lists one after the other
+    for (uint32_t r0 = 0; r0 < n_shards; r0 += 32) {
+      OutHead mine;
+      mine.max_freq = 0.0;
+      mine.offset = 0;
+      mine.count = 0;
+      if (r0 + lane < n_shards) mine = heads_all[(size_t)(r0 + lane) * head_stride + qi];
+      double mf = mine.max_freq;
+      for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(FULL, mf, o));
+      maxfreq = fmax(maxfreq, mf);
+      const uint32_t in_round = min(32u, n_shards - r0);
+      for (uint32_t k = 0; k < in_round; ++k) {
+        const uint32_t cnt = __shfl_sync(FULL, mine.count, k), off = __shfl_sync(FULL, mine.offset, k);
+        const OutRec* recs = recs_all + (size_t)(r0 + k) * rec_stride + off;
+        const uint32_t* gids = gids_all + (size_t)(r0 + k) * rec_stride + off;
+        for (uint32_t i = lane; i < cnt; i += 32) {
+          if (nsurv + i < scratch_cap) {
+            const OutRec o = recs[i];
+            SurvRec s;
+            s.dist = o.dist_score;
+            s.freq = (double)o.freq;
+            s.key = 0.0;
+            s.g = gids[i];
+            s.raw = o.freq;
+            s.vocab = o.vocab_id;
+            s.pad = 0;
+            surv[nsurv + i] = s;
+          }
         }
+        nsurv += cnt;
       }
-      nsurv += h.count;
     }
     __syncwarp();
     if (nsurv > scratch_cap) {  // cannot happen: the host sizes scratch_cap from the gathered counts

@@ -413,7 +413,7 @@ def run_ours(args):
                       ("dp_kernel+rank_kernel", rank_ms), ("confusable_kernels", conf_ms), ("finish_kernel", finish_ms))
         time_dominant = max(stage_list, key=lambda kv: kv[1])[0]
         index_bytes = ist["table_bytes"] + ist["bloom_bytes"] + 5 * ist["postings"] + 32 * ist["anagrams"] + ist["instance_bytes"]
-        hbm_resident = index_bytes > 100e6  # beyond the 126 MB L2 (two 63 MB halves)
+        hbm_resident = index_bytes > 126e6  # beyond the 126 MB L2
         # one line per kernel (group), each against the limit that binds IT:
         #  * Bloom stage: one independent 8-byte read per neighbourhood node over the Bloom filter's footprint -> measured
         #    random-read rate of this GPU at that footprint (tools/micro/randread.cu); also instruction-issue bound (ncu)

@@ -127,6 +127,6 @@ if traffic and launch_info[1]:
             allw = {allw["probe"].get("workload", "cfg2"): allw}
     except (OSError, ValueError):
         allw = {}
-    allw[launch_info[0]] = traffic
+    allw.setdefault(launch_info[0], {}).update(traffic)  # (a partial capture only replaces the kernels it holds)
     json.dump(allw, open(path, "w"), indent=1)
 print("wrote", os.path.join(PROF, f"{tag}_ncu_summary.md"))
