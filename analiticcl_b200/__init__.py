@@ -402,6 +402,13 @@ class VariantModel:
         finally:
             _lib().anl_result_set_free(rs)
 
+    def find_variants_partitioned(self, inputs, params, group=None, dst=0):
+        """Query-partitioned lookup over the ranks of a torch.distributed job (one process per GPU, every rank holding a
+        replica of this model; SURVEY 8e mode 1): each rank looks up its contiguous slice, rank `dst` gets the whole
+        list in input order (others None).  No data-path collective -- only the gather of the results."""
+        from . import parallel
+        return parallel.lookup_partitioned(list(inputs), lambda qs: self.find_variants_raw(qs, params), group=group, dst=dst)
+
     def find_all_matches(self, text, params):
         """bindings/python/src/lib.rs:752-805: [{"input", "offset": {"begin","end"}, "variants": [...]}, ...]
         with the selected variant first (+ "tag" / "seqnr" where context rules tagged the match).  With max_ngram > 1, a

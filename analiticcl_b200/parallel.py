@@ -38,12 +38,19 @@ def lookup_partitioned(queries, lookup, group=None, dst=0):
     return out
 
 
-def reduce_step_time(ms_local, units_local, device=None, group=None):
-    """bench.py's reduction: (max over ranks of the step time, sum over ranks of the units)."""
+def reduce_max_sum(times, units, device=None, group=None):
+    """bench.py's reduction over the ranks: element-wise MAX of `times` (a step is as slow as its slowest rank) and
+    element-wise SUM of `units` (every rank processed its own share).  Returns two lists of floats."""
     import torch
-    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
-    u = torch.tensor([float(units_local)], dtype=torch.float64, device=device)
+    t = torch.tensor([float(x) for x in times], dtype=torch.float64, device=device)
+    u = torch.tensor([float(x) for x in units], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
-    return float(t.item()), float(u.item())
+    return t.tolist(), u.tolist()
+
+
+def reduce_step_time(ms_local, units_local, device=None, group=None):
+    """(max over ranks of the step time, sum over ranks of the units)."""
+    t, u = reduce_max_sum([ms_local], [units_local], device=device, group=group)
+    return t[0], u[0]

@@ -387,13 +387,9 @@ def run_ours(args):
     d2h = n_e2e_call * (8 + 4) + 32 * int(n_results) + 48 * ((n_e2e_call + 65535) // 65536)
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s, probe_ms, score_ms], dtype=torch.float64, device="cuda")
-    w = torch.tensor([float(n), float(ctr.dl_cells)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, probe_ms_max, score_ms_max = t.tolist()
-    total_q, total_cells = w.tolist()
+    from analiticcl_b200 import parallel
+    (dev_ms_max, e2e_s_max, probe_ms_max, score_ms_max), (total_q, total_cells) = parallel.reduce_max_sum(
+        [dev_ms, e2e_s, probe_ms, score_ms], [float(n), float(ctr.dl_cells)], device="cuda")
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -664,9 +660,8 @@ def run_sharded(args):
     dist.barrier()
     dt = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
-    t = torch.tensor([dt] + [a / args.steps for a in acc], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt_max, score_ms, exchange_ms, merge_ms = t.tolist()
+    from analiticcl_b200 import parallel
+    (dt_max, score_ms, exchange_ms, merge_ms), _ = parallel.reduce_max_sum([dt] + [a / args.steps for a in acc], [n], device=dev)
     if rank == 0:
         line = {
             "metric": METRIC, "value": n / dt_max, "unit": "queries/s", "n_gpus": world, "steps": args.steps,

@@ -71,3 +71,44 @@ def test_bad_device_lists():
         m.build(devices=[0, 0])
     with pytest.raises(RuntimeError):
         m.build(devices=[0, 99])
+
+
+def _partitioned_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    import analiticcl_b200 as A
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # (plumbing only: the results are gathered as objects)
+    dev = rank % torch.cuda.device_count()
+    m = A.VariantModel(workloads.ALPHABET, A.Weights())
+    m.read_lexicon(workloads.lexicon_path("eng"))
+    m.build(device=dev)
+    qs = workloads.misspellings(workloads.read_words("eng"), 3001, 77)
+    res = m.find_variants_partitioned(qs, A.SearchParameters())
+    if rank == 0:
+        out.put(res)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_query_partitioned_processes_equal_oracle(eng_oracle):
+    """SURVEY 8e mode 1 as the Python mirror exposes it: two processes (one replica each, on GPU rank % n_gpus), every
+    rank looks up its contiguous slice, rank 0 gets the whole list in input order."""
+    import torch.multiprocessing as mp
+    from test_gpu_parity import assert_same, to_orc_params
+    import analiticcl_b200 as A
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_partitioned_worker, args=(r, 2, 29533, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    qs = workloads.misspellings(workloads.read_words("eng"), 3001, 77)
+    sp = A.SearchParameters()
+    assert_same(res, eng_oracle.find_variants_batch(qs, to_orc_params(sp), threads=0), qs, "2 query-partitioned processes")
