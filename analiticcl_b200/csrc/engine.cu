@@ -1626,11 +1626,19 @@ struct CallShared {
   std::string err;
   int status = ANL_OK;
   std::vector<cudaStream_t> streams;  // every stream that has copied into `out`: synchronised before `out` moves
+  // ANL_TIMELINE=1: per chunk, the device times of its stages (CUDA events against `ref`) and the host's own steps
+  bool timeline = false;
+  cudaEvent_t ref = nullptr;
+  std::chrono::steady_clock::time_point t0;
 };
 struct InFlight {
   uint64_t chunk, q0;
   DeviceBatch* b;
+  double t_launched = 0, t_placed = 0;  // host clock, ms since the call began (timeline only)
 };
+double host_ms(const CallShared& S) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S.t0).count();
+}
 
 void fail_call(CallShared& S, const std::string& e, int status) {  // (S.m held)
   if (!S.failed) {
@@ -1664,6 +1672,15 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
     if (!e->wait_download(f.b, &e2)) {
       std::lock_guard<std::mutex> lk(S.m);
       fail_call(S, e2, ANL_ERR_CUDA);
+    }
+    if (S.timeline && d == 0 && f.b->runs_recorded > 0) {  // (events of another device cannot be compared with `ref`)
+      float t[EV_PER_RUN];
+      for (int k = 0; k < EV_PER_RUN; ++k)
+        if (cudaEventElapsedTime(&t[k], S.ref, f.b->events[(size_t)(f.b->runs_recorded - 1) * EV_PER_RUN + k]) != cudaSuccess) t[k] = -1;
+      fprintf(stderr,
+              "[anl timeline] chunk %3llu n %6u | device: start %7.2f bloom %7.2f exact %7.2f pairs %7.2f score %7.2f conf %7.2f finish %7.2f "
+              "export %7.2f | host: launched %7.2f placed %7.2f downloaded %7.2f\n",
+              (unsigned long long)f.chunk, f.b->n, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], f.t_launched, f.t_placed, host_ms(S));
     }
     e->free_batch(f.b);
   };
@@ -1719,8 +1736,9 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
   auto place_front = [&]() {
     InFlight f = running.front();
     running.pop_front();
-    if (f.b) copying.push_back(f);  // (owned by `copying` from here on, whatever happens in place())
     place(f);
+    f.t_placed = S.timeline ? host_ms(S) : 0;
+    if (f.b) copying.push_back(f);  // (owned by `copying` from here on, whatever happens in place())
     while (copying.size() > 1) finish_copy();
   };
   for (uint64_t c = d; c < nchunks; c += D) {
@@ -1746,7 +1764,7 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
         fail_call(S, e2, s2);
       }
     }
-    running.push_back(InFlight{c, lo, b});
+    running.push_back(InFlight{c, lo, b, S.timeline ? host_ms(S) : 0, 0});
     while (running.size() >= DEPTH) place_front();
   }
   while (!running.empty()) place_front();
@@ -1803,6 +1821,12 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
   CallShared S;
   S.out = out;
   S.n_total = n;
+  S.t0 = std::chrono::steady_clock::now();
+  if (const char* e = getenv("ANL_TIMELINE")) S.timeline = atoi(e) != 0;
+  if (S.timeline) {
+    cudaSetDevice(engines[0]->device());
+    if (cudaEventCreate(&S.ref) != cudaSuccess || cudaEventRecord(S.ref, 0) != cudaSuccess) S.timeline = false;
+  }
   out->offsets.resize((size_t)n + 1);
   out->flags.resize(std::max<uint64_t>(n, 1));
   out->flags.resize(n);
@@ -1824,6 +1848,10 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
     device_loop(engines[0], 0, used, S, blob, offsets, n, p, CHUNK, DEPTH);
     serial_ranges_flag() = was;
     for (auto& t : th) t.join();
+  }
+  if (S.timeline) {
+    fprintf(stderr, "[anl timeline] call of %llu queries done at %.2f ms (host clock)\n", (unsigned long long)n, host_ms(S));
+    if (S.ref) cudaEventDestroy(S.ref);
   }
   if (S.failed) {
     *err = S.err;
