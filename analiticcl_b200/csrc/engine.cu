@@ -1628,6 +1628,8 @@ struct CallShared {
   std::vector<cudaStream_t> streams;  // every stream that has copied into `out`: synchronised before `out` moves
   // ANL_TIMELINE=1: per chunk, the device times of its stages (CUDA events against `ref`) and the host's own steps
   bool timeline = false;
+  bool stagger = true;    // ANL_STAGGER=0 launches the chunks back to back
+  int stagger_event = 1;  // which stage of the predecessor must be over (1 = Bloom stage, 2 = exact stage, ...)
   cudaEvent_t ref = nullptr;
   std::chrono::steady_clock::time_point t0;
 };
@@ -1752,6 +1754,14 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
     if (!skip) {
       std::string e2;
       int s2 = ANL_OK;
+      // Staggered starts: chunks launched back to back share the GPU evenly and therefore all END together -- the device
+      // then drains before the next wave can start (ANL_TIMELINE: two waves of four chunks, 3 ms lost per 1 M queries).
+      // A chunk is launched when its predecessor has left the Bloom stage (about a quarter of its work): the chunks in
+      // flight stay a quarter apart, one ends every quarter, and its successor starts into a busy device.
+      if (S.stagger && !running.empty() && running.back().b && running.back().b->runs_recorded > 0) {
+        DeviceBatch* prev = running.back().b;
+        cudaEventSynchronize(prev->events[(size_t)(prev->runs_recorded - 1) * EV_PER_RUN + S.stagger_event]);
+      }
       b = e->create_batch(blob, offsets + lo, m, p, false, false, &e2, &s2);
       if (b && !e->run_batch(b, nullptr, &e2)) {
         s2 = ANL_ERR_CUDA;
@@ -1823,6 +1833,10 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
   S.n_total = n;
   S.t0 = std::chrono::steady_clock::now();
   if (const char* e = getenv("ANL_TIMELINE")) S.timeline = atoi(e) != 0;
+  if (const char* e = getenv("ANL_STAGGER")) {
+    S.stagger = atoi(e) != 0;
+    if (atoi(e) >= 1 && atoi(e) < EV_PER_RUN) S.stagger_event = atoi(e);
+  }
   if (S.timeline) {
     cudaSetDevice(engines[0]->device());
     if (cudaEventCreate(&S.ref) != cudaSuccess || cudaEventRecord(S.ref, 0) != cudaSuccess) S.timeline = false;
