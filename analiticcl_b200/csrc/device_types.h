@@ -79,13 +79,27 @@ struct __attribute__((aligned(32))) AnaRec {
   uint32_t inst_cnt;  // instances
 };
 
-// Blocked Bloom filter in front of the table: one 64-bit word per key, BLOOM_BITS bits inside it.
-// A miss (the overwhelmingly common case) costs one 8-byte load.
+// Blocked Bloom filter in front of the table: one 64-bit word per key (fp_index), BLOOM_BITS bits inside ONE 32-bit
+// half of it (the half is bit 7 of the fingerprint, just below the word index's bits).  A probe is a 4-byte load and a
+// 32-bit mask test: with all three bits in a 64-bit word the mask alone cost ~24 instructions per node on the 32-bit
+// datapath (three 64-bit one-hot shifts), a tenth of the Bloom stage's instruction stream; here it is three SHL and a LOP3.
+// A miss (the overwhelmingly common case) costs one load.  The builders (host_model.cpp, gpu_build.cu) OR the 64-bit form.
 static const int BLOOM_BITS = 3;
-__host__ __device__ __forceinline__ uint64_t bloom_mask(uint64_t h) {
+__host__ __device__ __forceinline__ uint32_t bloom_half(uint64_t h) { return (uint32_t)(h >> 7) & 1u; }
+__host__ __device__ __forceinline__ uint32_t bloom_mask32(uint64_t h) {
   // bits taken from the top of the fingerprint (the word index uses bits 8..)
-  return (1ULL << ((h >> 58) & 63)) | (1ULL << ((h >> 52) & 63)) | (1ULL << ((h >> 46) & 63));
+  const uint32_t t = (uint32_t)(h >> 32);
+  return (1u << (t >> 27)) | (1u << ((t >> 22) & 31u)) | (1u << ((t >> 17) & 31u));
 }
+__host__ __device__ __forceinline__ uint64_t bloom_mask(uint64_t h) { return (uint64_t)bloom_mask32(h) << (32u * bloom_half(h)); }
+#ifdef __CUDACC__
+// the probe: true = all three bits set (the key may be in the table)
+__device__ __forceinline__ bool bloom_test(const uint64_t* __restrict__ bloom, uint64_t word_mask, uint64_t h) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bloom) + (((h >> 8) & word_mask) * 2 + bloom_half(h)));
+  const uint32_t m = bloom_mask32(h);
+  return (w & m) == m;
+}
+#endif
 
 // ---- insertion multisets --------------------------------------------------------------------------
 // Entry t of the table is one multiset of j >= 1 inserted symbols drawn from the classes that

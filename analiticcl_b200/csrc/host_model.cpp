@@ -901,7 +901,7 @@ bool HostModel::build_index(int sd, uint32_t shard, uint32_t n_shards, std::stri
 
 // ---- persistence of the built index -------------------------------------------------------------------------------
 namespace {
-const char kIndexMagic[8] = {'A', 'N', 'L', 'I', 'D', 'X', '0', '2'};
+const char kIndexMagic[8] = {'A', 'N', 'L', 'I', 'D', 'X', '0', '3'};  // (03: Bloom bits of a key inside one 32-bit half of its word)
 struct IndexFileHeader {  // fixed-size, little-endian hosts only (x86-64 / aarch64)
   char magic[8];
   uint32_t header_bytes, slot_bytes, key_bytes, max_k;

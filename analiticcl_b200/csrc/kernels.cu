@@ -467,9 +467,7 @@ __device__ __forceinline__ void stage(K1Shared& S, K1Warp& W, uint32_t& sqn, boo
 }
 
 __device__ __forceinline__ bool bloom_pass(const K1Shared& S, uint64_t h) {
-  const uint64_t word = __ldg(S.ix.bloom + fp_index(h, S.ix.bloom_mask));
-  const uint64_t m = bloom_mask(h);
-  return (word & m) == m;
+  return bloom_test(S.ix.bloom, S.ix.bloom_mask, h);
 }
 
 // The nodes X = D + I', |I'| >= 1, of the buffered deletion entries; lanes stride over the multiset table.
@@ -950,9 +948,7 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
           const bool probe = ok && (ccbit(S.charcount_mask, cx) || (sd == 1 && ka > d && ccbit(S.charcount_mask, cx + 1)));
           bool pass = false;
           if (probe) {
-            const uint64_t word = __ldg(bloom + fp_index(h, bloom_wmask));
-            const uint64_t m = bloom_mask(h);
-            pass = (word & m) == m;
+            pass = bloom_test(bloom, bloom_wmask, h);
           }
           c_probes += probe;
           c_pass += pass;
@@ -994,9 +990,7 @@ bloom_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uin
                   }
                   bool px = false;
                   if (active) {
-                    const uint64_t word = __ldg(bloom + fp_index(hx, bloom_wmask));
-                    const uint64_t m = bloom_mask(hx);
-                    px = (word & m) == m;
+                    px = bloom_test(bloom, bloom_wmask, hx);
                   }
                   c_probes += active;
                   c_pass += px;
