@@ -1826,8 +1826,8 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
   // larger chunks have fewer kernel tails, smaller ones a shorter ramp; calls that span few chunks stay at 65536)
   uint64_t CHUNK = n >= ((uint64_t)D << 19) ? (1u << 17) : (1u << 16);
   if (const char* e = getenv("ANL_CHUNK")) CHUNK = (uint64_t)std::max(1024, atoi(e));
-  size_t DEPTH = 4;  // (free_batch keeps as many batches cached: no device allocation after the first chunks)
-  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(4, std::max(1, atoi(e)));
+  size_t DEPTH = 6;  // (free_batch keeps 8 batches cached: no device allocation after the first chunks; measured 3: 36.9, 4: 36.9, 5: 37.6, 6: 37.9 M q/s)
+  if (const char* e = getenv("ANL_INFLIGHT")) DEPTH = (size_t)std::min(6, std::max(1, atoi(e)));
   CallShared S;
   S.out = out;
   S.n_total = n;
