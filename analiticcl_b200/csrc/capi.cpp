@@ -564,12 +564,12 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   // (uninitialised, recycled buffers: each window fills its own part in parallel)
   PodBuffer<uint8_t> looked;
   PodBuffer<uint32_t> cnt;
-  PodBuffer<uint64_t> off, dst;  // dst: first variant of each segment in ms->variants
+  PodBuffer<uint64_t> off;
   looked.resize(nseg + 1);
   cnt.resize(nseg + 1);
   off.resize(nseg + 1);
-  dst.resize(nseg + 1);
   ms->matches.resize(nseg);
+  ms->variants.reserve(1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
   int status = ANL_OK;
   size_t WINDOW = 1u << 20;  // unigram segments per window
   if (const char* e = getenv("ANL_SEARCH_WINDOW")) WINDOW = (size_t)std::max(1, atoi(e));
@@ -751,12 +751,21 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
       pt.lap("search: n-gram lookups");
     }
     if (!ok) break;
-    // this window's matches: variant lists copied behind those of the earlier windows
-    dst[s0] = vtotal;
-    for (uint64_t k = s0; k < s1; ++k) dst[k + 1] = dst[k] + cnt[k];
-    vtotal = dst[s1];
+    // this window's matches.  The variant lists of the window's DISTINCT strings go behind those of the earlier windows
+    // (two block copies: unigram pass, n-gram pass); every occurrence of a string points at the one list of its
+    // representative -- running text repeats itself, and a copy per occurrence was a quarter of the call.
+    const uint64_t n0 = rs[0].offsets.size() ? rs[0].offsets[rs[0].offsets.size() - 1] : 0;
+    const uint64_t n1 = (params->max_ngram > 1 && rs[1].offsets.size()) ? rs[1].offsets[rs[1].offsets.size() - 1] : 0;
+    const uint64_t base[2] = {vtotal, vtotal + n0};
+    vtotal += n0 + n1;
     ms->variants.resize(vtotal);
     anl_variant* vbase = ms->variants.data();
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint64_t cnt_pass = pass == 0 ? n0 : n1;
+      const anl_variant* src = rs[pass].variants.data();
+      anl_variant* dstp = vbase + base[pass];
+      parallel_ranges(cnt_pass, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) { memcpy(dstp + lo, src + lo, (size_t)(hi - lo) * sizeof(anl_variant)); });
+    }
     parallel_ranges(s1 - s0, 4096, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t k = s0 + lo; k < s0 + hi; ++k) {
         const SegmentSpan& sp = st.segs[k];
@@ -767,8 +776,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
         mm.n_variants = cnt[k];
         mm.selected = (looked[k] && cnt[k] > 0) ? 0 : -1;
         // index + 1 for now, turned into a pointer below (the buffer may still move)
-        mm.variants = looked[k] ? reinterpret_cast<const anl_variant*>(dst[k] + 1) : nullptr;
-        if (cnt[k]) memcpy(vbase + dst[k], rs[looked[k] - 1].variants.data() + off[k], (size_t)cnt[k] * sizeof(anl_variant));
+        mm.variants = looked[k] ? reinterpret_cast<const anl_variant*>(base[looked[k] - 1] + off[k] + 1) : nullptr;
       }
     });
     pt.lap("search: assemble matches");
@@ -811,8 +819,8 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
   pt.lap("consolidate: segmentation");
   if (st.segs.size() != in->matches.size())
     return fail(ANL_ERR_INVALID, "match set does not belong to this text / max_ngram (segment count differs)");
-  const std::vector<Boundary>& bounds = seg->bounds;
-  const std::vector<BatchDesc>& descs = seg->batches;
+  const PodBuffer<Boundary>& bounds = seg->bounds;
+  const PodBuffer<BatchDesc>& descs = seg->batches;
   const size_t nbatch = st.batch_first.size() - 1;
   if (descs.size() != nbatch) return fail(ANL_ERR_INVALID, "match set does not belong to this text (batch count differs)");
   const float fw = params->freq_weight;

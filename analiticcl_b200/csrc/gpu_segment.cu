@@ -190,15 +190,17 @@ __global__ void widen_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64
   if (i < n) out[i] = in[i];
 }
 
+// Scratch comes from the device's stream-ordered memory pool (release threshold raised once per device, ensure_tables):
+// a dozen cudaMalloc / cudaFree pairs per call cost more than the kernels; from the pool they are free after the first call.
 struct Pool {
   std::vector<void*> ptrs;
   ~Pool() {
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) cudaFreeAsync(p, 0);
   }
   template <class T>
   bool alloc(T** out, size_t count, std::string* err) {
     void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) {
+    if (cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), 0) != cudaSuccess) {
       cudaGetLastError();
       *err = "device segmentation: out of device memory";
       return false;
@@ -234,6 +236,12 @@ bool ensure_tables(int device, std::string* err) {
     *err = "alphabetic range table too large for the device";
     return false;
   }
+  {
+    cudaMemPool_t mp = nullptr;
+    uint64_t keep = 8ull << 30;  // freed scratch stays with the pool up to this much instead of going back to the driver
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess && mp) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+  }
   GS_TRY(cudaMemcpyToSymbol(c_seg_alpha, alpha.data(), alpha.size() * sizeof(uint32_t)));
   GS_TRY(cudaMemcpyToSymbol(c_seg_n_alpha, &n, sizeof n));
   if (device >= 0 && device < 64) g_tab_loaded[device] = true;
@@ -244,7 +252,7 @@ bool ensure_tables(int device, std::string* err) {
 
 // segment_text (search.cpp) on `device`; the same SegmentedText.  Texts of 2 GiB and more are left to the host.
 bool segment_text_device(int device, const std::string& text, uint32_t max_ngram, SegmentedText* stp, std::string* err,
-                         std::vector<Boundary>* bounds_out, std::vector<BatchDesc>* batches_out) {
+                         PodBuffer<Boundary>* bounds_out, PodBuffer<BatchDesc>* batches_out) {
   static_assert(sizeof(DBoundary) == sizeof(Boundary) && sizeof(DBatch) == sizeof(BatchDesc), "device records mirror the host's");
   SegmentedText& st = *stp;
   if (bounds_out) bounds_out->clear();

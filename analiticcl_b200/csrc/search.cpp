@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 
 #include "hostpool.h"
@@ -156,8 +157,8 @@ bool segment_any(int device, const std::string& text, uint32_t max_ngram, Segmen
   return true;
 }
 
-void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp, std::vector<Boundary>* bounds_out,
-                  std::vector<BatchDesc>* batches_out) {
+void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* stp, PodBuffer<Boundary>* bounds_out,
+                  PodBuffer<BatchDesc>* batches_out) {
   SegmentedText& st = *stp;
   st.segs.clear();
   st.batch_first.resize(1);
@@ -202,8 +203,14 @@ void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* st
       if (part[t] && !part[t]->empty())
         std::copy(part[t]->begin(), part[t]->end(), st.segs.data() + st.batch_first[range[t].first]);
   });
-  if (bounds_out) *bounds_out = bounds;
-  if (batches_out) *batches_out = descs;
+  if (bounds_out) {
+    bounds_out->resize(bounds.size());
+    if (!bounds.empty()) memcpy(bounds_out->data(), bounds.data(), bounds.size() * sizeof(Boundary));
+  }
+  if (batches_out) {
+    batches_out->resize(descs.size());
+    if (!descs.empty()) memcpy(batches_out->data(), descs.data(), descs.size() * sizeof(BatchDesc));
+  }
 }
 
 // most_likely_sequence, src/lib.rs:2088-2495, without language model and context rules.

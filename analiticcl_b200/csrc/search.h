@@ -36,13 +36,13 @@ void list_batches(const std::vector<Boundary>& bounds, std::vector<BatchDesc>* o
 const std::vector<Boundary>& find_boundaries(const std::string& text);  // valid until the calling thread's next call
 void find_match_ngrams(const std::string& text, const Boundary* bounds, size_t nbounds, uint32_t order, size_t begin, size_t end,
                        std::vector<SegmentSpan>* out);
-void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* out, std::vector<Boundary>* bounds_out = nullptr,
-                  std::vector<BatchDesc>* batches_out = nullptr);
+void segment_text(const std::string& text, uint32_t max_ngram, SegmentedText* out, PodBuffer<Boundary>* bounds_out = nullptr,
+                  PodBuffer<BatchDesc>* batches_out = nullptr);
 // The same segmentation computed on `device` (gpu_segment.cu): boundary detection, strengths, batches and n-gram spans
 // as kernels over the text in HBM.  false + *err on a CUDA error or a text of 2 GiB and more.
 // bounds_out / batches_out (optional): the boundaries (find_boundaries) and batch descriptors (list_batches) as well.
 bool segment_text_device(int device, const std::string& text, uint32_t max_ngram, SegmentedText* out, std::string* err,
-                         std::vector<Boundary>* bounds_out = nullptr, std::vector<BatchDesc>* batches_out = nullptr);
+                         PodBuffer<Boundary>* bounds_out = nullptr, PodBuffer<BatchDesc>* batches_out = nullptr);
 // Which producer a text of `len` bytes gets: the device for running text (>= 64 KiB, ANL_SEGMENT_DEVICE_MIN), the host
 // loop for short strings where a kernel launch would be the whole cost; ANL_SEGMENT=host|device forces one.
 bool segment_on_device(size_t len);
@@ -51,8 +51,8 @@ bool segment_on_device(size_t len);
 // the producer's spans plus the boundaries and batch descriptors they were cut from.
 struct Segmentation {
   SegmentedText st;
-  std::vector<Boundary> bounds;
-  std::vector<BatchDesc> batches;
+  PodBuffer<Boundary> bounds;  // (recycled blocks like the spans: a 100 MB array is not page-faulted in on every call)
+  PodBuffer<BatchDesc> batches;
   size_t text_len = 0;
   uint32_t max_ngram = 0;
 };
