@@ -807,10 +807,13 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
                                    const anl_search_params* params, anl_match_set** out) {
   if (!in || !params || !out || (!text && len > 0)) return fail(ANL_ERR_INVALID, "null argument");
   PhaseTimer pt;
-  const std::string t(text ? text : "", len);
+  // (a private copy of the text only where one is read: re-segmentation, boundary tokens of the language model)
+  std::string t;
   // the producer's own segmentation when the match set still carries it (anl_find_all_matches), else re-derived
   std::shared_ptr<Segmentation> seg = in->seg;
-  if (!seg || seg->text_len != len || seg->max_ngram != params->max_ngram) {
+  const bool resegment = !seg || seg->text_len != len || seg->max_ngram != params->max_ngram;
+  if (resegment || (hm && hm->have_lm())) t.assign(text ? text : "", len);
+  if (resegment) {
     seg = std::make_shared<Segmentation>();
     std::string err;
     segment_any(-1, t, params->max_ngram, seg.get(), &err);
