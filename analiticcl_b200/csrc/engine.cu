@@ -1629,6 +1629,7 @@ struct CallShared {
   // ANL_TIMELINE=1: per chunk, the device times of its stages (CUDA events against `ref`) and the host's own steps
   bool timeline = false;
   bool stagger = true;    // ANL_STAGGER=0 launches the chunks back to back
+  bool stagger_always = false;
   int stagger_event = 1;  // which stage of the predecessor must be over (1 = Bloom stage, 2 = exact stage, ...)
   cudaEvent_t ref = nullptr;
   std::chrono::steady_clock::time_point t0;
@@ -1675,14 +1676,17 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
       std::lock_guard<std::mutex> lk(S.m);
       fail_call(S, e2, ANL_ERR_CUDA);
     }
-    if (S.timeline && d == 0 && f.b->runs_recorded > 0) {  // (events of another device cannot be compared with `ref`)
+    if (S.timeline && f.b->runs_recorded > 0) {
       float t[EV_PER_RUN];
-      for (int k = 0; k < EV_PER_RUN; ++k)
-        if (cudaEventElapsedTime(&t[k], S.ref, f.b->events[(size_t)(f.b->runs_recorded - 1) * EV_PER_RUN + k]) != cudaSuccess) t[k] = -1;
+      for (int k = 0; k < EV_PER_RUN; ++k) {  // (events of another device cannot be compared with `ref`: relative to the chunk's own start)
+        cudaEvent_t from = d == 0 ? S.ref : f.b->events[(size_t)(f.b->runs_recorded - 1) * EV_PER_RUN];
+        if (cudaEventElapsedTime(&t[k], from, f.b->events[(size_t)(f.b->runs_recorded - 1) * EV_PER_RUN + k]) != cudaSuccess) t[k] = -1;
+      }
       fprintf(stderr,
-              "[anl timeline] chunk %3llu n %6u | device: start %7.2f bloom %7.2f exact %7.2f pairs %7.2f score %7.2f conf %7.2f finish %7.2f "
-              "export %7.2f | host: launched %7.2f placed %7.2f downloaded %7.2f\n",
-              (unsigned long long)f.chunk, f.b->n, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], f.t_launched, f.t_placed, host_ms(S));
+              "[anl timeline] dev %u chunk %3llu n %6u | device%s: start %7.2f bloom %7.2f exact %7.2f pairs %7.2f score %7.2f conf %7.2f "
+              "finish %7.2f export %7.2f | host: launched %7.2f placed %7.2f downloaded %7.2f\n",
+              d, (unsigned long long)f.chunk, f.b->n, d == 0 ? "" : " (since its start)", t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7],
+              f.t_launched, f.t_placed, host_ms(S));
     }
     e->free_batch(f.b);
   };
@@ -1743,7 +1747,8 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
     if (f.b) copying.push_back(f);  // (owned by `copying` from here on, whatever happens in place())
     while (copying.size() > 1) finish_copy();
   };
-  for (uint64_t c = d; c < nchunks; c += D) {
+  size_t launched = 0;
+  for (uint64_t c = d; c < nchunks; c += D, ++launched) {
     const uint64_t lo = c * CHUNK, m = std::min(CHUNK, n - lo);
     bool skip;
     {
@@ -1758,7 +1763,11 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
       // then drains before the next wave can start (ANL_TIMELINE: two waves of four chunks, 3 ms lost per 1 M queries).
       // A chunk is launched when its predecessor has left the Bloom stage (about a quarter of its work): the chunks in
       // flight stay a quarter apart, one ends every quarter, and its successor starts into a busy device.
-      if (S.stagger && !running.empty() && running.back().b && running.back().b->runs_recorded > 0) {
+      // Only while the pipeline fills (ANL_STAGGER_ALWAYS=1: before every launch): afterwards a launch follows a
+      // completion, which keeps the spacing by itself, and waiting for the predecessor's Bloom stage would hold launches
+      // back where that stage is half of a chunk's work (cfg 4, cfg 5).
+      if (S.stagger && (S.stagger_always || launched < DEPTH) && !running.empty() && running.back().b &&
+          running.back().b->runs_recorded > 0) {
         DeviceBatch* prev = running.back().b;
         cudaEventSynchronize(prev->events[(size_t)(prev->runs_recorded - 1) * EV_PER_RUN + S.stagger_event]);
       }
@@ -1833,6 +1842,7 @@ bool find_variants_batch_multi(const std::vector<Engine*>& engines, const char* 
   S.n_total = n;
   S.t0 = std::chrono::steady_clock::now();
   if (const char* e = getenv("ANL_TIMELINE")) S.timeline = atoi(e) != 0;
+  if (const char* e = getenv("ANL_STAGGER_ALWAYS")) S.stagger_always = atoi(e) != 0;
   if (const char* e = getenv("ANL_STAGGER")) {
     S.stagger = atoi(e) != 0;
     if (atoi(e) >= 1 && atoi(e) < EV_PER_RUN) S.stagger_event = atoi(e);

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""One anl_find_variants_batch call of cfg 2 (1 M queries) with ANL_TIMELINE=1: per chunk, when its stages ended on the
+"""usage: e2e_timeline.py [n_queries [n_devices]]
+One anl_find_variants_batch call of cfg 2 (1 M queries) with ANL_TIMELINE=1: per chunk, when its stages ended on the
 device (CUDA events against one reference) and when the host launched / placed / finished downloading it."""
 import ctypes as C
 import os
@@ -17,7 +18,11 @@ m = A.VariantModel(workloads.ALPHABET, A.Weights())
 m.read_lexicon(workloads.nld_freq_lexicon())
 for pat, w in workloads.CFG2_CONFUSABLES:
     m.add_to_confusables(pat, w)
-m.build(device=0)
+n_dev = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if n_dev > 1:
+    m.build(devices=list(range(n_dev)))  # one process, a replica on every GPU
+else:
+    m.build(device=0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 qs = workloads.cfg2_queries(1_000_000, 2003)
 qs = (qs * ((n + len(qs) - 1) // len(qs)))[:n]
