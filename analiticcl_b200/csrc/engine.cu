@@ -1628,7 +1628,7 @@ struct CallShared {
   std::vector<cudaStream_t> streams;  // every stream that has copied into `out`: synchronised before `out` moves
   // ANL_TIMELINE=1: per chunk, the device times of its stages (CUDA events against `ref`) and the host's own steps
   bool timeline = false;
-  bool stagger = true;    // ANL_STAGGER=0 launches the chunks back to back
+  bool stagger = false;   // ANL_STAGGER=1: staggered launches (below); off by default -- it gains 2-3 % on cfg 2 and costs 14 % on cfg 5
   bool stagger_always = false;
   int stagger_event = 1;  // which stage of the predecessor must be over (1 = Bloom stage, 2 = exact stage, ...)
   cudaEvent_t ref = nullptr;
@@ -1759,10 +1759,12 @@ void device_loop_body(Engine* e, unsigned d, unsigned D, CallShared& S, const ch
     if (!skip) {
       std::string e2;
       int s2 = ANL_OK;
-      // Staggered starts: chunks launched back to back share the GPU evenly and therefore all END together -- the device
-      // then drains before the next wave can start (ANL_TIMELINE: two waves of four chunks, 3 ms lost per 1 M queries).
-      // A chunk is launched when its predecessor has left the Bloom stage (about a quarter of its work): the chunks in
-      // flight stay a quarter apart, one ends every quarter, and its successor starts into a busy device.
+      // Staggered starts (ANL_STAGGER=1, an experiment kept as a knob): chunks launched back to back share the GPU evenly
+      // and therefore all END together -- the device then drains before the next wave can start (ANL_TIMELINE: two waves
+      // of four chunks).  With the knob a chunk is launched when its predecessor has left the Bloom stage, so the chunks
+      // in flight stay apart.  Measured (tools/e2e_matrix.py): cfg 2 +2-3 %, eng3 -2 %, cfg 4 +-0, cfg 5 -14 % -- the
+      // latency-bound probe kernels of an HBM-resident index WANT several chunks in the same stage at once (more loads
+      // in flight); so the default stays back-to-back.
       // Only while the pipeline fills (ANL_STAGGER_ALWAYS=1: before every launch): afterwards a launch follows a
       // completion, which keeps the spacing by itself, and waiting for the predecessor's Bloom stage would hold launches
       // back where that stage is half of a chunk's work (cfg 4, cfg 5).
