@@ -2642,9 +2642,11 @@ dp_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_
   unsigned long long c_dpp = 0, c_dpc = 0;
   for (;;) {
     uint32_t tile = 0;
-    if (lane == 0) tile = t_lo + atomicAdd(counter, 1u);
+    // (the pair list is sorted by shape, largest matrices last: walk it from the back so that the costly tiles start first)
+    if (lane == 0) tile = atomicAdd(counter, 1u);
     tile = __shfl_sync(FULL, tile, 0);
-    if (tile >= t_hi) break;
+    if (tile >= t_hi - t_lo) break;
+    tile = t_hi - 1 - tile;
     const uint32_t p = tile * 32 + lane;
     uint32_t qi = PAIR_HOLE, g = 0, d = 0;
     if (p < n_pos) {
@@ -3007,18 +3009,28 @@ dp_tma_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const ui
   }
 }
 
+// queries per counter increment of rank_kernel: at least ~24 grabs per warp, so that the warps end together
+static uint32_t rank_grab(uint32_t n, long long grid) {
+  const long long warps = grid * K2_WARPS;
+  long long g = (long long)n / (warps * 24);
+  if (g < 1) g = 1;
+  if (g > 8) g = 8;
+  return (uint32_t)g;
+}
+
 // ---- per query: features -> score -> rank / crop / cut-off -------------------------------------------------------------
 // One warp per query, but the per-query latency chain is kept short: a warp takes 32 queries per counter increment and
 // its lanes fetch their headers (flags, candidate count, dense base, length, case flag) side by side; queries with at
 // most 32 candidates (nearly all) keep their survivor lists in shared memory instead of the global scratch.
 constexpr uint32_t RK_SMEM_SURV = 32;
-constexpr uint32_t RK_GRAB = 8;  // queries per counter increment (few: a warp works its grab off serially)
+constexpr uint32_t RK_GRAB = 8;  // most queries per counter increment (a warp works its grab off serially; the launcher
+                                 // passes fewer for small batches: at 131 072 queries a grab of 8 left the SMs idle 45 % of the kernel)
 __global__ void __launch_bounds__(K2_WARPS * 32)
 rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint8_t* __restrict__ queries,
             const uint32_t* __restrict__ qlist, uint32_t* __restrict__ rec_query, uint32_t nq, const uint32_t* __restrict__ hits,
             const uint32_t* __restrict__ hit_count, uint32_t* __restrict__ qflags, const uint32_t* __restrict__ qbase,
             const uint32_t* __restrict__ res, uint32_t pair_cap, OutRec* __restrict__ out, uint32_t* __restrict__ out_gid,
-            OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters) {
+            OutHead* __restrict__ out_head, SurvRec* __restrict__ scratch, unsigned int* work, Counters* counters, uint32_t grab) {
   __shared__ SurvRec s_scr[K2_WARPS][2 * RK_SMEM_SURV];
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
@@ -3031,12 +3043,12 @@ rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint
   unsigned long long c_surv = 0, c_res = 0;
   for (;;) {
     uint32_t q0 = 0;
-    if (lane == 0) q0 = atomicAdd(work + PW_RANK, RK_GRAB);
+    if (lane == 0) q0 = atomicAdd(work + PW_RANK, grab);
     q0 = __shfl_sync(FULL, q0, 0);
     if (q0 >= nq) break;
     // headers of the grabbed queries, one per lane
     uint32_t m_flags = QF_EMPTY, m_nh = 0, m_base = 0, m_q = 0, m_len = 0;
-    if (lane < RK_GRAB && q0 + lane < nq) {
+    if (lane < grab && q0 + lane < nq) {
       const uint32_t qi = q0 + lane;
       m_flags = qflags[qi];
       m_nh = hit_count[qi];
@@ -3044,7 +3056,7 @@ rank_kernel(const DeviceIndex* __restrict__ ix, const BatchParams bp, const uint
       m_q = qlist ? qlist[qi] : qi;
       m_len = *reinterpret_cast<const uint16_t*>(queries + (size_t)m_q * bp.query_stride);  // length | flags << 8
     }
-    const uint32_t nblock = min(RK_GRAB, nq - q0);
+    const uint32_t nblock = min(grab, nq - q0);
     for (uint32_t t = 0; t < nblock; ++t) {
       const uint32_t qi = q0 + t;
       const uint32_t flags = __shfl_sync(FULL, m_flags, t);
@@ -3429,7 +3441,7 @@ cudaError_t launch_score_pairs(const DeviceIndex* d_ix, const DeviceIndex& h_ix,
     rank_kernel<<<(unsigned)grid, K2_WARPS * 32, 0, stream>>>(d_ix, bp, lb.queries, lb.qlist, lb.rec_query, lb.n, lb.hits, lb.hit_count,
                                                               lb.qflags, lb.qbase, lb.pair_res, lb.pair_cap, lb.out, lb.out_gid,
                                                               lb.out_head, reinterpret_cast<SurvRec*>(lb.scratch), lb.work,
-                                                              lb.counters);
+                                                              lb.counters, rank_grab(lb.n, grid));
     ++g_kernel_launches;
   }
   return cudaGetLastError();
@@ -3457,12 +3469,25 @@ cudaError_t launch_confusables(const DeviceIndex* d_ix, const BatchParams& bp, c
   // queue exit at once, and the long, divergent per-pair work is balanced by the block scheduler
   unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)bp.pool_cap + 63) / 64, (uint64_t)sm_count * 1024);
   if (blocks < 1) blocks = 1;
+  // Few pairs hold characters beyond ASCII, but a single diff is a long dependent chain (0.1-0.3 ms for one thread): on
+  // its own the wide kernel took 0.3 ms whatever the batch size -- per 131 072-query chunk as much as the byte kernel.
+  // It runs beside the byte kernel on the side stream (the two queues and the records they settle are disjoint).
+  const bool beside = lb.aux_stream && lb.ev_fork && lb.ev_join;
+  cudaStream_t wide_stream = stream;
+  cudaError_t e;
+  if (beside) {
+    if ((e = cudaEventRecord(lb.ev_fork, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(lb.aux_stream, lb.ev_fork, 0)) != cudaSuccess) return e;
+    wide_stream = lb.aux_stream;
+  }
+  confusable_wide_kernel<<<(unsigned)sm_count * 8, 64, 0, wide_stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 7, bp.pool_cap,
+                                                                         lb.out);
+  if (beside && (e = cudaEventRecord(lb.ev_join, lb.aux_stream)) != cudaSuccess) return e;
   confusable_kernel<<<blocks, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 3, bp.pool_cap, lb.out);
-  // (few pairs hold characters beyond ASCII: a small grid walks that queue)
-  confusable_wide_kernel<<<(unsigned)sm_count * 4, 64, 0, stream>>>(d_ix, lb.qblob, lb.qboff, lb.conf_work, lb.work + 7, bp.pool_cap,
-                                                                    lb.out);
   g_kernel_launches += 2;
-  return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (beside) return cudaStreamWaitEvent(stream, lb.ev_join, 0);
+  return cudaSuccess;
 }
 cudaError_t launch_finish(const BatchParams& bp, const LaunchBuffers& lb, int sm_count, cudaStream_t stream) {
   if (lb.n == 0 || !lb.conf_work) return cudaSuccess;

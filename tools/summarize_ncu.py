@@ -127,6 +127,7 @@ if traffic and launch_info[1]:
             allw = {allw["probe"].get("workload", "cfg2"): allw}
     except (OSError, ValueError):
         allw = {}
-    allw.setdefault(launch_info[0], {}).update(traffic)  # (a partial capture only replaces the kernels it holds)
+    key = launch_info[0] if launch_info[1] == 1_000_000 else f"{launch_info[0]}@{launch_info[1]}"  # (bench.py reads the 1 M-query entries)
+    allw.setdefault(key, {}).update(traffic)  # (a partial capture only replaces the kernels it holds)
     json.dump(allw, open(path, "w"), indent=1)
 print("wrote", os.path.join(PROF, f"{tag}_ncu_summary.md"))
