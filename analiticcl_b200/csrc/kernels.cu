@@ -1266,15 +1266,14 @@ __device__ __noinline__ double result_score(const BatchParams& bp, double dist, 
 }
 // rank_cmp (src/types.rs:344-365) with the gather id as the final key (== stable sort of the
 // reference's gather order)
+// Branch-free: equal distance scores are the rule (the scores are small-integer quotients), so a short-circuit chain
+// sent a handful of lanes down the tie path in nearly every iteration of the rank loop (ncu, eng k = 3: 4.4 of 32 lanes
+// on those lines, a third of the kernel's issue slots).  All comparisons are evaluated and combined as predicates.
 __device__ __forceinline__ bool ranks_before(const BatchParams& bp, bool gather_order, const SurvRec& a, const SurvRec& b) {
-  if (gather_order) return a.g < b.g;
-  if (bp.freq_weight_positive) {
-    if (a.key != b.key) return a.key > b.key;
-    return a.g < b.g;
-  }
-  if (a.dist != b.dist) return a.dist > b.dist;
-  if (a.freq != b.freq) return a.freq > b.freq;
-  return a.g < b.g;
+  const bool g_lt = a.g < b.g;
+  if (gather_order) return g_lt;
+  if (bp.freq_weight_positive) return (a.key > b.key) | ((a.key == b.key) & g_lt);
+  return (a.dist > b.dist) | ((a.dist == b.dist) & ((a.freq > b.freq) | ((a.freq == b.freq) & g_lt)));
 }
 
 // Triage of one (input a, candidate b) pair for confusable rescoring.
@@ -1463,7 +1462,7 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
 #pragma unroll 4
       for (uint32_t j = 0; j < nsurv; ++j) {  // (unrolled by 4: the loads from the scratch list overlap)
         const SurvRec b = surv[j];
-        rank += (j != i) && ranks_before(bp, gather_order, b, a);
+        rank += ranks_before(bp, gather_order, b, a) ? 1u : 0u;  // (gather ids are unique: a record never ranks before itself)
       }
       sorted[rank] = a;
     }
