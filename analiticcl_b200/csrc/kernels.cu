@@ -1456,17 +1456,58 @@ __device__ __forceinline__ uint32_t rank_crop_emit(const BatchParams& bp, const 
       surv[i] = r;
     }
     __syncwarp();
-    for (uint32_t i = lane; i < nsurv; i += 32) {
-      const SurvRec a = surv[i];
-      uint32_t rank = 0;
+    if (nsurv <= 32) {
+      for (uint32_t i = lane; i < nsurv; i += 32) {
+        const SurvRec a = surv[i];
+        uint32_t rank = 0;
 #pragma unroll 4
-      for (uint32_t j = 0; j < nsurv; ++j) {  // (unrolled by 4: the loads from the scratch list overlap)
-        const SurvRec b = surv[j];
-        rank += ranks_before(bp, gather_order, b, a) ? 1u : 0u;  // (gather ids are unique: a record never ranks before itself)
+        for (uint32_t j = 0; j < nsurv; ++j) {  // (unrolled by 4: the loads from the scratch list overlap)
+          const SurvRec b = surv[j];
+          rank += ranks_before(bp, gather_order, b, a) ? 1u : 0u;  // (gather ids are unique: a record never ranks before itself)
+        }
+        sorted[rank] = a;
       }
-      sorted[rank] = a;
+    } else {
+      // Long lists: counting every record against every other one is n * n / 32 comparisons per lane, and the few
+      // queries with hundreds of survivors were most of the kernel.  Instead every block of 32 records is sorted by
+      // itself (the same counting, inside the block), and a record's rank is its place in its own block plus, for
+      // every other block, the number of records that come before it -- a 6-step binary search in that sorted block
+      // (the order is strict and total: gather ids are unique).  n + 6 n / 32 comparisons per lane instead of n * n / 32.
+      for (uint32_t b0 = 0; b0 < nsurv; b0 += 32) {
+        const uint32_t bn = min(32u, nsurv - b0);
+        if (lane < bn) {
+          const SurvRec a = surv[b0 + lane];
+          uint32_t r = 0;
+#pragma unroll 4
+          for (uint32_t j = 0; j < bn; ++j) r += ranks_before(bp, gather_order, surv[b0 + j], a) ? 1u : 0u;
+          sorted[b0 + r] = a;
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      for (uint32_t i = lane; i < nsurv; i += 32) {
+        const SurvRec a = sorted[i];
+        const uint32_t mine = i & ~31u;
+        uint32_t rank = i - mine;
+        for (uint32_t b0 = 0; b0 < nsurv; b0 += 32) {
+          if (b0 == mine) continue;
+          const uint32_t bn = min(32u, nsurv - b0);
+          uint32_t lo = 0;  // records of this block that rank before `a`
+#pragma unroll
+          for (uint32_t step = 32; step >= 1; step >>= 1) {
+            const uint32_t p = lo + step;
+            if (p <= bn && ranks_before(bp, gather_order, sorted[b0 + p - 1], a)) lo = p;
+          }
+          rank += lo;
+        }
+        surv[rank] = a;  // (the unsorted list is not read any more: it takes the final order)
+      }
+      SurvRec* t = surv;
+      surv = sorted;
+      sorted = t;
     }
   }
+  __threadfence_block();
   __syncwarp();
 
   // ---- crop at max_matches with the reference's tie rules (src/lib.rs:1536-1589) ---------------------
