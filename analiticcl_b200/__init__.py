@@ -124,22 +124,35 @@ class SearchParameters:
             else:
                 print(f"Ignored unknown kwargs option {key}", file=sys.stderr)
 
-    max_anagram_distance = property(lambda self: _threshold_value(self.data.max_anagram_distance))
-    max_edit_distance = property(lambda self: _threshold_value(self.data.max_edit_distance))
-    max_matches = property(lambda self: int(self.data.max_matches))
+    # attributes with the setters the reference binding has (#[setter], bindings/python/src/lib.rs:262-446): the two
+    # thresholds, max_matches, max_ngram, max_seq, single_thread, the five weights, consolidate_matches, unicodeoffsets,
+    # stop_at_exact_match; score_threshold and cutoff_threshold are read-only there too
+    def _set_threshold(self, field, value):
+        setattr(self.data, field, _distance_threshold(value))  # (ValueError on a bad threshold, like the reference)
+
+    max_anagram_distance = property(lambda self: _threshold_value(self.data.max_anagram_distance),
+                                    lambda self, v: self._set_threshold("max_anagram_distance", v))
+    max_edit_distance = property(lambda self: _threshold_value(self.data.max_edit_distance),
+                                 lambda self, v: self._set_threshold("max_edit_distance", v))
+    max_matches = property(lambda self: int(self.data.max_matches), lambda self, v: setattr(self.data, "max_matches", int(v)))
     score_threshold = property(lambda self: float(self.data.score_threshold))
     cutoff_threshold = property(lambda self: float(self.data.cutoff_threshold))
-    max_ngram = property(lambda self: int(self.data.max_ngram))
-    max_seq = property(lambda self: int(self.data.max_seq))
-    single_thread = property(lambda self: bool(self.data.single_thread))
-    unicodeoffsets = property(lambda self: bool(self.data.unicodeoffsets))
-    freq_weight = property(lambda self: float(self.data.freq_weight))
-    lm_weight = property(lambda self: float(self.data.lm_weight))
-    contextrules_weight = property(lambda self: float(self.data.contextrules_weight))
-    variantmodel_weight = property(lambda self: float(self.data.variantmodel_weight))
-    context_weight = property(lambda self: float(self.data.context_weight))
-    consolidate_matches = property(lambda self: bool(self.data.consolidate_matches))
-    stop_at_exact_match = property(lambda self: self.data.stop_criterion == _capi.STOP_AT_EXACT_MATCH)
+    max_ngram = property(lambda self: int(self.data.max_ngram), lambda self, v: setattr(self.data, "max_ngram", int(v)))
+    max_seq = property(lambda self: int(self.data.max_seq), lambda self, v: setattr(self.data, "max_seq", int(v)))
+    single_thread = property(lambda self: bool(self.data.single_thread), lambda self, v: setattr(self.data, "single_thread", int(bool(v))))
+    unicodeoffsets = property(lambda self: bool(self.data.unicodeoffsets), lambda self, v: setattr(self.data, "unicodeoffsets", int(bool(v))))
+    freq_weight = property(lambda self: float(self.data.freq_weight), lambda self, v: setattr(self.data, "freq_weight", float(v)))
+    lm_weight = property(lambda self: float(self.data.lm_weight), lambda self, v: setattr(self.data, "lm_weight", float(v)))
+    contextrules_weight = property(lambda self: float(self.data.contextrules_weight),
+                                   lambda self, v: setattr(self.data, "contextrules_weight", float(v)))
+    variantmodel_weight = property(lambda self: float(self.data.variantmodel_weight),
+                                   lambda self, v: setattr(self.data, "variantmodel_weight", float(v)))
+    context_weight = property(lambda self: float(self.data.context_weight), lambda self, v: setattr(self.data, "context_weight", float(v)))
+    consolidate_matches = property(lambda self: bool(self.data.consolidate_matches),
+                                   lambda self, v: setattr(self.data, "consolidate_matches", int(bool(v))))
+    stop_at_exact_match = property(
+        lambda self: self.data.stop_criterion == _capi.STOP_AT_EXACT_MATCH,
+        lambda self, v: setattr(self.data, "stop_criterion", _capi.STOP_AT_EXACT_MATCH if v else _capi.STOP_EXHAUSTIVE))
 
     def to_dict(self):
         keys = ["max_anagram_distance", "max_edit_distance", "max_matches", "score_threshold", "cutoff_threshold",

@@ -62,6 +62,20 @@ def test_search_parameters_surface():
     assert w.to_dict() == {"ld": 0.6, "lcs": 0.125, "prefix": 0.125, "suffix": 0.125, "case": 0.125}
     v = A.VocabParams(freq_column=2, vocabtype="TRANSPARENT", freqhandling="sum")
     assert v.freq_column == 2 and v.data.vocab_type == 5 and v.data.freq_handling == 0
+    # the attributes the reference binding makes assignable (#[setter], bindings/python/src/lib.rs:262-446)
+    p = A.SearchParameters()
+    p.max_seq, p.lm_weight, p.variantmodel_weight, p.contextrules_weight, p.context_weight, p.freq_weight = 7, 2.5, 1.5, 0.5, 0.25, 0.75
+    p.single_thread, p.stop_at_exact_match, p.consolidate_matches, p.unicodeoffsets = True, True, False, True
+    p.max_anagram_distance, p.max_edit_distance, p.max_ngram, p.max_matches = 2, (0.5, 3), 2, 5
+    assert p.to_dict() == {"max_anagram_distance": 2, "max_edit_distance": (0.5, 3), "max_matches": 5, "score_threshold": 0.25,
+                           "cutoff_threshold": 2.0, "max_ngram": 2, "max_seq": 7, "single_thread": True, "freq_weight": 0.75,
+                           "lm_weight": 2.5, "contextrules_weight": 0.5, "variantmodel_weight": 1.5, "consolidate_matches": False,
+                           "unicodeoffsets": True}
+    assert p.stop_at_exact_match and p.context_weight == 0.25
+    with pytest.raises(ValueError):
+        p.max_edit_distance = "nonsense"
+    with pytest.raises(AttributeError):
+        p.score_threshold = 0.1  # (no setter in the reference binding either)
 
 
 def test_variant_list_loading_matches_oracle(tmp_path):
