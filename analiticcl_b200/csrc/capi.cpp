@@ -76,6 +76,31 @@ static anl_status on_exception() noexcept {
   }
 }
 
+// The positions i of [lo, hi) with pred(i), ascending, into *out -- on all cores (count per range, prefix, write): the
+// selections of anl_find_all_matches run over millions of segments per window.
+template <class Pred>
+static void parallel_select(uint64_t lo, uint64_t hi, Pred pred, std::vector<uint64_t>* out) {
+  const unsigned nt_max = host_threads();
+  std::vector<uint64_t> count(nt_max + 1, 0);
+  std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
+  const unsigned used = parallel_ranges(hi - lo, 1u << 15, [&](unsigned t, uint64_t a, uint64_t b) {
+    range[t] = {lo + a, lo + b};
+    uint64_t c = 0;
+    for (uint64_t i = lo + a; i < lo + b; ++i) c += pred(i) ? 1 : 0;
+    count[t + 1] = c;
+  });
+  for (unsigned t = 0; t < used; ++t) count[t + 1] += count[t];
+  out->resize(count[used]);
+  uint64_t* dst = out->data();
+  parallel_ranges(used, 1, [&](unsigned, uint64_t ta, uint64_t tb) {
+    for (uint64_t t = ta; t < tb; ++t) {
+      uint64_t w = count[t];
+      for (uint64_t i = range[t].first; i < range[t].second; ++i)
+        if (pred(i)) dst[w++] = i;
+    }
+  });
+}
+
 extern "C" {
 
 const char* anl_last_error(void) { return g_last_error.c_str(); }
@@ -650,12 +675,10 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
         }
       }
     });
-    uniq.clear();
-    for (uint64_t i = 0; i < np; ++i)
-      if (rep[i] == i) {
-        uniq_of[i] = (uint32_t)uniq.size();
-        uniq.push_back(i);
-      }
+    parallel_select(0, np, [&](uint64_t i) { return rep[i] == i; }, &uniq);
+    parallel_ranges(uniq.size(), 1u << 15, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t u = lo; u < hi; ++u) uniq_of[uniq[u]] = (uint32_t)u;
+    });
     parallel_ranges(np, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; ++i)
         if (rep[i] != i) uniq_of[i] = uniq_of[rep[i]];
@@ -716,9 +739,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
         off[k] = 0;
       }
     });
-    pick.clear();
-    for (uint64_t k = s0; k < s1; ++k)
-      if (st.segs[k].n == 1) pick.push_back(k);
+    parallel_select(s0, s1, [&](uint64_t k) { return st.segs[k].n == 1; }, &pick);
     ok = lookup(0);
     pt.lap("search: unigram lookups");
     if (ok && params->max_ngram > 1) {
