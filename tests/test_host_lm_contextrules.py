@@ -267,3 +267,36 @@ def test_lexicon_patterns_and_language_model_from_files(L, tmp_path):
     sp, op = sp_and_op(**{**TEST_PARAMS, "lm_weight": 0.0, "contextrules_weight": 0.0})
     r = o.find_all_matches("I tink", op)
     assert o.vocab_text(r[1]["variants"][r[1]["selected"]][0]) == "think"
+
+
+def test_pattern_parser_accepts_and_rejects_like_the_oracle(L):
+    """Random pattern strings (valid and malformed: stray operators, unknown words, empty positions, nested negation):
+    product and oracle must agree on accept / reject, and on what an accepted rule matches."""
+    rng = np.random.default_rng(99)
+    o, m = both(WORDS)
+    atoms = ["I", "think", "sink", "you", "?", "^", "nosuch", "", " ", "!", "|", "!(", ")", "@x", "are", "!(I|you)", "!think", "I|are"]
+    accepted = rejected = 0
+    for _ in range(400):
+        n = int(rng.integers(1, 4))
+        pat = ";".join("".join(str(rng.choice(atoms)) for _ in range(int(rng.integers(1, 3)))) for _ in range(n))
+        tag = ["t"] if rng.random() < 0.5 else []
+        off = [str(rng.choice(["0:", "1:1", ":", "0:2", "x", "1"]))] if tag and rng.random() < 0.5 else []
+        ok_o = ok_m = True
+        try:
+            o.add_contextrule(pat, 1.1, tag, off)
+        except RuntimeError:
+            ok_o = False
+        try:
+            m.add_contextrule(pat, 1.1, tag, off)
+        except (RuntimeError, ValueError):
+            ok_m = False
+        assert ok_o == ok_m, (pat, tag, off)
+        accepted += ok_o
+        rejected += not ok_o
+    assert accepted > 30 and rejected > 30
+    assert L.anl_model_contextrule_count(m._h) == orc.lib().orc_contextrule_count(o.h)
+    assert m.tags() == o.tags()
+    sp, op = sp_and_op(**{**TEST_PARAMS, "lm_weight": 0.0, "max_ngram": 1})
+    for text in ("I tink you are rihgt", "you sink I think", "zzzzzzzzzz I are"):
+        segments = o.find_all_segments(text, op)
+        assert product_sequence(L, m, text, sp, segments) == strip(o.find_all_matches(text, op, segments)), text
