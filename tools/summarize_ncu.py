@@ -60,6 +60,10 @@ for name in ("bloom", "exact", "pairfilter", "dp", "rank", "score", "confusable"
     rep = os.path.join(OUT, f"prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
+    # gpurun_out/ keeps the reports of earlier calls: only those written by THIS profile.sh run belong to the summary
+    stamp = os.path.join(OUT, "profile_launch.txt")
+    if os.path.exists(stamp) and os.path.getmtime(rep) + 1 < os.path.getmtime(stamp):
+        continue
     m = raw_metrics(rep)
     try:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
