@@ -41,7 +41,9 @@ struct anl_result_set {
 struct anl_match_set {
   uint64_t logical_lookups = 0, distinct_lookups = 0;
   PodBuffer<anl_match> matches;
-  PodBuffer<anl_variant> variants;  // all variant lists back to back; anl_match.variants points into it
+  // all variant lists back to back; anl_match.variants points into it.  Shared: a consolidated match set refers to the
+  // lists of the set it was made from instead of copying them, and keeps them alive when that set is freed.
+  std::shared_ptr<PodBuffer<anl_variant>> variants = std::make_shared<PodBuffer<anl_variant>>();
   std::shared_ptr<Segmentation> seg;  // the producer's segmentation (anl_find_all_matches), reused by the consolidation
   // tags assigned by context rules (Match.tag / Match.seqnr, src/search.rs:57-60): CSR over the matches; empty = none
   std::vector<uint64_t> tag_first;
@@ -594,7 +596,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
   cnt.resize(nseg + 1);
   off.resize(nseg + 1);
   ms->matches.resize(nseg);
-  ms->variants.reserve(1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
+  ms->variants->reserve(1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
   int status = ANL_OK;
   size_t WINDOW = 1u << 20;  // unigram segments per window
   if (const char* e = getenv("ANL_SEARCH_WINDOW")) WINDOW = (size_t)std::max(1, atoi(e));
@@ -779,8 +781,8 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
     const uint64_t n1 = (params->max_ngram > 1 && rs[1].offsets.size()) ? rs[1].offsets[rs[1].offsets.size() - 1] : 0;
     const uint64_t base[2] = {vtotal, vtotal + n0};
     vtotal += n0 + n1;
-    ms->variants.resize(vtotal);
-    anl_variant* vbase = ms->variants.data();
+    ms->variants->resize(vtotal);
+    anl_variant* vbase = ms->variants->data();
     for (int pass = 0; pass < 2; ++pass) {
       const uint64_t cnt_pass = pass == 0 ? n0 : n1;
       const anl_variant* src = rs[pass].variants.data();
@@ -804,7 +806,7 @@ anl_status anl_find_all_matches(anl_model* m, const char* text, size_t len, cons
     b0 = b1;
   }
   if (!ok) return fail(status ? status : ANL_ERR_CUDA, err);
-  const anl_variant* vbase = ms->variants.data();
+  const anl_variant* vbase = ms->variants->data();
   parallel_ranges(nseg, 1u << 16, [&](unsigned, uint64_t lo, uint64_t hi) {
     for (uint64_t k = lo; k < hi; ++k) {
       anl_match& mm = ms->matches[k];
@@ -860,7 +862,6 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
   std::vector<std::vector<SequenceStep>> part(nt_max);
   std::vector<std::vector<StepTags>> part_tags(nt_max);   // parallel to `part` when context rules are loaded
   std::vector<std::vector<uint64_t>> part_count(nt_max);  // steps per batch
-  std::vector<uint64_t> part_nvar(nt_max, 0);             // variants held by the chosen matches
   std::vector<std::pair<uint64_t, uint64_t>> range(nt_max, {0, 0});
   const bool want_tags = hm && !hm->context_rules.empty();
   const unsigned used = parallel_ranges(nbatch, 64, [&](unsigned tid, uint64_t lo, uint64_t hi) {
@@ -912,10 +913,6 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
         if (want_tags) part_tags[tid].resize(part[tid].size());
       }
       part_count[tid].push_back(part[tid].size() - before);
-      for (size_t i = before; i < part[tid].size(); ++i) {
-        const anl_match& mm = in->matches[s0 + part[tid][i].seg];
-        if (mm.variants) part_nvar[tid] += mm.n_variants;
-      }
     }
   });
   pt.lap("consolidate: lattices");
@@ -924,17 +921,13 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
   ms->logical_lookups = in->logical_lookups;
   ms->distinct_lookups = in->distinct_lookups;
   // every thread copies the matches of its own batches behind those of the threads before it
-  std::vector<uint64_t> first_match(used + 1, 0), first_variant(used + 1, 0);
-  for (unsigned tid = 0; tid < used; ++tid) {
-    first_match[tid + 1] = first_match[tid] + part[tid].size();
-    first_variant[tid + 1] = first_variant[tid] + part_nvar[tid];
-  }
+  std::vector<uint64_t> first_match(used + 1, 0);
+  for (unsigned tid = 0; tid < used; ++tid) first_match[tid + 1] = first_match[tid] + part[tid].size();
   ms->matches.resize(first_match[used]);
-  ms->variants.reserve(first_variant[used] + 1);  // (never a null base: a looked-up segment keeps a non-null variants pointer)
-  ms->variants.resize(first_variant[used]);
+  ms->variants = in->variants;  // (shared, not copied: the chosen matches keep pointing at their lists)
   parallel_ranges(used, 1, [&](unsigned, uint64_t tlo, uint64_t thi) {
     for (uint64_t tid = tlo; tid < thi; ++tid) {
-      uint64_t o = first_match[tid], v = first_variant[tid];
+      uint64_t o = first_match[tid];
       size_t pos = 0;
       for (uint64_t b = range[tid].first; b < range[tid].second; ++b) {
         const uint64_t c = part_count[tid][b - range[tid].first];
@@ -942,11 +935,6 @@ static anl_status consolidate_impl(const HostModel* hm, const anl_match_set* in,
           const SequenceStep& s = part[tid][pos];
           anl_match mm = in->matches[st.batch_first[b] + s.seg];
           mm.selected = s.variant < 0 ? -1 : s.variant;
-          if (mm.variants) {
-            if (mm.n_variants) memcpy(ms->variants.data() + v, mm.variants, (size_t)mm.n_variants * sizeof(anl_variant));
-            mm.variants = ms->variants.data() + v;
-            v += mm.n_variants;
-          }
           ms->matches[o++] = mm;
         }
       }
@@ -1086,9 +1074,9 @@ anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_
   std::unique_ptr<anl_match_set> ms_owner(new anl_match_set());
   anl_match_set* ms = ms_owner.get();
   ms->matches.resize(nseg);
-  ms->variants.reserve((nseg ? offsets[nseg] : 0) + 1);
-  ms->variants.resize(nseg ? offsets[nseg] : 0);
-  if (nseg && offsets[nseg]) memcpy(ms->variants.data(), variants, (size_t)offsets[nseg] * sizeof(anl_variant));
+  ms->variants->reserve((nseg ? offsets[nseg] : 0) + 1);
+  ms->variants->resize(nseg ? offsets[nseg] : 0);
+  if (nseg && offsets[nseg]) memcpy(ms->variants->data(), variants, (size_t)offsets[nseg] * sizeof(anl_variant));
   for (uint64_t k = 0; k < nseg; ++k) {
     const SegmentSpan& sp = st.segs[k];
     anl_match& mm = ms->matches[k];
@@ -1098,7 +1086,7 @@ anl_status anl_debug_match_set_build(const char* text, size_t len, uint32_t max_
     mm.n = sp.n;
     mm.n_variants = cnt;
     mm.selected = (looked[k] && cnt > 0) ? 0 : -1;
-    mm.variants = looked[k] ? ms->variants.data() + offsets[k] : nullptr;
+    mm.variants = looked[k] ? ms->variants->data() + offsets[k] : nullptr;
   }
   *out = ms_owner.release();
   return ANL_OK;
